@@ -1,0 +1,1115 @@
+// libautobz_cuda.so — C ABI + host-side engine (chunk planning, launches) for the AutoBZCore.jl
+// hot path on B200.  See include/autobz_cuda.h for the contract and the reference call sites.
+#include "../../include/autobz_cuda.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "abz_common.cuh"
+#include "abz_eig.cuh"
+#include "abz_iai.cuh"
+#include "abz_kernels.cuh"
+#include "abz_resolvent_mma.cuh"
+
+using namespace abz;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct Series {
+    double2* c = nullptr;
+    int n = 0, M[3] = {1, 1, 1}, lo[3] = {0, 0, 0};
+    double period[3] = {1, 1, 1};
+    ~Series() { if (c) cudaFree(c); }
+};
+
+struct Rule {
+    uint64_t series_id = 0;
+    Series* s = nullptr;
+    int N = 0;
+    bool full = true;
+    long np3 = 0, nrows = 0, nnz = 0;
+    std::vector<int> h_plane_k3, h_row_k2, h_node_k1;
+    std::vector<long> h_plane_rowptr, h_row_nodeptr;
+    std::vector<double> h_node_w;
+    int* d_plane_k3 = nullptr; long* d_plane_rowptr = nullptr;
+    int* d_row_k2 = nullptr; long* d_row_nodeptr = nullptr;
+    int* d_node_k1 = nullptr; double* d_node_w = nullptr;
+    double2* d_ptab[3] = {nullptr, nullptr, nullptr};
+    double2* d_H = nullptr;   // materialised H(k) [nnz][n*n]
+    ~Rule() {
+        cudaFree(d_plane_k3); cudaFree(d_plane_rowptr); cudaFree(d_row_k2); cudaFree(d_row_nodeptr);
+        cudaFree(d_node_k1); cudaFree(d_node_w); cudaFree(d_H);
+        for (auto& p : d_ptab) cudaFree(p);
+    }
+};
+
+struct Nest {
+    Series* s = nullptr;
+    int ndim = 3;
+    long cap2 = 0, cap1 = 0;
+    double2* L2 = nullptr; double2* L1 = nullptr;
+    ~Nest() { cudaFree(L2); cudaFree(L1); }
+};
+
+struct Chunk { long p0, p1, r0, r1; };
+
+}  // namespace
+
+struct abz_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t next_id = 1;
+    std::unordered_map<uint64_t, std::unique_ptr<Series>> series;
+    std::unordered_map<uint64_t, std::unique_ptr<Rule>> rules;
+    std::unordered_map<uint64_t, std::unique_ptr<Nest>> nests;
+    int resolvent_algo = 0;
+    size_t budget = (size_t)4096 << 20;
+    int fused_small = 1;
+    DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d;
+    long launches = 0;
+    std::vector<cudaEvent_t> events;
+    size_t ev_used = 0;
+    double eval_ms = 0, matfun_ms = 0;
+    int sm_count = 148;
+    // nccl (dlopen)
+    void* nccl_lib = nullptr; void* nccl_comm = nullptr; int nranks = 1;
+};
+
+namespace {
+
+int fail(abz_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(ctx, expr)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            cudaGetLastError();                                                                           \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? ABZ_E_OOM : ABZ_E_CUDA,                  \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                             \
+        }                                                                                                 \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx, name)                                                                           \
+    do {                                                                                                  \
+        (ctx)->launches++;                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                                             \
+        if (e__ != cudaSuccess) return fail(ctx, ABZ_E_CUDA, std::string(name) + " launch: " + cudaGetErrorString(e__)); \
+    } while (0)
+
+cudaEvent_t next_event(abz_ctx* ctx) {
+    if (ctx->ev_used == ctx->events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->events.push_back(e);
+    }
+    cudaEvent_t e = ctx->events[ctx->ev_used++];
+    cudaEventRecord(e, ctx->stream);
+    return e;
+}
+
+template <class T>
+int upload(abz_ctx* ctx, T** dptr, const std::vector<T>& h) {
+    *dptr = nullptr;
+    if (h.empty()) return ABZ_OK;
+    CU(ctx, cudaMalloc((void**)dptr, h.size() * sizeof(T)));
+    CU(ctx, cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return ABZ_OK;
+}
+
+Series* get_series(abz_ctx* ctx, abz_series_t id) {
+    auto it = ctx->series.find(id);
+    return it == ctx->series.end() ? nullptr : it->second.get();
+}
+Rule* get_rule(abz_ctx* ctx, abz_rule_t id) {
+    auto it = ctx->rules.find(id);
+    return it == ctx->rules.end() ? nullptr : it->second.get();
+}
+Nest* get_nest(abz_ctx* ctx, abz_nest_t id) {
+    auto it = ctx->nests.find(id);
+    return it == ctx->nests.end() ? nullptr : it->second.get();
+}
+
+int finish_rule(abz_ctx* ctx, Rule* r) {
+    Series* s = r->s;
+    int rc;
+    if ((rc = upload(ctx, &r->d_plane_k3, r->h_plane_k3))) return rc;
+    if ((rc = upload(ctx, &r->d_plane_rowptr, r->h_plane_rowptr))) return rc;
+    if ((rc = upload(ctx, &r->d_row_k2, r->h_row_k2))) return rc;
+    if ((rc = upload(ctx, &r->d_row_nodeptr, r->h_row_nodeptr))) return rc;
+    if (!r->full) {
+        if ((rc = upload(ctx, &r->d_node_k1, r->h_node_k1))) return rc;
+        if ((rc = upload(ctx, &r->d_node_w, r->h_node_w))) return rc;
+    }
+    for (int d = 0; d < 3; d++) {
+        size_t cnt = (size_t)s->M[d] * r->N;
+        CU(ctx, cudaMalloc((void**)&r->d_ptab[d], cnt * sizeof(double2)));
+        phase_table_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(r->d_ptab[d], s->M[d], s->lo[d], r->N);
+        LAUNCH_CHECK(ctx, "phase_table_kernel");
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABZ_OK;
+}
+
+// ---- chunk planning: consecutive planes while they fit; a plane larger than the cap is split by rows
+std::vector<Chunk> plan_chunks(const Rule* r, long node_cap, long row_cap, long plane_cap) {
+    std::vector<Chunk> out;
+    node_cap = std::max<long>(node_cap, 1); row_cap = std::max<long>(row_cap, 1); plane_cap = std::max<long>(plane_cap, 1);
+    long p = 0;
+    while (p < r->np3) {
+        long r0 = r->h_plane_rowptr[p];
+        long pr1 = r->h_plane_rowptr[p + 1];
+        long pn = r->h_row_nodeptr[pr1] - r->h_row_nodeptr[r0];
+        if (pn > node_cap || pr1 - r0 > row_cap) {
+            long ra = r0;
+            while (ra < pr1) {
+                long rb = ra + 1;
+                while (rb < pr1 && rb - ra < row_cap && r->h_row_nodeptr[rb + 1] - r->h_row_nodeptr[ra] <= node_cap) rb++;
+                out.push_back({p, p + 1, ra, rb});
+                ra = rb;
+            }
+            p++;
+            continue;
+        }
+        long q = p + 1;
+        while (q < r->np3 && q - p < plane_cap) {
+            long qr1 = r->h_plane_rowptr[q + 1];
+            if (qr1 - r0 > row_cap || r->h_row_nodeptr[qr1] - r->h_row_nodeptr[r0] > node_cap) break;
+            q++;
+        }
+        out.push_back({p, q, r0, r->h_plane_rowptr[q]});
+        p = q;
+    }
+    return out;
+}
+
+size_t stage_smem(int M) { return (size_t)((M + 1) & ~1) * (ST_RT + ST_JT) * sizeof(double2); }
+
+int launch_stage(abz_ctx* ctx, const double2* in, double2* out, const double2* ptab, const long* ptr, long b0,
+                 long nbatch, const int* klist, int N, int M, long rows, long in_stride) {
+    if (nbatch <= 0 || rows <= 0) return ABZ_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(contract_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    size_t smem = stage_smem(M);
+    if (smem > 200 * 1024) return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension");
+    dim3 grid((unsigned)nbatch, (unsigned)((rows + ST_RT - 1) / ST_RT));
+    contract_stage_kernel<<<grid, 128, smem, ctx->stream>>>(in, out, ptab, ptr, b0, klist, N, M, rows, in_stride);
+    LAUNCH_CHECK(ctx, "contract_stage_kernel");
+    return ABZ_OK;
+}
+
+// evaluate stages for a chunk.  upto = 1: stop after stage 2 (C1 rows; fused small path); 0: also H
+int eval_chunk(abz_ctx* ctx, Rule* r, const Chunk& ch, bool need_h, double2* Hdst) {
+    Series* s = r->s;
+    const long nn = (long)s->n * s->n;
+    const long rows2 = nn * s->M[0] * s->M[1], rows1 = nn * s->M[0];
+    const long nplanes = ch.p1 - ch.p0, nrows = ch.r1 - ch.r0;
+    CU(ctx, ctx->C2.reserve((size_t)nplanes * rows2 * sizeof(double2)));
+    CU(ctx, ctx->C1.reserve((size_t)nrows * rows1 * sizeof(double2)));
+    // stage 3: one batch over planes [p0,p1): use a 2-entry ptr built on the fly in tmp_d
+    long h_ptr3[2] = {ch.p0, ch.p1};
+    CU(ctx, ctx->tmp_d.reserve(4 * sizeof(long)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_d.p, h_ptr3, sizeof(h_ptr3), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_stage(ctx, s->c, ctx->C2.as<double2>(), r->d_ptab[2], ctx->tmp_d.as<long>(), 0, 1, r->d_plane_k3, r->N,
+                          s->M[2], rows2, 0);
+    if (rc) return rc;
+    // stage 2
+    bool whole = (ch.r0 == r->h_plane_rowptr[ch.p0] && ch.r1 == r->h_plane_rowptr[ch.p1]);
+    if (whole) {
+        rc = launch_stage(ctx, ctx->C2.as<double2>(), ctx->C1.as<double2>(), r->d_ptab[1], r->d_plane_rowptr, ch.p0, nplanes,
+                          r->d_row_k2, r->N, s->M[1], rows1, rows2);
+    } else {
+        long h_ptr2[2] = {ch.r0, ch.r1};
+        CU(ctx, cudaMemcpyAsync(ctx->tmp_d.as<long>() + 2, h_ptr2, sizeof(h_ptr2), cudaMemcpyHostToDevice, ctx->stream));
+        rc = launch_stage(ctx, ctx->C2.as<double2>(), ctx->C1.as<double2>(), r->d_ptab[1], ctx->tmp_d.as<long>() + 2, 0, 1,
+                          r->d_row_k2, r->N, s->M[1], rows1, rows2);
+    }
+    if (rc) return rc;
+    if (!need_h) return ABZ_OK;
+    // stage 1
+    rc = launch_stage(ctx, ctx->C1.as<double2>(), Hdst, r->d_ptab[0], r->d_row_nodeptr, ch.r0, nrows, r->d_node_k1, r->N,
+                      s->M[0], nn, rows1);
+    return rc;
+}
+
+int check_errflag(abz_ctx* ctx, const char* what) {
+    int h = 0;
+    CU(ctx, cudaMemcpyAsync(&h, ctx->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h) {
+        cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->stream);
+        return fail(ctx, ABZ_E_SINGULAR, std::string(what) + ": singular matrix or NaN/Inf in the integrand");
+    }
+    return ABZ_OK;
+}
+
+int upload_params(abz_ctx* ctx, int n, int nw, const double* z, const double* sigma) {
+    CU(ctx, ctx->zbuf.reserve((size_t)std::max(nw, 1) * sizeof(double2)));
+    if (z) CU(ctx, cudaMemcpyAsync(ctx->zbuf.p, z, (size_t)nw * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    if (sigma) {
+        size_t b = (size_t)nw * n * n * sizeof(double2);
+        CU(ctx, ctx->sigbuf.reserve(b));
+        CU(ctx, cudaMemcpyAsync(ctx->sigbuf.p, sigma, b, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return ABZ_OK;
+}
+
+size_t gj_smem_bytes(int n, int nw, int nwarps) {
+    size_t per_warp = (size_t)n * (n + 1) + (n + 1) / 2 + 1;
+    return ((size_t)n * n + nw + per_warp * nwarps) * sizeof(double2);
+}
+
+// matrix function on nk materialised matrices H (device).  mode 0: weighted partial sums -> acc (+=),
+// mode 1: values -> yout (device, [nk][nw])
+int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int n, int fkind, int nw,
+               const double2* z, const double2* sigma, int mode, double2* yout) {
+    if (nk <= 0) return ABZ_OK;
+    const long sm = ctx->sm_count;
+    if (fkind == ABZ_F_TRACE_H) {
+        long ncta = std::min<long>((nk + 255) / 256, sm * 8);
+        if (mode == 0) {
+            CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
+            trace_h_kernel<<<(unsigned)ncta, 256, 0, ctx->stream>>>(H, wnode, nk, n, 0, ctx->partial.as<double2>(), nw);
+            LAUNCH_CHECK(ctx, "trace_h_kernel");
+            reduce_partials_kernel<<<nw, 256, 0, ctx->stream>>>(ctx->partial.as<double2>(), ncta, nw, 1.0, ctx->acc.as<double2>());
+            LAUNCH_CHECK(ctx, "reduce_partials_kernel");
+        } else {
+            trace_h_kernel<<<(unsigned)ncta, 256, 0, ctx->stream>>>(H, wnode, nk, n, 1, yout, nw);
+            LAUNCH_CHECK(ctx, "trace_h_kernel");
+        }
+        return ABZ_OK;
+    }
+    int* ef = ctx->errflag.as<int>();
+    if (n <= 3) {
+        if (mode == 1) {
+            unsigned g = (unsigned)((nk + SM_THREADS - 1) / SM_THREADS);
+            if (n == 1) small_values_kernel<1><<<g, SM_THREADS, 0, ctx->stream>>>(H, nk, fkind, nw, z, sigma, yout, ef);
+            else if (n == 2) small_values_kernel<2><<<g, SM_THREADS, 0, ctx->stream>>>(H, nk, fkind, nw, z, sigma, yout, ef);
+            else small_values_kernel<3><<<g, SM_THREADS, 0, ctx->stream>>>(H, nk, fkind, nw, z, sigma, yout, ef);
+            LAUNCH_CHECK(ctx, "small_values_kernel");
+            return ABZ_OK;
+        }
+        // sums over a materialised H: handled by the caller through small_fused_kernel<_, true>
+        return fail(ctx, ABZ_E_INVALID, "internal: small-norb sums go through run_small_fused");
+    }
+    // DMMA register-resident fast path (norb == 32, scalar pivots inside 8x8 blocks)
+    bool use_mma = (ctx->resolvent_algo != 1) && mma_resolvent_supported(n);
+    if (use_mma) {
+        long ncta = 0;
+        int rc2 = mma_resolvent_partial_count(n, nk, nw, sm, &ncta);
+        if (rc2 == 0) {
+            if (mode == 0) {
+                CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
+                mma_resolvent_launch(H, wnode, nk, n, nw, z, sigma, 0, ctx->partial.as<double2>(), ef, ncta, ctx->stream);
+                LAUNCH_CHECK(ctx, "resolvent_mma_kernel");
+                reduce_partials_kernel<<<nw, 256, 0, ctx->stream>>>(ctx->partial.as<double2>(), ncta, nw, 1.0, ctx->acc.as<double2>());
+                LAUNCH_CHECK(ctx, "reduce_partials_kernel");
+            } else {
+                mma_resolvent_launch(H, wnode, nk, n, nw, z, sigma, 1, yout, ef, ncta, ctx->stream);
+                LAUNCH_CHECK(ctx, "resolvent_mma_kernel");
+            }
+            return ABZ_OK;
+        }
+    }
+    if (n > 64) return fail(ctx, ABZ_E_UNSUPPORTED, "norb > 64 is not supported by the resolvent kernels");
+    int nwarps = 8;
+    while (nwarps > 1 && gj_smem_bytes(n, nw, nwarps) > 200 * 1024) nwarps--;
+    size_t smem = gj_smem_bytes(n, nw, nwarps);
+    if (smem > 220 * 1024) return fail(ctx, ABZ_E_UNSUPPORTED, "too many frequencies per call for the generic resolvent kernel");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(resolvent_gj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_set = true;
+    }
+    // nodes per CTA: aim at ~4 CTAs per SM worth of CTAs, but keep every warp busy: work per node = nw matrices
+    long target_cta = sm * 4;
+    int kper = (int)std::max<long>(1, (nk + target_cta - 1) / target_cta);
+    long ncta = (nk + kper - 1) / kper;
+    if (mode == 0) {
+        CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
+        resolvent_gj_kernel<<<(unsigned)ncta, nwarps * 32, smem, ctx->stream>>>(H, wnode, nk, n, nw, z, sigma, kper, 0,
+                                                                               ctx->partial.as<double2>(), ef);
+        LAUNCH_CHECK(ctx, "resolvent_gj_kernel");
+        reduce_partials_kernel<<<nw, 256, 0, ctx->stream>>>(ctx->partial.as<double2>(), ncta, nw, 1.0, ctx->acc.as<double2>());
+        LAUNCH_CHECK(ctx, "reduce_partials_kernel");
+    } else {
+        resolvent_gj_kernel<<<(unsigned)ncta, nwarps * 32, smem, ctx->stream>>>(H, wnode, nk, n, nw, z, sigma, kper, 1, yout, ef);
+        LAUNCH_CHECK(ctx, "resolvent_gj_kernel");
+    }
+    return ABZ_OK;
+}
+
+template <bool FROM_H>
+int run_small_fused(abz_ctx* ctx, Rule* r, const double2* C1, const double2* Hmat, long r0, long nrows, int fkind,
+                    int nw, const double2* z, const double2* sigma) {
+    Series* s = r->s;
+    long nnodes = r->h_row_nodeptr[r0 + nrows] - r->h_row_nodeptr[r0];
+    if (nnodes <= 0) return ABZ_OK;
+    long ncta = std::min<long>((nnodes + SM_THREADS - 1) / SM_THREADS, (long)ctx->sm_count * 8);
+    int nwy = (fkind == ABZ_F_TRACE_H) ? 1 : (nw + SM_WCH - 1) / SM_WCH;
+    CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
+    dim3 grid((unsigned)ncta, (unsigned)nwy);
+    int* ef = ctx->errflag.as<int>();
+    double2* part = ctx->partial.as<double2>();
+#define SMALL_LAUNCH(NORB)                                                                                         \
+    small_fused_kernel<NORB, FROM_H><<<grid, SM_THREADS, 0, ctx->stream>>>(C1, Hmat, r->d_ptab[0], r->d_row_nodeptr, r0, nrows, \
+                                                                          r->d_node_k1, r->d_node_w, r->N, s->M[0], fkind, nw, z, \
+                                                                          sigma, part, ef)
+    if (s->n == 1) SMALL_LAUNCH(1);
+    else if (s->n == 2) SMALL_LAUNCH(2);
+    else SMALL_LAUNCH(3);
+#undef SMALL_LAUNCH
+    LAUNCH_CHECK(ctx, "small_fused_kernel");
+    reduce_partials_kernel<<<nw, 256, 0, ctx->stream>>>(part, ncta, nw, 1.0, ctx->acc.as<double2>());
+    LAUNCH_CHECK(ctx, "reduce_partials_kernel");
+    return ABZ_OK;
+}
+
+void collect_timings(abz_ctx* ctx, const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& ev_eval,
+                     const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& ev_mat) {
+    ctx->eval_ms = 0; ctx->matfun_ms = 0;
+    for (auto& p : ev_eval) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); ctx->eval_ms += ms; }
+    for (auto& p : ev_mat) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); ctx->matfun_ms += ms; }
+    ctx->ev_used = 0;
+}
+
+long node_cap_for(abz_ctx* ctx, int n) { return (long)std::max<size_t>(1, ctx->budget / ((size_t)n * n * sizeof(double2))); }
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int32_t abz_version(void) { return 100; }
+
+const char* abz_last_error(const abz_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t abz_ctx_create(int32_t device, abz_ctx** out) {
+    if (!out) return fail(nullptr, ABZ_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, ABZ_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, ABZ_E_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, ABZ_E_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, ABZ_E_UNSUPPORTED, "libautobz_cuda is built for sm_100a (B200) only");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, ABZ_E_CUDA, cudaGetErrorString(e));
+    abz_ctx* ctx = new abz_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, ABZ_E_CUDA, cudaGetErrorString(e));
+    }
+    if (ctx->errflag.reserve(sizeof(int)) != cudaSuccess) { delete ctx; return fail(nullptr, ABZ_E_OOM, "errflag alloc"); }
+    cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    *out = ctx;
+    return ABZ_OK;
+}
+
+int32_t abz_ctx_destroy(abz_ctx* ctx) {
+    if (!ctx) return ABZ_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    abz_comm_destroy(ctx);
+    ctx->rules.clear(); ctx->nests.clear(); ctx->series.clear();
+    for (auto e : ctx->events) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ABZ_OK;
+}
+
+int32_t abz_ctx_set_option(abz_ctx* ctx, int32_t option, int64_t value) {
+    if (!ctx) return ABZ_E_INVALID;
+    switch (option) {
+        case ABZ_OPT_RESOLVENT_ALGO: ctx->resolvent_algo = (int)value; return ABZ_OK;
+        case ABZ_OPT_MEM_BUDGET_MB: if (value < 1) return fail(ctx, ABZ_E_INVALID, "budget must be >= 1 MB");
+            ctx->budget = (size_t)value << 20; return ABZ_OK;
+        case ABZ_OPT_FUSED_SMALL: ctx->fused_small = (int)value; return ABZ_OK;
+    }
+    return fail(ctx, ABZ_E_INVALID, "unknown option");
+}
+
+int64_t abz_ctx_launch_count(const abz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t abz_ctx_last_timings(const abz_ctx* ctx, double* eval_ms, double* matfun_ms) {
+    if (!ctx) return ABZ_E_INVALID;
+    if (eval_ms) *eval_ms = ctx->eval_ms;
+    if (matfun_ms) *matfun_ms = ctx->matfun_ms;
+    return ABZ_OK;
+}
+
+int32_t abz_series_create(abz_ctx* ctx, const double* coeffs, int32_t is_complex, int32_t norb, const int32_t M[3],
+                          const int32_t lo[3], const double period[3], abz_series_t* out) {
+    if (!ctx) return ABZ_E_INVALID;
+    if (!coeffs || !M || !lo || !period || !out) return fail(ctx, ABZ_E_INVALID, "NULL argument");
+    if (norb < 1 || norb > 64) return fail(ctx, ABZ_E_UNSUPPORTED, "norb must be in 1..64");
+    for (int d = 0; d < 3; d++)
+        if (M[d] < 1 || !(period[d] > 0)) return fail(ctx, ABZ_E_INVALID, "M >= 1 and period > 0 required");
+    cudaSetDevice(ctx->device);
+    auto s = std::make_unique<Series>();
+    s->n = norb;
+    size_t cnt = (size_t)norb * norb;
+    for (int d = 0; d < 3; d++) { s->M[d] = M[d]; s->lo[d] = lo[d]; s->period[d] = period[d]; cnt *= M[d]; }
+    CU(ctx, cudaMalloc((void**)&s->c, cnt * sizeof(double2)));
+    if (is_complex) {
+        CU(ctx, cudaMemcpyAsync(s->c, coeffs, cnt * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        std::vector<double2> tmp(cnt);
+        for (size_t i = 0; i < cnt; i++) tmp[i] = make_double2(coeffs[i], 0.0);
+        CU(ctx, cudaMemcpyAsync(s->c, tmp.data(), cnt * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    uint64_t id = ctx->next_id++;
+    ctx->series[id] = std::move(s);
+    *out = id;
+    return ABZ_OK;
+}
+
+int32_t abz_series_destroy(abz_ctx* ctx, abz_series_t s) {
+    if (!ctx) return ABZ_E_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    return ctx->series.erase(s) ? ABZ_OK : fail(ctx, ABZ_E_INVALID, "unknown series handle");
+}
+
+int32_t abz_rule_create_full(abz_ctx* ctx, abz_series_t sid, int32_t npt, int32_t k3_lo, int32_t k3_hi, abz_rule_t* out) {
+    if (!ctx) return ABZ_E_INVALID;
+    Series* s = get_series(ctx, sid);
+    if (!s) return fail(ctx, ABZ_E_INVALID, "unknown series handle");
+    if (!out || npt < 1 || k3_lo < 0 || k3_hi > npt || k3_lo > k3_hi) return fail(ctx, ABZ_E_INVALID, "invalid grid range");
+    cudaSetDevice(ctx->device);
+    auto r = std::make_unique<Rule>();
+    r->series_id = sid; r->s = s; r->N = npt; r->full = true;
+    const long N = npt;
+    r->np3 = k3_hi - k3_lo;
+    r->nrows = r->np3 * N;
+    r->nnz = r->nrows * N;
+    r->h_plane_k3.resize(r->np3); r->h_plane_rowptr.resize(r->np3 + 1);
+    r->h_row_k2.resize(r->nrows); r->h_row_nodeptr.resize(r->nrows + 1);
+    for (long p = 0; p < r->np3; p++) { r->h_plane_k3[p] = (int)(k3_lo + p); r->h_plane_rowptr[p] = p * N; }
+    r->h_plane_rowptr[r->np3] = r->nrows;
+    for (long q = 0; q < r->nrows; q++) { r->h_row_k2[q] = (int)(q % N); r->h_row_nodeptr[q] = q * N; }
+    r->h_row_nodeptr[r->nrows] = r->nnz;
+    int rc = finish_rule(ctx, r.get());
+    if (rc) return rc;
+    uint64_t id = ctx->next_id++;
+    ctx->rules[id] = std::move(r);
+    *out = id;
+    return ABZ_OK;
+}
+
+int32_t abz_rule_create_sym(abz_ctx* ctx, abz_series_t sid, int32_t npt, const int32_t* wsym, int32_t k3_lo,
+                            int32_t k3_stride, abz_rule_t* out) {
+    if (!ctx) return ABZ_E_INVALID;
+    Series* s = get_series(ctx, sid);
+    if (!s) return fail(ctx, ABZ_E_INVALID, "unknown series handle");
+    if (!out || !wsym || npt < 1 || k3_lo < 0 || k3_stride < 1) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    cudaSetDevice(ctx->device);
+    auto r = std::make_unique<Rule>();
+    r->series_id = sid; r->s = s; r->N = npt; r->full = false;
+    const long N = npt;
+    r->h_plane_rowptr.push_back(0);
+    r->h_row_nodeptr.push_back(0);
+    for (long i3 = k3_lo; i3 < N; i3 += k3_stride) {
+        bool plane_open = false;
+        for (long i2 = 0; i2 < N; i2++) {
+            const int32_t* row = wsym + (i3 * N + i2) * N;
+            bool row_open = false;
+            for (long i1 = 0; i1 < N; i1++) {
+                if (!row[i1]) continue;
+                if (row[i1] < 0) return fail(ctx, ABZ_E_INVALID, "negative symmetry weight");
+                row_open = true;
+                r->h_node_k1.push_back((int)i1);
+                r->h_node_w.push_back((double)row[i1]);
+            }
+            if (row_open) {
+                plane_open = true;
+                r->h_row_k2.push_back((int)i2);
+                r->h_row_nodeptr.push_back((long)r->h_node_k1.size());
+            }
+        }
+        if (plane_open) {
+            r->h_plane_k3.push_back((int)i3);
+            r->h_plane_rowptr.push_back((long)r->h_row_k2.size());
+        }
+    }
+    r->np3 = (long)r->h_plane_k3.size();
+    r->nrows = (long)r->h_row_k2.size();
+    r->nnz = (long)r->h_node_k1.size();
+    int rc = finish_rule(ctx, r.get());
+    if (rc) return rc;
+    uint64_t id = ctx->next_id++;
+    ctx->rules[id] = std::move(r);
+    *out = id;
+    return ABZ_OK;
+}
+
+int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t* wsym_out, int64_t* nirr) {
+    if (!ctx) return ABZ_E_INVALID;
+    if (npt < 1 || nsyms < 1 || nsyms > 1024 || !syms || !wsym_out) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    cudaSetDevice(ctx->device);
+    size_t tot = (size_t)npt * npt * npt;
+    CU(ctx, ctx->tmp_a.reserve(tot * sizeof(int)));
+    CU(ctx, ctx->tmp_b.reserve((size_t)nsyms * 9 * sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, syms, (size_t)nsyms * 9 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    symptr_rule_kernel<<<(unsigned)((tot + 255) / 256), 256, (size_t)nsyms * 9 * sizeof(int), ctx->stream>>>(
+        npt, nsyms, ctx->tmp_b.as<int>(), ctx->tmp_a.as<int>());
+    LAUNCH_CHECK(ctx, "symptr_rule_kernel");
+    CU(ctx, cudaMemcpyAsync(wsym_out, ctx->tmp_a.p, tot * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nirr) {
+        int64_t c = 0;
+        for (size_t i = 0; i < tot; i++) c += wsym_out[i] != 0;
+        *nirr = c;
+    }
+    return ABZ_OK;
+}
+
+int32_t abz_rule_destroy(abz_ctx* ctx, abz_rule_t r) {
+    if (!ctx) return ABZ_E_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    return ctx->rules.erase(r) ? ABZ_OK : fail(ctx, ABZ_E_INVALID, "unknown rule handle");
+}
+
+int32_t abz_rule_info(abz_ctx* ctx, abz_rule_t rid, int64_t* nnodes, int32_t* norb, int32_t* npt) {
+    if (!ctx) return ABZ_E_INVALID;
+    Rule* r = get_rule(ctx, rid);
+    if (!r) return fail(ctx, ABZ_E_INVALID, "unknown rule handle");
+    if (nnodes) *nnodes = r->nnz;
+    if (norb) *norb = r->s->n;
+    if (npt) *npt = r->N;
+    return ABZ_OK;
+}
+
+int32_t abz_rule_materialize(abz_ctx* ctx, abz_rule_t rid) {
+    if (!ctx) return ABZ_E_INVALID;
+    Rule* r = get_rule(ctx, rid);
+    if (!r) return fail(ctx, ABZ_E_INVALID, "unknown rule handle");
+    if (r->d_H || r->nnz == 0) return ABZ_OK;
+    cudaSetDevice(ctx->device);
+    Series* s = r->s;
+    const long nn = (long)s->n * s->n;
+    size_t bytes = (size_t)r->nnz * nn * sizeof(double2);
+    size_t free_b = 0, total_b = 0;
+    CU(ctx, cudaMemGetInfo(&free_b, &total_b));
+    if (bytes > free_b - std::min<size_t>(free_b, ctx->budget + ((size_t)1 << 30)))
+        return fail(ctx, ABZ_E_OOM, "H(k) on this rule does not fit in device memory; use the streamed sums");
+    CU(ctx, cudaMalloc((void**)&r->d_H, bytes));
+    long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
+    auto chunks = plan_chunks(r, node_cap_for(ctx, s->n), (long)(ctx->budget / (rows1 * sizeof(double2))),
+                              (long)(ctx->budget / (rows2 * sizeof(double2))));
+    cudaEvent_t e0 = next_event(ctx);
+    for (auto& ch : chunks) {
+        int rc = eval_chunk(ctx, r, ch, true, r->d_H + r->h_row_nodeptr[ch.r0] * nn);
+        if (rc) { cudaFree(r->d_H); r->d_H = nullptr; return rc; }
+    }
+    cudaEvent_t e1 = next_event(ctx);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    collect_timings(ctx, {{e0, e1}}, {});
+    return ABZ_OK;
+}
+
+int32_t abz_rule_copy_out(abz_ctx* ctx, abz_rule_t rid, double* Hk, double* kfrac, double* w) {
+    if (!ctx) return ABZ_E_INVALID;
+    Rule* r = get_rule(ctx, rid);
+    if (!r) return fail(ctx, ABZ_E_INVALID, "unknown rule handle");
+    cudaSetDevice(ctx->device);
+    Series* s = r->s;
+    const long nn = (long)s->n * s->n;
+    if (kfrac || w) {
+        for (long p = 0; p < r->np3; p++)
+            for (long q = r->h_plane_rowptr[p]; q < r->h_plane_rowptr[p + 1]; q++)
+                for (long i = r->h_row_nodeptr[q]; i < r->h_row_nodeptr[q + 1]; i++) {
+                    int k1 = r->full ? (int)(i - r->h_row_nodeptr[q]) : r->h_node_k1[i];
+                    if (kfrac) {
+                        kfrac[3 * i] = (double)k1 / r->N;
+                        kfrac[3 * i + 1] = (double)r->h_row_k2[q] / r->N;
+                        kfrac[3 * i + 2] = (double)r->h_plane_k3[p] / r->N;
+                    }
+                    if (w) w[i] = r->full ? 1.0 : r->h_node_w[i];
+                }
+    }
+    if (!Hk) return ABZ_OK;
+    if (r->d_H) {
+        CU(ctx, cudaMemcpyAsync(Hk, r->d_H, (size_t)r->nnz * nn * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return ABZ_OK;
+    }
+    long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
+    auto chunks = plan_chunks(r, node_cap_for(ctx, s->n), (long)(ctx->budget / (rows1 * sizeof(double2))),
+                              (long)(ctx->budget / (rows2 * sizeof(double2))));
+    for (auto& ch : chunks) {
+        long n0 = r->h_row_nodeptr[ch.r0], n1 = r->h_row_nodeptr[ch.r1];
+        CU(ctx, ctx->Hc.reserve((size_t)(n1 - n0) * nn * sizeof(double2)));
+        int rc = eval_chunk(ctx, r, ch, true, ctx->Hc.as<double2>());
+        if (rc) return rc;
+        CU(ctx, cudaMemcpyAsync(Hk + 2 * n0 * nn, ctx->Hc.p, (size_t)(n1 - n0) * nn * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return ABZ_OK;
+}
+
+int32_t abz_rule_resolvent_sum(abz_ctx* ctx, abz_rule_t rid, int32_t fkind, int32_t nw, const double* z,
+                               const double* sigma, double scale, double* out) {
+    if (!ctx) return ABZ_E_INVALID;
+    Rule* r = get_rule(ctx, rid);
+    if (!r) return fail(ctx, ABZ_E_INVALID, "unknown rule handle");
+    if (fkind != ABZ_F_RESOLVENT_TRACE && fkind != ABZ_F_TRACE_H) return fail(ctx, ABZ_E_INVALID, "unknown integrand kind");
+    if (fkind == ABZ_F_TRACE_H) { nw = 1; sigma = nullptr; }
+    if (nw < 1 || !out || (fkind == ABZ_F_RESOLVENT_TRACE && !z)) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    cudaSetDevice(ctx->device);
+    Series* s = r->s;
+    const int n = s->n;
+    const long nn = (long)n * n;
+    int rc = upload_params(ctx, n, nw, fkind == ABZ_F_RESOLVENT_TRACE ? z : nullptr, sigma);
+    if (rc) return rc;
+    CU(ctx, ctx->acc.reserve((size_t)nw * sizeof(double2)));
+    CU(ctx, cudaMemsetAsync(ctx->acc.p, 0, (size_t)nw * sizeof(double2), ctx->stream));
+    const double2* dz = ctx->zbuf.as<double2>();
+    const double2* dsig = sigma ? ctx->sigbuf.as<double2>() : nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_eval, ev_mat;
+    ctx->ev_used = 0;
+    const bool small = (n <= 3);
+    if (r->d_H) {
+        cudaEvent_t e0 = next_event(ctx);
+        if (small) rc = run_small_fused<true>(ctx, r, nullptr, r->d_H, 0, r->nrows, fkind, nw, dz, dsig);
+        else rc = run_matfun(ctx, r->d_H, r->d_node_w, r->nnz, n, fkind, nw, dz, dsig, 0, nullptr);
+        if (rc) return rc;
+        ev_mat.push_back({e0, next_event(ctx)});
+    } else {
+        const bool fused = small && ctx->fused_small;
+        long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
+        long ncap = fused ? ((long)1 << 28) : node_cap_for(ctx, n);
+        auto chunks = plan_chunks(r, ncap, (long)(ctx->budget / (rows1 * sizeof(double2))),
+                                  (long)(ctx->budget / (rows2 * sizeof(double2))));
+        for (auto& ch : chunks) {
+            long n0 = r->h_row_nodeptr[ch.r0], n1 = r->h_row_nodeptr[ch.r1];
+            cudaEvent_t e0 = next_event(ctx);
+            if (!fused) CU(ctx, ctx->Hc.reserve((size_t)(n1 - n0) * nn * sizeof(double2)));
+            rc = eval_chunk(ctx, r, ch, !fused, ctx->Hc.as<double2>());
+            if (rc) return rc;
+            cudaEvent_t e1 = next_event(ctx);
+            if (fused) rc = run_small_fused<false>(ctx, r, ctx->C1.as<double2>(), nullptr, ch.r0, ch.r1 - ch.r0, fkind, nw, dz, dsig);
+            else if (small) {
+                // unfused small path (option): treat the chunk as a materialised block
+                rc = fail(ctx, ABZ_E_UNSUPPORTED, "unfused small-norb streaming is not implemented; materialize the rule");
+            } else
+                rc = run_matfun(ctx, ctx->Hc.as<double2>(), r->d_node_w ? r->d_node_w + n0 : nullptr, n1 - n0, n, fkind, nw, dz, dsig, 0, nullptr);
+            if (rc) return rc;
+            cudaEvent_t e2 = next_event(ctx);
+            ev_eval.push_back({e0, e1});
+            ev_mat.push_back({e1, e2});
+        }
+    }
+    std::vector<double2> h(nw);
+    CU(ctx, cudaMemcpyAsync(h.data(), ctx->acc.p, (size_t)nw * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = check_errflag(ctx, "abz_rule_resolvent_sum");
+    collect_timings(ctx, ev_eval, ev_mat);
+    if (rc) return rc;
+    for (int w = 0; w < nw; w++) { out[2 * w] = scale * h[w].x; out[2 * w + 1] = scale * h[w].y; }
+    return ABZ_OK;
+}
+
+static size_t eig_smem_bytes(int n, int threads) {
+    int np = (n + 1) & ~1, npair = np / 2;
+    return (size_t)n * (n + 1) * 16 + (size_t)npair * 16 + (size_t)npair * 8 + (size_t)n * 8 + (size_t)(2 * (threads / 32) + 2) * 8 +
+           (size_t)npair * 8 + 64;
+}
+
+static int run_eig(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int n, int mode, int kind, double p0, double p1,
+                   double* evals, double* acc) {
+    if (nk <= 0) return ABZ_OK;
+    int threads = std::min(256, std::max(32, ((n * ((n + 1) / 2) + 31) / 32) * 32));
+    size_t smem = eig_smem_bytes(n, threads);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(eig_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / smem));
+    long ncta = std::min<long>(nk, (long)ctx->sm_count * per_sm);
+    if (mode == 0) CU(ctx, ctx->partial.reserve((size_t)ncta * sizeof(double)));
+    eig_jacobi_kernel<<<(unsigned)ncta, threads, smem, ctx->stream>>>(H, wnode, nk, n, mode, kind, p0, p1, evals,
+                                                                     ctx->partial.as<double>(), ctx->errflag.as<int>());
+    LAUNCH_CHECK(ctx, "eig_jacobi_kernel");
+    if (mode == 0) {
+        reduce_real_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), ncta, 1.0, acc);
+        LAUNCH_CHECK(ctx, "reduce_real_kernel");
+    }
+    return ABZ_OK;
+}
+
+int32_t abz_rule_eig_sum(abz_ctx* ctx, abz_rule_t rid, int32_t kind, const double* params, double scale, double* out) {
+    if (!ctx) return ABZ_E_INVALID;
+    Rule* r = get_rule(ctx, rid);
+    if (!r) return fail(ctx, ABZ_E_INVALID, "unknown rule handle");
+    if (kind < 0 || kind > 3 || !out || (kind != 0 && !params)) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    cudaSetDevice(ctx->device);
+    Series* s = r->s;
+    const int n = s->n;
+    const long nn = (long)n * n;
+    double p0 = params ? params[0] : 0.0, p1 = params ? params[1] : 1.0;
+    CU(ctx, ctx->acc.reserve(sizeof(double2)));
+    CU(ctx, cudaMemsetAsync(ctx->acc.p, 0, sizeof(double2), ctx->stream));
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_eval, ev_mat;
+    ctx->ev_used = 0;
+    int rc;
+    if (r->d_H) {
+        cudaEvent_t e0 = next_event(ctx);
+        rc = run_eig(ctx, r->d_H, r->d_node_w, r->nnz, n, 0, kind, p0, p1, nullptr, ctx->acc.as<double>());
+        if (rc) return rc;
+        ev_mat.push_back({e0, next_event(ctx)});
+    } else {
+        long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
+        auto chunks = plan_chunks(r, node_cap_for(ctx, n), (long)(ctx->budget / (rows1 * sizeof(double2))),
+                                  (long)(ctx->budget / (rows2 * sizeof(double2))));
+        for (auto& ch : chunks) {
+            long n0 = r->h_row_nodeptr[ch.r0], n1 = r->h_row_nodeptr[ch.r1];
+            cudaEvent_t e0 = next_event(ctx);
+            CU(ctx, ctx->Hc.reserve((size_t)(n1 - n0) * nn * sizeof(double2)));
+            rc = eval_chunk(ctx, r, ch, true, ctx->Hc.as<double2>());
+            if (rc) return rc;
+            cudaEvent_t e1 = next_event(ctx);
+            rc = run_eig(ctx, ctx->Hc.as<double2>(), r->d_node_w ? r->d_node_w + n0 : nullptr, n1 - n0, n, 0, kind, p0, p1, nullptr,
+                         ctx->acc.as<double>());
+            if (rc) return rc;
+            cudaEvent_t e2 = next_event(ctx);
+            ev_eval.push_back({e0, e1});
+            ev_mat.push_back({e1, e2});
+        }
+    }
+    double h = 0;
+    CU(ctx, cudaMemcpyAsync(&h, ctx->acc.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = check_errflag(ctx, "abz_rule_eig_sum");
+    collect_timings(ctx, ev_eval, ev_mat);
+    if (rc) return rc;
+    out[0] = scale * h;
+    return ABZ_OK;
+}
+
+int32_t abz_rule_eigvals(abz_ctx* ctx, abz_rule_t rid, double* evals) {
+    if (!ctx) return ABZ_E_INVALID;
+    Rule* r = get_rule(ctx, rid);
+    if (!r) return fail(ctx, ABZ_E_INVALID, "unknown rule handle");
+    if (!evals) return fail(ctx, ABZ_E_INVALID, "NULL output");
+    cudaSetDevice(ctx->device);
+    Series* s = r->s;
+    const int n = s->n;
+    const long nn = (long)n * n;
+    long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
+    std::vector<Chunk> chunks;
+    if (r->d_H) chunks.push_back({0, r->np3, 0, r->nrows});
+    else chunks = plan_chunks(r, node_cap_for(ctx, n), (long)(ctx->budget / (rows1 * sizeof(double2))),
+                              (long)(ctx->budget / (rows2 * sizeof(double2))));
+    for (auto& ch : chunks) {
+        long n0 = r->h_row_nodeptr[ch.r0], n1 = r->h_row_nodeptr[ch.r1];
+        const double2* H = r->d_H;
+        if (!H) {
+            CU(ctx, ctx->Hc.reserve((size_t)(n1 - n0) * nn * sizeof(double2)));
+            int rc = eval_chunk(ctx, r, ch, true, ctx->Hc.as<double2>());
+            if (rc) return rc;
+            H = ctx->Hc.as<double2>();
+        }
+        CU(ctx, ctx->tmp_a.reserve((size_t)(n1 - n0) * n * sizeof(double)));
+        int rc = run_eig(ctx, H, nullptr, n1 - n0, n, 1, 0, 0, 1, ctx->tmp_a.as<double>(), nullptr);
+        if (rc) return rc;
+        CU(ctx, cudaMemcpyAsync(evals + n0 * n, ctx->tmp_a.p, (size_t)(n1 - n0) * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return check_errflag(ctx, "abz_rule_eigvals");
+}
+
+// ---- scattered points ---------------------------------------------------------------------------
+static int points_eval_dev(abz_ctx* ctx, Series* s, int64_t npts, const double* k, double2** Hdev) {
+    const long nn = (long)s->n * s->n;
+    CU(ctx, ctx->tmp_a.reserve((size_t)npts * 3 * sizeof(double)));
+    CU(ctx, ctx->Hc.reserve((size_t)npts * nn * sizeof(double2)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_a.p, k, (size_t)npts * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    size_t smem = (size_t)(s->M[0] + s->M[1] + s->M[2]) * sizeof(double2);
+    points_eval_kernel<<<(unsigned)npts, 128, smem, ctx->stream>>>(s->c, (int)nn, s->M[0], s->M[1], s->M[2], s->lo[0], s->lo[1],
+                                                                  s->lo[2], s->period[0], s->period[1], s->period[2],
+                                                                  ctx->tmp_a.as<double>(), ctx->Hc.as<double2>());
+    LAUNCH_CHECK(ctx, "points_eval_kernel");
+    *Hdev = ctx->Hc.as<double2>();
+    return ABZ_OK;
+}
+
+int32_t abz_points_eval(abz_ctx* ctx, abz_series_t sid, int64_t npts, const double* k, double* Hk) {
+    if (!ctx) return ABZ_E_INVALID;
+    Series* s = get_series(ctx, sid);
+    if (!s) return fail(ctx, ABZ_E_INVALID, "unknown series handle");
+    if (npts < 0 || (npts > 0 && (!k || !Hk))) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    if (npts == 0) return ABZ_OK;
+    cudaSetDevice(ctx->device);
+    double2* Hd;
+    int rc = points_eval_dev(ctx, s, npts, k, &Hd);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(Hk, Hd, (size_t)npts * s->n * s->n * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABZ_OK;
+}
+
+int32_t abz_points_resolvent(abz_ctx* ctx, abz_series_t sid, int64_t npts, const double* k, int32_t fkind, int32_t nw,
+                             const double* z, const double* sigma, double* y) {
+    if (!ctx) return ABZ_E_INVALID;
+    Series* s = get_series(ctx, sid);
+    if (!s) return fail(ctx, ABZ_E_INVALID, "unknown series handle");
+    if (fkind == ABZ_F_TRACE_H) { nw = 1; sigma = nullptr; }
+    if (npts < 0 || nw < 1 || (npts > 0 && (!k || !y)) || (fkind == ABZ_F_RESOLVENT_TRACE && !z))
+        return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    if (npts == 0) return ABZ_OK;
+    cudaSetDevice(ctx->device);
+    double2* Hd;
+    int rc = points_eval_dev(ctx, s, npts, k, &Hd);
+    if (rc) return rc;
+    rc = upload_params(ctx, s->n, nw, fkind == ABZ_F_RESOLVENT_TRACE ? z : nullptr, sigma);
+    if (rc) return rc;
+    CU(ctx, ctx->tmp_b.reserve((size_t)npts * nw * sizeof(double2)));
+    rc = run_matfun(ctx, Hd, nullptr, npts, s->n, fkind, nw, ctx->zbuf.as<double2>(), sigma ? ctx->sigbuf.as<double2>() : nullptr, 1,
+                    ctx->tmp_b.as<double2>());
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(y, ctx->tmp_b.p, (size_t)npts * nw * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    return check_errflag(ctx, "abz_points_resolvent");
+}
+
+// ---- IAI nest arena -------------------------------------------------------------------------------
+int32_t abz_nest_create(abz_ctx* ctx, abz_series_t sid, int32_t ndim, int64_t cap2, int64_t cap1, abz_nest_t* out) {
+    if (!ctx) return ABZ_E_INVALID;
+    Series* s = get_series(ctx, sid);
+    if (!s) return fail(ctx, ABZ_E_INVALID, "unknown series handle");
+    if (!out || ndim < 1 || ndim > 3 || cap2 < 0 || cap1 < 0) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    for (int d = ndim; d < 3; d++)
+        if (s->M[d] != 1) return fail(ctx, ABZ_E_INVALID, "variables in Fourier series don't match domain");
+    cudaSetDevice(ctx->device);
+    auto nst = std::make_unique<Nest>();
+    nst->s = s; nst->ndim = ndim; nst->cap2 = cap2; nst->cap1 = cap1;
+    const size_t nn = (size_t)s->n * s->n;
+    if (ndim == 3 && cap2 > 0) CU(ctx, cudaMalloc((void**)&nst->L2, (size_t)cap2 * nn * s->M[0] * s->M[1] * sizeof(double2)));
+    if (ndim >= 2 && cap1 > 0) CU(ctx, cudaMalloc((void**)&nst->L1, (size_t)cap1 * nn * s->M[0] * sizeof(double2)));
+    uint64_t id = ctx->next_id++;
+    ctx->nests[id] = std::move(nst);
+    *out = id;
+    return ABZ_OK;
+}
+
+int32_t abz_nest_destroy(abz_ctx* ctx, abz_nest_t nest) {
+    if (!ctx) return ABZ_E_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    return ctx->nests.erase(nest) ? ABZ_OK : fail(ctx, ABZ_E_INVALID, "unknown nest handle");
+}
+
+static int check_slots(abz_ctx* ctx, const int64_t* slot, int64_t n, int64_t cap, const char* what) {
+    for (int64_t i = 0; i < n; i++)
+        if (slot[i] < 0 || slot[i] >= cap) return fail(ctx, ABZ_E_INVALID, std::string(what) + ": slot index out of range");
+    return ABZ_OK;
+}
+
+int32_t abz_nest_contract3(abz_ctx* ctx, abz_nest_t nid, int64_t n, const double* x3, const int64_t* slot2) {
+    if (!ctx) return ABZ_E_INVALID;
+    Nest* nst = get_nest(ctx, nid);
+    if (!nst) return fail(ctx, ABZ_E_INVALID, "unknown nest handle");
+    if (nst->ndim != 3) return fail(ctx, ABZ_E_INVALID, "abz_nest_contract3 needs a 3-d nest");
+    if (n < 0 || (n > 0 && (!x3 || !slot2))) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    if (n == 0) return ABZ_OK;
+    int rc = check_slots(ctx, slot2, n, nst->cap2, "abz_nest_contract3");
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    Series* s = nst->s;
+    const long rows = (long)s->n * s->n * s->M[0] * s->M[1];
+    CU(ctx, ctx->tmp_a.reserve((size_t)n * sizeof(double)));
+    CU(ctx, ctx->tmp_b.reserve((size_t)n * sizeof(long)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_a.p, x3, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, slot2, (size_t)n * sizeof(long), cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((unsigned)((rows + 255) / 256), (unsigned)n);
+    nest_contract_kernel<<<grid, 256, (size_t)s->M[2] * sizeof(double2), ctx->stream>>>(
+        s->c, 0, nullptr, ctx->tmp_a.as<double>(), ctx->tmp_b.as<long>(), nst->L2, rows, s->M[2], s->lo[2], s->period[2]);
+    LAUNCH_CHECK(ctx, "nest_contract_kernel");
+    return ABZ_OK;
+}
+
+int32_t abz_nest_contract2(abz_ctx* ctx, abz_nest_t nid, int64_t n, const double* x2, const int64_t* parent, const int64_t* slot1) {
+    if (!ctx) return ABZ_E_INVALID;
+    Nest* nst = get_nest(ctx, nid);
+    if (!nst) return fail(ctx, ABZ_E_INVALID, "unknown nest handle");
+    if (nst->ndim < 2) return fail(ctx, ABZ_E_INVALID, "abz_nest_contract2 needs a nest with ndim >= 2");
+    if (n < 0 || (n > 0 && (!x2 || !slot1 || (nst->ndim == 3 && !parent)))) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    if (n == 0) return ABZ_OK;
+    int rc = check_slots(ctx, slot1, n, nst->cap1, "abz_nest_contract2");
+    if (rc) return rc;
+    if (nst->ndim == 3 && (rc = check_slots(ctx, parent, n, nst->cap2, "abz_nest_contract2(parent)"))) return rc;
+    cudaSetDevice(ctx->device);
+    Series* s = nst->s;
+    const long rows = (long)s->n * s->n * s->M[0];
+    CU(ctx, ctx->tmp_a.reserve((size_t)n * sizeof(double)));
+    CU(ctx, ctx->tmp_b.reserve((size_t)n * sizeof(long)));
+    CU(ctx, ctx->tmp_c.reserve((size_t)n * sizeof(long)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_a.p, x2, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, slot1, (size_t)n * sizeof(long), cudaMemcpyHostToDevice, ctx->stream));
+    const double2* src = s->c; const long* par = nullptr; long stride = 0;
+    if (nst->ndim == 3) {
+        CU(ctx, cudaMemcpyAsync(ctx->tmp_c.p, parent, (size_t)n * sizeof(long), cudaMemcpyHostToDevice, ctx->stream));
+        src = nst->L2; par = ctx->tmp_c.as<long>(); stride = rows * s->M[1];
+    }
+    dim3 grid((unsigned)((rows + 255) / 256), (unsigned)n);
+    nest_contract_kernel<<<grid, 256, (size_t)s->M[1] * sizeof(double2), ctx->stream>>>(
+        src, stride, par, ctx->tmp_a.as<double>(), ctx->tmp_b.as<long>(), nst->L1, rows, s->M[1], s->lo[1], s->period[1]);
+    LAUNCH_CHECK(ctx, "nest_contract_kernel");
+    return ABZ_OK;
+}
+
+int32_t abz_nest_eval(abz_ctx* ctx, abz_nest_t nid, int64_t npts, const double* x1, const int64_t* slot1, int32_t fkind,
+                      const double* z, const double* sigma, double* y) {
+    if (!ctx) return ABZ_E_INVALID;
+    Nest* nst = get_nest(ctx, nid);
+    if (!nst) return fail(ctx, ABZ_E_INVALID, "unknown nest handle");
+    if (npts < 0 || (npts > 0 && (!x1 || !y || (nst->ndim >= 2 && !slot1))) || (fkind == ABZ_F_RESOLVENT_TRACE && !z))
+        return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    if (npts == 0) return ABZ_OK;
+    int rc;
+    if (nst->ndim >= 2 && (rc = check_slots(ctx, slot1, npts, nst->cap1, "abz_nest_eval"))) return rc;
+    cudaSetDevice(ctx->device);
+    Series* s = nst->s;
+    const int n = s->n;
+    const long nn = (long)n * n;
+    CU(ctx, ctx->tmp_a.reserve((size_t)npts * sizeof(double)));
+    CU(ctx, ctx->tmp_b.reserve((size_t)npts * sizeof(long)));
+    CU(ctx, ctx->tmp_c.reserve((size_t)npts * sizeof(double2)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_a.p, x1, (size_t)npts * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const long* dslot = nullptr; const double2* L1 = s->c; long stride = 0;
+    if (nst->ndim >= 2) {
+        CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, slot1, (size_t)npts * sizeof(long), cudaMemcpyHostToDevice, ctx->stream));
+        dslot = ctx->tmp_b.as<long>(); L1 = nst->L1; stride = nn * s->M[0];
+    }
+    rc = upload_params(ctx, n, 1, fkind == ABZ_F_RESOLVENT_TRACE ? z : nullptr, sigma);
+    if (rc) return rc;
+    double2 zz = make_double2(z ? z[0] : 0.0, z ? z[1] : 0.0);
+    const double2* dsig = sigma ? ctx->sigbuf.as<double2>() : nullptr;
+    double2* yd = ctx->tmp_c.as<double2>();
+    int* ef = ctx->errflag.as<int>();
+    if (n <= 3) {
+        unsigned g = (unsigned)((npts + 127) / 128);
+#define NEST_LAUNCH(NORB) \
+    nest_eval_small_kernel<NORB><<<g, 128, 0, ctx->stream>>>(L1, stride, dslot, ctx->tmp_a.as<double>(), npts, s->M[0], s->lo[0], \
+                                                            s->period[0], fkind, zz, dsig, yd, ef)
+        if (n == 1) NEST_LAUNCH(1); else if (n == 2) NEST_LAUNCH(2); else NEST_LAUNCH(3);
+#undef NEST_LAUNCH
+        LAUNCH_CHECK(ctx, "nest_eval_small_kernel");
+    } else {
+        CU(ctx, ctx->Hc.reserve((size_t)npts * nn * sizeof(double2)));
+        dim3 grid((unsigned)((nn + 127) / 128), (unsigned)npts);
+        nest_eval_h_kernel<<<grid, 128, (size_t)s->M[0] * sizeof(double2), ctx->stream>>>(
+            L1, stride, dslot, ctx->tmp_a.as<double>(), (int)nn, s->M[0], s->lo[0], s->period[0], ctx->Hc.as<double2>());
+        LAUNCH_CHECK(ctx, "nest_eval_h_kernel");
+        rc = run_matfun(ctx, ctx->Hc.as<double2>(), nullptr, npts, n, fkind, 1, ctx->zbuf.as<double2>(), dsig, 1, yd);
+        if (rc) return rc;
+    }
+    CU(ctx, cudaMemcpyAsync(y, yd, (size_t)npts * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    return check_errflag(ctx, "abz_nest_eval");
+}
+
+// ---- NCCL through dlopen ----------------------------------------------------------------------------
+typedef struct { char internal[128]; } abz_nccl_uid;
+typedef int (*nccl_get_uid_t)(abz_nccl_uid*);
+typedef int (*nccl_init_rank_t)(void**, int, abz_nccl_uid, int);
+typedef int (*nccl_allreduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_destroy_t)(void*);
+
+static void* nccl_open(std::string* why) {
+    static void* lib = nullptr;
+    if (lib) return lib;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (auto nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) return lib; }
+    if (why) *why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+    return nullptr;
+}
+
+int32_t abz_comm_unique_id(void* uid128) {
+    std::string why;
+    void* lib = nccl_open(&why);
+    if (!lib) return fail(nullptr, ABZ_E_NCCL, why);
+    auto f = (nccl_get_uid_t)dlsym(lib, "ncclGetUniqueId");
+    if (!f || !uid128) return fail(nullptr, ABZ_E_NCCL, "ncclGetUniqueId unavailable");
+    return f((abz_nccl_uid*)uid128) == 0 ? ABZ_OK : fail(nullptr, ABZ_E_NCCL, "ncclGetUniqueId failed");
+}
+
+int32_t abz_comm_init(abz_ctx* ctx, int32_t rank, int32_t nranks, const void* uid128) {
+    if (!ctx) return ABZ_E_INVALID;
+    if (nranks < 1 || rank < 0 || rank >= nranks || !uid128) return fail(ctx, ABZ_E_INVALID, "invalid rank/nranks");
+    std::string why;
+    void* lib = nccl_open(&why);
+    if (!lib) return fail(ctx, ABZ_E_NCCL, why);
+    auto f = (nccl_init_rank_t)dlsym(lib, "ncclCommInitRank");
+    if (!f) return fail(ctx, ABZ_E_NCCL, "ncclCommInitRank unavailable");
+    cudaSetDevice(ctx->device);
+    abz_nccl_uid uid;
+    memcpy(&uid, uid128, sizeof(uid));
+    void* comm = nullptr;
+    if (f(&comm, nranks, uid, rank) != 0) return fail(ctx, ABZ_E_NCCL, "ncclCommInitRank failed");
+    ctx->nccl_lib = lib; ctx->nccl_comm = comm; ctx->nranks = nranks;
+    return ABZ_OK;
+}
+
+int32_t abz_allreduce_sum(abz_ctx* ctx, double* host_buf, int64_t n) {
+    if (!ctx) return ABZ_E_INVALID;
+    if (!ctx->nccl_comm) return ctx->nranks == 1 ? ABZ_OK : fail(ctx, ABZ_E_NCCL, "communicator not initialised");
+    if (n <= 0 || !host_buf) return fail(ctx, ABZ_E_INVALID, "invalid buffer");
+    auto f = (nccl_allreduce_t)dlsym(ctx->nccl_lib, "ncclAllReduce");
+    if (!f) return fail(ctx, ABZ_E_NCCL, "ncclAllReduce unavailable");
+    cudaSetDevice(ctx->device);
+    CU(ctx, ctx->tmp_a.reserve((size_t)n * sizeof(double)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_a.p, host_buf, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (f(ctx->tmp_a.p, ctx->tmp_a.p, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, ctx->stream) != 0)
+        return fail(ctx, ABZ_E_NCCL, "ncclAllReduce failed");
+    CU(ctx, cudaMemcpyAsync(host_buf, ctx->tmp_a.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABZ_OK;
+}
+
+int32_t abz_comm_destroy(abz_ctx* ctx) {
+    if (!ctx || !ctx->nccl_comm) return ABZ_OK;
+    auto f = (nccl_destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
+    if (f) f(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    return ABZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,417 @@
+// Kernels of the PTR hot path: phase tables (K0), separable contraction stages (K1, DMMA),
+// pivoted Gauss-Jordan resolvent (K3 generic), fused small-norb evaluation+resolvent (K3 small),
+// deterministic reductions (K5).  Hand-written for sm_100a.
+#pragma once
+#include "abz_common.cuh"
+
+namespace abz {
+
+// ------------------------------------------------------------------------------------------------
+// K0: phase table of a PTR dimension.  ptab[m*N + i] = exp(2 pi i * ((i*(m+lo)) mod N)/N)
+// Nodes u_i = i/N (AutoSymPTR.ptrpoints) scaled by the period and divided by it again inside
+// contract! (src/fourier.jl:133,149) => the phase depends on i*R mod N only: reduced exactly in
+// integer arithmetic before sincospi.
+// ------------------------------------------------------------------------------------------------
+__global__ void phase_table_kernel(double2* __restrict__ ptab, int M, int lo, int N) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)M * N) return;
+    int m = (int)(idx / N), i = (int)(idx % N);
+    long r = ((long)i * (long)(m + lo)) % N;
+    if (r < 0) r += N;
+    double s, c;
+    sincospi(2.0 * (double)r / (double)N, &s, &c);
+    ptab[idx] = make_double2(c, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: one separable contraction stage as a batched complex GEMM on the FP64 tensor cores.
+//   out[obase_b + j][row] = sum_m in[b][m][row] * P[m][k_j],   row < rows, j < kcount_b
+// (FourierSeriesEvaluators.contract! / evaluate on a whole vector of nodes at once; the three
+// uses are stage 3: rows = n^2 M1 M2, one batch, nodes = k3 planes; stage 2: rows = n^2 M1,
+// batch = plane, nodes = k2 rows of that plane; stage 1: rows = n^2, batch = (k2,k3) row,
+// nodes = k1 of that row — the loop nest of fourier_ptr!/_fourier_symptr!, src/fourier.jl:132-164,
+// 216-263, executed level by level.)
+// Complex product as a real GEMM: A'[row,(m,c)] = {Re,Im} in, B'[(m,c),(j,c')] = [[Pr,Pi],[-Pi,Pr]].
+// CTA = 4 warps, tile 64 rows x 32 nodes, K = 2*M (padded to a multiple of 4) in shared memory.
+// ptr[b0+b] .. ptr[b0+b+1] delimit the node list of batch b; klist == NULL means k_j = j.
+// ------------------------------------------------------------------------------------------------
+constexpr int ST_RT = 64;   // rows per CTA
+constexpr int ST_JT = 32;   // nodes per CTA iteration (8 per warp)
+
+__global__ void __launch_bounds__(128)
+contract_stage_kernel(const double2* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ ptab,
+                      const long* __restrict__ ptr, long b0, const int* __restrict__ klist, int N, int M, long rows,
+                      long in_batch_stride) {
+    extern __shared__ double2 st_smem[];
+    const int Mp = (M + 1) & ~1;
+    double2* sA = st_smem;                // [Mp][ST_RT]
+    double2* sP = st_smem + Mp * ST_RT;   // [Mp][ST_JT]
+    const long b = blockIdx.x;
+    const long row0 = (long)blockIdx.y * ST_RT;
+    const long koff = ptr[b0 + b];
+    const int kcount = (int)(ptr[b0 + b + 1] - koff);
+    const long obase = koff - ptr[b0];
+    if (kcount <= 0) return;
+    const double2* inb = in + b * in_batch_stride;
+    for (int idx = threadIdx.x; idx < Mp * ST_RT; idx += 128) {
+        int m = idx / ST_RT, r = idx % ST_RT;
+        long row = row0 + r;
+        sA[idx] = (m < M && row < rows) ? inb[(long)m * rows + row] : make_double2(0.0, 0.0);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int c = q & 1;
+    for (int j0 = 0; j0 < kcount; j0 += ST_JT) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < Mp * ST_JT; idx += 128) {
+            int m = idx / ST_JT, jj = idx % ST_JT;
+            int j = j0 + jj;
+            double2 p = make_double2(0.0, 0.0);
+            if (m < M && j < kcount) {
+                int k = klist ? klist[koff + j] : j;
+                p = ptab[(long)m * N + k];
+            }
+            sP[idx] = p;
+        }
+        __syncthreads();
+        const int jw = warp * 8;
+        if (j0 + jw >= kcount) continue;
+        double acc[8][2][2];
+#pragma unroll
+        for (int mf = 0; mf < 8; mf++)
+#pragma unroll
+            for (int nf = 0; nf < 2; nf++) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+        for (int ks = 0; ks < Mp / 2; ks++) {
+            const int m = 2 * ks + (q >> 1);
+            double bf[2];
+#pragma unroll
+            for (int nf = 0; nf < 2; nf++) {
+                double2 p = sP[m * ST_JT + jw + 4 * nf + (g >> 1)];
+                const int cp = g & 1;
+                bf[nf] = (c == cp) ? p.x : (c == 0 ? p.y : -p.y);
+            }
+#pragma unroll
+            for (int mf = 0; mf < 8; mf++) {
+                const double* a = reinterpret_cast<const double*>(&sA[m * ST_RT + mf * 8 + g]);
+                double af = a[c];
+                dmma884(acc[mf][0][0], acc[mf][0][1], af, bf[0]);
+                dmma884(acc[mf][1][0], acc[mf][1][1], af, bf[1]);
+            }
+        }
+#pragma unroll
+        for (int nf = 0; nf < 2; nf++) {
+            int j = j0 + jw + 4 * nf + q;
+            if (j >= kcount) continue;
+            double2* o = out + (obase + j) * rows;
+#pragma unroll
+            for (int mf = 0; mf < 8; mf++) {
+                long row = row0 + mf * 8 + g;
+                if (row < rows) o[row] = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: deterministic reduction of per-CTA partial sums:  acc[w] += scale * sum_c partial[c*nw + w]
+// One CTA (256 threads) per w; fixed strided order + fixed tree => bit-reproducible run to run.
+// (AutoSymPTR.quadsum's final accumulation, src/fourier.jl:204-207, 289-292.)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const double2* __restrict__ partial, long ncta, int nw, double scale, double2* __restrict__ acc) {
+    __shared__ double sx[256], sy[256];
+    const int w = blockIdx.x;
+    double x = 0.0, y = 0.0;
+    for (long c = threadIdx.x; c < ncta; c += 256) {
+        double2 p = partial[c * nw + w];
+        x += p.x; y += p.y;
+    }
+    sx[threadIdx.x] = x; sy[threadIdx.x] = y;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sx[threadIdx.x] += sx[threadIdx.x + s]; sy[threadIdx.x] += sy[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double2 a = acc[w];
+        a.x += scale * sx[0]; a.y += scale * sy[0];
+        acc[w] = a;
+    }
+}
+
+// block-level deterministic sum of NV complex values per thread -> partial[blockIdx.x*stride + v0 + v]
+template <int NV, int THREADS>
+__device__ __forceinline__ void block_reduce_store(double2 (&v)[NV], double2* __restrict__ dst, int nvalid) {
+    __shared__ double2 red[THREADS / 32][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        v[i].x = warp_sum(v[i].x);
+        v[i].y = warp_sum(v[i].y);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) red[warp][i] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV && threadIdx.x < nvalid) {
+        double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int wp = 0; wp < THREADS / 32; wp++) { s.x += red[wp][threadIdx.x].x; s.y += red[wp][threadIdx.x].y; }
+        dst[threadIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tr[(z - H - Sigma)^-1] for n <= 3 in registers (closed-form adjugate, as StaticArrays `inv` does
+// for the reference's SMatrix integrands, aps_example/aps_example.jl:30).
+// ------------------------------------------------------------------------------------------------
+template <int NORB>
+__device__ __forceinline__ double2 small_resolvent_trace(const double2 (&h)[NORB * NORB], double2 z, const double2* __restrict__ sg) {
+    double2 a[NORB * NORB];
+#pragma unroll
+    for (int j = 0; j < NORB; j++)
+#pragma unroll
+        for (int i = 0; i < NORB; i++) {
+            double2 v = make_double2(-h[i + j * NORB].x, -h[i + j * NORB].y);
+            if (sg) { v.x -= sg[i + j * NORB].x; v.y -= sg[i + j * NORB].y; }
+            if (i == j) { v.x += z.x; v.y += z.y; }
+            a[i + j * NORB] = v;
+        }
+    if (NORB == 1) return crecip(a[0]);
+    if (NORB == 2) {
+        double2 det = csub(cmul(a[0], a[3]), cmul(a[1], a[2]));
+        return cdiv(cadd(a[0], a[3]), det);
+    }
+    // NORB == 3: column-major a[i + 3j]
+    double2 a11 = a[0], a21 = a[1], a31 = a[2], a12 = a[3], a22 = a[4], a32 = a[5], a13 = a[6], a23 = a[7], a33 = a[8];
+    double2 c11 = csub(cmul(a22, a33), cmul(a23, a32));
+    double2 c22 = csub(cmul(a11, a33), cmul(a13, a31));
+    double2 c33 = csub(cmul(a11, a22), cmul(a12, a21));
+    double2 c12 = csub(cmul(a23, a31), cmul(a21, a33));
+    double2 c13 = csub(cmul(a21, a32), cmul(a22, a31));
+    double2 det = cadd(cadd(cmul(a11, c11), cmul(a12, c12)), cmul(a13, c13));
+    return cdiv(cadd(cadd(c11, c22), c33), det);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3-small: fused innermost evaluation + integrand + weighted partial sum for norb <= 3.
+// One thread per node: H(k) = sum_m C1[row][m] P1[m][k1] accumulated in registers (the innermost
+// `workspace_evaluate!` of fourier_ptr!/_fourier_symptr!, src/fourier.jl:136,230), then the
+// integrand for WCH frequencies (blockIdx.y selects the frequency chunk), times the node weight.
+// FROM_H = true reads a materialised H(k) instead (cached rule reused across parameters,
+// src/interfaces.jl:234-243).  Nothing of size nodes*n^2 is written to HBM.
+// row lookup: binary search in nodeptr[r0..r0+nrows]; identity (full grid) when klist == NULL.
+// ------------------------------------------------------------------------------------------------
+constexpr int SM_WCH = 4;
+constexpr int SM_THREADS = 256;
+
+template <int NORB, bool FROM_H>
+__global__ void __launch_bounds__(SM_THREADS)
+small_fused_kernel(const double2* __restrict__ C1, const double2* __restrict__ Hmat, const double2* __restrict__ ptab1,
+                   const long* __restrict__ nodeptr, long r0, long nrows, const int* __restrict__ klist,
+                   const double* __restrict__ wnode, int N, int M1, int fkind, int nw, const double2* __restrict__ z,
+                   const double2* __restrict__ sigma, double2* __restrict__ partial, int* __restrict__ errflag) {
+    constexpr int NN = NORB * NORB;
+    const long node_base = nodeptr[r0];
+    const long nnodes = nodeptr[r0 + nrows] - node_base;
+    const int w0 = blockIdx.y * SM_WCH;
+    double2 acc[SM_WCH];
+#pragma unroll
+    for (int i = 0; i < SM_WCH; i++) acc[i] = make_double2(0.0, 0.0);
+    for (long i = (long)blockIdx.x * SM_THREADS + threadIdx.x; i < nnodes; i += (long)gridDim.x * SM_THREADS) {
+        double2 h[NN];
+        if (FROM_H) {
+#pragma unroll
+            for (int e = 0; e < NN; e++) h[e] = Hmat[i * NN + e];
+        } else {
+            // find row: largest r with nodeptr[r0 + r] - node_base <= i
+            long lo = 0, hi = nrows;
+            while (hi - lo > 1) {
+                long mid = (lo + hi) >> 1;
+                if (nodeptr[r0 + mid] - node_base <= i) lo = mid; else hi = mid;
+            }
+            const long row = lo;
+            const int k1 = klist ? klist[node_base + i] : (int)(i - (nodeptr[r0 + row] - node_base));
+            const double2* c = C1 + row * (long)M1 * NN;
+#pragma unroll
+            for (int e = 0; e < NN; e++) h[e] = make_double2(0.0, 0.0);
+            for (int m = 0; m < M1; m++) {
+                double2 p = ptab1[(long)m * N + k1];
+#pragma unroll
+                for (int e = 0; e < NN; e++) h[e] = cfma(h[e], c[m * NN + e], p);
+            }
+        }
+        const double wt = wnode ? wnode[node_base + i] : 1.0;
+        if (fkind == 1) {
+            double2 t = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int d = 0; d < NORB; d++) { t.x += h[d * (NORB + 1)].x; t.y += h[d * (NORB + 1)].y; }
+            if (blockIdx.y == 0) { acc[0].x += wt * t.x; acc[0].y += wt * t.y; }
+        } else {
+#pragma unroll
+            for (int wi = 0; wi < SM_WCH; wi++) {
+                if (w0 + wi < nw) {
+                    double2 t = small_resolvent_trace<NORB>(h, z[w0 + wi], sigma ? sigma + (long)(w0 + wi) * NN : nullptr);
+                    if (!(isfinite(t.x) && isfinite(t.y))) *errflag = 1;
+                    acc[wi].x += wt * t.x; acc[wi].y += wt * t.y;
+                }
+            }
+        }
+    }
+    int nvalid = nw - w0 < SM_WCH ? nw - w0 : SM_WCH;
+    if (fkind == 1) nvalid = (blockIdx.y == 0) ? 1 : 0;
+    block_reduce_store<SM_WCH, SM_THREADS>(acc, partial + (long)blockIdx.x * nw + w0, nvalid);
+}
+
+// per-node values (no sum): y[i*nw + w] for the IAI batch path and tests.  One thread per node.
+template <int NORB>
+__global__ void __launch_bounds__(SM_THREADS)
+small_values_kernel(const double2* __restrict__ Hmat, long nnodes, int fkind, int nw, const double2* __restrict__ z,
+                    const double2* __restrict__ sigma, double2* __restrict__ y, int* __restrict__ errflag) {
+    constexpr int NN = NORB * NORB;
+    long i = (long)blockIdx.x * SM_THREADS + threadIdx.x;
+    if (i >= nnodes) return;
+    double2 h[NN];
+#pragma unroll
+    for (int e = 0; e < NN; e++) h[e] = Hmat[i * NN + e];
+    if (fkind == 1) {
+        double2 t = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int d = 0; d < NORB; d++) { t.x += h[d * (NORB + 1)].x; t.y += h[d * (NORB + 1)].y; }
+        for (int w = 0; w < nw; w++) y[i * nw + w] = t;
+        return;
+    }
+    for (int w = 0; w < nw; w++) {
+        double2 t = small_resolvent_trace<NORB>(h, z[w], sigma ? sigma + (long)w * NN : nullptr);
+        if (!(isfinite(t.x) && isfinite(t.y))) *errflag = 1;
+        y[i * nw + w] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3-generic: tr[(z - H(k) - Sigma_w)^-1] by in-place Gauss-Jordan inversion with partial
+// pivoting (LAPACK getrf/getri-equivalent robustness, as Julia's `inv(::Matrix)`), one warp per
+// (k, w) matrix held in shared memory, any norb <= 64.  The CTA stages H(k) once and its warps
+// sweep the frequencies, so H(k) is read from HBM once for all nw (the reference's batchsolve
+// shares the cached grid across parameters, src/interfaces.jl:234-243).
+// mode 0: partial[cta*nw + w] = sum over this CTA's nodes of wnode*trace   (weighted k-sum)
+// mode 1: y[k*nw + w] = trace                                            (per-node values)
+// shared: sH[n*n] | acc[nw] | per warp: A[n*(n+1)] , idx[n]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 warp_gj_trace(double2* __restrict__ A, int* __restrict__ idx, int n, int lda, int lane,
+                                                 bool& singular) {
+    for (int i = lane; i < n; i += 32) idx[i] = i;
+    __syncwarp();
+    for (int p = 0; p < n; p++) {
+        double best = -1.0;
+        int bi = p;
+        for (int i = p + lane; i < n; i += 32) {
+            double2 a = A[i + p * lda];
+            double v = fabs(a.x) + fabs(a.y);
+            if (v > best || !(v == v)) { best = v; bi = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, off);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ob > best || (ob == best && oi < bi) || !(ob == ob)) { best = ob; bi = oi; }
+        }
+        if (!(best > 0.0) || !isfinite(best)) { singular = true; return make_double2(nan(""), nan("")); }
+        if (bi != p) {
+            for (int j = lane; j < n; j += 32) {
+                double2 t = A[p + j * lda]; A[p + j * lda] = A[bi + j * lda]; A[bi + j * lda] = t;
+            }
+            if (lane == 0) { int t = idx[p]; idx[p] = idx[bi]; idx[bi] = t; }
+        }
+        __syncwarp();
+        const double2 rp = crecip(A[p + p * lda]);
+        double2 f0 = make_double2(0.0, 0.0), f1 = f0;
+        if (lane < n) f0 = A[lane + p * lda];
+        if (lane + 32 < n) f1 = A[lane + 32 + p * lda];
+        __syncwarp();
+        if (lane < n) A[lane + p * lda] = make_double2(lane == p ? 1.0 : 0.0, 0.0);
+        if (lane + 32 < n) A[lane + 32 + p * lda] = make_double2(lane + 32 == p ? 1.0 : 0.0, 0.0);
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) A[p + j * lda] = cmul(A[p + j * lda], rp);
+        __syncwarp();
+        for (int j = 0; j < n; j++) {
+            const double2 u = A[p + j * lda];
+            if (lane < n && lane != p) A[lane + j * lda] = cfnma(A[lane + j * lda], f0, u);
+            if (lane + 32 < n && lane + 32 != p) A[lane + 32 + j * lda] = cfnma(A[lane + 32 + j * lda], f1, u);
+        }
+        __syncwarp();
+    }
+    // A now holds (P A0)^-1 ; A0^-1 = B P  => trace = sum_k B[idx[k], k]
+    double tx = 0.0, ty = 0.0;
+    for (int k = lane; k < n; k += 32) {
+        double2 v = A[idx[k] + k * lda];
+        tx += v.x; ty += v.y;
+    }
+    return make_double2(warp_sum(tx), warp_sum(ty));
+}
+
+__global__ void resolvent_gj_kernel(const double2* __restrict__ H, const double* __restrict__ wnode, long nk, int n, int nw,
+                                    const double2* __restrict__ z, const double2* __restrict__ sigma, int kper, int mode,
+                                    double2* __restrict__ outp, int* __restrict__ errflag) {
+    extern __shared__ double2 gj_smem[];
+    const int nn = n * n, lda = n + 1;
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2* sH = gj_smem;
+    double2* sAcc = sH + nn;
+    double2* A = sAcc + nw + (long)warp * (n * lda + (n + 1) / 2 + 1);
+    int* idx = reinterpret_cast<int*>(A + n * lda);
+    for (int w = threadIdx.x; w < nw; w += blockDim.x) sAcc[w] = make_double2(0.0, 0.0);
+    const long k0 = (long)blockIdx.x * kper;
+    const long k1 = k0 + kper < nk ? k0 + kper : nk;
+    for (long k = k0; k < k1; k++) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < nn; e += blockDim.x) sH[e] = H[k * nn + e];
+        __syncthreads();
+        const double wt = wnode ? wnode[k] : 1.0;
+        for (int w = warp; w < nw; w += nwarps) {
+            const double2 zz = z[w];
+            const double2* sg = sigma ? sigma + (long)w * nn : nullptr;
+            for (int e = lane; e < nn; e += 32) {
+                int i = e % n, j = e / n;
+                double2 v = make_double2(-sH[e].x, -sH[e].y);
+                if (sg) { v.x -= sg[e].x; v.y -= sg[e].y; }
+                if (i == j) { v.x += zz.x; v.y += zz.y; }
+                A[i + j * lda] = v;
+            }
+            __syncwarp();
+            bool singular = false;
+            double2 t = warp_gj_trace(A, idx, n, lda, lane, singular);
+            if (lane == 0) {
+                if (singular || !(isfinite(t.x) && isfinite(t.y))) *errflag = 1;
+                if (mode == 0) { sAcc[w].x += wt * t.x; sAcc[w].y += wt * t.y; }
+                else outp[k * nw + w] = t;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (mode == 0)
+        for (int w = threadIdx.x; w < nw; w += blockDim.x) outp[(long)blockIdx.x * nw + w] = sAcc[w];
+}
+
+// tr H(k) weighted partial sums from a materialised H (fkind 1 for norb > 3)
+__global__ void __launch_bounds__(256)
+trace_h_kernel(const double2* __restrict__ H, const double* __restrict__ wnode, long nk, int n, int mode,
+               double2* __restrict__ outp, int nw) {
+    double2 acc[1];
+    acc[0] = make_double2(0.0, 0.0);
+    for (long k = (long)blockIdx.x * 256 + threadIdx.x; k < nk; k += (long)gridDim.x * 256) {
+        double tx = 0.0, ty = 0.0;
+        for (int d = 0; d < n; d++) { double2 v = H[k * n * n + d * (n + 1)]; tx += v.x; ty += v.y; }
+        if (mode == 1) {
+            for (int w = 0; w < nw; w++) outp[k * nw + w] = make_double2(tx, ty);
+        } else {
+            double wt = wnode ? wnode[k] : 1.0;
+            acc[0].x += wt * tx; acc[0].y += wt * ty;
+        }
+    }
+    if (mode == 0) block_reduce_store<1, 256>(acc, outp + (long)blockIdx.x * nw, 1);
+}
+
+}  // namespace abz

@@ -1,0 +1,145 @@
+/*
+ * autobz_cuda.h — C ABI of libautobz_cuda.so, the B200 (sm_100a) implementation of the
+ * data-parallel hot path of AutoBZCore.jl v0.3.8:
+ *   Wannier/Fourier interpolation H(k) = sum_R H_R exp(2 pi i k.R) on k-batches,
+ *   per-k resolvent trace tr[(z - H(k) - Sigma)^-1] / Hermitian eigenvalues,
+ *   and the quadrature-weighted k-sum.
+ *
+ * The reference has no FFI (it is pure Julia); every entry point below names the Julia call
+ * site (file:line under the AutoBZCore.jl tree) whose arithmetic it replaces.  Julia binds these
+ * with `ccall((:abz_..., "libautobz_cuda"), Int32, (...), ...)` (see INTEGRATION.md and
+ * julia/AutoBZCUDA.jl); Python binds them with ctypes (autobzcore.jl_b200/_lib.py).
+ *
+ * Conventions
+ *  - Every function returns int32: 0 = ABZ_OK, negative = ABZ_E_*; text via abz_last_error().
+ *  - No exceptions, no callbacks, no exit().  Caller owns all host buffers; the library owns
+ *    device memory behind opaque 64-bit handles with explicit *_destroy.
+ *  - Complex data is interleaved (re, im) Float64, i.e. Julia ComplexF64 / numpy complex128.
+ *  - coeffs layout  = ComplexF64[n, n, M1, M2, M3] column-major (Julia Array{SMatrix{n,n}} 3-d,
+ *    src/fourier.jl:127-130); H(k) layout = ComplexF64[n, n, nodes] with nodes in the reference's
+ *    iteration order (k1 fastest, src/fourier.jl:132-164, 216-263).
+ *  - A ctx is single-threaded (one CUDA stream); distinct ctx objects are independent.
+ *    Calls are synchronous with respect to returned host data.
+ */
+#ifndef AUTOBZ_CUDA_H
+#define AUTOBZ_CUDA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABZ_OK 0
+#define ABZ_E_INVALID (-1)      /* invalid argument (ArgumentError in the reference) */
+#define ABZ_E_OOM (-2)          /* device allocation failed / budget exceeded */
+#define ABZ_E_CUDA (-3)         /* CUDA runtime error */
+#define ABZ_E_SINGULAR (-4)     /* singular matrix or NaN/Inf in an integrand (QuadGK DomainError) */
+#define ABZ_E_UNSUPPORTED (-5)  /* shape outside the supported range */
+#define ABZ_E_NCCL (-6)         /* NCCL unavailable / failed */
+
+typedef struct abz_ctx abz_ctx;
+typedef uint64_t abz_series_t;  /* Fourier series (H_R coefficients) on the device */
+typedef uint64_t abz_rule_t;    /* quadrature rule: node set + (optionally cached) H(k) */
+typedef uint64_t abz_nest_t;    /* IAI arena: contracted series for nested panels */
+
+/* integrand on H(k):  (user integrand f(FourierValue(k, H(k)), p), src/fourier.jl:120) */
+#define ABZ_F_RESOLVENT_TRACE 0 /* tr[(z I - H - Sigma)^-1]  (aps_example/aps_example.jl:30, docs/src/examples.md:13-20) */
+#define ABZ_F_TRACE_H 1         /* tr H(k)                  (linear test integrand, test/fourier.jl:41) */
+/* eigenvalue integrands g(eig(Hermitian(H(k)))) (src/dos_ggr.jl:19,34) */
+#define ABZ_EIG_SUM 0           /* sum_n e_n */
+#define ABZ_EIG_FERMI_ENERGY 1  /* sum_n e_n f((e_n-mu)/T), params = {mu, T} */
+#define ABZ_EIG_FERMI_COUNT 2   /* sum_n f((e_n-mu)/T) */
+#define ABZ_EIG_GAUSS_DOS 3     /* sum_n exp(-((e_n-w)/s)^2)/(s sqrt(pi)), params = {w, s} */
+
+/* resolvent algorithm selection (abz_ctx_set_option ABZ_OPT_RESOLVENT_ALGO) */
+#define ABZ_OPT_RESOLVENT_ALGO 1   /* 0 auto, 1 generic pivoted Gauss-Jordan, 2 register/DMMA fast path */
+#define ABZ_OPT_MEM_BUDGET_MB 2    /* device workspace budget for streamed chunks (default 4096) */
+#define ABZ_OPT_FUSED_SMALL 3      /* 1 (default): fuse evaluation+resolvent for norb<=4 */
+
+int32_t abz_version(void);
+const char* abz_last_error(const abz_ctx* ctx);  /* ctx may be NULL: last error of abz_ctx_create */
+
+int32_t abz_ctx_create(int32_t device, abz_ctx** out);
+int32_t abz_ctx_destroy(abz_ctx* ctx);
+int32_t abz_ctx_set_option(abz_ctx* ctx, int32_t option, int64_t value);
+/* number of kernels launched by this ctx so far (bench.py "gpu_launches") */
+int64_t abz_ctx_launch_count(const abz_ctx* ctx);
+/* device time of the last matrix-function phase / evaluation phase in ms (CUDA events on the ctx stream) */
+int32_t abz_ctx_last_timings(const abz_ctx* ctx, double* eval_ms, double* matfun_ms);
+
+/* FourierSeries(C; period, offset): replaces FourierSeriesEvaluators.FourierSeries +
+ * workspace_allocate_vec (src/fourier.jl:56-86).  lo[d] = lowest R index per dimension
+ * (index + offset); is_complex = 0 means coeffs are Float64[n,n,M1,M2,M3].
+ * ndim < 3 series are passed with trailing M = 1, lo = 0. */
+int32_t abz_series_create(abz_ctx* ctx, const double* coeffs, int32_t is_complex, int32_t norb,
+                          const int32_t M[3], const int32_t lo[3], const double period[3], abz_series_t* out);
+int32_t abz_series_destroy(abz_ctx* ctx, abz_series_t s);
+
+/* ---- S1: rule construction -------------------------------------------------------------- */
+/* FourierPTR(w, T, Val(3), npt) (src/fourier.jl:166-174): full npt^3 grid, planes k3 in
+ * [k3_lo, k3_hi) (the multi-GPU shard unit; the reference threads over the same loop, :156). */
+int32_t abz_rule_create_full(abz_ctx* ctx, abz_series_t s, int32_t npt, int32_t k3_lo, int32_t k3_hi, abz_rule_t* out);
+/* FourierMonkhorstPack(w, T, Val(3), npt, syms) (src/fourier.jl:265-277): symmetry-reduced nodes
+ * given as AutoSymPTR.symptr_rule's wsym array Int32[npt,npt,npt] (i1 fastest; 0 = not a node,
+ * else orbit size).  Only planes k3 = k3_lo + i*k3_stride < npt are taken (k3_stride = nranks
+ * gives the reference's :scatter distribution, src/fourier.jl:246-255). */
+int32_t abz_rule_create_sym(abz_ctx* ctx, abz_series_t s, int32_t npt, const int32_t* wsym,
+                            int32_t k3_lo, int32_t k3_stride, abz_rule_t* out);
+/* AutoSymPTR.symptr_rule (call site src/fourier.jl:271) on the device: syms = Int32[3,3,nsyms]
+ * row-major per matrix, wsym_out = Int32[npt^3] host buffer; returns the irreducible count. */
+int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t* wsym_out, int64_t* nirr);
+int32_t abz_rule_destroy(abz_ctx* ctx, abz_rule_t r);
+/* length(rule) (src/fourier.jl:177, 284) and norb */
+int32_t abz_rule_info(abz_ctx* ctx, abz_rule_t r, int64_t* nnodes, int32_t* norb, int32_t* npt);
+/* Evaluate and keep H(k) at every node on the device (the reference's cached rule.s / rule.wxs,
+ * src/fourier.jl:127-130, 210-214).  ABZ_E_OOM if it does not fit the budget: then use the sums
+ * below, which stream k3 chunks instead. */
+int32_t abz_rule_materialize(abz_ctx* ctx, abz_rule_t r);
+/* getindex/iterate of the rule (src/fourier.jl:176-202, 279-285) for generic user integrands on
+ * the host: Hk = ComplexF64[n,n,nnodes], kfrac = Float64[3,nnodes], w = Float64[nnodes]; any may be NULL */
+int32_t abz_rule_copy_out(abz_ctx* ctx, abz_rule_t r, double* Hk, double* kfrac, double* w);
+
+/* ---- S2: rule application = quadsum(rule, f, scale) (src/fourier.jl:204-207, 289-292) ---- */
+/* out[2*nw] = scale * sum_i w_i f(H(k_i); z_w, Sigma_w).  fkind = ABZ_F_*.  z = ComplexF64[nw];
+ * sigma = ComplexF64[n,n,nw] or NULL.  Uses the cached H(k) when materialised, otherwise
+ * evaluates chunk by chunk (fused; nothing of size nnodes*n^2 touches HBM for norb<=4). */
+int32_t abz_rule_resolvent_sum(abz_ctx* ctx, abz_rule_t r, int32_t fkind, int32_t nw, const double* z,
+                               const double* sigma, double scale, double* out);
+/* out[0] = scale * sum_i w_i g(eigvals(H(k_i))), kind = ABZ_EIG_* */
+int32_t abz_rule_eig_sum(abz_ctx* ctx, abz_rule_t r, int32_t kind, const double* params, double scale, double* out);
+/* all eigenvalues, Float64[n, nnodes] ascending per node (GGR data pass, src/dos_ggr.jl:14-44) */
+int32_t abz_rule_eigvals(abz_ctx* ctx, abz_rule_t r, double* evals);
+
+/* ---- S3/S4: scattered nodes for IAI panels (src/fourier.jl:432-486) ----------------------- */
+/* workspace_evaluate(w, x) at npts arbitrary points (x NOT scaled by the period, :454):
+ * k = Float64[3,npts]; Hk = ComplexF64[n,n,npts] */
+int32_t abz_points_eval(abz_ctx* ctx, abz_series_t s, int64_t npts, const double* k, double* Hk);
+/* BatchIntegrand f!(y, x, p) for the resolvent (src/batch.jl:4-20): y[w + nw*i] = f(H(k_i); z_w) */
+int32_t abz_points_resolvent(abz_ctx* ctx, abz_series_t s, int64_t npts, const double* k, int32_t fkind,
+                             int32_t nw, const double* z, const double* sigma, double* y);
+/* Nested panels: an arena of contracted series living on the device.
+ * workspace_contract!(f.w, x) (src/fourier.jl:478): slot ids are caller-managed integers in
+ * [0, capacity).  Level 2 slots hold the series contracted at x3; level 1 slots at (x3, x2). */
+int32_t abz_nest_create(abz_ctx* ctx, abz_series_t s, int32_t ndim, int64_t cap2, int64_t cap1, abz_nest_t* out);
+int32_t abz_nest_destroy(abz_ctx* ctx, abz_nest_t nest);
+/* contract the root series at x3[i] into level-2 slot slot2[i], i < n (ndim == 3 only) */
+int32_t abz_nest_contract3(abz_ctx* ctx, abz_nest_t nest, int64_t n, const double* x3, const int64_t* slot2);
+/* contract level-2 slot parent[i] (or the root when ndim == 2) at x2[i] into level-1 slot slot1[i] */
+int32_t abz_nest_contract2(abz_ctx* ctx, abz_nest_t nest, int64_t n, const double* x2, const int64_t* parent,
+                           const int64_t* slot1);
+/* innermost closure (src/fourier.jl:452-456): evaluate level-1 slot slot1[i] (or the root when
+ * ndim == 1) at x1[i] and apply the integrand: y = ComplexF64[npts] */
+int32_t abz_nest_eval(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const double* x1, const int64_t* slot1,
+                      int32_t fkind, const double* z, const double* sigma, double* y);
+
+/* ---- multi-GPU: one small allreduce of partial sums ----------------------- */
+/* NCCL is dlopen'ed at first use (libnccl.so.2).  uid = 128-byte ncclUniqueId from rank 0. */
+int32_t abz_comm_unique_id(void* uid128);
+int32_t abz_comm_init(abz_ctx* ctx, int32_t rank, int32_t nranks, const void* uid128);
+int32_t abz_allreduce_sum(abz_ctx* ctx, double* host_buf, int64_t n);
+int32_t abz_comm_destroy(abz_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
