@@ -1,2 +1,20 @@
-"""autobz_b200 — B200-native hot path of AutoBZCore.jl behind the reference's solve/init API."""
+"""autobz_b200 — B200-native (sm_100a) hot path of AutoBZCore.jl v0.3.8 behind the reference's
+IntegralProblem / init / solve API: Wannier/Fourier interpolation of H(k), per-k resolvent trace and
+Hermitian eigenvalues, weighted k-sums, for PTR / AutoPTR / IAI on SymmetricBZ domains.
+
+All arithmetic on the path runs in libautobz_cuda.so (hand-written CUDA); there is no CPU fallback."""
 from . import _lib, synthetic  # noqa: F401
+from ._lib import AutoBZCudaError, SingularIntegrandError  # noqa: F401
+from .algorithms import (IAI, PTR, AutoPTR, AutoSymPTRJL, AuxQuadGKJL, EvalCounter, MonkhorstPack,  # noqa: F401
+                         NestedQuad)
+from .backend import DeviceBackend, default_context  # noqa: F401
+from .bz import (FBZ, CubicLimits, CubicSymIBZ, InversionSymIBZ, SymmetricBZ, TetrahedralLimits,  # noqa: F401
+                 cube_automorphisms, load_bz, nsyms)
+from .fourier import (AffineTraceIntegrand, DOSIntegrand, EigenIntegrand, FourierIntegrand, FourierSeries,  # noqa: F401
+                      FourierValue, TrGlocIntegrand, dos_integrand, gloc_trace_integrand)
+from .interfaces import (Basis, IntegralProblem, IntegralSolution, IntegralSolver, Shard, batchsolve, init,  # noqa: F401
+                         solve, solve_, torch_allreduce)
+from .wannier import read_w90_hrdat, read_wout_lattice  # noqa: F401
+
+# v0.4+ names of the reference API (BASELINE.json north_star) as aliases
+FourierIntegralFunction = FourierIntegrand

@@ -20,7 +20,7 @@ OPT_RESOLVENT_ALGO, OPT_MEM_BUDGET_MB, OPT_FUSED_SMALL = 1, 2, 3
 # every symbol include/autobz_cuda.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "abz_version", "abz_last_error", "abz_ctx_create", "abz_ctx_destroy", "abz_ctx_set_option", "abz_ctx_launch_count",
-    "abz_ctx_last_timings", "abz_series_create", "abz_series_destroy", "abz_rule_create_full", "abz_rule_create_sym",
+    "abz_ctx_last_timings", "abz_series_create", "abz_series_destroy", "abz_rule_create_full", "abz_rule_create_sym", "abz_rule_create_nodes",
     "abz_symptr_rule", "abz_rule_destroy", "abz_rule_info", "abz_rule_materialize", "abz_rule_copy_out",
     "abz_rule_resolvent_sum", "abz_rule_eig_sum", "abz_rule_eigvals", "abz_points_eval", "abz_points_resolvent",
     "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval",
@@ -66,6 +66,7 @@ def load():
     lib.abz_series_destroy.argtypes = [C.c_void_p, C.c_uint64]
     lib.abz_rule_create_full.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
     lib.abz_rule_create_sym.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_i32p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
+    lib.abz_rule_create_nodes.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int64, c_i32p, c_dp, C.POINTER(C.c_uint64)]
     lib.abz_symptr_rule.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i64p]
     lib.abz_rule_destroy.argtypes = [C.c_void_p, C.c_uint64]
     lib.abz_rule_info.argtypes = [C.c_void_p, C.c_uint64, c_i64p, c_i32p, c_i32p]
@@ -226,10 +227,15 @@ class DeviceSeries:
 class DeviceRule:
     """A quadrature rule on the device: FourierPTR (full grid) or FourierMonkhorstPack (wsym given)."""
 
-    def __init__(self, ctx, series, npt, wsym=None, k3_lo=0, k3_hi=None, k3_stride=1):
+    def __init__(self, ctx, series, npt, wsym=None, k3_lo=0, k3_hi=None, k3_stride=1, nodes=None, weights=None):
         self.ctx, self.series, self.npt = ctx, series, int(npt)
         h = C.c_uint64()
-        if wsym is None:
+        if nodes is not None:
+            idx = np.ascontiguousarray(np.asarray(nodes, dtype=np.int32).reshape(-1, 3))
+            wv = None if weights is None else np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+            ctx.check(ctx.lib.abz_rule_create_nodes(ctx.h, series.h, self.npt, idx.shape[0], idx.ctypes.data_as(c_i32p), _dp(wv),
+                                                    C.byref(h)))
+        elif wsym is None:
             k3_hi = self.npt if k3_hi is None else k3_hi
             ctx.check(ctx.lib.abz_rule_create_full(ctx.h, series.h, self.npt, int(k3_lo), int(k3_hi), C.byref(h)))
         else:

@@ -1,0 +1,164 @@
+"""Brillouin-zone domain, symmetries and iterated limits — host-side mirror of the reference's
+src/brillouin.jl:1-307 (SymmetricBZ, load_bz for FBZ / InversionSymIBZ / CubicSymIBZ) and of the
+IteratedIntegration.jl limit types it uses (CubicLimits, TetrahedralLimits).  Pure control plane:
+nothing here is on the data path."""
+import itertools
+
+import numpy as np
+
+
+class CubicLimits:
+    """IteratedIntegration.CubicLimits(a, b): x_d in [a_d, b_d]."""
+
+    def __init__(self, a, b):
+        self.a = tuple(float(x) for x in np.atleast_1d(a))
+        self.b = tuple(float(x) for x in np.atleast_1d(b))
+        if len(self.a) != len(self.b):
+            raise ValueError("endpoints must have the same length")
+
+    @property
+    def ndim(self):
+        return len(self.a)
+
+    def segments(self):
+        """limit_iterate(lims): segments of the outermost (last) variable."""
+        return (self.a[-1], self.b[-1])
+
+    def fix(self, x):
+        """fixandeliminate(lims, x)"""
+        return CubicLimits(self.a[:-1], self.b[:-1])
+
+    def interior_point(self):
+        return tuple((a + b) / 2 for a, b in zip(self.a, self.b))
+
+
+class TetrahedralLimits:
+    """IteratedIntegration.TetrahedralLimits(a): 0 <= x_d <= a_d s, then s <- x_d / a_d
+    (used by load_bz(CubicSymIBZ), src/brillouin.jl:301-307)."""
+
+    def __init__(self, a, s=1.0):
+        self.a = tuple(float(x) for x in np.atleast_1d(a))
+        self.s = float(s)
+
+    @property
+    def ndim(self):
+        return len(self.a)
+
+    def segments(self):
+        return (0.0, self.a[-1] * self.s)
+
+    def fix(self, x):
+        return TetrahedralLimits(self.a[:-1], float(x) / self.a[-1])
+
+    def interior_point(self):
+        pt, lims = [], self
+        while lims.ndim > 0:
+            a, b = lims.segments()
+            x = (a + b) / 2
+            pt.append(x)
+            lims = lims.fix(x)
+        return tuple(reversed(pt))
+
+
+class SymmetricBZ:
+    """SymmetricBZ(A, B, lims, syms) (src/brillouin.jl:33-41).  A, B hold the real / reciprocal basis
+    vectors in their columns; lims and syms are in the lattice basis (fractional coordinates)."""
+
+    def __init__(self, A, B, lims, syms):
+        self.A = np.array(A, dtype=float)
+        self.B = np.array(B, dtype=float)
+        self.lims = lims
+        self.syms = None if syms is None else [np.array(S) for S in syms]
+
+    @property
+    def ndim(self):
+        return self.A.shape[0]
+
+    @property
+    def nsyms(self):
+        return 1 if self.syms is None else len(self.syms)
+
+    @property
+    def is_full(self):
+        return self.syms is None
+
+    def __repr__(self):
+        return f"{self.ndim}-dimensional Brillouin zone with {'trivial' if self.is_full else self.nsyms} symmetries"
+
+
+def nsyms(bz):
+    return bz.nsyms
+
+
+def canonical_reciprocal_basis(A):
+    """B = A'^-1 2 pi (src/brillouin.jl:9)"""
+    A = np.array(A, dtype=float)
+    return np.linalg.solve(A.T, 2 * np.pi * np.eye(A.shape[0]))
+
+
+class FBZ:
+    def __init__(self, ndim=None):
+        self.ndim = ndim
+
+
+class InversionSymIBZ:
+    def __init__(self, ndim=None):
+        self.ndim = ndim
+
+
+class CubicSymIBZ:
+    def __init__(self, ndim=None):
+        self.ndim = ndim
+
+
+def sign_flip_matrices(d):
+    return [np.diag(np.array(s, dtype=np.int64)) for s in itertools.product((1, -1), repeat=d)]
+
+
+def permutation_matrices(d):
+    out = []
+    for p in itertools.permutations(range(d)):
+        m = np.zeros((d, d), dtype=np.int64)
+        for i in range(d):
+            m[i, p[i]] = 1
+        out.append(m)
+    return out
+
+
+def cube_automorphisms(d):
+    """S*P for sign flips S and permutations P (src/brillouin.jl:286): 2^d d! matrices incl. identity."""
+    return [S @ P for P in permutation_matrices(d) for S in sign_flip_matrices(d)]
+
+
+def load_bz(bz, A=None, B=None, atol=None):
+    """load_bz(bz::AbstractBZ, A, [B]) (src/brillouin.jl:179-307)."""
+    if A is None:
+        if bz.ndim is None:
+            raise ValueError("BZ dimension must be integer")
+        A = np.eye(bz.ndim)
+    A = np.array(A, dtype=float)
+    if A.ndim != 2 or A.shape[0] != A.shape[1]:
+        raise ValueError("A must be square")
+    d = A.shape[0]
+    if bz.ndim is not None and bz.ndim != d:
+        raise ValueError("dimension mismatch between the BZ type and the lattice")
+    B = canonical_reciprocal_basis(A) if B is None else np.array(B, dtype=float)
+    if B.shape != A.shape:
+        raise ValueError(f"Bravais lattices {A} and {B} must have the same shape")
+    tol = np.sqrt(np.finfo(float).eps) if atol is None else atol
+    if np.linalg.norm(A.T @ B - 2 * np.pi * np.eye(d)) >= tol:
+        raise ValueError(f"Real and reciprocal Bravais lattice bases non-orthogonal to tolerance {tol}")
+    if isinstance(bz, FBZ):
+        return SymmetricBZ(A, B, CubicLimits(np.zeros(d), np.ones(d)), None)
+    ortho = np.allclose(A.T @ A, np.diag(np.diag(A.T @ A)))
+    if isinstance(bz, InversionSymIBZ):
+        if not ortho:
+            import warnings
+            warnings.warn("Non-orthogonal lattice vectors detected with InversionSymIBZ. Unexpected behavior may occur")
+        return SymmetricBZ(A, B, CubicLimits(np.zeros(d), np.full(d, 0.5)), sign_flip_matrices(d))
+    if isinstance(bz, CubicSymIBZ):
+        if not ortho:
+            import warnings
+            warnings.warn("Non-orthogonal lattice vectors detected with CubicSymIBZ. Unexpected behavior may occur")
+        return SymmetricBZ(A, B, TetrahedralLimits(np.full(d, 0.5)), cube_automorphisms(d))
+    raise TypeError("unsupported BZ type (the polyhedral IBZ of SymmetryReduceBZ.jl is out of scope)")

@@ -584,6 +584,47 @@ int32_t abz_rule_create_sym(abz_ctx* ctx, abz_series_t sid, int32_t npt, const i
     return ABZ_OK;
 }
 
+int32_t abz_rule_create_nodes(abz_ctx* ctx, abz_series_t sid, int32_t npt, int64_t nnodes, const int32_t* idx,
+                              const double* w, abz_rule_t* out) {
+    if (!ctx) return ABZ_E_INVALID;
+    Series* s = get_series(ctx, sid);
+    if (!s) return fail(ctx, ABZ_E_INVALID, "unknown series handle");
+    if (!out || npt < 1 || nnodes < 0 || (nnodes > 0 && !idx)) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    cudaSetDevice(ctx->device);
+    auto r = std::make_unique<Rule>();
+    r->series_id = sid; r->s = s; r->N = npt; r->full = false;
+    r->h_plane_rowptr.push_back(0);
+    r->h_row_nodeptr.push_back(0);
+    long p3 = -1, p2 = -1, p1 = -1;
+    for (int64_t i = 0; i < nnodes; i++) {
+        long i1 = idx[3 * i], i2 = idx[3 * i + 1], i3 = idx[3 * i + 2];
+        if (i1 < 0 || i1 >= npt || i2 < 0 || i2 >= npt || i3 < 0 || i3 >= npt) return fail(ctx, ABZ_E_INVALID, "node index out of range");
+        bool newplane = (i3 != p3), newrow = newplane || (i2 != p2);
+        if (i3 < p3 || (!newplane && i2 < p2) || (!newrow && i1 <= p1))
+            return fail(ctx, ABZ_E_INVALID, "nodes must be sorted by (k3, k2, k1) without duplicates");
+        if (newrow && i > 0) r->h_row_nodeptr.push_back((long)r->h_node_k1.size());
+        if (newplane && i > 0) r->h_plane_rowptr.push_back((long)r->h_row_k2.size());
+        if (newplane) r->h_plane_k3.push_back((int)i3);
+        if (newrow) r->h_row_k2.push_back((int)i2);
+        r->h_node_k1.push_back((int)i1);
+        r->h_node_w.push_back(w ? w[i] : 1.0);
+        p3 = i3; p2 = i2; p1 = i1;
+    }
+    if (nnodes > 0) {
+        r->h_row_nodeptr.push_back((long)r->h_node_k1.size());
+        r->h_plane_rowptr.push_back((long)r->h_row_k2.size());
+    }
+    r->np3 = (long)r->h_plane_k3.size();
+    r->nrows = (long)r->h_row_k2.size();
+    r->nnz = (long)r->h_node_k1.size();
+    int rc = finish_rule(ctx, r.get());
+    if (rc) return rc;
+    uint64_t id = ctx->next_id++;
+    ctx->rules[id] = std::move(r);
+    *out = id;
+    return ABZ_OK;
+}
+
 int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t* wsym_out, int64_t* nirr) {
     if (!ctx) return ABZ_E_INVALID;
     if (npt < 1 || nsyms < 1 || nsyms > 1024 || !syms || !wsym_out) return fail(ctx, ABZ_E_INVALID, "invalid arguments");

@@ -1,0 +1,277 @@
+"""IAI host engine: nested adaptive Gauss-Kronrod (7,15) with the reference's control flow, batched
+level-synchronously for the device.
+
+Restates do_solve(::FourierIntegrand, lims, ::NestedQuad) + init_nest (src/fourier.jl:432-510) on top of
+QuadGK.jl's do_quadgk / adapt / refine / evalrule and DataStructures.jl's binary heap (the algorithms
+behind IteratedIntegration.auxquadgk, call site src/algorithms.jl:236-237).  Every 1-D adaptive
+integral is an independent state machine whose trajectory depends only on its own integrand values
+and tolerance, so evaluating all live panels of all live integrals in one device batch per round
+leaves every accept/refine decision — and hence EvalCounter's numevals (src/fourier.jl:516-523) —
+unchanged with respect to the sequential recursion."""
+import numpy as np
+
+# QUADPACK qk15 abscissae (x <= 0 half, as QuadGK.kronrod(7) orders them), Kronrod and Gauss weights
+GK_X = np.array([-0.991455371120812639206854697526329, -0.949107912342758524526189684047851,
+                 -0.864864423359769072789712788640926, -0.741531185599394439863864773280788,
+                 -0.586087235467691130294144838258730, -0.405845151377397166906606412076961,
+                 -0.207784955007898467600689403773245, 0.0])
+GK_W = np.array([0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
+                 0.104790010322250183839876322541518, 0.140653259715525918745189590510238,
+                 0.169004726639267902826583426598550, 0.190350578064785409913256402421014,
+                 0.204432940075298892414161999234649, 0.209482141084727828012999174891714])
+GK_GW = np.array([0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
+                  0.381830050505118944950369775488975, 0.417959183673469387755102040816327])
+
+# offsets (1 + x) and (1 - x) in QuadGK.evalrule's evaluation order:
+# (x2+,x2-),(x1+,x1-),(x4+,x4-),(x3+,x3-),(x6+,x6-),(x5+,x5-), centre, (x7+,x7-)
+_ORDER = [1, 0, 3, 2, 5, 4]
+_OFF = []
+for _i in _ORDER:
+    _OFF += [1.0 + GK_X[_i], 1.0 - GK_X[_i]]
+_OFF += [1.0, 1.0 + GK_X[6], 1.0 - GK_X[6]]
+_OFF = np.array(_OFF)
+# note: a + (1 + x[8]) s with x[8] = 0 equals a + s exactly
+
+
+def gk15_nodes(a, b):
+    """nodes of evalrule on [a, b]; a, b scalars or arrays -> (..., 15)"""
+    a = np.asarray(a, dtype=np.float64)
+    s = 0.5 * (np.asarray(b, dtype=np.float64) - a)
+    return a[..., None] + _OFF * s[..., None]
+
+
+def gk15_combine(a, b, f):
+    """QuadGK.evalrule: f (..., 15) values in gk15_nodes order -> (I, E), same operation order."""
+    s = 0.5 * (np.asarray(b, dtype=np.float64) - np.asarray(a, dtype=np.float64))
+    fg = f[..., 0] + f[..., 1]
+    fk = f[..., 2] + f[..., 3]
+    Ig = fg * GK_GW[0]
+    Ik = fg * GK_W[1] + fk * GK_W[0]
+    fg = f[..., 4] + f[..., 5]
+    fk = f[..., 6] + f[..., 7]
+    Ig = Ig + fg * GK_GW[1]
+    Ik = Ik + (fg * GK_W[3] + fk * GK_W[2])
+    fg = f[..., 8] + f[..., 9]
+    fk = f[..., 10] + f[..., 11]
+    Ig = Ig + fg * GK_GW[2]
+    Ik = Ik + (fg * GK_W[5] + fk * GK_W[4])
+    f0 = f[..., 12]
+    Ig = Ig + f0 * GK_GW[3]
+    Ik = Ik + (f0 * GK_W[7] + (f[..., 13] + f[..., 14]) * GK_W[6])
+    Iks = Ik * s
+    Igs = Ig * s
+    return Iks, np.abs(Iks - Igs)
+
+
+# ---- DataStructures.jl binary heap with Base.Reverse on Segment.E (segments are (E, a, b, I)) ---------
+def _lt_rev(x, y):
+    return y[0] < x[0]
+
+
+def _percolate_down(xs, i, x, n):
+    while True:
+        left = 2 * i
+        if left > n:
+            break
+        r = left + 1
+        j = left if (r > n or _lt_rev(xs[left - 1], xs[r - 1])) else r
+        if not _lt_rev(xs[j - 1], x):
+            break
+        xs[i - 1] = xs[j - 1]
+        i = j
+    xs[i - 1] = x
+
+
+def _percolate_up(xs, i, x):
+    while True:
+        j = i // 2
+        if j < 1:
+            break
+        if not _lt_rev(x, xs[j - 1]):
+            break
+        xs[i - 1] = xs[j - 1]
+        i = j
+    xs[i - 1] = x
+
+
+def heappop(xs):
+    x = xs[0]
+    y = xs.pop()
+    if xs:
+        _percolate_down(xs, 1, y, len(xs))
+    return x
+
+
+def heappush(xs, x):
+    xs.append(x)
+    _percolate_up(xs, len(xs), x)
+
+
+class DomainError(FloatingPointError):
+    """QuadGK throws DomainError when the integrand produces NaN/Inf."""
+
+
+class _Pend:
+    __slots__ = ("a", "b", "vals", "remaining", "tag")
+
+    def __init__(self, a, b, tag, dtype):
+        self.a, self.b, self.tag = a, b, tag
+        self.vals = np.empty(15, dtype=dtype)
+        self.remaining = 15
+
+
+class _Integral:
+    __slots__ = ("level", "lims", "atol", "slot", "parent", "heap", "I", "E", "numevals", "popped", "s1", "s2", "state")
+
+    def __init__(self, level, lims, atol, slot, parent):
+        self.level, self.lims, self.atol, self.slot, self.parent = level, lims, atol, slot, parent
+        self.heap, self.numevals, self.state = [], 0, 0
+        self.s1 = self.s2 = self.popped = None
+
+
+class NestedGK:
+    """One nested adaptive integration of a Fourier integrand over iterated limits.
+
+    nest: device arena (backend.make_nest) exposing contract3 / contract2 / eval
+    point_values(y) -> integrand values from the device's per-node output (e.g. DOS = -Im tr / pi)
+    """
+
+    def __init__(self, nest, ndim, lims, fkind, z, sigma, post, dtype, atol, rtol, maxevals, cap2=64, cap1=2048):
+        self.nest, self.ndim, self.lims = nest, ndim, lims
+        self.fkind, self.z, self.sigma, self.post, self.dtype = fkind, z, sigma, post, dtype
+        self.atol, self.rtol, self.maxevals = atol, rtol, maxevals
+        self.free2 = list(range(cap2 - 1, -1, -1))
+        self.free1 = list(range(cap1 - 1, -1, -1))
+        self.q_eval, self.q_c3, self.q_c2 = [], [], []
+        self.numevals = 0
+        self.rounds = 0
+        self.root_result = None
+
+    # ---- slots
+    def _alloc(self, level):
+        free = self.free2 if level == 2 else self.free1
+        if not free:
+            raise MemoryError("IAI arena exhausted (too many live panels)")
+        return free.pop()
+
+    def _free(self, level, slot):
+        (self.free2 if level == 2 else self.free1).append(slot)
+
+    # ---- state machine
+    def _start_segment(self, q, a, b, tag):
+        pend = _Pend(a, b, tag, self.dtype)
+        if q.level == 0:
+            self.q_eval.append((q, pend))
+            return
+        xs = gk15_nodes(a, b)
+        for i in range(15):
+            x = float(xs[i])
+            clims = q.lims.fix(x)
+            ca, cb = clims.segments()
+            length = cb - ca
+            slot = self._alloc(q.level)
+            if q.level == 2:
+                self.q_c3.append((x, slot))
+            else:
+                self.q_c2.append((x, q.slot, slot))
+            child = _Integral(q.level - 1, clims, q.atol / length if self.atol_given else q.atol, slot, (q, pend, i))
+            self._start_segment(child, ca, cb, 0)
+
+    def _finish(self, q):
+        heap = q.heap
+        Iv, Ev = heap[0][3], heap[0][0]
+        for s in heap[1:]:
+            Iv = Iv + s[3]
+            Ev = Ev + s[0]
+        if q.parent is None:
+            self.root_result = (Iv, Ev)
+            return
+        pq, pend, i = q.parent
+        self._free(pq.level, q.slot)
+        pend.vals[i] = Iv
+        pend.remaining -= 1
+        if pend.remaining == 0:
+            Is, Es = gk15_combine(pend.a, pend.b, pend.vals)
+            self._segment_done(pq, pend, Is[()], float(Es))
+
+    def _refine(self, q):
+        s = heappop(q.heap)
+        q.popped = s
+        mid = (s[1] + s[2]) / 2
+        q.s1 = q.s2 = None
+        q.state = 1
+        self._start_segment(q, s[1], mid, 1)
+        self._start_segment(q, mid, s[2], 2)
+
+    def _segment_done(self, q, pend, Is, Es):
+        if not np.isfinite(Es):
+            raise DomainError(f"integrand produced {Es} in the interval ({pend.a}, {pend.b})")
+        seg = (Es, pend.a, pend.b, Is)
+        if pend.tag == 0:
+            q.heap = [seg]
+            q.I, q.E, q.numevals = Is, Es, 15
+            if q.numevals >= self.maxevals or q.E <= q.atol or q.E <= self.rtol * abs(q.I):
+                self._finish(q)
+            else:
+                self._refine(q)
+            return
+        if pend.tag == 1:
+            q.s1 = seg
+        else:
+            q.s2 = seg
+        if q.s1 is None or q.s2 is None:
+            return
+        s = q.popped
+        q.I = (q.I - s[3]) + q.s1[3] + q.s2[3]
+        q.E = (q.E - s[0]) + q.s1[0] + q.s2[0]
+        q.numevals += 30
+        heappush(q.heap, q.s1)
+        heappush(q.heap, q.s2)
+        if q.E > q.atol and q.E > self.rtol * abs(q.I) and q.numevals < self.maxevals:
+            self._refine(q)
+        else:
+            self._finish(q)
+
+    # ---- driver
+    def run(self):
+        self.atol_given = self.atol is not None
+        atol = self.atol if self.atol_given else 0.0
+        rtol = self.rtol
+        if rtol is None:
+            rtol = np.sqrt(np.finfo(float).eps) if atol == 0 else 0.0
+        self.rtol = rtol
+        a, b = self.lims.segments()
+        root = _Integral(self.ndim - 1, self.lims, atol, None, None)
+        self._start_segment(root, a, b, 0)
+        while self.root_result is None:
+            self.rounds += 1
+            if self.q_c3:
+                xs = np.array([t[0] for t in self.q_c3])
+                sl = np.array([t[1] for t in self.q_c3], dtype=np.int64)
+                self.q_c3 = []
+                self.nest.contract3(xs, sl)
+            if self.q_c2:
+                xs = np.array([t[0] for t in self.q_c2])
+                par = None if self.ndim == 2 else np.array([t[1] for t in self.q_c2], dtype=np.int64)
+                sl = np.array([t[2] for t in self.q_c2], dtype=np.int64)
+                self.q_c2 = []
+                self.nest.contract2(xs, par, sl)
+            batch = self.q_eval
+            self.q_eval = []
+            if not batch:
+                raise RuntimeError("IAI engine stalled")
+            nseg = len(batch)
+            aa = np.array([p.a for _, p in batch])
+            bb = np.array([p.b for _, p in batch])
+            xs = gk15_nodes(aa, bb)
+            slots = None
+            if self.ndim >= 2:
+                slots = np.repeat(np.array([q.slot for q, _ in batch], dtype=np.int64), 15)
+            y = self.nest.eval(xs.reshape(-1), slots, self.z, self.sigma, self.fkind)
+            self.numevals += 15 * nseg
+            vals = self.post(y).reshape(nseg, 15)
+            Is, Es = gk15_combine(aa, bb, vals)
+            for i in range(nseg):
+                q, pend = batch[i]
+                self._segment_done(q, pend, Is[i], float(Es[i]))
+        return self.root_result[0], self.root_result[1], self.numevals

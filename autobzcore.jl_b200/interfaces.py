@@ -1,0 +1,406 @@
+"""IntegralProblem / init / solve / IntegralSolver / batchsolve — host-side mirror of
+src/interfaces.jl:34-243 and of the FourierIntegrand dispatch in src/fourier.jl:323-530 and
+src/brillouin.jl:321-499, with the arithmetic handed to libautobz_cuda.so through backend.py.
+
+Control flow kept on the host exactly as in the reference: tolerance rescaling by j = |det B| and
+nsyms (src/brillouin.jl:337-355, 429-444), symmetrisation of scalar results (TrivialRep, :98-107),
+AutoPTR's additive grid refinement and convergence test (AutoSymPTR.autosymptr, call site
+src/algorithms.jl:418-432), IAI's nested GK panels (iai.py)."""
+import time
+
+import numpy as np
+
+from . import _lib
+from .algorithms import (IAI, PTR, AutoPTR, AutoSymPTRJL, AuxQuadGKJL, EvalCounter, MonkhorstPack, NestedQuad,
+                         monkhorst_pack_schedule)
+from .backend import DeviceBackend
+from .bz import CubicLimits, SymmetricBZ, TetrahedralLimits
+from .fourier import FourierIntegrand, FourierValue
+from .iai import NestedGK
+
+
+class Basis:
+    """AutoSymPTR.Basis(B): the PTR domain (canonical_ptr_basis = identity, src/brillouin.jl:10)."""
+
+    def __init__(self, B):
+        self.B = np.array(B, dtype=float)
+
+    @property
+    def ndim(self):
+        return self.B.shape[0]
+
+
+class IntegralSolution:
+    """IntegralSolution{u, resid, retcode, numevals} (src/interfaces.jl:120-126); numevals = -1 if undefined."""
+
+    def __init__(self, u, resid, retcode=True, numevals=-1):
+        self.u, self.resid, self.retcode, self.numevals = u, resid, retcode, numevals
+
+    def __repr__(self):
+        return f"IntegralSolution(u={self.u!r}, resid={self.resid!r}, retcode={self.retcode}, numevals={self.numevals})"
+
+
+class IntegralProblem:
+    """IntegralProblem(f, domain, p=NullParameters()) (src/interfaces.jl:34-48)"""
+
+    def __init__(self, f, dom, p=None):
+        self.f, self.dom, self.p = f, dom, p
+
+
+class Shard:
+    """This rank's share of a multi-GPU solve: k3 planes are partitioned across ranks (contiguous blocks
+    for full grids, round-robin for symmetry-reduced ones, as the reference's thread chunks,
+    src/fourier.jl:156, 246-255) and partial sums meet in ONE small allreduce per rule evaluation."""
+
+    def __init__(self, rank=0, nranks=1, allreduce=None):
+        self.rank, self.nranks = int(rank), int(nranks)
+        self._allreduce = allreduce
+
+    def allreduce(self, arr):
+        if self.nranks == 1:
+            return arr
+        if self._allreduce is None:
+            raise RuntimeError("Shard with nranks > 1 needs an allreduce function")
+        return self._allreduce(arr)
+
+
+def torch_allreduce(device=None):
+    """allreduce over torch.distributed (NCCL over NVLink on GPU ranks, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    def f(arr):
+        a = np.ascontiguousarray(arr)
+        t = torch.from_numpy(a.view(np.float64).reshape(-1).copy())
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy().view(a.dtype).reshape(a.shape)
+
+    return f
+
+
+_CHECK = ("abstol", "reltol", "maxiters")
+
+
+def checkkwargs(kws):
+    """src/interfaces.jl:64-69"""
+    for k in kws:
+        if k not in _CHECK:
+            raise ValueError(f"keyword {k} unrecognized")
+
+
+def _norm(x):
+    return float(np.linalg.norm(np.atleast_1d(x)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameters (MixedParameters, src/parameters.jl:11-35): ((args...), {kws...})
+def _params(p):
+    if p is None:
+        return ((), {})
+    if isinstance(p, tuple) and len(p) == 2 and isinstance(p[1], dict):
+        return p
+    if isinstance(p, dict):
+        return ((), p)
+    if isinstance(p, (tuple, list)):
+        return (tuple(p), {})
+    return ((p,), {})
+
+
+class _BoundIntegrand:
+    """A FourierIntegrand with all parameters known, reduced to what the device needs."""
+
+    def __init__(self, f, plist):
+        self.f = f
+        self.native = f.native
+        self.plist = [_params(p) for p in plist]
+        if self.native:
+            self.bound = [f.f.bind(*f.merged(p)) for p in self.plist]
+            self.is_eig = f.f.is_eig
+            self.fkind = f.f.fkind
+
+    def rule_sums(self, rule):
+        """sum_i w_i f(x_i) over the rule's local nodes for every parameter -> list of values"""
+        f = self.f
+        if not self.native:
+            H, k, w = rule.copy_out()
+            Hm = np.moveaxis(H, 2, 0)
+            out = []
+            for p in self.plist:
+                acc = 0
+                for i in range(Hm.shape[0]):
+                    s = Hm[i] if f.s.norb > 1 else Hm[i][0, 0]
+                    acc = acc + w[i] * f(FourierValue(k[i, :f.s.ndim], s), p)
+                out.append(acc)
+            return out
+        if self.is_eig:
+            return [rule.eig_sum(f.f.kind, b) for b in self.bound]
+        if self.fkind == _lib.F_TRACE_H:
+            t = rule.resolvent_sum(None, None, _lib.F_TRACE_H)[0]
+            return [("affine", t, b) for b in self.bound]
+        zs = np.array([b[0] for b in self.bound], dtype=np.complex128)
+        sig = None
+        if any(b[1] is not None for b in self.bound):
+            n = f.s.norb
+            sig = np.zeros((n, n, len(self.bound)), dtype=np.complex128, order="F")
+            for i, b in enumerate(self.bound):
+                if b[1] is not None:
+                    sig[:, :, i] = np.asarray(b[1], dtype=np.complex128).reshape(n, n)
+        y = rule.resolvent_sum(zs, sig, _lib.F_RESOLVENT_TRACE)
+        return list(y)
+
+
+def _rule_apply(rule, bf, shard, ndim):
+    """(rule)(f, B, buffer) = quadsum(rule, f, vol/(npt^d nsyms)) (src/fourier.jl:204-207, 289-292), then
+    SymmetricRule's symmetrize (TrivialRep: x nsyms, src/brillouin.jl:107,127-130) — i.e. sum_i w_i f_i / npt^d
+    for scalar integrands.  Multi-rank: local partial sums + one allreduce."""
+    sums = bf.rule_sums(rule)
+    npt_d = float(rule.npt) ** ndim
+    if bf.native and not bf.is_eig and bf.fkind == _lib.F_TRACE_H:
+        # affine integrand a*tr(H)+b: sum_i w_i (a t_i + b) = a * sum_i w_i t_i + b * npt^d (sum w_i = npt^d)
+        t = np.array([sums[0][1]], dtype=np.complex128)
+        t = shard.allreduce(t)[0]
+        vals = [bd[0] * t / npt_d + bd[1] for (_, _, bd) in sums]
+        return vals
+    arr = np.array(sums)
+    if np.iscomplexobj(arr):
+        arr = arr.astype(np.complex128)
+    else:
+        arr = arr.astype(np.float64)
+    arr = shard.allreduce(arr)
+    vals = arr / npt_d
+    if bf.native and not bf.is_eig:
+        vals = bf.f.f.post(vals, None)
+    return list(vals)
+
+
+# ---------------------------------------------------------------------------------------------------
+class IntegralCache:
+    """IntegralCache (src/interfaces.jl:50-57): problem + algorithm + cacheval + kwargs, reusable across parameters."""
+
+    def __init__(self, f, dom, p, alg, kwargs, backend, shard):
+        self.f, self.dom, self.p, self.alg, self.kwargs = f, dom, p, alg, kwargs
+        self.backend, self.shard = backend, shard
+        self.cacheval = {}
+
+
+def init(prob, alg, backend=None, shard=None, **kwargs):
+    """init(prob, alg; kwargs...) (src/interfaces.jl:78-82): build the cache (rules / arena) once."""
+    checkkwargs(kwargs)
+    if not isinstance(prob.f, FourierIntegrand):
+        raise TypeError("autobz_b200 implements the FourierIntegrand hot path only (SURVEY.md §8)")
+    backend = backend if backend is not None else DeviceBackend()
+    shard = shard if shard is not None else Shard()
+    cache = IntegralCache(prob.f, prob.dom, prob.p, alg, kwargs, backend, shard)
+    _init_cacheval(cache)
+    return cache
+
+
+def solve_(cache, plist=None):
+    """solve!(cache) (src/interfaces.jl:116-118).  plist: several parameter sets solved against the same
+    cached rule in one device pass (the batchsolve fast path); returns one IntegralSolution per entry."""
+    single = plist is None
+    ps = [cache.p] if single else list(plist)
+    sols = _do_solve(cache, ps)
+    return sols[0] if single else sols
+
+
+def solve(prob, alg, backend=None, shard=None, **kwargs):
+    """solve(prob, alg; kwargs...) = solve!(init(prob, alg; kwargs...)) (src/interfaces.jl:106-109)"""
+    return solve_(init(prob, alg, backend=backend, shard=shard, **kwargs))
+
+
+# ---------------------------------------------------------------------------------------------------
+def _unwrap(alg):
+    counter = isinstance(alg, EvalCounter)
+    return (alg.alg if counter else alg), counter
+
+
+def _standard(dom, alg):
+    """bz_to_standard (src/brillouin.jl:375-377, 392-394, 418-420): (bz, unitless domain, standard algorithm, j, nsyms)"""
+    if isinstance(dom, SymmetricBZ):
+        j = abs(np.linalg.det(dom.B))
+        if isinstance(alg, IAI):
+            return dom.lims, NestedQuad(*alg.algs), j, dom.nsyms, dom.ndim
+        if isinstance(alg, PTR):
+            return Basis(np.eye(dom.ndim)), MonkhorstPack(npt=alg.npt, syms=dom.syms, nthreads=alg.nthreads), j, dom.nsyms, dom.ndim
+        if isinstance(alg, AutoPTR):
+            return (Basis(np.eye(dom.ndim)),
+                    AutoSymPTRJL(norm=alg.norm, a=alg.a, nmin=alg.nmin, nmax=alg.nmax, n0=alg.n0, dn=alg.dn, keepmost=alg.keepmost,
+                                 syms=dom.syms, nthreads=alg.nthreads), j, dom.nsyms, dom.ndim)
+        raise TypeError("unsupported BZ algorithm (TAI is out of scope, SURVEY.md §2)")
+    if isinstance(dom, Basis):
+        return dom, alg, None, None, dom.ndim
+    if isinstance(dom, (CubicLimits, TetrahedralLimits)):
+        return dom, alg, None, None, dom.ndim
+    raise TypeError("unsupported domain")
+
+
+def _init_cacheval(cache):
+    alg, _ = _unwrap(cache.alg)
+    dom, salg, j, ns, ndim = _standard(cache.dom, alg)
+    f = cache.f
+    if ndim != f.s.ndim:
+        raise ValueError("variables in Fourier series don't match domain")
+    cv = cache.cacheval
+    cv["std"] = (dom, salg, j, ns, ndim)
+    if isinstance(salg, MonkhorstPack):
+        # init_fourier_rule (src/fourier.jl:330-342): the rule (node set + device handles) is built at init
+        cv["rule"] = cache.backend.make_rule(f.s, ndim, salg.npt, salg.syms, cache.shard.rank, cache.shard.nranks)
+    elif isinstance(salg, AutoSymPTRJL):
+        # AutoSymPTR.alloc_cache builds the first rule at init (src/fourier.jl:348-360)
+        n0, dn = monkhorst_pack_schedule(salg.a, salg.nmin, salg.nmax, salg.n0, salg.dn)
+        cv["schedule"] = (n0, dn)
+        cv["rules"] = [cache.backend.make_rule(f.s, ndim, n0, salg.syms, cache.shard.rank, cache.shard.nranks)]
+    elif isinstance(salg, NestedQuad):
+        if not isinstance(dom, (CubicLimits, TetrahedralLimits)):
+            raise TypeError("NestedQuad needs iterated limits")
+        if not f.native or f.f.is_eig:
+            raise TypeError("IAI on the device supports the resolvent / affine integrands")
+        cv["nest"] = cache.backend.make_nest(f.s, ndim, 64, 2048)
+    else:
+        raise TypeError(f"unsupported algorithm {type(salg).__name__} for FourierIntegrand")
+
+
+def _do_solve(cache, ps):
+    alg, counter = _unwrap(cache.alg)
+    dom, salg, j, ns, ndim = cache.cacheval["std"]
+    kws = dict(cache.kwargs)
+    abstol, reltol = kws.get("abstol"), kws.get("reltol")
+    maxiters = kws.get("maxiters", 2 ** 62)
+    on_bz = j is not None
+    bf = _BoundIntegrand(cache.f, ps)
+    shard = cache.shard
+    if isinstance(salg, MonkhorstPack):
+        # do_solve_autobz (src/brillouin.jl:337-355): sol = rule(f) (scale vol/(npt^d nsyms)); val = j*nsyms*sol
+        rule = cache.cacheval["rule"]
+        vals = _rule_apply(rule, bf, shard, ndim)
+        sc = j if on_bz else abs(np.linalg.det(dom.B))
+        ne = len(rule) if counter else -1
+        return [IntegralSolution(sc * v, None, True, ne) for v in vals]
+    if isinstance(salg, AutoSymPTRJL):
+        sc = j if on_bz else abs(np.linalg.det(dom.B))
+        atol = None if abstol is None else abstol / sc     # src/brillouin.jl:433 (no nsyms: rule output is symmetrised)
+        sols = []
+        for p in ps:
+            val, err, ne = _autosymptr(cache, _BoundIntegrand(cache.f, [p]), salg, atol, reltol, maxiters, ndim)
+            sols.append(IntegralSolution(val * sc, err * sc, True, ne if counter else -1))
+        return sols
+    if isinstance(salg, NestedQuad):
+        sols = []
+        sc = j if on_bz else 1.0
+        atol = abstol
+        if on_bz and abstol is not None:
+            atol = abstol / (j * ns)                        # src/brillouin.jl:342
+        for p in ps:
+            b1 = _BoundIntegrand(cache.f, [p])
+            bound = b1.bound[0]
+            ff = cache.f.f
+            if b1.fkind == _lib.F_TRACE_H:
+                z, sigma = 0j, None
+                test = ff.post(np.zeros(1, dtype=np.complex128), bound)
+            else:
+                z, sigma = bound
+                test = ff.post(np.zeros(1, dtype=np.complex128), bound)
+            dtype = np.complex128 if np.iscomplexobj(test) else np.float64
+            eng = NestedGK(cache.cacheval["nest"], ndim, dom, b1.fkind, z, sigma, lambda y, ff=ff, bound=bound: ff.post(y, bound),
+                           dtype, atol, reltol, maxiters)
+            Iv, Ev, ne = eng.run()
+            cache.cacheval["iai_rounds"] = eng.rounds
+            mult = sc * (ns if on_bz else 1)                # val = j * symmetrize(f, bz, sol.u) (TrivialRep: x nsyms)
+            u = Iv * mult
+            u = complex(u) if dtype == np.complex128 else float(u)
+            sols.append(IntegralSolution(u, float(Ev) * mult, True, ne if counter else -1))
+        return sols
+    raise TypeError("unsupported algorithm")
+
+
+def _autosymptr(cache, bf, salg, atol, reltol, maxevals, ndim):
+    """AutoSymPTR.autosymptr (call site src/algorithms.jl:429): I1 = rule_1(f), I2 = rule_2(f), err = norm(I1 - I2);
+    refine with nextrule (npt + dn, src/fourier.jl:315-321) until err <= max(reltol*norm(I2), abstol) or
+    numevals >= maxevals.  Rules already in the cache (from another parameter) are reused; at most `keepmost`
+    are kept afterwards.  [restated; SURVEY.md App. A.2]"""
+    atol_ = 0.0 if atol is None else atol
+    rtol_ = reltol if reltol is not None else (np.sqrt(np.finfo(float).eps) if atol_ == 0 else 0.0)
+    rules = cache.cacheval["rules"]
+    n0, dn = cache.cacheval["schedule"]
+    f, backend, shard = cache.f, cache.backend, cache.shard
+
+    def rule_at(i):
+        while len(rules) <= i:
+            prev = rules[-1]
+            rules.append(backend.make_rule(f.s, ndim, prev.npt + dn, salg.syms, shard.rank, shard.nranks))
+        return rules[i]
+
+    numevals = 0
+    r1 = rule_at(0)
+    int1 = _rule_apply(r1, bf, shard, ndim)[0]
+    numevals += len(r1)
+    if numevals >= maxevals:
+        return int1, float("nan"), numevals
+    r2 = rule_at(1)
+    int2 = _rule_apply(r2, bf, shard, ndim)[0]
+    numevals += len(r2)
+    err = salg.norm(int1 - int2)
+    i = 1
+    while not (err <= max(rtol_ * salg.norm(int2), atol_)) and numevals < maxevals and np.isfinite(err):
+        i += 1
+        r = rule_at(i)
+        int1, int2 = int2, _rule_apply(r, bf, shard, ndim)[0]
+        numevals += len(r)
+        err = salg.norm(int1 - int2)
+    # keep the `keepmost` most refined rules for the next parameter (src/algorithms.jl:429 keepmost)
+    keep = max(1, salg.keepmost)
+    used = rules[: i + 1]
+    drop = used[:-keep] if len(used) > keep else []
+    for r in drop:
+        r.close()
+    cache.cacheval["rules"] = used[-keep:] if len(used) > keep else used
+    cache.cacheval["last_npt"] = used[-1].npt
+    return int2, err, numevals
+
+
+# ---------------------------------------------------------------------------------------------------
+class IntegralSolver:
+    """IntegralSolver(f, dom, alg; abstol, reltol, maxiters) / IntegralSolver(prob, alg; ...)
+    (src/interfaces.jl:142-187; FourierIntegrand functor src/fourier.jl:89-93): solver(args...; kws...) -> u."""
+
+    def __init__(self, *a, backend=None, shard=None, **kwargs):
+        if isinstance(a[0], IntegralProblem):
+            prob, alg = a[0], a[1]
+        else:
+            f, dom, alg = a[0], a[1], a[2]
+            prob = IntegralProblem(f, dom, None)
+        checkkwargs(kwargs)
+        self.prob, self.alg, self.kwargs = prob, alg, kwargs
+        self.cache = init(prob, alg, backend=backend, shard=shard, **kwargs)
+
+    def solve_p(self, p):
+        """solve_p(s, p) (src/interfaces.jl:174-182): remake_cache with merged parameters, then solve!"""
+        base = _params(self.prob.p)
+        q = _params(p)
+        merged = (base[0] + q[0], {**base[1], **q[1]})
+        return solve_(self.cache, [merged])[0]
+
+    def __call__(self, *args, **kws):
+        return self.solve_p((args, kws)).u
+
+
+def batchsolve(solver, ps, callback=None):
+    """batchsolve(solver, ps) (src/interfaces.jl:199-243): solve for every parameter in `ps` against ONE cached
+    rule.  The reference threads over parameters with the grid shared; here the parameters are an inner batch
+    dimension of the device kernels (one H(k) load, n_omega resolvents) whenever the algorithm is a fixed rule."""
+    plist = list(ps)
+    base = _params(solver.prob.p)
+    merged = []
+    for p in plist:
+        q = _params(p)
+        merged.append((base[0] + q[0], {**base[1], **q[1]}))
+    t0 = time.time()
+    sols = solve_(solver.cache, merged)
+    t = time.time() - t0
+    if callback is not None:
+        for i, (p, s) in enumerate(zip(plist, sols)):
+            callback(solver.prob.f, i, len(plist), p, s, t / max(1, len(plist)))
+    return np.array([s.u for s in sols])

@@ -85,6 +85,11 @@ int32_t abz_rule_create_full(abz_ctx* ctx, abz_series_t s, int32_t npt, int32_t 
  * gives the reference's :scatter distribution, src/fourier.jl:246-255). */
 int32_t abz_rule_create_sym(abz_ctx* ctx, abz_series_t s, int32_t npt, const int32_t* wsym,
                             int32_t k3_lo, int32_t k3_stride, abz_rule_t* out);
+/* The same rule from an explicit node list (the reference's rule.wxs vector of (w, x) pairs,
+ * src/fourier.jl:210-214): idx = Int32[3, nnodes] grid indices (i1, i2, i3) sorted by (i3, i2, i1),
+ * w = Float64[nnodes] or NULL (all 1).  Used for 1-d / 2-d series and custom node sets. */
+int32_t abz_rule_create_nodes(abz_ctx* ctx, abz_series_t s, int32_t npt, int64_t nnodes, const int32_t* idx,
+                              const double* w, abz_rule_t* out);
 /* AutoSymPTR.symptr_rule (call site src/fourier.jl:271) on the device: syms = Int32[3,3,nsyms]
  * row-major per matrix, wsym_out = Int32[npt^3] host buffer; returns the irreducible count. */
 int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t* wsym_out, int64_t* nirr);

@@ -1,0 +1,139 @@
+"""TEST DOUBLE: a backend with the interface of autobz_b200.backend.DeviceBackend whose arithmetic is the
+CPU oracle.  It exists so that the HOST control flow (tolerance rescaling, symmetrisation, AutoPTR loop,
+IAI engine, multi-rank sharding + allreduce) can be tested on a box without a GPU and compared with the
+reference's known-answer tests.  It lives under tests/ and is never imported by the product."""
+import ctypes as C
+
+import numpy as np
+
+import orc
+from autobz_b200.backend import symptr_nodes_lowdim
+
+
+def _oseries(fs):
+    c = np.asarray(fs.c, dtype=np.complex128)
+    while c.ndim < 5:
+        c = c[..., None]
+    lo = tuple(fs.lo) + (0,) * (3 - fs.ndim)
+    per = tuple(fs.period) + (1.0,) * (3 - fs.ndim)
+    return orc.Series(c, lo, per)
+
+
+class OracleRule:
+    def __init__(self, series, ndim, npt, syms, rank=0, nranks=1):
+        self.fs, self.so, self.ndim, self.npt = series, _oseries(series), ndim, int(npt)
+        if ndim == 3:
+            if syms is None:
+                i3, i2, i1 = np.meshgrid(np.arange(npt), np.arange(npt), np.arange(npt), indexing="ij")
+                idx = np.stack([i1.ravel(), i2.ravel(), i3.ravel()], axis=1)
+                w = np.ones(idx.shape[0])
+                lo, hi = (npt * rank) // nranks, (npt * (rank + 1)) // nranks
+                sel = (idx[:, 2] >= lo) & (idx[:, 2] < hi)
+            else:
+                sy = np.array([np.rint(np.asarray(S)).astype(np.int32) for S in syms])
+                ws, nirr = orc.symptr_rule(npt, sy)
+                i1, i2, i3 = np.nonzero(ws)
+                order = np.lexsort((i1, i2, i3))
+                idx = np.stack([i1[order], i2[order], i3[order]], axis=1)
+                w = ws[i1[order], i2[order], i3[order]].astype(float)
+                sel = (idx[:, 2] % nranks) == rank
+            self.nnodes_total = idx.shape[0]
+            self.idx, self.w = idx[sel], w[sel]
+        else:
+            idx, w = symptr_nodes_lowdim(npt, ndim, syms)
+            self.nnodes_total = idx.shape[0]
+            lo, hi = (idx.shape[0] * rank) // nranks, (idx.shape[0] * (rank + 1)) // nranks
+            self.idx, self.w = idx[lo:hi], w[lo:hi]
+        self.nnodes = self.idx.shape[0]
+        self._H = None
+
+    def __len__(self):
+        return self.nnodes_total
+
+    def _Hk(self):
+        if self._H is None:
+            self._H = orc.eval_points(self.so, self.idx / float(self.npt))
+        return self._H
+
+    def materialize(self):
+        self._Hk()
+
+    def copy_out(self):
+        return self._Hk(), self.idx / float(self.npt), self.w
+
+    def resolvent_sum(self, z, sigma, fkind):
+        H = self._Hk()
+        if self.nnodes == 0:
+            return np.zeros(1 if fkind == 1 else np.atleast_1d(z).size, dtype=complex)
+        if fkind == 1:
+            return np.array([np.sum(self.w * np.trace(H, axis1=0, axis2=1))])
+        y = orc.resolvent_trace_batch(H, z, sigma)
+        return (self.w[:, None] * y).sum(axis=0)
+
+    def eig_sum(self, kind, params):
+        ev = orc.eigvals_batch(self._Hk())
+        p0, p1 = params
+        f = lambda x: np.where(x > 0, np.exp(-np.abs(x)) / (1 + np.exp(-np.abs(x))), 1 / (1 + np.exp(-np.abs(x))))
+        if kind == 0:
+            g = ev
+        elif kind == 1:
+            g = ev * f((ev - p0) / p1)
+        elif kind == 2:
+            g = f((ev - p0) / p1)
+        else:
+            g = np.exp(-((ev - p0) / p1) ** 2) / (p1 * np.sqrt(np.pi))
+        return float(np.sum(self.w * g.sum(axis=1)))
+
+    def close(self):
+        pass
+
+
+class OracleNest:
+    def __init__(self, series, ndim):
+        self.so, self.ndim = _oseries(series), ndim
+        self.L2, self.L1 = {}, {}
+        self.n = series.norb
+
+    def _contract(self, src, rows, M, lo, period, x):
+        out = np.empty(rows, dtype=np.complex128)
+        orc.lib().orc_contract(src.ctypes.data_as(orc.c_dp), C.c_long(rows), C.c_int(M), C.c_int(lo), C.c_double(period),
+                               C.c_double(x), out.ctypes.data_as(orc.c_dp))
+        return out
+
+    def contract3(self, x3, slot2):
+        s = self.so
+        rows = s.n * s.n * s.M[0] * s.M[1]
+        flat = np.ascontiguousarray(s.c.reshape(-1, order="F"))
+        for x, sl in zip(x3, slot2):
+            self.L2[int(sl)] = self._contract(flat, rows, s.M[2], s.lo[2], s.period[2], float(x))
+
+    def contract2(self, x2, parent, slot1):
+        s = self.so
+        rows = s.n * s.n * s.M[0]
+        root = np.ascontiguousarray(s.c.reshape(-1, order="F"))
+        for i, (x, sl) in enumerate(zip(x2, slot1)):
+            src = root if parent is None else self.L2[int(parent[i])]
+            self.L1[int(sl)] = self._contract(src, rows, s.M[1], s.lo[1], s.period[1], float(x))
+
+    def eval(self, x1, slot1, z, sigma, fkind):
+        s = self.so
+        nn = s.n * s.n
+        root = np.ascontiguousarray(s.c.reshape(-1, order="F"))
+        H = np.empty((s.n, s.n, len(x1)), dtype=np.complex128, order="F")
+        for i, x in enumerate(x1):
+            src = root if slot1 is None else self.L1[int(slot1[i])]
+            H[:, :, i] = self._contract(src, nn, s.M[0], s.lo[0], s.period[0], float(x)).reshape(s.n, s.n, order="F")
+        if fkind == 1:
+            return np.trace(H, axis1=0, axis2=1).astype(np.complex128)
+        sg = None if sigma is None else np.asarray(sigma).reshape(s.n, s.n, 1)
+        return orc.resolvent_trace_batch(H, [z], sg)[:, 0]
+
+
+class OracleBackend:
+    launch_count = 0
+
+    def make_rule(self, series, ndim, npt, syms, rank=0, nranks=1):
+        return OracleRule(series, ndim, npt, syms, rank, nranks)
+
+    def make_nest(self, series, ndim, cap2, cap1):
+        return OracleNest(series, ndim)

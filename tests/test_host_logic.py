@@ -1,0 +1,186 @@
+"""Host control flow (BZ conventions, tolerance rescaling, AutoPTR loop, IAI engine, sharding) exercised on CPU
+through the oracle-backed test double, against the reference's own tests (test/fourier.jl, test/brillouin.jl).
+CPU only; the same tests run against the device backend in test_gpu_parity.py."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import autobz_b200 as ab
+from oracle_backend import OracleBackend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def lattice_series(d):
+    c, lo = ab.synthetic.integer_lattice(d)
+    return ab.FourierSeries(c[0, 0], period=1.0, lo=lo)
+
+
+def test_bz_construction():
+    # test/brillouin.jl:7-31
+    for d in (1, 2, 3):
+        A = np.eye(d)
+        assert ab.load_bz(ab.FBZ(), A).nsyms == 1
+        assert ab.load_bz(ab.InversionSymIBZ(), A).nsyms == 2 ** d
+        assert ab.load_bz(ab.CubicSymIBZ(), A).nsyms == math.factorial(d) * 2 ** d
+        assert isinstance(ab.load_bz(ab.FBZ(), A).lims, ab.CubicLimits)
+        assert isinstance(ab.load_bz(ab.CubicSymIBZ(), A).lims, ab.TetrahedralLimits)
+    bz = ab.load_bz(ab.FBZ(2), 2 * np.pi * np.eye(2))
+    assert np.allclose(bz.B, np.eye(2))
+    with pytest.raises(ValueError):
+        ab.load_bz(ab.FBZ(), np.eye(2), np.eye(2))          # non-reciprocal bases
+    syms = ab.cube_automorphisms(3)
+    assert len({S.tobytes() for S in syms}) == 48
+
+
+def test_tetrahedral_limits_volume():
+    lims = ab.TetrahedralLimits([0.5, 0.5, 0.5])
+    assert lims.segments() == (0.0, 0.5)
+    l2 = lims.fix(0.25)
+    assert l2.segments() == (0.0, 0.25)
+    assert l2.fix(0.1).segments() == (0.0, 0.1)
+
+
+def test_schedule_defaults():
+    from autobz_b200.algorithms import monkhorst_pack_schedule
+    assert monkhorst_pack_schedule(1.0, 50, 1000, 6.0, math.log(10)) == (50, 3)
+    assert monkhorst_pack_schedule(0.01, 50, 1000, 6.0, math.log(10)) == (600, 231)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("bzkind", ["fbz", "inv"])
+def test_fourier_jl_algorithms(d, bzkind):
+    """test/fourier.jl:40-56: for alg in (IAI, PTR, AutoPTR) x (plain, EvalCounter):
+    integral of 1.3*H(k) + 1 over the BZ of A = I(d) equals (2 pi)^d to atol 1e-6 (abstol=1e-6, reltol=0)."""
+    vol = (2 * np.pi) ** d
+    s = lattice_series(d)
+    bz = ab.load_bz(ab.FBZ() if bzkind == "fbz" else ab.InversionSymIBZ(), np.eye(d))
+    integrand = ab.FourierIntegrand(ab.AffineTraceIntegrand(), s, 1.3, b=1.0)
+    prob = ab.IntegralProblem(integrand, bz)
+    be = OracleBackend()
+    for alg in (ab.IAI(), ab.PTR(), ab.AutoPTR()):
+        for counter in (False, True):
+            new_alg = ab.EvalCounter(alg) if counter else alg
+            solver = ab.IntegralSolver(prob, new_alg, reltol=0, abstol=1e-6, backend=be)
+            assert abs(solver() - vol) < 1e-6
+            sol = solver.solve_p(None)
+            assert (sol.numevals > 0) == counter
+
+
+def test_evalcounter_counts():
+    s = lattice_series(3)
+    bz = ab.load_bz(ab.FBZ(), np.eye(3))
+    ibz = ab.load_bz(ab.CubicSymIBZ(), np.eye(3))
+    f = ab.FourierIntegrand(ab.AffineTraceIntegrand(), s, 0.0, b=1.0)     # constant integrand
+    be = OracleBackend()
+    # constant integrand: every GK panel converges at once -> 15^3 evaluations (test/brillouin.jl:96 per level)
+    sol = ab.solve(ab.IntegralProblem(f, bz), ab.EvalCounter(ab.IAI()), abstol=1e-8, backend=be)
+    assert sol.numevals == 15 ** 3 and abs(sol.u - (2 * np.pi) ** 3) < 1e-9
+    sol = ab.solve(ab.IntegralProblem(f, ibz), ab.EvalCounter(ab.IAI()), abstol=1e-8, backend=be)
+    assert sol.numevals == 15 ** 3 and abs(sol.u - (2 * np.pi) ** 3) < 1e-9
+    # PTR: numevals = number of (irreducible) nodes
+    sol = ab.solve(ab.IntegralProblem(f, bz), ab.EvalCounter(ab.PTR(npt=10)), backend=be)
+    assert sol.numevals == 1000
+    sol = ab.solve(ab.IntegralProblem(f, ibz), ab.EvalCounter(ab.PTR(npt=10)), backend=be)
+    assert sol.numevals == 56
+    # AutoPTR default schedule 50, 53 (converges immediately for a constant)
+    sol = ab.solve(ab.IntegralProblem(f, ibz), ab.EvalCounter(ab.AutoPTR()), abstol=1e-8, backend=be)
+    w50 = 50 * 51 * 52 // 6 if False else None
+    assert sol.numevals > 0 and abs(sol.u - (2 * np.pi) ** 3) < 1e-9
+
+
+@pytest.mark.parametrize("lims", ["cubic", "tetra"])
+def test_iai_engine_matches_recursive_oracle(orc, svo, lims):
+    """The level-synchronous engine must reproduce the sequential recursion decision for decision:
+    identical numevals and integrals equal to rounding (same oracle arithmetic on both sides)."""
+    H, lo, A = svo
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
+    S = orc.Series(H, lo)
+    be = OracleBackend()
+    eta, omega = 0.05, 12.5
+    if lims == "cubic":
+        bz = ab.load_bz(ab.FBZ(), A)
+        Io, Eo, neo = orc.iai(S, 3, 0, [0.0] * 3, [1.0] * 3, vkind=1, z=complex(omega, eta), atol=3e-2)
+        mult = abs(np.linalg.det(bz.B))
+        abstol = 3e-2 * mult
+    else:
+        bz = ab.load_bz(ab.CubicSymIBZ(), A)
+        Io, Eo, neo = orc.iai(S, 3, 1, [0.5] * 3, vkind=1, z=complex(omega, eta), atol=1e-3)
+        mult = abs(np.linalg.det(bz.B)) * 48
+        abstol = 1e-3 * mult
+    f = ab.FourierIntegrand(ab.dos_integrand, fs, eta)
+    sol = ab.solve(ab.IntegralProblem(f, bz, omega), ab.EvalCounter(ab.IAI()), abstol=abstol, backend=be)
+    assert sol.numevals == neo
+    assert abs(sol.u - mult * Io.real) <= 1e-12 * abs(sol.u)
+
+
+def test_ptr_and_autoptr_svo_vs_oracle(orc, svo):
+    H, lo, A = svo
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
+    S = orc.Series(H, lo)
+    be = OracleBackend()
+    bz = ab.load_bz(ab.FBZ(), A)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), A)
+    j = abs(np.linalg.det(bz.B))
+    f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=0.01)
+    ref = orc.ptr_sum(S, 24, [11.0 + 0.01j])[0] * j
+    for dom in (bz, ibz):
+        u = ab.solve(ab.IntegralProblem(f, dom, {"omega": 11.0}), ab.PTR(npt=24), backend=be).u
+        assert abs(u - ref) < 1e-11 * abs(ref)
+    # batchsolve == serial loop (test/brillouin.jl:98-111)
+    solver = ab.IntegralSolver(f, ibz, ab.PTR(npt=12), backend=be)
+    ws = [11.0, 12.0, 13.0]
+    assert np.allclose(ab.batchsolve(solver, [{"omega": w} for w in ws]), [solver(omega=w) for w in ws], rtol=1e-13)
+    # AutoPTR outside the band converges on the first pair of grids
+    sol = ab.solve(ab.IntegralProblem(f, ibz, {"omega": 11.0}), ab.EvalCounter(ab.AutoPTR(nmin=12, a=1.0)), abstol=1e-6, backend=be)
+    assert abs(sol.u - ref) < 1e-6
+
+
+def test_generic_python_integrand_host_path():
+    s = lattice_series(2)
+    bz = ab.load_bz(ab.FBZ(), np.eye(2))
+    f = ab.FourierIntegrand(lambda x, a, b=0.0: a * x.s + b, s, 1.3, b=1.0)
+    u = ab.solve(ab.IntegralProblem(f, bz), ab.PTR(npt=8), backend=OracleBackend()).u
+    assert abs(u - (2 * np.pi) ** 2) < 1e-10
+
+
+_GLOO_SCRIPT = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle")); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch.distributed as dist
+import autobz_b200 as ab
+from oracle_backend import OracleBackend
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+shard = ab.Shard(rank, 2, ab.torch_allreduce())
+H, lo = ab.synthetic.wannier_hamiltonian(3, 1, cubic=True)
+fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
+f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=2.0)
+out = []
+for dom in (ab.load_bz(ab.FBZ(), np.eye(3)), ab.load_bz(ab.CubicSymIBZ(), np.eye(3))):
+    for alg in (ab.PTR(npt=9), ab.EvalCounter(ab.AutoPTR(nmin=6, nmax=40))):
+        s2 = ab.solve(ab.IntegralProblem(f, dom, {{"omega": 0.3}}), alg, abstol=1e-5, backend=OracleBackend(), shard=shard)
+        s1 = ab.solve(ab.IntegralProblem(f, dom, {{"omega": 0.3}}), alg, abstol=1e-5, backend=OracleBackend())
+        out.append((abs(s2.u - s1.u) / abs(s1.u), s2.numevals == s1.numevals))
+ok = all(e < 1e-13 and c for e, c in out)
+print("RANK", rank, "OK" if ok else "FAIL", out)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    """world_size 2 over gloo: k3 planes sharded (contiguous for FBZ, round-robin for IBZ), one allreduce per rule,
+    identical convergence decisions and results equal to the single-rank solve to rounding."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "gloo2.py"
+    script.write_text(_GLOO_SCRIPT.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
