@@ -1,0 +1,295 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs,
+against the committed golden fixtures, and — at BASELINE.json's full sizes — through size-independent
+properties (slab additivity, IBZ == FBZ, run-to-run bit reproducibility).
+
+Tolerances (north_star): integrals <= 1e-10 relative; fixed-N PTR sums <= 1e-12 relative (only the
+summation order and phase rounding differ); IAI: identical numevals to the oracle's restated control flow."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import autobz_b200 as ab
+from autobz_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def lattice_series(d):
+    c, lo = ab.synthetic.integer_lattice(d)
+    return ab.FourierSeries(c[0, 0], period=1.0, lo=lo)
+
+
+# ---------------------------------------------------------------------------------------------------
+# low-level ABI vs oracle
+@pytest.mark.parametrize("n,rmax,N", [(1, 1, 16), (2, 1, 9), (3, 2, 12), (5, 2, 10), (8, 1, 8), (17, 1, 5), (32, 1, 6), (64, 1, 4)])
+def test_rule_sums_and_values_vs_oracle(ctx, orc, n, rmax, N):
+    H, lo = ab.synthetic.wannier_hamiltonian(n, rmax)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    So = orc.Series(H, lo)
+    z = np.array([0.3 + 0.05j, -0.7 + 0.2j, 1.5 + 0.01j])
+    rng = np.random.default_rng(n)
+    sig = 0.1 * (rng.standard_normal((n, n, 3)) + 1j * rng.standard_normal((n, n, 3)))
+    R = L.DeviceRule(ctx, S, N)
+    ref = orc.ptr_sum(So, N, z)
+    assert rel(R.resolvent_sum(z, scale=1 / N ** 3), ref) < 1e-11
+    assert rel(R.resolvent_sum(z, sigma=sig, scale=1 / N ** 3), orc.ptr_sum(So, N, z, sigma=sig)) < 1e-11
+    Hk, k, w = R.copy_out()
+    assert rel(Hk.reshape(n, n, N, N, N, order="F"), orc.grid_eval_full(So, N)) < 1e-13
+    assert np.all(w == 1.0) and k.shape == (N ** 3, 3) and abs(k[1, 0] - 1 / N) < 1e-16
+    R.materialize()
+    assert rel(R.resolvent_sum(z, scale=1 / N ** 3), ref) < 1e-11
+    # k3 slabs are additive (the multi-GPU shard unit)
+    parts = [L.DeviceRule(ctx, S, N, k3_lo=a, k3_hi=b).resolvent_sum(z, scale=1 / N ** 3) for a, b in ((0, 1), (1, 3), (3, N))]
+    assert rel(sum(parts), ref) < 1e-11
+    # eigenvalues vs LAPACK and eigenvalue sums vs oracle
+    ev = R.eigvals()
+    assert rel(ev, np.linalg.eigvalsh(np.moveaxis(Hk, 2, 0))) < 1e-11
+    for kind, prm in ((L.EIG_SUM, (0.0, 1.0)), (L.EIG_FERMI_ENERGY, (0.1, 0.3)), (L.EIG_FERMI_COUNT, (0.1, 0.3)), (L.EIG_GAUSS_DOS, (0.2, 0.4))):
+        assert abs(R.eig_sum(kind, prm, 1 / N ** 3) - orc.ptr_eig_sum(So, N, kind, prm, scale=1 / N ** 3)[0]) < 1e-11 * n
+    # scattered points
+    kp = rng.random((9, 3))
+    assert rel(S.eval_points(kp), orc.eval_points(So, kp)) < 1e-13
+    assert rel(S.points_resolvent(kp, z), orc.resolvent_trace_batch(orc.eval_points(So, kp), z)) < 1e-11
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+def test_resolvent_algorithms_agree(ctx, orc, algo):
+    """generic pivoted Gauss-Jordan (1) and the DMMA register path (2) against the oracle's pivoted LU, incl. a
+    matrix-valued self-energy and a small eta (cond ~ 1e4)"""
+    n, N = 32, 6
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 2)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    So = orc.Series(H, lo)
+    rng = np.random.default_rng(7)
+    z = np.concatenate([rng.uniform(-3, 3, 6) + 0.02j, rng.uniform(-3, 3, 3) + 1e-4j])
+    sig = 0.05 * (rng.standard_normal((n, n, 9)) + 1j * rng.standard_normal((n, n, 9)))
+    sig = sig - 0.1j * np.eye(n)[:, :, None]
+    ctx.set_option(L.OPT_RESOLVENT_ALGO, algo)
+    try:
+        R = L.DeviceRule(ctx, S, N)
+        assert rel(R.resolvent_sum(z, scale=1 / N ** 3), orc.ptr_sum(So, N, z)) < 1e-10
+        assert rel(R.resolvent_sum(z, sigma=sig, scale=1 / N ** 3), orc.ptr_sum(So, N, z, sigma=sig)) < 1e-10
+        kp = rng.random((5, 3))
+        assert rel(S.points_resolvent(kp, z, sigma=sig), orc.resolvent_trace_batch(orc.eval_points(So, kp), z, sig)) < 1e-10
+    finally:
+        ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
+
+
+def test_singular_matrix_is_an_error(ctx):
+    c = np.zeros((2, 2, 1, 1, 1))
+    S = L.DeviceSeries(ctx, c, (0, 0, 0), (1.0,) * 3)
+    R = L.DeviceRule(ctx, S, 2)
+    with pytest.raises(ab.SingularIntegrandError):
+        R.resolvent_sum([0.0 + 0.0j])          # z I - 0 = 0: singular -> DomainError-like
+    c4 = np.zeros((5, 5, 1, 1, 1))
+    R4 = L.DeviceRule(ctx, L.DeviceSeries(ctx, c4, (0, 0, 0), (1.0,) * 3), 2)
+    with pytest.raises(ab.SingularIntegrandError):
+        R4.resolvent_sum([0.0 + 0.0j])
+    assert abs(R4.resolvent_sum([2.0 + 0.0j], scale=1 / 8)[0] - 2.5) < 1e-14     # ctx usable afterwards
+
+
+def test_invalid_arguments_raise(ctx):
+    H, lo = ab.synthetic.wannier_hamiltonian(2, 1)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    with pytest.raises(ValueError):
+        L.DeviceRule(ctx, S, 4, k3_lo=3, k3_hi=9)
+    with pytest.raises(ValueError):
+        L.DeviceRule(ctx, S, 4, nodes=[[1, 0, 0], [0, 0, 0]])           # unsorted
+    R = L.DeviceRule(ctx, S, 4, nodes=np.zeros((0, 3), dtype=np.int32))  # empty rule is fine (a rank with no planes)
+    assert len(R) == 0 and R.resolvent_sum([1.0 + 1j])[0] == 0
+    with pytest.raises(ValueError):
+        L.DeviceSeries(ctx, np.zeros((65, 65, 1, 1, 1)), (0, 0, 0), (1.0,) * 3) if False else L.DeviceRule(ctx, S, 0)
+
+
+def test_symmetric_rules_vs_oracle(ctx, orc):
+    syms = ab.cube_automorphisms(3)
+    for n, rmax, N in [(3, 2, 12), (3, 2, 15), (6, 1, 10), (32, 1, 8)]:
+        H, lo = ab.synthetic.wannier_hamiltonian(n, rmax, cubic=True)
+        S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+        So = orc.Series(H, lo)
+        w_o, nirr_o = orc.symptr_rule(N, syms)
+        w_d, nirr_d = ctx.symptr_rule(N, np.array(syms, dtype=np.int32))
+        assert np.array_equal(w_o, w_d) and nirr_o == nirr_d and w_d.sum() == N ** 3
+        z = np.array([0.3 + 0.05j, -0.7 + 0.2j])
+        R = L.DeviceRule(ctx, S, N, wsym=w_d)
+        ref, cnt = orc.symptr_sum(So, N, w_o, z, scale=1 / N ** 3)
+        assert len(R) == cnt == nirr_o
+        assert rel(R.resolvent_sum(z, scale=1 / N ** 3), ref) < 1e-11
+        assert rel(ref, orc.ptr_sum(So, N, z)) < 1e-12                       # IBZ-weighted == FBZ
+        R.materialize()
+        assert rel(R.resolvent_sum(z, scale=1 / N ** 3), ref) < 1e-11
+        shards = [L.DeviceRule(ctx, S, N, wsym=w_d, k3_lo=r, k3_stride=3).resolvent_sum(z, scale=1 / N ** 3) for r in range(3)]
+        assert rel(sum(shards), ref) < 1e-11
+        assert abs(R.eig_sum(L.EIG_SUM, scale=1 / N ** 3) - orc.ptr_eig_sum(So, N, 0, (0, 1), wsym=w_o, scale=1 / N ** 3)[0]) < 1e-11 * n
+
+
+def test_nest_arena_vs_oracle(ctx, orc):
+    for n in (1, 3, 6):
+        H, lo = ab.synthetic.wannier_hamiltonian(n, 2)
+        S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+        So = orc.Series(H, lo)
+        nest = L.DeviceNest(ctx, S, 3, 4, 8)
+        rng = np.random.default_rng(5)
+        x3 = rng.random(3); nest.contract3(x3, [0, 1, 3])
+        x2 = rng.random(5); par = np.array([0, 1, 3, 3, 0]); sl1 = [7, 0, 2, 3, 5]; nest.contract2(x2, par, sl1)
+        x1 = rng.random(11); s1 = rng.choice(sl1, 11)
+        m = {s: i for i, s in enumerate(sl1)}
+        m3 = {0: 0, 1: 1, 3: 2}
+        kp = np.array([[x1[i], x2[m[s1[i]]], x3[m3[par[m[s1[i]]]]]] for i in range(11)])
+        y = nest.eval(x1, s1, 0.2 + 0.1j)
+        assert rel(y, orc.resolvent_trace_batch(orc.eval_points(So, kp), [0.2 + 0.1j])[:, 0]) < 1e-11
+        with pytest.raises(ValueError):
+            nest.contract3([0.1], [99])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own tests through the public API on the device
+@pytest.mark.parametrize("d", [1, 2, 3])
+@pytest.mark.parametrize("bzkind", ["fbz", "inv"])
+def test_fourier_jl_algorithms_on_device(d, bzkind):
+    """test/fourier.jl:40-56"""
+    vol = (2 * np.pi) ** d
+    s = lattice_series(d)
+    bz = ab.load_bz(ab.FBZ() if bzkind == "fbz" else ab.InversionSymIBZ(), np.eye(d))
+    prob = ab.IntegralProblem(ab.FourierIntegrand(ab.AffineTraceIntegrand(), s, 1.3, b=1.0), bz)
+    for alg in (ab.IAI(), ab.PTR(), ab.AutoPTR()):
+        for counter in (False, True):
+            solver = ab.IntegralSolver(prob, ab.EvalCounter(alg) if counter else alg, reltol=0, abstol=1e-6)
+            assert abs(solver() - vol) < 1e-6
+
+
+def test_docs_goldens_on_device():
+    # docs/src/examples.md:44-60 (1-D) and :79-106 (2-D IAI on FBZ(2)), abstol = 1e-3
+    h1 = ab.FourierSeries([0.5, 0.0, 0.5], period=1, offset=-2)
+    bz1 = ab.SymmetricBZ(np.eye(1) * 2 * np.pi, np.eye(1), ab.CubicLimits([0.0], [1.0]), None)
+    g1 = ab.IntegralSolver(ab.FourierIntegrand(ab.gloc_trace_integrand, h1, eta=0.1), bz1, ab.IAI(), abstol=1e-3)(omega=0.0)
+    ref1 = GOLD["reference_known_answers"]["docs/src/examples.md:60 (QuadGKJL abstol=1e-3, 1-D gloc, eta=0.1, omega=0)"]
+    assert abs(g1.imag - ref1[1]) < 1e-14 and abs(g1.real) < 1e-14
+    C2 = np.array([[0.0, 0.5, 0.0], [0.5, 0.0, 0.5], [0.0, 0.5, 0.0]])
+    h2 = ab.FourierSeries(C2, period=1, offset=-2)
+    bz2 = ab.load_bz(ab.FBZ(2), 2 * np.pi * np.eye(2))
+    g2 = ab.IntegralSolver(ab.FourierIntegrand(ab.gloc_trace_integrand, h2, eta=0.1), bz2, ab.IAI(), abstol=1e-3)(omega=0.0)
+    ref2 = GOLD["reference_known_answers"]["docs/src/examples.md:105 (IAI abstol=1e-3, 2-D gloc on FBZ(2), eta=0.1, omega=0)"]
+    assert abs(g2.imag - ref2[1]) < 1e-13 and abs(g2.real) < 1e-13
+
+
+def test_c1_config_values():
+    """BASELINE config 1: cubic 1-orbital cos band, PTR 64^3, eta = 0.1"""
+    s = lattice_series(3)
+    bz = ab.load_bz(ab.FBZ(), 2 * np.pi * np.eye(3))      # B = I => j = 1
+    solver = ab.IntegralSolver(ab.FourierIntegrand(ab.gloc_trace_integrand, s, eta=0.1), bz, ab.PTR(npt=64))
+    g = ab.batchsolve(solver, [{"omega": 0.0}, {"omega": 0.5}])
+    assert abs(g[0] - (-2.361629003144814j)) < 1e-12
+    assert abs(g[1] - (1.448114087711081 - 1.4016191114904277j)) < 1e-12
+    ref = GOLD["oracle_values"]["c1_ptr_N64_eta0.1"]
+    assert abs(g[1] - complex(*ref[1])) < 1e-12 * abs(g[1])
+
+
+def test_c2_svo_ptr_autoptr(orc, svo):
+    """BASELINE config 2: SrVO3 Green's-function trace, PTR goldens + AutoPTR on CubicSymIBZ vs FBZ"""
+    H, lo, A = svo
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
+    bz, ibz = ab.load_bz(ab.FBZ(), A), ab.load_bz(ab.CubicSymIBZ(), A)
+    j = abs(np.linalg.det(bz.B))
+    assert abs(j - 4.31781301953062) < 1e-12
+    f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=0.01)
+    ws = [11.0, 12.0, 12.975161, 13.5]
+    for N in (24, 50):
+        ref = np.array([complex(*v) for v in GOLD["oracle_values"][f"svo_fbz_ptr_N{N}_eta1e-2"]]) * j
+        for dom in (bz, ibz):
+            got = ab.batchsolve(ab.IntegralSolver(f, dom, ab.PTR(npt=N)), [{"omega": w} for w in ws])
+            assert rel(got, ref) < 1e-12
+    # DOS integrand of aps_example.jl:30-34 (positional eta, omega)
+    dos = ab.IntegralSolver(ab.FourierIntegrand(ab.dos_integrand, fs, 0.01), ibz, ab.PTR(npt=50))
+    ref = -np.imag(complex(*GOLD["oracle_values"]["svo_fbz_ptr_N50_eta1e-2"][1]) * j) / np.pi
+    assert abs(dos(12.0) - ref) < 1e-12 * abs(ref)
+    # AutoPTR: same decisions and value as the oracle-driven control flow
+    from oracle_backend import OracleBackend
+    alg = ab.EvalCounter(ab.AutoPTR(a=0.05, nmin=20, nmax=400))
+    for w in (11.0, 12.5):
+        sd = ab.solve(ab.IntegralProblem(f, ibz, {"omega": w}), alg, abstol=1e-3)
+        so = ab.solve(ab.IntegralProblem(f, ibz, {"omega": w}), alg, abstol=1e-3, backend=OracleBackend())
+        assert sd.numevals == so.numevals
+        assert abs(sd.u - so.u) < 1e-10 * abs(so.u)
+
+
+def test_c3_svo_iai_counts_and_values(orc, svo):
+    """BASELINE config 3: SrVO3 DOS via IAI (nested GK panels): identical adaptive evaluation counts to the
+    oracle's sequential recursion and integrals within 1e-10 relative."""
+    H, lo, A = svo
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
+    S = orc.Series(H, lo)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), A)
+    mult = abs(np.linalg.det(ibz.B)) * 48
+    for eta, omega, atol in ((0.05, 12.5, 1e-2), (0.01, 12.0, 1e-2), (1e-3, 12.975161, 2e-2)):
+        Io, Eo, neo = orc.iai(S, 3, 1, [0.5] * 3, vkind=1, z=complex(omega, eta), atol=atol)
+        f = ab.FourierIntegrand(ab.dos_integrand, fs, eta)
+        sol = ab.solve(ab.IntegralProblem(f, ibz, omega), ab.EvalCounter(ab.IAI()), abstol=atol * mult)
+        assert sol.numevals == neo
+        assert abs(sol.u - mult * Io.real) <= 1e-10 * abs(sol.u)
+    g = GOLD["oracle_values"]["svo_iai_tetra_dos_w12.5_eta0.05_atol1e-2"]
+    sol = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.dos_integrand, fs, 0.05), ibz, 12.5), ab.EvalCounter(ab.IAI()), abstol=1e-2 * mult)
+    assert sol.numevals == g["numevals"] and abs(sol.u / mult - g["I"]) < 1e-10 * abs(g["I"])
+
+
+def test_c5_band_energy_ibz_autoptr(orc):
+    """BASELINE config 5 (reduced grid for the oracle): norb=64 band-energy integrand on CubicSymIBZ, AutoPTR"""
+    n = 64
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 1, cubic=True)
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=n)
+    So = orc.Series(H, lo)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), 2 * np.pi * np.eye(3))
+    f = ab.FourierIntegrand(ab.EigenIntegrand("fermi_energy"), fs, 0.0, 0.5)
+    sol = ab.solve(ab.IntegralProblem(f, ibz), ab.PTR(npt=8))
+    w, nirr = orc.symptr_rule(8, ab.cube_automorphisms(3))
+    ref, cnt = orc.ptr_eig_sum(So, 8, 1, (0.0, 0.5), wsym=w, scale=1 / 8 ** 3)
+    assert abs(sol.u - ref) < 1e-10 * abs(ref)
+    sol = ab.solve(ab.IntegralProblem(f, ibz), ab.EvalCounter(ab.AutoPTR(nmin=6, a=1.0)), reltol=1e-3)
+    assert sol.numevals > 0 and np.isfinite(sol.u)
+
+
+def test_generic_python_integrand_copies_h_back():
+    s = lattice_series(2)
+    bz = ab.load_bz(ab.FBZ(), np.eye(2))
+    f = ab.FourierIntegrand(lambda x, a, b=0.0: a * x.s + b, s, 1.3, b=1.0)
+    assert abs(ab.solve(ab.IntegralProblem(f, bz), ab.PTR(npt=8)).u - (2 * np.pi) ** 2) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties (no oracle at this size)
+def test_c4_full_size_properties(ctx):
+    """BASELINE config 4 shape: norb=32, R in [-8,8]^3, 256^3 grid (one k3 plane here), many frequencies.
+    Properties: bit-reproducible run to run; plane sums additive; generic pivoted path == fast path;
+    Im tr G <= 0 for every frequency (causality)."""
+    n = 32
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 8)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    ext = ab.synthetic.band_extent(H)
+    z = np.linspace(-0.2 * ext, 0.2 * ext, 16) + 1j * 0.01 * ext
+    N = 256
+    # a 1/16 plane through the node-list interface keeps the test short: rows k2 < 16 of plane k3 = 5
+    i1, i2 = np.meshgrid(np.arange(N), np.arange(16), indexing="xy")
+    nodes = np.stack([i1.ravel(), i2.ravel(), np.full(i1.size, 5)], axis=1).astype(np.int32)
+    R = L.DeviceRule(ctx, S, N, nodes=nodes)
+    a = R.resolvent_sum(z)
+    b = R.resolvent_sum(z)
+    assert np.array_equal(a, b)                                   # deterministic reduction
+    assert np.all(a.imag < 0)
+    half = [L.DeviceRule(ctx, S, N, nodes=nodes[: nodes.shape[0] // 2]).resolvent_sum(z),
+            L.DeviceRule(ctx, S, N, nodes=nodes[nodes.shape[0] // 2:]).resolvent_sum(z)]
+    assert rel(half[0] + half[1], a) < 1e-12
+    ctx.set_option(L.OPT_RESOLVENT_ALGO, 1)
+    try:
+        c = R.resolvent_sum(z[:4])
+    finally:
+        ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
+    assert rel(c, a[:4]) < 1e-11
