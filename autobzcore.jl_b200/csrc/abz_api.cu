@@ -79,6 +79,7 @@ struct Nest {
 };
 
 struct Chunk { long p0, p1, r0, r1; };
+constexpr int ABZ_RETRY_PIVOTED = 1;   // internal: the unpivoted fast path saw a tiny pivot; rerun with the pivoted kernel
 
 }  // namespace
 
@@ -93,6 +94,7 @@ struct abz_ctx {
     int resolvent_algo = 0;
     size_t budget = (size_t)4096 << 20;
     int fused_small = 1;
+    bool force_generic = false;   // set while re-running a call whose fast path asked for pivoting
     DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d;
     long launches = 0;
     std::vector<cudaEvent_t> events;
@@ -271,6 +273,7 @@ int check_errflag(abz_ctx* ctx, const char* what) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (h) {
         cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->stream);
+        if ((h & 2) && !(h & 1) && !ctx->force_generic) return ABZ_RETRY_PIVOTED;
         return fail(ctx, ABZ_E_SINGULAR, std::string(what) + ": singular matrix or NaN/Inf in the integrand");
     }
     return ABZ_OK;
@@ -325,21 +328,20 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
         // sums over a materialised H: handled by the caller through small_fused_kernel<_, true>
         return fail(ctx, ABZ_E_INVALID, "internal: small-norb sums go through run_small_fused");
     }
-    // DMMA register-resident fast path (norb == 32, scalar pivots inside 8x8 blocks)
-    bool use_mma = (ctx->resolvent_algo != 1) && mma_resolvent_supported(n);
+    // DMMA register-resident fast path (norb <= 32; unpivoted block elimination with growth monitoring)
+    bool use_mma = (ctx->resolvent_algo != 1) && !ctx->force_generic && mma_resolvent_supported(n);
     if (use_mma) {
-        long ncta = 0;
-        int rc2 = mma_resolvent_partial_count(n, nk, nw, sm, &ncta);
-        if (rc2 == 0) {
+        long ncta = 0; int kper_m = 1;
+        if (mma_resolvent_plan(n, nk, nw, sm, &ncta, &kper_m) == 0) {
             if (mode == 0) {
                 CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
-                mma_resolvent_launch(H, wnode, nk, n, nw, z, sigma, 0, ctx->partial.as<double2>(), ef, ncta, ctx->stream);
-                LAUNCH_CHECK(ctx, "resolvent_mma_kernel");
+                CU(ctx, mma_resolvent_launch(H, wnode, nk, n, nw, z, sigma, 0, ctx->partial.as<double2>(), ef, ncta, kper_m, ctx->stream));
+                ctx->launches++;
                 reduce_partials_kernel<<<nw, 256, 0, ctx->stream>>>(ctx->partial.as<double2>(), ncta, nw, 1.0, ctx->acc.as<double2>());
                 LAUNCH_CHECK(ctx, "reduce_partials_kernel");
             } else {
-                mma_resolvent_launch(H, wnode, nk, n, nw, z, sigma, 1, yout, ef, ncta, ctx->stream);
-                LAUNCH_CHECK(ctx, "resolvent_mma_kernel");
+                CU(ctx, mma_resolvent_launch(H, wnode, nk, n, nw, z, sigma, 1, yout, ef, ncta, kper_m, ctx->stream));
+                ctx->launches++;
             }
             return ABZ_OK;
         }
@@ -731,7 +733,7 @@ int32_t abz_rule_copy_out(abz_ctx* ctx, abz_rule_t rid, double* Hk, double* kfra
     return ABZ_OK;
 }
 
-int32_t abz_rule_resolvent_sum(abz_ctx* ctx, abz_rule_t rid, int32_t fkind, int32_t nw, const double* z,
+static int32_t abz_rule_resolvent_sum_impl(abz_ctx* ctx, abz_rule_t rid, int32_t fkind, int32_t nw, const double* z,
                                const double* sigma, double scale, double* out) {
     if (!ctx) return ABZ_E_INVALID;
     Rule* r = get_rule(ctx, rid);
@@ -791,6 +793,18 @@ int32_t abz_rule_resolvent_sum(abz_ctx* ctx, abz_rule_t rid, int32_t fkind, int3
     for (int w = 0; w < nw; w++) { out[2 * w] = scale * h[w].x; out[2 * w + 1] = scale * h[w].y; }
     return ABZ_OK;
 }
+
+int32_t abz_rule_resolvent_sum(abz_ctx* ctx, abz_rule_t rid, int32_t fkind, int32_t nw, const double* z,
+                               const double* sigma, double scale, double* out) {
+    int32_t rc = abz_rule_resolvent_sum_impl(ctx, rid, fkind, nw, z, sigma, scale, out);
+    if (rc == ABZ_RETRY_PIVOTED) {
+        ctx->force_generic = true;
+        rc = abz_rule_resolvent_sum_impl(ctx, rid, fkind, nw, z, sigma, scale, out);
+        ctx->force_generic = false;
+    }
+    return rc;
+}
+
 
 static size_t eig_smem_bytes(int n, int threads) {
     int np = (n + 1) & ~1, npair = np / 2;
@@ -928,7 +942,7 @@ int32_t abz_points_eval(abz_ctx* ctx, abz_series_t sid, int64_t npts, const doub
     return ABZ_OK;
 }
 
-int32_t abz_points_resolvent(abz_ctx* ctx, abz_series_t sid, int64_t npts, const double* k, int32_t fkind, int32_t nw,
+static int32_t abz_points_resolvent_impl(abz_ctx* ctx, abz_series_t sid, int64_t npts, const double* k, int32_t fkind, int32_t nw,
                              const double* z, const double* sigma, double* y) {
     if (!ctx) return ABZ_E_INVALID;
     Series* s = get_series(ctx, sid);
@@ -950,6 +964,18 @@ int32_t abz_points_resolvent(abz_ctx* ctx, abz_series_t sid, int64_t npts, const
     CU(ctx, cudaMemcpyAsync(y, ctx->tmp_b.p, (size_t)npts * nw * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
     return check_errflag(ctx, "abz_points_resolvent");
 }
+
+int32_t abz_points_resolvent(abz_ctx* ctx, abz_series_t sid, int64_t npts, const double* k, int32_t fkind, int32_t nw,
+                             const double* z, const double* sigma, double* y) {
+    int32_t rc = abz_points_resolvent_impl(ctx, sid, npts, k, fkind, nw, z, sigma, y);
+    if (rc == ABZ_RETRY_PIVOTED) {
+        ctx->force_generic = true;
+        rc = abz_points_resolvent_impl(ctx, sid, npts, k, fkind, nw, z, sigma, y);
+        ctx->force_generic = false;
+    }
+    return rc;
+}
+
 
 // ---- IAI nest arena -------------------------------------------------------------------------------
 int32_t abz_nest_create(abz_ctx* ctx, abz_series_t sid, int32_t ndim, int64_t cap2, int64_t cap1, abz_nest_t* out) {
@@ -1037,7 +1063,7 @@ int32_t abz_nest_contract2(abz_ctx* ctx, abz_nest_t nid, int64_t n, const double
     return ABZ_OK;
 }
 
-int32_t abz_nest_eval(abz_ctx* ctx, abz_nest_t nid, int64_t npts, const double* x1, const int64_t* slot1, int32_t fkind,
+static int32_t abz_nest_eval_impl(abz_ctx* ctx, abz_nest_t nid, int64_t npts, const double* x1, const int64_t* slot1, int32_t fkind,
                       const double* z, const double* sigma, double* y) {
     if (!ctx) return ABZ_E_INVALID;
     Nest* nst = get_nest(ctx, nid);
@@ -1086,6 +1112,18 @@ int32_t abz_nest_eval(abz_ctx* ctx, abz_nest_t nid, int64_t npts, const double* 
     CU(ctx, cudaMemcpyAsync(y, yd, (size_t)npts * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
     return check_errflag(ctx, "abz_nest_eval");
 }
+
+int32_t abz_nest_eval(abz_ctx* ctx, abz_nest_t nid, int64_t npts, const double* x1, const int64_t* slot1, int32_t fkind,
+                      const double* z, const double* sigma, double* y) {
+    int32_t rc = abz_nest_eval_impl(ctx, nid, npts, x1, slot1, fkind, z, sigma, y);
+    if (rc == ABZ_RETRY_PIVOTED) {
+        ctx->force_generic = true;
+        rc = abz_nest_eval_impl(ctx, nid, npts, x1, slot1, fkind, z, sigma, y);
+        ctx->force_generic = false;
+    }
+    return rc;
+}
+
 
 // ---- NCCL through dlopen ----------------------------------------------------------------------------
 typedef struct { char internal[128]; } abz_nccl_uid;

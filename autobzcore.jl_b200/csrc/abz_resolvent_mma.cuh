@@ -1,10 +1,286 @@
-// K3-fast: register-resident blocked resolvent trace on the FP64 tensor cores (DMMA).
-// (placeholder interface; implemented below the generic path)
+// K3-fast: tr[(z - H(k) - Sigma_w)^-1] with the whole norb x norb complex matrix resident in the
+// registers of ONE warp, in the FP64 tensor-core accumulator layout, and every O(n^3) step done by
+// DMMA (mma.sync.m8n8k4.f64).  One warp per (k, w) matrix, norb <= 32 (padded to a multiple of 8).
+//
+// Layout: the matrix is an NB x NB grid of 8x8 complex blocks; lane = 4g + q holds, of every block,
+// row g, columns 2q and 2q+1 (re and im): the C/D fragment layout of DMMA.  Two facts make the
+// register-only formulation cheap:
+//   * a block in C layout IS a valid A operand: contracting over k' = 2q + t (t = 0,1 the two k-slabs)
+//     instead of k = q + 4t is just a permutation of the summation index, so the left operand needs no
+//     data movement at all;
+//   * the right operand (B fragment: row 2q + t, column g) is the same permutation of the block's
+//     transpose, reached with 4 64-bit shuffles per block (a perfect matching of the lane exchange
+//     graph), and the same fragment also gives tr(X Y) = sum_lanes X_C[t] * Y_Bfrag[t] for free.
+//
+// Algorithm (block LU without inter-block pivoting + trace of the inverse from the factors):
+//   for s: D_s = inv(S_s) (8x8 in-register Gauss-Jordan), L_is = A_is D_s, X_sj = D_s U_sj,
+//          A_ij -= L_is U_sj;                      A = L~ U~,  U~ = diag(S)(I + X~)
+//   V = U~^-1 by back substitution on blocks, M = L~^-1 by forward substitution,
+//   tr A^-1 = sum_s tr D_s + sum_{i<j} tr(V_ij M_ji).
+// 40 block products (320 DMMA) for norb = 32 against the 64 of a full inversion.
+// Pivoting: A = z - H - Sigma with a positive-definite anti-Hermitian part (Im z > 0, causal Sigma) has
+// every leading principal minor nonsingular (numerical range argument), so elimination without row
+// exchanges is safe; the kernel monitors the smallest pivot against max|a_ij| and raises a flag when
+// the smallest pivot falls below 2e-3 max|a_ij|, on which the host reruns the call with the pivoted Gauss-Jordan kernel.
 #pragma once
 #include "abz_common.cuh"
 
 namespace abz {
-inline bool mma_resolvent_supported(int n) { (void)n; return false; }
-inline int mma_resolvent_partial_count(int n, long nk, int nw, long sm, long* ncta) { (void)n; (void)nk; (void)nw; (void)sm; *ncta = 0; return -1; }
-inline void mma_resolvent_launch(const double2*, const double*, long, int, int, const double2*, const double2*, int, double2*, int*, long, cudaStream_t) {}
+
+struct BFrag { double r[2], i[2]; };
+
+// C-layout block (x*0: column 2q, x*1: column 2q+1 of row g) -> B fragment b[t] = X[2q + t][g]
+__device__ __forceinline__ BFrag to_bfrag(double xr0, double xr1, double xi0, double xi1, int src0, int src1, bool par) {
+    // round a: this lane presents slot (a ^ par); it receives the value for t = a ^ par from lane src_a
+    double pr0 = par ? xr1 : xr0, pr1 = par ? xr0 : xr1;
+    double pi0 = par ? xi1 : xi0, pi1 = par ? xi0 : xi1;
+    double vr0 = __shfl_sync(0xffffffffu, pr0, src0), vr1 = __shfl_sync(0xffffffffu, pr1, src1);
+    double vi0 = __shfl_sync(0xffffffffu, pi0, src0), vi1 = __shfl_sync(0xffffffffu, pi1, src1);
+    BFrag b;
+    b.r[0] = par ? vr1 : vr0; b.r[1] = par ? vr0 : vr1;
+    b.i[0] = par ? vi1 : vi0; b.i[1] = par ? vi0 : vi1;
+    return b;
+}
+
+// C += sgn * A * B (complex 8x8x8): A in C layout, B as fragment.  NEG = true subtracts.
+template <bool NEG>
+__device__ __forceinline__ void bmm(double& cr0, double& cr1, double& ci0, double& ci1, double ar0, double ar1, double ai0,
+                                    double ai1, const BFrag& b) {
+    const double pr0 = NEG ? -ar0 : ar0, pr1 = NEG ? -ar1 : ar1;     // +-Ar
+    const double pi0 = NEG ? -ai0 : ai0, pi1 = NEG ? -ai1 : ai1;     // +-Ai
+    const double mi0 = NEG ? ai0 : -ai0, mi1 = NEG ? ai1 : -ai1;     // -+Ai
+    // Cr += (+-Ar) Br + (-+Ai) Bi ; Ci += (+-Ar) Bi + (+-Ai) Br
+    dmma884(cr0, cr1, pr0, b.r[0]);
+    dmma884(ci0, ci1, pr0, b.i[0]);
+    dmma884(cr0, cr1, pr1, b.r[1]);
+    dmma884(ci0, ci1, pr1, b.i[1]);
+    dmma884(cr0, cr1, mi0, b.i[0]);
+    dmma884(ci0, ci1, pi0, b.r[0]);
+    dmma884(cr0, cr1, mi1, b.i[1]);
+    dmma884(ci0, ci1, pi1, b.r[1]);
+}
+
+// in-place inverse of an 8x8 complex block in C layout by Gauss-Jordan without row exchanges;
+// minpiv tracks min_p |pivot_p|_1
+__device__ __forceinline__ void inv8(double& xr0, double& xr1, double& xi0, double& xi1, int lane, double& minpiv) {
+    const int g = lane >> 2, q = lane & 3, quad = lane & ~3;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const int sg = p & 1, qp = p >> 1;
+        // pivot row restricted to my two columns
+        double pr0 = __shfl_sync(0xffffffffu, xr0, 4 * p + q), pr1 = __shfl_sync(0xffffffffu, xr1, 4 * p + q);
+        double pi0 = __shfl_sync(0xffffffffu, xi0, 4 * p + q), pi1 = __shfl_sync(0xffffffffu, xi1, 4 * p + q);
+        // pivot a_pp (from the pivot-row values held at quad lane qp) and my row's multiplier a_gp
+        double ppr = __shfl_sync(0xffffffffu, sg ? pr1 : pr0, quad | qp);
+        double ppi = __shfl_sync(0xffffffffu, sg ? pi1 : pi0, quad | qp);
+        double fr = __shfl_sync(0xffffffffu, sg ? xr1 : xr0, quad | qp);
+        double fi = __shfl_sync(0xffffffffu, sg ? xi1 : xi0, quad | qp);
+        minpiv = fmin(minpiv, fabs(ppr) + fabs(ppi));
+        const double dinv = 1.0 / (ppr * ppr + ppi * ppi);
+        const double rr = ppr * dinv, ri = -ppi * dinv;              // 1 / pivot
+        // scaled pivot row (a_pp := 1 before scaling)
+        const bool pc = (q == qp);
+        if (pc) { if (sg) { pr1 = 1.0; pi1 = 0.0; } else { pr0 = 1.0; pi0 = 0.0; } }
+        const double sr0 = pr0 * rr - pi0 * ri, si0 = pr0 * ri + pi0 * rr;
+        const double sr1 = pr1 * rr - pi1 * ri, si1 = pr1 * ri + pi1 * rr;
+        if (g == p) {
+            xr0 = sr0; xi0 = si0; xr1 = sr1; xi1 = si1;
+        } else {
+            if (pc) { if (sg) { xr1 = 0.0; xi1 = 0.0; } else { xr0 = 0.0; xi0 = 0.0; } }
+            xr0 = fma(-fr, sr0, xr0); xr0 = fma(fi, si0, xr0);
+            xi0 = fma(-fr, si0, xi0); xi0 = fma(-fi, sr0, xi0);
+            xr1 = fma(-fr, sr1, xr1); xr1 = fma(fi, si1, xr1);
+            xi1 = fma(-fr, si1, xi1); xi1 = fma(-fi, sr1, xi1);
+        }
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], double (&R1)[NB][NB], double (&I0)[NB][NB],
+                                                      double (&I1)[NB][NB], int lane, double& minpiv) {
+    const int g = lane >> 2, q = lane & 3;
+    const bool par = g & 1;
+    const int src0 = 4 * (2 * q + (par ? 1 : 0)) + (g >> 1);
+    const int src1 = 4 * (2 * q + (par ? 0 : 1)) + (g >> 1);
+    // ---- block LU
+#pragma unroll
+    for (int s = 0; s < NB; s++) {
+        inv8(R0[s][s], R1[s][s], I0[s][s], I1[s][s], lane, minpiv);      // D_s
+        if (s == NB - 1) break;
+        const BFrag bD = to_bfrag(R0[s][s], R1[s][s], I0[s][s], I1[s][s], src0, src1, par);
+#pragma unroll
+        for (int i = s + 1; i < NB; i++) {                               // L_is = A_is D_s
+            double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
+            bmm<false>(cr0, cr1, ci0, ci1, R0[i][s], R1[i][s], I0[i][s], I1[i][s], bD);
+            R0[i][s] = cr0; R1[i][s] = cr1; I0[i][s] = ci0; I1[i][s] = ci1;
+        }
+#pragma unroll
+        for (int j = s + 1; j < NB; j++) {
+            const BFrag bU = to_bfrag(R0[s][j], R1[s][j], I0[s][j], I1[s][j], src0, src1, par);
+            {                                                            // X_sj = D_s U_sj (replaces U_sj)
+                double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
+                bmm<false>(cr0, cr1, ci0, ci1, R0[s][s], R1[s][s], I0[s][s], I1[s][s], bU);
+                R0[s][j] = cr0; R1[s][j] = cr1; I0[s][j] = ci0; I1[s][j] = ci1;
+            }
+#pragma unroll
+            for (int i = s + 1; i < NB; i++)                             // A_ij -= L_is U_sj
+                bmm<true>(R0[i][j], R1[i][j], I0[i][j], I1[i][j], R0[i][s], R1[i][s], I0[i][s], I1[i][s], bU);
+        }
+    }
+    // ---- trace of the diagonal blocks D_s
+    double tr = 0.0, ti = 0.0;
+#pragma unroll
+    for (int s = 0; s < NB; s++) {
+        if (2 * q == g) { tr += R0[s][s]; ti += I0[s][s]; }
+        if (2 * q + 1 == g) { tr += R1[s][s]; ti += I1[s][s]; }
+    }
+    // ---- V = U~^-1 (strict upper blocks, in place over X), column by column from the right
+#pragma unroll
+    for (int j = NB - 1; j >= 1; j--) {
+        const BFrag bD = to_bfrag(R0[j][j], R1[j][j], I0[j][j], I1[j][j], src0, src1, par);
+        BFrag bV[NB];
+#pragma unroll
+        for (int i = j - 1; i >= 0; i--) {
+            double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
+            bmm<true>(cr0, cr1, ci0, ci1, R0[i][j], R1[i][j], I0[i][j], I1[i][j], bD);              // -X_ij D_j
+#pragma unroll
+            for (int t = i + 1; t < j; t++)
+                bmm<true>(cr0, cr1, ci0, ci1, R0[i][t], R1[i][t], I0[i][t], I1[i][t], bV[t]);       // -X_it V_tj
+            R0[i][j] = cr0; R1[i][j] = cr1; I0[i][j] = ci0; I1[i][j] = ci1;
+            if (i > 0) bV[i] = to_bfrag(cr0, cr1, ci0, ci1, src0, src1, par);
+        }
+    }
+    // ---- M = L~^-1 (strict lower blocks, in place over L), column by column from the left, and
+    //      tr += sum_{j<i} tr(V_ji M_ij) through the B fragment of M_ij
+#pragma unroll
+    for (int j = 0; j < NB - 1; j++) {
+        BFrag bM[NB];
+#pragma unroll
+        for (int i = j + 1; i < NB; i++) {
+            double cr0 = -R0[i][j], cr1 = -R1[i][j], ci0 = -I0[i][j], ci1 = -I1[i][j];
+#pragma unroll
+            for (int t = j + 1; t < i; t++)
+                bmm<true>(cr0, cr1, ci0, ci1, R0[i][t], R1[i][t], I0[i][t], I1[i][t], bM[t]);       // -L_it M_tj
+            R0[i][j] = cr0; R1[i][j] = cr1; I0[i][j] = ci0; I1[i][j] = ci1;
+            bM[i] = to_bfrag(cr0, cr1, ci0, ci1, src0, src1, par);
+            // V_ji[g][2q+t] * M_ij[2q+t][g]
+            tr += R0[j][i] * bM[i].r[0] - I0[j][i] * bM[i].i[0] + R1[j][i] * bM[i].r[1] - I1[j][i] * bM[i].i[1];
+            ti += R0[j][i] * bM[i].i[0] + I0[j][i] * bM[i].r[0] + R1[j][i] * bM[i].i[1] + I1[j][i] * bM[i].r[1];
+        }
+    }
+    return make_double2(warp_sum(tr), warp_sum(ti));
+}
+
+constexpr int MMA_WARPS = 8;
+
+// CTA c handles k-points [c*kper, (c+1)*kper) x all nw frequencies; warp w takes the (k, w) pairs
+// i = w, w + 8, ... of that chunk.  mode 0: outp[c*nw + w] = sum_k wnode_k tr ; mode 1: outp[k*nw + w] = tr
+// shared: acc[MMA_WARPS][nw] double2
+template <int NB>
+__global__ void __launch_bounds__(MMA_WARPS * 32, 1)
+resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ wnode, long nk, int n, int nw,
+                     const double2* __restrict__ z, const double2* __restrict__ sigma, int kper, int mode,
+                     double2* __restrict__ outp, int* __restrict__ errflag) {
+    extern __shared__ double2 mma_acc[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    double2* acc = mma_acc + (long)warp * nw;
+    if (mode == 0)
+        for (int w = lane; w < nw; w += 32) acc[w] = make_double2(0.0, 0.0);
+    __syncwarp();
+    const long k0 = (long)blockIdx.x * kper;
+    const long k1 = k0 + kper < nk ? k0 + kper : nk;
+    const long npairs = (k1 - k0) * nw;
+    const int npad = 8 * NB - n;
+    for (long it = warp; it < npairs; it += MMA_WARPS) {
+        const long k = k0 + it / nw;
+        const int w = (int)(it % nw);
+        const double2* Hk = H + k * (long)n * n;
+        const double2* sg = sigma ? sigma + (long)w * n * n : nullptr;
+        const double2 zz = z[w];
+        double R0[NB][NB], R1[NB][NB], I0[NB][NB], I1[NB][NB];
+        double amax = 0.0;
+#pragma unroll
+        for (int bj = 0; bj < NB; bj++)
+#pragma unroll
+            for (int bi = 0; bi < NB; bi++) {
+                const int row = 8 * bi + g, c0 = 8 * bj + 2 * q, c1 = c0 + 1;
+                double2 a0 = make_double2(0.0, 0.0), a1 = a0;
+                if (row < n && c0 < n) {
+                    a0 = Hk[row + (long)c0 * n];
+                    if (sg) { double2 s0 = sg[row + (long)c0 * n]; a0.x += s0.x; a0.y += s0.y; }
+                }
+                if (row < n && c1 < n) {
+                    a1 = Hk[row + (long)c1 * n];
+                    if (sg) { double2 s1 = sg[row + (long)c1 * n]; a1.x += s1.x; a1.y += s1.y; }
+                }
+                a0.x = -a0.x; a0.y = -a0.y; a1.x = -a1.x; a1.y = -a1.y;
+                if (row == c0) { if (row < n) { a0.x += zz.x; a0.y += zz.y; } else { a0.x = 1.0; a0.y = 0.0; } }
+                if (row == c1) { if (row < n) { a1.x += zz.x; a1.y += zz.y; } else { a1.x = 1.0; a1.y = 0.0; } }
+                R0[bi][bj] = a0.x; I0[bi][bj] = a0.y; R1[bi][bj] = a1.x; I1[bi][bj] = a1.y;
+                amax = fmax(amax, fmax(fabs(a0.x) + fabs(a0.y), fabs(a1.x) + fabs(a1.y)));
+            }
+        double minpiv = 1e300;
+        double2 t = warp_trace_inverse<NB>(R0, R1, I0, I1, lane, minpiv);
+        t.x -= (double)npad;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        if (lane == 0) {
+            if (!(minpiv > 2e-3 * amax) || !(isfinite(t.x) && isfinite(t.y))) atomicOr(errflag, 2);   // ask for the pivoted path
+            if (mode == 0) {
+                const double wt = wnode ? wnode[k] : 1.0;
+                acc[w].x += wt * t.x; acc[w].y += wt * t.y;
+            } else {
+                outp[k * nw + w] = t;
+            }
+        }
+    }
+    if (mode == 0) {
+        __syncthreads();
+        for (int w = threadIdx.x; w < nw; w += MMA_WARPS * 32) {
+            double sx = 0.0, sy = 0.0;
+#pragma unroll
+            for (int wp = 0; wp < MMA_WARPS; wp++) { double2 v = mma_acc[(long)wp * nw + w]; sx += v.x; sy += v.y; }
+            outp[(long)blockIdx.x * nw + w] = make_double2(sx, sy);
+        }
+    }
+}
+
+inline bool mma_resolvent_supported(int n) { return n >= 4 && n <= 32; }
+
+inline int mma_resolvent_plan(int n, long nk, int nw, long sm, long* ncta, int* kper) {
+    if (!mma_resolvent_supported(n)) return -1;
+    if ((size_t)nw * MMA_WARPS * sizeof(double2) > 160 * 1024) return -1;
+    long target = sm * 4;
+    long kp = (nk + target - 1) / target;
+    // keep every warp busy: at least ~4 matrices per warp per CTA
+    while (kp * nw < 4L * MMA_WARPS && kp < nk) kp++;
+    if (kp < 1) kp = 1;
+    *kper = (int)kp;
+    *ncta = (nk + kp - 1) / kp;
+    return 0;
+}
+
+inline cudaError_t mma_resolvent_launch(const double2* H, const double* wnode, long nk, int n, int nw, const double2* z,
+                                        const double2* sigma, int mode, double2* outp, int* errflag, long ncta, int kper,
+                                        cudaStream_t stream) {
+    const int NBv = (n + 7) / 8;
+    size_t smem = (size_t)nw * MMA_WARPS * sizeof(double2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(resolvent_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(resolvent_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(resolvent_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(resolvent_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
+    switch (NBv) {
+        case 1: resolvent_mma_kernel<1><<<(unsigned)ncta, MMA_WARPS * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag); break;
+        case 2: resolvent_mma_kernel<2><<<(unsigned)ncta, MMA_WARPS * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag); break;
+        case 3: resolvent_mma_kernel<3><<<(unsigned)ncta, MMA_WARPS * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag); break;
+        default: resolvent_mma_kernel<4><<<(unsigned)ncta, MMA_WARPS * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag); break;
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace abz

@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the AutoBZCore hot path on B200 (contract: see the build prompt).
+
+Workload (config.workload): BASELINE.json config 4 — synthetic Wannier Hamiltonian norb=32, R in [-8,8]^3
+(M=17 per dimension), PTR 256^3 k-grid, 128-point frequency sweep, integrand tr[(w + i eta - H(k))^-1].
+One "step" = each rank evaluates its k3 slab of `--planes` planes (default 32 = 256/8, so that N=8 ranks
+cover the whole 256^3 grid; weak scaling) for all 128 frequencies: Fourier stages 3/2/1 + resolvent + weighted
+k-sum.  metric = k-points/sec (H(k)+resolvent), whole-job aggregate over ranks.
+
+  value : device-resident (H_R already in HBM; rule built), CUDA events on the library's stream
+  e2e   : the same through the public API (IntegralSolver + batchsolve) with HOST buffers: H_R uploaded,
+          rule built, sums, results read back, partial sums all-reduced — every step
+  --impl reference : the CPU restatement of the reference path (oracle, OpenMP over k3 planes like the
+          reference's Threads.@threads loop) on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NORB, RMAX, NPT, NW = 32, 8, 256, 128
+METRIC = "k-points/sec (H(k)+resolvent)"
+
+
+def workload_inputs():
+    import autobz_b200 as ab
+    H, lo = ab.synthetic.wannier_hamiltonian(NORB, RMAX)
+    ext = ab.synthetic.band_extent(H)
+    # the spectrum of the synthetic H(k) lies well inside [-ext, ext]; sweep the central part, eta = 1e-2 * bandwidth scale
+    bw = 0.25 * ext
+    omegas = np.linspace(-bw, bw, NW)
+    eta = 1e-2 * 2 * bw
+    return H, lo, omegas, eta
+
+
+def flops_per_node(n=NORB, M=2 * RMAX + 1, N=NPT, nw=NW):
+    f_four = 8.0 * n * n * M * (1 + M / N + (M / N) ** 2)
+    f_res = 8.0 * n ** 3 * nw
+    return f_four, f_res
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); out["sm_max_mhz"] = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            busy = [x for x in sm if x > 0.5 * max(sm)]
+            out["sm_mhz"] = float(np.median(busy))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def measure_fp64_peak():
+    """cuBLAS ZGEMM 4096^3 burst (the FP64 denominator MEASURED_PEAKS.json lacks)."""
+    import torch
+    a = torch.randn(4096, 4096, dtype=torch.complex128, device="cuda")
+    b = torch.randn(4096, 4096, dtype=torch.complex128, device="cuda")
+    c = torch.empty_like(a)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 8.0 * 4096 ** 3 / best * 1e-9
+
+
+def cpu_sample(threads=None, target_s=15.0):
+    """CPU restatement on a bounded sample: `threads` k3 planes (one per thread, as the reference threads the
+    outermost k3 loop, src/fourier.jl:156) x r k2-rows x 256 k1 x 128 frequencies."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    orc.build()
+    H, lo, omegas, eta = workload_inputs()
+    S = orc.Series(H, lo)
+    z = omegas + 1j * eta
+    cores = threads or os.cpu_count() or 1
+    planes = min(cores, NPT)
+    # calibrate on a small sub-sample (first 16 frequencies, one row per plane)
+    t0 = time.time()
+    orc.ptr_sum(S, NPT, z[:16], k3_lo=0, k3_hi=planes, k2_lo=0, k2_hi=1, nthreads=cores)
+    t_cal = time.time() - t0
+    per_row = t_cal * (NW / 16.0)
+    rows = int(max(1, min(NPT, target_s / max(per_row, 1e-9))))
+    t0 = time.time()
+    orc.ptr_sum(S, NPT, z, k3_lo=0, k3_hi=planes, k2_lo=0, k2_hi=rows, nthreads=cores)
+    t = time.time() - t0
+    nodes = planes * rows * NPT
+    return {"value": nodes / t, "unit": "k-points/s", "cores": cores, "kind": "port",
+            "sample": f"{planes} k3-planes x {rows} k2-rows x {NPT} k1 = {nodes} k-points x {NW} freqs of the C4 workload in {t:.1f} s "
+                      f"(C/OpenMP restatement of the AutoBZCore 0.3.8 path, not Julia)"}, t
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    vals, times = [], []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb, t = cpu_sample(target_s=args.ref_seconds)
+        if i >= args.warmup:
+            vals.append(cb["value"]); times.append(t)
+    v = float(np.mean(vals))
+    cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "k-points/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4: synthetic Wannier H norb={NORB}, R in [-{RMAX},{RMAX}]^3, PTR {NPT}^3, {NW} freqs; bounded CPU sample per step"},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": "k-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--planes", type=int, default=NPT // 8, help="k3 planes per rank per step")
+    ap.add_argument("--ref-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--algo", type=int, default=0, help="resolvent algorithm: 0 auto, 1 generic, 2 DMMA")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import autobz_b200 as ab
+    from autobz_b200 import _lib as L
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = ab.default_context(local)
+    ctx.set_option(L.OPT_RESOLVENT_ALGO, args.algo)
+    H, lo, omegas, eta = workload_inputs()
+    z = omegas + 1j * eta
+    planes = args.planes
+    k3_lo = (rank * planes) % NPT
+    k3_hi = k3_lo + planes
+    nodes_rank = planes * NPT * NPT
+    fp64_peak = measure_fp64_peak() if rank == 0 else None
+
+    # ---------------- device-resident arm: H_R in HBM, rule built, time the sums
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    R = L.DeviceRule(ctx, S, NPT, k3_lo=k3_lo, k3_hi=k3_hi)
+    for _ in range(args.warmup):
+        R.resolvent_sum(z, scale=1.0 / NPT ** 3)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launch_count
+    ev_eval = ev_mat = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        part = R.resolvent_sum(z, scale=1.0 / NPT ** 3)
+        a, b = ctx.last_timings()
+        ev_eval += a; ev_mat += b
+    barrier()
+    t_dev = time.perf_counter() - t0
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if sampler else None
+    tt = torch.tensor([t_dev, (ev_eval + ev_mat) * 1e-3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev_max, t_events_max = float(tt[0]), float(tt[1])
+    R.close(); S.close()
+
+    # ---------------- end-to-end arm through the public API with host buffers
+    shard = ab.Shard(rank, world, ab.torch_allreduce(torch.device("cuda", local))) if world > 1 else ab.Shard()
+    # weak scaling: this run's grid is the slab set [0, world*planes) of the 256^3 grid; expressed through the public API
+    # as a PTR rule whose k3 range is sharded over ranks.  The full-grid API shards npt planes over nranks, so use a
+    # virtual world of NPT/planes ranks of which the first `world` exist.
+    vworld = max(1, NPT // planes)
+
+    class _VShard(ab.Shard):
+        def __init__(self):
+            super().__init__(rank, vworld, None)
+
+        def allreduce(self, arr):
+            return shard.allreduce(arr)
+
+    bz = ab.load_bz(ab.FBZ(), 2 * np.pi * np.eye(3))
+    plist = [{"omega": float(w)} for w in omegas]
+
+    def e2e_step():
+        fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=NORB)            # host buffer -> uploaded inside
+        f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=eta)
+        solver = ab.IntegralSolver(f, bz, ab.PTR(npt=NPT), shard=_VShard())
+        out = ab.batchsolve(solver, plist)
+        solver.cache.cacheval["rule"].close()
+        fs.drop_device()
+        return out
+
+    for _ in range(min(args.warmup, 1)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g = e2e_step()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e_max = float(te[0])
+
+    if rank == 0:
+        total_nodes = nodes_rank * world * args.steps
+        value = total_nodes / t_dev_max
+        e2e_val = total_nodes / t_e2e_max
+        f_four, f_res = flops_per_node()
+        # dominant kernel: the resolvent (matfun phase).  One launch = one chunk of nodes x 128 frequencies.
+        mat_s = ev_mat * 1e-3 / args.steps
+        achieved = f_res * nodes_rank / mat_s * 1e-12
+        roof = {"bound": "tensor", "kernel": "resolvent (FP64, DMMA/DFMA pipe)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp64_peak, "traffic": None,
+                "peak_source": "cuBLAS ZGEMM 4096^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "algorithmic_flops_per_kpoint": {"fourier": f_four, "resolvent": f_res},
+                "eval_ms_per_step": ev_eval / args.steps, "matfun_ms_per_step": ev_mat / args.steps}
+        cb = None
+        if not args.no_cpu_baseline:
+            cb, _ = cpu_sample(target_s=args.ref_seconds)
+        line = {"metric": METRIC, "value": value, "unit": "k-points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C4: synthetic Wannier H norb={NORB}, R in [-{RMAX},{RMAX}]^3 (M=17), PTR {NPT}^3 grid, {NW}-point frequency sweep; "
+                                       f"step = k3 slab of {planes} planes per rank (x{world} ranks; 8 ranks = whole grid)",
+                           "kpoints_per_step": nodes_rank * world, "k_omega_evals_per_sec": value * NW,
+                           "l2": "inputs larger than L2 (H(k) chunk 1-4 GB per pass)", "parallelism": f"k3-slab x{world}",
+                           "resolvent_algo": args.algo, "device_event_ms_per_step": 1e3 * t_events_max / args.steps},
+                "roofline": roof, "cpu_baseline": cb,
+                "e2e": {"value": e2e_val, "unit": "k-points/s", "h2d_bytes_per_step": int(H.nbytes + z.nbytes), "d2h_bytes_per_step": int(NW * 16),
+                        "ms_per_step": 1e3 * t_e2e_max / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "check": {"G_first": [float(g[0].real), float(g[0].imag)]}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -335,8 +335,8 @@ static int orc_node_values(const zc* H, int n, int fkind, int nw, const zc* z, c
  * nthreads == 1 reproduces the strictly sequential sum; with threads, per-plane partial sums
  * are added in k3 order (deterministic for any thread count).
  * ------------------------------------------------------------------------------------------- */
-int orc_ptr_sum(const double* coeffs, int n, const int* M, const int* lo, const double* period,
-                int N, int k3_lo, int k3_hi, int fkind, int nw, const double* zin, const double* sigma_in,
+int orc_ptr_sum_rows(const double* coeffs, int n, const int* M, const int* lo, const double* period,
+                int N, int k3_lo, int k3_hi, int k2_lo, int k2_hi, int fkind, int nw, const double* zin, const double* sigma_in,
                 double scale, double* out, int nthreads) {
     if (n < 1 || N < 1 || k3_lo < 0 || k3_hi > N || k3_lo > k3_hi || nw < 1) return ORC_E_ARG;
     orc_series s; orc_series_fill(&s, coeffs, n, M, lo, period);
@@ -362,7 +362,7 @@ int orc_ptr_sum(const double* coeffs, int n, const int* M, const int* lo, const 
         for (int i3 = k3_lo; i3 < k3_hi; i3++) {
             zc* acc = psum + (long)(i3 - k3_lo) * nw;
             orc_contract(s.C, r2, M[2], lo[2], period[2], period[2] * ((double)i3 / N), c2);
-            for (int i2 = 0; i2 < N; i2++) {
+            for (int i2 = k2_lo; i2 < k2_hi; i2++) {
                 orc_contract(c2, r1, M[1], lo[1], period[1], period[1] * ((double)i2 / N), c1);
                 for (int i1 = 0; i1 < N; i1++) {
                     orc_contract(c1, nn, M[0], lo[0], period[0], period[0] * ((double)i1 / N), h);
@@ -381,6 +381,12 @@ int orc_ptr_sum(const double* coeffs, int n, const int* M, const int* lo, const 
     }
     free(psum);
     return err ? ORC_E_NAN : ORC_OK;
+}
+
+int orc_ptr_sum(const double* coeffs, int n, const int* M, const int* lo, const double* period,
+                int N, int k3_lo, int k3_hi, int fkind, int nw, const double* zin, const double* sigma_in,
+                double scale, double* out, int nthreads) {
+    return orc_ptr_sum_rows(coeffs, n, M, lo, period, N, k3_lo, k3_hi, 0, N, fkind, nw, zin, sigma_in, scale, out, nthreads);
 }
 
 /* ---------------------------------------------------------------------------------------------

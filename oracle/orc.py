@@ -93,7 +93,7 @@ def eval_points(s, k):
     return H
 
 
-def ptr_sum(s, N, zs=None, sigma=None, fkind=0, scale=None, k3_lo=0, k3_hi=None, nthreads=0):
+def ptr_sum(s, N, zs=None, sigma=None, fkind=0, scale=None, k3_lo=0, k3_hi=None, nthreads=0, k2_lo=0, k2_hi=None):
     """scale * sum_k f(H(k)) over the full N^3 PTR grid planes [k3_lo, k3_hi); default scale 1/N^3."""
     k3_hi = N if k3_hi is None else k3_hi
     z = _z(0.0 if zs is None else zs)
@@ -101,8 +101,9 @@ def ptr_sum(s, N, zs=None, sigma=None, fkind=0, scale=None, k3_lo=0, k3_hi=None,
     sg, sgp = _sigma(sigma, s.n, nw)
     out = np.zeros(nw, dtype=np.complex128)
     scale = 1.0 / N ** 3 if scale is None else scale
-    rc = lib().orc_ptr_sum(*s.args(), C.c_int(N), C.c_int(k3_lo), C.c_int(k3_hi), C.c_int(fkind), C.c_int(nw),
-                           _dp(z), sgp, C.c_double(scale), _dp(out), C.c_int(nthreads))
+    k2_hi = N if k2_hi is None else k2_hi
+    rc = lib().orc_ptr_sum_rows(*s.args(), C.c_int(N), C.c_int(k3_lo), C.c_int(k3_hi), C.c_int(k2_lo), C.c_int(k2_hi),
+                                C.c_int(fkind), C.c_int(nw), _dp(z), sgp, C.c_double(scale), _dp(out), C.c_int(nthreads))
     if rc:
         raise FloatingPointError("oracle: singular matrix / NaN in integrand")
     return out
