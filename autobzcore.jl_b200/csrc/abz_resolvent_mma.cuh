@@ -23,6 +23,7 @@
 // exchanges is safe; the kernel monitors the smallest pivot against max|a_ij| and raises a flag when
 // the smallest pivot falls below 2e-3 max|a_ij|, on which the host reruns the call with the pivoted Gauss-Jordan kernel.
 #pragma once
+#include <cstdlib>
 #include "abz_common.cuh"
 
 namespace abz {
@@ -60,53 +61,70 @@ __device__ __forceinline__ void bmm(double& cr0, double& cr1, double& ci0, doubl
     dmma884(ci0, ci1, pi1, b.r[1]);
 }
 
-// in-place inverse of an 8x8 complex block in C layout by Gauss-Jordan without row exchanges;
-// minpiv tracks min_p |pivot_p|_1
-__device__ __forceinline__ void inv8(double& xr0, double& xr1, double& xi0, double& xi1, int lane, double& minpiv) {
+// branch-free reciprocal: MUFU.RCP64H seed (~2^-20) + two Newton steps (keeps the whole elimination in one
+// basic block so that ptxas can interleave the DMMA chains with the latency-bound pivot steps)
+__device__ __forceinline__ double fast_rcp(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    const double e = fma(-d, x, 1.0);      // 1 - d x0
+    const double e2 = e * e;               // = 1 - d x1 up to rounding (in parallel with x1)
+    x = fma(x, e, x);                      // x1
+    x = fma(x, e2, x);                     // x2: relative error ~ e^4 (seed 2^-20 -> 2^-80)
+    return x;
+}
+
+// sign flip on the integer pipe (keeps the FP64 pipe for FMA/DMMA work)
+__device__ __forceinline__ double dneg(double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
+
+// in-place inverse of an 8x8 complex block in C layout by Gauss-Jordan without row exchanges.
+// Per pivot p: m = a_gp / a_pp for every row g (row p itself uses m = 1 - 1/a_pp so that the same update
+// x -= m * pivot_row scales it), then the pivot column is overwritten (row p: 1/a_pp, others: -m).
+// f * conj(pivot) is formed while the reciprocal of |pivot|^2 is in flight: dependent FP64 depth 8 per step.
+// minhi tracks min_p |pivot_p|^2 through the high word (integer pipe).
+__device__ __forceinline__ void inv8(double& xr0, double& xr1, double& xi0, double& xi1, int lane, int& minhi) {
     const int g = lane >> 2, q = lane & 3, quad = lane & ~3;
 #pragma unroll
     for (int p = 0; p < 8; p++) {
         const int sg = p & 1, qp = p >> 1;
         // pivot row restricted to my two columns
-        double pr0 = __shfl_sync(0xffffffffu, xr0, 4 * p + q), pr1 = __shfl_sync(0xffffffffu, xr1, 4 * p + q);
-        double pi0 = __shfl_sync(0xffffffffu, xi0, 4 * p + q), pi1 = __shfl_sync(0xffffffffu, xi1, 4 * p + q);
+        const double pr0 = __shfl_sync(0xffffffffu, xr0, 4 * p + q), pr1 = __shfl_sync(0xffffffffu, xr1, 4 * p + q);
+        const double pi0 = __shfl_sync(0xffffffffu, xi0, 4 * p + q), pi1 = __shfl_sync(0xffffffffu, xi1, 4 * p + q);
         // pivot a_pp (from the pivot-row values held at quad lane qp) and my row's multiplier a_gp
-        double ppr = __shfl_sync(0xffffffffu, sg ? pr1 : pr0, quad | qp);
-        double ppi = __shfl_sync(0xffffffffu, sg ? pi1 : pi0, quad | qp);
-        double fr = __shfl_sync(0xffffffffu, sg ? xr1 : xr0, quad | qp);
-        double fi = __shfl_sync(0xffffffffu, sg ? xi1 : xi0, quad | qp);
-        minpiv = fmin(minpiv, fabs(ppr) + fabs(ppi));
-        const double dinv = 1.0 / (ppr * ppr + ppi * ppi);
-        const double rr = ppr * dinv, ri = -ppi * dinv;              // 1 / pivot
-        // scaled pivot row (a_pp := 1 before scaling)
-        const bool pc = (q == qp);
-        if (pc) { if (sg) { pr1 = 1.0; pi1 = 0.0; } else { pr0 = 1.0; pi0 = 0.0; } }
-        const double sr0 = pr0 * rr - pi0 * ri, si0 = pr0 * ri + pi0 * rr;
-        const double sr1 = pr1 * rr - pi1 * ri, si1 = pr1 * ri + pi1 * rr;
-        if (g == p) {
-            xr0 = sr0; xi0 = si0; xr1 = sr1; xi1 = si1;
-        } else {
-            if (pc) { if (sg) { xr1 = 0.0; xi1 = 0.0; } else { xr0 = 0.0; xi0 = 0.0; } }
-            xr0 = fma(-fr, sr0, xr0); xr0 = fma(fi, si0, xr0);
-            xi0 = fma(-fr, si0, xi0); xi0 = fma(-fi, sr0, xi0);
-            xr1 = fma(-fr, sr1, xr1); xr1 = fma(fi, si1, xr1);
-            xi1 = fma(-fr, si1, xi1); xi1 = fma(-fi, sr1, xi1);
+        const double ppr = __shfl_sync(0xffffffffu, sg ? pr1 : pr0, quad | qp);
+        const double ppi = __shfl_sync(0xffffffffu, sg ? pi1 : pi0, quad | qp);
+        const double fr = __shfl_sync(0xffffffffu, sg ? xr1 : xr0, quad | qp);
+        const double fi = __shfl_sync(0xffffffffu, sg ? xi1 : xi0, quad | qp);
+        const double d = fma(ppr, ppr, ppi * ppi);
+        minhi = min(minhi, __double2hiint(d));
+        const double tr_ = fma(fr, ppr, fi * ppi), ti_ = fma(-fr, ppi, fi * ppr);     // f * conj(pivot)
+        const double dinv = fast_rcp(d);
+        double mr = tr_ * dinv, mi = ti_ * dinv;                                       // a_gp / a_pp
+        const double rr = ppr * dinv, nri = ppi * dinv;                                 // 1 / a_pp = rr - i nri
+        const bool prow = (g == p);
+        if (prow) { mr = 1.0 - rr; mi = nri; }
+        xr0 = fma(-mr, pr0, xr0); xr0 = fma(mi, pi0, xr0);
+        xi0 = fma(-mr, pi0, xi0); xi0 = fma(-mi, pr0, xi0);
+        xr1 = fma(-mr, pr1, xr1); xr1 = fma(mi, pi1, xr1);
+        xi1 = fma(-mr, pi1, xi1); xi1 = fma(-mi, pr1, xi1);
+        if (q == qp) {
+            const double cr = prow ? rr : dneg(mr), ci = dneg(prow ? nri : mi);
+            if (sg) { xr1 = cr; xi1 = ci; } else { xr0 = cr; xi0 = ci; }
         }
     }
 }
 
 template <int NB>
 __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], double (&R1)[NB][NB], double (&I0)[NB][NB],
-                                                      double (&I1)[NB][NB], int lane, double& minpiv) {
+                                                      double (&I1)[NB][NB], int lane, int& minpiv) {
     const int g = lane >> 2, q = lane & 3;
     const bool par = g & 1;
     const int src0 = 4 * (2 * q + (par ? 1 : 0)) + (g >> 1);
     const int src1 = 4 * (2 * q + (par ? 0 : 1)) + (g >> 1);
-    // ---- block LU
+    // ---- block LU with look-ahead: S_{s+1} is inverted as soon as its update is complete, so that the
+    //      latency-bound pivot steps overlap the remaining (independent) trailing-update DMMAs
+    inv8(R0[0][0], R1[0][0], I0[0][0], I1[0][0], lane, minpiv);          // D_0
 #pragma unroll
-    for (int s = 0; s < NB; s++) {
-        inv8(R0[s][s], R1[s][s], I0[s][s], I1[s][s], lane, minpiv);      // D_s
-        if (s == NB - 1) break;
+    for (int s = 0; s < NB - 1; s++) {
         const BFrag bD = to_bfrag(R0[s][s], R1[s][s], I0[s][s], I1[s][s], src0, src1, par);
 #pragma unroll
         for (int i = s + 1; i < NB; i++) {                               // L_is = A_is D_s
@@ -117,14 +135,15 @@ __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], doub
 #pragma unroll
         for (int j = s + 1; j < NB; j++) {
             const BFrag bU = to_bfrag(R0[s][j], R1[s][j], I0[s][j], I1[s][j], src0, src1, par);
+#pragma unroll
+            for (int i = s + 1; i < NB; i++)                             // A_ij -= L_is U_sj
+                bmm<true>(R0[i][j], R1[i][j], I0[i][j], I1[i][j], R0[i][s], R1[i][s], I0[i][s], I1[i][s], bU);
+            if (j == s + 1) inv8(R0[j][j], R1[j][j], I0[j][j], I1[j][j], lane, minpiv);   // D_{s+1} (look-ahead)
             {                                                            // X_sj = D_s U_sj (replaces U_sj)
                 double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
                 bmm<false>(cr0, cr1, ci0, ci1, R0[s][s], R1[s][s], I0[s][s], I1[s][s], bU);
                 R0[s][j] = cr0; R1[s][j] = cr1; I0[s][j] = ci0; I1[s][j] = ci1;
             }
-#pragma unroll
-            for (int i = s + 1; i < NB; i++)                             // A_ij -= L_is U_sj
-                bmm<true>(R0[i][j], R1[i][j], I0[i][j], I1[i][j], R0[i][s], R1[i][s], I0[i][s], I1[i][s], bU);
         }
     }
     // ---- trace of the diagonal blocks D_s
@@ -134,49 +153,56 @@ __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], doub
         if (2 * q == g) { tr += R0[s][s]; ti += I0[s][s]; }
         if (2 * q + 1 == g) { tr += R1[s][s]; ti += I1[s][s]; }
     }
-    // ---- V = U~^-1 (strict upper blocks, in place over X), column by column from the right
+    // ---- V = U~^-1 (strict upper blocks, in place over X; columns right to left, rows bottom up) and
+    //      M = L~^-1 (strict lower blocks, in place over L; columns left to right, rows top down).
+    //      The two substitutions are independent dependency chains: their steps are interleaved.
+    {
+        BFrag bDj, bV[NB], bM[NB];
 #pragma unroll
-    for (int j = NB - 1; j >= 1; j--) {
-        const BFrag bD = to_bfrag(R0[j][j], R1[j][j], I0[j][j], I1[j][j], src0, src1, par);
-        BFrag bV[NB];
+        for (int jm = 0; jm < NB - 1; jm++) {
+            const int jv = NB - 1 - jm;
+            bDj = to_bfrag(R0[jv][jv], R1[jv][jv], I0[jv][jv], I1[jv][jv], src0, src1, par);
 #pragma unroll
-        for (int i = j - 1; i >= 0; i--) {
-            double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
-            bmm<true>(cr0, cr1, ci0, ci1, R0[i][j], R1[i][j], I0[i][j], I1[i][j], bD);              // -X_ij D_j
+            for (int im = jm + 1; im < NB; im++) {
+                const int iv = NB - 1 - im;
+                {   // V_{iv,jv} = -X_{iv,jv} D_jv - sum_{iv<t<jv} X_{iv,t} V_{t,jv}
+                    double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
+                    bmm<true>(cr0, cr1, ci0, ci1, R0[iv][jv], R1[iv][jv], I0[iv][jv], I1[iv][jv], bDj);
 #pragma unroll
-            for (int t = i + 1; t < j; t++)
-                bmm<true>(cr0, cr1, ci0, ci1, R0[i][t], R1[i][t], I0[i][t], I1[i][t], bV[t]);       // -X_it V_tj
-            R0[i][j] = cr0; R1[i][j] = cr1; I0[i][j] = ci0; I1[i][j] = ci1;
-            if (i > 0) bV[i] = to_bfrag(cr0, cr1, ci0, ci1, src0, src1, par);
+                    for (int t = iv + 1; t < jv; t++)
+                        bmm<true>(cr0, cr1, ci0, ci1, R0[iv][t], R1[iv][t], I0[iv][t], I1[iv][t], bV[t]);
+                    R0[iv][jv] = cr0; R1[iv][jv] = cr1; I0[iv][jv] = ci0; I1[iv][jv] = ci1;
+                    if (iv > 0) bV[iv] = to_bfrag(cr0, cr1, ci0, ci1, src0, src1, par);
+                }
+                {   // M_{im,jm} = -L_{im,jm} - sum_{jm<t<im} L_{im,t} M_{t,jm}
+                    double cr0 = -R0[im][jm], cr1 = -R1[im][jm], ci0 = -I0[im][jm], ci1 = -I1[im][jm];
+#pragma unroll
+                    for (int t = jm + 1; t < im; t++)
+                        bmm<true>(cr0, cr1, ci0, ci1, R0[im][t], R1[im][t], I0[im][t], I1[im][t], bM[t]);
+                    R0[im][jm] = cr0; R1[im][jm] = cr1; I0[im][jm] = ci0; I1[im][jm] = ci1;
+                    if (im < NB - 1) bM[im] = to_bfrag(cr0, cr1, ci0, ci1, src0, src1, par);
+                }
+            }
         }
     }
-    // ---- M = L~^-1 (strict lower blocks, in place over L), column by column from the left, and
-    //      tr += sum_{j<i} tr(V_ji M_ij) through the B fragment of M_ij
+    // ---- tr += sum_{j<i} tr(V_ji M_ij) = sum over lanes of V_ji[g][2q+t] * M_ij[2q+t][g] (B fragment of M_ij)
 #pragma unroll
-    for (int j = 0; j < NB - 1; j++) {
-        BFrag bM[NB];
+    for (int j = 0; j < NB - 1; j++)
 #pragma unroll
         for (int i = j + 1; i < NB; i++) {
-            double cr0 = -R0[i][j], cr1 = -R1[i][j], ci0 = -I0[i][j], ci1 = -I1[i][j];
-#pragma unroll
-            for (int t = j + 1; t < i; t++)
-                bmm<true>(cr0, cr1, ci0, ci1, R0[i][t], R1[i][t], I0[i][t], I1[i][t], bM[t]);       // -L_it M_tj
-            R0[i][j] = cr0; R1[i][j] = cr1; I0[i][j] = ci0; I1[i][j] = ci1;
-            bM[i] = to_bfrag(cr0, cr1, ci0, ci1, src0, src1, par);
-            // V_ji[g][2q+t] * M_ij[2q+t][g]
-            tr += R0[j][i] * bM[i].r[0] - I0[j][i] * bM[i].i[0] + R1[j][i] * bM[i].r[1] - I1[j][i] * bM[i].i[1];
-            ti += R0[j][i] * bM[i].i[0] + I0[j][i] * bM[i].r[0] + R1[j][i] * bM[i].i[1] + I1[j][i] * bM[i].r[1];
+            const BFrag b = to_bfrag(R0[i][j], R1[i][j], I0[i][j], I1[i][j], src0, src1, par);
+            tr += R0[j][i] * b.r[0] - I0[j][i] * b.i[0] + R1[j][i] * b.r[1] - I1[j][i] * b.i[1];
+            ti += R0[j][i] * b.i[0] + I0[j][i] * b.r[0] + R1[j][i] * b.i[1] + I1[j][i] * b.r[1];
         }
-    }
     return make_double2(warp_sum(tr), warp_sum(ti));
 }
 
-constexpr int MMA_WARPS = 8;
+constexpr int MMA_WARPS_MAX = 12;
 
 // CTA c handles k-points [c*kper, (c+1)*kper) x all nw frequencies; warp w takes the (k, w) pairs
 // i = w, w + 8, ... of that chunk.  mode 0: outp[c*nw + w] = sum_k wnode_k tr ; mode 1: outp[k*nw + w] = tr
 // shared: acc[MMA_WARPS][nw] double2
-template <int NB>
+template <int NB, int MMA_WARPS>
 __global__ void __launch_bounds__(MMA_WARPS * 32, 1)
 resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ wnode, long nk, int n, int nw,
                      const double2* __restrict__ z, const double2* __restrict__ sigma, int kper, int mode,
@@ -198,8 +224,9 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
         const double2* Hk = H + k * (long)n * n;
         const double2* sg = sigma ? sigma + (long)w * n * n : nullptr;
         const double2 zz = z[w];
+        // B = H + Sigma - z (= -A): no FP64 work off the diagonal; tr A^-1 = -tr B^-1
         double R0[NB][NB], R1[NB][NB], I0[NB][NB], I1[NB][NB];
-        double amax = 0.0;
+        int amaxhi = 0;     // max over entries of max(|re|, |im|), tracked through the high word (integer pipe)
 #pragma unroll
         for (int bj = 0; bj < NB; bj++)
 #pragma unroll
@@ -214,19 +241,23 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
                     a1 = Hk[row + (long)c1 * n];
                     if (sg) { double2 s1 = sg[row + (long)c1 * n]; a1.x += s1.x; a1.y += s1.y; }
                 }
-                a0.x = -a0.x; a0.y = -a0.y; a1.x = -a1.x; a1.y = -a1.y;
-                if (row == c0) { if (row < n) { a0.x += zz.x; a0.y += zz.y; } else { a0.x = 1.0; a0.y = 0.0; } }
-                if (row == c1) { if (row < n) { a1.x += zz.x; a1.y += zz.y; } else { a1.x = 1.0; a1.y = 0.0; } }
+                if (bi == bj) {
+                    if (row == c0) { if (row < n) { a0.x -= zz.x; a0.y -= zz.y; } else { a0.x = -1.0; a0.y = 0.0; } }
+                    if (row == c1) { if (row < n) { a1.x -= zz.x; a1.y -= zz.y; } else { a1.x = -1.0; a1.y = 0.0; } }
+                }
                 R0[bi][bj] = a0.x; I0[bi][bj] = a0.y; R1[bi][bj] = a1.x; I1[bi][bj] = a1.y;
-                amax = fmax(amax, fmax(fabs(a0.x) + fabs(a0.y), fabs(a1.x) + fabs(a1.y)));
+                amaxhi = max(amaxhi, max(max(__double2hiint(a0.x) & 0x7fffffff, __double2hiint(a0.y) & 0x7fffffff),
+                                         max(__double2hiint(a1.x) & 0x7fffffff, __double2hiint(a1.y) & 0x7fffffff)));
             }
-        double minpiv = 1e300;
-        double2 t = warp_trace_inverse<NB>(R0, R1, I0, I1, lane, minpiv);
-        t.x -= (double)npad;
+        int minhi = 0x7ff00000;
+        double2 t = warp_trace_inverse<NB>(R0, R1, I0, I1, lane, minhi);
+        t.x = -t.x - (double)npad; t.y = -t.y;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+        for (int off = 16; off > 0; off >>= 1) amaxhi = max(amaxhi, __shfl_xor_sync(0xffffffffu, amaxhi, off));
         if (lane == 0) {
-            if (!(minpiv > 2e-3 * amax) || !(isfinite(t.x) && isfinite(t.y))) atomicOr(errflag, 2);   // ask for the pivoted path
+            // smallest |pivot|^2 against (2e-3 * max|a|)^2 (both within 2^-20 through their high words)
+            const double pmin2 = __hiloint2double(minhi, 0), am = __hiloint2double(amaxhi, 0);
+            if (!(pmin2 > 4e-6 * am * am) || !(isfinite(t.x) && isfinite(t.y))) atomicOr(errflag, 2);   // ask for the pivoted path
             if (mode == 0) {
                 const double wt = wnode ? wnode[k] : 1.0;
                 acc[w].x += wt * t.x; acc[w].y += wt * t.y;
@@ -248,38 +279,58 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
 
 inline bool mma_resolvent_supported(int n) { return n >= 4 && n <= 32; }
 
+// warps per CTA (= per SM): 8 (255 registers) and 12 (168 registers, ~150 spill accesses) measure the same on B200
+// (the kernel is bound by the FP64 pipe that DMMA and DFMA share, not by occupancy); 8 is the default
+inline int mma_resolvent_warps() {
+    static int w = 0;
+    if (!w) {
+        const char* e = getenv("ABZ_MMA_WARPS");
+        w = (e && atoi(e) == 12) ? 12 : 8;
+    }
+    return w;
+}
+
 inline int mma_resolvent_plan(int n, long nk, int nw, long sm, long* ncta, int* kper) {
     if (!mma_resolvent_supported(n)) return -1;
-    if ((size_t)nw * MMA_WARPS * sizeof(double2) > 160 * 1024) return -1;
+    const int W = mma_resolvent_warps();
+    if ((size_t)nw * W * sizeof(double2) > 160 * 1024) return -1;
     long target = sm * 4;
     long kp = (nk + target - 1) / target;
     // keep every warp busy: at least ~4 matrices per warp per CTA
-    while (kp * nw < 4L * MMA_WARPS && kp < nk) kp++;
+    while (kp * nw < 4L * W && kp < nk) kp++;
     if (kp < 1) kp = 1;
     *kper = (int)kp;
     *ncta = (nk + kp - 1) / kp;
     return 0;
 }
 
+template <int NB, int W>
+inline void mma_launch_one(const double2* H, const double* wnode, long nk, int n, int nw, const double2* z, const double2* sigma,
+                           int mode, double2* outp, int* errflag, long ncta, int kper, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(resolvent_mma_kernel<NB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
+    size_t smem = (size_t)nw * W * sizeof(double2);
+    resolvent_mma_kernel<NB, W><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
+}
+
 inline cudaError_t mma_resolvent_launch(const double2* H, const double* wnode, long nk, int n, int nw, const double2* z,
                                         const double2* sigma, int mode, double2* outp, int* errflag, long ncta, int kper,
                                         cudaStream_t stream) {
     const int NBv = (n + 7) / 8;
-    size_t smem = (size_t)nw * MMA_WARPS * sizeof(double2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(resolvent_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(resolvent_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(resolvent_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(resolvent_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_set = true;
-    }
+    const int W = mma_resolvent_warps();
+#define ABZ_MMA_CASE(NBX)                                                                                            \
+    if (W == 8) mma_launch_one<NBX, 8>(H, wnode, nk, n, nw, z, sigma, mode, outp, errflag, ncta, kper, stream);      \
+    else mma_launch_one<NBX, 12>(H, wnode, nk, n, nw, z, sigma, mode, outp, errflag, ncta, kper, stream);
     switch (NBv) {
-        case 1: resolvent_mma_kernel<1><<<(unsigned)ncta, MMA_WARPS * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag); break;
-        case 2: resolvent_mma_kernel<2><<<(unsigned)ncta, MMA_WARPS * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag); break;
-        case 3: resolvent_mma_kernel<3><<<(unsigned)ncta, MMA_WARPS * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag); break;
-        default: resolvent_mma_kernel<4><<<(unsigned)ncta, MMA_WARPS * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag); break;
+        case 1: ABZ_MMA_CASE(1) break;
+        case 2: ABZ_MMA_CASE(2) break;
+        case 3: ABZ_MMA_CASE(3) break;
+        default: ABZ_MMA_CASE(4) break;
     }
+#undef ABZ_MMA_CASE
     return cudaGetLastError();
 }
 
