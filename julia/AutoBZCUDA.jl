@@ -1,0 +1,212 @@
+# AutoBZCUDA.jl — reference-side binding of libautobz_cuda.so for AutoBZCore.jl v0.3.8.
+#
+# Written blind (no Julia in the build image; syntax checked by eye only — see INTEGRATION.md).
+# It shows the exact ccall signatures a maintainer binds and how the device rules plug into the
+# reference's dispatch seams:
+#   S1  init_fourier_rule -> FourierPTR / FourierMonkhorstPack      (src/fourier.jl:330-337, 166-174, 265-277)
+#   S2  (rule)(f, B, buffer) = quadsum(...)                          (src/fourier.jl:204-207, 289-292)
+#   S3  BatchIntegrand f!(y, x, p)                                   (src/batch.jl:4-20)
+#   S4  IAI innermost / level closures                               (src/fourier.jl:432-486)
+# The adaptive control flow (autosymptr, auxquadgk, nested_quad) stays in Julia untouched.
+module AutoBZCUDA
+
+using AutoBZCore
+using AutoBZCore: FourierIntegrand, FourierValue, IntegralSolution, MonkhorstPack, AutoSymPTRJL
+using AutoSymPTR, FourierSeriesEvaluators, StaticArrays, LinearAlgebra
+import AutoBZCore: init_fourier_rule, rule_type
+import AutoSymPTR: nextrule
+
+const LIB = get(ENV, "AUTOBZ_CUDA_LIB", "libautobz_cuda")
+
+struct AbzError <: Exception
+    code::Int32
+    msg::String
+end
+Base.showerror(io::IO, e::AbzError) = print(io, "libautobz_cuda error ", e.code, ": ", e.msg)
+
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer=0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:abz_ctx_create, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, r)
+        rc == 0 || throw(AbzError(rc, unsafe_string(ccall((:abz_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
+        ctx = new(r[])
+        finalizer(c -> ccall((:abz_ctx_destroy, LIB), Int32, (Ptr{Cvoid},), c.h), ctx)
+        return ctx
+    end
+end
+
+function check(ctx::Context, rc::Int32)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:abz_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.h))
+    rc == -1 && throw(ArgumentError(msg))                       # ABZ_E_INVALID  (src/fourier.jl:167 style)
+    rc == -4 && throw(DomainError(NaN, msg))                    # ABZ_E_SINGULAR (QuadGK's DomainError)
+    throw(AbzError(rc, msg))
+end
+
+# one context per Julia thread: the reference protects per-thread state by copying (src/interfaces.jl:213)
+const CTXS = Dict{Int,Context}()
+context() = get!(() -> Context(parse(Int, get(ENV, "LOCAL_RANK", "0"))), CTXS, Threads.threadid())
+
+# ---- series: Array{SMatrix{n,n,T},3} (or OffsetArray) has the layout ComplexF64[n,n,M1,M2,M3] --------
+mutable struct DeviceSeries
+    ctx::Context
+    h::UInt64
+    norb::Int
+end
+
+function DeviceSeries(ctx::Context, s::FourierSeries{S,3}) where {S}
+    C = parent(s.c)                                            # strip OffsetArray axes
+    T = eltype(eltype(C))
+    n = size(eltype(C), 1)
+    M = Int32[size(C)...]
+    lo = Int32[(first(axes(s.c, d)) + s.o[d]) for d in 1:3]    # index + offset = R
+    per = Float64[s.t...]
+    h = Ref{UInt64}(0)
+    GC.@preserve C begin
+        rc = ccall((:abz_series_create, LIB), Int32,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ref{UInt64}),
+                   ctx.h, Ptr{Float64}(pointer(C)), T <: Complex ? 1 : 0, n, M, lo, per, h)
+    end
+    check(ctx, rc)
+    ds = DeviceSeries(ctx, h[], n)
+    finalizer(x -> ccall((:abz_series_destroy, LIB), Int32, (Ptr{Cvoid}, UInt64), x.ctx.h, x.h), ds)
+    return ds
+end
+
+# ---- S1: device rules with the interface of FourierPTR / FourierMonkhorstPack ------------------------
+mutable struct DeviceRule{d}
+    ctx::Context
+    h::UInt64
+    series::DeviceSeries
+    npt::Int
+    nsyms::Int
+    nnodes::Int
+end
+Base.length(r::DeviceRule) = r.nnodes
+rule_type(::DeviceRule{d}) where {d} = FourierValue{SVector{d,Float64},Nothing}
+
+function DeviceRule(ds::DeviceSeries, npt::Integer, syms)
+    ctx = ds.ctx
+    h = Ref{UInt64}(0)
+    if syms === nothing
+        check(ctx, ccall((:abz_rule_create_full, LIB), Int32, (Ptr{Cvoid}, UInt64, Int32, Int32, Int32, Ref{UInt64}),
+                         ctx.h, ds.h, npt, 0, npt, h))
+        nsym = 1
+    else
+        S = Int32[round(Int32, s[i, j]) for j in 1:3, i in 1:3, s in syms]       # row-major 3x3 per symmetry
+        wsym = Array{Int32}(undef, npt, npt, npt)
+        nirr = Ref{Int64}(0)
+        check(ctx, ccall((:abz_symptr_rule, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ref{Int64}),
+                         ctx.h, npt, length(syms), S, wsym, nirr))
+        check(ctx, ccall((:abz_rule_create_sym, LIB), Int32, (Ptr{Cvoid}, UInt64, Int32, Ptr{Int32}, Int32, Int32, Ref{UInt64}),
+                         ctx.h, ds.h, npt, wsym, 0, 1, h))
+        nsym = length(syms)
+    end
+    nn = Ref{Int64}(0); no = Ref{Int32}(0); np = Ref{Int32}(0)
+    check(ctx, ccall((:abz_rule_info, LIB), Int32, (Ptr{Cvoid}, UInt64, Ref{Int64}, Ref{Int32}, Ref{Int32}), ctx.h, h[], nn, no, np))
+    r = DeviceRule{3}(ctx, h[], ds, npt, nsym, nn[])
+    finalizer(x -> ccall((:abz_rule_destroy, LIB), Int32, (Ptr{Cvoid}, UInt64), x.ctx.h, x.h), r)
+    return r
+end
+
+# A FourierWorkspace that remembers its device copy
+struct CudaWorkspace{W}
+    w::W
+    ds::DeviceSeries
+end
+cuda_workspace(s::FourierSeries) = CudaWorkspace(AutoBZCore.workspace_allocate_vec(s, period(s)), DeviceSeries(context(), s))
+
+# replaces init_fourier_rule (src/fourier.jl:330-337)
+function init_fourier_rule(w::CudaWorkspace, dom::AutoSymPTR.Basis, alg::MonkhorstPack)
+    return DeviceRule(w.ds, alg.npt, alg.syms)
+end
+# AutoPTR: rule definition + nextrule (src/fourier.jl:296-321)
+struct DeviceRuleDef{S}
+    ds::DeviceSeries
+    m::AutoSymPTR.MonkhorstPackRule{S}
+end
+(r::DeviceRuleDef)(::Type{T}, ::Val{d}) where {T,d} = DeviceRule(r.ds, r.m.n₀, r.m.syms)
+nextrule(p::DeviceRule, r::DeviceRuleDef) = DeviceRule(r.ds, p.npt + r.m.Δn, r.m.syms)
+
+# ---- S2: rule application for the named integrands ---------------------------------------------------
+"tr[(ω + iη - H(k) - Σ)^-1] integrand marker: `ResolventTrace()(h_k::FourierValue; η, ω)` also works on the CPU path"
+struct ResolventTrace end
+(::ResolventTrace)(h_k::FourierValue; η, ω, Σ=nothing) =
+    tr(inv(complex(ω, η) * I - h_k.s - (Σ === nothing ? zero(h_k.s) : Σ)))
+
+"sum_i w_i tr[(z_w - H(k_i) - Σ_w)^-1] for all frequencies in one device pass; scale as AutoSymPTR.quadsum's"
+function resolvent_sum(rule::DeviceRule, z::Vector{ComplexF64}, Σ::Union{Nothing,Array{ComplexF64,3}}, scale::Float64)
+    out = Vector{ComplexF64}(undef, length(z))
+    GC.@preserve z Σ out begin
+        rc = ccall((:abz_rule_resolvent_sum, LIB), Int32,
+                   (Ptr{Cvoid}, UInt64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}),
+                   rule.ctx.h, rule.h, 0, length(z), Ptr{Float64}(pointer(z)),
+                   Σ === nothing ? Ptr{Float64}(C_NULL) : Ptr{Float64}(pointer(Σ)), scale, Ptr{Float64}(pointer(out)))
+    end
+    check(rule.ctx, rc)
+    return out
+end
+
+# (rule)(f, B, buffer): src/fourier.jl:204-207, 289-292.  vol/(npt^d nsyms) exactly as the reference.
+function (rule::DeviceRule{d})(f::AutoBZCore.ParameterIntegrand{ResolventTrace}, B::AutoSymPTR.Basis, buffer=nothing) where {d}
+    p = f.p
+    z = ComplexF64[complex(p.ω, p.η)]
+    scale = abs(det(B.B)) / (rule.npt^d * rule.nsyms)
+    return resolvent_sum(rule, z, nothing, scale)[1]
+end
+
+# generic user integrands: copy H(k) back and keep the reference's Julia path (iterate protocol, src/fourier.jl:176-202)
+function copy_out(rule::DeviceRule{d}) where {d}
+    n = rule.series.norb
+    Hk = Array{ComplexF64}(undef, n, n, rule.nnodes); k = Array{Float64}(undef, 3, rule.nnodes); w = Vector{Float64}(undef, rule.nnodes)
+    check(rule.ctx, ccall((:abz_rule_copy_out, LIB), Int32, (Ptr{Cvoid}, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                          rule.ctx.h, rule.h, Ptr{Float64}(pointer(Hk)), k, w))
+    return Hk, k, w
+end
+function (rule::DeviceRule{d})(f::F, B::AutoSymPTR.Basis, buffer=nothing) where {d,F}
+    Hk, k, w = copy_out(rule)
+    n = rule.series.norb
+    acc = sum(i -> w[i] * f(FourierValue(SVector{d}(k[1:d, i]), SMatrix{n,n}(view(Hk, :, :, i)))), 1:rule.nnodes)
+    return acc * abs(det(B.B)) / (rule.npt^d * rule.nsyms)
+end
+
+# ---- S3: BatchIntegrand f!(y, x, p) for scattered k (src/batch.jl:4-20) -------------------------------
+function resolvent_batch!(y::Vector{ComplexF64}, x::Vector{SVector{3,Float64}}, ds::DeviceSeries, z::ComplexF64)
+    resize!(y, length(x))
+    GC.@preserve y x begin
+        rc = ccall((:abz_points_resolvent, LIB), Int32,
+                   (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   ds.ctx.h, ds.h, length(x), Ptr{Float64}(pointer(x)), 0, 1, Ref(z), C_NULL, Ptr{Float64}(pointer(y)))
+    end
+    check(ds.ctx, rc)
+    return nothing
+end
+gpu_batch_integrand(ds::DeviceSeries; η, max_batch=2^16) =
+    BatchIntegrand((y, x, p) -> resolvent_batch!(y, x, ds, complex(p, η)), ComplexF64[], SVector{3,Float64}[], max_batch=max_batch)
+
+# ---- S4: IAI levels: arena of contracted series (workspace_contract!, src/fourier.jl:478) --------------
+mutable struct DeviceNest
+    ctx::Context
+    h::UInt64
+end
+function DeviceNest(ds::DeviceSeries, ndim, cap2, cap1)
+    h = Ref{UInt64}(0)
+    check(ds.ctx, ccall((:abz_nest_create, LIB), Int32, (Ptr{Cvoid}, UInt64, Int32, Int64, Int64, Ref{UInt64}), ds.ctx.h, ds.h, ndim, cap2, cap1, h))
+    return DeviceNest(ds.ctx, h[])
+end
+contract3!(n::DeviceNest, x3::Vector{Float64}, slot2::Vector{Int64}) =
+    check(n.ctx, ccall((:abz_nest_contract3, LIB), Int32, (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Ptr{Int64}), n.ctx.h, n.h, length(x3), x3, slot2))
+contract2!(n::DeviceNest, x2::Vector{Float64}, parent::Vector{Int64}, slot1::Vector{Int64}) =
+    check(n.ctx, ccall((:abz_nest_contract2, LIB), Int32, (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}), n.ctx.h, n.h, length(x2), x2, parent, slot1))
+function eval!(y::Vector{ComplexF64}, n::DeviceNest, x1::Vector{Float64}, slot1::Vector{Int64}, z::ComplexF64)
+    resize!(y, length(x1))
+    check(n.ctx, ccall((:abz_nest_eval, LIB), Int32, (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Ptr{Int64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       n.ctx.h, n.h, length(x1), x1, slot1, 0, Ref(z), C_NULL, Ptr{Float64}(pointer(y))))
+    return y
+end
+
+# v0.4+ API names (BASELINE.json north_star) as thin aliases
+const FourierIntegralFunction = FourierIntegrand
+
+end # module
