@@ -267,7 +267,10 @@ def main():
         mat_s = ev_mat * 1e-3 / args.steps
         achieved = f_res * nodes_rank / mat_s * 1e-12
         roof = {"bound": "tensor", "kernel": "resolvent (FP64, DMMA/DFMA pipe)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp64_peak, "traffic": None,
+                "frac": achieved / fp64_peak,
+                # dram__bytes_read+write of one resolvent launch, from the ncu --set full capture in profiles/ (16.68 kB per k-point
+                # = the 16 n^2 B of H(k) read once for all 128 frequencies; no re-reads), scaled to this run's launch size
+                "traffic": 16678.0 * min(nodes_rank, 262144), "traffic_source": "profiles/r01_ncu_full_resolvent_mma_raw.csv",
                 "peak_source": "cuBLAS ZGEMM 4096^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flops_per_kpoint": {"fourier": f_four, "resolvent": f_res},
                 "eval_ms_per_step": ev_eval / args.steps, "matfun_ms_per_step": ev_mat / args.steps}
