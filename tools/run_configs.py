@@ -1,0 +1,77 @@
+"""Runs the five BASELINE.json configurations through the public API on one B200 and prints one JSON line each
+(k-points/s, evaluations, device timings).  Parity for the same configs lives in tests/; this is the measurement."""
+import json, os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+import autobz_b200 as ab
+from autobz_b200 import _lib as L
+
+ctx = ab.default_context(0)
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+d = np.load(os.path.join(ROOT, "tests", "golden", "svo_hr.npz"))
+Hs, los, A = np.asfortranarray(d["H_R"]), tuple(int(x) for x in d["lo"]), d["A"]
+which = sys.argv[1:] or ["c1", "c2", "c3", "c5"]
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+if "c1" in which:
+    c, lo = ab.synthetic.integer_lattice(3)
+    s = ab.FourierSeries(c[0, 0], period=1.0, lo=lo)
+    bz = ab.load_bz(ab.FBZ(), 2 * np.pi * np.eye(3))
+    solver = ab.IntegralSolver(ab.FourierIntegrand(ab.gloc_trace_integrand, s, eta=0.1), bz, ab.PTR(npt=64))
+    solver(omega=0.0)
+    t = time.perf_counter(); reps = 20
+    for _ in range(reps): g = solver(omega=0.5)
+    dt = (time.perf_counter() - t) / reps
+    emit(config="C1 cubic 1-orbital PTR 64^3 eta=0.1", G=[g.real, g.imag], ms_per_solve=1e3 * dt, kpoints_per_s=64 ** 3 / dt, device_ms=ctx.last_timings())
+
+if "c2" in which:
+    fs = ab.FourierSeries(Hs, period=1.0, lo=los, norb=3)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), A)
+    f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=1e-2)
+    # fixed PTR sweeps: FBZ-equivalent throughput of the fused small-norb kernel
+    for npt, dom, name in ((200, ab.load_bz(ab.FBZ(), A), "FBZ"), (400, ibz, "CubicSymIBZ")):
+        solver = ab.IntegralSolver(f, dom, ab.PTR(npt=npt))
+        ws = [{"omega": w} for w in np.linspace(11.0, 14.0, 64)]
+        ab.batchsolve(solver, ws[:4])
+        t = time.perf_counter(); g = ab.batchsolve(solver, ws); dt = time.perf_counter() - t
+        nn = len(solver.cache.cacheval["rule"])
+        emit(config=f"C2 SrVO3 PTR npt={npt} {name} 64 freqs", nodes=nn, ms=1e3 * dt, kpoints_per_s=nn / dt, k_omega_per_s=nn * 64 / dt, device_ms=ctx.last_timings())
+    # AutoPTR eta=1e-2, reference-style schedule a = eta
+    for w in (11.0, 12.5):
+        alg = ab.EvalCounter(ab.AutoPTR(a=1e-2, nmin=50, nmax=1000))
+        t = time.perf_counter(); cache = ab.init(ab.IntegralProblem(f, ibz, {"omega": w}), alg, abstol=1e-3); t_init = time.perf_counter() - t
+        t = time.perf_counter(); sol = ab.solve_(cache); dt = time.perf_counter() - t
+        emit(config=f"C2 SrVO3 AutoPTR(a=eta=1e-2) CubicSymIBZ omega={w}", u=[sol.u.real, sol.u.imag], resid=float(sol.resid), numevals=sol.numevals,
+             last_npt=cache.cacheval.get("last_npt"), init_ms=1e3 * t_init, solve_ms=1e3 * dt, kpoints_per_s=sol.numevals / dt)
+
+if "c3" in which:
+    fs = ab.FourierSeries(Hs, period=1.0, lo=los, norb=3)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), A)
+    j48 = abs(np.linalg.det(ibz.B)) * 48
+    for eta, atol in ((1e-2, 1e-3), (1e-4, 1e-3)):
+        f = ab.FourierIntegrand(ab.dos_integrand, fs, eta)
+        for w in (12.0, 12.975161):
+            cache = ab.init(ab.IntegralProblem(f, ibz, w), ab.EvalCounter(ab.IAI()), abstol=atol)
+            l0 = ctx.launch_count
+            t = time.perf_counter(); sol = ab.solve_(cache); dt = time.perf_counter() - t
+            emit(config=f"C3 SrVO3 IAI eta={eta} abstol={atol} omega={w}", dos=sol.u, err=sol.resid, numevals=sol.numevals, s=dt, evals_per_s=sol.numevals / dt,
+                 rounds=cache.cacheval.get("iai_rounds"), launches=ctx.launch_count - l0)
+
+if "c5" in which:
+    n = 64
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 4, cubic=True)
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=n)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), 2 * np.pi * np.eye(3))
+    f = ab.FourierIntegrand(ab.EigenIntegrand("fermi_energy"), fs, 0.0, 0.5)
+    for npt in (48, 96, 144):
+        cache = ab.init(ab.IntegralProblem(f, ibz), ab.PTR(npt=npt))
+        ab.solve_(cache)
+        t = time.perf_counter(); sol = ab.solve_(cache); dt = time.perf_counter() - t
+        nn = len(cache.cacheval["rule"])
+        ev, mf = ctx.last_timings()
+        emit(config=f"C5 norb=64 band energy CubicSymIBZ PTR npt={npt}", u=sol.u, nodes=nn, ms=1e3 * dt, kpoints_per_s=nn / dt, eval_ms=ev, eig_ms=mf,
+             eig_tflops_credited=(32 / 3) * n ** 3 * nn / (mf * 1e-3) * 1e-12 if mf else None)
+    t = time.perf_counter(); sol = ab.solve(ab.IntegralProblem(f, ibz), ab.EvalCounter(ab.AutoPTR(a=1.0, nmin=48, dn=48.0)), reltol=1e-6); dt = time.perf_counter() - t
+    emit(config="C5 norb=64 band energy CubicSymIBZ AutoPTR 48->96->144", u=sol.u, resid=sol.resid, numevals=sol.numevals, s=dt)
