@@ -15,15 +15,16 @@ ABZ_OK = 0
 ABZ_E_INVALID, ABZ_E_OOM, ABZ_E_CUDA, ABZ_E_SINGULAR, ABZ_E_UNSUPPORTED, ABZ_E_NCCL = -1, -2, -3, -4, -5, -6
 F_RESOLVENT_TRACE, F_TRACE_H = 0, 1
 EIG_SUM, EIG_FERMI_ENERGY, EIG_FERMI_COUNT, EIG_GAUSS_DOS = 0, 1, 2, 3
-OPT_RESOLVENT_ALGO, OPT_MEM_BUDGET_MB, OPT_FUSED_SMALL = 1, 2, 3
+OPT_RESOLVENT_ALGO, OPT_MEM_BUDGET_MB, OPT_FUSED_SMALL, OPT_EIG_ALGO = 1, 2, 3, 4
+IAI_DEVICE_LEAVES = 1
 
 # every symbol include/autobz_cuda.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "abz_version", "abz_last_error", "abz_ctx_create", "abz_ctx_destroy", "abz_ctx_set_option", "abz_ctx_launch_count",
     "abz_ctx_last_timings", "abz_series_create", "abz_series_destroy", "abz_rule_create_full", "abz_rule_create_sym", "abz_rule_create_nodes",
-    "abz_symptr_rule", "abz_rule_destroy", "abz_rule_info", "abz_rule_materialize", "abz_rule_copy_out",
+    "abz_symptr_rule", "abz_rule_create_symptr", "abz_rule_destroy", "abz_rule_info", "abz_rule_materialize", "abz_rule_copy_out",
     "abz_rule_resolvent_sum", "abz_rule_eig_sum", "abz_rule_eigvals", "abz_points_eval", "abz_points_resolvent",
-    "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval",
+    "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval", "abz_iai_solve",
     "abz_comm_unique_id", "abz_comm_init", "abz_allreduce_sum", "abz_comm_destroy",
 ]
 
@@ -68,6 +69,8 @@ def load():
     lib.abz_rule_create_sym.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_i32p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]
     lib.abz_rule_create_nodes.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int64, c_i32p, c_dp, C.POINTER(C.c_uint64)]
     lib.abz_symptr_rule.argtypes = [C.c_void_p, C.c_int32, C.c_int32, c_i32p, c_i32p, c_i64p]
+    lib.abz_rule_create_symptr.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, c_i32p, C.c_int32, C.c_int32,
+                                           C.POINTER(C.c_uint64), c_i64p]
     lib.abz_rule_destroy.argtypes = [C.c_void_p, C.c_uint64]
     lib.abz_rule_info.argtypes = [C.c_void_p, C.c_uint64, c_i64p, c_i32p, c_i32p]
     lib.abz_rule_materialize.argtypes = [C.c_void_p, C.c_uint64]
@@ -82,6 +85,8 @@ def load():
     lib.abz_nest_contract3.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p]
     lib.abz_nest_contract2.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p, c_i64p]
     lib.abz_nest_eval.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p, C.c_int32, c_dp, c_dp, c_dp]
+    lib.abz_iai_solve.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, C.c_double,
+                                  C.c_double, C.c_int64, C.c_int32, c_dp, c_i64p]
     lib.abz_comm_unique_id.argtypes = [C.c_void_p]
     lib.abz_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     lib.abz_allreduce_sum.argtypes = [C.c_void_p, c_dp, C.c_int64]
@@ -227,10 +232,17 @@ class DeviceSeries:
 class DeviceRule:
     """A quadrature rule on the device: FourierPTR (full grid) or FourierMonkhorstPack (wsym given)."""
 
-    def __init__(self, ctx, series, npt, wsym=None, k3_lo=0, k3_hi=None, k3_stride=1, nodes=None, weights=None):
+    def __init__(self, ctx, series, npt, wsym=None, k3_lo=0, k3_hi=None, k3_stride=1, nodes=None, weights=None, syms=None):
         self.ctx, self.series, self.npt = ctx, series, int(npt)
         h = C.c_uint64()
-        if nodes is not None:
+        self.nirr_total = None
+        if syms is not None:
+            sy = np.ascontiguousarray(np.asarray(syms, dtype=np.int32).reshape(-1, 3, 3))
+            nirr = C.c_int64()
+            ctx.check(ctx.lib.abz_rule_create_symptr(ctx.h, series.h, self.npt, sy.shape[0], sy.ctypes.data_as(c_i32p), int(k3_lo),
+                                                     int(k3_stride), C.byref(h), C.byref(nirr)))
+            self.nirr_total = int(nirr.value)
+        elif nodes is not None:
             idx = np.ascontiguousarray(np.asarray(nodes, dtype=np.int32).reshape(-1, 3))
             wv = None if weights is None else np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
             ctx.check(ctx.lib.abz_rule_create_nodes(ctx.h, series.h, self.npt, idx.shape[0], idx.ctypes.data_as(c_i32p), _dp(wv),
@@ -340,3 +352,22 @@ class DeviceNest:
         self.ctx.check(self.ctx.lib.abz_nest_eval(self.ctx.h, self.h, x.size, _dp(x), None if s is None else s.ctypes.data_as(c_i64p),
                                                   fkind, _dp(zz), _dp(sg), _dp(y)))
         return y
+
+    def iai_solve(self, lkind, la, lb, fkind, vkind, z, sigma, lin, atol, rtol, maxevals, device_leaves=True):
+        """abz_iai_solve: the whole nested adaptive solve with the control flow on the library's host side.
+        Returns (I complex, E, numevals, rounds, launches)."""
+        la_ = np.ascontiguousarray(la, dtype=np.float64)
+        lb_ = None if lb is None else np.ascontiguousarray(lb, dtype=np.float64)
+        zz = _cz(0j if z is None else z)
+        n = self.series.n
+        sg = None if sigma is None else np.asfortranarray(np.asarray(sigma, dtype=np.complex128).reshape(n, n))
+        ln = None
+        if lin is not None:
+            a, b = complex(lin[0]), complex(lin[1])
+            ln = np.array([a.real, a.imag, b.real, b.imag], dtype=np.float64)
+        out = np.zeros(3)
+        stats = np.zeros(3, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.abz_iai_solve(self.ctx.h, self.h, int(lkind), _dp(la_), _dp(lb_), int(fkind), int(vkind), _dp(zz),
+                                                  _dp(sg), _dp(ln), float(atol), float(rtol), int(min(maxevals, 2 ** 62)),
+                                                  IAI_DEVICE_LEAVES if device_leaves else 0, _dp(out), stats.ctypes.data_as(c_i64p)))
+        return complex(out[0], out[1]), float(out[2]), int(stats[0]), int(stats[1]), int(stats[2])

@@ -78,9 +78,10 @@ class DeviceRule:
                 self.dev = _lib.DeviceRule(ctx, ds, self.npt, k3_lo=lo, k3_hi=hi)
                 self.nnodes_total = self.npt ** 3
             else:
-                wsym, nirr = backend.symptr_rule(self.npt, syms)
-                self.dev = _lib.DeviceRule(ctx, ds, self.npt, wsym=wsym, k3_lo=rank, k3_stride=nranks)
-                self.nnodes_total = nirr
+                # symptr_rule + CSR compaction on the device; the dense weights never visit the host
+                sy = embed_syms(syms, np.asarray(syms[0]).shape[0])
+                self.dev = _lib.DeviceRule(ctx, ds, self.npt, syms=sy, k3_lo=rank, k3_stride=nranks)
+                self.nnodes_total = self.dev.nirr_total
         else:
             idx, w = symptr_nodes_lowdim(self.npt, ndim, syms)
             self.nnodes_total = idx.shape[0]
@@ -110,8 +111,13 @@ class DeviceRule:
 
 
 class DeviceBackend:
-    def __init__(self, device=None, ctx=None):
+    """iai_engine: "native" (default) runs IAI's adaptive control flow in the library's C++ host engine
+    (abz_iai_solve, one call per solve); "python" drives abz_nest_* round by round from iai.NestedGK.
+    iai_device_leaves: run each innermost 1-D adaptive integral entirely on the device (norb <= 3)."""
+
+    def __init__(self, device=None, ctx=None, iai_engine="native", iai_device_leaves=True):
         self.ctx = ctx if ctx is not None else default_context(device)
+        self.iai_engine, self.iai_device_leaves = iai_engine, iai_device_leaves
         self._wsym_cache = {}
 
     def symptr_rule(self, npt, syms):

@@ -54,6 +54,7 @@ struct Rule {
     Series* s = nullptr;
     int N = 0;
     bool full = true;
+    bool nodes_on_host = true;   // false: node_k1 / node_w live on the device only (abz_rule_create_symptr)
     long np3 = 0, nrows = 0, nnz = 0;
     std::vector<int> h_plane_k3, h_row_k2, h_node_k1;
     std::vector<long> h_plane_rowptr, h_row_nodeptr;
@@ -94,8 +95,11 @@ struct abz_ctx {
     int resolvent_algo = 0;
     size_t budget = (size_t)4096 << 20;
     int fused_small = 1;
+    int eig_algo = 0;             // 0: tridiagonalisation + QL, 1: two-sided Jacobi
     bool force_generic = false;   // set while re-running a call whose fast path asked for pivoting
-    DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d;
+    DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d, iai_in, iai_out, eig_d, eig_e;
+    void* pin_in = nullptr; size_t pin_in_cap = 0;     // pinned staging for the IAI engine's per-round traffic
+    void* pin_out = nullptr; size_t pin_out_cap = 0;
     long launches = 0;
     std::vector<cudaEvent_t> events;
     size_t ev_used = 0;
@@ -169,7 +173,7 @@ int finish_rule(abz_ctx* ctx, Rule* r) {
     if ((rc = upload(ctx, &r->d_plane_rowptr, r->h_plane_rowptr))) return rc;
     if ((rc = upload(ctx, &r->d_row_k2, r->h_row_k2))) return rc;
     if ((rc = upload(ctx, &r->d_row_nodeptr, r->h_row_nodeptr))) return rc;
-    if (!r->full) {
+    if (!r->full && r->nodes_on_host) {
         if ((rc = upload(ctx, &r->d_node_k1, r->h_node_k1))) return rc;
         if ((rc = upload(ctx, &r->d_node_w, r->h_node_w))) return rc;
     }
@@ -453,6 +457,8 @@ int32_t abz_ctx_destroy(abz_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     abz_comm_destroy(ctx);
     ctx->rules.clear(); ctx->nests.clear(); ctx->series.clear();
+    if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
+    if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     for (auto e : ctx->events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -466,6 +472,7 @@ int32_t abz_ctx_set_option(abz_ctx* ctx, int32_t option, int64_t value) {
         case ABZ_OPT_MEM_BUDGET_MB: if (value < 1) return fail(ctx, ABZ_E_INVALID, "budget must be >= 1 MB");
             ctx->budget = (size_t)value << 20; return ABZ_OK;
         case ABZ_OPT_FUSED_SMALL: ctx->fused_small = (int)value; return ABZ_OK;
+        case ABZ_OPT_EIG_ALGO: ctx->eig_algo = (int)value; return ABZ_OK;
     }
     return fail(ctx, ABZ_E_INVALID, "unknown option");
 }
@@ -648,6 +655,95 @@ int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t*
     return ABZ_OK;
 }
 
+int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t k3_lo,
+                               int32_t k3_stride, abz_rule_t* out, int64_t* nirr_total) {
+    if (!ctx) return ABZ_E_INVALID;
+    Series* s = get_series(ctx, sid);
+    if (!s) return fail(ctx, ABZ_E_INVALID, "unknown series handle");
+    if (!out || npt < 1 || nsyms < 1 || nsyms > 1024 || !syms || k3_lo < 0 || k3_stride < 1)
+        return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    cudaSetDevice(ctx->device);
+    const long N = npt;
+    const size_t tot = (size_t)N * N * N;
+    // dense orbit weights on the device (never copied to the host)
+    DevBuf wbuf, cntbuf, k3buf;
+    CU(ctx, wbuf.reserve(tot * sizeof(int)));
+    CU(ctx, ctx->tmp_b.reserve((size_t)nsyms * 9 * sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, syms, (size_t)nsyms * 9 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    symptr_rule_kernel<<<(unsigned)((tot + 255) / 256), 256, (size_t)nsyms * 9 * sizeof(int), ctx->stream>>>(
+        npt, nsyms, ctx->tmp_b.as<int>(), wbuf.as<int>());
+    LAUNCH_CHECK(ctx, "symptr_rule_kernel");
+    // per-row counts: all planes when the total is wanted, else only this rank's
+    const bool want_total = (nirr_total != nullptr) && !(k3_lo == 0 && k3_stride == 1);
+    std::vector<int> cnt_all;
+    const long nplanes_sel = (k3_lo < N) ? (N - k3_lo + k3_stride - 1) / k3_stride : 0;
+    const long rows_sel = nplanes_sel * N;
+    std::vector<int> cnt(rows_sel);
+    CU(ctx, cntbuf.reserve((size_t)std::max<long>(N * N, 1) * sizeof(int)));
+    if (want_total) {
+        sym_row_count_kernel<<<(unsigned)((N * N * 32 + 255) / 256), 256, 0, ctx->stream>>>(wbuf.as<int>(), npt, 0, 1, N * N, cntbuf.as<int>());
+        LAUNCH_CHECK(ctx, "sym_row_count_kernel");
+        cnt_all.resize(N * N);
+        CU(ctx, cudaMemcpyAsync(cnt_all.data(), cntbuf.p, (size_t)N * N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        for (long p = 0; p < nplanes_sel; p++)
+            memcpy(cnt.data() + p * N, cnt_all.data() + (k3_lo + p * k3_stride) * N, (size_t)N * sizeof(int));
+    } else if (rows_sel > 0) {
+        sym_row_count_kernel<<<(unsigned)((rows_sel * 32 + 255) / 256), 256, 0, ctx->stream>>>(wbuf.as<int>(), npt, k3_lo, k3_stride,
+                                                                                             rows_sel, cntbuf.as<int>());
+        LAUNCH_CHECK(ctx, "sym_row_count_kernel");
+        CU(ctx, cudaMemcpyAsync(cnt.data(), cntbuf.p, (size_t)rows_sel * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (nirr_total) {
+        int64_t t = 0;
+        if (want_total) for (int c : cnt_all) t += c; else for (int c : cnt) t += c;
+        *nirr_total = t;
+    }
+    // CSR skeleton on the host (N^2 entries), node arrays on the device
+    auto r = std::make_unique<Rule>();
+    r->series_id = sid; r->s = s; r->N = npt; r->full = false; r->nodes_on_host = false;
+    r->h_plane_rowptr.push_back(0);
+    r->h_row_nodeptr.push_back(0);
+    std::vector<int> row_k3;
+    long nnz = 0;
+    for (long p = 0; p < nplanes_sel; p++) {
+        bool open = false;
+        for (long i2 = 0; i2 < N; i2++) {
+            const int c = cnt[p * N + i2];
+            if (!c) continue;
+            open = true;
+            nnz += c;
+            r->h_row_k2.push_back((int)i2);
+            row_k3.push_back((int)(k3_lo + p * k3_stride));
+            r->h_row_nodeptr.push_back(nnz);
+        }
+        if (open) {
+            r->h_plane_k3.push_back((int)(k3_lo + p * k3_stride));
+            r->h_plane_rowptr.push_back((long)r->h_row_k2.size());
+        }
+    }
+    r->np3 = (long)r->h_plane_k3.size();
+    r->nrows = (long)r->h_row_k2.size();
+    r->nnz = nnz;
+    int rc = finish_rule(ctx, r.get());
+    if (rc) return rc;
+    if (nnz > 0) {
+        CU(ctx, cudaMalloc((void**)&r->d_node_k1, (size_t)nnz * sizeof(int)));
+        CU(ctx, cudaMalloc((void**)&r->d_node_w, (size_t)nnz * sizeof(double)));
+        CU(ctx, k3buf.reserve(row_k3.size() * sizeof(int)));
+        CU(ctx, cudaMemcpyAsync(k3buf.p, row_k3.data(), row_k3.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        sym_row_fill_kernel<<<(unsigned)((r->nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            wbuf.as<int>(), npt, k3buf.as<int>(), r->d_row_k2, r->d_row_nodeptr, r->nrows, r->d_node_k1, r->d_node_w);
+        LAUNCH_CHECK(ctx, "sym_row_fill_kernel");
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    uint64_t id = ctx->next_id++;
+    ctx->rules[id] = std::move(r);
+    *out = id;
+    return ABZ_OK;
+}
+
 int32_t abz_rule_destroy(abz_ctx* ctx, abz_rule_t r) {
     if (!ctx) return ABZ_E_INVALID;
     cudaSetDevice(ctx->device);
@@ -700,6 +796,13 @@ int32_t abz_rule_copy_out(abz_ctx* ctx, abz_rule_t rid, double* Hk, double* kfra
     cudaSetDevice(ctx->device);
     Series* s = r->s;
     const long nn = (long)s->n * s->n;
+    if ((kfrac || w) && !r->full && !r->nodes_on_host && r->nnz > 0) {
+        r->h_node_k1.resize(r->nnz); r->h_node_w.resize(r->nnz);
+        CU(ctx, cudaMemcpyAsync(r->h_node_k1.data(), r->d_node_k1, (size_t)r->nnz * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(r->h_node_w.data(), r->d_node_w, (size_t)r->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        r->nodes_on_host = true;
+    }
     if (kfrac || w) {
         for (long p = 0; p < r->np3; p++)
             for (long q = r->h_plane_rowptr[p]; q < r->h_plane_rowptr[p + 1]; q++)
@@ -812,9 +915,8 @@ static size_t eig_smem_bytes(int n, int threads) {
            (size_t)npair * 8 + 64;
 }
 
-static int run_eig(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int n, int mode, int kind, double p0, double p1,
-                   double* evals, double* acc) {
-    if (nk <= 0) return ABZ_OK;
+static int run_eig_jacobi(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int n, int mode, int kind, double p0, double p1,
+                          double* evals, double* acc) {
     int threads = std::min(256, std::max(32, ((n * ((n + 1) / 2) + 31) / 32) * 32));
     size_t smem = eig_smem_bytes(n, threads);
     static bool attr_set = false;
@@ -827,6 +929,38 @@ static int run_eig(abz_ctx* ctx, const double2* H, const double* wnode, long nk,
     LAUNCH_CHECK(ctx, "eig_jacobi_kernel");
     if (mode == 0) {
         reduce_real_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), ncta, 1.0, acc);
+        LAUNCH_CHECK(ctx, "reduce_real_kernel");
+    }
+    return ABZ_OK;
+}
+
+// eigenvalues of nk materialised matrices: Householder tridiagonalisation (CTA per matrix) + implicit QL (thread per matrix)
+static int run_eig(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int n, int mode, int kind, double p0, double p1,
+                   double* evals, double* acc) {
+    if (nk <= 0) return ABZ_OK;
+    if (ctx->eig_algo == 1 || n > EIG_MAXN) return run_eig_jacobi(ctx, H, wnode, nk, n, mode, kind, p0, p1, evals, acc);
+    CU(ctx, ctx->eig_d.reserve((size_t)nk * n * sizeof(double)));
+    CU(ctx, ctx->eig_e.reserve((size_t)nk * n * sizeof(double)));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(eig_tridiag_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(eig_tridiag_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set = true;
+    }
+    const int RP = n > 32 ? 64 : 32;
+    const size_t smem = ((size_t)n * n + 5 * RP) * sizeof(double2);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (4 * RP), (220 * 1024) / (smem + 1024)));
+    const long ncta = std::min<long>(nk, (long)ctx->sm_count * per_sm);
+    if (RP == 32) eig_tridiag_kernel<32><<<(unsigned)ncta, 128, smem, ctx->stream>>>(H, nk, n, ctx->eig_d.as<double>(), ctx->eig_e.as<double>());
+    else eig_tridiag_kernel<64><<<(unsigned)ncta, 256, smem, ctx->stream>>>(H, nk, n, ctx->eig_d.as<double>(), ctx->eig_e.as<double>());
+    LAUNCH_CHECK(ctx, "eig_tridiag_kernel");
+    const long nblk = (nk + 31) / 32;
+    if (mode == 0) CU(ctx, ctx->partial.reserve((size_t)nblk * sizeof(double)));
+    eig_tql_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(ctx->eig_d.as<double>(), ctx->eig_e.as<double>(), wnode, nk, n, mode, kind, p0,
+                                                          p1, evals, ctx->partial.as<double>(), ctx->errflag.as<int>());
+    LAUNCH_CHECK(ctx, "eig_tql_kernel");
+    if (mode == 0) {
+        reduce_real_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), nblk, 1.0, acc);
         LAUNCH_CHECK(ctx, "reduce_real_kernel");
     }
     return ABZ_OK;
@@ -1122,6 +1256,205 @@ int32_t abz_nest_eval(abz_ctx* ctx, abz_nest_t nid, int64_t npts, const double* 
         ctx->force_generic = false;
     }
     return rc;
+}
+
+
+// ---- IAI: the whole nested adaptive solve, control flow on the library's host side -------------------
+namespace {
+
+int pin_reserve(abz_ctx* ctx, void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return ABZ_OK;
+    if (*p) { cudaFreeHost(*p); *p = nullptr; *cap = 0; }
+    size_t want = std::max<size_t>(bytes * 2, (size_t)1 << 16);
+    CU(ctx, cudaHostAlloc(p, want, cudaHostAllocDefault));
+    *cap = want;
+    return ABZ_OK;
+}
+
+struct IaiDeviceBackend {
+    abz_ctx* ctx; Nest* nst; int fkind, vkind; double2 z; const double2* dsig; abz_iai::cplx la, lb;
+    double rtol; int64_t maxevals;
+
+    int run_round(abz_iai::Round& R) {
+        int rc = run_once(R);
+        if (rc == ABZ_RETRY_PIVOTED) {       // the unpivoted fast resolvent saw a tiny pivot: redo the round pivoted
+            ctx->force_generic = true;
+            rc = run_once(R);
+        }
+        return rc;
+    }
+
+    int run_once(abz_iai::Round& R) {
+        Series* s = nst->s;
+        const int n = s->n;
+        const long nn = (long)n * n;
+        const size_t n3 = R.c3_x.size(), n2 = R.c2_x.size(), ns = R.seg_a.size(), nt = R.task_a.size();
+        if (n3 > 0 && nst->ndim != 3) return fail(ctx, ABZ_E_INVALID, "internal: level-2 contraction on a nest with ndim < 3");
+        // ---- pack [c3_x | c3_slot | c2_x | c2_parent | c2_slot | seg_a | seg_b | seg_slot | task_a | task_b | task_atol | task_slot]
+        const size_t words = 2 * n3 + 3 * n2 + 3 * ns + 4 * nt;
+        int rc = pin_reserve(ctx, &ctx->pin_in, &ctx->pin_in_cap, words * 8);
+        if (rc) return rc;
+        CU(ctx, ctx->iai_in.reserve(words * 8 + 8));
+        char* h = (char*)ctx->pin_in;
+        size_t off = 0;
+        auto put = [&](const void* src, size_t cnt) { size_t o = off; if (cnt) memcpy(h + 8 * off, src, 8 * cnt); off += cnt; return o; };
+        const size_t o_c3x = put(R.c3_x.data(), n3), o_c3s = put(R.c3_slot.data(), n3);
+        const size_t o_c2x = put(R.c2_x.data(), n2), o_c2p = put(R.c2_parent.data(), n2), o_c2s = put(R.c2_slot.data(), n2);
+        const size_t o_sa = put(R.seg_a.data(), ns), o_sb = put(R.seg_b.data(), ns), o_ss = put(R.seg_slot.data(), ns);
+        const size_t o_ta = put(R.task_a.data(), nt), o_tb = put(R.task_b.data(), nt), o_tt = put(R.task_atol.data(), nt),
+                     o_ts = put(R.task_slot.data(), nt);
+        if (words) CU(ctx, cudaMemcpyAsync(ctx->iai_in.p, h, words * 8, cudaMemcpyHostToDevice, ctx->stream));
+        const double* dD = ctx->iai_in.as<double>();
+        const long* dL = ctx->iai_in.as<long>();
+        // ---- contractions
+        if (n3) {
+            const long rows = nn * s->M[0] * s->M[1];
+            dim3 grid((unsigned)((rows + 255) / 256), (unsigned)n3);
+            nest_contract_kernel<<<grid, 256, (size_t)s->M[2] * sizeof(double2), ctx->stream>>>(
+                s->c, 0, nullptr, dD + o_c3x, dL + o_c3s, nst->L2, rows, s->M[2], s->lo[2], s->period[2]);
+            LAUNCH_CHECK(ctx, "nest_contract_kernel");
+        }
+        if (n2) {
+            const long rows = nn * s->M[0];
+            const bool root = (nst->ndim == 2);
+            dim3 grid((unsigned)((rows + 255) / 256), (unsigned)n2);
+            nest_contract_kernel<<<grid, 256, (size_t)s->M[1] * sizeof(double2), ctx->stream>>>(
+                root ? s->c : nst->L2, root ? 0 : rows * s->M[1], root ? nullptr : dL + o_c2p, dD + o_c2x, dL + o_c2s, nst->L1, rows,
+                s->M[1], s->lo[1], s->period[1]);
+            LAUNCH_CHECK(ctx, "nest_contract_kernel");
+        }
+        // ---- innermost panels
+        const size_t owords = 4 * ns + 4 * nt + 1;
+        rc = pin_reserve(ctx, &ctx->pin_out, &ctx->pin_out_cap, owords * 8);
+        if (rc) return rc;
+        CU(ctx, ctx->iai_out.reserve(owords * 8));
+        double* dout = ctx->iai_out.as<double>();
+        int* ef = ctx->errflag.as<int>();
+        const bool has_slots = (nst->ndim >= 2);
+        const double2* L1 = has_slots ? nst->L1 : s->c;
+        const long stride = has_slots ? nn * s->M[0] : 0;
+        if (ns) {
+            const long* sslot = has_slots ? dL + o_ss : nullptr;
+            if (n <= 3) {
+                unsigned g = (unsigned)((ns + 7) / 8);
+#define PANEL_LAUNCH(NORB)                                                                                               \
+    nest_panel_small_kernel<NORB><<<g, 128, 0, ctx->stream>>>(L1, stride, dD + o_sa, dD + o_sb, sslot, (long)ns, s->M[0], s->lo[0], \
+                                                             s->period[0], fkind, vkind, z, dsig, la, lb, dout, ef)
+                if (n == 1) PANEL_LAUNCH(1); else if (n == 2) PANEL_LAUNCH(2); else PANEL_LAUNCH(3);
+#undef PANEL_LAUNCH
+                LAUNCH_CHECK(ctx, "nest_panel_small_kernel");
+            } else {
+                const long npts = 15 * (long)ns;
+                CU(ctx, ctx->tmp_a.reserve((size_t)npts * sizeof(double)));
+                CU(ctx, ctx->tmp_b.reserve((size_t)npts * sizeof(long)));
+                CU(ctx, ctx->tmp_c.reserve((size_t)npts * sizeof(double2)));
+                CU(ctx, ctx->Hc.reserve((size_t)npts * nn * sizeof(double2)));
+                panel_nodes_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, ctx->stream>>>(dD + o_sa, dD + o_sb, sslot, (long)ns,
+                                                                                          ctx->tmp_a.as<double>(), ctx->tmp_b.as<long>());
+                LAUNCH_CHECK(ctx, "panel_nodes_kernel");
+                dim3 grid((unsigned)((nn + 127) / 128), (unsigned)npts);
+                nest_eval_h_kernel<<<grid, 128, (size_t)s->M[0] * sizeof(double2), ctx->stream>>>(
+                    L1, stride, has_slots ? ctx->tmp_b.as<long>() : nullptr, ctx->tmp_a.as<double>(), (int)nn, s->M[0], s->lo[0],
+                    s->period[0], ctx->Hc.as<double2>());
+                LAUNCH_CHECK(ctx, "nest_eval_h_kernel");
+                rc = run_matfun(ctx, ctx->Hc.as<double2>(), nullptr, npts, n, fkind, 1, ctx->zbuf.as<double2>(), dsig, 1,
+                                ctx->tmp_c.as<double2>());
+                if (rc) return rc;
+                panel_combine_kernel<<<(unsigned)((ns + 127) / 128), 128, 0, ctx->stream>>>(ctx->tmp_c.as<double2>(), dD + o_sa, dD + o_sb,
+                                                                                          (long)ns, vkind, la, lb, dout);
+                LAUNCH_CHECK(ctx, "panel_combine_kernel");
+            }
+        }
+        if (nt) {
+            if (n > 3 || !has_slots) return fail(ctx, ABZ_E_UNSUPPORTED, "device-side innermost integrals need norb <= 3 and ndim >= 2");
+            rc = launch_leaf(R, dD + o_ta, dD + o_tb, dD + o_tt, dL + o_ts, (long)nt, dout + 4 * ns);
+            if (rc) return rc;
+        }
+        CU(ctx, cudaMemcpyAsync(dout + 4 * ns + 4 * nt, ef, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->pin_out, dout, owords * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        const double* ho = (const double*)ctx->pin_out;
+        int flag = 0;
+        memcpy(&flag, ho + 4 * ns + 4 * nt, sizeof(int));
+        if (flag) {
+            cudaMemsetAsync(ef, 0, sizeof(int), ctx->stream);
+            if ((flag & 2) && !(flag & 1) && !ctx->force_generic) return ABZ_RETRY_PIVOTED;
+            if (flag & 4) return fail(ctx, ABZ_E_UNSUPPORTED, "abz_iai_solve: an innermost integral outgrew the device segment heap");
+            return fail(ctx, ABZ_E_SINGULAR, "abz_iai_solve: singular matrix or NaN/Inf in the integrand");
+        }
+        R.seg_I.resize(ns); R.seg_D.resize(ns);
+        for (size_t i = 0; i < ns; i++) {
+            R.seg_I[i] = abz_iai::cplx{ho[4 * i], ho[4 * i + 1]};
+            R.seg_D[i] = abz_iai::cplx{ho[4 * i + 2], ho[4 * i + 3]};
+        }
+        R.task_I.resize(nt); R.task_E.resize(nt); R.task_ne.resize(nt);
+        const double* ht = ho + 4 * ns;
+        for (size_t i = 0; i < nt; i++) {
+            R.task_I[i] = abz_iai::cplx{ht[4 * i], ht[4 * i + 1]};
+            R.task_E[i] = ht[4 * i + 2];
+            int64_t ne; memcpy(&ne, ht + 4 * i + 3, 8);
+            R.task_ne[i] = ne;
+        }
+        return ABZ_OK;
+    }
+
+    int launch_leaf(abz_iai::Round&, const double* ta, const double* tb, const double* tt, const long* ts, long nt, double* out) {
+        Series* s = nst->s;
+        const long stride = (long)s->n * s->n * s->M[0];
+        // global spill area for segment heaps deeper than the shared-memory levels
+        CU(ctx, ctx->tmp_d.reserve((size_t)nt * LEAF_SPILL * sizeof(LeafSeg) + 64));
+        unsigned g = (unsigned)((nt + LEAF_WARPS - 1) / LEAF_WARPS);
+        LeafSeg* spill = reinterpret_cast<LeafSeg*>(ctx->tmp_d.as<char>() + 64);
+#define LEAF_LAUNCH(NORB)                                                                                              \
+    iai_leaf_kernel<NORB><<<g, LEAF_WARPS * 32, 0, ctx->stream>>>(nst->L1, stride, ta, tb, tt, ts, nt, s->M[0], s->lo[0], s->period[0], \
+                                                                 fkind, vkind, z, dsig, la, lb, rtol, (long long)maxevals, spill, out, \
+                                                                 ctx->errflag.as<int>())
+        if (s->n == 1) LEAF_LAUNCH(1); else if (s->n == 2) LEAF_LAUNCH(2); else LEAF_LAUNCH(3);
+#undef LEAF_LAUNCH
+        LAUNCH_CHECK(ctx, "iai_leaf_kernel");
+        return ABZ_OK;
+    }
+};
+
+}  // namespace
+
+int32_t abz_iai_solve(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const double* la, const double* lb, int32_t fkind,
+                      int32_t vkind, const double* z, const double* sigma, const double* lin, double atol, double rtol,
+                      int64_t maxevals, int32_t flags, double* out, int64_t* stats) {
+    if (!ctx) return ABZ_E_INVALID;
+    Nest* nst = get_nest(ctx, nid);
+    if (!nst) return fail(ctx, ABZ_E_INVALID, "unknown nest handle");
+    if ((lkind != 0 && lkind != 1) || !la || (lkind == 0 && !lb) || !out || vkind < 0 || vkind > 2 ||
+        (fkind != ABZ_F_RESOLVENT_TRACE && fkind != ABZ_F_TRACE_H) || (fkind == ABZ_F_RESOLVENT_TRACE && !z) || (vkind == 2 && !lin) ||
+        !(atol >= 0) || !(rtol >= 0) || maxevals < 1)
+        return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    cudaSetDevice(ctx->device);
+    Series* s = nst->s;
+    if (fkind == ABZ_F_TRACE_H) sigma = nullptr;
+    int rc = upload_params(ctx, s->n, 1, fkind == ABZ_F_RESOLVENT_TRACE ? z : nullptr, sigma);
+    if (rc) return rc;
+    abz_iai::Limits lims;
+    lims.kind = lkind; lims.nd = nst->ndim; lims.s = 1.0;
+    for (int d = 0; d < nst->ndim; d++) { lims.a[d] = la[d]; lims.b[d] = lb ? lb[d] : 0.0; }
+    IaiDeviceBackend be;
+    be.ctx = ctx; be.nst = nst; be.fkind = fkind; be.vkind = vkind;
+    be.z = make_double2(z ? z[0] : 0.0, z ? z[1] : 0.0);
+    be.dsig = sigma ? ctx->sigbuf.as<double2>() : nullptr;
+    be.la = abz_iai::cplx{lin ? lin[0] : 1.0, lin ? lin[1] : 0.0};
+    be.lb = abz_iai::cplx{lin ? lin[2] : 0.0, lin ? lin[3] : 0.0};
+    be.rtol = rtol; be.maxevals = maxevals;
+    const bool leaf = (flags & ABZ_IAI_DEVICE_LEAVES) && s->n <= 3 && nst->ndim >= 2;
+    const long launches0 = ctx->launches;
+    abz_iai::Engine<IaiDeviceBackend> eng(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, leaf);
+    rc = eng.run();
+    ctx->force_generic = false;
+    if (stats) { stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = ctx->launches - launches0; }
+    if (rc == abz_iai::IAI_E_NAN) return fail(ctx, ABZ_E_SINGULAR, eng.error);
+    if (rc == abz_iai::IAI_E_ARENA) return fail(ctx, ABZ_E_OOM, eng.error);
+    if (rc == abz_iai::IAI_E_STALL) return fail(ctx, ABZ_E_INVALID, eng.error);
+    if (rc) return rc;
+    out[0] = eng.result.re; out[1] = eng.result.im; out[2] = eng.result_err;
+    return ABZ_OK;
 }
 
 

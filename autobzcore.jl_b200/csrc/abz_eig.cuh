@@ -150,6 +150,164 @@ __global__ void eig_jacobi_kernel(const double2* __restrict__ H, const double* _
     if (mode == 0 && tid == 0) partial[blockIdx.x] = my_acc;
 }
 
+// ---- K4-fast: Householder tridiagonalisation (one CTA per k, matrix in shared memory) + implicit QL per thread ----
+// eigen(Hermitian(H(k))) (src/dos_ggr.jl:19,34), eigenvalues only.  Stage A reduces (H + H^H)/2 to a real symmetric
+// tridiagonal matrix by n-2 Hermitian Householder reflections P = I - tau v v^H (real tau, v = y + e^{i arg y_1}|y| e_1):
+// A22 <- A22 - v w^H - w v^H with p = tau A22 v, w = p - (tau/2)(v^H p) v; only |beta| = |y| of the complex off-diagonal
+// is kept (the spectrum does not depend on its phase).  Thread (i, q) of a 4*RP-thread CTA owns row i and the trailing
+// columns c+1+q, c+5+q, ...: shared-memory reads are conflict-free (lanes = consecutive rows of one column).
+// Outputs are structure-of-arrays d[i*nk + k], e[i*nk + k] so that stage B (one thread per matrix) loads coalesced.
+template <int RP>
+__global__ void __launch_bounds__(4 * RP)
+eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout) {
+    extern __shared__ double2 et_smem[];
+    double2* A = et_smem;            // [n*n], column-major, lda = n
+    double2* pb = A + (long)n * n;   // [4][RP] partial mat-vec sums
+    double2* wv = pb + 4 * RP;       // [RP]
+    const int tid = threadIdx.x, i = tid % RP, q = tid / RP, lane = tid & 31, warp = tid >> 5;
+    for (long k = blockIdx.x; k < nk; k += gridDim.x) {
+        __syncthreads();
+        const double2* Hk = H + k * (long)n * n;
+        for (int e = tid; e < n * n; e += 4 * RP) {
+            int r = e % n, j = e / n;
+            double2 a = Hk[r + (long)j * n], b = Hk[j + (long)r * n];
+            A[r + j * n] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+        }
+        __syncthreads();
+        for (int c = 0; c < n - 1; c++) {
+            const double2* col = A + (long)c * n;
+            // Householder vector of column c (every warp computes it redundantly: no block-level reduction needed)
+            double sig = 0.0;
+            for (int r = c + 2 + lane; r < n; r += 32) { double2 a = col[r]; sig = fma(a.x, a.x, fma(a.y, a.y, sig)); }
+            sig = warp_sum(sig);
+            const double2 alpha = col[c + 1];
+            const double aa = alpha.x * alpha.x + alpha.y * alpha.y;
+            const double ynorm = sqrt(sig + aa);
+            if (tid == 0) { dout[(long)c * nk + k] = A[c + c * n].x; eout[(long)c * nk + k] = ynorm; }
+            if (sig == 0.0) continue;               // column already tridiagonal (always true for c = n-2)
+            const double absa = sqrt(aa);
+            const double2 ph = absa > 0.0 ? make_double2(alpha.x / absa, alpha.y / absa) : make_double2(1.0, 0.0);
+            const double2 v0 = make_double2(alpha.x + ph.x * ynorm, alpha.y + ph.y * ynorm);
+            const double tau = 1.0 / (ynorm * (ynorm + absa));
+            const bool active = (i > c && i < n);
+            // p = A22 v (partial over this thread's columns)
+            double2 acc = make_double2(0.0, 0.0);
+            if (active)
+                for (int j = c + 1 + q; j < n; j += 4) {
+                    const double2 vj = (j == c + 1) ? v0 : col[j];
+                    acc = cfma(acc, A[i + j * n], vj);
+                }
+            pb[q * RP + i] = acc;
+            __syncthreads();
+            // w = p - (tau/2)(v^H p) v, every warp redundantly; warp 0 publishes it
+            double2 pr[RP / 32], vr[RP / 32];
+            double dot = 0.0;
+#pragma unroll
+            for (int t = 0; t < RP / 32; t++) {
+                const int r = lane + 32 * t;
+                pr[t] = make_double2(0.0, 0.0); vr[t] = make_double2(0.0, 0.0);
+                if (r > c && r < n) {
+                    const double2 s0 = pb[r], s1 = pb[RP + r], s2 = pb[2 * RP + r], s3 = pb[3 * RP + r];
+                    pr[t] = make_double2(tau * ((s0.x + s1.x) + (s2.x + s3.x)), tau * ((s0.y + s1.y) + (s2.y + s3.y)));
+                    vr[t] = (r == c + 1) ? v0 : col[r];
+                    dot += vr[t].x * pr[t].x + vr[t].y * pr[t].y;      // Re(conj(v) p); the imaginary part is rounding noise
+                }
+            }
+            dot = warp_sum(dot);
+            const double gam = 0.5 * tau * dot;
+            if (warp == 0) {
+#pragma unroll
+                for (int t = 0; t < RP / 32; t++) {
+                    const int r = lane + 32 * t;
+                    if (r > c && r < n) wv[r] = make_double2(pr[t].x - gam * vr[t].x, pr[t].y - gam * vr[t].y);
+                }
+            }
+            __syncthreads();
+            // A22 <- A22 - v w^H - w v^H
+            if (active) {
+                const double2 vi = (i == c + 1) ? v0 : col[i];
+                const double2 wi = wv[i];
+                for (int j = c + 1 + q; j < n; j += 4) {
+                    const double2 vj = (j == c + 1) ? v0 : col[j];
+                    const double2 wj = wv[j];
+                    double2 a = A[i + j * n];
+                    a.x -= vi.x * wj.x + vi.y * wj.y + wi.x * vj.x + wi.y * vj.y;
+                    a.y -= vi.y * wj.x - vi.x * wj.y + wi.y * vj.x - wi.x * vj.y;
+                    A[i + j * n] = a;
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) { dout[(long)(n - 1) * nk + k] = A[(n - 1) + (n - 1) * n].x; eout[(long)(n - 1) * nk + k] = 0.0; }
+    }
+}
+
+// Stage B: eigenvalues of the real symmetric tridiagonal (d, e) by the implicit QL algorithm with Wilkinson shifts
+// (EISPACK imtql1 / "tqli" without vectors), one thread per matrix.  mode 0: partial[cta] = sum_k wnode_k sum_n g(e_n);
+// mode 1: evals[k*n + i] ascending.
+constexpr int EIG_MAXN = 64;
+__global__ void __launch_bounds__(32)
+eig_tql_kernel(const double* __restrict__ din, const double* __restrict__ ein, const double* __restrict__ wnode, long nk, int n,
+               int mode, int kind, double p0, double p1, double* __restrict__ evals, double* __restrict__ partial,
+               int* __restrict__ errflag) {
+    const long k = (long)blockIdx.x * 32 + threadIdx.x;
+    double d[EIG_MAXN], e[EIG_MAXN];
+    double val = 0.0;
+    if (k < nk) {
+        bool bad = false;
+        for (int i = 0; i < n; i++) { d[i] = din[(long)i * nk + k]; e[i] = ein[(long)i * nk + k]; bad |= !(isfinite(d[i]) && isfinite(e[i])); }
+        if (bad) { *errflag = 1; }
+        else {
+            for (int l = 0; l < n; l++) {
+                int iter = 0, m;
+                do {
+                    for (m = l; m < n - 1; m++) {
+                        const double dd = fabs(d[m]) + fabs(d[m + 1]);
+                        if (fabs(e[m]) <= 2.220446049250313e-16 * dd) break;
+                    }
+                    if (m != l) {
+                        if (iter++ == 60) { *errflag = 1; break; }
+                        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                        double r = hypot(g, 1.0);
+                        g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? r : -r));
+                        double s = 1.0, c = 1.0, p = 0.0;
+                        int i;
+                        for (i = m - 1; i >= l; i--) {
+                            double f = s * e[i], b = c * e[i];
+                            e[i + 1] = (r = hypot(f, g));
+                            if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+                            s = f / r; c = g / r;
+                            g = d[i + 1] - p;
+                            r = (d[i] - g) * s + 2.0 * c * b;
+                            d[i + 1] = g + (p = s * r);
+                            g = c * r - b;
+                        }
+                        if (r == 0.0 && i >= l) continue;
+                        d[l] -= p; e[l] = g; e[m] = 0.0;
+                    }
+                } while (m != l);
+            }
+            if (mode == 1) {
+                for (int i = 1; i < n; i++) {     // insertion sort, ascending
+                    const double x = d[i];
+                    int j = i - 1;
+                    while (j >= 0 && d[j] > x) { d[j + 1] = d[j]; j--; }
+                    d[j + 1] = x;
+                }
+                for (int i = 0; i < n; i++) evals[k * n + i] = d[i];
+            } else {
+                double v = 0.0;
+                for (int i = 0; i < n; i++) v += eig_kernel_value(d[i], kind, p0, p1);
+                val = (wnode ? wnode[k] : 1.0) * v;
+            }
+        }
+    }
+    if (mode == 0) {
+        val = warp_sum(val);
+        if (threadIdx.x == 0) partial[blockIdx.x] = val;
+    }
+}
+
 // deterministic reduction of real partials: acc[0] += scale * sum_c partial[c]
 __global__ void __launch_bounds__(256) reduce_real_kernel(const double* __restrict__ partial, long n, double scale, double* __restrict__ acc) {
     __shared__ double sx[256];

@@ -5,6 +5,7 @@
 #pragma once
 #include "abz_common.cuh"
 #include "abz_kernels.cuh"
+#include "abz_iai_engine.hpp"
 
 namespace abz {
 
@@ -28,18 +29,13 @@ nest_contract_kernel(const double2* __restrict__ src, long src_stride, const lon
     dst[slot[i] * rows + row] = acc;
 }
 
-// innermost closure for norb <= 3: evaluate the 1-D series of slot1[i] at x1[i] and apply the integrand
-// (workspace_evaluate! + f.f(v, p), src/fourier.jl:452-456).  One thread per node.
+// innermost closure for norb <= 3: evaluate the 1-D series c[M1][NN] at xi and apply the integrand
+// (workspace_evaluate! + f.f(v, p), src/fourier.jl:452-456)
 template <int NORB>
-__global__ void __launch_bounds__(128)
-nest_eval_small_kernel(const double2* __restrict__ L1, long l1_stride, const long* __restrict__ slot1,
-                       const double* __restrict__ x1, long npts, int M1, int lo, double period, int fkind, double2 z,
-                       const double2* __restrict__ sigma, double2* __restrict__ y, int* __restrict__ errflag) {
+__device__ __forceinline__ double2 nest_point_small(const double2* __restrict__ c, double xi, int M1, int lo, double period,
+                                                    int fkind, double2 z, const double2* __restrict__ sigma,
+                                                    int* __restrict__ errflag) {
     constexpr int NN = NORB * NORB;
-    const long i = (long)blockIdx.x * 128 + threadIdx.x;
-    if (i >= npts) return;
-    const double2* c = L1 + (slot1 ? slot1[i] * l1_stride : 0);
-    const double xi = x1[i];
     double2 h[NN];
 #pragma unroll
     for (int e = 0; e < NN; e++) h[e] = make_double2(0.0, 0.0);
@@ -57,7 +53,203 @@ nest_eval_small_kernel(const double2* __restrict__ L1, long l1_stride, const lon
         t = small_resolvent_trace<NORB>(h, z, sigma);
         if (!(isfinite(t.x) && isfinite(t.y))) *errflag = 1;
     }
-    y[i] = t;
+    return t;
+}
+
+// One thread per node.
+template <int NORB>
+__global__ void __launch_bounds__(128)
+nest_eval_small_kernel(const double2* __restrict__ L1, long l1_stride, const long* __restrict__ slot1,
+                       const double* __restrict__ x1, long npts, int M1, int lo, double period, int fkind, double2 z,
+                       const double2* __restrict__ sigma, double2* __restrict__ y, int* __restrict__ errflag) {
+    const long i = (long)blockIdx.x * 128 + threadIdx.x;
+    if (i >= npts) return;
+    const double2* c = L1 + (slot1 ? slot1[i] * l1_stride : 0);
+    y[i] = nest_point_small<NORB>(c, x1[i], M1, lo, period, fkind, z, sigma, errflag);
+}
+
+// Innermost GK(7,15) panels for norb <= 3, fused: 16 lanes per panel [a,b] evaluate the 15 nodes of
+// QuadGK.evalrule on the series in level-1 slot `seg_slot`, apply the integrand, and lane 0 combines them in
+// evalrule's operation order (no FMA contraction: bit-identical to the host's gk_combine).
+// out[4*seg] = (I.re, I.im, D.re, D.im), D = Kronrod - Gauss.
+template <int NORB>
+__global__ void __launch_bounds__(128)
+nest_panel_small_kernel(const double2* __restrict__ L1, long l1_stride, const double* __restrict__ seg_a,
+                        const double* __restrict__ seg_b, const long* __restrict__ seg_slot, long nseg, int M1, int lo,
+                        double period, int fkind, int vkind, double2 z, const double2* __restrict__ sigma,
+                        abz_iai::cplx la, abz_iai::cplx lb, double* __restrict__ out, int* __restrict__ errflag) {
+    __shared__ abz_iai::cplx vals[8][16];
+    const int ls = threadIdx.x >> 4, j = threadIdx.x & 15;
+    const long seg = (long)blockIdx.x * 8 + ls;
+    double a = 0.0, b = 0.0;
+    if (seg < nseg) {
+        a = seg_a[seg]; b = seg_b[seg];
+        if (j < 15) {
+            const double2* c = L1 + (seg_slot ? seg_slot[seg] * l1_stride : 0);
+            double2 y = nest_point_small<NORB>(c, abz_iai::gk_node(a, b, j), M1, lo, period, fkind, z, sigma, errflag);
+            vals[ls][j] = abz_iai::post_value(vkind, abz_iai::cplx{y.x, y.y}, la, lb);
+        }
+    }
+    __syncthreads();
+    if (seg < nseg && j == 0) {
+        abz_iai::cplx I, D;
+        abz_iai::gk_combine(a, b, vals[ls], &I, &D);
+        out[4 * seg] = I.re; out[4 * seg + 1] = I.im; out[4 * seg + 2] = D.re; out[4 * seg + 3] = D.im;
+    }
+}
+
+// general norb: nodes of the queued panels (then nest_eval_h_kernel + the resolvent kernel + panel_combine_kernel)
+__global__ void __launch_bounds__(128)
+panel_nodes_kernel(const double* __restrict__ seg_a, const double* __restrict__ seg_b, const long* __restrict__ seg_slot,
+                   long nseg, double* __restrict__ x, long* __restrict__ slot) {
+    const long t = (long)blockIdx.x * 128 + threadIdx.x;
+    if (t >= nseg * 15) return;
+    const long seg = t / 15; const int j = (int)(t % 15);
+    x[t] = abz_iai::gk_node(seg_a[seg], seg_b[seg], j);
+    if (seg_slot) slot[t] = seg_slot[seg];
+}
+__global__ void __launch_bounds__(128)
+panel_combine_kernel(const double2* __restrict__ y, const double* __restrict__ seg_a, const double* __restrict__ seg_b,
+                     long nseg, int vkind, abz_iai::cplx la, abz_iai::cplx lb, double* __restrict__ out) {
+    const long seg = (long)blockIdx.x * 128 + threadIdx.x;
+    if (seg >= nseg) return;
+    abz_iai::cplx f[15], I, D;
+#pragma unroll
+    for (int j = 0; j < 15; j++) { double2 v = y[seg * 15 + j]; f[j] = abz_iai::post_value(vkind, abz_iai::cplx{v.x, v.y}, la, lb); }
+    abz_iai::gk_combine(seg_a[seg], seg_b[seg], f, &I, &D);
+    out[4 * seg] = I.re; out[4 * seg + 1] = I.im; out[4 * seg + 2] = D.re; out[4 * seg + 3] = D.im;
+}
+
+// ---- device-side innermost adaptive integrals ------------------------------------------------------------
+// One warp per innermost 1-D integral (QuadGK do_quadgk/adapt/refine on the series of one level-1 slot):
+// lanes 0-14 / 16-30 evaluate the 15 nodes of the two halves of the popped segment, lanes 0 and 16 combine them
+// (evalrule's order, no FMA contraction), lane 0 keeps the DataStructures.jl binary heap (Reverse on E): entries
+// 1..63 in shared memory, deeper ones in a per-task global spill area.  Same arithmetic per node as
+// nest_panel_small_kernel, hence the same accept/refine decisions as the host-driven engine.
+constexpr int LEAF_WARPS = 4;
+constexpr int LEAF_SMEM_SEGS = 63;
+constexpr int LEAF_SPILL = 1024;
+struct LeafSeg { double E, a, b, Ire, Iim; };
+
+__device__ __forceinline__ double leaf_abs(abz_iai::cplx v) { return v.im == 0.0 ? fabs(v.re) : hypot(v.re, v.im); }
+
+template <int NORB>
+__global__ void __launch_bounds__(LEAF_WARPS * 32)
+iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __restrict__ task_a,
+                const double* __restrict__ task_b, const double* __restrict__ task_atol, const long* __restrict__ task_slot,
+                long ntask, int M1, int lo, double period, int fkind, int vkind, double2 z, const double2* __restrict__ sigma,
+                abz_iai::cplx la, abz_iai::cplx lb, double rtol, long long maxevals, LeafSeg* __restrict__ spill,
+                double* __restrict__ out, int* __restrict__ errflag) {
+    __shared__ LeafSeg heap_s[LEAF_WARPS][LEAF_SMEM_SEGS];
+    __shared__ abz_iai::cplx vals[LEAF_WARPS][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long task = (long)blockIdx.x * LEAF_WARPS + w;
+    if (task >= ntask) return;
+    const double2* c = L1 + task_slot[task] * l1_stride;
+    const double atol = task_atol[task];
+    LeafSeg* hs = heap_s[w];
+    LeafSeg* hg = spill + task * LEAF_SPILL;
+#define LEAF_AT(i) (((i) <= LEAF_SMEM_SEGS) ? hs[(i) - 1] : hg[(i) - 1 - LEAF_SMEM_SEGS])
+    const int half = lane >> 4, j = lane & 15;
+    // ---- first panel
+    double pa = task_a[task], pb = task_b[task];
+    if (half == 0 && j < 15) {
+        double2 y = nest_point_small<NORB>(c, abz_iai::gk_node(pa, pb, j), M1, lo, period, fkind, z, sigma, errflag);
+        vals[w][lane] = abz_iai::post_value(vkind, abz_iai::cplx{y.x, y.y}, la, lb);
+    }
+    __syncwarp();
+    abz_iai::cplx I{0.0, 0.0};
+    double E = 0.0;
+    long len = 1;
+    long long ne = 15;
+    int go = 0;
+    if (lane == 0) {
+        abz_iai::cplx D;
+        abz_iai::gk_combine(pa, pb, vals[w], &I, &D);
+        E = leaf_abs(D);
+        hs[0] = LeafSeg{E, pa, pb, I.re, I.im};
+        if (!isfinite(E)) { atomicOr(errflag, 1); go = 0; }
+        else go = !(ne >= maxevals || E <= atol || E <= rtol * leaf_abs(I));
+    }
+    go = __shfl_sync(0xffffffffu, go, 0);
+    while (go) {
+        // ---- pop the segment with the largest error (lane 0), bisect it
+        double sa = 0.0, sb = 0.0, sE = 0.0;
+        abz_iai::cplx sI{0.0, 0.0};
+        if (lane == 0) {
+            LeafSeg top = hs[0];
+            sa = top.a; sb = top.b; sE = top.E; sI = abz_iai::cplx{top.Ire, top.Iim};
+            LeafSeg y = LEAF_AT(len);
+            len--;
+            if (len > 0) {   // percolate_down(xs, 1, y)
+                long i = 1;
+                for (;;) {
+                    long l = 2 * i;
+                    if (l > len) break;
+                    long r = l + 1;
+                    long jj = l;
+                    if (r <= len) { if (!(LEAF_AT(r).E < LEAF_AT(l).E)) jj = r; }
+                    if (!(y.E < LEAF_AT(jj).E)) break;
+                    LEAF_AT(i) = LEAF_AT(jj);
+                    i = jj;
+                }
+                LEAF_AT(i) = y;
+            }
+        }
+        sa = __shfl_sync(0xffffffffu, sa, 0);
+        sb = __shfl_sync(0xffffffffu, sb, 0);
+        const double mid = (sa + sb) / 2;
+        pa = half ? mid : sa;
+        pb = half ? sb : mid;
+        __syncwarp();
+        if (j < 15) {
+            double2 y = nest_point_small<NORB>(c, abz_iai::gk_node(pa, pb, j), M1, lo, period, fkind, z, sigma, errflag);
+            vals[w][lane] = abz_iai::post_value(vkind, abz_iai::cplx{y.x, y.y}, la, lb);
+        }
+        __syncwarp();
+        abz_iai::cplx nI{0.0, 0.0};
+        double nE = 0.0;
+        if (j == 0) {
+            abz_iai::cplx D;
+            abz_iai::gk_combine(pa, pb, vals[w] + 16 * half, &nI, &D);
+            nE = leaf_abs(D);
+        }
+        const double I2re = __shfl_sync(0xffffffffu, nI.re, 16), I2im = __shfl_sync(0xffffffffu, nI.im, 16);
+        const double E2 = __shfl_sync(0xffffffffu, nE, 16);
+        if (lane == 0) {
+            I = abz_iai::cplx{(I.re - sI.re) + nI.re + I2re, (I.im - sI.im) + nI.im + I2im};
+            E = (E - sE) + nE + E2;
+            ne += 30;
+            if (!(isfinite(nE) && isfinite(E2))) { atomicOr(errflag, 1); go = 0; }
+            else if (len + 2 > LEAF_SMEM_SEGS + LEAF_SPILL) { atomicOr(errflag, 4); go = 0; }
+            else {
+                LeafSeg sg[2] = {LeafSeg{nE, sa, mid, nI.re, nI.im}, LeafSeg{E2, mid, sb, I2re, I2im}};
+#pragma unroll
+                for (int t = 0; t < 2; t++) {   // push!: percolate_up(xs, len, x)
+                    len++;
+                    long i = len;
+                    for (;;) {
+                        long p = i / 2;
+                        if (p < 1) break;
+                        if (!(LEAF_AT(p).E < sg[t].E)) break;
+                        LEAF_AT(i) = LEAF_AT(p);
+                        i = p;
+                    }
+                    LEAF_AT(i) = sg[t];
+                }
+                go = (E > atol && E > rtol * leaf_abs(I) && ne < maxevals);
+            }
+        }
+        go = __shfl_sync(0xffffffffu, go, 0);
+    }
+    if (lane == 0) {
+        abz_iai::cplx Iv{hs[0].Ire, hs[0].Iim};
+        double Ev = hs[0].E;
+        for (long k = 2; k <= len; k++) { const LeafSeg sgk = LEAF_AT(k); Iv.re += sgk.Ire; Iv.im += sgk.Iim; Ev += sgk.E; }
+        out[4 * task] = Iv.re; out[4 * task + 1] = Iv.im; out[4 * task + 2] = Ev;
+        reinterpret_cast<long long*>(out)[4 * task + 3] = ne;
+    }
+#undef LEAF_AT
 }
 
 // general norb: evaluate H at the nodes into a buffer (then the generic resolvent kernel runs on it)
@@ -147,6 +339,44 @@ symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restri
     }
     if (is_min && !has_self) cnt++;   // identity absent from the list
     wsym[idx] = is_min ? cnt : 0;
+}
+
+// CSR construction of the symmetry-reduced rule on the device (the reference's flags arrays,
+// src/fourier.jl:237-243): one warp per (k2, k3) row of the dense weight array.
+// pass 1: rowcnt[p*N + i2] = #irreducible nodes in row i2 of selected plane p (i3 = k3_lo + p*k3_stride)
+__global__ void __launch_bounds__(256)
+sym_row_count_kernel(const int* __restrict__ wsym, int N, int k3_lo, int k3_stride, long nrows_all, int* __restrict__ rowcnt) {
+    const long row = ((long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows_all) return;
+    const long p = row / N, i2 = row % N;
+    const int* w = wsym + (((long)k3_lo + p * k3_stride) * N + i2) * N;
+    int c = 0;
+    for (int i1 = lane; i1 < N; i1 += 32) c += (w[i1] != 0);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if (lane == 0) rowcnt[row] = c;
+}
+// pass 2: node_k1 / node_w of every non-empty row at its CSR offset, k1 ascending
+__global__ void __launch_bounds__(256)
+sym_row_fill_kernel(const int* __restrict__ wsym, int N, const int* __restrict__ row_k3, const int* __restrict__ row_k2,
+                    const long* __restrict__ row_nodeptr, long nrows, int* __restrict__ node_k1, double* __restrict__ node_w) {
+    const long row = ((long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const int* w = wsym + ((long)row_k3[row] * N + row_k2[row]) * N;
+    long off = row_nodeptr[row];
+    for (int base = 0; base < N; base += 32) {
+        const int i1 = base + lane;
+        const int v = (i1 < N) ? w[i1] : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, v != 0);
+        if (v != 0) {
+            const long o = off + __popc(m & ((1u << lane) - 1u));
+            node_k1[o] = i1;
+            node_w[o] = (double)v;
+        }
+        off += __popc(m);
+    }
 }
 
 }  // namespace abz

@@ -1,0 +1,392 @@
+// Host-side IAI engine: nested adaptive Gauss-Kronrod (7,15) with the reference's control flow,
+// batched level-synchronously for the device.  Pure C++ (no CUDA) so that the same state machine can
+// be driven by the device backend (abz_api.cu) and, in tests/, by a CPU backend.
+//
+// Restates do_solve(::FourierIntegrand, lims, ::NestedQuad) + init_nest (src/fourier.jl:432-510) on
+// top of QuadGK.jl's do_quadgk / adapt / refine / evalrule and DataStructures.jl's binary heap with
+// Base.Reverse on Segment.E (call site of IteratedIntegration.auxquadgk: src/algorithms.jl:236-237).
+// Every 1-D adaptive integral is an independent state machine whose trajectory depends only on its
+// own integrand values and tolerance; evaluating all live panels of all live integrals in one device
+// batch per round leaves every accept/refine decision - and hence EvalCounter's numevals
+// (src/fourier.jl:516-523) - unchanged with respect to the sequential recursion.
+//
+// With leaf_tasks = true the innermost (level-0) integrals are not run by this state machine: each is
+// handed to the backend as ONE task (slot, a, b, atol) that returns (I, E, numevals) - the device runs
+// the whole 1-D adaptive loop with one warp per task (abz_iai.cuh, iai_leaf_kernel).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <deque>
+#include <string>
+#include <vector>
+
+#if defined(__CUDACC__)
+#define ABZ_HD __host__ __device__
+#else
+#define ABZ_HD
+#endif
+
+namespace abz_iai {
+
+struct cplx { double re, im; };
+
+// round-to-nearest products/sums that the compiler must not contract into FMAs, so that host and
+// device combine panels with bit-identical arithmetic (QuadGK.evalrule's operation order)
+ABZ_HD inline double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+ABZ_HD inline double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+ABZ_HD inline cplx cadd_rn(cplx a, cplx b) { return cplx{add_rn(a.re, b.re), add_rn(a.im, b.im)}; }
+ABZ_HD inline cplx csub_rn(cplx a, cplx b) { return cplx{add_rn(a.re, -b.re), add_rn(a.im, -b.im)}; }
+ABZ_HD inline cplx cscale_rn(cplx a, double w) { return cplx{mul_rn(a.re, w), mul_rn(a.im, w)}; }
+
+// QUADPACK qk15 abscissae (x <= 0 half, as QuadGK.kronrod(7) orders them), Kronrod and Gauss weights
+#define ABZ_GK_X0 (-0.991455371120812639206854697526329)
+#define ABZ_GK_X1 (-0.949107912342758524526189684047851)
+#define ABZ_GK_X2 (-0.864864423359769072789712788640926)
+#define ABZ_GK_X3 (-0.741531185599394439863864773280788)
+#define ABZ_GK_X4 (-0.586087235467691130294144838258730)
+#define ABZ_GK_X5 (-0.405845151377397166906606412076961)
+#define ABZ_GK_X6 (-0.207784955007898467600689403773245)
+#define ABZ_GK_W0 0.022935322010529224963732008058970
+#define ABZ_GK_W1 0.063092092629978553290700663189204
+#define ABZ_GK_W2 0.104790010322250183839876322541518
+#define ABZ_GK_W3 0.140653259715525918745189590510238
+#define ABZ_GK_W4 0.169004726639267902826583426598550
+#define ABZ_GK_W5 0.190350578064785409913256402421014
+#define ABZ_GK_W6 0.204432940075298892414161999234649
+#define ABZ_GK_W7 0.209482141084727828012999174891714
+#define ABZ_GK_G0 0.129484966168869693270611432679082
+#define ABZ_GK_G1 0.279705391489276667901467771423780
+#define ABZ_GK_G2 0.381830050505118944950369775488975
+#define ABZ_GK_G3 0.417959183673469387755102040816327
+
+// offsets (1 + x) and (1 - x) in QuadGK.evalrule's evaluation order:
+// (x2+,x2-),(x1+,x1-),(x4+,x4-),(x3+,x3-),(x6+,x6-),(x5+,x5-), centre, (x7+,x7-)
+ABZ_HD inline double gk_off(int j) {
+    switch (j) {
+        case 0: return 1.0 + ABZ_GK_X1;
+        case 1: return 1.0 - ABZ_GK_X1;
+        case 2: return 1.0 + ABZ_GK_X0;
+        case 3: return 1.0 - ABZ_GK_X0;
+        case 4: return 1.0 + ABZ_GK_X3;
+        case 5: return 1.0 - ABZ_GK_X3;
+        case 6: return 1.0 + ABZ_GK_X2;
+        case 7: return 1.0 - ABZ_GK_X2;
+        case 8: return 1.0 + ABZ_GK_X5;
+        case 9: return 1.0 - ABZ_GK_X5;
+        case 10: return 1.0 + ABZ_GK_X4;
+        case 11: return 1.0 - ABZ_GK_X4;
+        case 12: return 1.0;
+        case 13: return 1.0 + ABZ_GK_X6;
+        default: return 1.0 - ABZ_GK_X6;
+    }
+}
+// node j of evalrule on [a, b]
+ABZ_HD inline double gk_node(double a, double b, int j) {
+    double s = mul_rn(0.5, add_rn(b, -a));
+    return add_rn(a, mul_rn(gk_off(j), s));
+}
+
+// QuadGK.evalrule: 15 values in gk_node order -> Kronrod estimate I and (Kronrod - Gauss) difference D;
+// the panel error is |D|
+ABZ_HD inline void gk_combine(double a, double b, const cplx* f, cplx* I, cplx* D) {
+    double s = mul_rn(0.5, add_rn(b, -a));
+    cplx fg = cadd_rn(f[0], f[1]), fk = cadd_rn(f[2], f[3]);
+    cplx Ig = cscale_rn(fg, ABZ_GK_G0);
+    cplx Ik = cadd_rn(cscale_rn(fg, ABZ_GK_W1), cscale_rn(fk, ABZ_GK_W0));
+    fg = cadd_rn(f[4], f[5]); fk = cadd_rn(f[6], f[7]);
+    Ig = cadd_rn(Ig, cscale_rn(fg, ABZ_GK_G1));
+    Ik = cadd_rn(Ik, cadd_rn(cscale_rn(fg, ABZ_GK_W3), cscale_rn(fk, ABZ_GK_W2)));
+    fg = cadd_rn(f[8], f[9]); fk = cadd_rn(f[10], f[11]);
+    Ig = cadd_rn(Ig, cscale_rn(fg, ABZ_GK_G2));
+    Ik = cadd_rn(Ik, cadd_rn(cscale_rn(fg, ABZ_GK_W5), cscale_rn(fk, ABZ_GK_W4)));
+    Ig = cadd_rn(Ig, cscale_rn(f[12], ABZ_GK_G3));
+    Ik = cadd_rn(Ik, cadd_rn(cscale_rn(f[12], ABZ_GK_W7), cscale_rn(cadd_rn(f[13], f[14]), ABZ_GK_W6)));
+    cplx Iks = cscale_rn(Ik, s), Igs = cscale_rn(Ig, s);
+    *I = Iks;
+    *D = csub_rn(Iks, Igs);
+}
+
+// value of the user integrand from the device's per-node quantity y (tr G or tr H):
+// vkind 0: y;  1: -Im(y)/pi (aps_example/aps_example.jl:30);  2: a*y + b (test/fourier.jl:41)
+ABZ_HD inline cplx post_value(int vkind, cplx y, cplx la, cplx lb) {
+    if (vkind == 0) return y;
+    if (vkind == 1) return cplx{-y.im / 3.14159265358979323846, 0.0};
+    cplx t{add_rn(mul_rn(la.re, y.re), -mul_rn(la.im, y.im)), add_rn(mul_rn(la.re, y.im), mul_rn(la.im, y.re))};
+    return cadd_rn(t, lb);
+}
+
+// ---- iterated limits (IteratedIntegration.CubicLimits / TetrahedralLimits) ----------------------
+struct Limits {
+    int kind = 0, nd = 0;   // kind 0: x_d in [a_d, b_d];  1: 0 <= x_d <= a_d s, then s <- x_d / a_d
+    double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, s = 1.0;
+    void segments(double* lo, double* hi) const {
+        if (kind == 0) { *lo = a[nd - 1]; *hi = b[nd - 1]; }
+        else { *lo = 0.0; *hi = a[nd - 1] * s; }
+    }
+    Limits fix(double x) const {
+        Limits r = *this;
+        r.nd = nd - 1;
+        if (kind == 1) r.s = x / a[nd - 1];
+        return r;
+    }
+};
+
+struct Seg { double E, a, b; cplx I; };
+
+// DataStructures.jl BinaryHeap with Base.Reverse: lt(x, y) = y.E < x.E
+inline bool seg_lt_rev(const Seg& x, const Seg& y) { return y.E < x.E; }
+inline void heap_percolate_down(std::vector<Seg>& xs, size_t i, Seg x) {   // 1-based i
+    const size_t n = xs.size();
+    for (;;) {
+        size_t l = 2 * i;
+        if (l > n) break;
+        size_t r = l + 1;
+        size_t j = (r > n || seg_lt_rev(xs[l - 1], xs[r - 1])) ? l : r;
+        if (!seg_lt_rev(xs[j - 1], x)) break;
+        xs[i - 1] = xs[j - 1];
+        i = j;
+    }
+    xs[i - 1] = x;
+}
+inline void heap_percolate_up(std::vector<Seg>& xs, size_t i, Seg x) {
+    for (;;) {
+        size_t j = i / 2;
+        if (j < 1) break;
+        if (!seg_lt_rev(x, xs[j - 1])) break;
+        xs[i - 1] = xs[j - 1];
+        i = j;
+    }
+    xs[i - 1] = x;
+}
+inline Seg heap_pop(std::vector<Seg>& xs) {
+    Seg x = xs[0];
+    Seg y = xs.back();
+    xs.pop_back();
+    if (!xs.empty()) heap_percolate_down(xs, 1, y);
+    return x;
+}
+inline void heap_push(std::vector<Seg>& xs, const Seg& x) {
+    xs.push_back(x);
+    heap_percolate_up(xs, xs.size(), x);
+}
+
+// ---- one round of device work ----------------------------------------------------------------------
+struct Round {
+    // contractions queued by the panels started in the previous round (workspace_contract!, src/fourier.jl:478)
+    std::vector<double> c3_x; std::vector<int64_t> c3_slot;
+    std::vector<double> c2_x; std::vector<int64_t> c2_parent, c2_slot;
+    // innermost panels: evaluate the 15 nodes of [a, b] on the series in level-1 slot `slot` and combine
+    std::vector<double> seg_a, seg_b; std::vector<int64_t> seg_slot;
+    std::vector<cplx> seg_I, seg_D;                       // outputs
+    // leaf tasks: whole innermost adaptive integrals
+    std::vector<double> task_a, task_b, task_atol; std::vector<int64_t> task_slot;
+    std::vector<cplx> task_I; std::vector<double> task_E; std::vector<int64_t> task_ne;   // outputs
+    void clear_inputs() {
+        c3_x.clear(); c3_slot.clear(); c2_x.clear(); c2_parent.clear(); c2_slot.clear();
+        seg_a.clear(); seg_b.clear(); seg_slot.clear();
+        task_a.clear(); task_b.clear(); task_atol.clear(); task_slot.clear();
+    }
+};
+
+enum { IAI_OK = 0, IAI_E_NAN = -4, IAI_E_ARENA = -2, IAI_E_STALL = -7 };
+
+// Backend concept:  int run_round(Round&)  fills the outputs for the queued inputs, returns 0 or an error code.
+template <class Backend>
+class Engine {
+public:
+    Engine(Backend& be, int ndim, const Limits& lims, double atol, double rtol, int64_t maxevals, int64_t cap2,
+           int64_t cap1, bool leaf_tasks)
+        : be_(be), ndim_(ndim), lims_(lims), atol_(atol), rtol_(rtol), maxevals_(maxevals),
+          leaf_tasks_(leaf_tasks && ndim >= 2) {
+        for (int64_t i = cap2 - 1; i >= 0; i--) free2_.push_back(i);
+        for (int64_t i = cap1 - 1; i >= 0; i--) free1_.push_back(i);
+    }
+
+    int64_t numevals = 0, rounds = 0;
+    cplx result{0, 0};
+    double result_err = 0;
+    std::string error;
+
+    int run() {
+        double a, b;
+        lims_.segments(&a, &b);
+        int root = new_integral(ndim_ - 1, lims_, atol_, -1, -1, -1, -1);
+        int rc = start_segment(root, a, b, 0);
+        if (rc) return rc;
+        while (!done_) {
+            rounds++;
+            cur_.clear_inputs();
+            std::swap(cur_, next_);           // cur_ = inputs queued so far, next_ = empty
+            std::vector<Item> segs, tasks;
+            segs.swap(q_seg_); tasks.swap(q_task_);
+            if (segs.empty() && tasks.empty()) { error = "IAI engine stalled"; return IAI_E_STALL; }
+            rc = be_.run_round(cur_);
+            if (rc) return rc;
+            numevals += 15 * (int64_t)segs.size();
+            for (size_t i = 0; i < segs.size(); i++) {
+                cplx D = cur_.seg_D[i];
+                double E = std::hypot(D.re, D.im);
+                rc = segment_done(segs[i].q, segs[i].pend, cur_.seg_I[i], E);
+                if (rc) return rc;
+            }
+            for (size_t i = 0; i < tasks.size(); i++) {
+                numevals += cur_.task_ne[i];
+                double E = cur_.task_E[i];
+                if (!std::isfinite(E)) return nan_error(pends_[tasks[i].pend]);
+                rc = child_done(tasks[i].q, tasks[i].pend, tasks[i].i, tasks[i].slot, cur_.task_I[i]);
+                if (rc) return rc;
+            }
+        }
+        return IAI_OK;
+    }
+
+private:
+    struct Pend { double a, b; cplx vals[15]; int remaining, tag; };
+    struct Integral {
+        int level; Limits lims; double atol; int64_t slot; int pq, ppend, pi;   // parent integral / panel / node
+        std::vector<Seg> heap; cplx I; double E; int64_t numevals; Seg popped, s1, s2; bool has1, has2;
+    };
+    struct Item { int q, pend, i; int64_t slot; };
+
+    Backend& be_;
+    int ndim_; Limits lims_; double atol_, rtol_; int64_t maxevals_; bool leaf_tasks_;
+    std::deque<Integral> ints_; std::vector<int> free_int_;
+    std::deque<Pend> pends_; std::vector<int> free_pend_;
+    std::vector<int64_t> free2_, free1_;
+    std::vector<Item> q_seg_, q_task_;
+    Round cur_, next_;
+    bool done_ = false;
+
+    int new_integral(int level, const Limits& lims, double atol, int64_t slot, int pq, int ppend, int pi) {
+        int id;
+        if (!free_int_.empty()) { id = free_int_.back(); free_int_.pop_back(); }
+        else { id = (int)ints_.size(); ints_.emplace_back(); }
+        Integral& q = ints_[id];
+        q.level = level; q.lims = lims; q.atol = atol; q.slot = slot; q.pq = pq; q.ppend = ppend; q.pi = pi;
+        q.heap.clear(); q.I = cplx{0, 0}; q.E = 0; q.numevals = 0; q.has1 = q.has2 = false;
+        return id;
+    }
+    int new_pend(double a, double b, int tag) {
+        int id;
+        if (!free_pend_.empty()) { id = free_pend_.back(); free_pend_.pop_back(); }
+        else { id = (int)pends_.size(); pends_.emplace_back(); }
+        Pend& p = pends_[id];
+        p.a = a; p.b = b; p.tag = tag; p.remaining = 15;
+        return id;
+    }
+    int alloc_slot(int level, int64_t* slot) {
+        std::vector<int64_t>& fr = (level == 2) ? free2_ : free1_;
+        if (fr.empty()) { error = "IAI arena exhausted (too many live panels)"; return IAI_E_ARENA; }
+        *slot = fr.back(); fr.pop_back();
+        return IAI_OK;
+    }
+    void free_slot(int level, int64_t slot) { ((level == 2) ? free2_ : free1_).push_back(slot); }
+    int nan_error(const Pend& p) {
+        error = "integrand produced NaN/Inf in the interval (" + std::to_string(p.a) + ", " + std::to_string(p.b) + ")";
+        return IAI_E_NAN;
+    }
+
+    // evalrule on [a, b] of integral q: innermost -> queue the panel; outer -> spawn 15 child integrals
+    int start_segment(int qi, double a, double b, int tag) {
+        int pend = new_pend(a, b, tag);
+        const int level = ints_[qi].level;
+        if (level == 0) {
+            q_seg_.push_back(Item{qi, pend, 0, 0});
+            next_.seg_a.push_back(a); next_.seg_b.push_back(b); next_.seg_slot.push_back(ints_[qi].slot);
+            return IAI_OK;
+        }
+        for (int i = 0; i < 15; i++) {
+            const double x = gk_node(a, b, i);
+            const Limits clims = ints_[qi].lims.fix(x);
+            double ca, cb;
+            clims.segments(&ca, &cb);
+            const double len = cb - ca;
+            int64_t slot;
+            int rc = alloc_slot(level, &slot);
+            if (rc) return rc;
+            if (level == 2) { next_.c3_x.push_back(x); next_.c3_slot.push_back(slot); }
+            else { next_.c2_x.push_back(x); next_.c2_parent.push_back(ints_[qi].slot); next_.c2_slot.push_back(slot); }
+            const double catol = ints_[qi].atol / len;        // inner abstol = abstol/len (src/fourier.jl:479-480)
+            if (level == 1 && leaf_tasks_) {
+                q_task_.push_back(Item{qi, pend, i, slot});
+                next_.task_a.push_back(ca); next_.task_b.push_back(cb); next_.task_atol.push_back(catol);
+                next_.task_slot.push_back(slot);
+                continue;
+            }
+            int child = new_integral(level - 1, clims, catol, slot, qi, pend, i);
+            rc = start_segment(child, ca, cb, 0);
+            if (rc) return rc;
+        }
+        return IAI_OK;
+    }
+
+    // a child integral (node i of panel `pend` of integral qi) finished with value v
+    int child_done(int qi, int pend, int i, int64_t slot, cplx v) {
+        free_slot(ints_[qi].level, slot);
+        Pend& p = pends_[pend];
+        p.vals[i] = v;
+        if (--p.remaining > 0) return IAI_OK;
+        cplx I, D;
+        gk_combine(p.a, p.b, p.vals, &I, &D);
+        return segment_done(qi, pend, I, std::hypot(D.re, D.im));
+    }
+
+    int finish(int qi) {
+        Integral& q = ints_[qi];
+        cplx Iv = q.heap[0].I; double Ev = q.heap[0].E;
+        for (size_t k = 1; k < q.heap.size(); k++) { Iv = cplx{Iv.re + q.heap[k].I.re, Iv.im + q.heap[k].I.im}; Ev += q.heap[k].E; }
+        if (q.pq < 0) { result = Iv; result_err = Ev; done_ = true; return IAI_OK; }
+        const int pq = q.pq, ppend = q.ppend, pi = q.pi; const int64_t slot = q.slot;
+        free_int_.push_back(qi);
+        return child_done(pq, ppend, pi, slot, Iv);
+    }
+
+    int refine(int qi) {
+        Integral& q = ints_[qi];
+        Seg s = heap_pop(q.heap);
+        q.popped = s;
+        const double mid = (s.a + s.b) / 2;
+        q.has1 = q.has2 = false;
+        int rc = start_segment(qi, s.a, mid, 1);
+        if (rc) return rc;
+        return start_segment(qi, mid, s.b, 2);
+    }
+
+    int segment_done(int qi, int pend, cplx Is, double Es) {
+        const Pend p = pends_[pend];
+        free_pend_.push_back(pend);
+        if (!std::isfinite(Es)) return nan_error(p);
+        Integral& q = ints_[qi];
+        const Seg seg{Es, p.a, p.b, Is};
+        if (p.tag == 0) {
+            q.heap.clear(); q.heap.push_back(seg);
+            q.I = Is; q.E = Es; q.numevals = 15;
+            if (q.numevals >= maxevals_ || q.E <= q.atol || q.E <= rtol_ * std::hypot(q.I.re, q.I.im)) return finish(qi);
+            return refine(qi);
+        }
+        if (p.tag == 1) { q.s1 = seg; q.has1 = true; } else { q.s2 = seg; q.has2 = true; }
+        if (!(q.has1 && q.has2)) return IAI_OK;
+        const Seg& s = q.popped;
+        q.I = cplx{(q.I.re - s.I.re) + q.s1.I.re + q.s2.I.re, (q.I.im - s.I.im) + q.s1.I.im + q.s2.I.im};
+        q.E = (q.E - s.E) + q.s1.E + q.s2.E;
+        q.numevals += 30;
+        heap_push(q.heap, q.s1);
+        heap_push(q.heap, q.s2);
+        if (q.E > q.atol && q.E > rtol_ * std::hypot(q.I.re, q.I.im) && q.numevals < maxevals_) return refine(qi);
+        return finish(qi);
+    }
+};
+
+}  // namespace abz_iai

@@ -304,16 +304,43 @@ def _do_solve(cache, ps):
                 z, sigma = bound
                 test = ff.post(np.zeros(1, dtype=np.complex128), bound)
             dtype = np.complex128 if np.iscomplexobj(test) else np.float64
-            eng = NestedGK(cache.cacheval["nest"], ndim, dom, b1.fkind, z, sigma, lambda y, ff=ff, bound=bound: ff.post(y, bound),
-                           dtype, atol, reltol, maxiters)
-            Iv, Ev, ne = eng.run()
-            cache.cacheval["iai_rounds"] = eng.rounds
+            nest = cache.cacheval["nest"]
+            vkind = _native_vkind(ff)
+            if vkind is not None and hasattr(nest, "iai_solve") and getattr(cache.backend, "iai_engine", "python") == "native":
+                # abz_iai_solve: same control flow, run by the library's C++ host engine (one ccall per solve)
+                atol_ = 0.0 if atol is None else atol
+                rtol_ = reltol if reltol is not None else (np.sqrt(np.finfo(float).eps) if atol_ == 0 else 0.0)
+                lkind = 1 if isinstance(dom, TetrahedralLimits) else 0
+                la = dom.a
+                lb = dom.b if lkind == 0 else None
+                if lkind == 1 and dom.s != 1.0:
+                    raise ValueError("TetrahedralLimits must start at s = 1")
+                lin = bound if vkind == 2 else None
+                Iv, Ev, ne, rounds, launches = nest.iai_solve(lkind, la, lb, b1.fkind, vkind, z, sigma, lin, atol_, rtol_, maxiters,
+                                                              device_leaves=getattr(cache.backend, "iai_device_leaves", True))
+                cache.cacheval["iai_rounds"] = rounds
+                Iv = Iv if dtype == np.complex128 else Iv.real
+            else:
+                eng = NestedGK(nest, ndim, dom, b1.fkind, z, sigma, lambda y, ff=ff, bound=bound: ff.post(y, bound),
+                               dtype, atol, reltol, maxiters)
+                Iv, Ev, ne = eng.run()
+                cache.cacheval["iai_rounds"] = eng.rounds
             mult = sc * (ns if on_bz else 1)                # val = j * symmetrize(f, bz, sol.u) (TrivialRep: x nsyms)
             u = Iv * mult
             u = complex(u) if dtype == np.complex128 else float(u)
             sols.append(IntegralSolution(u, float(Ev) * mult, True, ne if counter else -1))
         return sols
     raise TypeError("unsupported algorithm")
+
+
+def _native_vkind(ff):
+    """abz_iai_solve's value map for the integrand (0 identity, 1 -Im/pi, 2 a*y+b), or None when only its Python
+    `post` knows it (subclasses that override post fall back to the Python engine)."""
+    from .fourier import AffineTraceIntegrand, DOSIntegrand, TrGlocIntegrand
+    for cls, vk in ((DOSIntegrand, 1), (AffineTraceIntegrand, 2), (TrGlocIntegrand, 0)):
+        if type(ff) is cls:
+            return vk
+    return None
 
 
 def _autosymptr(cache, bf, salg, atol, reltol, maxevals, ndim):

@@ -55,6 +55,7 @@ typedef uint64_t abz_nest_t;    /* IAI arena: contracted series for nested panel
 #define ABZ_OPT_RESOLVENT_ALGO 1   /* 0 auto, 1 generic pivoted Gauss-Jordan, 2 register/DMMA fast path */
 #define ABZ_OPT_MEM_BUDGET_MB 2    /* device workspace budget for streamed chunks (default 4096) */
 #define ABZ_OPT_FUSED_SMALL 3      /* 1 (default): fuse evaluation+resolvent for norb<=4 */
+#define ABZ_OPT_EIG_ALGO 4         /* 0 (default): Householder tridiagonalisation + implicit QL; 1: cyclic two-sided Jacobi */
 
 int32_t abz_version(void);
 const char* abz_last_error(const abz_ctx* ctx);  /* ctx may be NULL: last error of abz_ctx_create */
@@ -93,6 +94,12 @@ int32_t abz_rule_create_nodes(abz_ctx* ctx, abz_series_t s, int32_t npt, int64_t
 /* AutoSymPTR.symptr_rule (call site src/fourier.jl:271) on the device: syms = Int32[3,3,nsyms]
  * row-major per matrix, wsym_out = Int32[npt^3] host buffer; returns the irreducible count. */
 int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t* wsym_out, int64_t* nirr);
+/* symptr_rule + FourierMonkhorstPack in one step, entirely on the device (src/fourier.jl:265-277): the dense
+ * weight array never visits the host, the CSR node lists are compacted by a warp-per-row kernel.  Same node set,
+ * order and weights as abz_symptr_rule followed by abz_rule_create_sym.  nirr_total (may be NULL) = length(rule)
+ * over ALL k3 planes, whatever (k3_lo, k3_stride) selects for this rank. */
+int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t s, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t k3_lo,
+                               int32_t k3_stride, abz_rule_t* out, int64_t* nirr_total);
 int32_t abz_rule_destroy(abz_ctx* ctx, abz_rule_t r);
 /* length(rule) (src/fourier.jl:177, 284) and norb */
 int32_t abz_rule_info(abz_ctx* ctx, abz_rule_t r, int64_t* nnodes, int32_t* norb, int32_t* npt);
@@ -136,6 +143,21 @@ int32_t abz_nest_contract2(abz_ctx* ctx, abz_nest_t nest, int64_t n, const doubl
  * ndim == 1) at x1[i] and apply the integrand: y = ComplexF64[npts] */
 int32_t abz_nest_eval(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const double* x1, const int64_t* slot1,
                       int32_t fkind, const double* z, const double* sigma, double* y);
+
+/* The whole nested adaptive solve do_solve(f::FourierIntegrand, lims, ::NestedQuad) (src/fourier.jl:493-510) with
+ * GK(7,15) at every level (AuxQuadGKJL/QuadGKJL defaults, src/algorithms.jl:215-240): the adaptive control flow
+ * (QuadGK do_quadgk/adapt/refine, DataStructures heap, inner abstol = abstol/len, src/fourier.jl:479-480) runs on
+ * the library's host side, every round of live innermost panels is one device batch on `nest`'s arena.
+ * For hosts whose own loop is too slow to drive abz_nest_* round by round (Python); a Julia host may use either.
+ *   lkind 0: CubicLimits(la, lb);  1: TetrahedralLimits(la)  (load_bz(CubicSymIBZ), src/brillouin.jl:301-307)
+ *   fkind = ABZ_F_*;  vkind 0: value = y;  1: -Im(y)/pi (aps_example.jl:30);  2: lin[0:2]*y + lin[2:4] (complex a, b)
+ *   atol, rtol, maxevals apply to the outermost integral exactly as abstol/reltol/maxiters of the reference.
+ *   flags: ABZ_IAI_DEVICE_LEAVES = run each innermost 1-D adaptive integral entirely on the device (norb <= 3)
+ *   out = {Re I, Im I, E};  stats = {numevals (EvalCounter semantics), device rounds, kernel launches} or NULL */
+#define ABZ_IAI_DEVICE_LEAVES 1
+int32_t abz_iai_solve(abz_ctx* ctx, abz_nest_t nest, int32_t lkind, const double* la, const double* lb, int32_t fkind,
+                      int32_t vkind, const double* z, const double* sigma, const double* lin, double atol, double rtol,
+                      int64_t maxevals, int32_t flags, double* out, int64_t* stats);
 
 /* ---- multi-GPU: one small allreduce of partial sums ----------------------- */
 /* NCCL is dlopen'ed at first use (libnccl.so.2).  uid = 128-byte ncclUniqueId from rank 0. */

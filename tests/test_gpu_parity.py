@@ -294,3 +294,121 @@ def test_c4_full_size_properties(ctx):
     finally:
         ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
     assert rel(c, a[:4]) < 1e-11
+
+
+# ---------------------------------------------------------------------------------------------------
+# abz_iai_solve: the library's C++ host engine, with host-driven panels and with device-side innermost integrals
+@pytest.mark.parametrize("engine,leaves", [("python", False), ("native", False), ("native", True)])
+def test_iai_engines_agree_with_oracle(ctx, orc, svo, engine, leaves):
+    """All three ways of driving IAI (Python round loop over abz_nest_*, abz_iai_solve with host-driven innermost
+    panels, abz_iai_solve with one warp per innermost adaptive integral) make the oracle's decisions: identical
+    numevals, integrals <= 1e-10 relative."""
+    H, lo, A = svo
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
+    S = orc.Series(H, lo)
+    be = ab.DeviceBackend(ctx=ctx, iai_engine=engine, iai_device_leaves=leaves)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), A)
+    fbz = ab.load_bz(ab.FBZ(), A)
+    j = abs(np.linalg.det(ibz.B))
+    for eta, omega, atol in ((0.05, 12.5, 1e-2), (0.01, 12.0, 1e-2), (2e-3, 12.975161, 2e-2)):
+        Io, Eo, neo = orc.iai(S, 3, 1, [0.5] * 3, vkind=1, z=complex(omega, eta), atol=atol)
+        f = ab.FourierIntegrand(ab.dos_integrand, fs, eta)
+        sol = ab.solve(ab.IntegralProblem(f, ibz, omega), ab.EvalCounter(ab.IAI()), abstol=atol * j * 48, backend=be)
+        assert sol.numevals == neo
+        assert abs(sol.u - j * 48 * Io.real) <= 1e-10 * abs(sol.u)
+        assert abs(sol.resid - j * 48 * Eo) <= 1e-6 * sol.resid
+    # complex-valued integrand on the full BZ (CubicLimits), relative tolerance only
+    Io, Eo, neo = orc.iai(S, 3, 0, [0.0] * 3, [1.0] * 3, vkind=0, z=complex(12.3, 0.1), atol=0.0, rtol=1e-4)
+    f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=0.1)
+    sol = ab.solve(ab.IntegralProblem(f, fbz, {"omega": 12.3}), ab.EvalCounter(ab.IAI()), reltol=1e-4, backend=be)
+    assert sol.numevals == neo
+    assert abs(sol.u - j * Io) <= 1e-10 * abs(sol.u)
+
+
+@pytest.mark.parametrize("leaves", [False, True])
+def test_iai_native_low_dim_large_norb_and_errors(ctx, orc, leaves):
+    be = ab.DeviceBackend(ctx=ctx, iai_engine="native", iai_device_leaves=leaves)
+    # docs/src/examples.md:44-60 (1-D) and :79-106 (2-D IAI on FBZ(2)), abstol = 1e-3: reference known answers
+    h1 = ab.FourierSeries([0.5, 0.0, 0.5], period=1, offset=-2)
+    bz1 = ab.SymmetricBZ(np.eye(1) * 2 * np.pi, np.eye(1), ab.CubicLimits([0.0], [1.0]), None)
+    g1 = ab.IntegralSolver(ab.FourierIntegrand(ab.gloc_trace_integrand, h1, eta=0.1), bz1, ab.IAI(), abstol=1e-3, backend=be)(omega=0.0)
+    ref1 = GOLD["reference_known_answers"]["docs/src/examples.md:60 (QuadGKJL abstol=1e-3, 1-D gloc, eta=0.1, omega=0)"]
+    assert abs(g1.imag - ref1[1]) < 1e-14 and abs(g1.real) < 1e-14
+    C2 = np.array([[0.0, 0.5, 0.0], [0.5, 0.0, 0.5], [0.0, 0.5, 0.0]])
+    h2 = ab.FourierSeries(C2, period=1, offset=-2)
+    bz2 = ab.load_bz(ab.FBZ(2), 2 * np.pi * np.eye(2))
+    g2 = ab.IntegralSolver(ab.FourierIntegrand(ab.gloc_trace_integrand, h2, eta=0.1), bz2, ab.IAI(), abstol=1e-3, backend=be)(omega=0.0)
+    ref2 = GOLD["reference_known_answers"]["docs/src/examples.md:105 (IAI abstol=1e-3, 2-D gloc on FBZ(2), eta=0.1, omega=0)"]
+    assert abs(g2.imag - ref2[1]) < 1e-13 and abs(g2.real) < 1e-13
+    # 5-orbital resolvent through the generic (nodes -> H -> resolvent kernel -> combine) path, 2-D, vs oracle
+    n = 5
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 2)
+    H2, lo2 = np.asfortranarray(H[:, :, :, :, 2]), lo[:2]
+    fs = ab.FourierSeries(H2, period=1.0, lo=lo2, norb=n)
+    So = orc.Series(H2[..., None], tuple(lo2) + (0,))
+    z = complex(0.2, 0.15)
+    Io, Eo, neo = orc.iai(So, 2, 0, [0.0] * 2, [1.0] * 2, vkind=0, z=z, atol=1e-4)
+    bz2 = ab.load_bz(ab.FBZ(2), 2 * np.pi * np.eye(2))
+    f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=0.15)
+    sol = ab.solve(ab.IntegralProblem(f, bz2, {"omega": 0.2}), ab.EvalCounter(ab.IAI()), abstol=1e-4, backend=be)
+    assert sol.numevals == neo and abs(sol.u - Io) <= 1e-10 * abs(Io)
+    # NaN/Inf in the integrand surfaces as an error (QuadGK DomainError): z on a pole of a diagonal 1-orbital band
+    hc = ab.FourierSeries([0.0, 1.0, 0.0], period=1, offset=-2)
+    with pytest.raises(FloatingPointError):
+        ab.IntegralSolver(ab.FourierIntegrand(ab.gloc_trace_integrand, hc, eta=0.0), bz1, ab.IAI(), abstol=1e-3, backend=be)(omega=1.0)
+
+
+@pytest.mark.parametrize("npt", [7, 12, 33])
+def test_rule_create_symptr_on_device_matches_host_path(ctx, orc, npt):
+    """abz_rule_create_symptr (weights + CSR compaction on the device) == abz_symptr_rule -> abz_rule_create_sym
+    == the oracle's symptr_rule: same nodes, order, weights, sums; sharded by k3 planes the parts add up."""
+    n = 3
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 2, cubic=True)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    syms = np.array(ab.cube_automorphisms(3), dtype=np.int32)
+    w_host, nirr = ctx.symptr_rule(npt, syms)
+    w_orc, nirr_o = orc.symptr_rule(npt, syms)
+    assert nirr == nirr_o and np.array_equal(w_host, w_orc)
+    Ra = L.DeviceRule(ctx, S, npt, wsym=w_host)
+    Rb = L.DeviceRule(ctx, S, npt, syms=syms)
+    assert len(Ra) == len(Rb) == nirr == Rb.nirr_total
+    Ha, ka, wa = Ra.copy_out()
+    Hb, kb, wb = Rb.copy_out()
+    assert np.array_equal(ka, kb) and np.array_equal(wa, wb) and np.array_equal(Ha, Hb)
+    assert wb.sum() == npt ** 3
+    z = np.array([0.3 + 0.05j, -0.7 + 0.2j])
+    assert np.array_equal(Ra.resolvent_sum(z), Rb.resolvent_sum(z))
+    parts = [L.DeviceRule(ctx, S, npt, syms=syms, k3_lo=r, k3_stride=3) for r in range(3)]
+    assert all(p.nirr_total == nirr for p in parts) and sum(len(p) for p in parts) == nirr
+    assert rel(sum(p.resolvent_sum(z) for p in parts), Ra.resolvent_sum(z)) < 1e-13
+    # inversion-only group and the trivial group
+    inv = np.array([np.eye(3), -np.eye(3)], dtype=np.int32)
+    Rc = L.DeviceRule(ctx, S, npt, syms=inv)
+    wi, ni = orc.symptr_rule(npt, inv)
+    assert len(Rc) == ni
+    assert rel(Rc.resolvent_sum(z), L.DeviceRule(ctx, S, npt).resolvent_sum(z)) < 1e-12
+
+
+@pytest.mark.parametrize("n", [2, 7, 31, 32, 33, 64])
+def test_eig_algorithms_agree_with_lapack(ctx, n):
+    """Householder tridiagonalisation + implicit QL (default) and cyclic Jacobi (option) against LAPACK zheev on
+    H(k) of a synthetic Wannier Hamiltonian, incl. a degenerate spectrum (H = 0 -> all eigenvalues 0; diagonal H)."""
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 1)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    R = L.DeviceRule(ctx, S, 5)
+    Hk, _, _ = R.copy_out()
+    ref = np.linalg.eigvalsh(np.moveaxis(Hk, 2, 0))
+    ev_fast = R.eigvals()
+    ctx.set_option(L.OPT_EIG_ALGO, 1)
+    try:
+        ev_jac = R.eigvals()
+        sj = R.eig_sum(L.EIG_FERMI_ENERGY, (0.1, 0.3))
+    finally:
+        ctx.set_option(L.OPT_EIG_ALGO, 0)
+    assert rel(ev_fast, ref) < 1e-13 and rel(ev_jac, ref) < 1e-12
+    assert np.all(np.diff(ev_fast, axis=1) >= 0)
+    assert abs(R.eig_sum(L.EIG_FERMI_ENERGY, (0.1, 0.3)) - sj) < 1e-11 * abs(sj)
+    Hd = np.zeros_like(H)
+    Hd[:, :, -lo[0], -lo[1], -lo[2]] = np.diag(np.repeat(np.arange((n + 1) // 2), 2)[:n])
+    Rd = L.DeviceRule(ctx, L.DeviceSeries(ctx, Hd, lo, (1.0,) * 3), 3)
+    assert np.array_equal(Rd.eigvals(), np.tile(np.repeat(np.arange((n + 1) // 2), 2)[:n].astype(float), (27, 1)))

@@ -1,0 +1,99 @@
+"""The library's C++ host-side IAI engine (csrc/abz_iai_engine.hpp, behind abz_iai_solve) driven on CPU by an
+oracle-backed test double (tests/native/iai_engine_cpu.cpp): it must reproduce the oracle's sequential recursion
+(orc_iai) decision for decision - identical numevals, integrals equal to rounding - both with host-driven innermost
+panels and with whole innermost integrals handed out as leaf tasks (what the device does with one warp per task)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "native"))
+
+c_dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def eng(orc):
+    import build
+    lib = C.CDLL(build.build())
+    return lib
+
+
+def _solve(lib, S, ndim, lkind, la, lb, fkind, vkind, z, lin, atol, rtol, leaf, maxevals=2 ** 62, cap2=64, cap1=2048):
+    i3 = lambda v: (C.c_int * 3)(*[int(x) for x in v])
+    d3 = lambda v: (C.c_double * 3)(*[float(x) for x in v])
+    la_ = np.ascontiguousarray(la, dtype=np.float64)
+    lb_ = None if lb is None else np.ascontiguousarray(lb, dtype=np.float64)
+    zz = np.array([z.real, z.imag])
+    ln = None if lin is None else np.ascontiguousarray(lin, dtype=np.float64)
+    out = np.zeros(3)
+    st = (C.c_long * 3)()
+    dp = lambda a: None if a is None else a.ctypes.data_as(c_dp)
+    rc = lib.iai_cpu_solve(dp(S.c), C.c_int(S.n), C.c_int(ndim), i3(S.M), i3(S.lo), d3(S.period), C.c_int(lkind), dp(la_), dp(lb_),
+                           C.c_int(fkind), C.c_int(vkind), dp(zz), None, dp(ln), C.c_double(atol), C.c_double(rtol),
+                           C.c_long(maxevals), C.c_int(int(leaf)), C.c_long(cap2), C.c_long(cap1), dp(out), st)
+    return rc, complex(out[0], out[1]), out[2], int(st[0]), int(st[1])
+
+
+@pytest.mark.parametrize("leaf", [False, True])
+@pytest.mark.parametrize("lims", ["cubic", "tetra"])
+def test_engine_matches_recursion_svo(orc, eng, svo, lims, leaf):
+    H, lo, A = svo
+    S = orc.Series(H, lo)
+    z = complex(12.5, 0.05)
+    if lims == "cubic":
+        args, atol = (0, [0.0] * 3, [1.0] * 3), 3e-2
+    else:
+        args, atol = (1, [0.5] * 3, None), 1e-3
+    Io, Eo, neo = orc.iai(S, 3, args[0], args[1], args[2], vkind=1, z=z, atol=atol)
+    rc, I, E, ne, rounds = _solve(eng, S, 3, args[0], args[1], args[2], 0, 1, z, None, atol, 0.0, leaf)
+    assert rc == 0
+    assert ne == neo
+    assert abs(I - Io) <= 1e-13 * abs(Io) and abs(E - Eo) <= 1e-9 * Eo
+    if leaf:   # leaf tasks collapse the innermost adaptive loops into one device round each
+        _, _, _, _, rounds_host = _solve(eng, S, 3, args[0], args[1], args[2], 0, 1, z, None, atol, 0.0, False)
+        assert rounds < rounds_host
+
+
+@pytest.mark.parametrize("leaf", [False, True])
+def test_engine_complex_values_and_rtol(orc, eng, svo, leaf):
+    """complex-valued integrand (tr G), relative tolerance only, maxevals cut-off"""
+    H, lo, A = svo
+    S = orc.Series(H, lo)
+    z = complex(12.0, 0.1)
+    Io, Eo, neo = orc.iai(S, 3, 1, [0.5] * 3, None, vkind=0, z=z, atol=0.0, rtol=1e-3)
+    rc, I, E, ne, _ = _solve(eng, S, 3, 1, [0.5] * 3, None, 0, 0, z, None, 0.0, 1e-3, leaf)
+    assert rc == 0 and ne == neo and abs(I - Io) <= 1e-13 * abs(Io)
+    Io, Eo, neo = orc.iai(S, 3, 1, [0.5] * 3, None, vkind=0, z=z, atol=1e-9, maxevals=45)
+    rc, I, E, ne, _ = _solve(eng, S, 3, 1, [0.5] * 3, None, 0, 0, z, None, 1e-9, 0.0, leaf, maxevals=45)
+    assert rc == 0 and ne == neo and abs(I - Io) <= 1e-13 * abs(Io)
+
+
+@pytest.mark.parametrize("ndim", [1, 2])
+def test_engine_low_dimensions_and_affine(orc, eng, ndim):
+    """docs/src/examples.md:44-60,79-106 shapes (1-D, 2-D cos bands) and the affine integrand of test/fourier.jl:41"""
+    shape = (1, 1) + (3,) * ndim + (1,) * (3 - ndim)
+    c = np.zeros(shape, dtype=complex)
+    for d in range(ndim):
+        for sgn in (0, 2):
+            idx = [0, 0] + [1] * ndim + [0] * (3 - ndim)
+            idx[2 + d] = sgn
+            c[tuple(idx)] = 0.5
+    S = orc.Series(c, (-1,) * ndim + (0,) * (3 - ndim))
+    z = complex(0.0, 0.1)
+    Io, Eo, neo = orc.iai(S, ndim, 0, [0.0] * ndim, [1.0] * ndim, vkind=0, z=z, atol=1e-3)
+    for leaf in (False, True):
+        rc, I, E, ne, _ = _solve(eng, S, ndim, 0, [0.0] * ndim, [1.0] * ndim, 0, 0, z, None, 1e-3, 0.0, leaf)
+        assert rc == 0 and ne == neo and abs(I - Io) <= 1e-13 * abs(Io)
+    Io, Eo, neo = orc.iai(S, ndim, 0, [0.0] * ndim, [1.0] * ndim, vkind=2, lin=(1.3, 1.0), atol=1e-8)
+    rc, I, E, ne, _ = _solve(eng, S, ndim, 0, [0.0] * ndim, [1.0] * ndim, 1, 2, 0j, [1.3, 0.0, 1.0, 0.0], 1e-8, 0.0, False)
+    assert rc == 0 and ne == neo and abs(I - Io) <= 1e-13 * abs(Io) and abs(I - 1.0) < 1e-9
+
+
+def test_engine_arena_exhaustion_is_an_error(orc, eng, svo):
+    H, lo, A = svo
+    S = orc.Series(H, lo)
+    rc, *_ = _solve(eng, S, 3, 1, [0.5] * 3, None, 0, 1, complex(12.5, 0.05), None, 1e-3, 0.0, False, cap2=8, cap1=2048)
+    assert rc == -2

@@ -50,14 +50,20 @@ if "c3" in which:
     fs = ab.FourierSeries(Hs, period=1.0, lo=los, norb=3)
     ibz = ab.load_bz(ab.CubicSymIBZ(), A)
     j48 = abs(np.linalg.det(ibz.B)) * 48
+    modes = {"native+device-leaves": ab.DeviceBackend(ctx=ctx, iai_engine="native", iai_device_leaves=True),
+             "native": ab.DeviceBackend(ctx=ctx, iai_engine="native", iai_device_leaves=False),
+             "python": ab.DeviceBackend(ctx=ctx, iai_engine="python")}
     for eta, atol in ((1e-2, 1e-3), (1e-4, 1e-3)):
         f = ab.FourierIntegrand(ab.dos_integrand, fs, eta)
         for w in (12.0, 12.975161):
-            cache = ab.init(ab.IntegralProblem(f, ibz, w), ab.EvalCounter(ab.IAI()), abstol=atol)
-            l0 = ctx.launch_count
-            t = time.perf_counter(); sol = ab.solve_(cache); dt = time.perf_counter() - t
-            emit(config=f"C3 SrVO3 IAI eta={eta} abstol={atol} omega={w}", dos=sol.u, err=sol.resid, numevals=sol.numevals, s=dt, evals_per_s=sol.numevals / dt,
-                 rounds=cache.cacheval.get("iai_rounds"), launches=ctx.launch_count - l0)
+            for mode, be in modes.items():
+                if mode == "python" and (eta < 1e-3 or "nopy" in which):
+                    continue
+                cache = ab.init(ab.IntegralProblem(f, ibz, w), ab.EvalCounter(ab.IAI()), abstol=atol, backend=be)
+                l0 = ctx.launch_count
+                t = time.perf_counter(); sol = ab.solve_(cache); dt = time.perf_counter() - t
+                emit(config=f"C3 SrVO3 IAI eta={eta} abstol={atol} omega={w}", engine=mode, dos=sol.u, err=sol.resid, numevals=sol.numevals, s=dt,
+                     evals_per_s=sol.numevals / dt, rounds=cache.cacheval.get("iai_rounds"), launches=ctx.launch_count - l0)
 
 if "c5" in which:
     n = 64
