@@ -10,7 +10,7 @@ from .algorithms import (IAI, PTR, AutoPTR, AutoSymPTRJL, AuxQuadGKJL, EvalCount
 from .backend import DeviceBackend, default_context  # noqa: F401
 from .bz import (FBZ, CubicLimits, CubicSymIBZ, InversionSymIBZ, SymmetricBZ, TetrahedralLimits,  # noqa: F401
                  cube_automorphisms, load_bz, nsyms)
-from .fourier import (AffineTraceIntegrand, DOSIntegrand, EigenIntegrand, FourierIntegrand, FourierSeries,  # noqa: F401
+from .fourier import (AffineTraceIntegrand, BatchIntegrand, DOSIntegrand, EigenIntegrand, FourierIntegrand, FourierSeries,  # noqa: F401
                       FourierValue, TrGlocIntegrand, dos_integrand, gloc_trace_integrand)
 from .interfaces import (Basis, IntegralProblem, IntegralSolution, IntegralSolver, Shard, batchsolve, init,  # noqa: F401
                          solve, solve_, torch_allreduce)
@@ -18,3 +18,5 @@ from .wannier import read_w90_hrdat, read_wout_lattice  # noqa: F401
 
 # v0.4+ names of the reference API (BASELINE.json north_star) as aliases
 FourierIntegralFunction = FourierIntegrand
+CommonSolveFourierIntegralFunction = FourierIntegrand
+BatchIntegralFunction = BatchIntegrand

@@ -24,7 +24,7 @@ EXPORTS = [
     "abz_ctx_last_timings", "abz_series_create", "abz_series_destroy", "abz_rule_create_full", "abz_rule_create_sym", "abz_rule_create_nodes",
     "abz_symptr_rule", "abz_rule_create_symptr", "abz_rule_destroy", "abz_rule_info", "abz_rule_materialize", "abz_rule_copy_out",
     "abz_rule_resolvent_sum", "abz_rule_eig_sum", "abz_rule_eigvals", "abz_points_eval", "abz_points_resolvent",
-    "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval", "abz_iai_solve",
+    "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval", "abz_nest_eval_h", "abz_iai_solve",
     "abz_comm_unique_id", "abz_comm_init", "abz_allreduce_sum", "abz_comm_destroy",
 ]
 
@@ -85,6 +85,7 @@ def load():
     lib.abz_nest_contract3.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p]
     lib.abz_nest_contract2.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p, c_i64p]
     lib.abz_nest_eval.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p, C.c_int32, c_dp, c_dp, c_dp]
+    lib.abz_nest_eval_h.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p, c_dp]
     lib.abz_iai_solve.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, C.c_double,
                                   C.c_double, C.c_int64, C.c_int32, c_dp, c_i64p]
     lib.abz_comm_unique_id.argtypes = [C.c_void_p]
@@ -352,6 +353,16 @@ class DeviceNest:
         self.ctx.check(self.ctx.lib.abz_nest_eval(self.ctx.h, self.h, x.size, _dp(x), None if s is None else s.ctypes.data_as(c_i64p),
                                                   fkind, _dp(zz), _dp(sg), _dp(y)))
         return y
+
+    def eval_h(self, x1, slot1):
+        """H at the nodes of innermost panels, [n, n, npts] (for integrands evaluated on the host)"""
+        x = np.ascontiguousarray(x1, dtype=np.float64)
+        s = None if slot1 is None else np.ascontiguousarray(slot1, dtype=np.int64)
+        n = self.series.n
+        H = np.empty((n, n, x.size), dtype=np.complex128, order="F")
+        self.ctx.check(self.ctx.lib.abz_nest_eval_h(self.ctx.h, self.h, x.size, _dp(x), None if s is None else s.ctypes.data_as(c_i64p),
+                                                    _dp(H)))
+        return H
 
     def iai_solve(self, lkind, la, lb, fkind, vkind, z, sigma, lin, atol, rtol, maxevals, device_leaves=True):
         """abz_iai_solve: the whole nested adaptive solve with the control flow on the library's host side.

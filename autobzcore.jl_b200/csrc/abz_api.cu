@@ -384,16 +384,29 @@ int run_small_fused(abz_ctx* ctx, Rule* r, const double2* C1, const double2* Hma
     Series* s = r->s;
     long nnodes = r->h_row_nodeptr[r0 + nrows] - r->h_row_nodeptr[r0];
     if (nnodes <= 0) return ABZ_OK;
-    long ncta = std::min<long>((nnodes + SM_THREADS - 1) / SM_THREADS, (long)ctx->sm_count * 8);
-    int nwy = (fkind == ABZ_F_TRACE_H) ? 1 : (nw + SM_WCH - 1) / SM_WCH;
+    const long per_cta = (long)SM_THREADS * SM_NB;
+    long ncta = std::min<long>((nnodes + per_cta - 1) / per_cta, (long)ctx->sm_count * 8);
+    if (fkind == ABZ_F_TRACE_H) nw = 1;
+    int nwy = (nw + SM_WMAX - 1) / SM_WMAX;
+    const size_t smem = (size_t)9 * std::min(nw, SM_WMAX) * sizeof(double2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(small_fused_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(small_fused_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(small_fused_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(small_fused_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(small_fused_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(small_fused_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
     CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
     dim3 grid((unsigned)ncta, (unsigned)nwy);
     int* ef = ctx->errflag.as<int>();
     double2* part = ctx->partial.as<double2>();
 #define SMALL_LAUNCH(NORB)                                                                                         \
-    small_fused_kernel<NORB, FROM_H><<<grid, SM_THREADS, 0, ctx->stream>>>(C1, Hmat, r->d_ptab[0], r->d_row_nodeptr, r0, nrows, \
-                                                                          r->d_node_k1, r->d_node_w, r->N, s->M[0], fkind, nw, z, \
-                                                                          sigma, part, ef)
+    small_fused_kernel<NORB, FROM_H><<<grid, SM_THREADS, smem, ctx->stream>>>(C1, Hmat, r->d_ptab[0], r->d_row_nodeptr, r0, nrows, \
+                                                                             r->d_node_k1, r->d_node_w, r->N, s->M[0], fkind, nw, z, \
+                                                                             sigma, part, ef)
     if (s->n == 1) SMALL_LAUNCH(1);
     else if (s->n == 2) SMALL_LAUNCH(2);
     else SMALL_LAUNCH(3);
@@ -637,6 +650,8 @@ int32_t abz_rule_create_nodes(abz_ctx* ctx, abz_series_t sid, int32_t npt, int64
 int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t* wsym_out, int64_t* nirr) {
     if (!ctx) return ABZ_E_INVALID;
     if (npt < 1 || nsyms < 1 || nsyms > 1024 || !syms || !wsym_out) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    for (int t = 0; t < 9 * nsyms; t++)
+        if ((long)std::abs((long)syms[t]) * 3 * npt >= ((long)1 << 31)) return fail(ctx, ABZ_E_INVALID, "symmetry matrix entries too large");
     cudaSetDevice(ctx->device);
     size_t tot = (size_t)npt * npt * npt;
     CU(ctx, ctx->tmp_a.reserve(tot * sizeof(int)));
@@ -662,6 +677,8 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
     if (!s) return fail(ctx, ABZ_E_INVALID, "unknown series handle");
     if (!out || npt < 1 || nsyms < 1 || nsyms > 1024 || !syms || k3_lo < 0 || k3_stride < 1)
         return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    for (int t = 0; t < 9 * nsyms; t++)
+        if ((long)std::abs((long)syms[t]) * 3 * npt >= ((long)1 << 31)) return fail(ctx, ABZ_E_INVALID, "symmetry matrix entries too large");
     cudaSetDevice(ctx->device);
     const long N = npt;
     const size_t tot = (size_t)N * N * N;
@@ -1256,6 +1273,36 @@ int32_t abz_nest_eval(abz_ctx* ctx, abz_nest_t nid, int64_t npts, const double* 
         ctx->force_generic = false;
     }
     return rc;
+}
+
+
+int32_t abz_nest_eval_h(abz_ctx* ctx, abz_nest_t nid, int64_t npts, const double* x1, const int64_t* slot1, double* Hk) {
+    if (!ctx) return ABZ_E_INVALID;
+    Nest* nst = get_nest(ctx, nid);
+    if (!nst) return fail(ctx, ABZ_E_INVALID, "unknown nest handle");
+    if (npts < 0 || (npts > 0 && (!x1 || !Hk || (nst->ndim >= 2 && !slot1)))) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    if (npts == 0) return ABZ_OK;
+    int rc;
+    if (nst->ndim >= 2 && (rc = check_slots(ctx, slot1, npts, nst->cap1, "abz_nest_eval_h"))) return rc;
+    cudaSetDevice(ctx->device);
+    Series* s = nst->s;
+    const long nn = (long)s->n * s->n;
+    CU(ctx, ctx->tmp_a.reserve((size_t)npts * sizeof(double)));
+    CU(ctx, ctx->tmp_b.reserve((size_t)npts * sizeof(long)));
+    CU(ctx, ctx->Hc.reserve((size_t)npts * nn * sizeof(double2)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_a.p, x1, (size_t)npts * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const long* dslot = nullptr; const double2* L1 = s->c; long stride = 0;
+    if (nst->ndim >= 2) {
+        CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, slot1, (size_t)npts * sizeof(long), cudaMemcpyHostToDevice, ctx->stream));
+        dslot = ctx->tmp_b.as<long>(); L1 = nst->L1; stride = nn * s->M[0];
+    }
+    dim3 grid((unsigned)((nn + 127) / 128), (unsigned)npts);
+    nest_eval_h_kernel<<<grid, 128, (size_t)s->M[0] * sizeof(double2), ctx->stream>>>(L1, stride, dslot, ctx->tmp_a.as<double>(), (int)nn,
+                                                                                      s->M[0], s->lo[0], s->period[0], ctx->Hc.as<double2>());
+    LAUNCH_CHECK(ctx, "nest_eval_h_kernel");
+    CU(ctx, cudaMemcpyAsync(Hk, ctx->Hc.p, (size_t)npts * nn * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABZ_OK;
 }
 
 

@@ -305,6 +305,15 @@ points_eval_kernel(const double2* __restrict__ C, int nn, int M1, int M2, int M3
 // AutoSymPTR.symptr_rule on the device (call site src/fourier.jl:271).  Orbit representative =
 // the image with the smallest column-major linear index (which is the first node of the orbit met
 // by the reference's column-major scan); weight = number of distinct images.
+__device__ __forceinline__ int symptr_image(const int* __restrict__ S, int i1, int i2, int i3, int N) {
+    // |S_ab| i < 2^31 is checked on the host (entries of lattice-basis symmetries are tiny integers)
+    int j1 = (S[0] * i1 + S[1] * i2 + S[2] * i3) % N;
+    int j2 = (S[3] * i1 + S[4] * i2 + S[5] * i3) % N;
+    int j3 = (S[6] * i1 + S[7] * i2 + S[8] * i3) % N;
+    j1 += (j1 < 0) ? N : 0; j2 += (j2 < 0) ? N : 0; j3 += (j3 < 0) ? N : 0;
+    return j1 + N * j2;          // in-plane part; the caller combines with j3
+}
+
 __global__ void __launch_bounds__(256)
 symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restrict__ wsym) {
     extern __shared__ int sy[];
@@ -314,31 +323,50 @@ symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restri
     const long idx = (long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= tot) return;
     const int i1 = (int)(idx % N), i2 = (int)((idx / N) % N), i3 = (int)(idx / ((long)N * N));
-    // images (deduplicated by counting only the first occurrence among the symmetry list)
-    int cnt = 0;
-    bool is_min = true, has_self = false;
-    for (int s = 0; s < nsyms && is_min; s++) {
+    const long NN = (long)N * N;
+    // pass 1: is this node the smallest linear index of its orbit?  (most nodes leave after a few symmetries)
+    bool has_self = false;
+    for (int s = 0; s < nsyms; s++) {
         const int* S = sy + 9 * s;
-        long j1 = (long)S[0] * i1 + (long)S[1] * i2 + (long)S[2] * i3;
-        long j2 = (long)S[3] * i1 + (long)S[4] * i2 + (long)S[5] * i3;
-        long j3 = (long)S[6] * i1 + (long)S[7] * i2 + (long)S[8] * i3;
-        j1 = ((j1 % N) + N) % N; j2 = ((j2 % N) + N) % N; j3 = ((j3 % N) + N) % N;
-        const long jdx = (j3 * N + j2) * N + j1;
-        if (jdx < idx) { is_min = false; break; }
-        if (jdx == idx) has_self = true;
-        bool dup = false;
-        for (int r = 0; r < s; r++) {
-            const int* R = sy + 9 * r;
-            long q1 = (long)R[0] * i1 + (long)R[1] * i2 + (long)R[2] * i3;
-            long q2 = (long)R[3] * i1 + (long)R[4] * i2 + (long)R[5] * i3;
-            long q3 = (long)R[6] * i1 + (long)R[7] * i2 + (long)R[8] * i3;
-            q1 = ((q1 % N) + N) % N; q2 = ((q2 % N) + N) % N; q3 = ((q3 % N) + N) % N;
-            if ((q3 * N + q2) * N + q1 == jdx) { dup = true; break; }
-        }
-        if (!dup) cnt++;
+        int j3 = (S[6] * i1 + S[7] * i2 + S[8] * i3) % N;
+        j3 += (j3 < 0) ? N : 0;
+        const long jdx = (long)j3 * NN + symptr_image(S, i1, i2, i3, N);
+        if (jdx < idx) { wsym[idx] = 0; return; }
+        has_self |= (jdx == idx);
     }
-    if (is_min && !has_self) cnt++;   // identity absent from the list
-    wsym[idx] = is_min ? cnt : 0;
+    // pass 2 (irreducible nodes only, ~1/nsyms of the grid): weight = number of distinct images
+    int cnt = has_self ? 0 : 1;   // identity absent from the list: the node itself still belongs to its orbit
+    constexpr int CACHE = 64;
+    if (nsyms <= CACHE) {
+        long img[CACHE];
+        for (int s = 0; s < nsyms; s++) {
+            const int* S = sy + 9 * s;
+            int j3 = (S[6] * i1 + S[7] * i2 + S[8] * i3) % N;
+            j3 += (j3 < 0) ? N : 0;
+            img[s] = (long)j3 * NN + symptr_image(S, i1, i2, i3, N);
+        }
+        for (int s = 0; s < nsyms; s++) {
+            bool dup = false;
+            for (int r = 0; r < s; r++) dup |= (img[r] == img[s]);
+            cnt += dup ? 0 : 1;
+        }
+    } else {
+        for (int s = 0; s < nsyms; s++) {
+            const int* S = sy + 9 * s;
+            int j3 = (S[6] * i1 + S[7] * i2 + S[8] * i3) % N;
+            j3 += (j3 < 0) ? N : 0;
+            const long jdx = (long)j3 * NN + symptr_image(S, i1, i2, i3, N);
+            bool dup = false;
+            for (int r = 0; r < s && !dup; r++) {
+                const int* R = sy + 9 * r;
+                int q3 = (R[6] * i1 + R[7] * i2 + R[8] * i3) % N;
+                q3 += (q3 < 0) ? N : 0;
+                dup = ((long)q3 * NN + symptr_image(R, i1, i2, i3, N) == jdx);
+            }
+            cnt += dup ? 0 : 1;
+        }
+    }
+    wsym[idx] = cnt;
 }
 
 // CSR construction of the symmetry-reduced rule on the device (the reference's flags arrays,

@@ -203,65 +203,91 @@ __device__ __forceinline__ double2 small_resolvent_trace(const double2 (&h)[NORB
 // src/interfaces.jl:234-243).  Nothing of size nodes*n^2 is written to HBM.
 // row lookup: binary search in nodeptr[r0..r0+nrows]; identity (full grid) when klist == NULL.
 // ------------------------------------------------------------------------------------------------
-constexpr int SM_WCH = 4;
 constexpr int SM_THREADS = 256;
+constexpr int SM_NB = 2;          // nodes per thread per sweep (their H(k) stay in registers for all frequencies)
+constexpr int SM_WMAX = 1024;     // frequencies per CTA pass (shared accumulators: 9 * 16 B each)
 
+// Each thread evaluates H(k) ONCE for SM_NB nodes and then sweeps all frequencies with the matrices in registers;
+// per frequency the weighted traces are summed over the warp with a fixed xor-shuffle tree and lane 0 adds them to
+// the warp's shared accumulator, so the reduction order - hence the result - is bit-reproducible run to run.
+// blockIdx.y selects a chunk of SM_WMAX frequencies (one chunk unless nw > 1024).
+// shared: zs[nwc] | wacc[8][nwc]
 template <int NORB, bool FROM_H>
-__global__ void __launch_bounds__(SM_THREADS)
+__global__ void __launch_bounds__(SM_THREADS, 2)
 small_fused_kernel(const double2* __restrict__ C1, const double2* __restrict__ Hmat, const double2* __restrict__ ptab1,
                    const long* __restrict__ nodeptr, long r0, long nrows, const int* __restrict__ klist,
                    const double* __restrict__ wnode, int N, int M1, int fkind, int nw, const double2* __restrict__ z,
                    const double2* __restrict__ sigma, double2* __restrict__ partial, int* __restrict__ errflag) {
     constexpr int NN = NORB * NORB;
+    extern __shared__ double2 sf_smem[];
+    const int w0 = blockIdx.y * SM_WMAX;
+    const int nwc = (fkind == 1) ? 1 : min(SM_WMAX, nw - w0);
+    double2* zs = sf_smem;            // [nwc]
+    double2* wacc = sf_smem + nwc;    // [8][nwc]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < nwc; t += SM_THREADS) zs[t] = (fkind == 1) ? make_double2(0.0, 0.0) : z[w0 + t];
+    for (int t = threadIdx.x; t < 8 * nwc; t += SM_THREADS) wacc[t] = make_double2(0.0, 0.0);
+    __syncthreads();
     const long node_base = nodeptr[r0];
     const long nnodes = nodeptr[r0 + nrows] - node_base;
-    const int w0 = blockIdx.y * SM_WCH;
-    double2 acc[SM_WCH];
+    for (long base = (long)blockIdx.x * (SM_THREADS * SM_NB); base < nnodes; base += (long)gridDim.x * (SM_THREADS * SM_NB)) {
+        double2 h[SM_NB][NN];
+        double wt[SM_NB];
 #pragma unroll
-    for (int i = 0; i < SM_WCH; i++) acc[i] = make_double2(0.0, 0.0);
-    for (long i = (long)blockIdx.x * SM_THREADS + threadIdx.x; i < nnodes; i += (long)gridDim.x * SM_THREADS) {
-        double2 h[NN];
-        if (FROM_H) {
+        for (int b = 0; b < SM_NB; b++) {
+            const long i = base + b * SM_THREADS + threadIdx.x;
+            wt[b] = 0.0;
 #pragma unroll
-            for (int e = 0; e < NN; e++) h[e] = Hmat[i * NN + e];
-        } else {
-            // find row: largest r with nodeptr[r0 + r] - node_base <= i
-            long lo = 0, hi = nrows;
-            while (hi - lo > 1) {
-                long mid = (lo + hi) >> 1;
-                if (nodeptr[r0 + mid] - node_base <= i) lo = mid; else hi = mid;
-            }
-            const long row = lo;
-            const int k1 = klist ? klist[node_base + i] : (int)(i - (nodeptr[r0 + row] - node_base));
-            const double2* c = C1 + row * (long)M1 * NN;
+            for (int e = 0; e < NN; e++) h[b][e] = make_double2(0.0, 0.0);
+            if (i >= nnodes) continue;
+            wt[b] = wnode ? wnode[node_base + i] : 1.0;
+            if (FROM_H) {
 #pragma unroll
-            for (int e = 0; e < NN; e++) h[e] = make_double2(0.0, 0.0);
-            for (int m = 0; m < M1; m++) {
-                double2 p = ptab1[(long)m * N + k1];
+                for (int e = 0; e < NN; e++) h[b][e] = Hmat[i * NN + e];
+            } else {
+                // find row: largest r with nodeptr[r0 + r] - node_base <= i
+                long lo = 0, hi = nrows;
+                while (hi - lo > 1) {
+                    long mid = (lo + hi) >> 1;
+                    if (nodeptr[r0 + mid] - node_base <= i) lo = mid; else hi = mid;
+                }
+                const long row = lo;
+                const int k1 = klist ? klist[node_base + i] : (int)(i - (nodeptr[r0 + row] - node_base));
+                const double2* c = C1 + row * (long)M1 * NN;
+                for (int m = 0; m < M1; m++) {
+                    double2 p = ptab1[(long)m * N + k1];
 #pragma unroll
-                for (int e = 0; e < NN; e++) h[e] = cfma(h[e], c[m * NN + e], p);
-            }
-        }
-        const double wt = wnode ? wnode[node_base + i] : 1.0;
-        if (fkind == 1) {
-            double2 t = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int d = 0; d < NORB; d++) { t.x += h[d * (NORB + 1)].x; t.y += h[d * (NORB + 1)].y; }
-            if (blockIdx.y == 0) { acc[0].x += wt * t.x; acc[0].y += wt * t.y; }
-        } else {
-#pragma unroll
-            for (int wi = 0; wi < SM_WCH; wi++) {
-                if (w0 + wi < nw) {
-                    double2 t = small_resolvent_trace<NORB>(h, z[w0 + wi], sigma ? sigma + (long)(w0 + wi) * NN : nullptr);
-                    if (!(isfinite(t.x) && isfinite(t.y))) *errflag = 1;
-                    acc[wi].x += wt * t.x; acc[wi].y += wt * t.y;
+                    for (int e = 0; e < NN; e++) h[b][e] = cfma(h[b][e], c[m * NN + e], p);
                 }
             }
         }
+        for (int w = 0; w < nwc; w++) {
+            double2 sv = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int b = 0; b < SM_NB; b++) {
+                double2 t;
+                if (fkind == 1) {
+                    t = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int d = 0; d < NORB; d++) { t.x += h[b][d * (NORB + 1)].x; t.y += h[b][d * (NORB + 1)].y; }
+                } else {
+                    t = small_resolvent_trace<NORB>(h[b], zs[w], sigma ? sigma + (long)(w0 + w) * NN : nullptr);
+                    if (wt[b] != 0.0 && !(isfinite(t.x) && isfinite(t.y))) *errflag = 1;
+                }
+                if (wt[b] != 0.0) { sv.x += wt[b] * t.x; sv.y += wt[b] * t.y; }
+            }
+            sv.x = warp_sum(sv.x);
+            sv.y = warp_sum(sv.y);
+            if (lane == 0) { double2 a = wacc[warp * nwc + w]; a.x += sv.x; a.y += sv.y; wacc[warp * nwc + w] = a; }
+        }
     }
-    int nvalid = nw - w0 < SM_WCH ? nw - w0 : SM_WCH;
-    if (fkind == 1) nvalid = (blockIdx.y == 0) ? 1 : 0;
-    block_reduce_store<SM_WCH, SM_THREADS>(acc, partial + (long)blockIdx.x * nw + w0, nvalid);
+    __syncthreads();
+    for (int t = threadIdx.x; t < nwc; t += SM_THREADS) {
+        double2 a = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int wp = 0; wp < 8; wp++) { a.x += wacc[wp * nwc + t].x; a.y += wacc[wp * nwc + t].y; }
+        partial[(long)blockIdx.x * nw + w0 + t] = a;
+    }
 }
 
 // per-node values (no sum): y[i*nw + w] for the IAI batch path and tests.  One thread per node.

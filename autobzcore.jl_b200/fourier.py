@@ -66,6 +66,19 @@ class FourierValue:
         self.x, self.s = x, s
 
 
+class BatchIntegrand:
+    """BatchIntegrand(f!, y, x; max_batch) (src/batch.jl:10-38): f!(y, x, args...; kws...) fills y[i] with the integrand at
+    node i of a whole vector of nodes - the reference's documented hook for threads / GPU / distributed evaluation.
+    As the integrand of a FourierIntegrand, x is a FourierValue whose fields are arrays: x.x [nb, ndim] the nodes and
+    x.s [nb, n, n] (or [nb] for a scalar series) the series values, evaluated on the device; y is a preallocated
+    numpy array of length nb and dtype `dtype`.  max_batch is the soft cap on nb (src/batch.jl:17)."""
+
+    def __init__(self, f, dtype=np.complex128, max_batch=None):
+        if max_batch is not None and max_batch <= 0:
+            raise ValueError("maximum batch size must be positive")
+        self.f, self.dtype, self.max_batch = f, np.dtype(dtype), max_batch
+
+
 class _NativeIntegrand:
     """Base of the integrands whose arithmetic runs on the device."""
     fkind = _lib.F_RESOLVENT_TRACE
@@ -180,3 +193,20 @@ class FourierIntegrand:
         if self.native:
             raise TypeError("device-native integrands are evaluated by the specialised rules")
         return self.f(x, *args, **kws)
+
+    def host_values(self, H, k, p=None):
+        """values of a host (non-native) integrand on a batch of nodes: H [n, n, nb] from the device, k [nb, ndim].
+        BatchIntegrand: f!(y, x, p) in chunks of max_batch (src/batch.jl:4-20); plain callable: node by node."""
+        args, kws = self.merged(p)
+        nb = H.shape[2]
+        Hm = np.moveaxis(H, 2, 0)
+        if self.s.norb == 1:
+            Hm = Hm[:, 0, 0]
+        if isinstance(self.f, BatchIntegrand):
+            y = np.empty(nb, dtype=self.f.dtype)
+            step = nb if self.f.max_batch is None else int(self.f.max_batch)
+            for a in range(0, nb, max(step, 1)):
+                b = min(nb, a + step)
+                self.f.f(y[a:b], FourierValue(k[a:b], Hm[a:b]), *args, **kws)
+            return y
+        return np.array([self.f(FourierValue(k[i], Hm[i]), *args, **kws) for i in range(nb)])

@@ -121,10 +121,11 @@ class _Pend:
 
 
 class _Integral:
-    __slots__ = ("level", "lims", "atol", "slot", "parent", "heap", "I", "E", "numevals", "popped", "s1", "s2", "state")
+    __slots__ = ("level", "lims", "atol", "slot", "parent", "heap", "I", "E", "numevals", "popped", "s1", "s2", "state", "outer")
 
-    def __init__(self, level, lims, atol, slot, parent):
+    def __init__(self, level, lims, atol, slot, parent, outer=()):
         self.level, self.lims, self.atol, self.slot, self.parent = level, lims, atol, slot, parent
+        self.outer = outer          # coordinates already fixed by the outer integrals: (x_{level+2}, ..., x_ndim)
         self.heap, self.numevals, self.state = [], 0, 0
         self.s1 = self.s2 = self.popped = None
 
@@ -132,13 +133,16 @@ class _Integral:
 class NestedGK:
     """One nested adaptive integration of a Fourier integrand over iterated limits.
 
-    nest: device arena (backend.make_nest) exposing contract3 / contract2 / eval
-    point_values(y) -> integrand values from the device's per-node output (e.g. DOS = -Im tr / pi)
+    nest: device arena (backend.make_nest) exposing contract3 / contract2 / eval / eval_h
+    post(y) -> integrand values from the device's per-node output (e.g. DOS = -Im tr / pi)
+    user(H, k) -> integrand values for a generic host integrand: H [n, n, npts] from the device (abz_nest_eval_h),
+                  k [npts, ndim] the full points (FourierValue(limit_iterate(lims, state, x), H), src/fourier.jl:454)
     """
 
-    def __init__(self, nest, ndim, lims, fkind, z, sigma, post, dtype, atol, rtol, maxevals, cap2=64, cap1=2048):
+    def __init__(self, nest, ndim, lims, fkind, z, sigma, post, dtype, atol, rtol, maxevals, cap2=64, cap1=2048, user=None):
         self.nest, self.ndim, self.lims = nest, ndim, lims
         self.fkind, self.z, self.sigma, self.post, self.dtype = fkind, z, sigma, post, dtype
+        self.user = user
         self.atol, self.rtol, self.maxevals = atol, rtol, maxevals
         self.free2 = list(range(cap2 - 1, -1, -1))
         self.free1 = list(range(cap1 - 1, -1, -1))
@@ -174,7 +178,8 @@ class NestedGK:
                 self.q_c3.append((x, slot))
             else:
                 self.q_c2.append((x, q.slot, slot))
-            child = _Integral(q.level - 1, clims, q.atol / length if self.atol_given else q.atol, slot, (q, pend, i))
+            child = _Integral(q.level - 1, clims, q.atol / length if self.atol_given else q.atol, slot, (q, pend, i),
+                              (x,) + q.outer)
             self._start_segment(child, ca, cb, 0)
 
     def _finish(self, q):
@@ -267,9 +272,17 @@ class NestedGK:
             slots = None
             if self.ndim >= 2:
                 slots = np.repeat(np.array([q.slot for q, _ in batch], dtype=np.int64), 15)
-            y = self.nest.eval(xs.reshape(-1), slots, self.z, self.sigma, self.fkind)
+            if self.user is not None:
+                H = self.nest.eval_h(xs.reshape(-1), slots)
+                k = np.empty((15 * nseg, self.ndim))
+                k[:, 0] = xs.reshape(-1)
+                if self.ndim > 1:
+                    k[:, 1:] = np.repeat(np.array([q.outer for q, _ in batch], dtype=np.float64).reshape(nseg, self.ndim - 1), 15, axis=0)
+                vals = np.asarray(self.user(H, k), dtype=self.dtype).reshape(nseg, 15)
+            else:
+                y = self.nest.eval(xs.reshape(-1), slots, self.z, self.sigma, self.fkind)
+                vals = self.post(y).reshape(nseg, 15)
             self.numevals += 15 * nseg
-            vals = self.post(y).reshape(nseg, 15)
             Is, Es = gk15_combine(aa, bb, vals)
             for i in range(nseg):
                 q, pend = batch[i]

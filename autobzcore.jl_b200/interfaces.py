@@ -124,16 +124,9 @@ class _BoundIntegrand:
         """sum_i w_i f(x_i) over the rule's local nodes for every parameter -> list of values"""
         f = self.f
         if not self.native:
+            # generic / batch user integrand on the host (S3 seam, src/batch.jl:4-20): H(k) comes back from the device
             H, k, w = rule.copy_out()
-            Hm = np.moveaxis(H, 2, 0)
-            out = []
-            for p in self.plist:
-                acc = 0
-                for i in range(Hm.shape[0]):
-                    s = Hm[i] if f.s.norb > 1 else Hm[i][0, 0]
-                    acc = acc + w[i] * f(FourierValue(k[i, :f.s.ndim], s), p)
-                out.append(acc)
-            return out
+            return [np.sum(w * f.host_values(H, k[:, :f.s.ndim], p)) if H.shape[2] else 0.0 for p in self.plist]
         if self.is_eig:
             return [rule.eig_sum(f.f.kind, b) for b in self.bound]
         if self.fkind == _lib.F_TRACE_H:
@@ -256,8 +249,8 @@ def _init_cacheval(cache):
     elif isinstance(salg, NestedQuad):
         if not isinstance(dom, (CubicLimits, TetrahedralLimits)):
             raise TypeError("NestedQuad needs iterated limits")
-        if not f.native or f.f.is_eig:
-            raise TypeError("IAI on the device supports the resolvent / affine integrands")
+        if f.native and f.f.is_eig:
+            raise TypeError("IAI on the device supports the resolvent / affine integrands and host (batch) integrands")
         cv["nest"] = cache.backend.make_nest(f.s, ndim, 64, 2048)
     else:
         raise TypeError(f"unsupported algorithm {type(salg).__name__} for FourierIntegrand")
@@ -295,6 +288,23 @@ def _do_solve(cache, ps):
             atol = abstol / (j * ns)                        # src/brillouin.jl:342
         for p in ps:
             b1 = _BoundIntegrand(cache.f, [p])
+            if not b1.native:
+                # generic / batch host integrand: H at the panel nodes comes from the device (abz_nest_eval_h)
+                fi, pp = cache.f, b1.plist[0]
+                real = [True]
+
+                def user(H, k, fi=fi, pp=pp, real=real):
+                    v = np.asarray(fi.host_values(H, k, pp))
+                    real[0] = real[0] and not np.iscomplexobj(v)
+                    return v
+
+                eng = NestedGK(cache.cacheval["nest"], ndim, dom, None, None, None, None, np.complex128, atol, reltol, maxiters, user=user)
+                Iv, Ev, ne = eng.run()
+                cache.cacheval["iai_rounds"] = eng.rounds
+                mult = sc * (ns if on_bz else 1)
+                u = Iv * mult
+                sols.append(IntegralSolution(float(u.real) if real[0] else complex(u), float(Ev) * mult, True, ne if counter else -1))
+                continue
             bound = b1.bound[0]
             ff = cache.f.f
             if b1.fkind == _lib.F_TRACE_H:
@@ -354,27 +364,37 @@ def _autosymptr(cache, bf, salg, atol, reltol, maxevals, ndim):
     n0, dn = cache.cacheval["schedule"]
     f, backend, shard = cache.f, cache.backend, cache.shard
 
+    timing = cache.cacheval.setdefault("timing", [])
+
     def rule_at(i):
         while len(rules) <= i:
             prev = rules[-1]
+            t0 = time.perf_counter()
             rules.append(backend.make_rule(f.s, ndim, prev.npt + dn, salg.syms, shard.rank, shard.nranks))
+            timing.append(("make_rule", prev.npt + dn, time.perf_counter() - t0))
         return rules[i]
+
+    def apply(r):
+        t0 = time.perf_counter()
+        v = _rule_apply(r, bf, shard, ndim)[0]
+        timing.append(("apply", r.npt, time.perf_counter() - t0))
+        return v
 
     numevals = 0
     r1 = rule_at(0)
-    int1 = _rule_apply(r1, bf, shard, ndim)[0]
+    int1 = apply(r1)
     numevals += len(r1)
     if numevals >= maxevals:
         return int1, float("nan"), numevals
     r2 = rule_at(1)
-    int2 = _rule_apply(r2, bf, shard, ndim)[0]
+    int2 = apply(r2)
     numevals += len(r2)
     err = salg.norm(int1 - int2)
     i = 1
     while not (err <= max(rtol_ * salg.norm(int2), atol_)) and numevals < maxevals and np.isfinite(err):
         i += 1
         r = rule_at(i)
-        int1, int2 = int2, _rule_apply(r, bf, shard, ndim)[0]
+        int1, int2 = int2, apply(r)
         numevals += len(r)
         err = salg.norm(int1 - int2)
     # keep the `keepmost` most refined rules for the next parameter (src/algorithms.jl:429 keepmost)

@@ -144,6 +144,9 @@ int32_t abz_nest_contract2(abz_ctx* ctx, abz_nest_t nest, int64_t n, const doubl
 int32_t abz_nest_eval(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const double* x1, const int64_t* slot1,
                       int32_t fkind, const double* z, const double* sigma, double* y);
 
+/* the same closure for a generic user integrand evaluated by the host (f.f(FourierValue(k, H(k)), p), src/fourier.jl:452-456;
+ * BatchIntegrand's f!(y, x, p), src/batch.jl:4-20): only H at the nodes, Hk = ComplexF64[n,n,npts] */
+int32_t abz_nest_eval_h(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const double* x1, const int64_t* slot1, double* Hk);
 /* The whole nested adaptive solve do_solve(f::FourierIntegrand, lims, ::NestedQuad) (src/fourier.jl:493-510) with
  * GK(7,15) at every level (AuxQuadGKJL/QuadGKJL defaults, src/algorithms.jl:215-240): the adaptive control flow
  * (QuadGK do_quadgk/adapt/refine, DataStructures heap, inner abstol = abstol/len, src/fourier.jl:479-480) runs on

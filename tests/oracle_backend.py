@@ -115,6 +115,16 @@ class OracleNest:
             src = root if parent is None else self.L2[int(parent[i])]
             self.L1[int(sl)] = self._contract(src, rows, s.M[1], s.lo[1], s.period[1], float(x))
 
+    def eval_h(self, x1, slot1):
+        s = self.so
+        nn = s.n * s.n
+        root = np.ascontiguousarray(s.c.reshape(-1, order="F"))
+        H = np.empty((s.n, s.n, len(x1)), dtype=np.complex128, order="F")
+        for i, x in enumerate(x1):
+            src = root if slot1 is None else self.L1[int(slot1[i])]
+            H[:, :, i] = self._contract(src, nn, s.M[0], s.lo[0], s.period[0], float(x)).reshape(s.n, s.n, order="F")
+        return H
+
     def eval(self, x1, slot1, z, sigma, fkind):
         s = self.so
         nn = s.n * s.n

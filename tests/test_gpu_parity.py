@@ -412,3 +412,28 @@ def test_eig_algorithms_agree_with_lapack(ctx, n):
     Hd[:, :, -lo[0], -lo[1], -lo[2]] = np.diag(np.repeat(np.arange((n + 1) // 2), 2)[:n])
     Rd = L.DeviceRule(ctx, L.DeviceSeries(ctx, Hd, lo, (1.0,) * 3), 3)
     assert np.array_equal(Rd.eigvals(), np.tile(np.repeat(np.arange((n + 1) // 2), 2)[:n].astype(float), (27, 1)))
+
+
+def test_generic_and_batch_integrands_on_device(ctx, orc, svo):
+    """S3/S4 seams for user integrands evaluated on the host: H(k) at the rule nodes (abz_rule_copy_out) or at IAI panel
+    nodes (abz_nest_eval_h) comes from the device; a plain callable and its BatchIntegrand form reproduce the native
+    DOS integrand: same value to 1e-10 and the same adaptive evaluation count."""
+    H, lo, A = svo
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), A)
+    eta, omega = 0.1, 12.5
+
+    def dos(x, eta, omega):
+        return -np.imag(np.trace(np.linalg.inv(complex(omega, eta) * np.eye(3) - x.s))) / np.pi
+
+    def dos_batch(y, x, eta, omega):
+        assert x.s.shape == (len(y), 3, 3) and x.x.shape == (len(y), 3)
+        y[:] = -np.imag(np.trace(np.linalg.inv(complex(omega, eta) * np.eye(3) - x.s), axis1=1, axis2=2)) / np.pi
+
+    for alg, kw in ((ab.IAI(), dict(abstol=5e-1)), (ab.PTR(npt=12), {})):
+        ref = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.dos_integrand, fs, eta), ibz, omega), ab.EvalCounter(alg), **kw)
+        for integrand in (ab.FourierIntegrand(dos, fs, eta), ab.FourierIntegrand(ab.BatchIntegrand(dos_batch, dtype=np.float64, max_batch=4096), fs, eta)):
+            sol = ab.solve(ab.IntegralProblem(integrand, ibz, omega), ab.EvalCounter(alg), **kw)
+            assert sol.numevals == ref.numevals
+            assert abs(sol.u - ref.u) <= 1e-10 * abs(ref.u)
+            assert isinstance(sol.u, float)

@@ -184,3 +184,46 @@ def test_two_rank_gloo_sharding(tmp_path):
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_generic_and_batch_integrands_match_native(d):
+    """test/fourier.jl:24-56: a plain user integrand f(x::FourierValue, a; b) = a*x.s + b and its BatchIntegrand form
+    f!(y, x, a; b) (src/batch.jl:10-38, the S3 seam) give the same integrals - and, for IAI, the same adaptive
+    evaluation counts - as the device-native affine integrand, for IAI / PTR / AutoPTR."""
+    vol = (2 * np.pi) ** d
+    s = lattice_series(d)
+    be = OracleBackend()
+
+    def f(x, a, b=0.0):
+        return a * x.s + b
+
+    calls = []
+
+    def fb(y, x, a, b=0.0):
+        calls.append(len(y))
+        assert x.x.shape == (len(y), d) and x.s.shape == (len(y),)
+        y[:] = a * x.s + b
+
+    for bz in (ab.load_bz(ab.FBZ(), np.eye(d)), ab.load_bz(ab.InversionSymIBZ(), np.eye(d))):
+        for alg in (ab.IAI(), ab.PTR(npt=12), ab.AutoPTR()):
+            ref = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.AffineTraceIntegrand(), s, 1.3, b=1.0), bz), ab.EvalCounter(alg),
+                           reltol=0, abstol=1e-6, backend=be)
+            for integrand in (ab.FourierIntegrand(f, s, 1.3, b=1.0), ab.FourierIntegrand(ab.BatchIntegrand(fb, max_batch=100), s, 1.3, b=1.0)):
+                sol = ab.solve(ab.IntegralProblem(integrand, bz), ab.EvalCounter(alg), reltol=0, abstol=1e-6, backend=be)
+                assert abs(sol.u - vol) < 1e-6 and abs(sol.u - ref.u) < 1e-9
+                assert sol.numevals == ref.numevals
+    assert calls and max(calls) <= 100
+    assert ab.BatchIntegralFunction is ab.BatchIntegrand and ab.FourierIntegralFunction is ab.FourierIntegrand
+    with pytest.raises(ValueError):
+        ab.BatchIntegrand(fb, max_batch=0)
+
+
+def test_generic_integrand_sees_full_k_points_in_iai():
+    """the innermost closure passes FourierValue(limit_iterate(lims, state, x), H(x)) (src/fourier.jl:454): the integrand
+    sees the full k = (k1, k2, k3).  Integrate k1 + 2 k2 + 4 k3 over the unit cube = 3.5 (per unit |det B|)."""
+    s = lattice_series(3)
+    bz = ab.load_bz(ab.FBZ(), 2 * np.pi * np.eye(3))           # B = I  =>  j = 1
+    f = ab.FourierIntegrand(lambda x: x.x[0] + 2 * x.x[1] + 4 * x.x[2] + 0 * x.s.real, s)
+    sol = ab.solve(ab.IntegralProblem(f, bz), ab.EvalCounter(ab.IAI()), abstol=1e-10, backend=OracleBackend())
+    assert abs(sol.u - 3.5) < 1e-12 and sol.numevals == 15 ** 3 and isinstance(sol.u, float)

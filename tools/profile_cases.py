@@ -1,0 +1,50 @@
+"""Short single-GPU cases that launch every kernel family of the library a few times, for `ncu --set full -k regex:...`
+(one capture per change; see profiles/).  Usage: python tools/profile_cases.py [contract] [small] [eig] [iai]"""
+import os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+import autobz_b200 as ab
+from autobz_b200 import _lib as L
+
+ctx = ab.default_context(0)
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+which = sys.argv[1:] or ["contract", "small", "eig", "iai"]
+d = np.load(os.path.join(ROOT, "tests", "golden", "svo_hr.npz"))
+Hs, los, A = np.asfortranarray(d["H_R"]), tuple(int(x) for x in d["lo"]), d["A"]
+
+if "contract" in which:
+    # C4 shape: norb 32, M 17, one k3 plane of the 256^3 grid: stage 3 / 2 / 1 contractions, then 8 resolvents per node
+    H, lo = ab.synthetic.wannier_hamiltonian(32, 8)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    R = L.DeviceRule(ctx, S, 256, k3_lo=0, k3_hi=1)
+    R.materialize()
+    ext = ab.synthetic.band_extent(H)
+    z = np.linspace(-0.2 * ext, 0.2 * ext, 8) + 1j * 0.01 * ext
+    print("contract", R.resolvent_sum(z)[:2], ctx.last_timings())
+    R.close(); S.close()
+
+if "small" in which:
+    fs = ab.FourierSeries(Hs, period=1.0, lo=los, norb=3)
+    f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=1e-2)
+    ws = [{"omega": w} for w in np.linspace(11.0, 14.0, 16)]
+    for npt, dom in ((200, ab.load_bz(ab.FBZ(), A)), (400, ab.load_bz(ab.CubicSymIBZ(), A))):
+        solver = ab.IntegralSolver(f, dom, ab.PTR(npt=npt))
+        print("small", npt, ab.batchsolve(solver, ws)[:1], ctx.last_timings())
+
+if "eig" in which:
+    n = 64
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 4, cubic=True)
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=n)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), 2 * np.pi * np.eye(3))
+    f = ab.FourierIntegrand(ab.EigenIntegrand("fermi_energy"), fs, 0.0, 0.5)
+    sol = ab.solve(ab.IntegralProblem(f, ibz), ab.PTR(npt=96))
+    print("eig", sol.u, ctx.last_timings())
+
+if "iai" in which:
+    fs = ab.FourierSeries(Hs, period=1.0, lo=los, norb=3)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), A)
+    f = ab.FourierIntegrand(ab.dos_integrand, fs, 0.05)
+    for leaves in (True, False):
+        be = ab.DeviceBackend(ctx=ctx, iai_engine="native", iai_device_leaves=leaves)
+        sol = ab.solve(ab.IntegralProblem(f, ibz, 12.5), ab.EvalCounter(ab.IAI()), abstol=3e-1, backend=be)
+        print("iai", leaves, sol.u, sol.numevals)

@@ -1,5 +1,7 @@
-"""Runs the five BASELINE.json configurations through the public API on one B200 and prints one JSON line each
-(k-points/s, evaluations, device timings).  Parity for the same configs lives in tests/; this is the measurement."""
+"""Runs the BASELINE.json configurations through the public API on one B200 and prints one JSON line each
+(k-points/s, evaluations, device timings).  Parity for the same configs lives in tests/; this is the measurement.
+With "cpu" among the arguments the CPU oracle (C/OpenMP restatement of the reference path, oracle/) is timed beside
+each config on a bounded sample of the same workload on this box's host cores - a reported baseline."""
 import json, os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
@@ -11,6 +13,13 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 d = np.load(os.path.join(ROOT, "tests", "golden", "svo_hr.npz"))
 Hs, los, A = np.asfortranarray(d["H_R"]), tuple(int(x) for x in d["lo"]), d["A"]
 which = sys.argv[1:] or ["c1", "c2", "c3", "c5"]
+
+# bring the clocks up before the first measurement
+_w = L.DeviceRule(ctx, L.DeviceSeries(ctx, *ab.synthetic.wannier_hamiltonian(32, 2), (1.0,) * 3), 32)
+for _ in range(3):
+    _w.resolvent_sum(np.linspace(-1, 1, 32) + 0.05j)
+_w.close()
+
 
 def emit(**kw):
     print(json.dumps(kw), flush=True)
@@ -44,7 +53,8 @@ if "c2" in which:
         t = time.perf_counter(); cache = ab.init(ab.IntegralProblem(f, ibz, {"omega": w}), alg, abstol=1e-3); t_init = time.perf_counter() - t
         t = time.perf_counter(); sol = ab.solve_(cache); dt = time.perf_counter() - t
         emit(config=f"C2 SrVO3 AutoPTR(a=eta=1e-2) CubicSymIBZ omega={w}", u=[sol.u.real, sol.u.imag], resid=float(sol.resid), numevals=sol.numevals,
-             last_npt=cache.cacheval.get("last_npt"), init_ms=1e3 * t_init, solve_ms=1e3 * dt, kpoints_per_s=sol.numevals / dt)
+             last_npt=cache.cacheval.get("last_npt"), init_ms=1e3 * t_init, solve_ms=1e3 * dt, kpoints_per_s=sol.numevals / dt,
+             phases=[(a, b, round(1e3 * c, 2)) for a, b, c in cache.cacheval.get("timing", [])])
 
 if "c3" in which:
     fs = ab.FourierSeries(Hs, period=1.0, lo=los, norb=3)
@@ -81,3 +91,29 @@ if "c5" in which:
              eig_tflops_credited=(32 / 3) * n ** 3 * nn / (mf * 1e-3) * 1e-12 if mf else None)
     t = time.perf_counter(); sol = ab.solve(ab.IntegralProblem(f, ibz), ab.EvalCounter(ab.AutoPTR(a=1.0, nmin=48, dn=48.0)), reltol=1e-6); dt = time.perf_counter() - t
     emit(config="C5 norb=64 band energy CubicSymIBZ AutoPTR 48->96->144", u=sol.u, resid=sol.resid, numevals=sol.numevals, s=dt)
+
+if "cpu" in which:
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    nth = orc.lib().orc_max_threads()
+    So = orc.Series(Hs, los)
+    syms = np.array(ab.cube_automorphisms(3), dtype=np.int32)
+    # C2: symmetric PTR sum, SrVO3, 64 frequencies, npt = 100 (29 316 irreducible nodes)
+    w, nirr = orc.symptr_rule(100, syms)
+    zs = np.linspace(11.0, 14.0, 64) + 1e-2j
+    t = time.perf_counter(); orc.symptr_sum(So, 100, w, zs); dt = time.perf_counter() - t
+    emit(config="CPU oracle C2 SrVO3 symmetric PTR npt=100, 64 freqs", cores=nth, nodes=nirr, s=dt, kpoints_per_s=nirr / dt, k_omega_per_s=nirr * 64 / dt)
+    # C3: IAI eta = 1e-2 (sequential recursion, one core - the reference's IAI is single-threaded)
+    for wv in (12.0, 12.975161):
+        t = time.perf_counter(); Io, Eo, ne = orc.iai(So, 3, 1, [0.5] * 3, vkind=1, z=complex(wv, 1e-2), atol=1e-3 / (abs(np.linalg.det(2 * np.pi * np.linalg.inv(A).T)) * 48)); dt = time.perf_counter() - t
+        emit(config=f"CPU oracle C3 SrVO3 IAI eta=0.01 abstol=0.001 omega={wv}", cores=1, numevals=ne, s=dt, evals_per_s=ne / dt)
+    # C5: norb = 64 band-energy sum on the IBZ, npt = 16 (oracle: Jacobi eigenvalues; beside it LAPACK zheevd through numpy,
+    # which is what the reference's eigen(Hermitian(h)) calls, on the same H(k), one core)
+    H5, lo5 = ab.synthetic.wannier_hamiltonian(64, 4, cubic=True)
+    S5 = orc.Series(H5, lo5)
+    w5, n5 = orc.symptr_rule(16, syms)
+    t = time.perf_counter(); orc.ptr_eig_sum(S5, 16, 1, (0.0, 0.5), wsym=w5, scale=1 / 16 ** 3); dt = time.perf_counter() - t
+    emit(config="CPU oracle C5 norb=64 band energy CubicSymIBZ PTR npt=16 (Jacobi)", cores=nth, nodes=n5, s=dt, kpoints_per_s=n5 / dt)
+    Hk = np.moveaxis(orc.eval_points(S5, np.random.default_rng(0).random((2000, 3))), 2, 0).copy()
+    t = time.perf_counter(); np.linalg.eigvalsh(Hk); dt = time.perf_counter() - t
+    emit(config="CPU LAPACK (numpy eigvalsh) 64x64 complex Hermitian, 2000 matrices", cores=1, s=dt, matrices_per_s=2000 / dt)
