@@ -219,7 +219,7 @@ std::vector<Chunk> plan_chunks(const Rule* r, long node_cap, long row_cap, long 
     return out;
 }
 
-size_t stage_smem(int M) { return (size_t)((M + 1) & ~1) * (ST_RT + ST_JT) * sizeof(double2); }
+size_t stage_smem(int M) { return (size_t)((M + 1) & ~1) * (ST_RT + 2 * ST_JT) * sizeof(double2) + 64; }
 
 int launch_stage(abz_ctx* ctx, const double2* in, double2* out, const double2* ptab, const long* ptr, long b0,
                  long nbatch, const int* klist, int N, int M, long rows, long in_stride) {
@@ -1321,6 +1321,16 @@ int pin_reserve(abz_ctx* ctx, void** p, size_t* cap, size_t bytes) {
 struct IaiDeviceBackend {
     abz_ctx* ctx; Nest* nst; int fkind, vkind; double2 z; const double2* dsig; abz_iai::cplx la, lb;
     double rtol; int64_t maxevals;
+    abz_exchange_fn xfn = nullptr; void* xuser = nullptr;
+
+    // in-place sum over ranks: the caller's hook (e.g. a host-language MPI / torch.distributed allreduce) or NCCL on the ctx communicator
+    int exchange(double* buf, size_t n) {
+        if (xfn) {
+            if (xfn(buf, (int64_t)n, xuser) != 0) return fail(ctx, ABZ_E_NCCL, "abz_iai_solve_sharded: the exchange callback failed");
+            return ABZ_OK;
+        }
+        return abz_allreduce_sum(ctx, buf, (int64_t)n);
+    }
 
     int run_round(abz_iai::Round& R) {
         int rc = run_once(R);
@@ -1468,7 +1478,18 @@ struct IaiDeviceBackend {
 int32_t abz_iai_solve(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const double* la, const double* lb, int32_t fkind,
                       int32_t vkind, const double* z, const double* sigma, const double* lin, double atol, double rtol,
                       int64_t maxevals, int32_t flags, double* out, int64_t* stats) {
+    return abz_iai_solve_sharded(ctx, nid, lkind, la, lb, fkind, vkind, z, sigma, lin, atol, rtol, maxevals, flags, 0, 1, nullptr, nullptr,
+                                 out, stats);
+}
+
+int32_t abz_iai_solve_sharded(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const double* la, const double* lb, int32_t fkind,
+                              int32_t vkind, const double* z, const double* sigma, const double* lin, double atol, double rtol,
+                              int64_t maxevals, int32_t flags, int32_t rank, int32_t nranks, abz_exchange_fn exchange,
+                              void* exchange_user, double* out, int64_t* stats) {
     if (!ctx) return ABZ_E_INVALID;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, ABZ_E_INVALID, "invalid rank/nranks");
+    if (nranks > 1 && !exchange && !ctx->nccl_comm)
+        return fail(ctx, ABZ_E_NCCL, "abz_iai_solve_sharded: nranks > 1 needs an exchange callback or abz_comm_init");
     Nest* nst = get_nest(ctx, nid);
     if (!nst) return fail(ctx, ABZ_E_INVALID, "unknown nest handle");
     if ((lkind != 0 && lkind != 1) || !la || (lkind == 0 && !lb) || !out || vkind < 0 || vkind > 2 ||
@@ -1490,12 +1511,13 @@ int32_t abz_iai_solve(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const double*
     be.la = abz_iai::cplx{lin ? lin[0] : 1.0, lin ? lin[1] : 0.0};
     be.lb = abz_iai::cplx{lin ? lin[2] : 0.0, lin ? lin[3] : 0.0};
     be.rtol = rtol; be.maxevals = maxevals;
+    be.xfn = exchange; be.xuser = exchange_user;
     const bool leaf = (flags & ABZ_IAI_DEVICE_LEAVES) && s->n <= 3 && nst->ndim >= 2;
     const long launches0 = ctx->launches;
-    abz_iai::Engine<IaiDeviceBackend> eng(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, leaf);
+    abz_iai::Engine<IaiDeviceBackend> eng(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, leaf, rank, nranks);
     rc = eng.run();
     ctx->force_generic = false;
-    if (stats) { stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = ctx->launches - launches0; }
+    if (stats) { stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = ctx->launches - launches0; stats[3] = eng.exchanges; }
     if (rc == abz_iai::IAI_E_NAN) return fail(ctx, ABZ_E_SINGULAR, eng.error);
     if (rc == abz_iai::IAI_E_ARENA) return fail(ctx, ABZ_E_OOM, eng.error);
     if (rc == abz_iai::IAI_E_STALL) return fail(ctx, ABZ_E_INVALID, eng.error);

@@ -10,6 +10,12 @@
 // batch per round leaves every accept/refine decision - and hence EvalCounter's numevals
 // (src/fourier.jl:516-523) - unchanged with respect to the sequential recursion.
 //
+// Multi-rank: the 15 nodes of every panel of the OUTERMOST integral are dealt round-robin to the ranks;
+// each rank runs the inner integrals of its own nodes, and when its local work is exhausted all ranks meet in ONE small
+// sum-allreduce per outer refinement step (values of the outstanding outer panels, zeros for nodes a rank does not own,
+// plus evaluation counts), after which every rank makes the identical accept/refine decision.  x + 0 is exact, so the
+// result is bit-identical to the single-rank solve.
+//
 // With leaf_tasks = true the innermost (level-0) integrals are not run by this state machine: each is
 // handed to the backend as ONE task (slot, a, b, atol) that returns (I, E, numevals) - the device runs
 // the whole 1-D adaptive loop with one warp per task (abz_iai.cuh, iai_leaf_kernel).
@@ -202,19 +208,20 @@ struct Round {
 
 enum { IAI_OK = 0, IAI_E_NAN = -4, IAI_E_ARENA = -2, IAI_E_STALL = -7 };
 
-// Backend concept:  int run_round(Round&)  fills the outputs for the queued inputs, returns 0 or an error code.
+// Backend concept:  int run_round(Round&)  fills the outputs for the queued inputs, returns 0 or an error code;
+//                   int exchange(double* buf, size_t n)  in-place sum over ranks (only called when nranks > 1).
 template <class Backend>
 class Engine {
 public:
     Engine(Backend& be, int ndim, const Limits& lims, double atol, double rtol, int64_t maxevals, int64_t cap2,
-           int64_t cap1, bool leaf_tasks)
+           int64_t cap1, bool leaf_tasks, int rank = 0, int nranks = 1)
         : be_(be), ndim_(ndim), lims_(lims), atol_(atol), rtol_(rtol), maxevals_(maxevals),
-          leaf_tasks_(leaf_tasks && ndim >= 2) {
+          leaf_tasks_(leaf_tasks && ndim >= 2), rank_(rank), nranks_(ndim >= 2 ? nranks : 1) {
         for (int64_t i = cap2 - 1; i >= 0; i--) free2_.push_back(i);
         for (int64_t i = cap1 - 1; i >= 0; i--) free1_.push_back(i);
     }
 
-    int64_t numevals = 0, rounds = 0;
+    int64_t numevals = 0, rounds = 0, exchanges = 0;   // numevals: all ranks' evaluations once the solve has finished
     cplx result{0, 0};
     double result_err = 0;
     std::string error;
@@ -225,35 +232,47 @@ public:
         int root = new_integral(ndim_ - 1, lims_, atol_, -1, -1, -1, -1);
         int rc = start_segment(root, a, b, 0);
         if (rc) return rc;
+        int local_rc = IAI_OK;
         while (!done_) {
+            if ((q_seg_.empty() && q_task_.empty()) || local_rc) {
+                // local work exhausted: single rank = stalled; several ranks = meet the others (one allreduce)
+                if (nranks_ == 1) { if (local_rc) return local_rc; error = "IAI engine stalled"; return IAI_E_STALL; }
+                rc = exchange_step(local_rc);
+                if (rc) return rc;
+                continue;
+            }
             rounds++;
             cur_.clear_inputs();
             std::swap(cur_, next_);           // cur_ = inputs queued so far, next_ = empty
             std::vector<Item> segs, tasks;
             segs.swap(q_seg_); tasks.swap(q_task_);
-            if (segs.empty() && tasks.empty()) { error = "IAI engine stalled"; return IAI_E_STALL; }
             rc = be_.run_round(cur_);
-            if (rc) return rc;
+            if (rc) { if (nranks_ == 1) return rc; local_rc = rc; continue; }
             numevals += 15 * (int64_t)segs.size();
-            for (size_t i = 0; i < segs.size(); i++) {
+            for (size_t i = 0; i < segs.size() && !rc; i++) {
                 cplx D = cur_.seg_D[i];
                 double E = std::hypot(D.re, D.im);
                 rc = segment_done(segs[i].q, segs[i].pend, cur_.seg_I[i], E);
-                if (rc) return rc;
             }
-            for (size_t i = 0; i < tasks.size(); i++) {
+            for (size_t i = 0; i < tasks.size() && !rc; i++) {
                 numevals += cur_.task_ne[i];
                 double E = cur_.task_E[i];
-                if (!std::isfinite(E)) return nan_error(pends_[tasks[i].pend]);
-                rc = child_done(tasks[i].q, tasks[i].pend, tasks[i].i, tasks[i].slot, cur_.task_I[i]);
-                if (rc) return rc;
+                if (!std::isfinite(E)) rc = nan_error(pends_[tasks[i].pend]);
+                else rc = child_done(tasks[i].q, tasks[i].pend, tasks[i].i, tasks[i].slot, cur_.task_I[i]);
             }
+            if (rc) { if (nranks_ == 1) return rc; local_rc = rc; }
+        }
+        if (nranks_ > 1) {   // total evaluation count over the ranks (EvalCounter semantics of the whole solve)
+            double ne = (double)numevals;
+            rc = be_.exchange(&ne, 1);
+            if (rc) return rc;
+            numevals = (int64_t)ne;
         }
         return IAI_OK;
     }
 
 private:
-    struct Pend { double a, b; cplx vals[15]; int remaining, tag; };
+    struct Pend { double a, b; cplx vals[15]; int remaining, tag; bool shared; };
     struct Integral {
         int level; Limits lims; double atol; int64_t slot; int pq, ppend, pi;   // parent integral / panel / node
         std::vector<Seg> heap; cplx I; double E; int64_t numevals; Seg popped, s1, s2; bool has1, has2;
@@ -262,6 +281,8 @@ private:
 
     Backend& be_;
     int ndim_; Limits lims_; double atol_, rtol_; int64_t maxevals_; bool leaf_tasks_;
+    int rank_, nranks_; int64_t spawn_counter_ = 0;
+    std::vector<std::pair<int, int>> shared_pends_;    // outstanding (integral, panel) of the outermost integral, creation order
     std::deque<Integral> ints_; std::vector<int> free_int_;
     std::deque<Pend> pends_; std::vector<int> free_pend_;
     std::vector<int64_t> free2_, free1_;
@@ -283,7 +304,8 @@ private:
         if (!free_pend_.empty()) { id = free_pend_.back(); free_pend_.pop_back(); }
         else { id = (int)pends_.size(); pends_.emplace_back(); }
         Pend& p = pends_[id];
-        p.a = a; p.b = b; p.tag = tag; p.remaining = 15;
+        p.a = a; p.b = b; p.tag = tag; p.remaining = 15; p.shared = false;
+        for (int i = 0; i < 15; i++) p.vals[i] = cplx{0.0, 0.0};
         return id;
     }
     int alloc_slot(int level, int64_t* slot) {
@@ -307,7 +329,10 @@ private:
             next_.seg_a.push_back(a); next_.seg_b.push_back(b); next_.seg_slot.push_back(ints_[qi].slot);
             return IAI_OK;
         }
+        const bool shared = (nranks_ > 1 && level == ndim_ - 1);
+        if (shared) { pends_[pend].shared = true; shared_pends_.push_back({qi, pend}); }
         for (int i = 0; i < 15; i++) {
+            if (shared && (spawn_counter_++ % nranks_) != rank_) continue;   // another rank owns this node
             const double x = gk_node(a, b, i);
             const Limits clims = ints_[qi].lims.fix(x);
             double ca, cb;
@@ -337,10 +362,39 @@ private:
         free_slot(ints_[qi].level, slot);
         Pend& p = pends_[pend];
         p.vals[i] = v;
+        if (p.shared) return IAI_OK;           // combined in exchange_step once every rank has delivered its nodes
         if (--p.remaining > 0) return IAI_OK;
         cplx I, D;
         gk_combine(p.a, p.b, p.vals, &I, &D);
         return segment_done(qi, pend, I, std::hypot(D.re, D.im));
+    }
+
+    // all ranks: sum the outstanding outermost panels' node values (zeros for foreign nodes), then decide identically
+    int exchange_step(int local_rc) {
+        exchanges++;
+        std::vector<std::pair<int, int>> sp;
+        sp.swap(shared_pends_);
+        std::vector<double> buf(30 * sp.size() + 1, 0.0);
+        for (size_t k = 0; k < sp.size(); k++)
+            for (int i = 0; i < 15; i++) { buf[30 * k + 2 * i] = pends_[sp[k].second].vals[i].re; buf[30 * k + 2 * i + 1] = pends_[sp[k].second].vals[i].im; }
+        buf[30 * sp.size()] = local_rc ? 1.0 : 0.0;
+        int rc = be_.exchange(buf.data(), buf.size());
+        if (rc) return rc;
+        if (buf[30 * sp.size()] != 0.0) {
+            if (local_rc) return local_rc;
+            error = "IAI: another rank reported an error (singular matrix or NaN/Inf in the integrand)";
+            return IAI_E_NAN;
+        }
+        if (sp.empty()) { error = "IAI engine stalled"; return IAI_E_STALL; }
+        for (size_t k = 0; k < sp.size(); k++) {
+            Pend& p = pends_[sp[k].second];
+            for (int i = 0; i < 15; i++) p.vals[i] = cplx{buf[30 * k + 2 * i], buf[30 * k + 2 * i + 1]};
+            cplx I, D;
+            gk_combine(p.a, p.b, p.vals, &I, &D);
+            rc = segment_done(sp[k].first, sp[k].second, I, std::hypot(D.re, D.im));
+            if (rc) return rc;
+        }
+        return IAI_OK;
     }
 
     int finish(int qi) {

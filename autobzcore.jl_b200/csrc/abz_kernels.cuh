@@ -33,19 +33,25 @@ __global__ void phase_table_kernel(double2* __restrict__ ptab, int M, int lo, in
 // 216-263, executed level by level.)
 // Complex product as a real GEMM: A'[row,(m,c)] = {Re,Im} in, B'[(m,c),(j,c')] = [[Pr,Pi],[-Pi,Pr]].
 // CTA = 4 warps, tile 64 rows x 32 nodes, K = 2*M (padded to a multiple of 4) in shared memory.
+// Staging: the coefficient tile (M rows of 64 contiguous complex numbers) arrives by TMA bulk copies (cp.async.bulk,
+// one per m, completing on an mbarrier) issued by one thread; on full grids the phase tiles (M rows of 32 contiguous
+// table entries) are TMA bulk copies too, double-buffered so that tile t+1 is in flight while tile t feeds the DMMAs;
+// on symmetry-reduced grids (klist != NULL) the phase tile is a gather and is staged by the threads.
 // ptr[b0+b] .. ptr[b0+b+1] delimit the node list of batch b; klist == NULL means k_j = j.
+// shared: sA[Mp][64] | sP[2][Mp][32] | 3 mbarriers
 // ------------------------------------------------------------------------------------------------
 constexpr int ST_RT = 64;   // rows per CTA
 constexpr int ST_JT = 32;   // nodes per CTA iteration (8 per warp)
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 contract_stage_kernel(const double2* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ ptab,
                       const long* __restrict__ ptr, long b0, const int* __restrict__ klist, int N, int M, long rows,
                       long in_batch_stride) {
-    extern __shared__ double2 st_smem[];
+    extern __shared__ __align__(128) double2 st_smem[];
     const int Mp = (M + 1) & ~1;
-    double2* sA = st_smem;                // [Mp][ST_RT]
-    double2* sP = st_smem + Mp * ST_RT;   // [Mp][ST_JT]
+    double2* sA = st_smem;                      // [Mp][ST_RT]
+    double2* sP = st_smem + Mp * ST_RT;         // [2][Mp][ST_JT]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Mp * ST_JT);   // [0]: A tile, [1], [2]: phase tiles
     const long b = blockIdx.x;
     const long row0 = (long)blockIdx.y * ST_RT;
     const long koff = ptr[b0 + b];
@@ -53,62 +59,91 @@ contract_stage_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     const long obase = koff - ptr[b0];
     if (kcount <= 0) return;
     const double2* inb = in + b * in_batch_stride;
+    const int vrows = (int)min((long)ST_RT, rows - row0);
+    const int ntiles = (kcount + ST_JT - 1) / ST_JT;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        mbar_fence_init();
+    }
+    // zero the padding that the bulk copies never touch: rows m >= M, columns beyond a partial row tile
     for (int idx = threadIdx.x; idx < Mp * ST_RT; idx += 128) {
         int m = idx / ST_RT, r = idx % ST_RT;
-        long row = row0 + r;
-        sA[idx] = (m < M && row < rows) ? inb[(long)m * rows + row] : make_double2(0.0, 0.0);
+        if (m >= M || r >= vrows) sA[idx] = make_double2(0.0, 0.0);
+    }
+    for (int idx = threadIdx.x; idx < 2 * Mp * ST_JT; idx += 128) sP[idx] = make_double2(0.0, 0.0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // order these generic-proxy writes before the bulk copies
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bars[0], (uint32_t)(M * vrows * sizeof(double2)));
+        for (int m = 0; m < M; m++) bulk_g2s(sA + m * ST_RT, inb + (long)m * rows + row0, (uint32_t)(vrows * sizeof(double2)), &bars[0]);
+        if (!klist) {
+            const int vj = min(ST_JT, kcount);
+            mbar_expect_tx(&bars[1], (uint32_t)(M * vj * sizeof(double2)));
+            for (int m = 0; m < M; m++) bulk_g2s(sP + m * ST_JT, ptab + (long)m * N, (uint32_t)(vj * sizeof(double2)), &bars[1]);
+        }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     const int c = q & 1;
-    for (int j0 = 0; j0 < kcount; j0 += ST_JT) {
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < Mp * ST_JT; idx += 128) {
-            int m = idx / ST_JT, jj = idx % ST_JT;
-            int j = j0 + jj;
-            double2 p = make_double2(0.0, 0.0);
-            if (m < M && j < kcount) {
-                int k = klist ? klist[koff + j] : j;
-                p = ptab[(long)m * N + k];
+    for (int t = 0; t < ntiles; t++) {
+        const int j0 = t * ST_JT;
+        double2* sPt = sP + (t & 1) * Mp * ST_JT;
+        if (klist) {
+            for (int idx = threadIdx.x; idx < M * ST_JT; idx += 128) {
+                int m = idx / ST_JT, jj = idx % ST_JT;
+                int j = j0 + jj;
+                sPt[idx] = (j < kcount) ? ptab[(long)m * N + klist[koff + j]] : make_double2(0.0, 0.0);
             }
-            sP[idx] = p;
+            __syncthreads();
+        } else {
+            if (threadIdx.x == 0 && t + 1 < ntiles) {      // prefetch the next phase tile into the other buffer
+                const int jn = j0 + ST_JT;
+                const int vj = min(ST_JT, kcount - jn);
+                uint64_t* bn = &bars[1 + ((t + 1) & 1)];
+                double2* sPn = sP + ((t + 1) & 1) * Mp * ST_JT;
+                mbar_expect_tx(bn, (uint32_t)(M * vj * sizeof(double2)));
+                for (int m = 0; m < M; m++) bulk_g2s(sPn + m * ST_JT, ptab + (long)m * N + jn, (uint32_t)(vj * sizeof(double2)), bn);
+            }
+            mbar_wait(&bars[1 + (t & 1)], (uint32_t)((t >> 1) & 1));
         }
-        __syncthreads();
+        if (t == 0) mbar_wait(&bars[0], 0);
         const int jw = warp * 8;
-        if (j0 + jw >= kcount) continue;
-        double acc[8][2][2];
+        if (j0 + jw < kcount) {
+            double acc[8][2][2];
 #pragma unroll
-        for (int mf = 0; mf < 8; mf++)
+            for (int mf = 0; mf < 8; mf++)
 #pragma unroll
-            for (int nf = 0; nf < 2; nf++) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
-        for (int ks = 0; ks < Mp / 2; ks++) {
-            const int m = 2 * ks + (q >> 1);
-            double bf[2];
+                for (int nf = 0; nf < 2; nf++) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+            for (int ks = 0; ks < Mp / 2; ks++) {
+                const int m = 2 * ks + (q >> 1);
+                double bf[2];
+#pragma unroll
+                for (int nf = 0; nf < 2; nf++) {
+                    double2 p = sPt[m * ST_JT + jw + 4 * nf + (g >> 1)];
+                    const int cp = g & 1;
+                    bf[nf] = (c == cp) ? p.x : (c == 0 ? p.y : -p.y);
+                }
+#pragma unroll
+                for (int mf = 0; mf < 8; mf++) {
+                    const double* a = reinterpret_cast<const double*>(&sA[m * ST_RT + mf * 8 + g]);
+                    double af = a[c];
+                    dmma884(acc[mf][0][0], acc[mf][0][1], af, bf[0]);
+                    dmma884(acc[mf][1][0], acc[mf][1][1], af, bf[1]);
+                }
+            }
 #pragma unroll
             for (int nf = 0; nf < 2; nf++) {
-                double2 p = sP[m * ST_JT + jw + 4 * nf + (g >> 1)];
-                const int cp = g & 1;
-                bf[nf] = (c == cp) ? p.x : (c == 0 ? p.y : -p.y);
-            }
+                int j = j0 + jw + 4 * nf + q;
+                if (j >= kcount) continue;
+                double2* o = out + (obase + j) * rows;
 #pragma unroll
-            for (int mf = 0; mf < 8; mf++) {
-                const double* a = reinterpret_cast<const double*>(&sA[m * ST_RT + mf * 8 + g]);
-                double af = a[c];
-                dmma884(acc[mf][0][0], acc[mf][0][1], af, bf[0]);
-                dmma884(acc[mf][1][0], acc[mf][1][1], af, bf[1]);
+                for (int mf = 0; mf < 8; mf++) {
+                    long row = row0 + mf * 8 + g;
+                    if (row < rows) o[row] = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+                }
             }
         }
-#pragma unroll
-        for (int nf = 0; nf < 2; nf++) {
-            int j = j0 + jw + 4 * nf + q;
-            if (j >= kcount) continue;
-            double2* o = out + (obase + j) * rows;
-#pragma unroll
-            for (int mf = 0; mf < 8; mf++) {
-                long row = row0 + mf * 8 + g;
-                if (row < rows) o[row] = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
-            }
-        }
+        __syncthreads();      // everyone is done with sPt before it is refilled (tile t+2)
     }
 }
 

@@ -327,7 +327,9 @@ def _do_solve(cache, ps):
                     raise ValueError("TetrahedralLimits must start at s = 1")
                 lin = bound if vkind == 2 else None
                 Iv, Ev, ne, rounds, launches = nest.iai_solve(lkind, la, lb, b1.fkind, vkind, z, sigma, lin, atol_, rtol_, maxiters,
-                                                              device_leaves=getattr(cache.backend, "iai_device_leaves", True))
+                                                              device_leaves=getattr(cache.backend, "iai_device_leaves", True),
+                                                              rank=shard.rank, nranks=shard.nranks,
+                                                              allreduce=shard.allreduce if shard.nranks > 1 else None)
                 cache.cacheval["iai_rounds"] = rounds
                 Iv = Iv if dtype == np.complex128 else Iv.real
             else:

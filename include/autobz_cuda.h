@@ -156,11 +156,24 @@ int32_t abz_nest_eval_h(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const doubl
  *   fkind = ABZ_F_*;  vkind 0: value = y;  1: -Im(y)/pi (aps_example.jl:30);  2: lin[0:2]*y + lin[2:4] (complex a, b)
  *   atol, rtol, maxevals apply to the outermost integral exactly as abstol/reltol/maxiters of the reference.
  *   flags: ABZ_IAI_DEVICE_LEAVES = run each innermost 1-D adaptive integral entirely on the device (norb <= 3)
- *   out = {Re I, Im I, E};  stats = {numevals (EvalCounter semantics), device rounds, kernel launches} or NULL */
+ *   out = {Re I, Im I, E};  stats = Int64[4] {numevals (EvalCounter semantics), device rounds, kernel launches,
+ *   exchanges} or NULL */
 #define ABZ_IAI_DEVICE_LEAVES 1
 int32_t abz_iai_solve(abz_ctx* ctx, abz_nest_t nest, int32_t lkind, const double* la, const double* lb, int32_t fkind,
                       int32_t vkind, const double* z, const double* sigma, const double* lin, double atol, double rtol,
                       int64_t maxevals, int32_t flags, double* out, int64_t* stats);
+
+/* Multi-GPU IAI: the 15 nodes of every panel of the OUTERMOST integral are dealt round-robin to the
+ * ranks; each rank integrates its own nodes and all ranks meet in one small sum-allreduce per outer refinement step,
+ * then take the identical accept/refine decision (bit-identical result to the single-rank solve; stats[0] = evaluations
+ * of all ranks).  The allreduce is `exchange` (in-place sum of n doubles over the ranks, return 0 on success; e.g. a
+ * @cfunction around MPI.Allreduce!) or, when NULL, NCCL on the communicator of abz_comm_init.  Collective: every rank
+ * must call it with the same arguments. */
+typedef int32_t (*abz_exchange_fn)(double* buf, int64_t n, void* user);
+int32_t abz_iai_solve_sharded(abz_ctx* ctx, abz_nest_t nest, int32_t lkind, const double* la, const double* lb, int32_t fkind,
+                              int32_t vkind, const double* z, const double* sigma, const double* lin, double atol, double rtol,
+                              int64_t maxevals, int32_t flags, int32_t rank, int32_t nranks, abz_exchange_fn exchange,
+                              void* exchange_user, double* out, int64_t* stats);
 
 /* ---- multi-GPU: one small allreduce of partial sums ----------------------- */
 /* NCCL is dlopen'ed at first use (libnccl.so.2).  uid = 128-byte ncclUniqueId from rank 0. */

@@ -21,6 +21,8 @@ struct CpuBackend {
     int fkind, vkind; double z[2]; const double* sigma; cplx la, lb; double rtol; int64_t maxevals;
     std::map<int64_t, std::vector<double>> L2, L1;
     long launches = 0;
+    int (*xfn)(double*, long, void*) = nullptr;
+    int exchange(double* buf, size_t n) { return xfn ? xfn(buf, (long)n, nullptr) : -6; }
 
     cplx point(const std::vector<double>* c1, double x) {
         const long nn = (long)n * n;
@@ -95,18 +97,18 @@ struct CpuBackend {
 extern "C" int iai_cpu_solve(const double* coeffs, int n, int ndim, const int* M, const int* lo, const double* period, int lkind,
                              const double* la, const double* lb, int fkind, int vkind, const double* z, const double* sigma,
                              const double* lin, double atol, double rtol, long maxevals, int leaf_tasks, long cap2, long cap1,
-                             double* out, long* stats) {
+                             int rank, int nranks, int (*xfn)(double*, long, void*), double* out, long* stats) {
     CpuBackend be;
     be.coeffs = coeffs; be.n = n; be.ndim = ndim;
     for (int d = 0; d < 3; d++) { be.M[d] = d < ndim ? M[d] : 1; be.lo[d] = d < ndim ? lo[d] : 0; be.period[d] = d < ndim ? period[d] : 1.0; }
     be.fkind = fkind; be.vkind = vkind; be.z[0] = z ? z[0] : 0; be.z[1] = z ? z[1] : 0; be.sigma = sigma;
     be.la = cplx{lin ? lin[0] : 1.0, lin ? lin[1] : 0.0}; be.lb = cplx{lin ? lin[2] : 0.0, lin ? lin[3] : 0.0};
-    be.rtol = rtol; be.maxevals = maxevals;
+    be.rtol = rtol; be.maxevals = maxevals; be.xfn = xfn;
     Limits lims; lims.kind = lkind; lims.nd = ndim; lims.s = 1.0;
     for (int d = 0; d < ndim; d++) { lims.a[d] = la[d]; lims.b[d] = lb ? lb[d] : 0.0; }
-    Engine<CpuBackend> eng(be, ndim, lims, atol, rtol, maxevals, cap2, cap1, leaf_tasks != 0);
+    Engine<CpuBackend> eng(be, ndim, lims, atol, rtol, maxevals, cap2, cap1, leaf_tasks != 0, rank, nranks);
     int rc = eng.run();
-    stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = be.launches;
+    stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = be.launches; stats[3] = eng.exchanges;
     if (rc) return rc;
     out[0] = eng.result.re; out[1] = eng.result.im; out[2] = eng.result_err;
     return 0;

@@ -21,7 +21,11 @@ def eng(orc):
     return lib
 
 
-def _solve(lib, S, ndim, lkind, la, lb, fkind, vkind, z, lin, atol, rtol, leaf, maxevals=2 ** 62, cap2=64, cap1=2048):
+XFN = C.CFUNCTYPE(C.c_int, c_dp, C.c_long, C.c_void_p)
+
+
+def _solve(lib, S, ndim, lkind, la, lb, fkind, vkind, z, lin, atol, rtol, leaf, maxevals=2 ** 62, cap2=64, cap1=2048, rank=0, nranks=1,
+           xfn=None):
     i3 = lambda v: (C.c_int * 3)(*[int(x) for x in v])
     d3 = lambda v: (C.c_double * 3)(*[float(x) for x in v])
     la_ = np.ascontiguousarray(la, dtype=np.float64)
@@ -29,11 +33,12 @@ def _solve(lib, S, ndim, lkind, la, lb, fkind, vkind, z, lin, atol, rtol, leaf, 
     zz = np.array([z.real, z.imag])
     ln = None if lin is None else np.ascontiguousarray(lin, dtype=np.float64)
     out = np.zeros(3)
-    st = (C.c_long * 3)()
+    st = (C.c_long * 4)()
     dp = lambda a: None if a is None else a.ctypes.data_as(c_dp)
     rc = lib.iai_cpu_solve(dp(S.c), C.c_int(S.n), C.c_int(ndim), i3(S.M), i3(S.lo), d3(S.period), C.c_int(lkind), dp(la_), dp(lb_),
                            C.c_int(fkind), C.c_int(vkind), dp(zz), None, dp(ln), C.c_double(atol), C.c_double(rtol),
-                           C.c_long(maxevals), C.c_int(int(leaf)), C.c_long(cap2), C.c_long(cap1), dp(out), st)
+                           C.c_long(maxevals), C.c_int(int(leaf)), C.c_long(cap2), C.c_long(cap1), C.c_int(rank), C.c_int(nranks),
+                           xfn if xfn is not None else XFN(0), dp(out), st)
     return rc, complex(out[0], out[1]), out[2], int(st[0]), int(st[1])
 
 
@@ -97,3 +102,62 @@ def test_engine_arena_exhaustion_is_an_error(orc, eng, svo):
     S = orc.Series(H, lo)
     rc, *_ = _solve(eng, S, 3, 1, [0.5] * 3, None, 0, 1, complex(12.5, 0.05), None, 1e-3, 0.0, False, cap2=8, cap1=2048)
     assert rc == -2
+
+
+_GLOO_IAI = r'''
+import ctypes as C, os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle")); sys.path.insert(0, os.path.join({root!r}, "tests"))
+sys.path.insert(0, os.path.join({root!r}, "tests", "native"))
+import numpy as np, torch, torch.distributed as dist
+import orc, build
+from test_iai_engine_native import _solve, XFN
+nranks = {nranks}
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=nranks)
+rank = dist.get_rank()
+lib = C.CDLL(build.build())
+calls = [0]
+def allreduce(buf, n, user):
+    a = np.ctypeslib.as_array(buf, shape=(n,))
+    t = torch.from_numpy(a.copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    a[:] = t.numpy()
+    calls[0] += 1
+    return 0
+xfn = XFN(allreduce)
+d = np.load(os.path.join({root!r}, "tests", "golden", "svo_hr.npz"))
+S = orc.Series(np.asfortranarray(d["H_R"]), tuple(int(x) for x in d["lo"]))
+ok = True
+for leaf in (False, True):
+    for (lk, la, lb, atol) in ((1, [0.5] * 3, None, 1e-3), (0, [0.0] * 3, [1.0] * 3, 3e-2)):
+        z = complex(12.5, 0.05)
+        rc1, I1, E1, ne1, r1 = _solve(lib, S, 3, lk, la, lb, 0, 1, z, None, atol, 0.0, leaf)
+        rc2, I2, E2, ne2, r2 = _solve(lib, S, 3, lk, la, lb, 0, 1, z, None, atol, 0.0, leaf, rank=rank, nranks=nranks, xfn=xfn)
+        good = rc1 == 0 and rc2 == 0 and I1 == I2 and E1 == E2 and ne1 == ne2     # bit-identical, evaluations of all ranks
+        ok = ok and good
+        print("RANK", rank, "leaf", leaf, "lims", lk, "OK" if good else "FAIL", I1, I2, ne1, ne2, "rounds", r1, r2, flush=True)
+# a pole on one rank's share surfaces as an error on every rank (no hang)
+c = np.zeros((1, 1, 3, 3, 1), dtype=complex); c[0, 0, 1, 1, 0] = 1.0
+S1 = orc.Series(c, (-1, -1, 0))
+rc, *_ = _solve(lib, S1, 2, 0, [0.0] * 2, [1.0] * 2, 0, 0, complex(1.0, 0.0), None, 1e-3, 0.0, False, rank=rank, nranks=nranks, xfn=xfn)
+ok = ok and rc == -4
+print("RANK", rank, "error rc", rc, "allreduce calls", calls[0], flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+'''
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_engine_sharded_over_ranks_gloo(tmp_path, orc, eng, nranks):
+    """world_size 2 and 3 over gloo: the outermost panels' nodes are dealt round-robin to the ranks, one small allreduce per
+    outer refinement step; integral, error estimate and total evaluation count are bit-identical to the single-rank solve,
+    and an integrand error on one rank stops every rank."""
+    import socket
+    import subprocess
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "gloo_iai.py"
+    script.write_text(_GLOO_IAI.format(root=root, port=port, nranks=nranks))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(nranks)]
+    outs = [p.communicate(timeout=600)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

@@ -44,9 +44,12 @@ if "c2" in which:
         solver = ab.IntegralSolver(f, dom, ab.PTR(npt=npt))
         ws = [{"omega": w} for w in np.linspace(11.0, 14.0, 64)]
         ab.batchsolve(solver, ws[:4])
-        t = time.perf_counter(); g = ab.batchsolve(solver, ws); dt = time.perf_counter() - t
+        dt, dev = 1e9, None
+        for _ in range(4):       # best of 4: a single 1-5 ms kernel right after host-side set-up otherwise sees the idle clocks
+            t = time.perf_counter(); g = ab.batchsolve(solver, ws); d1 = time.perf_counter() - t
+            if d1 < dt: dt, dev = d1, ctx.last_timings()
         nn = len(solver.cache.cacheval["rule"])
-        emit(config=f"C2 SrVO3 PTR npt={npt} {name} 64 freqs", nodes=nn, ms=1e3 * dt, kpoints_per_s=nn / dt, k_omega_per_s=nn * 64 / dt, device_ms=ctx.last_timings())
+        emit(config=f"C2 SrVO3 PTR npt={npt} {name} 64 freqs (best of 4)", nodes=nn, ms=1e3 * dt, kpoints_per_s=nn / dt, k_omega_per_s=nn * 64 / dt, device_ms=dev)
     # AutoPTR eta=1e-2, reference-style schedule a = eta
     for w in (11.0, 12.5):
         alg = ab.EvalCounter(ab.AutoPTR(a=1e-2, nmin=50, nmax=1000))
@@ -84,9 +87,11 @@ if "c5" in which:
     for npt in (48, 96, 144):
         cache = ab.init(ab.IntegralProblem(f, ibz), ab.PTR(npt=npt))
         ab.solve_(cache)
-        t = time.perf_counter(); sol = ab.solve_(cache); dt = time.perf_counter() - t
+        dt = 1e9
+        for _ in range(3):
+            t = time.perf_counter(); sol = ab.solve_(cache); d1 = time.perf_counter() - t
+            if d1 < dt: dt, (ev, mf) = d1, ctx.last_timings()
         nn = len(cache.cacheval["rule"])
-        ev, mf = ctx.last_timings()
         emit(config=f"C5 norb=64 band energy CubicSymIBZ PTR npt={npt}", u=sol.u, nodes=nn, ms=1e3 * dt, kpoints_per_s=nn / dt, eval_ms=ev, eig_ms=mf,
              eig_tflops_credited=(32 / 3) * n ** 3 * nn / (mf * 1e-3) * 1e-12 if mf else None)
     t = time.perf_counter(); sol = ab.solve(ab.IntegralProblem(f, ibz), ab.EvalCounter(ab.AutoPTR(a=1.0, nmin=48, dn=48.0)), reltol=1e-6); dt = time.perf_counter() - t
