@@ -10,6 +10,7 @@ from .algorithms import (IAI, PTR, AutoPTR, AutoSymPTRJL, AuxQuadGKJL, EvalCount
 from .backend import DeviceBackend, default_context  # noqa: F401
 from .bz import (FBZ, CubicLimits, CubicSymIBZ, InversionSymIBZ, SymmetricBZ, TetrahedralLimits,  # noqa: F401
                  cube_automorphisms, load_bz, nsyms)
+from .dos import GGR, DOSCache, DOSProblem, DOSSolution  # noqa: F401
 from .fourier import (AffineTraceIntegrand, BatchIntegrand, DOSIntegrand, EigenIntegrand, FourierIntegrand, FourierSeries,  # noqa: F401
                       FourierValue, TrGlocIntegrand, dos_integrand, gloc_trace_integrand)
 from .interfaces import (Basis, IntegralProblem, IntegralSolution, IntegralSolver, Shard, batchsolve, init,  # noqa: F401

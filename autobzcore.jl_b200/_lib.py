@@ -23,7 +23,7 @@ EXPORTS = [
     "abz_version", "abz_last_error", "abz_ctx_create", "abz_ctx_destroy", "abz_ctx_set_option", "abz_ctx_launch_count",
     "abz_ctx_last_timings", "abz_series_create", "abz_series_destroy", "abz_rule_create_full", "abz_rule_create_sym", "abz_rule_create_nodes",
     "abz_symptr_rule", "abz_rule_create_symptr", "abz_rule_destroy", "abz_rule_info", "abz_rule_materialize", "abz_rule_copy_out",
-    "abz_rule_resolvent_sum", "abz_rule_eig_sum", "abz_rule_eigvals", "abz_points_eval", "abz_points_resolvent",
+    "abz_rule_resolvent_sum", "abz_rule_eig_sum", "abz_rule_eigvals", "abz_rule_ggr_data", "abz_rule_ggr_sum", "abz_points_eval", "abz_points_resolvent",
     "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval", "abz_nest_eval_h", "abz_iai_solve", "abz_iai_solve_sharded",
     "abz_comm_unique_id", "abz_comm_init", "abz_allreduce_sum", "abz_comm_destroy",
 ]
@@ -79,6 +79,8 @@ def load():
     lib.abz_rule_resolvent_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, c_dp, c_dp, C.c_double, c_dp]
     lib.abz_rule_eig_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, C.c_double, c_dp]
     lib.abz_rule_eigvals.argtypes = [C.c_void_p, C.c_uint64, c_dp]
+    lib.abz_rule_ggr_data.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp]
+    lib.abz_rule_ggr_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, C.c_double, c_dp]
     lib.abz_points_eval.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_dp]
     lib.abz_points_resolvent.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, C.c_int32, C.c_int32, c_dp, c_dp, c_dp]
     lib.abz_nest_create.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]
@@ -311,6 +313,26 @@ class DeviceRule:
         ev = np.empty((self.nnodes, self.series.n))
         self.ctx.check(self.ctx.lib.abz_rule_eigvals(self.ctx.h, self.h, _dp(ev)))
         return ev
+
+
+def _ggr_data(self, ndim, copy=True):
+    """get_ggr_data on the device: (energies [nnodes, n] ascending, velocities [nnodes, ndim, n]); cached in the rule"""
+    n = self.series.n
+    e = np.empty((self.nnodes, n)) if copy else None
+    v = np.empty((self.nnodes, ndim, n)) if copy else None
+    self.ctx.check(self.ctx.lib.abz_rule_ggr_data(self.ctx.h, self.h, int(ndim), _dp(e), _dp(v)))
+    return e, v
+
+
+def _ggr_sum(self, E, scale=1.0):
+    Ev = np.ascontiguousarray(np.atleast_1d(np.asarray(E, dtype=np.float64)))
+    out = np.empty(Ev.size)
+    self.ctx.check(self.ctx.lib.abz_rule_ggr_sum(self.ctx.h, self.h, Ev.size, _dp(Ev), float(scale), _dp(out)))
+    return out
+
+
+DeviceRule.ggr_data = _ggr_data
+DeviceRule.ggr_sum = _ggr_sum
 
 
 class DeviceNest:

@@ -106,6 +106,14 @@ class DeviceRule:
     def copy_out(self):
         return self.dev.copy_out()
 
+    def ggr_data(self, ndim, copy=True):
+        """get_ggr_data (src/dos_ggr.jl:14-44) on the local nodes: (energies, velocities), cached on the device"""
+        return self.dev.ggr_data(ndim, copy=copy)
+
+    def ggr_sum(self, E):
+        """sum_ggr (src/dos_ggr.jl:58-65) over the local nodes for every energy in E"""
+        return self.dev.ggr_sum(E)
+
     def close(self):
         self.dev.close()
 

@@ -64,7 +64,9 @@ struct Rule {
     int* d_node_k1 = nullptr; double* d_node_w = nullptr;
     double2* d_ptab[3] = {nullptr, nullptr, nullptr};
     double2* d_H = nullptr;   // materialised H(k) [nnz][n*n]
+    double* d_ggr_e = nullptr; double* d_ggr_v = nullptr; int ggr_ndim = 0;   // GGR data pass: energies [nnz][n], velocities [nnz][ndim][n]
     ~Rule() {
+        cudaFree(d_ggr_e); cudaFree(d_ggr_v);
         cudaFree(d_plane_k3); cudaFree(d_plane_rowptr); cudaFree(d_row_k2); cudaFree(d_row_nodeptr);
         cudaFree(d_node_k1); cudaFree(d_node_w); cudaFree(d_H);
         for (auto& p : d_ptab) cudaFree(p);
@@ -238,8 +240,9 @@ int launch_stage(abz_ctx* ctx, const double2* in, double2* out, const double2* p
 }
 
 // evaluate stages for a chunk.  upto = 1: stop after stage 2 (C1 rows; fused small path); 0: also H
-int eval_chunk(abz_ctx* ctx, Rule* r, const Chunk& ch, bool need_h, double2* Hdst) {
+int eval_chunk(abz_ctx* ctx, Rule* r, const Chunk& ch, bool need_h, double2* Hdst, const double2* coeffs = nullptr) {
     Series* s = r->s;
+    if (!coeffs) coeffs = s->c;
     const long nn = (long)s->n * s->n;
     const long rows2 = nn * s->M[0] * s->M[1], rows1 = nn * s->M[0];
     const long nplanes = ch.p1 - ch.p0, nrows = ch.r1 - ch.r0;
@@ -249,7 +252,7 @@ int eval_chunk(abz_ctx* ctx, Rule* r, const Chunk& ch, bool need_h, double2* Hds
     long h_ptr3[2] = {ch.p0, ch.p1};
     CU(ctx, ctx->tmp_d.reserve(4 * sizeof(long)));
     CU(ctx, cudaMemcpyAsync(ctx->tmp_d.p, h_ptr3, sizeof(h_ptr3), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = launch_stage(ctx, s->c, ctx->C2.as<double2>(), r->d_ptab[2], ctx->tmp_d.as<long>(), 0, 1, r->d_plane_k3, r->N,
+    int rc = launch_stage(ctx, coeffs, ctx->C2.as<double2>(), r->d_ptab[2], ctx->tmp_d.as<long>(), 0, 1, r->d_plane_k3, r->N,
                           s->M[2], rows2, 0);
     if (rc) return rc;
     // stage 2
@@ -1061,6 +1064,94 @@ int32_t abz_rule_eigvals(abz_ctx* ctx, abz_rule_t rid, double* evals) {
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return check_errflag(ctx, "abz_rule_eigvals");
+}
+
+// ---- GGR data pass and sum (src/dos_ggr.jl) ----------------------------------------------------------------------
+int32_t abz_rule_ggr_data(abz_ctx* ctx, abz_rule_t rid, int32_t ndim, double* energies, double* velocities) {
+    if (!ctx) return ABZ_E_INVALID;
+    Rule* r = get_rule(ctx, rid);
+    if (!r) return fail(ctx, ABZ_E_INVALID, "unknown rule handle");
+    Series* s = r->s;
+    if (ndim < 1 || ndim > 3) return fail(ctx, ABZ_E_INVALID, "GGR implemented for up to 3d BZ");
+    for (int d = ndim; d < 3; d++)
+        if (s->M[d] != 1) return fail(ctx, ABZ_E_INVALID, "variables in Fourier series don't match domain");
+    cudaSetDevice(ctx->device);
+    const int n = s->n;
+    const long nn = (long)n * n;
+    if (n > 64) return fail(ctx, ABZ_E_UNSUPPORTED, "norb > 64 is not supported by the GGR data pass");
+    if (r->nnz > 0 && (!r->d_ggr_e || r->ggr_ndim != ndim)) {
+        cudaFree(r->d_ggr_e); cudaFree(r->d_ggr_v); r->d_ggr_e = r->d_ggr_v = nullptr;
+        CU(ctx, cudaMalloc((void**)&r->d_ggr_e, (size_t)r->nnz * n * sizeof(double)));
+        CU(ctx, cudaMalloc((void**)&r->d_ggr_v, (size_t)r->nnz * n * ndim * sizeof(double)));
+        // JacobianSeries coefficients: 2 pi i R_d / period_d * H_R
+        const size_t ctot = (size_t)nn * s->M[0] * s->M[1] * s->M[2];
+        DevBuf dco[3], Vc[3];
+        for (int d = 0; d < ndim; d++) {
+            CU(ctx, dco[d].reserve(ctot * sizeof(double2)));
+            jacobian_coeff_kernel<<<(unsigned)((ctot + 255) / 256), 256, 0, ctx->stream>>>(s->c, dco[d].as<double2>(), nn, s->M[0], s->M[1],
+                                                                                          s->M[2], s->lo[d], d, s->period[d]);
+            LAUNCH_CHECK(ctx, "jacobian_coeff_kernel");
+        }
+        const int np = (n + 1) & ~1, npair = np / 2;
+        const int threads = std::min(256, std::max(64, ((n * ((n + 1) / 2) + 31) / 32) * 32));
+        const size_t smem = ((size_t)n * (n + 1) + (size_t)n * n + npair) * 16 + (size_t)(npair + 3 * n + 2 * (threads / 32) + 2) * 8 +
+                            (size_t)2 * npair * 4 + 64;
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(eig_jacobi_vel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
+        long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
+        const size_t share = ctx->budget / 4;
+        auto chunks = plan_chunks(r, (long)std::max<size_t>(1, share / (nn * sizeof(double2))), (long)(ctx->budget / (rows1 * sizeof(double2))),
+                                  (long)(ctx->budget / (rows2 * sizeof(double2))));
+        cudaEvent_t e0 = next_event(ctx);
+        for (auto& ch : chunks) {
+            const long n0 = r->h_row_nodeptr[ch.r0], n1 = r->h_row_nodeptr[ch.r1], nk = n1 - n0;
+            if (nk <= 0) continue;
+            CU(ctx, ctx->Hc.reserve((size_t)nk * nn * sizeof(double2)));
+            int rc = eval_chunk(ctx, r, ch, true, ctx->Hc.as<double2>());
+            if (rc) return rc;
+            for (int d = 0; d < ndim; d++) {
+                CU(ctx, Vc[d].reserve((size_t)nk * nn * sizeof(double2)));
+                rc = eval_chunk(ctx, r, ch, true, Vc[d].as<double2>(), dco[d].as<double2>());
+                if (rc) return rc;
+            }
+            const long ncta = std::min<long>(nk, (long)ctx->sm_count * per_sm);
+            eig_jacobi_vel_kernel<<<(unsigned)ncta, threads, smem, ctx->stream>>>(
+                ctx->Hc.as<double2>(), Vc[0].as<double2>(), Vc[1].as<double2>(), Vc[2].as<double2>(), nk, n, ndim, s->period[0], s->period[1],
+                s->period[2], r->d_ggr_e + n0 * n, r->d_ggr_v + n0 * n * ndim, ctx->errflag.as<int>());
+            LAUNCH_CHECK(ctx, "eig_jacobi_vel_kernel");
+        }
+        cudaEvent_t e1 = next_event(ctx);
+        int rc = check_errflag(ctx, "abz_rule_ggr_data");
+        collect_timings(ctx, {}, {{e0, e1}});
+        if (rc) { cudaFree(r->d_ggr_e); cudaFree(r->d_ggr_v); r->d_ggr_e = r->d_ggr_v = nullptr; return rc; }
+        r->ggr_ndim = ndim;
+    }
+    if (energies && r->nnz > 0)
+        CU(ctx, cudaMemcpyAsync(energies, r->d_ggr_e, (size_t)r->nnz * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (velocities && r->nnz > 0)
+        CU(ctx, cudaMemcpyAsync(velocities, r->d_ggr_v, (size_t)r->nnz * n * ndim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABZ_OK;
+}
+
+int32_t abz_rule_ggr_sum(abz_ctx* ctx, abz_rule_t rid, int32_t nE, const double* E, double scale, double* out) {
+    if (!ctx) return ABZ_E_INVALID;
+    Rule* r = get_rule(ctx, rid);
+    if (!r) return fail(ctx, ABZ_E_INVALID, "unknown rule handle");
+    if (nE < 1 || !E || !out) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    if (r->nnz > 0 && !r->d_ggr_e) return fail(ctx, ABZ_E_INVALID, "abz_rule_ggr_sum: call abz_rule_ggr_data first");
+    cudaSetDevice(ctx->device);
+    if (r->nnz == 0) { for (int i = 0; i < nE; i++) out[i] = 0.0; return ABZ_OK; }
+    CU(ctx, ctx->tmp_a.reserve((size_t)nE * sizeof(double)));
+    CU(ctx, ctx->tmp_c.reserve((size_t)nE * sizeof(double)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_a.p, E, (size_t)nE * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ggr_sum_kernel<<<(unsigned)nE, 256, 0, ctx->stream>>>(r->d_ggr_e, r->d_ggr_v, r->d_node_w, r->nnz, r->s->n, r->ggr_ndim, 1.0 / (2.0 * r->N),
+                                                         ctx->tmp_a.as<double>(), scale, ctx->tmp_c.as<double>());
+    LAUNCH_CHECK(ctx, "ggr_sum_kernel");
+    CU(ctx, cudaMemcpyAsync(out, ctx->tmp_c.p, (size_t)nE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABZ_OK;
 }
 
 // ---- scattered points ---------------------------------------------------------------------------

@@ -150,6 +150,210 @@ __global__ void eig_jacobi_kernel(const double2* __restrict__ H, const double* _
     if (mode == 0 && tid == 0) partial[blockIdx.x] = my_acc;
 }
 
+// ---- GGR data pass (src/dos_ggr.jl:14-44): band energies AND band velocities at every node -----------------------
+// e, U = eigen(Hermitian(h)); v_d = real(diag(U' V_d U)) * period_d, with V_d = dH/dk_d evaluated by the same
+// contraction pipeline on the JacobianSeries coefficients.  One CTA per node: two-sided cyclic Jacobi as in
+// eig_jacobi_kernel with the rotations accumulated into U (shared memory), then u_j^H V_d u_j for every band with a
+// fixed-order (bit-reproducible) reduction.  Outputs ascending in energy: eout[k*n + r], vout[(k*ndim + d)*n + r].
+// shared: A[n*(n+1)] | U[n*n] | rs[np/2] double2 | rc[np/2] | d[n] | vel[2*n] | red[...] | pq[np] int
+__global__ void eig_jacobi_vel_kernel(const double2* __restrict__ H, const double2* __restrict__ V0, const double2* __restrict__ V1,
+                                      const double2* __restrict__ V2, long nk, int n, int ndim, double t0, double t1, double t2,
+                                      double* __restrict__ eout, double* __restrict__ vout, int* __restrict__ errflag) {
+    extern __shared__ double2 eg_smem[];
+    const int lda = n + 1;
+    const int np = (n + 1) & ~1;
+    const int npair = np / 2;
+    double2* A = eg_smem;
+    double2* U = A + (long)n * lda;
+    double2* rs = U + (long)n * n;
+    double* rc = reinterpret_cast<double*>(rs + npair);
+    double* d = rc + npair;
+    double* vel = d + n;                 // [2][n] partial sums over the two 32-row chunks
+    double* red = vel + 2 * n;
+    int* pq = reinterpret_cast<int*>(red + 2 * (blockDim.x / 32) + 2);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    for (long k = blockIdx.x; k < nk; k += gridDim.x) {
+        __syncthreads();
+        const double2* Hk = H + k * (long)n * n;
+        for (int e = tid; e < n * n; e += nthr) {
+            int i = e % n, j = e / n;
+            double2 a = Hk[i + (long)j * n], b = Hk[j + (long)i * n];
+            A[i + j * lda] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+            U[i + j * n] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+        }
+        __syncthreads();
+        for (int sweep = 0; sweep < 40; sweep++) {
+            double off = 0.0, tot = 0.0;
+            for (int e = tid; e < n * n; e += nthr) {
+                int i = e % n, j = e / n;
+                double2 a = A[i + j * lda];
+                double v = a.x * a.x + a.y * a.y;
+                tot += v;
+                if (i != j) off += v;
+            }
+            off = warp_sum(off); tot = warp_sum(tot);
+            if (lane == 0) { red[2 * warp] = off; red[2 * warp + 1] = tot; }
+            __syncthreads();
+            if (tid == 0) {
+                double o = 0.0, t = 0.0;
+                for (int w = 0; w < nwarp; w++) { o += red[2 * w]; t += red[2 * w + 1]; }
+                red[2 * nwarp] = o; red[2 * nwarp + 1] = t;
+            }
+            __syncthreads();
+            const double o = red[2 * nwarp], t = red[2 * nwarp + 1];
+            __syncthreads();
+            if (!(t == t) || !isfinite(t)) { if (tid == 0) *errflag = 1; break; }
+            if (o <= 1e-30 * t) break;
+            for (int s = 0; s < np - 1; s++) {
+                if (tid < npair) {
+                    int p, q;
+                    rr_pair(np, s, tid, p, q);
+                    double c = 1.0; double2 sp = make_double2(0.0, 0.0);
+                    if (q < n) {
+                        double2 apq = A[p + q * lda];
+                        double g = hypot(apq.x, apq.y);
+                        if (g > 0.0) {
+                            double app = A[p + p * lda].x, aqq = A[q + q * lda].x;
+                            double tau = (aqq - app) / (2.0 * g);
+                            double tt = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                            c = 1.0 / sqrt(1.0 + tt * tt);
+                            double sn = tt * c;
+                            sp = make_double2(sn * apq.x / g, sn * apq.y / g);
+                        }
+                    } else { q = -1; }
+                    pq[2 * tid] = p; pq[2 * tid + 1] = q;
+                    rc[tid] = c; rs[tid] = sp;
+                }
+                __syncthreads();
+                // columns of A and of U: X <- X J
+                for (int item = tid; item < npair * n; item += nthr) {
+                    int t2 = item / n, i = item % n;
+                    int p = pq[2 * t2], q = pq[2 * t2 + 1];
+                    if (q < 0) continue;
+                    double c = rc[t2]; double2 sp = rs[t2];
+                    double2 akp = A[i + p * lda], akq = A[i + q * lda];
+                    A[i + p * lda] = make_double2(c * akp.x - (sp.x * akq.x + sp.y * akq.y), c * akp.y - (sp.x * akq.y - sp.y * akq.x));
+                    A[i + q * lda] = make_double2(sp.x * akp.x - sp.y * akp.y + c * akq.x, sp.x * akp.y + sp.y * akp.x + c * akq.y);
+                    double2 ukp = U[i + p * n], ukq = U[i + q * n];
+                    U[i + p * n] = make_double2(c * ukp.x - (sp.x * ukq.x + sp.y * ukq.y), c * ukp.y - (sp.x * ukq.y - sp.y * ukq.x));
+                    U[i + q * n] = make_double2(sp.x * ukp.x - sp.y * ukp.y + c * ukq.x, sp.x * ukp.y + sp.y * ukp.x + c * ukq.y);
+                }
+                __syncthreads();
+                // rows of A: A <- J^H A
+                for (int item = tid; item < npair * n; item += nthr) {
+                    int t2 = item / n, j = item % n;
+                    int p = pq[2 * t2], q = pq[2 * t2 + 1];
+                    if (q < 0) continue;
+                    double c = rc[t2]; double2 sp = rs[t2];
+                    double2 apk = A[p + j * lda], aqk = A[q + j * lda];
+                    A[p + j * lda] = make_double2(c * apk.x - (sp.x * aqk.x - sp.y * aqk.y), c * apk.y - (sp.x * aqk.y + sp.y * aqk.x));
+                    A[q + j * lda] = make_double2(sp.x * apk.x + sp.y * apk.y + c * aqk.x, sp.x * apk.y - sp.y * apk.x + c * aqk.y);
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = tid; i < n; i += nthr) d[i] = A[i + i * lda].x;
+        __syncthreads();
+        for (int i = tid; i < n; i += nthr) {
+            double di = d[i];
+            int rank = 0;
+            for (int j = 0; j < n; j++) { double dj = d[j]; rank += (dj < di) || (dj == di && j < i); }
+            eout[k * n + rank] = di;
+            pq[i] = rank;                    // pq is free now: band -> position in ascending order
+        }
+        // velocities: for every direction load V_d into A's storage and form u_j^H V_d u_j
+        const int n32 = (n + 31) & ~31;
+        for (int dir = 0; dir < ndim; dir++) {
+            __syncthreads();
+            const double2* Vk = (dir == 0 ? V0 : dir == 1 ? V1 : V2) + k * (long)n * n;
+            for (int e = tid; e < n * n; e += nthr) A[(e % n) + (e / n) * lda] = Vk[e];
+            for (int e = tid; e < 2 * n; e += nthr) vel[e] = 0.0;
+            __syncthreads();
+            for (int item = tid; item < n32 * n; item += nthr) {       // (a, j): a fastest, one j per warp pass
+                const int a = item % n32, j = item / n32;
+                double part = 0.0;
+                if (a < n) {
+                    double2 tsum = make_double2(0.0, 0.0);
+                    for (int b = 0; b < n; b++) tsum = cfma(tsum, A[a + b * lda], U[b + j * n]);
+                    const double2 ua = U[a + j * n];
+                    part = ua.x * tsum.x + ua.y * tsum.y;                // Re(conj(u_a) t)
+                }
+                part = warp_sum(part);
+                if (lane == 0) vel[(a >> 5) * n + j] += part;            // a >> 5 < 2 for n <= 64: distinct addresses per warp pass
+            }
+            __syncthreads();
+            const double per = dir == 0 ? t0 : dir == 1 ? t1 : t2;
+            for (int j = tid; j < n; j += nthr) vout[(k * ndim + dir) * n + pq[j]] = (vel[j] + vel[n + j]) * per;
+        }
+    }
+}
+
+// sum_ggr (src/dos_ggr.jl:58-104): out[iE] = sum_nodes w * sum_bands ggr_formula(b, E, e, v...), b = 1/(2 npt).
+// One CTA per energy E; fixed strided order + fixed tree => bit-reproducible.
+__device__ __forceinline__ double ggr_formula(int ndim, double b, double E, double e, double a1, double a2, double a3) {
+    const double dw = fabs(E - e);
+    if (ndim == 1) {
+        const double v1 = fabs(a1);
+        return (dw <= b * v1) ? 1.0 / v1 : 0.0;
+    }
+    if (ndim == 2) {
+        const double v1 = fmax(fabs(a1), fabs(a2)), v2 = fmin(fabs(a1), fabs(a2));
+        const double w1 = b * fabs(v1 - v2), w3 = b * (v1 + v2);
+        if (dw <= w1) return 2 * b / v1;
+        if (w1 <= dw && dw <= w3) return (b * (v1 + v2) - dw) / (v1 * v2);
+        return 0.0;
+    }
+    double x0 = fabs(a1), x1 = fabs(a2), x2 = fabs(a3), t;
+    if (x0 > x1) { t = x0; x0 = x1; x1 = t; }
+    if (x1 > x2) { t = x1; x1 = x2; x2 = t; }
+    if (x0 > x1) { t = x0; x0 = x1; x1 = t; }
+    const double v3 = x0, v2 = x1, v1 = x2;
+    const double w1 = b * fabs(v1 - v2 - v3), w2 = b * (v1 - v2 + v3), w3 = b * (v1 + v2 - v3), w4 = b * (v1 + v2 + v3);
+    const double v = sqrt(v1 * v1 + v2 * v2 + v3 * v3);
+    if (v1 >= v2 + v3 && dw <= w1) return 4 * b * b / v1;
+    if (v1 <= v2 + v3 && dw <= w1) return (2 * b * b * (v1 * v2 + v2 * v3 + v3 * v1) - (dw * dw + (v * b) * (v * b))) / (v1 * v2 * v3);
+    if (w1 <= dw && dw <= w2)
+        return (b * b * (v1 * v2 + 3 * v2 * v3 + v3 * v1) - b * dw * (-v1 + v2 + v3) - (dw * dw + (v * b) * (v * b)) / 2) / (v1 * v2 * v3);
+    if (w2 <= dw && dw <= w3) return 2 * b * (b * (v1 + v2) - dw) / (v1 * v2);
+    if (w3 <= dw && dw <= w4) { const double u = b * (v1 + v2 + v3) - dw; return u * u / (2 * v1 * v2 * v3); }
+    return 0.0;
+}
+__global__ void __launch_bounds__(256)
+ggr_sum_kernel(const double* __restrict__ e, const double* __restrict__ v, const double* __restrict__ wnode, long nk, int n, int ndim,
+               double b, const double* __restrict__ E, double scale, double* __restrict__ out) {
+    __shared__ double sx[256];
+    const double Ei = E[blockIdx.x];
+    double acc = 0.0;
+    for (long item = threadIdx.x; item < nk * n; item += 256) {
+        const long k = item / n; const int j = (int)(item % n);
+        const double* vk = v + k * ndim * n;
+        const double f = ggr_formula(ndim, b, Ei, e[item], vk[j], ndim > 1 ? vk[n + j] : 0.0, ndim > 2 ? vk[2 * n + j] : 0.0);
+        acc += (wnode ? wnode[k] : 1.0) * f;
+    }
+    sx[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sx[threadIdx.x] += sx[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = scale * sx[0];
+}
+
+// JacobianSeries (src/dos_ggr.jl:6): coefficients of dH/dk_dim = 2 pi i R_dim / period_dim * H_R
+__global__ void __launch_bounds__(256)
+jacobian_coeff_kernel(const double2* __restrict__ c, double2* __restrict__ out, long nn, int M1, int M2, int M3, int lo, int dim,
+                      double period) {
+    const long tot = nn * M1 * M2 * M3;
+    const long idx = (long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= tot) return;
+    const long blk = idx / nn;
+    const int m = dim == 0 ? (int)(blk % M1) : dim == 1 ? (int)((blk / M1) % M2) : (int)(blk / ((long)M1 * M2));
+    const double f = 2.0 * 3.14159265358979323846 * (double)(m + lo) / period;
+    const double2 a = c[idx];
+    out[idx] = make_double2(-f * a.y, f * a.x);
+}
+
 // ---- K4-fast: Householder tridiagonalisation (one CTA per k, matrix in shared memory) + implicit QL per thread ----
 // eigen(Hermitian(H(k))) (src/dos_ggr.jl:19,34), eigenvalues only.  Stage A reduces (H + H^H)/2 to a real symmetric
 // tridiagonal matrix by n-2 Hermitian Householder reflections P = I - tau v v^H (real tau, v = y + e^{i arg y_1}|y| e_1):

@@ -179,7 +179,11 @@ class IntegralCache:
 
 
 def init(prob, alg, backend=None, shard=None, **kwargs):
-    """init(prob, alg; kwargs...) (src/interfaces.jl:78-82): build the cache (rules / arena) once."""
+    """init(prob, alg; kwargs...) (src/interfaces.jl:78-82): build the cache (rules / arena) once.
+    DOSProblem + DOSAlgorithm dispatch to dos.dos_init (src/dos_interfaces.jl:84-88)."""
+    from . import dos
+    if isinstance(prob, dos.DOSProblem):
+        return dos.dos_init(prob, alg, backend=backend, shard=shard, **kwargs)
     checkkwargs(kwargs)
     if not isinstance(prob.f, FourierIntegrand):
         raise TypeError("autobz_b200 implements the FourierIntegrand hot path only (SURVEY.md §8)")
@@ -193,6 +197,9 @@ def init(prob, alg, backend=None, shard=None, **kwargs):
 def solve_(cache, plist=None):
     """solve!(cache) (src/interfaces.jl:116-118).  plist: several parameter sets solved against the same
     cached rule in one device pass (the batchsolve fast path); returns one IntegralSolution per entry."""
+    from . import dos
+    if isinstance(cache, dos.DOSCache):
+        return dos.dos_solve_(cache)
     single = plist is None
     ps = [cache.p] if single else list(plist)
     sols = _do_solve(cache, ps)

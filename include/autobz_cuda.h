@@ -122,6 +122,15 @@ int32_t abz_rule_eig_sum(abz_ctx* ctx, abz_rule_t r, int32_t kind, const double*
 /* all eigenvalues, Float64[n, nnodes] ascending per node (GGR data pass, src/dos_ggr.jl:14-44) */
 int32_t abz_rule_eigvals(abz_ctx* ctx, abz_rule_t r, double* evals);
 
+/* ---- GGR density of states (src/dos_ggr.jl) ------------------------------------------------ */
+/* get_ggr_data (src/dos_ggr.jl:14-44): at every node e = eigen(Hermitian(h)).values and the band velocities
+ * v_d = real(diag(U' V_d U)) * period_d, V_d from JacobianSeries(h) (coefficient R times 2 pi i R_d / period_d),
+ * d < ndim.  Cached on the device in the rule; optionally copied out: energies = Float64[n, nnodes] ascending,
+ * velocities = Float64[n, ndim, nnodes] (either may be NULL). */
+int32_t abz_rule_ggr_data(abz_ctx* ctx, abz_rule_t r, int32_t ndim, double* energies, double* velocities);
+/* sum_ggr (src/dos_ggr.jl:58-104): out[i] = scale * sum_nodes w sum_bands ggr_formula(1/(2 npt), E_i, e, v...) */
+int32_t abz_rule_ggr_sum(abz_ctx* ctx, abz_rule_t r, int32_t nE, const double* E, double scale, double* out);
+
 /* ---- S3/S4: scattered nodes for IAI panels (src/fourier.jl:432-486) ----------------------- */
 /* workspace_evaluate(w, x) at npts arbitrary points (x NOT scaled by the period, :454):
  * k = Float64[3,npts]; Hk = ComplexF64[n,n,npts] */

@@ -95,12 +95,12 @@ function DeviceRule(ds::DeviceSeries, npt::Integer, syms)
         nsym = 1
     else
         S = Int32[round(Int32, s[i, j]) for j in 1:3, i in 1:3, s in syms]       # row-major 3x3 per symmetry
-        wsym = Array{Int32}(undef, npt, npt, npt)
         nirr = Ref{Int64}(0)
-        check(ctx, ccall((:abz_symptr_rule, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ref{Int64}),
-                         ctx.h, npt, length(syms), S, wsym, nirr))
-        check(ctx, ccall((:abz_rule_create_sym, LIB), Int32, (Ptr{Cvoid}, UInt64, Int32, Ptr{Int32}, Int32, Int32, Ref{UInt64}),
-                         ctx.h, ds.h, npt, wsym, 0, 1, h))
+        # symptr_rule + CSR compaction on the device; the dense Int32[npt,npt,npt] weights never visit the host
+        # (abz_symptr_rule + abz_rule_create_sym remain for callers that already hold AutoSymPTR's wsym array)
+        check(ctx, ccall((:abz_rule_create_symptr, LIB), Int32,
+                         (Ptr{Cvoid}, UInt64, Int32, Int32, Ptr{Int32}, Int32, Int32, Ref{UInt64}, Ref{Int64}),
+                         ctx.h, ds.h, npt, length(syms), S, 0, 1, h, nirr))
         nsym = length(syms)
     end
     nn = Ref{Int64}(0); no = Ref{Int32}(0); np = Ref{Int32}(0)
@@ -204,6 +204,28 @@ function eval!(y::Vector{ComplexF64}, n::DeviceNest, x1::Vector{Float64}, slot1:
     check(n.ctx, ccall((:abz_nest_eval, LIB), Int32, (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Ptr{Int64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                        n.ctx.h, n.h, length(x1), x1, slot1, 0, Ref(z), C_NULL, Ptr{Float64}(pointer(y))))
     return y
+end
+
+# H at the panel nodes for integrands evaluated in Julia (f.f(FourierValue(k, H), p), src/fourier.jl:452-456)
+function eval_h!(Hk::Array{ComplexF64,3}, n::DeviceNest, x1::Vector{Float64}, slot1::Vector{Int64})
+    check(n.ctx, ccall((:abz_nest_eval_h, LIB), Int32, (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}),
+                       n.ctx.h, n.h, length(x1), x1, slot1, Ptr{Float64}(pointer(Hk))))
+    return Hk
+end
+
+# The whole nested solve in one call (do_solve(f::FourierIntegrand, lims, ::NestedQuad), src/fourier.jl:493-510): same
+# control flow as IteratedIntegration/QuadGK, run by the library's host engine.  lims::CubicLimits or TetrahedralLimits.
+# vkind 0: tr G, 1: -Im(tr G)/pi (aps_example.jl:30).  exchange: @cfunction(allreduce!, Int32, (Ptr{Float64}, Int64, Ptr{Cvoid}))
+# for multi-rank solves (outermost panel nodes dealt to ranks), or C_NULL to use the NCCL communicator of abz_comm_init.
+function iai_solve(n::DeviceNest, lkind::Integer, la::Vector{Float64}, lb, z::ComplexF64; vkind=0, abstol=0.0, reltol=0.0,
+                   maxiters=typemax(Int64) >> 1, device_leaves=true, rank=0, nranks=1, exchange=C_NULL)
+    out = zeros(3); stats = zeros(Int64, 4)
+    check(n.ctx, ccall((:abz_iai_solve_sharded, LIB), Int32,
+                       (Ptr{Cvoid}, UInt64, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                        Float64, Float64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}),
+                       n.ctx.h, n.h, lkind, la, lb === nothing ? C_NULL : lb, 0, vkind, Ref(z), C_NULL, C_NULL,
+                       abstol, reltol, maxiters, device_leaves ? 1 : 0, rank, nranks, exchange, C_NULL, out, stats))
+    return IntegralSolution(vkind == 1 ? out[1] : complex(out[1], out[2]), out[3], true, Int(stats[1]))
 end
 
 # v0.4+ API names (BASELINE.json north_star) as thin aliases

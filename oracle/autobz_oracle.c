@@ -830,6 +830,178 @@ int orc_iai(const double* coeffs, int n, int dim, const int* M, const int* lo, c
     return rc ? rc : err;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * GGR density of states (src/dos_ggr.jl): data pass get_ggr_data (:14-44) = at every node of the
+ * (symmetry-reduced) PTR grid the band energies e = eigen(Hermitian(h)).values and the band velocities
+ * v_d = real(diag(U' V_d U)) * period_d with V_d the series of JacobianSeries(h), i.e. coefficient R
+ * multiplied by 2 pi i R_d / period_d [FourierSeriesEvaluators, restated]; then sum_ggr (:58-65) with the
+ * generalized Gilat-Raubenheimer formulas ggr_formula (:67-104), b = 1/(2 npt).
+ * ------------------------------------------------------------------------------------------- */
+/* eigen-decomposition of the hermitised matrix by cyclic Jacobi with accumulated rotations.
+ * w ascending, U[:, j] the eigenvector of w[j] (column-major).  work: 2 n^2 zc */
+int orc_eigh(const zc* Hin, int n, double* w, zc* U, zc* work) {
+    zc* A = work; zc* V = work + (long)n * n;
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+            A[i + (long)j * n] = 0.5 * (Hin[i + (long)j * n] + conj(Hin[j + (long)i * n]));
+            V[i + (long)j * n] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int j = 0; j < n; j++)
+            for (int i = 0; i < n; i++) {
+                zc a = A[i + (long)j * n];
+                double v = creal(a) * creal(a) + cimag(a) * cimag(a);
+                if (i == j) diag += v; else off += v;
+            }
+        if (off <= 1e-32 * (diag + off) || off == 0.0) break;
+        for (int p = 0; p < n - 1; p++)
+            for (int q = p + 1; q < n; q++) {
+                zc apq = A[p + (long)q * n];
+                double g = cabs(apq);
+                if (g == 0.0) continue;
+                double app = creal(A[p + (long)p * n]), aqq = creal(A[q + (long)q * n]);
+                double tau = (aqq - app) / (2.0 * g);
+                double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                double c = 1.0 / sqrt(1.0 + t * t), sn = t * c;
+                zc ph = apq / g;
+                for (int k = 0; k < n; k++) {
+                    zc akp = A[k + (long)p * n], akq = A[k + (long)q * n];
+                    A[k + (long)p * n] = c * akp - sn * conj(ph) * akq;
+                    A[k + (long)q * n] = sn * ph * akp + c * akq;
+                    zc vkp = V[k + (long)p * n], vkq = V[k + (long)q * n];
+                    V[k + (long)p * n] = c * vkp - sn * conj(ph) * vkq;
+                    V[k + (long)q * n] = sn * ph * vkp + c * vkq;
+                }
+                for (int k = 0; k < n; k++) {
+                    zc apk = A[p + (long)k * n], aqk = A[q + (long)k * n];
+                    A[p + (long)k * n] = c * apk - sn * ph * aqk;
+                    A[q + (long)k * n] = sn * conj(ph) * apk + c * aqk;
+                }
+            }
+    }
+    /* sort ascending (stable selection on the diagonal) */
+    for (int j = 0; j < n; j++) {
+        double dj = creal(A[j + (long)j * n]);
+        int rank = 0;
+        for (int i = 0; i < n; i++) { double di = creal(A[i + (long)i * n]); rank += (di < dj) || (di == dj && i < j); }
+        w[rank] = dj;
+        for (int k = 0; k < n; k++) U[k + (long)rank * n] = V[k + (long)j * n];
+    }
+    return ORC_OK;
+}
+
+/* data pass over the rule's nodes in its iteration order (k1 fastest; wsym == NULL: full grid, weight 1).
+ * wout[nnodes], eout[n*nnodes], vout[n*ndim*nnodes] (per node: v_1[1..n], ..., v_ndim[1..n]); returns nnodes */
+long orc_ggr_data(const double* coeffs, int n, int ndim, const int* M, const int* lo, const double* period, int N,
+                  const int32_t* wsym, double* wout, double* eout, double* vout) {
+    orc_series s; orc_series_fill(&s, coeffs, n, M, lo, period);
+    long nn = (long)n * n, r2 = nn * M[0] * M[1], r1 = nn * M[0], tot = r2 * M[2];
+    zc* D[3] = {0, 0, 0};
+    for (int d = 0; d < ndim; d++) {
+        D[d] = (zc*)malloc(sizeof(zc) * tot);
+        for (int m3 = 0; m3 < M[2]; m3++)
+            for (int m2 = 0; m2 < M[1]; m2++)
+                for (int m1 = 0; m1 < M[0]; m1++) {
+                    int R = (d == 0 ? m1 + lo[0] : d == 1 ? m2 + lo[1] : m3 + lo[2]);
+                    zc f = IU * (2.0 * M_PI * (double)R / period[d]);
+                    long base = (((long)m3 * M[1] + m2) * M[0] + m1) * nn;
+                    for (long e = 0; e < nn; e++) D[d][base + e] = f * s.C[base + e];
+                }
+    }
+    zc* c2 = (zc*)malloc(sizeof(zc) * r2 * 4); zc* c1 = (zc*)malloc(sizeof(zc) * r1 * 4); zc* h = (zc*)malloc(sizeof(zc) * nn * 4);
+    zc* U = (zc*)malloc(sizeof(zc) * nn); zc* work = (zc*)malloc(sizeof(zc) * nn * 2); zc* T = (zc*)malloc(sizeof(zc) * nn);
+    long cnt = 0;
+    int N3 = (ndim >= 3) ? N : 1, N2 = (ndim >= 2) ? N : 1;
+    for (int i3 = 0; i3 < N3; i3++) {
+        int have3 = 0;
+        for (int i2 = 0; i2 < N2; i2++) {
+            int have2 = 0;
+            for (int i1 = 0; i1 < N; i1++) {
+                long idx = ((long)i3 * N2 + i2) * N + i1;
+                int wt = wsym ? wsym[idx] : 1;
+                if (!wt) continue;
+                for (int q = 0; q <= ndim; q++) {
+                    const zc* C = q == 0 ? s.C : D[q - 1];
+                    if (!have3) orc_contract(C, r2, M[2], lo[2], period[2], period[2] * ((double)i3 / N), c2 + q * r2);
+                    if (!have2) orc_contract(c2 + q * r2, r1, M[1], lo[1], period[1], period[1] * ((double)i2 / N), c1 + q * r1);
+                    orc_contract(c1 + q * r1, nn, M[0], lo[0], period[0], period[0] * ((double)i1 / N), h + q * nn);
+                }
+                have3 = have2 = 1;
+                orc_eigh(h, n, eout + cnt * n, U, work);
+                for (int d = 0; d < ndim; d++) {
+                    const zc* V = h + (long)(d + 1) * nn;
+                    for (int j = 0; j < n; j++) {
+                        zc acc = 0.0;
+                        for (int a = 0; a < n; a++) {
+                            zc t = 0.0;
+                            for (int bb = 0; bb < n; bb++) t += V[a + (long)bb * n] * U[bb + (long)j * n];
+                            acc += conj(U[a + (long)j * n]) * t;
+                        }
+                        vout[(cnt * ndim + d) * n + j] = creal(acc) * period[d];
+                    }
+                }
+                wout[cnt] = (double)wt;
+                cnt++;
+            }
+        }
+    }
+    for (int d = 0; d < 3; d++) free(D[d]);
+    free(c2); free(c1); free(h); free(U); free(work); free(T);
+    return cnt;
+}
+
+static double ggr1(double b, double E, double e, double v1) {
+    v1 = fabs(v1);
+    double dw = fabs(E - e), w1 = b * v1;
+    return (0.0 <= dw && dw <= w1) ? 1.0 / v1 : 0.0;
+}
+static double ggr2(double b, double E, double e, double a1, double a2) {
+    double v1 = fmax(fabs(a1), fabs(a2)), v2 = fmin(fabs(a1), fabs(a2));
+    double dw = fabs(E - e), w1 = b * fabs(v1 - v2), w3 = b * (v1 + v2);
+    if (0.0 <= dw && dw <= w1) return 2 * b / v1;
+    if (w1 <= dw && dw <= w3) return (b * (v1 + v2) - dw) / (v1 * v2);
+    return 0.0;
+}
+static double ggr3(double b, double E, double e, double a1, double a2, double a3) {
+    double x[3] = {fabs(a1), fabs(a2), fabs(a3)};
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 2 - i; j++) if (x[j] > x[j + 1]) { double t = x[j]; x[j] = x[j + 1]; x[j + 1] = t; }
+    double v3 = x[0], v2 = x[1], v1 = x[2];
+    double dw = fabs(E - e);
+    double w1 = b * fabs(v1 - v2 - v3), w2 = b * (v1 - v2 + v3), w3 = b * (v1 + v2 - v3), w4 = b * (v1 + v2 + v3);
+    double v = sqrt(v1 * v1 + v2 * v2 + v3 * v3);   /* hypot(v1, v2, v3) */
+    if (v1 >= v2 + v3 && 0.0 <= dw && dw <= w1) return 4 * b * b / v1;
+    if (v1 <= v2 + v3 && 0.0 <= dw && dw <= w1)
+        return (2 * b * b * (v1 * v2 + v2 * v3 + v3 * v1) - (dw * dw + (v * b) * (v * b))) / (v1 * v2 * v3);
+    if (w1 <= dw && dw <= w2)
+        return (b * b * (v1 * v2 + 3 * v2 * v3 + v3 * v1) - b * dw * (-v1 + v2 + v3) - (dw * dw + (v * b) * (v * b)) / 2) / (v1 * v2 * v3);
+    if (w2 <= dw && dw <= w3) return 2 * b * (b * (v1 + v2) - dw) / (v1 * v2);
+    if (w3 <= dw && dw <= w4) { double t = b * (v1 + v2 + v3) - dw; return t * t / (2 * v1 * v2 * v3); }
+    return 0.0;
+}
+/* sum_ggr: out[iE] = sum_nodes w * sum_bands ggr_formula(b, E, e, v...) */
+int orc_ggr_sum(int ndim, int npt, int nE, const double* E, long nnodes, int n, const double* w, const double* e, const double* v,
+                double* out) {
+    if (ndim < 1 || ndim > 3) return ORC_E_ARG;
+    double b = 1.0 / (2.0 * npt);
+    for (int iE = 0; iE < nE; iE++) {
+        double acc = 0.0;
+        for (long k = 0; k < nnodes; k++) {
+            double sb = 0.0;
+            for (int j = 0; j < n; j++) {
+                const double* vk = v + k * ndim * n;
+                double ej = e[k * n + j];
+                if (ndim == 1) sb += ggr1(b, E[iE], ej, vk[j]);
+                else if (ndim == 2) sb += ggr2(b, E[iE], ej, vk[j], vk[n + j]);
+                else sb += ggr3(b, E[iE], ej, vk[j], vk[n + j], vk[2 * n + j]);
+            }
+            acc += w[k] * sb;
+        }
+        out[iE] = acc;
+    }
+    return ORC_OK;
+}
+
 /* batch helpers for tests: resolvent traces / eigenvalues of nk materialised matrices */
 int orc_resolvent_trace_batch(const double* H, int n, long nk, int nw, const double* z, const double* sigma, double* out) {
     zc* work = (zc*)malloc(sizeof(zc) * ((long)n * n + n)); int* piv = (int*)malloc(sizeof(int) * n);

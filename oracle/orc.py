@@ -210,3 +210,28 @@ def iai(s, dim, lkind, la, lb=None, vkind=0, z=0.0, sigma=None, lin=(1.0, 0.0), 
     if rc:
         raise FloatingPointError("oracle: NaN/Inf in integrand (DomainError)")
     return complex(out[0], out[1]), out[2], int(ne[0])
+
+
+def ggr_data(s, ndim, N, wsym=None):
+    """get_ggr_data (src/dos_ggr.jl:14-44): (weights [nnodes], energies [nnodes, n], velocities [nnodes, ndim, n])"""
+    nmax = N ** ndim
+    wp = None
+    if wsym is not None:
+        w32 = np.asfortranarray(wsym, dtype=np.int32)
+        wp = w32.ctypes.data_as(C.POINTER(C.c_int32))
+        nmax = int(np.count_nonzero(w32))
+    w = np.zeros(nmax); e = np.zeros((nmax, s.n)); v = np.zeros((nmax, ndim, s.n))
+    lib().orc_ggr_data.restype = C.c_long
+    cnt = lib().orc_ggr_data(*s.args()[:2], C.c_int(ndim), *s.args()[2:], C.c_int(N), wp, _dp(w), _dp(e), _dp(v))
+    assert cnt == nmax, (cnt, nmax)
+    return w, e, v
+
+
+def ggr_sum(ndim, npt, E, w, e, v):
+    """sum_ggr (src/dos_ggr.jl:58-65)"""
+    Ev = np.ascontiguousarray(np.atleast_1d(np.asarray(E, dtype=np.float64)))
+    out = np.zeros(Ev.size)
+    rc = lib().orc_ggr_sum(C.c_int(ndim), C.c_int(npt), C.c_int(Ev.size), _dp(Ev), C.c_long(w.size), C.c_int(e.shape[1]),
+                           _dp(np.ascontiguousarray(w)), _dp(np.ascontiguousarray(e)), _dp(np.ascontiguousarray(v)), _dp(out))
+    assert rc == 0
+    return out

@@ -22,6 +22,7 @@ def _oseries(fs):
 class OracleRule:
     def __init__(self, series, ndim, npt, syms, rank=0, nranks=1):
         self.fs, self.so, self.ndim, self.npt = series, _oseries(series), ndim, int(npt)
+        self._syms = syms
         if ndim == 3:
             if syms is None:
                 i3, i2, i1 = np.meshgrid(np.arange(npt), np.arange(npt), np.arange(npt), indexing="ij")
@@ -39,11 +40,13 @@ class OracleRule:
                 sel = (idx[:, 2] % nranks) == rank
             self.nnodes_total = idx.shape[0]
             self.idx, self.w = idx[sel], w[sel]
+            self._sel = sel
         else:
             idx, w = symptr_nodes_lowdim(npt, ndim, syms)
             self.nnodes_total = idx.shape[0]
             lo, hi = (idx.shape[0] * rank) // nranks, (idx.shape[0] * (rank + 1)) // nranks
             self.idx, self.w = idx[lo:hi], w[lo:hi]
+            self._sel = slice(lo, hi)
         self.nnodes = self.idx.shape[0]
         self._H = None
 
@@ -83,6 +86,28 @@ class OracleRule:
         else:
             g = np.exp(-((ev - p0) / p1) ** 2) / (p1 * np.sqrt(np.pi))
         return float(np.sum(self.w * g.sum(axis=1)))
+
+    def ggr_data(self, ndim, copy=True):
+        # the oracle's data pass runs over the rule's full node set; keep this rank's nodes
+        if self.ndim == 3 and self._syms is not None:
+            sy = np.array([np.rint(np.asarray(S)).astype(np.int32) for S in self._syms])
+            ws, _ = orc.symptr_rule(self.npt, sy)
+        elif self._syms is None:
+            ws = None
+        else:
+            ws = np.zeros((self.npt,) * self.ndim + (1,) * (3 - self.ndim), dtype=np.int32, order="F")
+            idx, w = symptr_nodes_lowdim(self.npt, self.ndim, self._syms)
+            ws[tuple(idx[:, d] for d in range(self.ndim)) + (0,) * (3 - self.ndim)] = w.astype(np.int32)
+        w, e, v = orc.ggr_data(self.so, self.ndim, self.npt, ws)
+        sel = self._sel
+        self._ggr = (w[sel], e[sel], v[sel])
+        return (self._ggr[1], self._ggr[2]) if copy else (None, None)
+
+    def ggr_sum(self, E):
+        w, e, v = self._ggr
+        if w.size == 0:
+            return np.zeros(np.atleast_1d(E).size)
+        return orc.ggr_sum(self.ndim, self.npt, E, w, e, v)
 
     def close(self):
         pass
