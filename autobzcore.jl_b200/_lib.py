@@ -23,7 +23,7 @@ EXPORTS = [
     "abz_version", "abz_last_error", "abz_ctx_create", "abz_ctx_destroy", "abz_ctx_set_option", "abz_ctx_launch_count",
     "abz_ctx_last_timings", "abz_series_create", "abz_series_destroy", "abz_rule_create_full", "abz_rule_create_sym", "abz_rule_create_nodes",
     "abz_symptr_rule", "abz_rule_create_symptr", "abz_rule_destroy", "abz_rule_info", "abz_rule_materialize", "abz_rule_copy_out",
-    "abz_rule_resolvent_sum", "abz_rule_eig_sum", "abz_rule_eigvals", "abz_rule_ggr_data", "abz_rule_ggr_sum", "abz_points_eval", "abz_points_resolvent",
+    "abz_rule_resolvent_sum", "abz_rule_resolvent_matrix_sum", "abz_rule_eig_sum", "abz_rule_eigvals", "abz_rule_ggr_data", "abz_rule_ggr_sum", "abz_points_eval", "abz_points_resolvent",
     "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval", "abz_nest_eval_h", "abz_iai_solve", "abz_iai_solve_sharded",
     "abz_comm_unique_id", "abz_comm_init", "abz_allreduce_sum", "abz_comm_destroy",
 ]
@@ -77,6 +77,7 @@ def load():
     lib.abz_rule_materialize.argtypes = [C.c_void_p, C.c_uint64]
     lib.abz_rule_copy_out.argtypes = [C.c_void_p, C.c_uint64, c_dp, c_dp, c_dp]
     lib.abz_rule_resolvent_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, c_dp, c_dp, C.c_double, c_dp]
+    lib.abz_rule_resolvent_matrix_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp, C.c_double, c_dp]
     lib.abz_rule_eig_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, C.c_double, c_dp]
     lib.abz_rule_eigvals.argtypes = [C.c_void_p, C.c_uint64, c_dp]
     lib.abz_rule_ggr_data.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp]
@@ -302,6 +303,15 @@ class DeviceRule:
         out = np.empty(nw, dtype=np.complex128)
         self.ctx.check(self.ctx.lib.abz_rule_resolvent_sum(self.ctx.h, self.h, fkind, nw, _dp(zz), _dp(sg), float(scale), _dp(out)))
         return out
+
+    def resolvent_matrix_sum(self, z, sigma=None, scale=1.0):
+        """scale * sum_i w_i (z_w - H(k_i) - Sigma_w)^-1 -> [nw, n, n]"""
+        zz = _cz(z)
+        nw, n = zz.size, self.series.n
+        sg = None if sigma is None else np.asfortranarray(np.asarray(sigma, dtype=np.complex128).reshape(n, n, nw))
+        out = np.empty((n, n, nw), dtype=np.complex128, order="F")
+        self.ctx.check(self.ctx.lib.abz_rule_resolvent_matrix_sum(self.ctx.h, self.h, nw, _dp(zz), _dp(sg), float(scale), _dp(out)))
+        return np.ascontiguousarray(np.moveaxis(out, 2, 0))
 
     def eig_sum(self, kind, params=(0.0, 1.0), scale=1.0):
         prm = np.ascontiguousarray(np.asarray(params, dtype=np.float64))

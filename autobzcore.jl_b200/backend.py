@@ -100,6 +100,10 @@ class DeviceRule:
         """sum_i w_i f(H(k_i)) over the local nodes, one value per frequency (unscaled)."""
         return self.dev.resolvent_sum(z, sigma=sigma, scale=1.0, fkind=fkind)
 
+    def resolvent_matrix_sum(self, z, sigma):
+        """sum_i w_i (z - H(k_i) - Sigma)^-1 over the local nodes -> [nw, n, n] (unscaled)"""
+        return self.dev.resolvent_matrix_sum(z, sigma=sigma, scale=1.0)
+
     def eig_sum(self, kind, params):
         return self.dev.eig_sum(kind, params, scale=1.0)
 

@@ -929,6 +929,76 @@ int32_t abz_rule_resolvent_sum(abz_ctx* ctx, abz_rule_t rid, int32_t fkind, int3
 }
 
 
+// G(w) = scale * sum_i w_i (z_w - H(k_i) - Sigma_w)^-1, matrix-valued (docs/src/examples.md:20,90)
+int32_t abz_rule_resolvent_matrix_sum(abz_ctx* ctx, abz_rule_t rid, int32_t nw, const double* z, const double* sigma, double scale,
+                                      double* out) {
+    if (!ctx) return ABZ_E_INVALID;
+    Rule* r = get_rule(ctx, rid);
+    if (!r) return fail(ctx, ABZ_E_INVALID, "unknown rule handle");
+    if (nw < 1 || !z || !out) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    cudaSetDevice(ctx->device);
+    Series* s = r->s;
+    const int n = s->n;
+    const long nn = (long)n * n;
+    if (n > 64) return fail(ctx, ABZ_E_UNSUPPORTED, "norb > 64 is not supported by the resolvent kernels");
+    int rc = upload_params(ctx, n, nw, z, sigma);
+    if (rc) return rc;
+    const size_t nacc = (size_t)nw * nn;
+    CU(ctx, ctx->acc.reserve(nacc * sizeof(double2)));
+    CU(ctx, cudaMemsetAsync(ctx->acc.p, 0, nacc * sizeof(double2), ctx->stream));
+    const size_t per_warp = ((size_t)n * (n + 1) + (n + 1) / 2 + 1 + nn) * sizeof(double2);
+    const int nwarps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
+    const size_t smem = per_warp * nwarps;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(resolvent_gj_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
+    std::vector<Chunk> chunks;
+    long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
+    if (r->d_H) chunks.push_back({0, r->np3, 0, r->nrows});
+    else chunks = plan_chunks(r, node_cap_for(ctx, n), (long)(ctx->budget / (rows1 * sizeof(double2))), (long)(ctx->budget / (rows2 * sizeof(double2))));
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_eval, ev_mat;
+    ctx->ev_used = 0;
+    for (auto& ch : chunks) {
+        const long n0 = r->h_row_nodeptr[ch.r0], n1 = r->h_row_nodeptr[ch.r1], nk = n1 - n0;
+        if (nk <= 0) continue;
+        cudaEvent_t e0 = next_event(ctx);
+        const double2* Hd = r->d_H ? r->d_H + n0 * nn : nullptr;
+        if (!Hd) {
+            CU(ctx, ctx->Hc.reserve((size_t)nk * nn * sizeof(double2)));
+            rc = eval_chunk(ctx, r, ch, true, ctx->Hc.as<double2>());
+            if (rc) return rc;
+            Hd = ctx->Hc.as<double2>();
+        }
+        cudaEvent_t e1 = next_event(ctx);
+        // node chunks per frequency: enough CTAs to fill the chip, few enough that the partials stay small
+        const long target = std::max<long>(1, ((long)ctx->sm_count * 2 + nw - 1) / nw);
+        const int kper = (int)std::max<long>(nwarps, (nk + target - 1) / target);
+        const long ncta = (nk + kper - 1) / kper;
+        CU(ctx, ctx->partial.reserve((size_t)ncta * nacc * sizeof(double2)));
+        dim3 grid((unsigned)ncta, (unsigned)nw);
+        resolvent_gj_matrix_kernel<<<grid, nwarps * 32, smem, ctx->stream>>>(Hd, r->d_node_w ? r->d_node_w + n0 : nullptr, nk, n, nw,
+                                                                            ctx->zbuf.as<double2>(), sigma ? ctx->sigbuf.as<double2>() : nullptr,
+                                                                            kper, ctx->partial.as<double2>(), ctx->errflag.as<int>());
+        LAUNCH_CHECK(ctx, "resolvent_gj_matrix_kernel");
+        const long nred = (long)nacc;
+        for (long off = 0; off < nred; off += 65535) {      // one CTA per output element
+            const int cnt = (int)std::min<long>(65535, nred - off);
+            reduce_partials_strided_kernel<<<cnt, 256, 0, ctx->stream>>>(ctx->partial.as<double2>() + off, ncta, nred, 1.0, ctx->acc.as<double2>() + off);
+            LAUNCH_CHECK(ctx, "reduce_partials_strided_kernel");
+        }
+        cudaEvent_t e2 = next_event(ctx);
+        ev_eval.push_back({e0, e1});
+        ev_mat.push_back({e1, e2});
+    }
+    std::vector<double2> h(nacc);
+    CU(ctx, cudaMemcpyAsync(h.data(), ctx->acc.p, nacc * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = check_errflag(ctx, "abz_rule_resolvent_matrix_sum");
+    collect_timings(ctx, ev_eval, ev_mat);
+    if (rc == ABZ_RETRY_PIVOTED) rc = ABZ_OK;
+    if (rc) return rc;
+    for (size_t i = 0; i < nacc; i++) { out[2 * i] = scale * h[i].x; out[2 * i + 1] = scale * h[i].y; }
+    return ABZ_OK;
+}
+
 static size_t eig_smem_bytes(int n, int threads) {
     int np = (n + 1) & ~1, npair = np / 2;
     return (size_t)n * (n + 1) * 16 + (size_t)npair * 16 + (size_t)npair * 8 + (size_t)n * 8 + (size_t)(2 * (threads / 32) + 2) * 8 +

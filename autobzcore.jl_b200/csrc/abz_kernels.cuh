@@ -174,6 +174,29 @@ reduce_partials_kernel(const double2* __restrict__ partial, long ncta, int nw, d
     }
 }
 
+// the same reduction with an explicit partial stride: acc[w] += scale * sum_c partial[c*stride + w], w = blockIdx.x
+__global__ void __launch_bounds__(256)
+reduce_partials_strided_kernel(const double2* __restrict__ partial, long ncta, long stride, double scale, double2* __restrict__ acc) {
+    __shared__ double sx[256], sy[256];
+    const int w = blockIdx.x;
+    double x = 0.0, y = 0.0;
+    for (long c = threadIdx.x; c < ncta; c += 256) {
+        double2 p = partial[c * stride + w];
+        x += p.x; y += p.y;
+    }
+    sx[threadIdx.x] = x; sy[threadIdx.x] = y;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sx[threadIdx.x] += sx[threadIdx.x + s]; sy[threadIdx.x] += sy[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double2 a = acc[w];
+        a.x += scale * sx[0]; a.y += scale * sy[0];
+        acc[w] = a;
+    }
+}
+
 // block-level deterministic sum of NV complex values per thread -> partial[blockIdx.x*stride + v0 + v]
 template <int NV, int THREADS>
 __device__ __forceinline__ void block_reduce_store(double2 (&v)[NV], double2* __restrict__ dst, int nvalid) {
@@ -454,6 +477,60 @@ __global__ void resolvent_gj_kernel(const double2* __restrict__ H, const double*
     __syncthreads();
     if (mode == 0)
         for (int w = threadIdx.x; w < nw; w += blockDim.x) outp[(long)blockIdx.x * nw + w] = sAcc[w];
+}
+
+// Matrix-valued Green's function sum: partial[(cta*nw + w)*n*n + e] = sum over this CTA's nodes of wnode * [(z_w - H(k) - Sigma_w)^-1]_e
+// (the docs' gloc_integrand returns inv(...), docs/src/examples.md:20,90).  grid = (node chunks, nw); one warp per node with
+// the pivoted Gauss-Jordan inverse in its shared workspace and a private n x n accumulator, summed over warps in fixed order.
+// shared per warp: A[n*(n+1)] | idx[n] | acc[n*n]
+__global__ void resolvent_gj_matrix_kernel(const double2* __restrict__ H, const double* __restrict__ wnode, long nk, int n, int nw,
+                                           const double2* __restrict__ z, const double2* __restrict__ sigma, int kper,
+                                           double2* __restrict__ partial, int* __restrict__ errflag) {
+    extern __shared__ double2 gj_smem[];
+    const int nn = n * n, lda = n + 1;
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long per_warp = (long)n * lda + (n + 1) / 2 + 1 + nn;
+    double2* A = gj_smem + warp * per_warp;
+    int* idx = reinterpret_cast<int*>(A + n * lda);
+    double2* acc = A + n * lda + (n + 1) / 2 + 1;
+    const int w = blockIdx.y;
+    const double2 zz = z[w];
+    const double2* sg = sigma ? sigma + (long)w * nn : nullptr;
+    for (int e = lane; e < nn; e += 32) acc[e] = make_double2(0.0, 0.0);
+    const long k0 = (long)blockIdx.x * kper;
+    const long k1 = k0 + kper < nk ? k0 + kper : nk;
+    for (long k = k0 + warp; k < k1; k += nwarps) {
+        const double2* Hk = H + k * nn;
+        for (int e = lane; e < nn; e += 32) {
+            int i = e % n, j = e / n;
+            double2 h = Hk[e];
+            double2 v = make_double2(-h.x, -h.y);
+            if (sg) { v.x -= sg[e].x; v.y -= sg[e].y; }
+            if (i == j) { v.x += zz.x; v.y += zz.y; }
+            A[i + j * lda] = v;
+        }
+        __syncwarp();
+        bool singular = false;
+        double2 t = warp_gj_trace(A, idx, n, lda, lane, singular);
+        if (singular || !(isfinite(t.x) && isfinite(t.y))) { if (lane == 0) *errflag = 1; __syncwarp(); continue; }
+        __syncwarp();
+        const double wt = wnode ? wnode[k] : 1.0;
+        // A holds B = (P A0)^-1 and A0^-1[:, idx[m]] = B[:, m]
+        for (int e = lane; e < nn; e += 32) {
+            int i = e % n, m = e / n;
+            double2 b = A[i + m * lda];
+            double2* dst = acc + i + idx[m] * n;
+            dst->x += wt * b.x; dst->y += wt * b.y;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    double2* out = partial + ((long)blockIdx.x * nw + w) * nn;
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+        double2 sacc = make_double2(0.0, 0.0);
+        for (int wp = 0; wp < nwarps; wp++) { double2 v = gj_smem[wp * per_warp + n * lda + (n + 1) / 2 + 1 + e]; sacc.x += v.x; sacc.y += v.y; }
+        out[e] = sacc;
+    }
 }
 
 // tr H(k) weighted partial sums from a materialised H (fkind 1 for norb > 3)

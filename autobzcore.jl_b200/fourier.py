@@ -83,6 +83,7 @@ class _NativeIntegrand:
     """Base of the integrands whose arithmetic runs on the device."""
     fkind = _lib.F_RESOLVENT_TRACE
     is_eig = False
+    is_matrix = False
 
     def post(self, y, bound=None):
         """map the device value(s) to the integrand's value (vectorised)"""
@@ -118,6 +119,18 @@ class TrGlocIntegrand(_NativeIntegrand):
             z = z - complex(sigma)
             sigma = None
         return z, sigma
+
+
+class GlocIntegrand(TrGlocIntegrand):
+    """gloc_integrand(h_k; eta, omega) = inv(complex(omega, eta) I - h_k.s) (docs/src/examples.md:20,90): the matrix-valued
+    local Green's function.  PTR / AutoPTR sums run on the device (abz_rule_resolvent_matrix_sum).  Its SymRep is UnknownRep
+    unless `symmetrize` is given: on an IBZ the reference then returns the IBZ integral as is (src/brillouin.jl:107);
+    symmetrize(bz, G) -> G_FBZ lets the caller supply the representation, e.g. sum_S S G S^H."""
+    is_matrix = True
+    vkind = None
+
+    def __init__(self, symmetrize=None):
+        self.symmetrize = symmetrize
 
 
 class DOSIntegrand(TrGlocIntegrand):
@@ -167,6 +180,7 @@ class EigenIntegrand(_NativeIntegrand):
 # ready-made instances named as in the reference's examples
 dos_integrand = DOSIntegrand()
 gloc_trace_integrand = TrGlocIntegrand()
+gloc_integrand = GlocIntegrand()
 
 
 class FourierIntegrand:

@@ -94,6 +94,11 @@ def _norm(x):
     return float(np.linalg.norm(np.atleast_1d(x)))
 
 
+def _alg_norm(salg):
+    """the algorithm's norm; the default `abs` stands for LinearAlgebra.norm (Frobenius on matrix-valued integrals)"""
+    return _norm if salg.norm is abs else salg.norm
+
+
 # ---------------------------------------------------------------------------------------------------
 # parameters (MixedParameters, src/parameters.jl:11-35): ((args...), {kws...})
 def _params(p):
@@ -140,8 +145,16 @@ class _BoundIntegrand:
             for i, b in enumerate(self.bound):
                 if b[1] is not None:
                     sig[:, :, i] = np.asarray(b[1], dtype=np.complex128).reshape(n, n)
+        if f.f.is_matrix:
+            return list(rule.resolvent_matrix_sum(zs, sig))
         y = rule.resolvent_sum(zs, sig, _lib.F_RESOLVENT_TRACE)
         return list(y)
+
+
+WARN_UNKNOWN_SYMMETRY = ("A symmetric BZ was used with an integrand whose symmetry representation is unknown.\n"
+                         "For correctness, the calculation will be repeated on the full BZ.\n"
+                         "However, it is better either to integrate without symmetries or to use symmetries by extending "
+                         "SymRep for your type.")     # src/brillouin.jl:332-336
 
 
 def _rule_apply(rule, bf, shard, ndim):
@@ -163,6 +176,13 @@ def _rule_apply(rule, bf, shard, ndim):
         arr = arr.astype(np.float64)
     arr = shard.allreduce(arr)
     vals = arr / npt_d
+    if bf.native and not bf.is_eig and bf.f.f.is_matrix:
+        # matrix-valued: the rule output is sum_i w_i f_i vol/(npt^d nsyms); the integrand's SymRep maps it to the FBZ
+        # (symmetrize(f, bz, x), src/brillouin.jl:86-107,127-130)
+        nsym = getattr(rule, "nsyms", 1)
+        if nsym > 1:
+            return [bf.f.f.symmetrize(bf.bz, v / nsym) for v in vals]
+        return list(vals)
     if bf.native and not bf.is_eig:
         vals = bf.f.f.post(vals, None)
     return list(vals)
@@ -271,7 +291,18 @@ def _do_solve(cache, ps):
     maxiters = kws.get("maxiters", 2 ** 62)
     on_bz = j is not None
     bf = _BoundIntegrand(cache.f, ps)
+    bf.bz = cache.dom
     shard = cache.shard
+    if bf.native and not bf.is_eig and cache.f.f.is_matrix:
+        if isinstance(salg, NestedQuad):
+            raise TypeError("IAI on the device supports scalar-valued integrands; use PTR / AutoPTR for the matrix-valued gloc_integrand")
+        if on_bz and cache.dom.syms is not None and cache.f.f.symmetrize is None:
+            # do_solve_autobz (src/brillouin.jl:348-353): unknown SymRep + non-trivial value => repeat on the full BZ
+            import warnings
+            warnings.warn(WARN_UNKNOWN_SYMMETRY)
+            fbz = SymmetricBZ(cache.dom.A, cache.dom.B, CubicLimits([0.0] * ndim, [1.0] * ndim), None)
+            sub = init(IntegralProblem(cache.f, fbz, cache.p), cache.alg, backend=cache.backend, shard=cache.shard, **cache.kwargs)
+            return _do_solve(sub, ps)
     if isinstance(salg, MonkhorstPack):
         # do_solve_autobz (src/brillouin.jl:337-355): sol = rule(f) (scale vol/(npt^d nsyms)); val = j*nsyms*sol
         rule = cache.cacheval["rule"]
@@ -284,7 +315,9 @@ def _do_solve(cache, ps):
         atol = None if abstol is None else abstol / sc     # src/brillouin.jl:433 (no nsyms: rule output is symmetrised)
         sols = []
         for p in ps:
-            val, err, ne = _autosymptr(cache, _BoundIntegrand(cache.f, [p]), salg, atol, reltol, maxiters, ndim)
+            b1 = _BoundIntegrand(cache.f, [p])
+            b1.bz = cache.dom
+            val, err, ne = _autosymptr(cache, b1, salg, atol, reltol, maxiters, ndim)
             sols.append(IntegralSolution(val * sc, err * sc, True, ne if counter else -1))
         return sols
     if isinstance(salg, NestedQuad):
@@ -398,14 +431,15 @@ def _autosymptr(cache, bf, salg, atol, reltol, maxevals, ndim):
     r2 = rule_at(1)
     int2 = apply(r2)
     numevals += len(r2)
-    err = salg.norm(int1 - int2)
+    norm = _alg_norm(salg)
+    err = norm(int1 - int2)
     i = 1
-    while not (err <= max(rtol_ * salg.norm(int2), atol_)) and numevals < maxevals and np.isfinite(err):
+    while not (err <= max(rtol_ * norm(int2), atol_)) and numevals < maxevals and np.isfinite(err):
         i += 1
         r = rule_at(i)
         int1, int2 = int2, apply(r)
         numevals += len(r)
-        err = salg.norm(int1 - int2)
+        err = norm(int1 - int2)
     # keep the `keepmost` most refined rules for the next parameter (src/algorithms.jl:429 keepmost)
     keep = max(1, salg.keepmost)
     used = rules[: i + 1]

@@ -132,6 +132,47 @@ def cpu_sample(threads=None, target_s=15.0):
                       f"(C/OpenMP restatement of the AutoBZCore 0.3.8 path, not Julia)"}, t
 
 
+def other_configs(ctx):
+    """The other BASELINE.json configs (C2, C3, C5) through the public API on this GPU, a few seconds in total; reported
+    beside the headline under "other_configs" (parity for them lives in tests/, CPU baselines in tools/run_configs.py)."""
+    import autobz_b200 as ab
+    out = []
+    d = np.load(os.path.join(ROOT, "tests", "golden", "svo_hr.npz"))
+    Hs, los, A = np.asfortranarray(d["H_R"]), tuple(int(x) for x in d["lo"]), d["A"]
+    fs = ab.FourierSeries(Hs, period=1.0, lo=los, norb=3)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), A)
+
+    def best(fn, reps=3):
+        t_best, r = 1e30, None
+        for _ in range(reps):
+            t = time.perf_counter(); r = fn(); t_best = min(t_best, time.perf_counter() - t)
+        return r, t_best
+
+    f2 = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=1e-2)
+    solver = ab.IntegralSolver(f2, ibz, ab.PTR(npt=400))
+    ws = [{"omega": w} for w in np.linspace(11.0, 14.0, 64)]
+    ab.batchsolve(solver, ws[:2])
+    _, t = best(lambda: ab.batchsolve(solver, ws))
+    nn = len(solver.cache.cacheval["rule"])
+    out.append({"config": "C2 SrVO3 Green's-function trace, PTR npt=400 on CubicSymIBZ, 64 freqs, eta=1e-2", "irreducible_kpoints": nn,
+                "ms": 1e3 * t, "kpoints_per_s": nn / t, "k_omega_per_s": 64 * nn / t})
+    sol, t = best(lambda: ab.solve(ab.IntegralProblem(f2, ibz, {"omega": 12.5}), ab.EvalCounter(ab.AutoPTR(a=1e-2, nmin=50, nmax=1000)), abstol=1e-3), 2)
+    out.append({"config": "C2 SrVO3 AutoPTR(a=eta=1e-2) on CubicSymIBZ, omega=12.5, abstol=1e-3 (rule construction included)",
+                "numevals": sol.numevals, "ms": 1e3 * t, "kpoints_per_s": sol.numevals / t})
+    f3 = ab.FourierIntegrand(ab.dos_integrand, fs, 1e-4)
+    sol, t = best(lambda: ab.solve(ab.IntegralProblem(f3, ibz, 12.0), ab.EvalCounter(ab.IAI()), abstol=1e-3), 2)
+    out.append({"config": "C3 SrVO3 DOS via IAI, eta=1e-4, omega=12.0, abstol=1e-3", "numevals": sol.numevals, "s": t, "evals_per_s": sol.numevals / t})
+    H5, lo5 = ab.synthetic.wannier_hamiltonian(64, 4, cubic=True)
+    f5 = ab.FourierIntegrand(ab.EigenIntegrand("fermi_energy"), ab.FourierSeries(H5, period=1.0, lo=lo5, norb=64), 0.0, 0.5)
+    cache = ab.init(ab.IntegralProblem(f5, ab.load_bz(ab.CubicSymIBZ(), 2 * np.pi * np.eye(3))), ab.PTR(npt=96))
+    ab.solve_(cache)
+    _, t = best(lambda: ab.solve_(cache))
+    nn = len(cache.cacheval["rule"])
+    out.append({"config": "C5 norb=64 band-energy integrand (Hermitian eigenvalues) on CubicSymIBZ, PTR npt=96", "irreducible_kpoints": nn,
+                "ms": 1e3 * t, "kpoints_per_s": nn / t})
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -162,6 +203,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--algo", type=int, default=0, help="resolvent algorithm: 0 auto, 1 generic, 2 DMMA")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -277,6 +319,12 @@ def main():
         cb = None
         if not args.no_cpu_baseline:
             cb, _ = cpu_sample(target_s=args.ref_seconds)
+        others = None
+        if world == 1 and not args.no_other_configs:
+            try:
+                others = other_configs(ctx)
+            except Exception as e:      # never lose the headline line to a secondary measurement
+                others = [{"error": repr(e)}]
         line = {"metric": METRIC, "value": value, "unit": "k-points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
@@ -288,7 +336,7 @@ def main():
                 "roofline": roof, "cpu_baseline": cb,
                 "e2e": {"value": e2e_val, "unit": "k-points/s", "h2d_bytes_per_step": int(H.nbytes + z.nbytes), "d2h_bytes_per_step": int(NW * 16),
                         "ms_per_step": 1e3 * t_e2e_max / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks,
+                "gpu_launches": int(launches), "clocks": clocks, "other_configs": others,
                 "check": {"G_first": [float(g[0].real), float(g[0].imag)]}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -117,6 +117,11 @@ int32_t abz_rule_copy_out(abz_ctx* ctx, abz_rule_t r, double* Hk, double* kfrac,
  * evaluates chunk by chunk (fused; nothing of size nnodes*n^2 touches HBM for norb<=4). */
 int32_t abz_rule_resolvent_sum(abz_ctx* ctx, abz_rule_t r, int32_t fkind, int32_t nw, const double* z,
                                const double* sigma, double scale, double* out);
+/* matrix-valued integrand gloc_integrand(h_k; eta, omega) = inv(complex(omega, eta) I - h_k.s) (docs/src/examples.md:20,90):
+ * out = ComplexF64[n,n,nw], out[:,:,w] = scale * sum_i w_i (z_w I - H(k_i) - Sigma_w)^-1 (pivoted Gauss-Jordan inverse).
+ * On an IBZ the caller symmetrises the result with its SymRep (src/brillouin.jl:86-107; UnknownRep leaves it as is). */
+int32_t abz_rule_resolvent_matrix_sum(abz_ctx* ctx, abz_rule_t r, int32_t nw, const double* z, const double* sigma, double scale,
+                                      double* out);
 /* out[0] = scale * sum_i w_i g(eigvals(H(k_i))), kind = ABZ_EIG_* */
 int32_t abz_rule_eig_sum(abz_ctx* ctx, abz_rule_t r, int32_t kind, const double* params, double scale, double* out);
 /* all eigenvalues, Float64[n, nnodes] ascending per node (GGR data pass, src/dos_ggr.jl:14-44) */

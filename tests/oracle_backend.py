@@ -23,6 +23,7 @@ class OracleRule:
     def __init__(self, series, ndim, npt, syms, rank=0, nranks=1):
         self.fs, self.so, self.ndim, self.npt = series, _oseries(series), ndim, int(npt)
         self._syms = syms
+        self.nsyms = 1 if syms is None else len(syms)
         if ndim == 3:
             if syms is None:
                 i3, i2, i1 = np.meshgrid(np.arange(npt), np.arange(npt), np.arange(npt), indexing="ij")
@@ -72,6 +73,17 @@ class OracleRule:
             return np.array([np.sum(self.w * np.trace(H, axis1=0, axis2=1))])
         y = orc.resolvent_trace_batch(H, z, sigma)
         return (self.w[:, None] * y).sum(axis=0)
+
+    def resolvent_matrix_sum(self, z, sigma):
+        H = np.moveaxis(self._Hk(), 2, 0)
+        n = H.shape[1]
+        zs = np.atleast_1d(z)
+        out = np.zeros((zs.size, n, n), dtype=complex)
+        for w, zz in enumerate(zs):
+            sg = 0 if sigma is None else np.asarray(sigma).reshape(n, n, zs.size)[:, :, w]
+            if self.nnodes:
+                out[w] = np.tensordot(self.w, np.linalg.inv(zz * np.eye(n) - H - sg), axes=(0, 0))
+        return out
 
     def eig_sum(self, kind, params):
         ev = orc.eigvals_batch(self._Hk())

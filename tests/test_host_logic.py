@@ -227,3 +227,35 @@ def test_generic_integrand_sees_full_k_points_in_iai():
     f = ab.FourierIntegrand(lambda x: x.x[0] + 2 * x.x[1] + 4 * x.x[2] + 0 * x.s.real, s)
     sol = ab.solve(ab.IntegralProblem(f, bz), ab.EvalCounter(ab.IAI()), abstol=1e-10, backend=OracleBackend())
     assert abs(sol.u - 3.5) < 1e-12 and sol.numevals == 15 ** 3 and isinstance(sol.u, float)
+
+
+def test_matrix_valued_gloc_integrand_and_symrep(orc):
+    """docs/src/examples.md:20,90: gloc_integrand returns inv(complex(omega, eta) I - h_k.s), a matrix.  On a symmetric BZ the
+    reference symmetrises with the integrand's SymRep (src/brillouin.jl:86-107); with UnknownRep it warns and repeats the
+    calculation on the full BZ (src/brillouin.jl:348-353)."""
+    n = 3
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 1, cubic=True)      # orbital action trivial: G(Sk) = G(k)
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=n)
+    be = OracleBackend()
+    fbz, ibz = ab.load_bz(ab.FBZ(), np.eye(3)), ab.load_bz(ab.CubicSymIBZ(), np.eye(3))
+    p = {"omega": 0.3}
+    ref = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_integrand, fs, eta=0.4), fbz, p), ab.PTR(npt=8), backend=be).u
+    assert ref.shape == (n, n)
+    tr = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=0.4), fbz, p), ab.PTR(npt=8), backend=be).u
+    assert abs(np.trace(ref) - tr) < 1e-12 * abs(tr)
+    # a SymRep for which the representation is trivial: symmetrize(bz, x) = nsyms x
+    sym = ab.GlocIntegrand(symmetrize=lambda bz, x: bz.nsyms * x)
+    got = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(sym, fs, eta=0.4), ibz, p), ab.PTR(npt=8), backend=be).u
+    assert np.max(np.abs(got - ref)) < 1e-12 * np.max(np.abs(ref))
+    # UnknownRep: warning + full-BZ recomputation
+    with pytest.warns(UserWarning, match="symmetry representation is unknown"):
+        got = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_integrand, fs, eta=0.4), ibz, p), ab.PTR(npt=8), backend=be).u
+    assert np.max(np.abs(got - ref)) < 1e-13 * np.max(np.abs(ref))
+    # AutoPTR converges in the Frobenius norm; batchsolve returns one matrix per frequency
+    sol = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(sym, fs, eta=0.4), ibz, p), ab.EvalCounter(ab.AutoPTR(nmin=4, a=0.4)), abstol=1e-6, backend=be)
+    assert sol.u.shape == (n, n) and sol.resid <= 1e-6 and sol.numevals > 0
+    solver = ab.IntegralSolver(ab.FourierIntegrand(ab.gloc_integrand, fs, eta=0.4), fbz, ab.PTR(npt=6), backend=be)
+    G = ab.batchsolve(solver, [{"omega": w} for w in (0.0, 0.3)])
+    assert G.shape == (2, n, n)
+    with pytest.raises(TypeError):
+        ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_integrand, fs, eta=0.4), fbz, p), ab.IAI(), backend=be)
