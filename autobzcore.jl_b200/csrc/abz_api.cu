@@ -335,6 +335,39 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
         // sums over a materialised H: handled by the caller through small_fused_kernel<_, true>
         return fail(ctx, ABZ_E_INVALID, "internal: small-norb sums go through run_small_fused");
     }
+    // frequency sweep from one tridiagonalisation per k (opt-in: Hermitian H(k), scalar self-energy folded into z)
+    if (ctx->resolvent_algo == 3 && !sigma && n <= EIG_MAXN && !ctx->force_generic) {
+        CU(ctx, ctx->eig_d.reserve((size_t)nk * n * sizeof(double)));
+        CU(ctx, ctx->eig_e.reserve((size_t)nk * n * sizeof(double)));
+        static bool attr_set_t = false;
+        if (!attr_set_t) {
+            cudaFuncSetAttribute(eig_tridiag_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaFuncSetAttribute(eig_tridiag_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            attr_set_t = true;
+        }
+        const int RP = n > 32 ? 64 : 32;
+        const size_t smem_t = ((size_t)n * n + 5 * RP) * sizeof(double2);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (4 * RP), (220 * 1024) / (smem_t + 1024)));
+        const long ncta_t = std::min<long>(nk, sm * per_sm);
+        if (RP == 32) eig_tridiag_kernel<32><<<(unsigned)ncta_t, 128, smem_t, ctx->stream>>>(H, nk, n, ctx->eig_d.as<double>(), ctx->eig_e.as<double>());
+        else eig_tridiag_kernel<64><<<(unsigned)ncta_t, 256, smem_t, ctx->stream>>>(H, nk, n, ctx->eig_d.as<double>(), ctx->eig_e.as<double>());
+        LAUNCH_CHECK(ctx, "eig_tridiag_kernel");
+        const long ncx = (nk + TS_THREADS - 1) / TS_THREADS;
+        dim3 grid((unsigned)ncx, (unsigned)((nw + TS_WCH - 1) / TS_WCH));
+        if (mode == 0) {
+            CU(ctx, ctx->partial.reserve((size_t)ncx * nw * sizeof(double2)));
+            tridiag_resolvent_kernel<<<grid, TS_THREADS, 0, ctx->stream>>>(ctx->eig_d.as<double>(), ctx->eig_e.as<double>(), wnode, nk, n, nw, z, 0,
+                                                                          ctx->partial.as<double2>(), ef);
+            LAUNCH_CHECK(ctx, "tridiag_resolvent_kernel");
+            reduce_partials_kernel<<<nw, 256, 0, ctx->stream>>>(ctx->partial.as<double2>(), ncx, nw, 1.0, ctx->acc.as<double2>());
+            LAUNCH_CHECK(ctx, "reduce_partials_kernel");
+        } else {
+            tridiag_resolvent_kernel<<<grid, TS_THREADS, 0, ctx->stream>>>(ctx->eig_d.as<double>(), ctx->eig_e.as<double>(), wnode, nk, n, nw, z, 1,
+                                                                          yout, ef);
+            LAUNCH_CHECK(ctx, "tridiag_resolvent_kernel");
+        }
+        return ABZ_OK;
+    }
     // DMMA register-resident fast path (norb <= 32; unpivoted block elimination with growth monitoring)
     bool use_mma = (ctx->resolvent_algo != 1) && !ctx->force_generic && mma_resolvent_supported(n);
     if (use_mma) {

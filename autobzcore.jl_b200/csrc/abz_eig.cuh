@@ -512,6 +512,66 @@ eig_tql_kernel(const double* __restrict__ din, const double* __restrict__ ein, c
     }
 }
 
+// ---- K3-sweep: tr[(z_w - H(k))^-1] for MANY frequencies from ONE tridiagonalisation per k --------------------------
+// For Hermitian H(k) and a scalar self-energy (folded into z) the trace of the resolvent is invariant under the
+// unitary reduction T = Q^H H Q of eig_tridiag_kernel, and for the real symmetric tridiagonal T (diagonal d, off-diagonal
+// e) it is the logarithmic derivative of the characteristic polynomial, p_n'(z)/p_n(z) = sum_k r_k'/r_k with the
+// continued fraction r_k = (z - d_k) - e_{k-1}^2 / r_{k-1}, r_k' = 1 + e_{k-1}^2 r_{k-1}' / r_{k-1}^2 (Im r_k >= Im z > 0:
+// no small divisors).  O(n) per frequency instead of the O(n^3) inverse: the frequency sweep of batchsolve
+// (src/interfaces.jl:199-243) costs one O(n^3) reduction per k-point.  Thread = one k, loops over a chunk of frequencies.
+// mode 0: partial[blockIdx.x*nw + w] = sum over this CTA's nodes of wnode * trace;  mode 1: y[k*nw + w] = trace
+constexpr int TS_THREADS = 128;
+constexpr int TS_WCH = 16;
+__global__ void __launch_bounds__(TS_THREADS)
+tridiag_resolvent_kernel(const double* __restrict__ din, const double* __restrict__ ein, const double* __restrict__ wnode, long nk,
+                         int n, int nw, const double2* __restrict__ z, int mode, double2* __restrict__ outp, int* __restrict__ errflag) {
+    __shared__ double2 acc[TS_THREADS / 32][TS_WCH];
+    const long k = (long)blockIdx.x * TS_THREADS + threadIdx.x;
+    const int w0 = blockIdx.y * TS_WCH;
+    const int nwc = min(TS_WCH, nw - w0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double d[EIG_MAXN], e2[EIG_MAXN];
+    const bool valid = k < nk;
+    if (valid)
+        for (int i = 0; i < n; i++) { d[i] = din[(long)i * nk + k]; const double ev = ein[(long)i * nk + k]; e2[i] = ev * ev; }
+    const double wt = valid ? (wnode ? wnode[k] : 1.0) : 0.0;
+    for (int wi = 0; wi < nwc; wi++) {
+        double2 t = make_double2(0.0, 0.0);
+        if (valid) {
+            const double2 zz = z[w0 + wi];
+            double2 r = make_double2(zz.x - d[0], zz.y);     // r_1
+            double2 rp = make_double2(1.0, 0.0);              // r_1'
+            for (int i = 1; i < n; i++) {
+                const double2 inv = crecip(r);
+                const double2 q = cmul(rp, inv);              // r_{i}'/r_{i}
+                t.x += q.x; t.y += q.y;
+                const double2 u = make_double2(e2[i - 1] * inv.x, e2[i - 1] * inv.y);
+                r = make_double2(zz.x - d[i] - u.x, zz.y - u.y);
+                const double2 uq = cmul(u, q);
+                rp = make_double2(1.0 + uq.x, uq.y);
+            }
+            const double2 q = cmul(rp, crecip(r));
+            t.x += q.x; t.y += q.y;
+            if (!(isfinite(t.x) && isfinite(t.y))) *errflag = 1;
+        }
+        if (mode == 1) {
+            if (valid) outp[k * nw + w0 + wi] = t;
+        } else {
+            double sx = warp_sum(wt * t.x), sy = warp_sum(wt * t.y);
+            if (lane == 0) acc[warp][wi] = make_double2(sx, sy);
+        }
+    }
+    if (mode == 0) {
+        __syncthreads();
+        if (threadIdx.x < nwc) {
+            double2 a = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int wp = 0; wp < TS_THREADS / 32; wp++) { a.x += acc[wp][threadIdx.x].x; a.y += acc[wp][threadIdx.x].y; }
+            outp[(long)blockIdx.x * nw + w0 + threadIdx.x] = a;
+        }
+    }
+}
+
 // deterministic reduction of real partials: acc[0] += scale * sum_c partial[c]
 __global__ void __launch_bounds__(256) reduce_real_kernel(const double* __restrict__ partial, long n, double scale, double* __restrict__ acc) {
     __shared__ double sx[256];

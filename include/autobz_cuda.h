@@ -52,7 +52,9 @@ typedef uint64_t abz_nest_t;    /* IAI arena: contracted series for nested panel
 #define ABZ_EIG_GAUSS_DOS 3     /* sum_n exp(-((e_n-w)/s)^2)/(s sqrt(pi)), params = {w, s} */
 
 /* resolvent algorithm selection (abz_ctx_set_option ABZ_OPT_RESOLVENT_ALGO) */
-#define ABZ_OPT_RESOLVENT_ALGO 1   /* 0 auto, 1 generic pivoted Gauss-Jordan, 2 register/DMMA fast path */
+#define ABZ_OPT_RESOLVENT_ALGO 1   /* 0 auto, 1 generic pivoted Gauss-Jordan, 2 register/DMMA fast path, 3 frequency sweep from one
+                                    * Householder tridiagonalisation per k: tr (z-H)^-1 = p'(z)/p(z), O(n) per frequency - opt-in, needs
+                                    * Hermitian H(k) and a scalar (or no) self-energy; a matrix Sigma falls back to 0 */
 #define ABZ_OPT_MEM_BUDGET_MB 2    /* device workspace budget for streamed chunks (default 4096) */
 #define ABZ_OPT_FUSED_SMALL 3      /* 1 (default): fuse evaluation+resolvent for norb<=4 */
 #define ABZ_OPT_EIG_ALGO 4         /* 0 (default): Householder tridiagonalisation + implicit QL; 1: cyclic two-sided Jacobi */

@@ -469,3 +469,31 @@ def test_matrix_valued_green_function_sum(ctx, orc, n, N):
     b = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.GlocIntegrand(symmetrize=lambda bz, x: bz.nsyms * x), fs, eta=0.25),
                                     ab.load_bz(ab.CubicSymIBZ(), np.eye(3)), p), ab.PTR(npt=N)).u
     assert rel(b, a) < 1e-11
+
+
+@pytest.mark.parametrize("n,rmax,N", [(4, 1, 6), (7, 2, 5), (32, 1, 5), (33, 1, 4), (64, 1, 3)])
+def test_frequency_sweep_from_one_tridiagonalisation(ctx, orc, n, rmax, N):
+    """ABZ_OPT_RESOLVENT_ALGO = 3: tr (z - H(k))^-1 for all frequencies from one Householder reduction per k
+    (p'(z)/p(z) of the tridiagonal form) against the oracle's pivoted-LU resolvent, sums and per-node values; a matrix
+    self-energy silently takes the LU path."""
+    H, lo = ab.synthetic.wannier_hamiltonian(n, rmax)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    So = orc.Series(H, lo)
+    ext = ab.synthetic.band_extent(H)
+    z = np.linspace(-0.3 * ext, 0.3 * ext, 37) + 1j * 0.01 * ext
+    R = L.DeviceRule(ctx, S, N)
+    ref = orc.ptr_sum(So, N, z)
+    rng = np.random.default_rng(n)
+    sig = 0.1 * (rng.standard_normal((n, n, z.size)) + 1j * rng.standard_normal((n, n, z.size)))
+    kp = rng.random((11, 3))
+    ctx.set_option(L.OPT_RESOLVENT_ALGO, 3)
+    try:
+        assert rel(R.resolvent_sum(z, scale=1 / N ** 3), ref) < 1e-11
+        R.materialize()
+        a = R.resolvent_sum(z, scale=1 / N ** 3)
+        assert rel(a, ref) < 1e-11 and np.array_equal(a, R.resolvent_sum(z, scale=1 / N ** 3))
+        assert rel(R.resolvent_sum(z, sigma=sig, scale=1 / N ** 3), orc.ptr_sum(So, N, z, sigma=sig)) < 1e-11
+        y = S.points_resolvent(kp, z)
+    finally:
+        ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
+    assert rel(y, orc.resolvent_trace_batch(orc.eval_points(So, kp), z)) < 1e-11
