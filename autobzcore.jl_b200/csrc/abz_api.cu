@@ -286,6 +286,45 @@ int check_errflag(abz_ctx* ctx, const char* what) {
     return ABZ_OK;
 }
 
+// Householder tridiagonalisation of nk materialised matrices into ctx->eig_d / eig_e (structure of arrays):
+// n <= 32: one warp per matrix with the rows in registers; else one CTA per matrix in shared memory
+static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n) {
+    CU(ctx, ctx->eig_d.reserve((size_t)nk * n * sizeof(double)));
+    CU(ctx, ctx->eig_e.reserve((size_t)nk * n * sizeof(double)));
+    double* dd = ctx->eig_d.as<double>(); double* ee = ctx->eig_e.as<double>();
+    if (n <= 32 && ctx->eig_algo != 2) {
+        const long nblk = std::min<long>((nk + 3) / 4, (long)ctx->sm_count * 16);
+        static int minb = 0;      // resident CTAs per SM the compiler budgets registers for (2: 255 registers, 3: 168 + a few spills)
+        if (!minb) { const char* e = getenv("ABZ_TRIDIAG_MINB"); minb = (e && atoi(e) == 2) ? 2 : 3; }
+#define TRIDIAG_WARP(NX)                                                                                    \
+    do {                                                                                                    \
+        if (minb == 2) eig_tridiag_warp_kernel<NX, 2><<<(unsigned)nblk, 128, 0, ctx->stream>>>(H, nk, n, dd, ee); \
+        else eig_tridiag_warp_kernel<NX, 3><<<(unsigned)nblk, 128, 0, ctx->stream>>>(H, nk, n, dd, ee);           \
+    } while (0)
+        if (n <= 8) TRIDIAG_WARP(8);
+        else if (n <= 16) TRIDIAG_WARP(16);
+        else if (n <= 24) TRIDIAG_WARP(24);
+        else TRIDIAG_WARP(32);
+#undef TRIDIAG_WARP
+        LAUNCH_CHECK(ctx, "eig_tridiag_warp_kernel");
+        return ABZ_OK;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(eig_tridiag_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(eig_tridiag_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set = true;
+    }
+    const int RP = n > 32 ? 64 : 32;
+    const size_t smem = ((size_t)n * n + 5 * RP) * sizeof(double2);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (4 * RP), (220 * 1024) / (smem + 1024)));
+    const long ncta = std::min<long>(nk, (long)ctx->sm_count * per_sm);
+    if (RP == 32) eig_tridiag_kernel<32><<<(unsigned)ncta, 128, smem, ctx->stream>>>(H, nk, n, dd, ee);
+    else eig_tridiag_kernel<64><<<(unsigned)ncta, 256, smem, ctx->stream>>>(H, nk, n, dd, ee);
+    LAUNCH_CHECK(ctx, "eig_tridiag_kernel");
+    return ABZ_OK;
+}
+
 int upload_params(abz_ctx* ctx, int n, int nw, const double* z, const double* sigma) {
     CU(ctx, ctx->zbuf.reserve((size_t)std::max(nw, 1) * sizeof(double2)));
     if (z) CU(ctx, cudaMemcpyAsync(ctx->zbuf.p, z, (size_t)nw * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
@@ -337,21 +376,7 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
     }
     // frequency sweep from one tridiagonalisation per k (opt-in: Hermitian H(k), scalar self-energy folded into z)
     if (ctx->resolvent_algo == 3 && !sigma && n <= EIG_MAXN && !ctx->force_generic) {
-        CU(ctx, ctx->eig_d.reserve((size_t)nk * n * sizeof(double)));
-        CU(ctx, ctx->eig_e.reserve((size_t)nk * n * sizeof(double)));
-        static bool attr_set_t = false;
-        if (!attr_set_t) {
-            cudaFuncSetAttribute(eig_tridiag_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            cudaFuncSetAttribute(eig_tridiag_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            attr_set_t = true;
-        }
-        const int RP = n > 32 ? 64 : 32;
-        const size_t smem_t = ((size_t)n * n + 5 * RP) * sizeof(double2);
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (4 * RP), (220 * 1024) / (smem_t + 1024)));
-        const long ncta_t = std::min<long>(nk, sm * per_sm);
-        if (RP == 32) eig_tridiag_kernel<32><<<(unsigned)ncta_t, 128, smem_t, ctx->stream>>>(H, nk, n, ctx->eig_d.as<double>(), ctx->eig_e.as<double>());
-        else eig_tridiag_kernel<64><<<(unsigned)ncta_t, 256, smem_t, ctx->stream>>>(H, nk, n, ctx->eig_d.as<double>(), ctx->eig_e.as<double>());
-        LAUNCH_CHECK(ctx, "eig_tridiag_kernel");
+        { int rct = launch_tridiag(ctx, H, nk, n); if (rct) return rct; }
         const long ncx = (nk + TS_THREADS - 1) / TS_THREADS;
         dim3 grid((unsigned)ncx, (unsigned)((nw + TS_WCH - 1) / TS_WCH));
         if (mode == 0) {
@@ -1062,21 +1087,7 @@ static int run_eig(abz_ctx* ctx, const double2* H, const double* wnode, long nk,
                    double* evals, double* acc) {
     if (nk <= 0) return ABZ_OK;
     if (ctx->eig_algo == 1 || n > EIG_MAXN) return run_eig_jacobi(ctx, H, wnode, nk, n, mode, kind, p0, p1, evals, acc);
-    CU(ctx, ctx->eig_d.reserve((size_t)nk * n * sizeof(double)));
-    CU(ctx, ctx->eig_e.reserve((size_t)nk * n * sizeof(double)));
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(eig_tridiag_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaFuncSetAttribute(eig_tridiag_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
-    }
-    const int RP = n > 32 ? 64 : 32;
-    const size_t smem = ((size_t)n * n + 5 * RP) * sizeof(double2);
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (4 * RP), (220 * 1024) / (smem + 1024)));
-    const long ncta = std::min<long>(nk, (long)ctx->sm_count * per_sm);
-    if (RP == 32) eig_tridiag_kernel<32><<<(unsigned)ncta, 128, smem, ctx->stream>>>(H, nk, n, ctx->eig_d.as<double>(), ctx->eig_e.as<double>());
-    else eig_tridiag_kernel<64><<<(unsigned)ncta, 256, smem, ctx->stream>>>(H, nk, n, ctx->eig_d.as<double>(), ctx->eig_e.as<double>());
-    LAUNCH_CHECK(ctx, "eig_tridiag_kernel");
+    { int rct = launch_tridiag(ctx, H, nk, n); if (rct) return rct; }
     const long nblk = (nk + 31) / 32;
     if (mode == 0) CU(ctx, ctx->partial.reserve((size_t)nblk * sizeof(double)));
     eig_tql_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(ctx->eig_d.as<double>(), ctx->eig_e.as<double>(), wnode, nk, n, mode, kind, p0,

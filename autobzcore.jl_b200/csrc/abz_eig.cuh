@@ -446,6 +446,68 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
     }
 }
 
+// Register-resident variant for n <= 32: ONE WARP per matrix, lane i holds row i of the (zero-padded to N) matrix in
+// registers, the column loop fully unrolled so that every register index is static.  No block barriers: the Householder
+// vector v and the update vector w are broadcast through a per-warp shared-memory line (one LDS.128 per use), norms and
+// dot products are xor-shuffle trees.  Same arithmetic as eig_tridiag_kernel (same reflector, same update).
+template <int N, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+eig_tridiag_warp_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout) {
+    __shared__ double2 bc[4][2][32];      // per warp: v and w
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2* sv = bc[warp][0];
+    double2* sw = bc[warp][1];
+    for (long k = (long)blockIdx.x * 4 + warp; k < nk; k += (long)gridDim.x * 4) {
+        const double2* Hk = H + k * (long)n * n;
+        double2 a[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            a[j] = make_double2(0.0, 0.0);
+            if (lane < n && j < n) {
+                const double2 x = Hk[lane + (long)j * n], y = Hk[j + (long)lane * n];
+                a[j] = make_double2(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < N - 1; c++) {
+            const double2 x = a[c];                                       // my element of column c
+            double sig = (lane >= c + 2) ? fma(x.x, x.x, x.y * x.y) : 0.0;
+            sig = warp_sum(sig);
+            const double alr = __shfl_sync(0xffffffffu, x.x, c + 1), ali = __shfl_sync(0xffffffffu, x.y, c + 1);
+            const double aa = alr * alr + ali * ali;
+            const double ynorm = sqrt(sig + aa);
+            if (lane == c && c < n) { dout[(long)c * nk + k] = a[c].x; eout[(long)c * nk + k] = ynorm; }
+            if (sig == 0.0) continue;                                      // warp-uniform
+            const double absa = sqrt(aa);
+            const double2 ph = absa > 0.0 ? make_double2(alr / absa, ali / absa) : make_double2(1.0, 0.0);
+            const double tau = 1.0 / (ynorm * (ynorm + absa));
+            double2 v = make_double2(0.0, 0.0);
+            if (lane == c + 1) v = make_double2(alr + ph.x * ynorm, ali + ph.y * ynorm);
+            else if (lane > c + 1) v = x;
+            __syncwarp();
+            sv[lane] = v;
+            __syncwarp();
+            double2 p = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int j = c + 1; j < N; j++) p = cfma(p, a[j], sv[j]);
+            p.x *= tau; p.y *= tau;
+            if (lane <= c) p = make_double2(0.0, 0.0);
+            const double dot = warp_sum(v.x * p.x + v.y * p.y);
+            const double gam = 0.5 * tau * dot;
+            const double2 w = make_double2(p.x - gam * v.x, p.y - gam * v.y);
+            sw[lane] = w;
+            __syncwarp();
+#pragma unroll
+            for (int j = c + 1; j < N; j++) {
+                const double2 vj = sv[j], wj = sw[j];
+                a[j].x -= v.x * wj.x + v.y * wj.y + w.x * vj.x + w.y * vj.y;
+                a[j].y -= v.y * wj.x - v.x * wj.y + w.y * vj.x - w.x * vj.y;
+            }
+        }
+        if (lane == N - 1 && N - 1 < n) { dout[(long)(N - 1) * nk + k] = a[N - 1].x; eout[(long)(N - 1) * nk + k] = 0.0; }
+    }
+}
+
 // Stage B: eigenvalues of the real symmetric tridiagonal (d, e) by the implicit QL algorithm with Wilkinson shifts
 // (EISPACK imtql1 / "tqli" without vectors), one thread per matrix.  mode 0: partial[cta] = sum_k wnode_k sum_n g(e_n);
 // mode 1: evals[k*n + i] ascending.

@@ -57,7 +57,9 @@ typedef uint64_t abz_nest_t;    /* IAI arena: contracted series for nested panel
                                     * Hermitian H(k) and a scalar (or no) self-energy; a matrix Sigma falls back to 0 */
 #define ABZ_OPT_MEM_BUDGET_MB 2    /* device workspace budget for streamed chunks (default 4096) */
 #define ABZ_OPT_FUSED_SMALL 3      /* 1 (default): fuse evaluation+resolvent for norb<=4 */
-#define ABZ_OPT_EIG_ALGO 4         /* 0 (default): Householder tridiagonalisation + implicit QL; 1: cyclic two-sided Jacobi */
+#define ABZ_OPT_EIG_ALGO 4         /* 0 (default): Householder tridiagonalisation (warp-per-matrix in registers for norb <= 32,
+                                    * CTA-per-matrix in shared memory above) + implicit QL; 1: cyclic two-sided Jacobi;
+                                    * 2: as 0 but always the shared-memory tridiagonalisation (cross-check) */
 
 int32_t abz_version(void);
 const char* abz_last_error(const abz_ctx* ctx);  /* ctx may be NULL: last error of abz_ctx_create */

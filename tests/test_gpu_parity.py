@@ -497,3 +497,21 @@ def test_frequency_sweep_from_one_tridiagonalisation(ctx, orc, n, rmax, N):
     finally:
         ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
     assert rel(y, orc.resolvent_trace_batch(orc.eval_points(So, kp), z)) < 1e-11
+
+
+@pytest.mark.parametrize("n", [2, 5, 8, 9, 16, 23, 24, 31, 32])
+def test_register_resident_tridiagonalisation(ctx, n):
+    """norb <= 32: the warp-per-matrix register-resident Householder kernel (default) and the shared-memory kernel
+    (ABZ_OPT_EIG_ALGO = 2) give the same spectrum as LAPACK, including zero-padded sizes that are not multiples of 8"""
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 1)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    R = L.DeviceRule(ctx, S, 6)
+    Hk, _, _ = R.copy_out()
+    ref = np.linalg.eigvalsh(np.moveaxis(Hk, 2, 0))
+    ev = R.eigvals()
+    ctx.set_option(L.OPT_EIG_ALGO, 2)
+    try:
+        ev2 = R.eigvals()
+    finally:
+        ctx.set_option(L.OPT_EIG_ALGO, 0)
+    assert rel(ev, ref) < 1e-13 and rel(ev2, ref) < 1e-13
