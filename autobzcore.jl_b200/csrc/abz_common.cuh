@@ -40,6 +40,18 @@ __device__ __forceinline__ double2 crecip(double2 a) {
 }
 __device__ __forceinline__ double2 cdiv(double2 a, double2 b) { return cmul(a, crecip(b)); }
 
+// branch-free reciprocal: MUFU.RCP64H seed (~2^-20) + two Newton steps (keeps the whole elimination in one
+// basic block so that ptxas can interleave the DMMA chains with the latency-bound pivot steps)
+__device__ __forceinline__ double fast_rcp(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    const double e = fma(-d, x, 1.0);      // 1 - d x0
+    const double e2 = e * e;               // = 1 - d x1 up to rounding (in parallel with x1)
+    x = fma(x, e, x);                      // x1
+    x = fma(x, e2, x);                     // x2: relative error ~ e^4 (seed 2^-20 -> 2^-80)
+    return x;
+}
+
 // exp(2 pi i frac) with the argument reduced to [-1/2, 1/2]
 __device__ __forceinline__ double2 cis2pi(double frac) {
     frac -= rint(frac);

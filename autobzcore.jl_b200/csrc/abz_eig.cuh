@@ -365,9 +365,10 @@ template <int RP>
 __global__ void __launch_bounds__(4 * RP)
 eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout) {
     extern __shared__ double2 et_smem[];
-    double2* A = et_smem;            // [n*n], column-major, lda = n
-    double2* pb = A + (long)n * n;   // [4][RP] partial mat-vec sums
-    double2* wv = pb + 4 * RP;       // [RP]
+    constexpr int LDA = RP;            // compile-time leading dimension: column j starts at A + j*RP (a shift, no IMAD)
+    double2* A = et_smem;              // [n][LDA], column-major
+    double2* pb = A + (long)n * LDA;   // [4][RP] partial mat-vec sums
+    double2* wv = pb + 4 * RP;         // [RP]
     const int tid = threadIdx.x, i = tid % RP, q = tid / RP, lane = tid & 31, warp = tid >> 5;
     for (long k = blockIdx.x; k < nk; k += gridDim.x) {
         __syncthreads();
@@ -375,11 +376,11 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
         for (int e = tid; e < n * n; e += 4 * RP) {
             int r = e % n, j = e / n;
             double2 a = Hk[r + (long)j * n], b = Hk[j + (long)r * n];
-            A[r + j * n] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+            A[r + j * LDA] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
         }
         __syncthreads();
         for (int c = 0; c < n - 1; c++) {
-            const double2* col = A + (long)c * n;
+            const double2* col = A + c * LDA;
             // Householder vector of column c (every warp computes it redundantly: no block-level reduction needed)
             double sig = 0.0;
             for (int r = c + 2 + lane; r < n; r += 32) { double2 a = col[r]; sig = fma(a.x, a.x, fma(a.y, a.y, sig)); }
@@ -387,20 +388,22 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
             const double2 alpha = col[c + 1];
             const double aa = alpha.x * alpha.x + alpha.y * alpha.y;
             const double ynorm = sqrt(sig + aa);
-            if (tid == 0) { dout[(long)c * nk + k] = A[c + c * n].x; eout[(long)c * nk + k] = ynorm; }
+            if (tid == 0) { dout[(long)c * nk + k] = A[c + c * LDA].x; eout[(long)c * nk + k] = ynorm; }
             if (sig == 0.0) continue;               // column already tridiagonal (always true for c = n-2)
             const double absa = sqrt(aa);
             const double2 ph = absa > 0.0 ? make_double2(alpha.x / absa, alpha.y / absa) : make_double2(1.0, 0.0);
             const double2 v0 = make_double2(alpha.x + ph.x * ynorm, alpha.y + ph.y * ynorm);
             const double tau = 1.0 / (ynorm * (ynorm + absa));
             const bool active = (i > c && i < n);
-            // p = A22 v (partial over this thread's columns)
+            // p = A22 v (partial over this thread's columns j = c+1+q, c+5+q, ...; the j = c+1 term carries v0)
             double2 acc = make_double2(0.0, 0.0);
-            if (active)
-                for (int j = c + 1 + q; j < n; j += 4) {
-                    const double2 vj = (j == c + 1) ? v0 : col[j];
-                    acc = cfma(acc, A[i + j * n], vj);
-                }
+            if (active) {
+                int j = c + 1 + q;
+                const double2* Ap = A + i + j * LDA;
+                if (q == 0) { acc = cfma(acc, *Ap, v0); j += 4; Ap += 4 * LDA; }
+#pragma unroll 4
+                for (; j < n; j += 4, Ap += 4 * LDA) acc = cfma(acc, *Ap, col[j]);
+            }
             pb[q * RP + i] = acc;
             __syncthreads();
             // w = p - (tau/2)(v^H p) v, every warp redundantly; warp 0 publishes it
@@ -431,18 +434,28 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
             if (active) {
                 const double2 vi = (i == c + 1) ? v0 : col[i];
                 const double2 wi = wv[i];
-                for (int j = c + 1 + q; j < n; j += 4) {
-                    const double2 vj = (j == c + 1) ? v0 : col[j];
+                int j = c + 1 + q;
+                double2* Ap = A + i + j * LDA;
+                if (q == 0) {
                     const double2 wj = wv[j];
-                    double2 a = A[i + j * n];
+                    double2 a = *Ap;
+                    a.x -= vi.x * wj.x + vi.y * wj.y + wi.x * v0.x + wi.y * v0.y;
+                    a.y -= vi.y * wj.x - vi.x * wj.y + wi.y * v0.x - wi.x * v0.y;
+                    *Ap = a;
+                    j += 4; Ap += 4 * LDA;
+                }
+#pragma unroll 4
+                for (; j < n; j += 4, Ap += 4 * LDA) {
+                    const double2 vj = col[j], wj = wv[j];
+                    double2 a = *Ap;
                     a.x -= vi.x * wj.x + vi.y * wj.y + wi.x * vj.x + wi.y * vj.y;
                     a.y -= vi.y * wj.x - vi.x * wj.y + wi.y * vj.x - wi.x * vj.y;
-                    A[i + j * n] = a;
+                    *Ap = a;
                 }
             }
             __syncthreads();
         }
-        if (tid == 0) { dout[(long)(n - 1) * nk + k] = A[(n - 1) + (n - 1) * n].x; eout[(long)(n - 1) * nk + k] = 0.0; }
+        if (tid == 0) { dout[(long)(n - 1) * nk + k] = A[(n - 1) + (n - 1) * LDA].x; eout[(long)(n - 1) * nk + k] = 0.0; }
     }
 }
 
@@ -604,7 +617,9 @@ tridiag_resolvent_kernel(const double* __restrict__ din, const double* __restric
             double2 r = make_double2(zz.x - d[0], zz.y);     // r_1
             double2 rp = make_double2(1.0, 0.0);              // r_1'
             for (int i = 1; i < n; i++) {
-                const double2 inv = crecip(r);
+                // 1/r = conj(r)/|r|^2 with a branch-free reciprocal (Im r >= Im z > 0: |r|^2 is never small)
+                const double s = fast_rcp(fma(r.x, r.x, r.y * r.y));
+                const double2 inv = make_double2(r.x * s, -r.y * s);
                 const double2 q = cmul(rp, inv);              // r_{i}'/r_{i}
                 t.x += q.x; t.y += q.y;
                 const double2 u = make_double2(e2[i - 1] * inv.x, e2[i - 1] * inv.y);
@@ -612,8 +627,11 @@ tridiag_resolvent_kernel(const double* __restrict__ din, const double* __restric
                 const double2 uq = cmul(u, q);
                 rp = make_double2(1.0 + uq.x, uq.y);
             }
-            const double2 q = cmul(rp, crecip(r));
-            t.x += q.x; t.y += q.y;
+            {
+                const double s = fast_rcp(fma(r.x, r.x, r.y * r.y));
+                const double2 q = cmul(rp, make_double2(r.x * s, -r.y * s));
+                t.x += q.x; t.y += q.y;
+            }
             if (!(isfinite(t.x) && isfinite(t.y))) *errflag = 1;
         }
         if (mode == 1) {

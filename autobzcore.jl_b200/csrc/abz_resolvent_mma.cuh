@@ -61,18 +61,6 @@ __device__ __forceinline__ void bmm(double& cr0, double& cr1, double& ci0, doubl
     dmma884(ci0, ci1, pi1, b.r[1]);
 }
 
-// branch-free reciprocal: MUFU.RCP64H seed (~2^-20) + two Newton steps (keeps the whole elimination in one
-// basic block so that ptxas can interleave the DMMA chains with the latency-bound pivot steps)
-__device__ __forceinline__ double fast_rcp(double d) {
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-    const double e = fma(-d, x, 1.0);      // 1 - d x0
-    const double e2 = e * e;               // = 1 - d x1 up to rounding (in parallel with x1)
-    x = fma(x, e, x);                      // x1
-    x = fma(x, e2, x);                     // x2: relative error ~ e^4 (seed 2^-20 -> 2^-80)
-    return x;
-}
-
 // sign flip on the integer pipe (keeps the FP64 pipe for FMA/DMMA work)
 __device__ __forceinline__ double dneg(double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
 
