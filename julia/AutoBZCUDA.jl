@@ -156,6 +156,37 @@ function (rule::DeviceRule{d})(f::AutoBZCore.ParameterIntegrand{ResolventTrace},
     return resolvent_sum(rule, z, nothing, scale)[1]
 end
 
+"sum_i w_i (z_w - H(k_i) - Σ_w)^-1: the matrix-valued gloc_integrand of docs/src/examples.md:20,90 (symmetrise with your SymRep)"
+function resolvent_matrix_sum(rule::DeviceRule, z::Vector{ComplexF64}, Σ::Union{Nothing,Array{ComplexF64,3}}, scale::Float64)
+    n = rule.series.norb
+    out = Array{ComplexF64}(undef, n, n, length(z))
+    GC.@preserve z Σ out begin
+        rc = ccall((:abz_rule_resolvent_matrix_sum, LIB), Int32,
+                   (Ptr{Cvoid}, UInt64, Int32, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}),
+                   rule.ctx.h, rule.h, length(z), Ptr{Float64}(pointer(z)),
+                   Σ === nothing ? Ptr{Float64}(C_NULL) : Ptr{Float64}(pointer(Σ)), scale, Ptr{Float64}(pointer(out)))
+    end
+    check(rule.ctx, rc)
+    return out
+end
+
+# GGR (src/dos_ggr.jl): get_ggr_data on the device (energies + band velocities at every node), then sum_ggr for a list of energies.
+# Drop-in for init_cacheval(h, domain, p, alg::GGR) / dos_solve: weights stay on the device with the rule.
+function ggr_data!(rule::DeviceRule{d}; copy=false) where {d}
+    n = rule.series.norb
+    e = copy ? Array{Float64}(undef, n, rule.nnodes) : nothing
+    v = copy ? Array{Float64}(undef, n, d, rule.nnodes) : nothing
+    check(rule.ctx, ccall((:abz_rule_ggr_data, LIB), Int32, (Ptr{Cvoid}, UInt64, Int32, Ptr{Float64}, Ptr{Float64}),
+                          rule.ctx.h, rule.h, d, copy ? e : C_NULL, copy ? v : C_NULL))
+    return e, v
+end
+function ggr_sum(rule::DeviceRule, E::Vector{Float64})
+    out = similar(E)
+    check(rule.ctx, ccall((:abz_rule_ggr_sum, LIB), Int32, (Ptr{Cvoid}, UInt64, Int32, Ptr{Float64}, Float64, Ptr{Float64}),
+                          rule.ctx.h, rule.h, length(E), E, 1.0, out))
+    return out
+end
+
 # generic user integrands: copy H(k) back and keep the reference's Julia path (iterate protocol, src/fourier.jl:176-202)
 function copy_out(rule::DeviceRule{d}) where {d}
     n = rule.series.norb
