@@ -494,3 +494,34 @@ def batchsolve(solver, ps, callback=None):
         for i, (p, s) in enumerate(zip(plist, sols)):
             callback(solver.prob.f, i, len(plist), p, s, t / max(1, len(plist)))
     return np.array([s.u for s in sols])
+
+
+def batchsolve_log(path, solver, ps, verb=False):
+    """batchsolve(h5, f::IntegralSolver, ps) of ext/HDF5Ext.jl:116-158: solve for every parameter and record, per parameter,
+    the datasets of the reference's HDF5 archive - I (result), E (error estimate, NaN if none), t (seconds), retcode,
+    numevals, and the parameters (positional "args/<j>", keyword "kwargs/<name>").  h5py is not part of this image, so the
+    archive is written as a NumPy .npz with those dataset names; `numpy.load(path)` gives them back.  Returns the results."""
+    plist = list(ps)
+    n = len(plist)
+    rec = {"E": np.full(n, np.nan), "t": np.zeros(n), "retcode": np.zeros(n, dtype=np.int32), "numevals": np.zeros(n, dtype=np.int64)}
+    results = [None] * n
+
+    def cb(_, i, ntot, p, sol, t):
+        if verb:
+            print(f"{i + 1:5d} / {ntot} done in {t:e} (s)")
+        results[i] = sol.u
+        rec["E"][i] = np.nan if sol.resid is None else float(np.max(np.abs(sol.resid)))
+        rec["t"][i] = t
+        rec["retcode"][i] = int(bool(sol.retcode))
+        rec["numevals"][i] = sol.numevals
+
+    out = batchsolve(solver, plist, callback=cb)
+    rec["I"] = np.array(results)
+    for i, p in enumerate(plist):
+        args, kws = _params(p)
+        for j, a in enumerate(args):
+            rec.setdefault(f"args/{j + 1}", np.zeros(n, dtype=np.asarray(a).dtype))[i] = a
+        for k, v in kws.items():
+            rec.setdefault(f"kwargs/{k}", np.zeros(n, dtype=np.asarray(v).dtype))[i] = v
+    np.savez(path, **rec)
+    return out

@@ -259,3 +259,21 @@ def test_matrix_valued_gloc_integrand_and_symrep(orc):
     assert G.shape == (2, n, n)
     with pytest.raises(TypeError):
         ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_integrand, fs, eta=0.4), fbz, p), ab.IAI(), backend=be)
+
+
+def test_batchsolve_log_archive(tmp_path, orc, svo):
+    """ext/HDF5Ext.jl:116-158: batchsolve into an archive with datasets I, E, t, retcode, numevals and the parameters"""
+    H, lo, A = svo
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
+    bz = ab.load_bz(ab.CubicSymIBZ(), A)
+    solver = ab.IntegralSolver(ab.FourierIntegrand(ab.dos_integrand, fs, 0.1), bz, ab.EvalCounter(ab.PTR(npt=8)), backend=OracleBackend())
+    ws = [12.0, 12.5, 13.0]
+    out = ab.batchsolve_log(tmp_path / "sweep.npz", solver, ws)
+    arc = np.load(tmp_path / "sweep.npz")
+    assert set(arc.files) >= {"I", "E", "t", "retcode", "numevals", "args/1"}
+    assert np.array_equal(arc["I"], out) and np.array_equal(arc["args/1"], ws)
+    assert np.all(arc["retcode"] == 1) and np.all(arc["numevals"] == len(solver.cache.cacheval["rule"])) and np.all(np.isnan(arc["E"]))
+    solver2 = ab.IntegralSolver(ab.FourierIntegrand(ab.gloc_trace_integrand, fs), bz, ab.PTR(npt=6), backend=OracleBackend())
+    ab.batchsolve_log(tmp_path / "kw.npz", solver2, [{"eta": 0.1, "omega": w} for w in ws])
+    arc = np.load(tmp_path / "kw.npz")
+    assert np.array_equal(arc["kwargs/omega"], ws) and arc["I"].dtype == np.complex128

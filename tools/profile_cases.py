@@ -8,7 +8,7 @@ from autobz_b200 import _lib as L
 
 ctx = ab.default_context(0)
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-which = sys.argv[1:] or ["contract", "small", "eig", "iai"]
+which = sys.argv[1:] or ["contract", "small", "eig", "iai", "sweep", "ggr", "matrix"]
 d = np.load(os.path.join(ROOT, "tests", "golden", "svo_hr.npz"))
 Hs, los, A = np.asfortranarray(d["H_R"]), tuple(int(x) for x in d["lo"]), d["A"]
 
@@ -48,3 +48,31 @@ if "iai" in which:
         be = ab.DeviceBackend(ctx=ctx, iai_engine="native", iai_device_leaves=leaves)
         sol = ab.solve(ab.IntegralProblem(f, ibz, 12.5), ab.EvalCounter(ab.IAI()), abstol=3e-1, backend=be)
         print("iai", leaves, sol.u, sol.numevals)
+
+if "sweep" in which:
+    # C4 shape, one k3 plane, 128 frequencies through the opt-in sweep path (tridiagonalise once per k, p'/p per frequency)
+    H, lo = ab.synthetic.wannier_hamiltonian(32, 8)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    R = L.DeviceRule(ctx, S, 256, k3_lo=0, k3_hi=1)
+    R.materialize()
+    ext = ab.synthetic.band_extent(H)
+    z = np.linspace(-0.2 * ext, 0.2 * ext, 128) + 1j * 0.01 * ext
+    ctx.set_option(L.OPT_RESOLVENT_ALGO, 3)
+    print("sweep", R.resolvent_sum(z)[:2], ctx.last_timings())
+    ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
+    R.close(); S.close()
+
+if "ggr" in which:
+    # GGR data pass + sum: graphene-like 2-band model is too small to time; use a 16-orbital cubic model on the IBZ, npt = 32
+    H, lo = ab.synthetic.wannier_hamiltonian(16, 2, cubic=True)
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=16)
+    cache = ab.init(ab.DOSProblem(fs, np.linspace(-1.0, 1.0, 64), ab.load_bz(ab.CubicSymIBZ(), np.eye(3))), ab.GGR(npt=32))
+    print("ggr", ab.solve_(cache).u[:3], ctx.last_timings())
+
+if "matrix" in which:
+    H, lo = ab.synthetic.wannier_hamiltonian(32, 2)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    R = L.DeviceRule(ctx, S, 24)
+    z = np.linspace(-1.0, 1.0, 8) + 0.05j
+    print("matrix", R.resolvent_matrix_sum(z)[0, 0, :2], ctx.last_timings())
+    R.close(); S.close()
