@@ -439,8 +439,8 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
                 if (q == 0) {
                     const double2 wj = wv[j];
                     double2 a = *Ap;
-                    a.x -= vi.x * wj.x + vi.y * wj.y + wi.x * v0.x + wi.y * v0.y;
-                    a.y -= vi.y * wj.x - vi.x * wj.y + wi.y * v0.x - wi.x * v0.y;
+                    a.x = fma(-wi.y, v0.y, fma(-wi.x, v0.x, fma(-vi.y, wj.y, fma(-vi.x, wj.x, a.x))));
+                    a.y = fma(wi.x, v0.y, fma(-wi.y, v0.x, fma(vi.x, wj.y, fma(-vi.y, wj.x, a.y))));
                     *Ap = a;
                     j += 4; Ap += 4 * LDA;
                 }
@@ -448,8 +448,8 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
                 for (; j < n; j += 4, Ap += 4 * LDA) {
                     const double2 vj = col[j], wj = wv[j];
                     double2 a = *Ap;
-                    a.x -= vi.x * wj.x + vi.y * wj.y + wi.x * vj.x + wi.y * vj.y;
-                    a.y -= vi.y * wj.x - vi.x * wj.y + wi.y * vj.x - wi.x * vj.y;
+                    a.x = fma(-wi.y, vj.y, fma(-wi.x, vj.x, fma(-vi.y, wj.y, fma(-vi.x, wj.x, a.x))));
+                    a.y = fma(wi.x, vj.y, fma(-wi.y, vj.x, fma(vi.x, wj.y, fma(-vi.y, wj.x, a.y))));
                     *Ap = a;
                 }
             }
@@ -513,8 +513,8 @@ eig_tridiag_warp_kernel(const double2* __restrict__ H, long nk, int n, double* _
 #pragma unroll
             for (int j = c + 1; j < N; j++) {
                 const double2 vj = sv[j], wj = sw[j];
-                a[j].x -= v.x * wj.x + v.y * wj.y + w.x * vj.x + w.y * vj.y;
-                a[j].y -= v.y * wj.x - v.x * wj.y + w.y * vj.x - w.x * vj.y;
+                a[j].x = fma(-w.y, vj.y, fma(-w.x, vj.x, fma(-v.y, wj.y, fma(-v.x, wj.x, a[j].x))));
+                a[j].y = fma(w.x, vj.y, fma(-w.y, vj.x, fma(v.x, wj.y, fma(-v.y, wj.x, a[j].y))));
             }
         }
         if (lane == N - 1 && N - 1 < n) { dout[(long)(N - 1) * nk + k] = a[N - 1].x; eout[(long)(N - 1) * nk + k] = 0.0; }
