@@ -99,7 +99,7 @@ struct abz_ctx {
     int fused_small = 1;
     int eig_algo = 0;             // 0: tridiagonalisation + QL, 1: two-sided Jacobi
     bool force_generic = false;   // set while re-running a call whose fast path asked for pivoting
-    DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d, iai_in, iai_out, eig_d, eig_e;
+    DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d, iai_in, iai_out, eig_d, eig_e, symw;
     void* pin_in = nullptr; size_t pin_in_cap = 0;     // pinned staging for the IAI engine's per-round traffic
     void* pin_out = nullptr; size_t pin_out_cap = 0;
     long launches = 0;
@@ -708,6 +708,17 @@ int32_t abz_rule_create_nodes(abz_ctx* ctx, abz_series_t sid, int32_t npt, int64
     return ABZ_OK;
 }
 
+// symptr_rule_kernel with the fast modular reduction whenever every intermediate |S i| stays below 2^22
+static void launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms, const int* d_syms, int* d_w) {
+    long smax = 0;
+    for (int t = 0; t < 9 * nsyms; t++) smax = std::max<long>(smax, std::labs((long)h_syms[t]));
+    const size_t tot = (size_t)npt * npt * npt;
+    const unsigned grid = (unsigned)((tot + 255) / 256);
+    const size_t smem = (size_t)nsyms * 9 * sizeof(int);
+    if (3 * smax * npt < (1L << 22)) symptr_rule_kernel<true><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, d_w);
+    else symptr_rule_kernel<false><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, d_w);
+}
+
 int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t* wsym_out, int64_t* nirr) {
     if (!ctx) return ABZ_E_INVALID;
     if (npt < 1 || nsyms < 1 || nsyms > 1024 || !syms || !wsym_out) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
@@ -718,8 +729,7 @@ int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t*
     CU(ctx, ctx->tmp_a.reserve(tot * sizeof(int)));
     CU(ctx, ctx->tmp_b.reserve((size_t)nsyms * 9 * sizeof(int)));
     CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, syms, (size_t)nsyms * 9 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    symptr_rule_kernel<<<(unsigned)((tot + 255) / 256), 256, (size_t)nsyms * 9 * sizeof(int), ctx->stream>>>(
-        npt, nsyms, ctx->tmp_b.as<int>(), ctx->tmp_a.as<int>());
+    launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), ctx->tmp_a.as<int>());
     LAUNCH_CHECK(ctx, "symptr_rule_kernel");
     CU(ctx, cudaMemcpyAsync(wsym_out, ctx->tmp_a.p, tot * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -744,12 +754,12 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
     const long N = npt;
     const size_t tot = (size_t)N * N * N;
     // dense orbit weights on the device (never copied to the host)
-    DevBuf wbuf, cntbuf, k3buf;
+    DevBuf& wbuf = ctx->symw;      // dense orbit weights: kept across rules (AutoPTR builds one per refinement)
+    DevBuf cntbuf, k3buf;
     CU(ctx, wbuf.reserve(tot * sizeof(int)));
     CU(ctx, ctx->tmp_b.reserve((size_t)nsyms * 9 * sizeof(int)));
     CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, syms, (size_t)nsyms * 9 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    symptr_rule_kernel<<<(unsigned)((tot + 255) / 256), 256, (size_t)nsyms * 9 * sizeof(int), ctx->stream>>>(
-        npt, nsyms, ctx->tmp_b.as<int>(), wbuf.as<int>());
+    launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), wbuf.as<int>());
     LAUNCH_CHECK(ctx, "symptr_rule_kernel");
     // per-row counts: all planes when the total is wanted, else only this rank's
     const bool want_total = (nirr_total != nullptr) && !(k3_lo == 0 && k3_stride == 1);

@@ -305,15 +305,28 @@ points_eval_kernel(const double2* __restrict__ C, int nn, int M1, int M2, int M3
 // AutoSymPTR.symptr_rule on the device (call site src/fourier.jl:271).  Orbit representative =
 // the image with the smallest column-major linear index (which is the first node of the orbit met
 // by the reference's column-major scan); weight = number of distinct images.
-__device__ __forceinline__ int symptr_image(const int* __restrict__ S, int i1, int i2, int i3, int N) {
-    // |S_ab| i < 2^31 is checked on the host (entries of lattice-basis symmetries are tiny integers)
-    int j1 = (S[0] * i1 + S[1] * i2 + S[2] * i3) % N;
-    int j2 = (S[3] * i1 + S[4] * i2 + S[5] * i3) % N;
-    int j3 = (S[6] * i1 + S[7] * i2 + S[8] * i3) % N;
-    j1 += (j1 < 0) ? N : 0; j2 += (j2 < 0) ? N : 0; j3 += (j3 < 0) ? N : 0;
-    return j1 + N * j2;          // in-plane part; the caller combines with j3
+// j mod N in [0, N).  FAST: |j| < 2^22 (checked on the host): quotient from a float reciprocal, one fix-up each way.
+template <bool FAST>
+__device__ __forceinline__ int symptr_mod(int j, int N, float invN) {
+    if (FAST) {
+        int r = j - __float2int_rd((float)j * invN) * N;
+        r += (r < 0) ? N : 0;
+        r -= (r >= N) ? N : 0;
+        return r;
+    }
+    int r = j % N;
+    return r + ((r < 0) ? N : 0);
+}
+// linear index of the image of (i1, i2, i3) under the 3x3 integer matrix S (row-major)
+template <bool FAST>
+__device__ __forceinline__ long symptr_image(const int* __restrict__ S, int i1, int i2, int i3, int N, float invN, long NN) {
+    const int j1 = symptr_mod<FAST>(S[0] * i1 + S[1] * i2 + S[2] * i3, N, invN);
+    const int j2 = symptr_mod<FAST>(S[3] * i1 + S[4] * i2 + S[5] * i3, N, invN);
+    const int j3 = symptr_mod<FAST>(S[6] * i1 + S[7] * i2 + S[8] * i3, N, invN);
+    return (long)j3 * NN + (j1 + N * j2);
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restrict__ wsym) {
     extern __shared__ int sy[];
@@ -324,13 +337,11 @@ symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restri
     if (idx >= tot) return;
     const int i1 = (int)(idx % N), i2 = (int)((idx / N) % N), i3 = (int)(idx / ((long)N * N));
     const long NN = (long)N * N;
+    const float invN = 1.0f / (float)N;
     // pass 1: is this node the smallest linear index of its orbit?  (most nodes leave after a few symmetries)
     bool has_self = false;
     for (int s = 0; s < nsyms; s++) {
-        const int* S = sy + 9 * s;
-        int j3 = (S[6] * i1 + S[7] * i2 + S[8] * i3) % N;
-        j3 += (j3 < 0) ? N : 0;
-        const long jdx = (long)j3 * NN + symptr_image(S, i1, i2, i3, N);
+        const long jdx = symptr_image<FAST>(sy + 9 * s, i1, i2, i3, N, invN, NN);
         if (jdx < idx) { wsym[idx] = 0; return; }
         has_self |= (jdx == idx);
     }
@@ -339,12 +350,7 @@ symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restri
     constexpr int CACHE = 64;
     if (nsyms <= CACHE) {
         long img[CACHE];
-        for (int s = 0; s < nsyms; s++) {
-            const int* S = sy + 9 * s;
-            int j3 = (S[6] * i1 + S[7] * i2 + S[8] * i3) % N;
-            j3 += (j3 < 0) ? N : 0;
-            img[s] = (long)j3 * NN + symptr_image(S, i1, i2, i3, N);
-        }
+        for (int s = 0; s < nsyms; s++) img[s] = symptr_image<FAST>(sy + 9 * s, i1, i2, i3, N, invN, NN);
         for (int s = 0; s < nsyms; s++) {
             bool dup = false;
             for (int r = 0; r < s; r++) dup |= (img[r] == img[s]);
@@ -352,17 +358,9 @@ symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restri
         }
     } else {
         for (int s = 0; s < nsyms; s++) {
-            const int* S = sy + 9 * s;
-            int j3 = (S[6] * i1 + S[7] * i2 + S[8] * i3) % N;
-            j3 += (j3 < 0) ? N : 0;
-            const long jdx = (long)j3 * NN + symptr_image(S, i1, i2, i3, N);
+            const long jdx = symptr_image<FAST>(sy + 9 * s, i1, i2, i3, N, invN, NN);
             bool dup = false;
-            for (int r = 0; r < s && !dup; r++) {
-                const int* R = sy + 9 * r;
-                int q3 = (R[6] * i1 + R[7] * i2 + R[8] * i3) % N;
-                q3 += (q3 < 0) ? N : 0;
-                dup = ((long)q3 * NN + symptr_image(R, i1, i2, i3, N) == jdx);
-            }
+            for (int r = 0; r < s && !dup; r++) dup = (symptr_image<FAST>(sy + 9 * r, i1, i2, i3, N, invN, NN) == jdx);
             cnt += dup ? 0 : 1;
         }
     }
