@@ -547,15 +547,16 @@ eig_tql_kernel(const double* __restrict__ din, const double* __restrict__ ein, c
                     if (m != l) {
                         if (iter++ == 60) { *errflag = 1; break; }
                         double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
-                        double r = hypot(g, 1.0);
+                        double r = sqrt(fma(g, g, 1.0));
                         g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? r : -r));
                         double s = 1.0, c = 1.0, p = 0.0;
                         int i;
                         for (i = m - 1; i >= l; i--) {
                             double f = s * e[i], b = c * e[i];
-                            e[i + 1] = (r = hypot(f, g));
+                            e[i + 1] = (r = sqrt(fma(f, f, g * g)));      // plain sqrt: band energies are nowhere near the overflow range
                             if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
-                            s = f / r; c = g / r;
+                            const double rinv = 1.0 / r;
+                            s = f * rinv; c = g * rinv;
                             g = d[i + 1] - p;
                             r = (d[i] - g) * s + 2.0 * c * b;
                             d[i + 1] = g + (p = s * r);
