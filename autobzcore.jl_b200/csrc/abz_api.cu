@@ -316,8 +316,8 @@ static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n) {
         attr_set = true;
     }
     const int RP = n > 32 ? 64 : 32;
-    const size_t smem = ((size_t)n * RP + 5 * RP) * sizeof(double2);
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (4 * RP), (220 * 1024) / (smem + 1024)));
+    const size_t smem = ((size_t)n * RP + RP + (size_t)(4 * RP / 32) * (RP - 1)) * sizeof(double2);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (4 * RP), (size_t)232448 / (smem + 1024)));
     const long ncta = std::min<long>(nk, (long)ctx->sm_count * per_sm);
     if (RP == 32) eig_tridiag_kernel<32><<<(unsigned)ncta, 128, smem, ctx->stream>>>(H, nk, n, dd, ee);
     else eig_tridiag_kernel<64><<<(unsigned)ncta, 256, smem, ctx->stream>>>(H, nk, n, dd, ee);

@@ -366,10 +366,15 @@ __global__ void __launch_bounds__(4 * RP)
 eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout) {
     extern __shared__ double2 et_smem[];
     constexpr int LDA = RP;            // compile-time leading dimension: column j starts at A + j*RP (a shift, no IMAD)
+    constexpr int NWARP = 4 * RP / 32;
     double2* A = et_smem;              // [n][LDA], column-major
-    double2* pb = A + (long)n * LDA;   // [4][RP] partial mat-vec sums
-    double2* wv = pb + 4 * RP;         // [RP]
-    const int tid = threadIdx.x, i = tid % RP, q = tid / RP, lane = tid & 31, warp = tid >> 5;
+    double2* pb = A + (long)n * LDA;   // [RP] mat-vec result (before scaling by tau)
+    // thread (row i, column quarter q): the 4 quarters of a row are adjacent lanes, so the partial mat-vec sums meet in two
+    // shuffles; a warp covers 8 rows x 4 columns = 32 distinct 16-byte words per access (4 wavefronts, the minimum)
+    const int tid = threadIdx.x, i = tid >> 2, q = tid & 3, lane = tid & 31, warp = tid >> 5;
+    // [NWARP][RP-1]: every warp keeps its own copy of w (no block barrier before the update); only rows >= 1 are ever used,
+    // and dropping row 0 is what lets three 64 x 64 matrices share one SM's shared memory
+    double2* wv = pb + RP + warp * (RP - 1) - 1;
     for (long k = blockIdx.x; k < nk; k += gridDim.x) {
         __syncthreads();
         const double2* Hk = H + k * (long)n * n;
@@ -401,12 +406,20 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
                 int j = c + 1 + q;
                 const double2* Ap = A + i + j * LDA;
                 if (q == 0) { acc = cfma(acc, *Ap, v0); j += 4; Ap += 4 * LDA; }
-#pragma unroll 4
-                for (; j < n; j += 4, Ap += 4 * LDA) acc = cfma(acc, *Ap, col[j]);
+                double2 acc1 = make_double2(0.0, 0.0);       // two accumulators: halves the dependent FMA chain
+#pragma unroll 2
+                for (; j + 4 < n; j += 8, Ap += 8 * LDA) {
+                    acc = cfma(acc, *Ap, col[j]);
+                    acc1 = cfma(acc1, Ap[4 * LDA], col[j + 4]);
+                }
+                if (j < n) acc = cfma(acc, *Ap, col[j]);
+                acc.x += acc1.x; acc.y += acc1.y;
             }
-            pb[q * RP + i] = acc;
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+            if (q == 0 && i < RP) pb[i] = acc;
             __syncthreads();
-            // w = p - (tau/2)(v^H p) v, every warp redundantly; warp 0 publishes it
+            // w = p - (tau/2)(v^H p) v, every warp redundantly into its own copy
             double2 pr[RP / 32], vr[RP / 32];
             double dot = 0.0;
 #pragma unroll
@@ -414,22 +427,20 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
                 const int r = lane + 32 * t;
                 pr[t] = make_double2(0.0, 0.0); vr[t] = make_double2(0.0, 0.0);
                 if (r > c && r < n) {
-                    const double2 s0 = pb[r], s1 = pb[RP + r], s2 = pb[2 * RP + r], s3 = pb[3 * RP + r];
-                    pr[t] = make_double2(tau * ((s0.x + s1.x) + (s2.x + s3.x)), tau * ((s0.y + s1.y) + (s2.y + s3.y)));
+                    const double2 s0 = pb[r];
+                    pr[t] = make_double2(tau * s0.x, tau * s0.y);
                     vr[t] = (r == c + 1) ? v0 : col[r];
                     dot += vr[t].x * pr[t].x + vr[t].y * pr[t].y;      // Re(conj(v) p); the imaginary part is rounding noise
                 }
             }
             dot = warp_sum(dot);
             const double gam = 0.5 * tau * dot;
-            if (warp == 0) {
 #pragma unroll
-                for (int t = 0; t < RP / 32; t++) {
-                    const int r = lane + 32 * t;
-                    if (r > c && r < n) wv[r] = make_double2(pr[t].x - gam * vr[t].x, pr[t].y - gam * vr[t].y);
-                }
+            for (int t = 0; t < RP / 32; t++) {
+                const int r = lane + 32 * t;
+                if (r > c && r < n) wv[r] = make_double2(pr[t].x - gam * vr[t].x, pr[t].y - gam * vr[t].y);
             }
-            __syncthreads();
+            __syncwarp();
             // A22 <- A22 - v w^H - w v^H
             if (active) {
                 const double2 vi = (i == c + 1) ? v0 : col[i];
@@ -500,10 +511,13 @@ eig_tridiag_warp_kernel(const double2* __restrict__ H, long nk, int n, double* _
             __syncwarp();
             sv[lane] = v;
             __syncwarp();
-            double2 p = make_double2(0.0, 0.0);
+            double2 p = make_double2(0.0, 0.0), p1 = make_double2(0.0, 0.0);   // two accumulators: shorter dependent chain
 #pragma unroll
-            for (int j = c + 1; j < N; j++) p = cfma(p, a[j], sv[j]);
-            p.x *= tau; p.y *= tau;
+            for (int j = c + 1; j < N; j += 2) {
+                p = cfma(p, a[j], sv[j]);
+                if (j + 1 < N) p1 = cfma(p1, a[j + 1], sv[j + 1]);
+            }
+            p.x = (p.x + p1.x) * tau; p.y = (p.y + p1.y) * tau;
             if (lane <= c) p = make_double2(0.0, 0.0);
             const double dot = warp_sum(v.x * p.x + v.y * p.y);
             const double gam = 0.5 * tau * dot;
