@@ -280,6 +280,8 @@ int check_errflag(abz_ctx* ctx, const char* what) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (h) {
         cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->stream);
+        if (h & 8) return fail(ctx, ABZ_E_INVALID, std::string(what) + ": H(k) is not Hermitian - the frequency-sweep resolvent "
+                                                   "(ABZ_OPT_RESOLVENT_ALGO = 3) does not apply; use algorithm 0");
         if ((h & 2) && !(h & 1) && !ctx->force_generic) return ABZ_RETRY_PIVOTED;
         return fail(ctx, ABZ_E_SINGULAR, std::string(what) + ": singular matrix or NaN/Inf in the integrand");
     }
@@ -288,7 +290,7 @@ int check_errflag(abz_ctx* ctx, const char* what) {
 
 // Householder tridiagonalisation of nk materialised matrices into ctx->eig_d / eig_e (structure of arrays):
 // n <= 32: one warp per matrix with the rows in registers; else one CTA per matrix in shared memory
-static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n) {
+static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n, int* herm_flag = nullptr) {
     CU(ctx, ctx->eig_d.reserve((size_t)nk * n * sizeof(double)));
     CU(ctx, ctx->eig_e.reserve((size_t)nk * n * sizeof(double)));
     double* dd = ctx->eig_d.as<double>(); double* ee = ctx->eig_e.as<double>();
@@ -298,8 +300,8 @@ static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n) {
         if (!minb) { const char* e = getenv("ABZ_TRIDIAG_MINB"); minb = (e && atoi(e) == 2) ? 2 : 3; }
 #define TRIDIAG_WARP(NX)                                                                                    \
     do {                                                                                                    \
-        if (minb == 2) eig_tridiag_warp_kernel<NX, 2><<<(unsigned)nblk, 128, 0, ctx->stream>>>(H, nk, n, dd, ee); \
-        else eig_tridiag_warp_kernel<NX, 3><<<(unsigned)nblk, 128, 0, ctx->stream>>>(H, nk, n, dd, ee);           \
+        if (minb == 2) eig_tridiag_warp_kernel<NX, 2><<<(unsigned)nblk, 128, 0, ctx->stream>>>(H, nk, n, dd, ee, herm_flag); \
+        else eig_tridiag_warp_kernel<NX, 3><<<(unsigned)nblk, 128, 0, ctx->stream>>>(H, nk, n, dd, ee, herm_flag);           \
     } while (0)
         if (n <= 8) TRIDIAG_WARP(8);
         else if (n <= 16) TRIDIAG_WARP(16);
@@ -319,8 +321,8 @@ static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n) {
     const size_t smem = ((size_t)n * RP + RP + (size_t)(4 * RP / 32) * (RP - 1)) * sizeof(double2);
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (4 * RP), (size_t)232448 / (smem + 1024)));
     const long ncta = std::min<long>(nk, (long)ctx->sm_count * per_sm);
-    if (RP == 32) eig_tridiag_kernel<32><<<(unsigned)ncta, 128, smem, ctx->stream>>>(H, nk, n, dd, ee);
-    else eig_tridiag_kernel<64><<<(unsigned)ncta, 256, smem, ctx->stream>>>(H, nk, n, dd, ee);
+    if (RP == 32) eig_tridiag_kernel<32><<<(unsigned)ncta, 128, smem, ctx->stream>>>(H, nk, n, dd, ee, herm_flag);
+    else eig_tridiag_kernel<64><<<(unsigned)ncta, 256, smem, ctx->stream>>>(H, nk, n, dd, ee, herm_flag);
     LAUNCH_CHECK(ctx, "eig_tridiag_kernel");
     return ABZ_OK;
 }
@@ -376,7 +378,7 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
     }
     // frequency sweep from one tridiagonalisation per k (opt-in: Hermitian H(k), scalar self-energy folded into z)
     if (ctx->resolvent_algo == 3 && !sigma && n <= EIG_MAXN && !ctx->force_generic) {
-        { int rct = launch_tridiag(ctx, H, nk, n); if (rct) return rct; }
+        { int rct = launch_tridiag(ctx, H, nk, n, ef); if (rct) return rct; }
         const long ncx = (nk + TS_THREADS - 1) / TS_THREADS;
         dim3 grid((unsigned)ncx, (unsigned)((nw + TS_WCH - 1) / TS_WCH));
         if (mode == 0) {

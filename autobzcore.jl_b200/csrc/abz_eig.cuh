@@ -363,15 +363,18 @@ jacobian_coeff_kernel(const double2* __restrict__ c, double2* __restrict__ out, 
 // Outputs are structure-of-arrays d[i*nk + k], e[i*nk + k] so that stage B (one thread per matrix) loads coalesced.
 template <int RP>
 __global__ void __launch_bounds__(4 * RP)
-eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout) {
+eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout,
+                   int* __restrict__ herm_flag) {
     extern __shared__ double2 et_smem[];
     constexpr int LDA = RP;            // compile-time leading dimension: column j starts at A + j*RP (a shift, no IMAD)
     constexpr int NWARP = 4 * RP / 32;
     double2* A = et_smem;              // [n][LDA], column-major
     double2* pb = A + (long)n * LDA;   // [RP] mat-vec result (before scaling by tau)
-    // thread (row i, column quarter q): the 4 quarters of a row are adjacent lanes, so the partial mat-vec sums meet in two
-    // shuffles; a warp covers 8 rows x 4 columns = 32 distinct 16-byte words per access (4 wavefronts, the minimum)
-    const int tid = threadIdx.x, i = tid >> 2, q = tid & 3, lane = tid & 31, warp = tid >> 5;
+    // thread (row i, column quarter q): a warp covers 8 rows x 4 quarters with lane = 8 q + (i mod 8), so every quarter-warp
+    // reads 8 consecutive rows of ONE column (128 contiguous bytes: conflict-free 128-bit accesses) and the four partial
+    // mat-vec sums of a row meet in two shuffles (xor 8, xor 16)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = warp * 8 + (lane & 7), q = lane >> 3;
     // [NWARP][RP-1]: every warp keeps its own copy of w (no block barrier before the update); only rows >= 1 are ever used,
     // and dropping row 0 is what lets three 64 x 64 matrices share one SM's shared memory
     double2* wv = pb + RP + warp * (RP - 1) - 1;
@@ -382,6 +385,10 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
             int r = e % n, j = e / n;
             double2 a = Hk[r + (long)j * n], b = Hk[j + (long)r * n];
             A[r + j * LDA] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+            if (herm_flag) {       // the frequency-sweep path is only valid for Hermitian H(k)
+                const double dx = a.x - b.x, dy = a.y + b.y;
+                if (dx * dx + dy * dy > 1e-20 * (a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y) + 1e-290) atomicOr(herm_flag, 8);
+            }
         }
         __syncthreads();
         for (int c = 0; c < n - 1; c++) {
@@ -415,8 +422,8 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
                 if (j < n) acc = cfma(acc, *Ap, col[j]);
                 acc.x += acc1.x; acc.y += acc1.y;
             }
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 8); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 8);
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
             if (q == 0 && i < RP) pb[i] = acc;
             __syncthreads();
             // w = p - (tau/2)(v^H p) v, every warp redundantly into its own copy
@@ -476,7 +483,8 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
 // dot products are xor-shuffle trees.  Same arithmetic as eig_tridiag_kernel (same reflector, same update).
 template <int N, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-eig_tridiag_warp_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout) {
+eig_tridiag_warp_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout,
+                        int* __restrict__ herm_flag) {
     __shared__ double2 bc[4][2][32];      // per warp: v and w
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double2* sv = bc[warp][0];
@@ -490,6 +498,10 @@ eig_tridiag_warp_kernel(const double2* __restrict__ H, long nk, int n, double* _
             if (lane < n && j < n) {
                 const double2 x = Hk[lane + (long)j * n], y = Hk[j + (long)lane * n];
                 a[j] = make_double2(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+                if (herm_flag) {   // the frequency-sweep path is only valid for Hermitian H(k)
+                    const double dx = x.x - y.x, dy = x.y + y.y;
+                    if (dx * dx + dy * dy > 1e-20 * (x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y) + 1e-290) atomicOr(herm_flag, 8);
+                }
             }
         }
 #pragma unroll

@@ -515,3 +515,23 @@ def test_register_resident_tridiagonalisation(ctx, n):
     finally:
         ctx.set_option(L.OPT_EIG_ALGO, 0)
     assert rel(ev, ref) < 1e-13 and rel(ev2, ref) < 1e-13
+
+
+@pytest.mark.parametrize("n", [6, 40])
+def test_frequency_sweep_rejects_non_hermitian_h(ctx, orc, n):
+    """the sweep path is only valid for Hermitian H(k): a series without H_{-R} = H_R^dagger is refused (ValueError), while the
+    LU path (Julia's inv) handles it"""
+    rng = np.random.default_rng(n)
+    H = rng.standard_normal((n, n, 3, 3, 3)) + 1j * rng.standard_normal((n, n, 3, 3, 3))
+    S = L.DeviceSeries(ctx, H, (-1, -1, -1), (1.0,) * 3)
+    z = np.array([0.3 + 2.5j, -0.4 + 3.0j])
+    R = L.DeviceRule(ctx, S, 4)
+    ref = orc.ptr_sum(orc.Series(H, (-1, -1, -1)), 4, z)
+    assert rel(R.resolvent_sum(z, scale=1 / 64), ref) < 1e-10
+    ctx.set_option(L.OPT_RESOLVENT_ALGO, 3)
+    try:
+        with pytest.raises(ValueError, match="not Hermitian"):
+            R.resolvent_sum(z)
+    finally:
+        ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
+    assert rel(R.resolvent_sum(z, scale=1 / 64), ref) < 1e-10       # the context stays usable
