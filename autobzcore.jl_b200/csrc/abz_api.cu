@@ -1611,8 +1611,17 @@ struct IaiDeviceBackend {
             const long* sslot = has_slots ? dL + o_ss : nullptr;
             if (n <= 3) {
                 unsigned g = (unsigned)((ns + 7) / 8);
+                static bool attr_panel = false;
+                if (!attr_panel) {
+                    cudaFuncSetAttribute(nest_panel_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                    cudaFuncSetAttribute(nest_panel_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                    cudaFuncSetAttribute(nest_panel_small_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                    attr_panel = true;
+                }
+                if ((size_t)8 * s->M[0] * n * n * sizeof(double2) > 160 * 1024)
+                    return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension for the IAI panel kernel");
 #define PANEL_LAUNCH(NORB)                                                                                               \
-    nest_panel_small_kernel<NORB><<<g, 128, 0, ctx->stream>>>(L1, stride, dD + o_sa, dD + o_sb, sslot, (long)ns, s->M[0], s->lo[0], \
+    nest_panel_small_kernel<NORB><<<g, 128, (size_t)8 * s->M[0] * NORB * NORB * sizeof(double2), ctx->stream>>>(L1, stride, dD + o_sa, dD + o_sb, sslot, (long)ns, s->M[0], s->lo[0], \
                                                              s->period[0], fkind, vkind, z, dsig, la, lb, dout, ef)
                 if (n == 1) PANEL_LAUNCH(1); else if (n == 2) PANEL_LAUNCH(2); else PANEL_LAUNCH(3);
 #undef PANEL_LAUNCH
@@ -1678,9 +1687,18 @@ struct IaiDeviceBackend {
         // global spill area for segment heaps deeper than the shared-memory levels
         CU(ctx, ctx->tmp_d.reserve((size_t)nt * LEAF_SPILL * sizeof(LeafSeg) + 64));
         unsigned g = (unsigned)((nt + LEAF_WARPS - 1) / LEAF_WARPS);
+        static bool attr_leaf = false;
+        if (!attr_leaf) {
+            cudaFuncSetAttribute(iai_leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(iai_leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(iai_leaf_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            attr_leaf = true;
+        }
+        if ((size_t)LEAF_WARPS * s->M[0] * s->n * s->n * sizeof(double2) > 160 * 1024)
+            return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension for the IAI leaf kernel");
         LeafSeg* spill = reinterpret_cast<LeafSeg*>(ctx->tmp_d.as<char>() + 64);
 #define LEAF_LAUNCH(NORB)                                                                                              \
-    iai_leaf_kernel<NORB><<<g, LEAF_WARPS * 32, 0, ctx->stream>>>(nst->L1, stride, ta, tb, tt, ts, nt, s->M[0], s->lo[0], s->period[0], \
+    iai_leaf_kernel<NORB><<<g, LEAF_WARPS * 32, (size_t)LEAF_WARPS * s->M[0] * NORB * NORB * sizeof(double2), ctx->stream>>>(nst->L1, stride, ta, tb, tt, ts, nt, s->M[0], s->lo[0], s->period[0], \
                                                                  fkind, vkind, z, dsig, la, lb, rtol, (long long)maxevals, spill, out, \
                                                                  ctx->errflag.as<int>())
         if (s->n == 1) LEAF_LAUNCH(1); else if (s->n == 2) LEAF_LAUNCH(2); else LEAF_LAUNCH(3);

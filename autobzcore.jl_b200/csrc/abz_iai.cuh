@@ -78,17 +78,22 @@ nest_panel_small_kernel(const double2* __restrict__ L1, long l1_stride, const do
                         const double* __restrict__ seg_b, const long* __restrict__ seg_slot, long nseg, int M1, int lo,
                         double period, int fkind, int vkind, double2 z, const double2* __restrict__ sigma,
                         abz_iai::cplx la, abz_iai::cplx lb, double* __restrict__ out, int* __restrict__ errflag) {
+    constexpr int NN = NORB * NORB;
     __shared__ abz_iai::cplx vals[8][16];
+    extern __shared__ double2 np_coef[];              // [8][M1*NN]: the 1-D series of each panel's slot, staged once
     const int ls = threadIdx.x >> 4, j = threadIdx.x & 15;
     const long seg = (long)blockIdx.x * 8 + ls;
     double a = 0.0, b = 0.0;
+    double2* cs = np_coef + ls * (M1 * NN);
     if (seg < nseg) {
         a = seg_a[seg]; b = seg_b[seg];
-        if (j < 15) {
-            const double2* c = L1 + (seg_slot ? seg_slot[seg] * l1_stride : 0);
-            double2 y = nest_point_small<NORB>(c, abz_iai::gk_node(a, b, j), M1, lo, period, fkind, z, sigma, errflag);
-            vals[ls][j] = abz_iai::post_value(vkind, abz_iai::cplx{y.x, y.y}, la, lb);
-        }
+        const double2* c = L1 + (seg_slot ? seg_slot[seg] * l1_stride : 0);
+        for (int e = j; e < M1 * NN; e += 16) cs[e] = c[e];       // coalesced 128-bit loads by the panel's 16 lanes
+    }
+    __syncthreads();
+    if (seg < nseg && j < 15) {
+        double2 y = nest_point_small<NORB>(cs, abz_iai::gk_node(a, b, j), M1, lo, period, fkind, z, sigma, errflag);
+        vals[ls][j] = abz_iai::post_value(vkind, abz_iai::cplx{y.x, y.y}, la, lb);
     }
     __syncthreads();
     if (seg < nseg && j == 0) {
@@ -140,12 +145,19 @@ iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __
                 long ntask, int M1, int lo, double period, int fkind, int vkind, double2 z, const double2* __restrict__ sigma,
                 abz_iai::cplx la, abz_iai::cplx lb, double rtol, long long maxevals, LeafSeg* __restrict__ spill,
                 double* __restrict__ out, int* __restrict__ errflag) {
+    constexpr int NN = NORB * NORB;
     __shared__ LeafSeg heap_s[LEAF_WARPS][LEAF_SMEM_SEGS];
     __shared__ abz_iai::cplx vals[LEAF_WARPS][32];
+    extern __shared__ double2 leaf_coef[];            // [LEAF_WARPS][M1*NN]: this task's 1-D series, staged once per integral
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long task = (long)blockIdx.x * LEAF_WARPS + w;
     if (task >= ntask) return;
-    const double2* c = L1 + task_slot[task] * l1_stride;
+    double2* c = leaf_coef + w * (M1 * NN);
+    {
+        const double2* cg = L1 + task_slot[task] * l1_stride;
+        for (int e = lane; e < M1 * NN; e += 32) c[e] = cg[e];        // coalesced 128-bit loads
+    }
+    __syncwarp();
     const double atol = task_atol[task];
     LeafSeg* hs = heap_s[w];
     LeafSeg* hg = spill + task * LEAF_SPILL;
