@@ -381,13 +381,23 @@ eig_tridiag_kernel(const double2* __restrict__ H, long nk, int n, double* __rest
     for (long k = blockIdx.x; k < nk; k += gridDim.x) {
         __syncthreads();
         const double2* Hk = H + k * (long)n * n;
+        double asym = 0.0, tot = 0.0;
         for (int e = tid; e < n * n; e += 4 * RP) {
             int r = e % n, j = e / n;
             double2 a = Hk[r + (long)j * n], b = Hk[j + (long)r * n];
             A[r + j * LDA] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
-            if (herm_flag) {       // the frequency-sweep path is only valid for Hermitian H(k)
-                const double dx = a.x - b.x, dy = a.y + b.y;
-                if (dx * dx + dy * dy > 1e-20 * (a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y) + 1e-290) atomicOr(herm_flag, 8);
+            const double dx = a.x - b.x, dy = a.y + b.y;
+            asym += dx * dx + dy * dy;
+            tot += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+        }
+        if (herm_flag) {       // the frequency-sweep path is only valid for Hermitian H(k): ||H - H^H||_F <= 1e-10 ||H||_F
+            asym = warp_sum(asym); tot = warp_sum(tot);
+            if (lane == 0) { pb[2 * warp] = make_double2(asym, tot); }
+            __syncthreads();
+            if (tid == 0) {
+                double sa = 0.0, st = 0.0;
+                for (int w = 0; w < NWARP; w++) { sa += pb[2 * w].x; st += pb[2 * w].y; }
+                if (sa > 1e-20 * st) atomicOr(herm_flag, 8);
             }
         }
         __syncthreads();
@@ -492,17 +502,21 @@ eig_tridiag_warp_kernel(const double2* __restrict__ H, long nk, int n, double* _
     for (long k = (long)blockIdx.x * 4 + warp; k < nk; k += (long)gridDim.x * 4) {
         const double2* Hk = H + k * (long)n * n;
         double2 a[N];
+        double asym = 0.0, tot = 0.0;
 #pragma unroll
         for (int j = 0; j < N; j++) {
             a[j] = make_double2(0.0, 0.0);
             if (lane < n && j < n) {
                 const double2 x = Hk[lane + (long)j * n], y = Hk[j + (long)lane * n];
                 a[j] = make_double2(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
-                if (herm_flag) {   // the frequency-sweep path is only valid for Hermitian H(k)
-                    const double dx = x.x - y.x, dy = x.y + y.y;
-                    if (dx * dx + dy * dy > 1e-20 * (x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y) + 1e-290) atomicOr(herm_flag, 8);
-                }
+                const double dx = x.x - y.x, dy = x.y + y.y;
+                asym += dx * dx + dy * dy;
+                tot += x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y;
             }
+        }
+        if (herm_flag) {   // the frequency-sweep path is only valid for Hermitian H(k): ||H - H^H||_F <= 1e-10 ||H||_F
+            asym = warp_sum(asym); tot = warp_sum(tot);
+            if (lane == 0 && asym > 1e-20 * tot) atomicOr(herm_flag, 8);
         }
 #pragma unroll
         for (int c = 0; c < N - 1; c++) {

@@ -299,13 +299,19 @@ def main():
     bz = ab.load_bz(ab.FBZ(), 2 * np.pi * np.eye(3))
     plist = [{"omega": float(w)} for w in omegas]
 
+    e2e_phases = []
+
     def e2e_step():
+        t0 = time.perf_counter()
         fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=NORB)            # host buffer -> uploaded inside
         f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=eta)
         solver = ab.IntegralSolver(f, bz, ab.PTR(npt=NPT), shard=_VShard())
+        t1 = time.perf_counter()
         out = ab.batchsolve(solver, plist)
+        t2 = time.perf_counter()
         solver.cache.cacheval["rule"].close()
         fs.drop_device()
+        e2e_phases.append((1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2)) + tuple(ctx.last_timings()))
         return out
 
     for _ in range(min(args.warmup, 1)):
@@ -356,7 +362,9 @@ def main():
                            "resolvent_algo": args.algo, "device_event_ms_per_step": 1e3 * t_events_max / args.steps},
                 "roofline": roof, "cpu_baseline": cb,
                 "e2e": {"value": e2e_val, "unit": "k-points/s", "h2d_bytes_per_step": int(H.nbytes + z.nbytes), "d2h_bytes_per_step": int(NW * 16),
-                        "ms_per_step": 1e3 * t_e2e_max / args.steps},
+                        "ms_per_step": 1e3 * t_e2e_max / args.steps,
+                        "phases_ms_last_step": dict(zip(("upload_and_rule", "batchsolve", "teardown", "device_eval", "device_matfun"),
+                                                        [round(x, 2) for x in e2e_phases[-1]]))},
                 "gpu_launches": int(launches), "clocks": clocks, "other_configs": others, "frequency_sweep_fast_path": sweep,
                 "check": {"G_first": [float(g[0].real), float(g[0].imag)]}}
         print(json.dumps(line), flush=True)

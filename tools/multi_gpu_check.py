@@ -67,6 +67,25 @@ good = abs(one.u - many.u) <= 1e-12 * abs(one.u) and one.numevals == many.numeva
 ok = ok and good
 emit(case="C5 norb=64 band energy CubicSymIBZ AutoPTR 48->96->144", ranks=world, rel_diff=abs(one.u - many.u) / abs(one.u), numevals=many.numevals,
      kpoints_per_s_1rank=one.numevals / t1, kpoints_per_s_sharded=many.numevals / tn, speedup=t1 / tn)
+# the library's own NCCL path (abz_comm_init / abz_allreduce_sum through dlopen): unique id from rank 0 over torch.distributed,
+# then a raw allreduce and a sharded IAI solve whose exchange is NCCL inside the library (exchange callback = NULL)
+from autobz_b200 import _lib as L
+uid = [L.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+ctx.comm_init(rank, world, uid[0])
+v = np.arange(4, dtype=np.float64) + rank
+ctx.allreduce_sum(v)
+good = bool(np.array_equal(v, world * np.arange(4) + world * (world - 1) / 2))
+f = ab.FourierIntegrand(ab.dos_integrand, fs, 1e-2)
+nest = L.DeviceNest(ctx, fs.device(ctx), 3, 64, 2048)
+jb = abs(np.linalg.det(ibz.B)) * 48
+args = (1, ibz.lims.a, None, L.F_RESOLVENT_TRACE, 1, complex(12.0, 1e-2), None, None, 1e-3 / jb, 0.0, 2 ** 62)
+I1, E1, ne1, _, _ = nest.iai_solve(*args)
+In, En, nen, _, _ = nest.iai_solve(*args, rank=rank, nranks=world, allreduce=None)
+good = good and I1 == In and E1 == En and ne1 == nen
+ok = ok and good
+emit(case="library NCCL path: abz_allreduce_sum + abz_iai_solve_sharded(exchange=NULL)", ranks=world, identical=bool(good), numevals=nen,
+     exchanges=nest.last_exchanges)
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 dist.destroy_process_group()
