@@ -269,6 +269,9 @@ inline bool mma_resolvent_supported(int n) { return n >= 4 && n <= 32; }
 
 // warps per CTA (= per SM): 8 (255 registers) and 12 (168 registers, ~150 spill accesses) measure the same on B200;
 // 10 warps cannot have more than 168 registers either (warps are allocated four at a time: a 192-register, 320-thread
+// launch is refused with "too many resources requested"), and rebuilding the B fragments of the substitution phase at every
+// use instead of keeping bV[] / bM[] does not lower the 12-warp variant's spills (the pressure peak is in the LU phase);
+// 10 warps cannot have more than 168 registers either (warps are allocated four at a time: a 192-register, 320-thread
 // launch is refused with "too many resources requested")
 // (the kernel is bound by the FP64 pipe that DMMA and DFMA share, not by occupancy); 8 is the default
 inline int mma_resolvent_warps() {
