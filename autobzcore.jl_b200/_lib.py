@@ -324,25 +324,21 @@ class DeviceRule:
         self.ctx.check(self.ctx.lib.abz_rule_eigvals(self.ctx.h, self.h, _dp(ev)))
         return ev
 
+    def ggr_data(self, ndim, copy=True):
+        """get_ggr_data on the device: (energies [nnodes, n] ascending, velocities [nnodes, ndim, n]); cached in the rule"""
+        n = self.series.n
+        e = np.empty((self.nnodes, n)) if copy else None
+        v = np.empty((self.nnodes, ndim, n)) if copy else None
+        self.ctx.check(self.ctx.lib.abz_rule_ggr_data(self.ctx.h, self.h, int(ndim), _dp(e), _dp(v)))
+        return e, v
 
-def _ggr_data(self, ndim, copy=True):
-    """get_ggr_data on the device: (energies [nnodes, n] ascending, velocities [nnodes, ndim, n]); cached in the rule"""
-    n = self.series.n
-    e = np.empty((self.nnodes, n)) if copy else None
-    v = np.empty((self.nnodes, ndim, n)) if copy else None
-    self.ctx.check(self.ctx.lib.abz_rule_ggr_data(self.ctx.h, self.h, int(ndim), _dp(e), _dp(v)))
-    return e, v
+    def ggr_sum(self, E, scale=1.0):
+        """sum_ggr over the rule's nodes for every energy in E (needs ggr_data first)"""
+        Ev = np.ascontiguousarray(np.atleast_1d(np.asarray(E, dtype=np.float64)))
+        out = np.empty(Ev.size)
+        self.ctx.check(self.ctx.lib.abz_rule_ggr_sum(self.ctx.h, self.h, Ev.size, _dp(Ev), float(scale), _dp(out)))
+        return out
 
-
-def _ggr_sum(self, E, scale=1.0):
-    Ev = np.ascontiguousarray(np.atleast_1d(np.asarray(E, dtype=np.float64)))
-    out = np.empty(Ev.size)
-    self.ctx.check(self.ctx.lib.abz_rule_ggr_sum(self.ctx.h, self.h, Ev.size, _dp(Ev), float(scale), _dp(out)))
-    return out
-
-
-DeviceRule.ggr_data = _ggr_data
-DeviceRule.ggr_sum = _ggr_sum
 
 
 class DeviceNest:
