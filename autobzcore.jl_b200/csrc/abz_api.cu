@@ -89,8 +89,6 @@ constexpr int ABZ_RETRY_PIVOTED = 1;   // internal: the unpivoted fast path saw 
 struct abz_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;                  // second stream for the QL pieces of run_eig
-    std::vector<cudaEvent_t> pipe_events;
     std::string err;
     uint64_t next_id = 1;
     std::unordered_map<uint64_t, std::unique_ptr<Series>> series;
@@ -292,13 +290,10 @@ int check_errflag(abz_ctx* ctx, const char* what) {
 
 // Householder tridiagonalisation of nk materialised matrices into ctx->eig_d / eig_e (structure of arrays):
 // n <= 32: one warp per matrix with the rows in registers; else one CTA per matrix in shared memory
-static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n, int* herm_flag = nullptr, double* dd = nullptr,
-                          double* ee = nullptr) {
-    if (!dd) {
-        CU(ctx, ctx->eig_d.reserve((size_t)nk * n * sizeof(double)));
-        CU(ctx, ctx->eig_e.reserve((size_t)nk * n * sizeof(double)));
-        dd = ctx->eig_d.as<double>(); ee = ctx->eig_e.as<double>();
-    }
+static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n, int* herm_flag = nullptr) {
+    CU(ctx, ctx->eig_d.reserve((size_t)nk * n * sizeof(double)));
+    CU(ctx, ctx->eig_e.reserve((size_t)nk * n * sizeof(double)));
+    double* dd = ctx->eig_d.as<double>(); double* ee = ctx->eig_e.as<double>();
     if (n <= 32 && ctx->eig_algo != 2) {
         const long nblk = std::min<long>((nk + 3) / 4, (long)ctx->sm_count * 16);
         static int minb = 0;      // resident CTAs per SM the compiler budgets registers for (2: 255 registers, 3: 168 + a few spills)
@@ -541,8 +536,6 @@ int32_t abz_ctx_destroy(abz_ctx* ctx) {
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     for (auto e : ctx->events) cudaEventDestroy(e);
-    for (auto e : ctx->pipe_events) cudaEventDestroy(e);
-    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ABZ_OK;
@@ -1106,37 +1099,12 @@ static int run_eig(abz_ctx* ctx, const double2* H, const double* wnode, long nk,
                    double* evals, double* acc) {
     if (nk <= 0) return ABZ_OK;
     if (ctx->eig_algo == 1 || n > EIG_MAXN) return run_eig_jacobi(ctx, H, wnode, nk, n, mode, kind, p0, p1, evals, acc);
-    // Pipeline over pieces of the batch: the implicit-QL kernel (one thread per matrix) is latency-bound and leaves the SMs
-    // mostly idle, the Householder kernel is throughput-bound - so piece p's QL runs on a second stream underneath piece
-    // p+1's tridiagonalisation (double-buffered d/e).
-    const long P = std::max<long>(4096, (((nk + 7) / 8 + 31) / 32) * 32);
-    const long npieces = (nk + P - 1) / P;
-    const long nblk = (nk + 31) / 32;                 // P is a multiple of 32: block offsets of the pieces are exact
+    { int rct = launch_tridiag(ctx, H, nk, n); if (rct) return rct; }
+    const long nblk = (nk + 31) / 32;
     if (mode == 0) CU(ctx, ctx->partial.reserve((size_t)nblk * sizeof(double)));
-    CU(ctx, ctx->eig_d.reserve((size_t)2 * P * n * sizeof(double)));
-    CU(ctx, ctx->eig_e.reserve((size_t)2 * P * n * sizeof(double)));
-    if (!ctx->stream2) CU(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-    while ((long)ctx->pipe_events.size() < 2 * npieces) {
-        cudaEvent_t e;
-        CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        ctx->pipe_events.push_back(e);
-    }
-    for (long p = 0; p < npieces; p++) {
-        const long k0 = p * P, nkp = std::min(P, nk - k0);
-        double* dd = ctx->eig_d.as<double>() + (p & 1) * P * n;
-        double* ee = ctx->eig_e.as<double>() + (p & 1) * P * n;
-        if (p >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[2 * (p - 2) + 1], 0));   // buffer free again
-        { int rct = launch_tridiag(ctx, H + k0 * (long)n * n, nkp, n, nullptr, dd, ee); if (rct) return rct; }
-        CU(ctx, cudaEventRecord(ctx->pipe_events[2 * p], ctx->stream));
-        cudaStream_t qs = npieces > 1 ? ctx->stream2 : ctx->stream;
-        if (npieces > 1) CU(ctx, cudaStreamWaitEvent(qs, ctx->pipe_events[2 * p], 0));
-        eig_tql_kernel<<<(unsigned)((nkp + 31) / 32), 32, 0, qs>>>(dd, ee, wnode ? wnode + k0 : nullptr, nkp, n, mode, kind, p0, p1,
-                                                                   evals ? evals + k0 * n : nullptr,
-                                                                   ctx->partial.as<double>() + k0 / 32, ctx->errflag.as<int>());
-        LAUNCH_CHECK(ctx, "eig_tql_kernel");
-        if (npieces > 1) CU(ctx, cudaEventRecord(ctx->pipe_events[2 * p + 1], qs));
-    }
-    if (npieces > 1) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[2 * (npieces - 1) + 1], 0));
+    eig_tql_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(ctx->eig_d.as<double>(), ctx->eig_e.as<double>(), wnode, nk, n, mode, kind, p0,
+                                                          p1, evals, ctx->partial.as<double>(), ctx->errflag.as<int>());
+    LAUNCH_CHECK(ctx, "eig_tql_kernel");
     if (mode == 0) {
         reduce_real_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), nblk, 1.0, acc);
         LAUNCH_CHECK(ctx, "reduce_real_kernel");
