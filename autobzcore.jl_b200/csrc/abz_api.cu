@@ -1102,7 +1102,7 @@ static int run_eig(abz_ctx* ctx, const double2* H, const double* wnode, long nk,
     { int rct = launch_tridiag(ctx, H, nk, n); if (rct) return rct; }
     const long nblk = (nk + 31) / 32;
     if (mode == 0) CU(ctx, ctx->partial.reserve((size_t)nblk * sizeof(double)));
-    eig_tql_kernel<<<(unsigned)nblk, 32, 0, ctx->stream>>>(ctx->eig_d.as<double>(), ctx->eig_e.as<double>(), wnode, nk, n, mode, kind, p0,
+    eig_tql_kernel<<<(unsigned)nblk, 32, (size_t)2 * n * 32 * sizeof(double), ctx->stream>>>(ctx->eig_d.as<double>(), ctx->eig_e.as<double>(), wnode, nk, n, mode, kind, p0,
                                                           p1, evals, ctx->partial.as<double>(), ctx->errflag.as<int>());
     LAUNCH_CHECK(ctx, "eig_tql_kernel");
     if (mode == 0) {

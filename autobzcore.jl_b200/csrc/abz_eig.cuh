@@ -565,59 +565,75 @@ eig_tridiag_warp_kernel(const double2* __restrict__ H, long nk, int n, double* _
 // (EISPACK imtql1 / "tqli" without vectors), one thread per matrix.  mode 0: partial[cta] = sum_k wnode_k sum_n g(e_n);
 // mode 1: evals[k*n + i] ascending.
 constexpr int EIG_MAXN = 64;
+// The working arrays d[i], e[i] of thread `lane` live in shared memory as ds[i*32 + lane]: whatever index each lane is at
+// (the lanes of a warp diverge in l, m, i), lane t only touches banks 2t, 2t+1 - two wavefronts per access, no conflicts -
+// where per-thread local arrays gave 32 scattered sectors per access.  shared: 2 * n * 32 doubles per (one-warp) block.
+#define TQL_D(i) ds[(i) * 32 + lane]
+#define TQL_E(i) es[(i) * 32 + lane]
 __global__ void __launch_bounds__(32)
 eig_tql_kernel(const double* __restrict__ din, const double* __restrict__ ein, const double* __restrict__ wnode, long nk, int n,
                int mode, int kind, double p0, double p1, double* __restrict__ evals, double* __restrict__ partial,
                int* __restrict__ errflag) {
+    extern __shared__ double tql_smem[];
+    double* ds = tql_smem;
+    double* es = tql_smem + n * 32;
+    const int lane = threadIdx.x;
     const long k = (long)blockIdx.x * 32 + threadIdx.x;
-    double d[EIG_MAXN], e[EIG_MAXN];
     double val = 0.0;
     if (k < nk) {
         bool bad = false;
-        for (int i = 0; i < n; i++) { d[i] = din[(long)i * nk + k]; e[i] = ein[(long)i * nk + k]; bad |= !(isfinite(d[i]) && isfinite(e[i])); }
+        for (int i = 0; i < n; i++) {
+            const double dv = din[(long)i * nk + k], ev = ein[(long)i * nk + k];
+            TQL_D(i) = dv; TQL_E(i) = ev;
+            bad |= !(isfinite(dv) && isfinite(ev));
+        }
         if (bad) { *errflag = 1; }
         else {
             for (int l = 0; l < n; l++) {
                 int iter = 0, m;
                 do {
                     for (m = l; m < n - 1; m++) {
-                        const double dd = fabs(d[m]) + fabs(d[m + 1]);
-                        if (fabs(e[m]) <= 2.220446049250313e-16 * dd) break;
+                        const double dd = fabs(TQL_D(m)) + fabs(TQL_D(m + 1));
+                        if (fabs(TQL_E(m)) <= 2.220446049250313e-16 * dd) break;
                     }
                     if (m != l) {
                         if (iter++ == 60) { *errflag = 1; break; }
-                        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                        const double dl = TQL_D(l), el = TQL_E(l);
+                        double g = (TQL_D(l + 1) - dl) / (2.0 * el);
                         double r = sqrt(fma(g, g, 1.0));
-                        g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? r : -r));
+                        g = TQL_D(m) - dl + el / (g + (g >= 0.0 ? r : -r));
                         double s = 1.0, c = 1.0, p = 0.0;
                         int i;
                         for (i = m - 1; i >= l; i--) {
-                            double f = s * e[i], b = c * e[i];
-                            e[i + 1] = (r = sqrt(fma(f, f, g * g)));      // plain sqrt: band energies are nowhere near the overflow range
-                            if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+                            const double ei = TQL_E(i);
+                            double f = s * ei, b = c * ei;
+                            r = sqrt(fma(f, f, g * g));      // plain sqrt: band energies are nowhere near the overflow range
+                            TQL_E(i + 1) = r;
+                            if (r == 0.0) { TQL_D(i + 1) -= p; TQL_E(m) = 0.0; break; }
                             const double rinv = 1.0 / r;
                             s = f * rinv; c = g * rinv;
-                            g = d[i + 1] - p;
-                            r = (d[i] - g) * s + 2.0 * c * b;
-                            d[i + 1] = g + (p = s * r);
+                            g = TQL_D(i + 1) - p;
+                            r = (TQL_D(i) - g) * s + 2.0 * c * b;
+                            p = s * r;
+                            TQL_D(i + 1) = g + p;
                             g = c * r - b;
                         }
                         if (r == 0.0 && i >= l) continue;
-                        d[l] -= p; e[l] = g; e[m] = 0.0;
+                        TQL_D(l) -= p; TQL_E(l) = g; TQL_E(m) = 0.0;
                     }
                 } while (m != l);
             }
             if (mode == 1) {
                 for (int i = 1; i < n; i++) {     // insertion sort, ascending
-                    const double x = d[i];
+                    const double x = TQL_D(i);
                     int j = i - 1;
-                    while (j >= 0 && d[j] > x) { d[j + 1] = d[j]; j--; }
-                    d[j + 1] = x;
+                    while (j >= 0 && TQL_D(j) > x) { TQL_D(j + 1) = TQL_D(j); j--; }
+                    TQL_D(j + 1) = x;
                 }
-                for (int i = 0; i < n; i++) evals[k * n + i] = d[i];
+                for (int i = 0; i < n; i++) evals[k * n + i] = TQL_D(i);
             } else {
                 double v = 0.0;
-                for (int i = 0; i < n; i++) v += eig_kernel_value(d[i], kind, p0, p1);
+                for (int i = 0; i < n; i++) v += eig_kernel_value(TQL_D(i), kind, p0, p1);
                 val = (wnode ? wnode[k] : 1.0) * v;
             }
         }
@@ -627,6 +643,8 @@ eig_tql_kernel(const double* __restrict__ din, const double* __restrict__ ein, c
         if (threadIdx.x == 0) partial[blockIdx.x] = val;
     }
 }
+#undef TQL_D
+#undef TQL_E
 
 // ---- K3-sweep: tr[(z_w - H(k))^-1] for MANY frequencies from ONE tridiagonalisation per k --------------------------
 // For Hermitian H(k) and a scalar self-energy (folded into z) the trace of the resolvent is invariant under the
