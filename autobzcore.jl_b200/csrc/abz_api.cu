@@ -42,14 +42,22 @@ struct DevBuf {
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// Device-memory pool of a context: series / rule / arena buffers are recycled by (rounded) size instead of going through
+// cudaMalloc / cudaFree, whose cost on a busy device is erratic (measured: 0.7 ms to 256 ms for the same teardown) and
+// which would otherwise sit inside every solve that builds a rule (AutoPTR refinements, the end-to-end path).
+cudaError_t pool_alloc(abz_ctx* ctx, void** p, size_t bytes);
+void pool_free(abz_ctx* ctx, void* p);
+
 struct Series {
+    abz_ctx* ctx = nullptr;
     double2* c = nullptr;
     int n = 0, M[3] = {1, 1, 1}, lo[3] = {0, 0, 0};
     double period[3] = {1, 1, 1};
-    ~Series() { if (c) cudaFree(c); }
+    ~Series() { pool_free(ctx, c); }
 };
 
 struct Rule {
+    abz_ctx* ctx = nullptr;
     uint64_t series_id = 0;
     Series* s = nullptr;
     int N = 0;
@@ -66,19 +74,20 @@ struct Rule {
     double2* d_H = nullptr;   // materialised H(k) [nnz][n*n]
     double* d_ggr_e = nullptr; double* d_ggr_v = nullptr; int ggr_ndim = 0;   // GGR data pass: energies [nnz][n], velocities [nnz][ndim][n]
     ~Rule() {
-        cudaFree(d_ggr_e); cudaFree(d_ggr_v);
-        cudaFree(d_plane_k3); cudaFree(d_plane_rowptr); cudaFree(d_row_k2); cudaFree(d_row_nodeptr);
-        cudaFree(d_node_k1); cudaFree(d_node_w); cudaFree(d_H);
-        for (auto& p : d_ptab) cudaFree(p);
+        pool_free(ctx, d_ggr_e); pool_free(ctx, d_ggr_v);
+        pool_free(ctx, d_plane_k3); pool_free(ctx, d_plane_rowptr); pool_free(ctx, d_row_k2); pool_free(ctx, d_row_nodeptr);
+        pool_free(ctx, d_node_k1); pool_free(ctx, d_node_w); pool_free(ctx, d_H);
+        for (auto& p : d_ptab) pool_free(ctx, p);
     }
 };
 
 struct Nest {
+    abz_ctx* ctx = nullptr;
     Series* s = nullptr;
     int ndim = 3;
     long cap2 = 0, cap1 = 0;
     double2* L2 = nullptr; double2* L1 = nullptr;
-    ~Nest() { cudaFree(L2); cudaFree(L1); }
+    ~Nest() { pool_free(ctx, L2); pool_free(ctx, L1); }
 };
 
 struct Chunk { long p0, p1, r0, r1; };
@@ -89,6 +98,9 @@ constexpr int ABZ_RETRY_PIVOTED = 1;   // internal: the unpivoted fast path saw 
 struct abz_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    std::unordered_map<void*, size_t> pool_size;                    // every live or pooled block -> rounded size
+    std::unordered_map<size_t, std::vector<void*>> pool_free_list;   // rounded size -> free blocks
+    size_t pool_held = 0, pool_cap = (size_t)8 << 30;               // bytes parked in the free lists / their limit
     std::string err;
     uint64_t next_id = 1;
     std::unordered_map<uint64_t, std::unique_ptr<Series>> series;
@@ -116,6 +128,46 @@ namespace {
 int fail(abz_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg; else g_create_error = msg;
     return code;
+}
+
+size_t pool_round(size_t b) { const size_t g = b > ((size_t)1 << 20) ? ((size_t)1 << 20) : 4096; return ((b + g - 1) / g) * g; }
+
+cudaError_t pool_alloc(abz_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) return cudaSuccess;
+    const size_t r = pool_round(bytes);
+    auto it = ctx->pool_free_list.find(r);
+    if (it != ctx->pool_free_list.end() && !it->second.empty()) {
+        *p = it->second.back();
+        it->second.pop_back();
+        ctx->pool_held -= r;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, r);
+    if (e != cudaSuccess) {            // out of memory: give the parked blocks back to the driver and retry once
+        cudaGetLastError();
+        for (auto& kv : ctx->pool_free_list) { for (void* q : kv.second) { cudaFree(q); ctx->pool_size.erase(q); } kv.second.clear(); }
+        ctx->pool_held = 0;
+        e = cudaMalloc(p, r);
+    }
+    if (e == cudaSuccess) ctx->pool_size[*p] = r; else *p = nullptr;
+    return e;
+}
+
+void pool_free(abz_ctx* ctx, void* p) {
+    if (!p) return;
+    if (!ctx) { cudaFree(p); return; }
+    auto it = ctx->pool_size.find(p);
+    if (it == ctx->pool_size.end()) { cudaFree(p); return; }
+    const size_t r = it->second;
+    if (ctx->pool_held + r > ctx->pool_cap) { cudaFree(p); ctx->pool_size.erase(it); return; }
+    ctx->pool_free_list[r].push_back(p);       // work that used p is ordered before any reuse: one stream per context
+    ctx->pool_held += r;
+}
+
+void pool_release(abz_ctx* ctx) {
+    for (auto& kv : ctx->pool_free_list) for (void* q : kv.second) cudaFree(q);
+    ctx->pool_free_list.clear(); ctx->pool_size.clear(); ctx->pool_held = 0;
 }
 
 #define CU(ctx, expr)                                                                                     \
@@ -150,7 +202,7 @@ template <class T>
 int upload(abz_ctx* ctx, T** dptr, const std::vector<T>& h) {
     *dptr = nullptr;
     if (h.empty()) return ABZ_OK;
-    CU(ctx, cudaMalloc((void**)dptr, h.size() * sizeof(T)));
+    CU(ctx, pool_alloc(ctx, (void**)dptr, h.size() * sizeof(T)));
     CU(ctx, cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     return ABZ_OK;
 }
@@ -181,7 +233,7 @@ int finish_rule(abz_ctx* ctx, Rule* r) {
     }
     for (int d = 0; d < 3; d++) {
         size_t cnt = (size_t)s->M[d] * r->N;
-        CU(ctx, cudaMalloc((void**)&r->d_ptab[d], cnt * sizeof(double2)));
+        CU(ctx, pool_alloc(ctx, (void**)&r->d_ptab[d], cnt * sizeof(double2)));
         phase_table_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(r->d_ptab[d], s->M[d], s->lo[d], r->N);
         LAUNCH_CHECK(ctx, "phase_table_kernel");
     }
@@ -533,6 +585,7 @@ int32_t abz_ctx_destroy(abz_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     abz_comm_destroy(ctx);
     ctx->rules.clear(); ctx->nests.clear(); ctx->series.clear();
+    pool_release(ctx);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     for (auto e : ctx->events) cudaEventDestroy(e);
@@ -571,10 +624,11 @@ int32_t abz_series_create(abz_ctx* ctx, const double* coeffs, int32_t is_complex
         if (M[d] < 1 || !(period[d] > 0)) return fail(ctx, ABZ_E_INVALID, "M >= 1 and period > 0 required");
     cudaSetDevice(ctx->device);
     auto s = std::make_unique<Series>();
+    s->ctx = ctx;
     s->n = norb;
     size_t cnt = (size_t)norb * norb;
     for (int d = 0; d < 3; d++) { s->M[d] = M[d]; s->lo[d] = lo[d]; s->period[d] = period[d]; cnt *= M[d]; }
-    CU(ctx, cudaMalloc((void**)&s->c, cnt * sizeof(double2)));
+    CU(ctx, pool_alloc(ctx, (void**)&s->c, cnt * sizeof(double2)));
     if (is_complex) {
         CU(ctx, cudaMemcpyAsync(s->c, coeffs, cnt * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -604,6 +658,7 @@ int32_t abz_rule_create_full(abz_ctx* ctx, abz_series_t sid, int32_t npt, int32_
     if (!out || npt < 1 || k3_lo < 0 || k3_hi > npt || k3_lo > k3_hi) return fail(ctx, ABZ_E_INVALID, "invalid grid range");
     cudaSetDevice(ctx->device);
     auto r = std::make_unique<Rule>();
+    r->ctx = ctx;
     r->series_id = sid; r->s = s; r->N = npt; r->full = true;
     const long N = npt;
     r->np3 = k3_hi - k3_lo;
@@ -631,6 +686,7 @@ int32_t abz_rule_create_sym(abz_ctx* ctx, abz_series_t sid, int32_t npt, const i
     if (!out || !wsym || npt < 1 || k3_lo < 0 || k3_stride < 1) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
     cudaSetDevice(ctx->device);
     auto r = std::make_unique<Rule>();
+    r->ctx = ctx;
     r->series_id = sid; r->s = s; r->N = npt; r->full = false;
     const long N = npt;
     r->h_plane_rowptr.push_back(0);
@@ -677,6 +733,7 @@ int32_t abz_rule_create_nodes(abz_ctx* ctx, abz_series_t sid, int32_t npt, int64
     if (!out || npt < 1 || nnodes < 0 || (nnodes > 0 && !idx)) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
     cudaSetDevice(ctx->device);
     auto r = std::make_unique<Rule>();
+    r->ctx = ctx;
     r->series_id = sid; r->s = s; r->N = npt; r->full = false;
     r->h_plane_rowptr.push_back(0);
     r->h_row_nodeptr.push_back(0);
@@ -792,6 +849,7 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
     }
     // CSR skeleton on the host (N^2 entries), node arrays on the device
     auto r = std::make_unique<Rule>();
+    r->ctx = ctx;
     r->series_id = sid; r->s = s; r->N = npt; r->full = false; r->nodes_on_host = false;
     r->h_plane_rowptr.push_back(0);
     r->h_row_nodeptr.push_back(0);
@@ -819,8 +877,8 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
     int rc = finish_rule(ctx, r.get());
     if (rc) return rc;
     if (nnz > 0) {
-        CU(ctx, cudaMalloc((void**)&r->d_node_k1, (size_t)nnz * sizeof(int)));
-        CU(ctx, cudaMalloc((void**)&r->d_node_w, (size_t)nnz * sizeof(double)));
+        CU(ctx, pool_alloc(ctx, (void**)&r->d_node_k1, (size_t)nnz * sizeof(int)));
+        CU(ctx, pool_alloc(ctx, (void**)&r->d_node_w, (size_t)nnz * sizeof(double)));
         CU(ctx, k3buf.reserve(row_k3.size() * sizeof(int)));
         CU(ctx, cudaMemcpyAsync(k3buf.p, row_k3.data(), row_k3.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         sym_row_fill_kernel<<<(unsigned)((r->nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(
@@ -864,14 +922,14 @@ int32_t abz_rule_materialize(abz_ctx* ctx, abz_rule_t rid) {
     CU(ctx, cudaMemGetInfo(&free_b, &total_b));
     if (bytes > free_b - std::min<size_t>(free_b, ctx->budget + ((size_t)1 << 30)))
         return fail(ctx, ABZ_E_OOM, "H(k) on this rule does not fit in device memory; use the streamed sums");
-    CU(ctx, cudaMalloc((void**)&r->d_H, bytes));
+    CU(ctx, pool_alloc(ctx, (void**)&r->d_H, bytes));
     long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
     auto chunks = plan_chunks(r, node_cap_for(ctx, s->n), (long)(ctx->budget / (rows1 * sizeof(double2))),
                               (long)(ctx->budget / (rows2 * sizeof(double2))));
     cudaEvent_t e0 = next_event(ctx);
     for (auto& ch : chunks) {
         int rc = eval_chunk(ctx, r, ch, true, r->d_H + r->h_row_nodeptr[ch.r0] * nn);
-        if (rc) { cudaFree(r->d_H); r->d_H = nullptr; return rc; }
+        if (rc) { pool_free(ctx, r->d_H); r->d_H = nullptr; return rc; }
     }
     cudaEvent_t e1 = next_event(ctx);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1206,9 +1264,9 @@ int32_t abz_rule_ggr_data(abz_ctx* ctx, abz_rule_t rid, int32_t ndim, double* en
     const long nn = (long)n * n;
     if (n > 64) return fail(ctx, ABZ_E_UNSUPPORTED, "norb > 64 is not supported by the GGR data pass");
     if (r->nnz > 0 && (!r->d_ggr_e || r->ggr_ndim != ndim)) {
-        cudaFree(r->d_ggr_e); cudaFree(r->d_ggr_v); r->d_ggr_e = r->d_ggr_v = nullptr;
-        CU(ctx, cudaMalloc((void**)&r->d_ggr_e, (size_t)r->nnz * n * sizeof(double)));
-        CU(ctx, cudaMalloc((void**)&r->d_ggr_v, (size_t)r->nnz * n * ndim * sizeof(double)));
+        pool_free(ctx, r->d_ggr_e); pool_free(ctx, r->d_ggr_v); r->d_ggr_e = r->d_ggr_v = nullptr;
+        CU(ctx, pool_alloc(ctx, (void**)&r->d_ggr_e, (size_t)r->nnz * n * sizeof(double)));
+        CU(ctx, pool_alloc(ctx, (void**)&r->d_ggr_v, (size_t)r->nnz * n * ndim * sizeof(double)));
         // JacobianSeries coefficients: 2 pi i R_d / period_d * H_R
         const size_t ctot = (size_t)nn * s->M[0] * s->M[1] * s->M[2];
         DevBuf dco[3], Vc[3];
@@ -1250,7 +1308,7 @@ int32_t abz_rule_ggr_data(abz_ctx* ctx, abz_rule_t rid, int32_t ndim, double* en
         cudaEvent_t e1 = next_event(ctx);
         int rc = check_errflag(ctx, "abz_rule_ggr_data");
         collect_timings(ctx, {}, {{e0, e1}});
-        if (rc) { cudaFree(r->d_ggr_e); cudaFree(r->d_ggr_v); r->d_ggr_e = r->d_ggr_v = nullptr; return rc; }
+        if (rc) { pool_free(ctx, r->d_ggr_e); pool_free(ctx, r->d_ggr_v); r->d_ggr_e = r->d_ggr_v = nullptr; return rc; }
         r->ggr_ndim = ndim;
     }
     if (energies && r->nnz > 0)
@@ -1355,10 +1413,11 @@ int32_t abz_nest_create(abz_ctx* ctx, abz_series_t sid, int32_t ndim, int64_t ca
         if (s->M[d] != 1) return fail(ctx, ABZ_E_INVALID, "variables in Fourier series don't match domain");
     cudaSetDevice(ctx->device);
     auto nst = std::make_unique<Nest>();
+    nst->ctx = ctx;
     nst->s = s; nst->ndim = ndim; nst->cap2 = cap2; nst->cap1 = cap1;
     const size_t nn = (size_t)s->n * s->n;
-    if (ndim == 3 && cap2 > 0) CU(ctx, cudaMalloc((void**)&nst->L2, (size_t)cap2 * nn * s->M[0] * s->M[1] * sizeof(double2)));
-    if (ndim >= 2 && cap1 > 0) CU(ctx, cudaMalloc((void**)&nst->L1, (size_t)cap1 * nn * s->M[0] * sizeof(double2)));
+    if (ndim == 3 && cap2 > 0) CU(ctx, pool_alloc(ctx, (void**)&nst->L2, (size_t)cap2 * nn * s->M[0] * s->M[1] * sizeof(double2)));
+    if (ndim >= 2 && cap1 > 0) CU(ctx, pool_alloc(ctx, (void**)&nst->L1, (size_t)cap1 * nn * s->M[0] * sizeof(double2)));
     uint64_t id = ctx->next_id++;
     ctx->nests[id] = std::move(nst);
     *out = id;
