@@ -535,3 +535,29 @@ def test_frequency_sweep_rejects_non_hermitian_h(ctx, orc, n):
     finally:
         ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
     assert rel(R.resolvent_sum(z, scale=1 / 64), ref) < 1e-10       # the context stays usable
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_iai_device_vs_oracle_on_random_problems(ctx, orc, seed):
+    """random Hermitian series (1-3 orbitals, 1-3 dimensions, cubic / tetrahedral limits, real DOS / complex trace values):
+    the device engine with one warp per innermost integral takes the oracle recursion's decisions (same numevals) and agrees
+    to 1e-10"""
+    rng = np.random.default_rng(1000 + seed)
+    ndim, n = 1 + seed % 3, 1 + (seed // 3) % 3
+    lkind, vkind = seed % 2, (seed // 2) % 2
+    M = (3,) * ndim
+    c = rng.standard_normal((n, n) + M) + 1j * rng.standard_normal((n, n) + M)
+    rev = (slice(None), slice(None)) + (slice(None, None, -1),) * ndim
+    c = 0.5 * (c + np.conj(np.swapaxes(c[rev], 0, 1)))
+    fs = ab.FourierSeries(c, period=1.0, lo=(-1,) * ndim, norb=n)
+    So = orc.Series(c.reshape((n, n) + M + (1,) * (3 - ndim)), (-1,) * ndim + (0,) * (3 - ndim))
+    z = complex(rng.uniform(-1, 1), [0.3, 0.1, 0.05][seed % 3])
+    tol = [3e-1, 3e-2, 3e-3][(seed // 4) % 3]
+    la = [0.5] * ndim if lkind else [0.0] * ndim
+    lb = None if lkind else [1.0] * ndim
+    Io, Eo, neo = orc.iai(So, ndim, lkind, la, lb, vkind=vkind, z=z, atol=tol)
+    nest = L.DeviceNest(ctx, fs.device(ctx), ndim, 64 if ndim == 3 else 0, 2048 if ndim >= 2 else 0)
+    for leaves in (True, False):
+        I, E, ne, rounds, launches = nest.iai_solve(lkind, la, lb, L.F_RESOLVENT_TRACE, vkind, z, None, None, tol, 0.0, 2 ** 62, device_leaves=leaves)
+        assert ne == neo
+        assert abs(I - Io) <= 1e-10 * max(abs(Io), 1e-12)

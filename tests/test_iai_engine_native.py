@@ -161,3 +161,29 @@ def test_engine_sharded_over_ranks_gloo(tmp_path, orc, eng, nranks):
     outs = [p.communicate(timeout=600)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_engine_matches_recursion_on_random_problems(orc, eng):
+    """property test: on random small Wannier-like series, random complex frequencies, tolerances, limits and dimensions the
+    level-synchronous engine (both modes) takes exactly the oracle recursion's decisions"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(seed=st.integers(0, 10 ** 6), ndim=st.integers(1, 3), n=st.integers(1, 3), lkind=st.integers(0, 1), leaf=st.booleans(),
+           vkind=st.integers(0, 1), tol=st.sampled_from([3e-1, 3e-2, 3e-3]), eta=st.sampled_from([0.3, 0.1, 0.05]))
+    def check(seed, ndim, n, lkind, leaf, vkind, tol, eta):
+        rng = np.random.default_rng(seed)
+        M = (3,) * ndim + (1,) * (3 - ndim)
+        c = rng.standard_normal((n, n) + M) + 1j * rng.standard_normal((n, n) + M)
+        # Hermitian H(k): H_{-R} = H_R^dagger
+        c = 0.5 * (c + np.conj(np.transpose(c[:, :, ::-1, ::-1, ::-1], (1, 0, 2, 3, 4))))
+        S = orc.Series(c, (-1,) * ndim + (0,) * (3 - ndim))
+        z = complex(rng.uniform(-1, 1), eta)
+        la = [0.5] * ndim if lkind else [0.0] * ndim
+        lb = None if lkind else [1.0] * ndim
+        Io, Eo, neo = orc.iai(S, ndim, lkind, la, lb, vkind=vkind, z=z, atol=tol)
+        rc, I, E, ne, _ = _solve(eng, S, ndim, lkind, la, lb, 0, vkind, z, None, tol, 0.0, leaf)
+        assert rc == 0 and ne == neo
+        assert abs(I - Io) <= 1e-12 * max(abs(Io), 1e-12) and abs(E - Eo) <= 1e-9 * max(Eo, 1e-300)
+
+    check()
