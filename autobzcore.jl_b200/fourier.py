@@ -79,6 +79,23 @@ class BatchIntegrand:
         self.f, self.dtype, self.max_batch = f, np.dtype(dtype), max_batch
 
 
+class NestedBatchIntegrand:
+    """NestedBatchIntegrand(f::Tuple, y, x; max_batch) (src/batch.jl:50-77): the reference's container of per-thread worker
+    copies of one integrand for multi-threaded nested evaluation (FourierIntegrand(p, ws, nest), test/fourier.jl:24-37).
+    Here the batch is what goes to the device, so the workers collapse to the first one: it is evaluated on whole batches
+    of nodes (H(k) from the device), at most max_batch at a time.  Results equal the un-nested integrand's."""
+
+    def __init__(self, f, dtype=np.complex128, max_batch=None):
+        workers = tuple(f) if isinstance(f, (tuple, list)) else (f,)
+        if not workers:
+            raise ValueError("NestedBatchIntegrand needs at least one worker")
+        if max_batch is not None and max_batch <= 0:
+            raise ValueError("maximum batch size must be positive")
+        while isinstance(workers[0], NestedBatchIntegrand):      # nests of nests: same integrand underneath
+            workers = workers[0].f
+        self.f, self.dtype, self.max_batch = workers, np.dtype(dtype), max_batch
+
+
 class _NativeIntegrand:
     """Base of the integrands whose arithmetic runs on the device."""
     fkind = _lib.F_RESOLVENT_TRACE
@@ -187,9 +204,20 @@ class FourierIntegrand:
     """FourierIntegrand(f, s, args...; kws...) (src/fourier.jl:37-58): integrand f(FourierValue(x, s(x)), args...; kws...)
     with the series evaluated one dimension at a time by the specialised rules."""
 
-    def __init__(self, f, s, *args, **kws):
+    def __init__(self, f, s, *args, nest=None, **kws):
         if not isinstance(s, FourierSeries):
             raise TypeError("s must be a FourierSeries")
+        if nest is not None:
+            # FourierIntegrand(f, w, nest::NestedBatchIntegrand) (src/fourier.jl:37-46): the nest's workers evaluate f
+            if not isinstance(nest, NestedBatchIntegrand):
+                raise TypeError("nest must be a NestedBatchIntegrand")
+            worker, mb, dt = nest.f[0], nest.max_batch, nest.dtype
+
+            def batch(y, x, *a, **k):
+                for i in range(len(y)):
+                    y[i] = worker(FourierValue(x.x[i], x.s[i]), *a, **k)
+
+            f = BatchIntegrand(batch, dtype=dt, max_batch=mb)
         self.f, self.s, self.args, self.kws = f, s, tuple(args), dict(kws)
 
     @property

@@ -277,3 +277,25 @@ def test_batchsolve_log_archive(tmp_path, orc, svo):
     ab.batchsolve_log(tmp_path / "kw.npz", solver2, [{"eta": 0.1, "omega": w} for w in ws])
     arc = np.load(tmp_path / "kw.npz")
     assert np.array_equal(arc["kwargs/omega"], ws) and arc["I"].dtype == np.complex128
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_nested_batch_integrand_equals_plain(d):
+    """test/fourier.jl:24-37: prob1 = FourierIntegrand(p, s), prob2 = FourierIntegrand(p, ws, nest) with
+    nest = NestedBatchIntegrand(ntuple(n -> deepcopy(p), nouter), ...): solve(prob1, alg).u ~ solve(prob2, alg).u for
+    NestedQuad(AuxQuadGKJL()) on CubicLimits and MonkhorstPack on the basis."""
+    s = lattice_series(d)
+    be = OracleBackend()
+
+    def p(x, a, b=0.0):
+        return a * x.s + b
+
+    nest = ab.NestedBatchIntegrand(tuple(p for _ in range(3)), dtype=np.complex128, max_batch=50)
+    f1 = ab.FourierIntegrand(p, s, 1.3, b=4.2)
+    f2 = ab.FourierIntegrand(p, s, 1.3, nest=nest, b=4.2)
+    for alg, dom in ((ab.NestedQuad(ab.AuxQuadGKJL()), ab.CubicLimits([0.0] * d, [1.0] * d)), (ab.MonkhorstPack(npt=9), ab.Basis(np.eye(d)))):
+        u1 = ab.solve(ab.IntegralProblem(f1, dom), alg, abstol=1e-8, backend=be).u
+        u2 = ab.solve(ab.IntegralProblem(f2, dom), alg, abstol=1e-8, backend=be).u
+        assert abs(u1 - u2) < 1e-12 * abs(u1) and abs(u1 - 4.2) < 1e-7
+    with pytest.raises(TypeError):
+        ab.FourierIntegrand(p, s, nest=object())
