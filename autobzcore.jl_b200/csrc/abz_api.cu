@@ -110,6 +110,7 @@ struct abz_ctx {
     size_t budget = (size_t)4096 << 20;
     int fused_small = 1;
     int eig_algo = 0;             // 0: tridiagonalisation + QL, 1: two-sided Jacobi
+    int leaf_spill = LEAF_SPILL;  // segments per device-side innermost integral beyond the 63 kept in shared memory
     bool force_generic = false;   // set while re-running a call whose fast path asked for pivoting
     DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d, iai_in, iai_out, eig_d, eig_e, symw;
     void* pin_in = nullptr; size_t pin_in_cap = 0;     // pinned staging for the IAI engine's per-round traffic
@@ -602,6 +603,8 @@ int32_t abz_ctx_set_option(abz_ctx* ctx, int32_t option, int64_t value) {
             ctx->budget = (size_t)value << 20; return ABZ_OK;
         case ABZ_OPT_FUSED_SMALL: ctx->fused_small = (int)value; return ABZ_OK;
         case ABZ_OPT_EIG_ALGO: ctx->eig_algo = (int)value; return ABZ_OK;
+        case ABZ_OPT_IAI_LEAF_SPILL: if (value < 1 || value > (1 << 20)) return fail(ctx, ABZ_E_INVALID, "spill capacity out of range");
+            ctx->leaf_spill = (int)value; return ABZ_OK;
     }
     return fail(ctx, ABZ_E_INVALID, "unknown option");
 }
@@ -1598,6 +1601,7 @@ struct IaiDeviceBackend {
     abz_ctx* ctx; Nest* nst; int fkind, vkind; double2 z; const double2* dsig; abz_iai::cplx la, lb;
     double rtol; int64_t maxevals;
     abz_exchange_fn xfn = nullptr; void* xuser = nullptr;
+    bool heap_overflow = false;
 
     // in-place sum over ranks: the caller's hook (e.g. a host-language MPI / torch.distributed allreduce) or NCCL on the ctx communicator
     int exchange(double* buf, size_t n) {
@@ -1721,7 +1725,7 @@ struct IaiDeviceBackend {
         if (flag) {
             cudaMemsetAsync(ef, 0, sizeof(int), ctx->stream);
             if ((flag & 2) && !(flag & 1) && !ctx->force_generic) return ABZ_RETRY_PIVOTED;
-            if (flag & 4) return fail(ctx, ABZ_E_UNSUPPORTED, "abz_iai_solve: an innermost integral outgrew the device segment heap");
+            if (flag & 4) { heap_overflow = true; return fail(ctx, ABZ_E_UNSUPPORTED, "abz_iai_solve: an innermost integral outgrew the device segment heap"); }
             return fail(ctx, ABZ_E_SINGULAR, "abz_iai_solve: singular matrix or NaN/Inf in the integrand");
         }
         R.seg_I.resize(ns); R.seg_D.resize(ns);
@@ -1744,7 +1748,8 @@ struct IaiDeviceBackend {
         Series* s = nst->s;
         const long stride = (long)s->n * s->n * s->M[0];
         // global spill area for segment heaps deeper than the shared-memory levels
-        CU(ctx, ctx->tmp_d.reserve((size_t)nt * LEAF_SPILL * sizeof(LeafSeg) + 64));
+        const int spill_cap = ctx->leaf_spill;
+        CU(ctx, ctx->tmp_d.reserve((size_t)nt * spill_cap * sizeof(LeafSeg) + 64));
         unsigned g = (unsigned)((nt + LEAF_WARPS - 1) / LEAF_WARPS);
         static bool attr_leaf = false;
         if (!attr_leaf) {
@@ -1758,7 +1763,7 @@ struct IaiDeviceBackend {
         LeafSeg* spill = reinterpret_cast<LeafSeg*>(ctx->tmp_d.as<char>() + 64);
 #define LEAF_LAUNCH(NORB)                                                                                              \
     iai_leaf_kernel<NORB><<<g, LEAF_WARPS * 32, (size_t)LEAF_WARPS * s->M[0] * NORB * NORB * sizeof(double2), ctx->stream>>>(nst->L1, stride, ta, tb, tt, ts, nt, s->M[0], s->lo[0], s->period[0], \
-                                                                 fkind, vkind, z, dsig, la, lb, rtol, (long long)maxevals, spill, out, \
+                                                                 fkind, vkind, z, dsig, la, lb, rtol, (long long)maxevals, spill, spill_cap, out, \
                                                                  ctx->errflag.as<int>())
         if (s->n == 1) LEAF_LAUNCH(1); else if (s->n == 2) LEAF_LAUNCH(2); else LEAF_LAUNCH(3);
 #undef LEAF_LAUNCH
@@ -1811,6 +1816,21 @@ int32_t abz_iai_solve_sharded(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
     abz_iai::Engine<IaiDeviceBackend> eng(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, leaf, rank, nranks);
     rc = eng.run();
     ctx->force_generic = false;
+    if (rc == ABZ_E_UNSUPPORTED && leaf && be.heap_overflow && nranks == 1) {
+        // an innermost integral outgrew the device segment heap (1087 segments): same solve with host-driven innermost panels,
+        // whose heaps live in host memory (single rank only: ranks must not diverge in their exchange sequence)
+        be.heap_overflow = false;
+        abz_iai::Engine<IaiDeviceBackend> eng2(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, false, rank, nranks);
+        rc = eng2.run();
+        ctx->force_generic = false;
+        if (stats) { stats[0] = eng2.numevals; stats[1] = eng.rounds + eng2.rounds; stats[2] = ctx->launches - launches0; stats[3] = 0; }
+        if (rc == abz_iai::IAI_E_NAN) return fail(ctx, ABZ_E_SINGULAR, eng2.error);
+        if (rc == abz_iai::IAI_E_ARENA) return fail(ctx, ABZ_E_OOM, eng2.error);
+        if (rc == abz_iai::IAI_E_STALL) return fail(ctx, ABZ_E_INVALID, eng2.error);
+        if (rc) return rc;
+        out[0] = eng2.result.re; out[1] = eng2.result.im; out[2] = eng2.result_err;
+        return ABZ_OK;
+    }
     if (stats) { stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = ctx->launches - launches0; stats[3] = eng.exchanges; }
     if (rc == abz_iai::IAI_E_NAN) return fail(ctx, ABZ_E_SINGULAR, eng.error);
     if (rc == abz_iai::IAI_E_ARENA) return fail(ctx, ABZ_E_OOM, eng.error);

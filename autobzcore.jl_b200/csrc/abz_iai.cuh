@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(LEAF_WARPS * 32)
 iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __restrict__ task_a,
                 const double* __restrict__ task_b, const double* __restrict__ task_atol, const long* __restrict__ task_slot,
                 long ntask, int M1, int lo, double period, int fkind, int vkind, double2 z, const double2* __restrict__ sigma,
-                abz_iai::cplx la, abz_iai::cplx lb, double rtol, long long maxevals, LeafSeg* __restrict__ spill,
+                abz_iai::cplx la, abz_iai::cplx lb, double rtol, long long maxevals, LeafSeg* __restrict__ spill, int spill_cap,
                 double* __restrict__ out, int* __restrict__ errflag) {
     constexpr int NN = NORB * NORB;
     __shared__ LeafSeg heap_s[LEAF_WARPS][LEAF_SMEM_SEGS];
@@ -160,7 +160,7 @@ iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __
     __syncwarp();
     const double atol = task_atol[task];
     LeafSeg* hs = heap_s[w];
-    LeafSeg* hg = spill + task * LEAF_SPILL;
+    LeafSeg* hg = spill + task * (long)spill_cap;
 #define LEAF_AT(i) (((i) <= LEAF_SMEM_SEGS) ? hs[(i) - 1] : hg[(i) - 1 - LEAF_SMEM_SEGS])
     const int half = lane >> 4, j = lane & 15;
     // ---- first panel
@@ -233,7 +233,7 @@ iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __
             E = (E - sE) + nE + E2;
             ne += 30;
             if (!(isfinite(nE) && isfinite(E2))) { atomicOr(errflag, 1); go = 0; }
-            else if (len + 2 > LEAF_SMEM_SEGS + LEAF_SPILL) { atomicOr(errflag, 4); go = 0; }
+            else if (len + 2 > LEAF_SMEM_SEGS + spill_cap) { atomicOr(errflag, 4); go = 0; }
             else {
                 LeafSeg sg[2] = {LeafSeg{nE, sa, mid, nI.re, nI.im}, LeafSeg{E2, mid, sb, I2re, I2im}};
 #pragma unroll
