@@ -603,7 +603,7 @@ int32_t abz_ctx_set_option(abz_ctx* ctx, int32_t option, int64_t value) {
             ctx->budget = (size_t)value << 20; return ABZ_OK;
         case ABZ_OPT_FUSED_SMALL: ctx->fused_small = (int)value; return ABZ_OK;
         case ABZ_OPT_EIG_ALGO: ctx->eig_algo = (int)value; return ABZ_OK;
-        case ABZ_OPT_IAI_LEAF_SPILL: if (value < 1 || value > (1 << 20)) return fail(ctx, ABZ_E_INVALID, "spill capacity out of range");
+        case ABZ_OPT_IAI_LEAF_SPILL: if (value == 0 || value < -63 || value > (1 << 20)) return fail(ctx, ABZ_E_INVALID, "spill capacity out of range");
             ctx->leaf_spill = (int)value; return ABZ_OK;
     }
     return fail(ctx, ABZ_E_INVALID, "unknown option");
@@ -1749,7 +1749,7 @@ struct IaiDeviceBackend {
         const long stride = (long)s->n * s->n * s->M[0];
         // global spill area for segment heaps deeper than the shared-memory levels
         const int spill_cap = ctx->leaf_spill;
-        CU(ctx, ctx->tmp_d.reserve((size_t)nt * spill_cap * sizeof(LeafSeg) + 64));
+        CU(ctx, ctx->tmp_d.reserve((size_t)nt * std::max(spill_cap, 1) * sizeof(LeafSeg) + 64));
         unsigned g = (unsigned)((nt + LEAF_WARPS - 1) / LEAF_WARPS);
         static bool attr_leaf = false;
         if (!attr_leaf) {

@@ -160,7 +160,8 @@ iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __
     __syncwarp();
     const double atol = task_atol[task];
     LeafSeg* hs = heap_s[w];
-    LeafSeg* hg = spill + task * (long)spill_cap;
+    LeafSeg* hg = spill + task * (long)(spill_cap > 0 ? spill_cap : 1);
+    const int cap_total = spill_cap < 0 ? -spill_cap : LEAF_SMEM_SEGS + spill_cap;   // negative: total capacity (test hook)
 #define LEAF_AT(i) (((i) <= LEAF_SMEM_SEGS) ? hs[(i) - 1] : hg[(i) - 1 - LEAF_SMEM_SEGS])
     const int half = lane >> 4, j = lane & 15;
     // ---- first panel
@@ -233,7 +234,7 @@ iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __
             E = (E - sE) + nE + E2;
             ne += 30;
             if (!(isfinite(nE) && isfinite(E2))) { atomicOr(errflag, 1); go = 0; }
-            else if (len + 2 > LEAF_SMEM_SEGS + spill_cap) { atomicOr(errflag, 4); go = 0; }
+            else if (len + 2 > cap_total) { atomicOr(errflag, 4); go = 0; }
             else {
                 LeafSeg sg[2] = {LeafSeg{nE, sa, mid, nI.re, nI.im}, LeafSeg{E2, mid, sb, I2re, I2im}};
 #pragma unroll

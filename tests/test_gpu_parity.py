@@ -564,17 +564,21 @@ def test_iai_device_vs_oracle_on_random_problems(ctx, orc, seed):
 
 
 def test_iai_leaf_heap_overflow_falls_back_to_host_panels(ctx, orc, svo):
-    """an innermost integral that outgrows the device segment heap (shrunk here to 63 + 1 segments) is redone with host-driven
-    panels: same numevals and value as the oracle, no error"""
+    """an innermost integral that outgrows the device segment heap (shrunk here to 2 segments in total) is redone with
+    host-driven panels: same numevals and value as the oracle, no error"""
     H, lo, A = svo
     fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
     S = orc.Series(H, lo)
-    Io, Eo, neo = orc.iai(S, 3, 1, [0.5] * 3, vkind=1, z=complex(12.975161, 2e-3), atol=2e-2)
+    Io, Eo, neo = orc.iai(S, 3, 1, [0.5] * 3, vkind=1, z=complex(12.975161, 2e-3), atol=1e-3)
     nest = L.DeviceNest(ctx, fs.device(ctx), 3, 64, 2048)
-    ctx.set_option(L.OPT_IAI_LEAF_SPILL, 1)
+    ctx.set_option(L.OPT_IAI_LEAF_SPILL, -2)
     try:
-        I, E, ne, rounds, launches = nest.iai_solve(1, [0.5] * 3, None, L.F_RESOLVENT_TRACE, 1, complex(12.975161, 2e-3), None, None, 2e-2, 0.0,
+        I, E, ne, rounds, launches = nest.iai_solve(1, [0.5] * 3, None, L.F_RESOLVENT_TRACE, 1, complex(12.975161, 2e-3), None, None, 1e-3, 0.0,
                                                     2 ** 62, device_leaves=True)
     finally:
         ctx.set_option(L.OPT_IAI_LEAF_SPILL, 1024)
     assert ne == neo and abs(I.real - Io.real) <= 1e-10 * abs(Io.real)
+    # the fallback really happened: its round count = the aborted device-leaf rounds + all rounds of the host-panel solve
+    _, _, _, rounds_host, _ = nest.iai_solve(1, [0.5] * 3, None, L.F_RESOLVENT_TRACE, 1, complex(12.975161, 2e-3), None, None, 1e-3, 0.0,
+                                             2 ** 62, device_leaves=False)
+    assert rounds > rounds_host
