@@ -236,10 +236,10 @@ __device__ __forceinline__ double2 small_resolvent_trace(const double2 (&h)[NORB
             if (i == j) { v.x += z.x; v.y += z.y; }
             a[i + j * NORB] = v;
         }
-    if (NORB == 1) return crecip(a[0]);
+    if (NORB == 1) return crecip_fast(a[0]);
     if (NORB == 2) {
         double2 det = csub(cmul(a[0], a[3]), cmul(a[1], a[2]));
-        return cdiv(cadd(a[0], a[3]), det);
+        return cdiv_fast(cadd(a[0], a[3]), det);
     }
     // NORB == 3: column-major a[i + 3j]
     double2 a11 = a[0], a21 = a[1], a31 = a[2], a12 = a[3], a22 = a[4], a32 = a[5], a13 = a[6], a23 = a[7], a33 = a[8];
@@ -249,7 +249,7 @@ __device__ __forceinline__ double2 small_resolvent_trace(const double2 (&h)[NORB
     double2 c12 = csub(cmul(a23, a31), cmul(a21, a33));
     double2 c13 = csub(cmul(a21, a32), cmul(a22, a31));
     double2 det = cadd(cadd(cmul(a11, c11), cmul(a12, c12)), cmul(a13, c13));
-    return cdiv(cadd(cadd(c11, c22), c33), det);
+    return cdiv_fast(cadd(cadd(c11, c22), c33), det);
 }
 
 // Frequency-independent part of tr[(z - H)^-1] for n <= 3 without a matrix self-energy: only the diagonal of z - H
@@ -285,15 +285,15 @@ __device__ __forceinline__ double2 small_trace_prepped(const SmallPrep<NORB>& s,
     double2 d[NORB];
 #pragma unroll
     for (int i = 0; i < NORB; i++) d[i] = csub(z, s.hd[i]);
-    if (NORB == 1) return crecip(d[0]);
-    if (NORB == 2) return cdiv(cadd(d[0], d[1]), csub(cmul(d[0], d[1]), s.P[0]));
+    if (NORB == 1) return crecip_fast(d[0]);
+    if (NORB == 2) return cdiv_fast(cadd(d[0], d[1]), csub(cmul(d[0], d[1]), s.P[0]));
     const double2 s1 = cmul(d[1], d[2]), s2 = cmul(d[0], d[2]), s3 = cmul(d[0], d[1]);
     const double2 num = csub(cadd(cadd(s1, s2), s3), s.Psum);
     double2 det = cmul(d[0], csub(s1, s.P[0]));
     det = csub(det, cmul(d[1], s.P[1]));
     det = csub(det, cmul(d[2], s.P[2]));
     det = cadd(det, s.Q);
-    return cdiv(num, det);
+    return cdiv_fast(num, det);
 }
 
 // ------------------------------------------------------------------------------------------------
