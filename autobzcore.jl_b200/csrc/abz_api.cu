@@ -112,7 +112,7 @@ struct abz_ctx {
     int eig_algo = 0;             // 0: tridiagonalisation + QL, 1: two-sided Jacobi
     int leaf_spill = LEAF_SPILL;  // segments per device-side innermost integral beyond the 63 kept in shared memory
     bool force_generic = false;   // set while re-running a call whose fast path asked for pivoting
-    DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d, iai_in, iai_out, eig_d, eig_e, symw;
+    DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d, iai_in, iai_out, eig_d, eig_e, symw, symlist;
     void* pin_in = nullptr; size_t pin_in_cap = 0;     // pinned staging for the IAI engine's per-round traffic
     void* pin_out = nullptr; size_t pin_out_cap = 0;
     long launches = 0;
@@ -771,14 +771,47 @@ int32_t abz_rule_create_nodes(abz_ctx* ctx, abz_series_t sid, int32_t npt, int64
 }
 
 // symptr_rule_kernel with the fast modular reduction whenever every intermediate |S i| stays below 2^22
-static void launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms, const int* d_syms, int* d_w) {
+static int launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms, const int* d_syms, int* d_w) {
     long smax = 0;
     for (int t = 0; t < 9 * nsyms; t++) smax = std::max<long>(smax, std::labs((long)h_syms[t]));
     const size_t tot = (size_t)npt * npt * npt;
     const unsigned grid = (unsigned)((tot + 255) / 256);
     const size_t smem = (size_t)nsyms * 9 * sizeof(int);
-    if (3 * smax * npt < (1L << 22)) symptr_rule_kernel<true><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, d_w);
+    const bool fast = 3 * smax * npt < (1L << 22);
+    // large grids, at most 64 symmetries: three phases with compaction (see abz_iai.cuh); else the one-kernel version
+    if (fast && nsyms <= 64 && nsyms > 8 && tot >= ((size_t)1 << 22) && tot < ((size_t)1 << 32)) {
+        const unsigned cap1 = (unsigned)(tot / 2 + 1024), cap2 = (unsigned)(tot / 4 + 1024);
+        DevBuf& lb = ctx->symlist;
+        CU(ctx, lb.reserve(((size_t)cap1 + cap2 + 16) * sizeof(unsigned)));
+        unsigned* cnt = lb.as<unsigned>();           // [0]: survivors of phase 1, [1]: irreducible points, [2]: overflow flag
+        unsigned* l1 = cnt + 16;
+        unsigned* l2 = l1 + cap1;
+        CU(ctx, cudaMemsetAsync(cnt, 0, 16 * sizeof(unsigned), ctx->stream));
+        CU(ctx, cudaMemsetAsync(d_w, 0, tot * sizeof(int), ctx->stream));
+        symptr_filter_kernel<true><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, 0, 8, d_syms, nullptr, nullptr, (long)tot, l1, cnt, cap1,
+                                                                    reinterpret_cast<int*>(cnt + 2));
+        LAUNCH_CHECK(ctx, "symptr_filter_kernel");
+        unsigned h[3] = {0, 0, 0};
+        CU(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!h[2] && h[0] > 0) {
+            symptr_filter_kernel<true><<<(h[0] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, 8, nsyms, d_syms, l1, cnt, (long)tot, l2, cnt + 1,
+                                                                                     cap2, reinterpret_cast<int*>(cnt + 2));
+            LAUNCH_CHECK(ctx, "symptr_filter_kernel");
+            CU(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            if (!h[2] && h[1] > 0) {
+                symptr_weight_kernel<true><<<(h[1] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, l2, cnt + 1, d_w);
+                LAUNCH_CHECK(ctx, "symptr_weight_kernel");
+            }
+        }
+        if (!h[2]) return ABZ_OK;
+        // a list overflowed (symmetry list with an unusual order): fall through to the one-kernel version, which overwrites d_w
+    }
+    if (fast) symptr_rule_kernel<true><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, d_w);
     else symptr_rule_kernel<false><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, d_w);
+    LAUNCH_CHECK(ctx, "symptr_rule_kernel");
+    return ABZ_OK;
 }
 
 int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t* wsym_out, int64_t* nirr) {
@@ -791,8 +824,7 @@ int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t*
     CU(ctx, ctx->tmp_a.reserve(tot * sizeof(int)));
     CU(ctx, ctx->tmp_b.reserve((size_t)nsyms * 9 * sizeof(int)));
     CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, syms, (size_t)nsyms * 9 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), ctx->tmp_a.as<int>());
-    LAUNCH_CHECK(ctx, "symptr_rule_kernel");
+    { int rcs = launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), ctx->tmp_a.as<int>()); if (rcs) return rcs; }
     CU(ctx, cudaMemcpyAsync(wsym_out, ctx->tmp_a.p, tot * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (nirr) {
@@ -821,8 +853,7 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
     CU(ctx, wbuf.reserve(tot * sizeof(int)));
     CU(ctx, ctx->tmp_b.reserve((size_t)nsyms * 9 * sizeof(int)));
     CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, syms, (size_t)nsyms * 9 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), wbuf.as<int>());
-    LAUNCH_CHECK(ctx, "symptr_rule_kernel");
+    { int rcs = launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), wbuf.as<int>()); if (rcs) return rcs; }
     // per-row counts: all planes when the total is wanted, else only this rank's
     const bool want_total = (nirr_total != nullptr) && !(k3_lo == 0 && k3_stride == 1);
     std::vector<int> cnt_all;

@@ -582,3 +582,19 @@ def test_iai_leaf_heap_overflow_falls_back_to_host_panels(ctx, orc, svo):
     _, _, _, rounds_host, _ = nest.iai_solve(1, [0.5] * 3, None, L.F_RESOLVENT_TRACE, 1, complex(12.975161, 2e-3), None, None, 1e-3, 0.0,
                                              2 ** 62, device_leaves=False)
     assert rounds > rounds_host
+
+
+def test_symptr_three_phase_path_on_a_large_grid(ctx, orc):
+    """npt^3 >= 2^22 takes the three-phase (filter / filter / weight, with compaction) version of symptr_rule: identical weight
+    array to the oracle's for the cubic group and for a group given in an unusual order (identity last, inversion first)"""
+    npt = 165
+    syms = np.array(ab.cube_automorphisms(3), dtype=np.int32)
+    w_o, n_o = orc.symptr_rule(npt, syms)
+    w_d, n_d = ctx.symptr_rule(npt, syms)
+    assert n_d == n_o and np.array_equal(w_d, w_o) and int(w_d.sum()) == npt ** 3
+    perm = np.concatenate([syms[::-1][:1], syms[1:-1][::-1], syms[:1]])
+    w_p, n_p = ctx.symptr_rule(npt, perm)
+    assert n_p == n_o and np.array_equal(w_p, w_o)
+    H, lo = ab.synthetic.wannier_hamiltonian(2, 1, cubic=True)
+    R = L.DeviceRule(ctx, L.DeviceSeries(ctx, H, lo, (1.0,) * 3), npt, syms=syms)
+    assert len(R) == n_o and R.copy_out()[2].sum() == npt ** 3
