@@ -778,9 +778,32 @@ static int launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms
     const unsigned grid = (unsigned)((tot + 255) / 256);
     const size_t smem = (size_t)nsyms * 9 * sizeof(int);
     const bool fast = 3 * smax * npt < (1L << 22);
-    // large grids, at most 64 symmetries: three phases with compaction (see abz_iai.cuh); else the one-kernel version
+    // large grids, at most 64 symmetries: phases with compaction (see abz_iai.cuh); else the one-kernel version
     if (fast && nsyms <= 64 && nsyms > 8 && tot >= ((size_t)1 << 22) && tot < ((size_t)1 << 32)) {
-        const unsigned cap1 = (unsigned)(tot / 2 + 1024), cap2 = (unsigned)(tot / 4 + 1024);
+        // is the list a group (identity in it, no duplicates, closed under products)?  then weight = nsyms / |stabiliser|
+        bool group = true;
+        {
+            auto eq = [&](const int32_t* A, const int32_t* B) { for (int t = 0; t < 9; t++) if (A[t] != B[t]) return false; return true; };
+            const int32_t I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            bool has_id = false;
+            for (int a = 0; a < nsyms && group; a++) {
+                has_id |= eq(h_syms + 9 * a, I9);
+                for (int b = 0; b < a; b++) if (eq(h_syms + 9 * a, h_syms + 9 * b)) group = false;
+            }
+            group = group && has_id;
+            for (int a = 0; a < nsyms && group; a++)
+                for (int b = 0; b < nsyms && group; b++) {
+                    int32_t P[9];
+                    for (int i = 0; i < 3; i++)
+                        for (int j = 0; j < 3; j++)
+                            P[3 * i + j] = h_syms[9 * a + 3 * i] * h_syms[9 * b + j] + h_syms[9 * a + 3 * i + 1] * h_syms[9 * b + 3 + j] +
+                                           h_syms[9 * a + 3 * i + 2] * h_syms[9 * b + 6 + j];
+                    bool found = false;
+                    for (int c = 0; c < nsyms && !found; c++) found = eq(P, h_syms + 9 * c);
+                    group = found;
+                }
+        }
+        const unsigned cap1 = (unsigned)(tot / 2 + 1024), cap2 = group ? 16u : (unsigned)(tot / 4 + 1024);
         DevBuf& lb = ctx->symlist;
         CU(ctx, lb.reserve(((size_t)cap1 + cap2 + 16) * sizeof(unsigned)));
         unsigned* cnt = lb.as<unsigned>();           // [0]: survivors of phase 1, [1]: irreducible points, [2]: overflow flag
@@ -788,21 +811,28 @@ static int launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms
         unsigned* l2 = l1 + cap1;
         CU(ctx, cudaMemsetAsync(cnt, 0, 16 * sizeof(unsigned), ctx->stream));
         CU(ctx, cudaMemsetAsync(d_w, 0, tot * sizeof(int), ctx->stream));
-        symptr_filter_kernel<true><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, 0, 8, d_syms, nullptr, nullptr, (long)tot, l1, cnt, cap1,
-                                                                    reinterpret_cast<int*>(cnt + 2));
+        dim3 g1((unsigned)(((size_t)npt * npt + 255) / 256), (unsigned)npt);
+        symptr_filter_kernel<true, false><<<g1, 256, smem, ctx->stream>>>(npt, nsyms, 0, 8, d_syms, nullptr, nullptr, l1, cnt, cap1,
+                                                                         reinterpret_cast<int*>(cnt + 2), d_w);
         LAUNCH_CHECK(ctx, "symptr_filter_kernel");
         unsigned h[3] = {0, 0, 0};
         CU(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         if (!h[2] && h[0] > 0) {
-            symptr_filter_kernel<true><<<(h[0] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, 8, nsyms, d_syms, l1, cnt, (long)tot, l2, cnt + 1,
-                                                                                     cap2, reinterpret_cast<int*>(cnt + 2));
-            LAUNCH_CHECK(ctx, "symptr_filter_kernel");
-            CU(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(ctx, cudaStreamSynchronize(ctx->stream));
-            if (!h[2] && h[1] > 0) {
-                symptr_weight_kernel<true><<<(h[1] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, l2, cnt + 1, d_w);
-                LAUNCH_CHECK(ctx, "symptr_weight_kernel");
+            if (group) {
+                symptr_filter_kernel<true, true><<<(h[0] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, 8, nsyms, d_syms, l1, cnt, l2, cnt + 1,
+                                                                                                cap2, reinterpret_cast<int*>(cnt + 2), d_w);
+                LAUNCH_CHECK(ctx, "symptr_filter_kernel");
+            } else {
+                symptr_filter_kernel<true, false><<<(h[0] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, 8, nsyms, d_syms, l1, cnt, l2, cnt + 1,
+                                                                                                 cap2, reinterpret_cast<int*>(cnt + 2), d_w);
+                LAUNCH_CHECK(ctx, "symptr_filter_kernel");
+                CU(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(ctx, cudaStreamSynchronize(ctx->stream));
+                if (!h[2] && h[1] > 0) {
+                    symptr_weight_kernel<true><<<(h[1] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, l2, cnt + 1, d_w);
+                    LAUNCH_CHECK(ctx, "symptr_weight_kernel");
+                }
             }
         }
         if (!h[2]) return ABZ_OK;

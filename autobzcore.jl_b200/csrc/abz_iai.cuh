@@ -386,26 +386,58 @@ symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restri
 //   phase 2  the survivors try all symmetries, the irreducible points are compacted again;
 //   phase 3  one thread per irreducible point counts its distinct images (homogeneous work, full warps).
 // wsym must be zero on entry; only irreducible points are written.  Lists hold 32-bit linear indices (N^3 < 2^32).
-template <bool FAST>
+// phase 1 (in_list == NULL): grid = (ceil(N^2 / 256), N), blockIdx.y = i3 - 32-bit index arithmetic only;
+// phase 2 (in_list != NULL): grid = ceil(count / 256).  GROUP: the symmetry list is a group (checked on the host), so the
+// weight of an irreducible point is nsyms / |stabiliser| and phase 2 writes wsym itself (no phase 3).
+template <bool FAST, bool GROUP>
 __global__ void __launch_bounds__(256)
 symptr_filter_kernel(int N, int nsyms, int s0, int s1, const int* __restrict__ syms, const unsigned* __restrict__ in_list,
-                     const unsigned* __restrict__ in_count, long tot, unsigned* __restrict__ out_list, unsigned* __restrict__ out_count,
-                     unsigned out_cap, int* __restrict__ overflow) {
+                     const unsigned* __restrict__ in_count, unsigned* __restrict__ out_list, unsigned* __restrict__ out_count,
+                     unsigned out_cap, int* __restrict__ overflow, int* __restrict__ wsym) {
     extern __shared__ int sy[];
     for (int t = threadIdx.x; t < 9 * nsyms; t += 256) sy[t] = syms[t];
     __syncthreads();
-    const long nin = in_list ? (long)*in_count : tot;
-    const long t = (long)blockIdx.x * 256 + threadIdx.x;
     bool keep = false;
-    long idx = 0;
-    if (t < nin) {
-        idx = in_list ? (long)in_list[t] : t;
-        const int i1 = (int)(idx % N), i2 = (int)((idx / N) % N), i3 = (int)(idx / ((long)N * N));
+    unsigned idx = 0;
+    int i1 = 0, i2 = 0, i3 = 0;
+    if (in_list) {
+        const unsigned t = blockIdx.x * 256u + threadIdx.x;
+        if (t < *in_count) {
+            idx = in_list[t];
+            const unsigned plane = (unsigned)N * (unsigned)N;
+            i3 = (int)(idx / plane);
+            const unsigned r = idx - (unsigned)i3 * plane;
+            i2 = (int)(r / (unsigned)N); i1 = (int)(r - (unsigned)i2 * (unsigned)N);
+            keep = true;
+        }
+    } else {
+        const unsigned r = blockIdx.x * 256u + threadIdx.x;
+        if (r < (unsigned)N * (unsigned)N) {
+            i3 = (int)blockIdx.y;
+            i2 = (int)(r / (unsigned)N); i1 = (int)(r - (unsigned)i2 * (unsigned)N);
+            idx = (unsigned)i3 * (unsigned)N * (unsigned)N + r;
+            keep = true;
+        }
+    }
+    int stab = 0;
+    if (keep) {
         const long NN = (long)N * N;
         const float invN = 1.0f / (float)N;
-        keep = true;
-        for (int s = s0; s < s1; s++)
-            if (symptr_image<FAST>(sy + 9 * s, i1, i2, i3, N, invN, NN) < idx) { keep = false; break; }
+        for (int s = s0; s < s1; s++) {
+            const long jdx = symptr_image<FAST>(sy + 9 * s, i1, i2, i3, N, invN, NN);
+            if (jdx < (long)idx) { keep = false; break; }
+            stab += (jdx == (long)idx);
+        }
+    }
+    if (GROUP && in_list) {          // final pass of a group: irreducible points get their weight here
+        if (keep) {
+            // symmetries s < s0 were all >= idx in phase 1; count the ones that fix the point among them too
+            const long NN = (long)N * N;
+            const float invN = 1.0f / (float)N;
+            for (int s = 0; s < s0; s++) stab += (symptr_image<FAST>(sy + 9 * s, i1, i2, i3, N, invN, NN) == (long)idx);
+            wsym[idx] = nsyms / stab;
+        }
+        return;
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (m) {
@@ -415,7 +447,7 @@ symptr_filter_kernel(int N, int nsyms, int s0, int s1, const int* __restrict__ s
         base = __shfl_sync(0xffffffffu, base, 0);
         if (keep) {
             const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
-            if (pos < out_cap) out_list[pos] = (unsigned)idx; else *overflow = 1;
+            if (pos < out_cap) out_list[pos] = idx; else *overflow = 1;
         }
     }
 }

@@ -598,3 +598,8 @@ def test_symptr_three_phase_path_on_a_large_grid(ctx, orc):
     H, lo = ab.synthetic.wannier_hamiltonian(2, 1, cubic=True)
     R = L.DeviceRule(ctx, L.DeviceSeries(ctx, H, lo, (1.0,) * 3), npt, syms=syms)
     assert len(R) == n_o and R.copy_out()[2].sum() == npt ** 3
+    # a list that is NOT a group (20 of the 48, identity removed): weights by counting distinct images (phase 3), as the oracle
+    part = syms[1:21]
+    w_q, n_q = orc.symptr_rule(npt, part)
+    w_r, n_r = ctx.symptr_rule(npt, part)
+    assert n_r == n_q and np.array_equal(w_r, w_q)
