@@ -771,7 +771,35 @@ int32_t abz_rule_create_nodes(abz_ctx* ctx, abz_series_t sid, int32_t npt, int64
 }
 
 // symptr_rule_kernel with the fast modular reduction whenever every intermediate |S i| stays below 2^22
+// The symmetry list must be a group (identity in it, no duplicates, closed under products), as every list from load_bz is:
+// AutoSymPTR.symptr_rule's sequential scan is order-dependent otherwise, and the device version relies on
+// "representative = smallest linear index of the orbit" and weight = nsyms / |stabiliser|.
+static bool syms_form_group(const int32_t* h_syms, int nsyms) {
+    auto eq = [&](const int32_t* A, const int32_t* B) { for (int t = 0; t < 9; t++) if (A[t] != B[t]) return false; return true; };
+    const int32_t I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    bool has_id = false;
+    for (int a = 0; a < nsyms; a++) {
+        has_id |= eq(h_syms + 9 * a, I9);
+        for (int b = 0; b < a; b++) if (eq(h_syms + 9 * a, h_syms + 9 * b)) return false;
+    }
+    if (!has_id) return false;
+    for (int a = 0; a < nsyms; a++)
+        for (int b = 0; b < nsyms; b++) {
+            int32_t P[9];
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++)
+                    P[3 * i + j] = h_syms[9 * a + 3 * i] * h_syms[9 * b + j] + h_syms[9 * a + 3 * i + 1] * h_syms[9 * b + 3 + j] +
+                                   h_syms[9 * a + 3 * i + 2] * h_syms[9 * b + 6 + j];
+            bool found = false;
+            for (int c = 0; c < nsyms && !found; c++) found = eq(P, h_syms + 9 * c);
+            if (!found) return false;
+        }
+    return true;
+}
+
 static int launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms, const int* d_syms, int* d_w) {
+    if (!syms_form_group(h_syms, nsyms))
+        return fail(ctx, ABZ_E_INVALID, "the symmetries must form a group (identity included, closed under products, no duplicates)");
     long smax = 0;
     for (int t = 0; t < 9 * nsyms; t++) smax = std::max<long>(smax, std::labs((long)h_syms[t]));
     const size_t tot = (size_t)npt * npt * npt;
@@ -780,30 +808,7 @@ static int launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms
     const bool fast = 3 * smax * npt < (1L << 22);
     // large grids, at most 64 symmetries: phases with compaction (see abz_iai.cuh); else the one-kernel version
     if (fast && nsyms <= 64 && nsyms > 8 && tot >= ((size_t)1 << 22) && tot < ((size_t)1 << 32)) {
-        // is the list a group (identity in it, no duplicates, closed under products)?  then weight = nsyms / |stabiliser|
-        bool group = true;
-        {
-            auto eq = [&](const int32_t* A, const int32_t* B) { for (int t = 0; t < 9; t++) if (A[t] != B[t]) return false; return true; };
-            const int32_t I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-            bool has_id = false;
-            for (int a = 0; a < nsyms && group; a++) {
-                has_id |= eq(h_syms + 9 * a, I9);
-                for (int b = 0; b < a; b++) if (eq(h_syms + 9 * a, h_syms + 9 * b)) group = false;
-            }
-            group = group && has_id;
-            for (int a = 0; a < nsyms && group; a++)
-                for (int b = 0; b < nsyms && group; b++) {
-                    int32_t P[9];
-                    for (int i = 0; i < 3; i++)
-                        for (int j = 0; j < 3; j++)
-                            P[3 * i + j] = h_syms[9 * a + 3 * i] * h_syms[9 * b + j] + h_syms[9 * a + 3 * i + 1] * h_syms[9 * b + 3 + j] +
-                                           h_syms[9 * a + 3 * i + 2] * h_syms[9 * b + 6 + j];
-                    bool found = false;
-                    for (int c = 0; c < nsyms && !found; c++) found = eq(P, h_syms + 9 * c);
-                    group = found;
-                }
-        }
-        const unsigned cap1 = (unsigned)(tot / 2 + 1024), cap2 = group ? 16u : (unsigned)(tot / 4 + 1024);
+        const unsigned cap1 = (unsigned)(tot / 2 + 1024), cap2 = 16u;
         DevBuf& lb = ctx->symlist;
         CU(ctx, lb.reserve(((size_t)cap1 + cap2 + 16) * sizeof(unsigned)));
         unsigned* cnt = lb.as<unsigned>();           // [0]: survivors of phase 1, [1]: irreducible points, [2]: overflow flag
@@ -819,21 +824,9 @@ static int launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms
         CU(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         if (!h[2] && h[0] > 0) {
-            if (group) {
-                symptr_filter_kernel<true, true><<<(h[0] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, 8, nsyms, d_syms, l1, cnt, l2, cnt + 1,
-                                                                                                cap2, reinterpret_cast<int*>(cnt + 2), d_w);
-                LAUNCH_CHECK(ctx, "symptr_filter_kernel");
-            } else {
-                symptr_filter_kernel<true, false><<<(h[0] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, 8, nsyms, d_syms, l1, cnt, l2, cnt + 1,
-                                                                                                 cap2, reinterpret_cast<int*>(cnt + 2), d_w);
-                LAUNCH_CHECK(ctx, "symptr_filter_kernel");
-                CU(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-                CU(ctx, cudaStreamSynchronize(ctx->stream));
-                if (!h[2] && h[1] > 0) {
-                    symptr_weight_kernel<true><<<(h[1] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, l2, cnt + 1, d_w);
-                    LAUNCH_CHECK(ctx, "symptr_weight_kernel");
-                }
-            }
+            symptr_filter_kernel<true, true><<<(h[0] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, 8, nsyms, d_syms, l1, cnt, l2, cnt + 1,
+                                                                                            cap2, reinterpret_cast<int*>(cnt + 2), d_w);
+            LAUNCH_CHECK(ctx, "symptr_filter_kernel");
         }
         if (!h[2]) return ABZ_OK;
         // a list overflowed (symmetry list with an unusual order): fall through to the one-kernel version, which overwrites d_w

@@ -380,11 +380,11 @@ symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restri
     wsym[idx] = cnt;
 }
 
-// Three-phase variant for large grids: in symptr_rule_kernel the rare irreducible lanes (1 / nsyms of the grid) run ~100x the
+// Two-phase variant for large grids: in symptr_rule_kernel the rare irreducible lanes (1 / nsyms of the grid) run ~100x the
 // work of the others and hold their whole warp, so the kernel runs at a few per cent lane utilisation.  Here
 //   phase 1  every grid point tries the first few symmetries and the survivors (points not yet beaten) are compacted;
-//   phase 2  the survivors try all symmetries, the irreducible points are compacted again;
-//   phase 3  one thread per irreducible point counts its distinct images (homogeneous work, full warps).
+//   phase 2  the survivors try the remaining symmetries; an irreducible point gets weight nsyms / |stabiliser| (the list
+//            is a group: checked on the host).
 // wsym must be zero on entry; only irreducible points are written.  Lists hold 32-bit linear indices (N^3 < 2^32).
 // phase 1 (in_list == NULL): grid = (ceil(N^2 / 256), N), blockIdx.y = i3 - 32-bit index arithmetic only;
 // phase 2 (in_list != NULL): grid = ceil(count / 256).  GROUP: the symmetry list is a group (checked on the host), so the
@@ -451,32 +451,6 @@ symptr_filter_kernel(int N, int nsyms, int s0, int s1, const int* __restrict__ s
         }
     }
 }
-template <bool FAST>
-__global__ void __launch_bounds__(256)
-symptr_weight_kernel(int N, int nsyms, const int* __restrict__ syms, const unsigned* __restrict__ list, const unsigned* __restrict__ count,
-                     int* __restrict__ wsym) {
-    extern __shared__ int sy[];
-    for (int t = threadIdx.x; t < 9 * nsyms; t += 256) sy[t] = syms[t];
-    __syncthreads();
-    const long t = (long)blockIdx.x * 256 + threadIdx.x;
-    if (t >= (long)*count) return;
-    const long idx = (long)list[t];
-    const int i1 = (int)(idx % N), i2 = (int)((idx / N) % N), i3 = (int)(idx / ((long)N * N));
-    const long NN = (long)N * N;
-    const float invN = 1.0f / (float)N;
-    constexpr int CACHE = 64;
-    long img[CACHE];
-    bool has_self = false;
-    for (int s = 0; s < nsyms; s++) { img[s] = symptr_image<FAST>(sy + 9 * s, i1, i2, i3, N, invN, NN); has_self |= (img[s] == idx); }
-    int cnt = has_self ? 0 : 1;
-    for (int s = 0; s < nsyms; s++) {
-        bool dup = false;
-        for (int r = 0; r < s; r++) dup |= (img[r] == img[s]);
-        cnt += dup ? 0 : 1;
-    }
-    wsym[idx] = cnt;
-}
-
 // CSR construction of the symmetry-reduced rule on the device (the reference's flags arrays,
 // src/fourier.jl:237-243): one warp per (k2, k3) row of the dense weight array.
 // pass 1: rowcnt[p*N + i2] = #irreducible nodes in row i2 of selected plane p (i3 = k3_lo + p*k3_stride)

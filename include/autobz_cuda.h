@@ -99,7 +99,9 @@ int32_t abz_rule_create_sym(abz_ctx* ctx, abz_series_t s, int32_t npt, const int
 int32_t abz_rule_create_nodes(abz_ctx* ctx, abz_series_t s, int32_t npt, int64_t nnodes, const int32_t* idx,
                               const double* w, abz_rule_t* out);
 /* AutoSymPTR.symptr_rule (call site src/fourier.jl:271) on the device: syms = Int32[3,3,nsyms]
- * row-major per matrix, wsym_out = Int32[npt^3] host buffer; returns the irreducible count. */
+ * row-major per matrix, wsym_out = Int32[npt^3] host buffer; returns the irreducible count.
+ * The list must be a group (identity included, closed under products, no duplicates) - every list load_bz produces is;
+ * ABZ_E_INVALID otherwise (the reference's sequential scan is order-dependent for non-groups). */
 int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t* wsym_out, int64_t* nirr);
 /* symptr_rule + FourierMonkhorstPack in one step, entirely on the device (src/fourier.jl:265-277): the dense
  * weight array never visits the host, the CSR node lists are compacted by a warp-per-row kernel.  Same node set,
