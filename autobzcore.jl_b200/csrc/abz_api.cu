@@ -364,6 +364,12 @@ static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n, int* h
         LAUNCH_CHECK(ctx, "eig_tridiag_warp_kernel");
         return ABZ_OK;
     }
+    if (n > 32 && n <= 64 && ctx->eig_algo != 2) {
+        const long ncta = std::min<long>(nk, (long)ctx->sm_count * 2);
+        eig_tridiag_reg64_kernel<<<(unsigned)ncta, 256, 0, ctx->stream>>>(H, nk, n, dd, ee, herm_flag);
+        LAUNCH_CHECK(ctx, "eig_tridiag_reg64_kernel");
+        return ABZ_OK;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(eig_tridiag_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);

@@ -561,6 +561,129 @@ eig_tridiag_warp_kernel(const double2* __restrict__ H, long nk, int n, double* _
     }
 }
 
+// Register-resident variant for 32 < n <= 64: one CTA of 256 threads per matrix, thread (row i, quarter q) keeps the 16
+// elements A[i][q + 4 s] of its row in registers; the column loop is fully unrolled, so register indices are static and the
+// slots left of the current column are not even emitted.  Shared memory only carries the Householder vector v (double
+// buffered), the mat-vec result and one copy of w per warp: the shared-memory kernel above spends 66 % of the LSU
+// wavefront budget on re-reading A, this one reads v_j / w_j broadcasts only.  Two block barriers per column.
+__global__ void __launch_bounds__(256, 2)
+eig_tridiag_reg64_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout,
+                         int* __restrict__ herm_flag) {
+    constexpr int N = 64, NS = 16;
+    __shared__ double2 vbuf[2][N];
+    __shared__ double2 pb[N];
+    __shared__ double2 wbuf[8][N];
+    __shared__ double2 red[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = warp * 8 + (lane & 7), q = lane >> 3;
+    double2* wv = wbuf[warp];
+    for (long k = blockIdx.x; k < nk; k += gridDim.x) {
+        const double2* Hk = H + k * (long)n * n;
+        double2 a[NS];
+        double asym = 0.0, tot = 0.0;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const int j = q + 4 * s;
+            a[s] = make_double2(0.0, 0.0);
+            if (i < n && j < n) {
+                const double2 x = Hk[i + (long)j * n], y = Hk[j + (long)i * n];
+                a[s] = make_double2(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+                const double dx = x.x - y.x, dy = x.y + y.y;
+                asym += dx * dx + dy * dy;
+                tot += x.x * x.x + x.y * x.y + y.x * y.x + y.y * y.y;
+            }
+        }
+        if (herm_flag) {       // the frequency-sweep path is only valid for Hermitian H(k): ||H - H^H||_F <= 1e-10 ||H||_F
+            asym = warp_sum(asym); tot = warp_sum(tot);
+            __syncthreads();
+            if (lane == 0) red[warp] = make_double2(asym, tot);
+            __syncthreads();
+            if (tid == 0) {
+                double sa = 0.0, st = 0.0;
+                for (int w = 0; w < 8; w++) { sa += red[w].x; st += red[w].y; }
+                if (sa > 1e-20 * st) atomicOr(herm_flag, 8);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < N - 1; c++) {
+            double2* vs = vbuf[c & 1];
+            if (q == (c & 3)) vs[i] = a[c >> 2];                       // column c of the current matrix
+            __syncthreads();
+            // Householder vector of column c (every warp redundantly)
+            const double2 x0 = vs[lane], x1 = vs[lane + 32];
+            double sig = ((lane >= c + 2) ? fma(x0.x, x0.x, x0.y * x0.y) : 0.0) + ((lane + 32 >= c + 2) ? fma(x1.x, x1.x, x1.y * x1.y) : 0.0);
+            sig = warp_sum(sig);
+            const double2 alpha = vs[c + 1];
+            const double aa = alpha.x * alpha.x + alpha.y * alpha.y;
+            const double ynorm = sqrt(sig + aa);
+            if (i == c && q == (c & 3) && c < n) { dout[(long)c * nk + k] = a[c >> 2].x; eout[(long)c * nk + k] = ynorm; }
+            if (sig == 0.0) continue;                                  // uniform over the CTA: column already tridiagonal
+            const double absa = sqrt(aa);
+            const double2 ph = absa > 0.0 ? make_double2(alpha.x / absa, alpha.y / absa) : make_double2(1.0, 0.0);
+            const double2 v0 = make_double2(alpha.x + ph.x * ynorm, alpha.y + ph.y * ynorm);
+            const double tau = 1.0 / (ynorm * (ynorm + absa));
+            const bool active = (i > c);
+            // p = A22 v: my quarter of the columns, slots whose four columns are all <= c are not emitted
+            double2 acc = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+            if (active) {
+#pragma unroll
+                for (int s = (c + 1) >> 2; s < NS; s++) {
+                    const int j = q + 4 * s;
+                    if (j > c) {
+                        const double2 vj = (j == c + 1) ? v0 : vs[j];
+                        if (s & 1) acc1 = cfma(acc1, a[s], vj); else acc = cfma(acc, a[s], vj);
+                    }
+                }
+                acc.x += acc1.x; acc.y += acc1.y;
+            }
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 8); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 8);
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+            if (q == 0) pb[i] = acc;
+            __syncthreads();
+            // w = p - (tau/2)(v^H p) v, every warp into its own copy
+            double2 pr[2], vr[2];
+            double dot = 0.0;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int r = lane + 32 * t;
+                pr[t] = make_double2(0.0, 0.0); vr[t] = make_double2(0.0, 0.0);
+                if (r > c) {
+                    const double2 s0 = pb[r];
+                    pr[t] = make_double2(tau * s0.x, tau * s0.y);
+                    vr[t] = (r == c + 1) ? v0 : vs[r];
+                    dot += vr[t].x * pr[t].x + vr[t].y * pr[t].y;
+                }
+            }
+            dot = warp_sum(dot);
+            const double gam = 0.5 * tau * dot;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int r = lane + 32 * t;
+                if (r > c) wv[r] = make_double2(pr[t].x - gam * vr[t].x, pr[t].y - gam * vr[t].y);
+            }
+            __syncwarp();
+            if (active) {
+                const double2 vi = (i == c + 1) ? v0 : vs[i];
+                const double2 wi = wv[i];
+#pragma unroll
+                for (int s = (c + 1) >> 2; s < NS; s++) {
+                    const int j = q + 4 * s;
+                    if (j > c) {
+                        const double2 vj = (j == c + 1) ? v0 : vs[j];
+                        const double2 wj = wv[j];
+                        a[s].x = fma(-wi.y, vj.y, fma(-wi.x, vj.x, fma(-vi.y, wj.y, fma(-vi.x, wj.x, a[s].x))));
+                        a[s].y = fma(wi.x, vj.y, fma(-wi.y, vj.x, fma(vi.x, wj.y, fma(-vi.y, wj.x, a[s].y))));
+                    }
+                }
+            }
+            // no barrier here: the next column publishes into the other half of vbuf, pb is rewritten only after the next
+            // barrier, and wv is private to the warp
+        }
+        if (i == N - 1 && q == 3 && N - 1 < n) { dout[(long)(N - 1) * nk + k] = a[NS - 1].x; eout[(long)(N - 1) * nk + k] = 0.0; }
+        __syncthreads();
+    }
+}
+
 // Stage B: eigenvalues of the real symmetric tridiagonal (d, e) by the implicit QL algorithm with Wilkinson shifts
 // (EISPACK imtql1 / "tqli" without vectors), one thread per matrix.  mode 0: partial[cta] = sum_k wnode_k sum_n g(e_n);
 // mode 1: evals[k*n + i] ascending.

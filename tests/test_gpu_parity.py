@@ -389,7 +389,7 @@ def test_rule_create_symptr_on_device_matches_host_path(ctx, orc, npt):
     assert rel(Rc.resolvent_sum(z), L.DeviceRule(ctx, S, npt).resolvent_sum(z)) < 1e-12
 
 
-@pytest.mark.parametrize("n", [2, 7, 31, 32, 33, 64])
+@pytest.mark.parametrize("n", [2, 7, 31, 32, 33, 40, 63, 64])
 def test_eig_algorithms_agree_with_lapack(ctx, n):
     """Householder tridiagonalisation + implicit QL (default) and cyclic Jacobi (option) against LAPACK zheev on
     H(k) of a synthetic Wannier Hamiltonian, incl. a degenerate spectrum (H = 0 -> all eigenvalues 0; diagonal H)."""
