@@ -561,11 +561,55 @@ eig_tridiag_warp_kernel(const double2* __restrict__ H, long nk, int n, double* _
     }
 }
 
+// Householder parameters of column c (in vs[]) for one warp: v0 = y_1 + e^{i arg y_1}|y|, tau = 1/(|y|(|y| + |y_1|)),
+// ynorm = |y|; returns sig = sum_{r >= c+2} |y_r|^2 (0: nothing to eliminate).  Not inlined: the callers unroll 63 columns.
+__device__ __noinline__ double householder_params64(const double2* __restrict__ vs, int c, int lane, double2* v0, double* tau,
+                                                     double* ynorm) {
+    const double2 x0 = vs[lane], x1 = vs[lane + 32];
+    double sig = ((lane >= c + 2) ? fma(x0.x, x0.x, x0.y * x0.y) : 0.0) + ((lane + 32 >= c + 2) ? fma(x1.x, x1.x, x1.y * x1.y) : 0.0);
+    sig = warp_sum(sig);
+    const double2 alpha = vs[c + 1];
+    const double aa = alpha.x * alpha.x + alpha.y * alpha.y;
+    const double yn = sqrt(sig + aa), absa = sqrt(aa);
+    const double ia = absa > 0.0 ? fast_rcp(absa) : 0.0;
+    const double2 ph = absa > 0.0 ? make_double2(alpha.x * ia, alpha.y * ia) : make_double2(1.0, 0.0);
+    *v0 = make_double2(alpha.x + ph.x * yn, alpha.y + ph.y * yn);
+    *tau = (sig > 0.0) ? fast_rcp(yn * (yn + absa)) : 0.0;
+    *ynorm = yn;
+    return sig;
+}
+// w = p - (tau/2)(v^H p) v from the mat-vec result pb[] (unscaled) into this warp's copy wv[]
+__device__ __noinline__ void householder_w64(const double2* __restrict__ pb, const double2* __restrict__ vs, double2* __restrict__ wv,
+                                             int c, int lane, double2 v0, double tau) {
+    double2 pr[2], vr[2];
+    double dot = 0.0;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int r = lane + 32 * t;
+        pr[t] = make_double2(0.0, 0.0); vr[t] = make_double2(0.0, 0.0);
+        if (r > c) {
+            const double2 s0 = pb[r];
+            pr[t] = make_double2(tau * s0.x, tau * s0.y);
+            vr[t] = (r == c + 1) ? v0 : vs[r];
+            dot += vr[t].x * pr[t].x + vr[t].y * pr[t].y;
+        }
+    }
+    dot = warp_sum(dot);
+    const double gam = 0.5 * tau * dot;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int r = lane + 32 * t;
+        if (r > c) wv[r] = make_double2(pr[t].x - gam * vr[t].x, pr[t].y - gam * vr[t].y);
+    }
+    __syncwarp();
+}
+
 // Register-resident variant for 32 < n <= 64: one CTA of 256 threads per matrix, thread (row i, quarter q) keeps the 16
 // elements A[i][q + 4 s] of its row in registers; the column loop is fully unrolled, so register indices are static and the
 // slots left of the current column are not even emitted.  Shared memory only carries the Householder vector v (double
 // buffered), the mat-vec result and one copy of w per warp: the shared-memory kernel above spends 66 % of the LSU
-// wavefront budget on re-reading A, this one reads v_j / w_j broadcasts only.  Two block barriers per column.
+// wavefront budget on re-reading A, this one reads v_j / w_j broadcasts only.  Two block barriers per column; warps whose
+// eight rows are all above the current column only take part in the barriers.
 __global__ void __launch_bounds__(256, 2)
 eig_tridiag_reg64_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout,
                          int* __restrict__ herm_flag) {
@@ -607,72 +651,50 @@ eig_tridiag_reg64_kernel(const double2* __restrict__ H, long nk, int n, double* 
 #pragma unroll
         for (int c = 0; c < N - 1; c++) {
             double2* vs = vbuf[c & 1];
-            if (q == (c & 3)) vs[i] = a[c >> 2];                       // column c of the current matrix
+            const bool warp_on = (warp * 8 + 7 > c);                   // some of this warp's rows lie below the diagonal entry
+            if (warp_on && q == (c & 3)) vs[i] = a[c >> 2];            // column c of the current matrix (rows > c are needed)
+            if (i == c && q == (c & 3) && c < n) dout[(long)c * nk + k] = a[c >> 2].x;
             __syncthreads();
-            // Householder vector of column c (every warp redundantly)
-            const double2 x0 = vs[lane], x1 = vs[lane + 32];
-            double sig = ((lane >= c + 2) ? fma(x0.x, x0.x, x0.y * x0.y) : 0.0) + ((lane + 32 >= c + 2) ? fma(x1.x, x1.x, x1.y * x1.y) : 0.0);
-            sig = warp_sum(sig);
-            const double2 alpha = vs[c + 1];
-            const double aa = alpha.x * alpha.x + alpha.y * alpha.y;
-            const double ynorm = sqrt(sig + aa);
-            if (i == c && q == (c & 3) && c < n) { dout[(long)c * nk + k] = a[c >> 2].x; eout[(long)c * nk + k] = ynorm; }
-            if (sig == 0.0) continue;                                  // uniform over the CTA: column already tridiagonal
-            const double absa = sqrt(aa);
-            const double2 ph = absa > 0.0 ? make_double2(alpha.x / absa, alpha.y / absa) : make_double2(1.0, 0.0);
-            const double2 v0 = make_double2(alpha.x + ph.x * ynorm, alpha.y + ph.y * ynorm);
-            const double tau = 1.0 / (ynorm * (ynorm + absa));
-            const bool active = (i > c);
-            // p = A22 v: my quarter of the columns, slots whose four columns are all <= c are not emitted
-            double2 acc = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
-            if (active) {
+            double2 v0 = make_double2(0.0, 0.0);
+            double tau = 0.0, sig = 0.0;
+            bool active = false;
+            if (warp_on) {
+                double ynorm;
+                sig = householder_params64(vs, c, lane, &v0, &tau, &ynorm);
+                if (i == c + 1 && q == 0 && c < n) eout[(long)c * nk + k] = ynorm;
+                active = (i > c) && (sig != 0.0);
+                // p = A22 v: my quarter of the columns, slots whose four columns are all <= c are not emitted
+                double2 acc = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+                if (active) {
 #pragma unroll
-                for (int s = (c + 1) >> 2; s < NS; s++) {
-                    const int j = q + 4 * s;
-                    if (j > c) {
-                        const double2 vj = (j == c + 1) ? v0 : vs[j];
-                        if (s & 1) acc1 = cfma(acc1, a[s], vj); else acc = cfma(acc, a[s], vj);
+                    for (int s = (c + 1) >> 2; s < NS; s++) {
+                        const int j = q + 4 * s;
+                        if (j > c) {
+                            const double2 vj = (j == c + 1) ? v0 : vs[j];
+                            if (s & 1) acc1 = cfma(acc1, a[s], vj); else acc = cfma(acc, a[s], vj);
+                        }
                     }
+                    acc.x += acc1.x; acc.y += acc1.y;
                 }
-                acc.x += acc1.x; acc.y += acc1.y;
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 8); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 8);
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+                if (q == 0) pb[i] = acc;
             }
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 8); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 8);
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-            if (q == 0) pb[i] = acc;
             __syncthreads();
-            // w = p - (tau/2)(v^H p) v, every warp into its own copy
-            double2 pr[2], vr[2];
-            double dot = 0.0;
+            if (warp_on && sig != 0.0) {
+                householder_w64(pb, vs, wv, c, lane, v0, tau);
+                if (active) {
+                    const double2 vi = (i == c + 1) ? v0 : vs[i];
+                    const double2 wi = wv[i];
 #pragma unroll
-            for (int t = 0; t < 2; t++) {
-                const int r = lane + 32 * t;
-                pr[t] = make_double2(0.0, 0.0); vr[t] = make_double2(0.0, 0.0);
-                if (r > c) {
-                    const double2 s0 = pb[r];
-                    pr[t] = make_double2(tau * s0.x, tau * s0.y);
-                    vr[t] = (r == c + 1) ? v0 : vs[r];
-                    dot += vr[t].x * pr[t].x + vr[t].y * pr[t].y;
-                }
-            }
-            dot = warp_sum(dot);
-            const double gam = 0.5 * tau * dot;
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-                const int r = lane + 32 * t;
-                if (r > c) wv[r] = make_double2(pr[t].x - gam * vr[t].x, pr[t].y - gam * vr[t].y);
-            }
-            __syncwarp();
-            if (active) {
-                const double2 vi = (i == c + 1) ? v0 : vs[i];
-                const double2 wi = wv[i];
-#pragma unroll
-                for (int s = (c + 1) >> 2; s < NS; s++) {
-                    const int j = q + 4 * s;
-                    if (j > c) {
-                        const double2 vj = (j == c + 1) ? v0 : vs[j];
-                        const double2 wj = wv[j];
-                        a[s].x = fma(-wi.y, vj.y, fma(-wi.x, vj.x, fma(-vi.y, wj.y, fma(-vi.x, wj.x, a[s].x))));
-                        a[s].y = fma(wi.x, vj.y, fma(-wi.y, vj.x, fma(vi.x, wj.y, fma(-vi.y, wj.x, a[s].y))));
+                    for (int s = (c + 1) >> 2; s < NS; s++) {
+                        const int j = q + 4 * s;
+                        if (j > c) {
+                            const double2 vj = (j == c + 1) ? v0 : vs[j];
+                            const double2 wj = wv[j];
+                            a[s].x = fma(-wi.y, vj.y, fma(-wi.x, vj.x, fma(-vi.y, wj.y, fma(-vi.x, wj.x, a[s].x))));
+                            a[s].y = fma(wi.x, vj.y, fma(-wi.y, vj.x, fma(vi.x, wj.y, fma(-vi.y, wj.x, a[s].y))));
+                        }
                     }
                 }
             }
