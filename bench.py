@@ -217,7 +217,14 @@ def main():
     import autobz_b200 as ab
     from autobz_b200 import _lib as L
 
-    torch.cuda.set_device(local)
+    for attempt in range(4):            # a freshly vacated GPU has been seen to refuse cuInit once ("CUDA driver initialization failed")
+        try:
+            torch.cuda.set_device(local)
+            break
+        except RuntimeError:
+            if attempt == 3:
+                raise
+            time.sleep(5.0)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
