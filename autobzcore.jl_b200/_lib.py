@@ -116,7 +116,15 @@ class Context:
     def __init__(self, device=0):
         self.lib = load()
         h = C.c_void_p()
-        rc = self.lib.abz_ctx_create(int(device), C.byref(h))
+        rc = ABZ_OK
+        for attempt in range(3):
+            rc = self.lib.abz_ctx_create(int(device), C.byref(h))
+            msg = "" if rc == ABZ_OK else self.lib.abz_last_error(None).decode()
+            # a just-vacated GPU has been seen to refuse driver initialisation once; an absent device stays absent
+            if rc != ABZ_E_CUDA or "initialization" not in msg or attempt == 2:
+                break
+            import time
+            time.sleep(3.0)
         if rc != ABZ_OK:
             raise AutoBZCudaError(rc, self.lib.abz_last_error(None).decode())
         self.h = h
