@@ -347,7 +347,8 @@ def main():
                 # dram__bytes_read+write of one resolvent launch, from the ncu --set full capture in profiles/ (16.68 kB per k-point
                 # = the 16 n^2 B of H(k) read once for all 128 frequencies; no re-reads), scaled to this run's launch size
                 "traffic": 16678.0 * min(nodes_rank, 262144), "traffic_source": "profiles/r01_ncu_full_resolvent_mma_raw.csv",
-                "peak_source": "cuBLAS ZGEMM 4096^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "peak_source": "cuBLAS ZGEMM 4096^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 entry; a 4 s sustained ZGEMM "
+                               "measures the same 36.8 TFLOP/s, profiles/r01_fp64_peaks.json)",
                 "algorithmic_flops_per_kpoint": {"fourier": f_four, "resolvent": f_res},
                 "eval_ms_per_step": ev_eval / args.steps, "matfun_ms_per_step": ev_mat / args.steps}
         cb = None
