@@ -39,10 +39,33 @@ __device__ __forceinline__ double2 nest_point_small(const double2* __restrict__ 
     double2 h[NN];
 #pragma unroll
     for (int e = 0; e < NN; e++) h[e] = make_double2(0.0, 0.0);
-    for (int m = 0; m < M1; m++) {
-        double2 p = cis2pi(xi * (double)(m + lo) / period);
+    // phases e^{2 pi i x R / period}, R = lo .. lo + M1 - 1, by powers of w = e^{2 pi i x / period} outwards from R = 0
+    // (one sincospi per node; |R| <= ~5 multiplications deep, the same few-ulp accuracy as reducing x R directly)
+    const double2 w = cis2pi(xi / period);
+    const int m0 = -lo;
+    if (m0 >= 0 && m0 < M1) {
 #pragma unroll
-        for (int e = 0; e < NN; e++) h[e] = cfma(h[e], c[m * NN + e], p);
+        for (int e = 0; e < NN; e++) h[e] = c[m0 * NN + e];
+        double2 p = w;
+        for (int m = m0 + 1; m < M1; m++) {
+#pragma unroll
+            for (int e = 0; e < NN; e++) h[e] = cfma(h[e], c[m * NN + e], p);
+            p = cmul(p, w);
+        }
+        const double2 wc = make_double2(w.x, -w.y);
+        p = wc;
+        for (int m = m0 - 1; m >= 0; m--) {
+#pragma unroll
+            for (int e = 0; e < NN; e++) h[e] = cfma(h[e], c[m * NN + e], p);
+            p = cmul(p, wc);
+        }
+    } else {
+        double2 p = cis2pi(xi * (double)lo / period);
+        for (int m = 0; m < M1; m++) {
+#pragma unroll
+            for (int e = 0; e < NN; e++) h[e] = cfma(h[e], c[m * NN + e], p);
+            p = cmul(p, w);
+        }
     }
     double2 t;
     if (fkind == 1) {
