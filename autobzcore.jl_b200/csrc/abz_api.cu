@@ -19,6 +19,7 @@
 #include "abz_iai.cuh"
 #include "abz_kernels.cuh"
 #include "abz_resolvent_mma.cuh"
+#include "abz_resolvent_gjreg.cuh"
 
 using namespace abz;
 
@@ -397,6 +398,33 @@ int upload_params(abz_ctx* ctx, int n, int nw, const double* z, const double* si
     return ABZ_OK;
 }
 
+// register-resident Gauss-Jordan teams (abz_resolvent_gjreg.cuh): variant 0 = 32 columns per thread, 168 registers (12 warps per SM),
+// 1 = 32 columns, 255 registers (8 warps, deeper prefetch of the pivot row), 2 = 16 columns per thread (teams twice as wide, 16 warps)
+// Defaults from measurements (profiles/r01_generic_resolvent_timing.log): traces 0, matrix-valued sums 2; ABZ_GJ_VARIANT overrides.
+static int gj_variant(bool matrix) {
+    static const int env = getenv("ABZ_GJ_VARIANT") ? atoi(getenv("ABZ_GJ_VARIANT")) : -1;
+    if (env >= 0 && env <= 2) return env;
+    return matrix ? 2 : 0;
+}
+static int gj_ctas_per_sm(int n, bool matrix) {
+    const int v = gj_variant(matrix);
+    if (n <= 32) return v == 0 ? 12 : 8;
+    return v == 0 ? 3 : 2;
+}
+#define GJ_DISPATCH(KERNEL, matrix, n, grid, smem, stream, ...)                                                       \
+    do {                                                                                                       \
+        const int v_ = gj_variant(matrix);                                                                        \
+        if ((n) <= 32) {                                                                                       \
+            if (v_ == 0) KERNEL<32, 32, 4, 12><<<grid, 32, smem, stream>>>(__VA_ARGS__);                       \
+            else if (v_ == 1) KERNEL<32, 32, 16, 8><<<grid, 32, smem, stream>>>(__VA_ARGS__);                  \
+            else KERNEL<32, 16, 8, 8><<<grid, 64, smem, stream>>>(__VA_ARGS__);                                \
+        } else {                                                                                               \
+            if (v_ == 0) KERNEL<64, 32, 4, 3><<<grid, 128, smem, stream>>>(__VA_ARGS__);                       \
+            else if (v_ == 1) KERNEL<64, 32, 16, 2><<<grid, 128, smem, stream>>>(__VA_ARGS__);                 \
+            else KERNEL<64, 16, 8, 2><<<grid, 256, smem, stream>>>(__VA_ARGS__);                               \
+        }                                                                                                      \
+    } while (0)
+
 size_t gj_smem_bytes(int n, int nw, int nwarps) {
     size_t per_warp = (size_t)n * (n + 1) + (n + 1) / 2 + 1;
     return ((size_t)n * n + nw + per_warp * nwarps) * sizeof(double2);
@@ -455,7 +483,7 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
         return ABZ_OK;
     }
     // DMMA register-resident fast path (norb <= 32; unpivoted block elimination with growth monitoring)
-    bool use_mma = (ctx->resolvent_algo != 1) && !ctx->force_generic && mma_resolvent_supported(n);
+    bool use_mma = (ctx->resolvent_algo != 1 && ctx->resolvent_algo != 4) && !ctx->force_generic && mma_resolvent_supported(n);
     if (use_mma) {
         long ncta = 0; int kper_m = 1;
         if (mma_resolvent_plan(n, nk, nw, sm, &ncta, &kper_m) == 0) {
@@ -473,6 +501,28 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
         }
     }
     if (n > 64) return fail(ctx, ABZ_E_UNSUPPORTED, "norb > 64 is not supported by the resolvent kernels");
+    if (ctx->resolvent_algo != 4 && !(n <= 12 && ctx->resolvent_algo != 1)) {   // (tiny matrices: the padded 32-row teams waste most lanes)
+        // register-resident pivoted Gauss-Jordan: one team (1 or 4 warps) per matrix, grid = (node chunks, frequency chunks)
+        const long target = (long)sm * gj_ctas_per_sm(n, false);   // one resident wave
+        const long chunks_k = std::min<long>(nk, target);
+        const int kper = (int)((nk + chunks_k - 1) / chunks_k);
+        const long ncx = (nk + kper - 1) / kper;
+        const long chunks_w = std::min<long>(nw, std::max<long>(1, target / ncx));
+        const int wper = (int)std::min<long>(64, (nw + chunks_w - 1) / chunks_w);
+        dim3 grid((unsigned)ncx, (unsigned)((nw + wper - 1) / wper));
+        double2* dst = yout;
+        if (mode == 0) {
+            CU(ctx, ctx->partial.reserve((size_t)ncx * nw * sizeof(double2)));
+            dst = ctx->partial.as<double2>();
+        }
+        GJ_DISPATCH(resolvent_gjreg_kernel, false, n, grid, 0, ctx->stream, H, wnode, nk, n, nw, z, sigma, kper, wper, mode, dst, ef);
+        LAUNCH_CHECK(ctx, "resolvent_gjreg_kernel");
+        if (mode == 0) {
+            reduce_partials_kernel<<<nw, 256, 0, ctx->stream>>>(ctx->partial.as<double2>(), ncx, nw, 1.0, ctx->acc.as<double2>());
+            LAUNCH_CHECK(ctx, "reduce_partials_kernel");
+        }
+        return ABZ_OK;
+    }
     int nwarps = 8;
     while (nwarps > 1 && gj_smem_bytes(n, nw, nwarps) > 200 * 1024) nwarps--;
     size_t smem = gj_smem_bytes(n, nw, nwarps);
@@ -1161,14 +1211,29 @@ int32_t abz_rule_resolvent_matrix_sum(abz_ctx* ctx, abz_rule_t rid, int32_t nw, 
         }
         cudaEvent_t e1 = next_event(ctx);
         // node chunks per frequency: enough CTAs to fill the chip, few enough that the partials stay small
-        const long target = std::max<long>(1, ((long)ctx->sm_count * 2 + nw - 1) / nw);
-        const int kper = (int)std::max<long>(nwarps, (nk + target - 1) / target);
+        const bool legacy = (ctx->resolvent_algo == 4) || (n <= 12 && ctx->resolvent_algo != 1);   // tiny matrices: a padded 32-row team wastes most of its lanes
+        const long per_sm = legacy ? 2 : gj_ctas_per_sm(n, true);
+        const long target = std::max<long>(1, ((long)ctx->sm_count * per_sm + nw - 1) / nw);
+        const int kper = (int)std::max<long>(legacy ? nwarps : 1, (nk + target - 1) / target);
         const long ncta = (nk + kper - 1) / kper;
         CU(ctx, ctx->partial.reserve((size_t)ncta * nacc * sizeof(double2)));
         dim3 grid((unsigned)ncta, (unsigned)nw);
-        resolvent_gj_matrix_kernel<<<grid, nwarps * 32, smem, ctx->stream>>>(Hd, r->d_node_w ? r->d_node_w + n0 : nullptr, nk, n, nw,
-                                                                            ctx->zbuf.as<double2>(), sigma ? ctx->sigbuf.as<double2>() : nullptr,
-                                                                            kper, ctx->partial.as<double2>(), ctx->errflag.as<int>());
+        const double* wn = r->d_node_w ? r->d_node_w + n0 : nullptr;
+        const double2* sgd = sigma ? ctx->sigbuf.as<double2>() : nullptr;
+        if (legacy) {
+            resolvent_gj_matrix_kernel<<<grid, nwarps * 32, smem, ctx->stream>>>(Hd, wn, nk, n, nw, ctx->zbuf.as<double2>(), sgd, kper,
+                                                                                ctx->partial.as<double2>(), ctx->errflag.as<int>());
+        } else {
+            static bool gj_attr = false;
+            if (!gj_attr) {
+                cudaFuncSetAttribute(resolvent_gjreg_matrix_kernel<64, 32, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                cudaFuncSetAttribute(resolvent_gjreg_matrix_kernel<64, 32, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                cudaFuncSetAttribute(resolvent_gjreg_matrix_kernel<64, 16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                gj_attr = true;
+            }
+            GJ_DISPATCH(resolvent_gjreg_matrix_kernel, true, n, grid, (size_t)nn * sizeof(double2), ctx->stream, Hd, wn, nk, n, nw,
+                        ctx->zbuf.as<double2>(), sgd, kper, ctx->partial.as<double2>(), ctx->errflag.as<int>());
+        }
         LAUNCH_CHECK(ctx, "resolvent_gj_matrix_kernel");
         const long nred = (long)nacc;
         for (long off = 0; off < nred; off += 65535) {      // one CTA per output element

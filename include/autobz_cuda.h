@@ -52,7 +52,8 @@ typedef uint64_t abz_nest_t;    /* IAI arena: contracted series for nested panel
 #define ABZ_EIG_GAUSS_DOS 3     /* sum_n exp(-((e_n-w)/s)^2)/(s sqrt(pi)), params = {w, s} */
 
 /* resolvent algorithm selection (abz_ctx_set_option ABZ_OPT_RESOLVENT_ALGO) */
-#define ABZ_OPT_RESOLVENT_ALGO 1   /* 0 auto, 1 generic pivoted Gauss-Jordan, 2 register/DMMA fast path, 3 frequency sweep from one
+#define ABZ_OPT_RESOLVENT_ALGO 1   /* 0 auto, 1 generic pivoted Gauss-Jordan (register-resident; 4 = the earlier shared-memory
+                                    * formulation, kept for cross-checks), 2 register/DMMA fast path, 3 frequency sweep from one
                                     * Householder tridiagonalisation per k: tr (z-H)^-1 = p'(z)/p(z), O(n) per frequency - opt-in, needs
                                     * Hermitian H(k) and a scalar (or no) self-energy; a matrix Sigma falls back to 0 */
 #define ABZ_OPT_MEM_BUDGET_MB 2    /* device workspace budget for streamed chunks (default 4096) */

@@ -84,6 +84,43 @@ def test_resolvent_algorithms_agree(ctx, orc, algo):
         ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
 
 
+@pytest.mark.parametrize("n", [4, 9, 31, 32, 33, 47, 64])
+@pytest.mark.parametrize("algo", [1, 4])
+def test_pivoted_gauss_jordan_needs_its_pivoting(ctx, orc, n, algo):
+    """the pivoted kernels (1: register-resident teams, 4: shared-memory) on matrices whose leading minors vanish:
+    H has a zero diagonal and z = 0 + i 1e-9, so elimination without row exchanges would divide by ~1e-9;
+    traces (weighted sum and per point) and the matrix-valued sum against the oracle's pivoted LU / numpy"""
+    rng = np.random.default_rng(100 + n)
+    c = np.zeros((n, n, 3, 1, 1), complex)
+    for m in range(3):
+        a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        np.fill_diagonal(a, 0.0)
+        c[:, :, m, 0, 0] = a
+    c[:, :, 2, 0, 0] = c[:, :, 0, 0, 0].conj().T
+    c[:, :, 1, 0, 0] = c[:, :, 1, 0, 0] + c[:, :, 1, 0, 0].conj().T
+    lo = (-1, 0, 0)
+    S = L.DeviceSeries(ctx, c, lo, (1.0,) * 3)
+    So = orc.Series(c, lo)
+    z = np.array([1e-9j, 0.3 + 1e-9j, -0.7 + 0.05j])
+    N = 4
+    ctx.set_option(L.OPT_RESOLVENT_ALGO, algo)
+    try:
+        R = L.DeviceRule(ctx, S, N)
+        assert rel(R.resolvent_sum(z, scale=1 / N ** 3), orc.ptr_sum(So, N, z)) < 1e-10
+        kp = rng.random((7, 3))
+        Hk = orc.eval_points(So, kp)
+        assert rel(S.points_resolvent(kp, z), orc.resolvent_trace_batch(Hk, z)) < 1e-10
+        G = R.resolvent_matrix_sum(z, scale=1 / N ** 3)
+        want = np.zeros((len(z), n, n), complex)
+        for i in range(N):
+            Hi = orc.eval_points(So, np.array([[i / N, 0.0, 0.0]]))[:, :, 0]
+            for w, zz in enumerate(z):
+                want[w] += np.linalg.inv(zz * np.eye(n) - Hi) / N
+        assert np.max(np.abs(G - want)) < 1e-10 * np.max(np.abs(want))
+    finally:
+        ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
+
+
 def test_singular_matrix_is_an_error(ctx):
     c = np.zeros((2, 2, 1, 1, 1))
     S = L.DeviceSeries(ctx, c, (0, 0, 0), (1.0,) * 3)
