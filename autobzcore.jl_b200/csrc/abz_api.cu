@@ -12,6 +12,7 @@
 #include <memory>
 #include <string>
 #include <unordered_map>
+#include <map>
 #include <vector>
 
 #include "abz_common.cuh"
@@ -100,8 +101,8 @@ struct abz_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::unordered_map<void*, size_t> pool_size;                    // every live or pooled block -> rounded size
-    std::unordered_map<size_t, std::vector<void*>> pool_free_list;   // rounded size -> free blocks
-    size_t pool_held = 0, pool_cap = (size_t)8 << 30;               // bytes parked in the free lists / their limit
+    std::map<size_t, std::vector<void*>> pool_free_list;             // rounded size -> free blocks (ordered: best fit)
+    size_t pool_held = 0, pool_cap = (size_t)16 << 30;              // bytes parked in the free lists / their limit
     std::string err;
     uint64_t next_id = 1;
     std::unordered_map<uint64_t, std::unique_ptr<Series>> series;
@@ -138,11 +139,12 @@ cudaError_t pool_alloc(abz_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
     if (bytes == 0) return cudaSuccess;
     const size_t r = pool_round(bytes);
-    auto it = ctx->pool_free_list.find(r);
-    if (it != ctx->pool_free_list.end() && !it->second.empty()) {
+    // best fit among the parked blocks, wasting at most the request again (a changed workload reuses what is parked)
+    for (auto it = ctx->pool_free_list.lower_bound(r); it != ctx->pool_free_list.end() && it->first <= 2 * r; ++it) {
+        if (it->second.empty()) continue;
         *p = it->second.back();
         it->second.pop_back();
-        ctx->pool_held -= r;
+        ctx->pool_held -= it->first;
         return cudaSuccess;
     }
     cudaError_t e = cudaMalloc(p, r);
@@ -162,7 +164,24 @@ void pool_free(abz_ctx* ctx, void* p) {
     auto it = ctx->pool_size.find(p);
     if (it == ctx->pool_size.end()) { cudaFree(p); return; }
     const size_t r = it->second;
-    if (ctx->pool_held + r > ctx->pool_cap) { cudaFree(p); ctx->pool_size.erase(it); return; }
+    if (r > ctx->pool_cap) { cudaFree(p); ctx->pool_size.erase(it); return; }
+    // over the limit: the most recently used block stays, the largest parked blocks go back to the driver
+    while (ctx->pool_held + r > ctx->pool_cap) {
+        auto big = ctx->pool_free_list.end();
+        bool evicted = false;
+        while (big != ctx->pool_free_list.begin()) {
+            --big;
+            if (big->second.empty()) continue;
+            void* q = big->second.back();
+            big->second.pop_back();
+            cudaFree(q);
+            ctx->pool_size.erase(q);
+            ctx->pool_held -= big->first;
+            evicted = true;
+            break;
+        }
+        if (!evicted) break;
+    }
     ctx->pool_free_list[r].push_back(p);       // work that used p is ordered before any reuse: one stream per context
     ctx->pool_held += r;
 }
