@@ -78,8 +78,14 @@ __device__ __forceinline__ void inv8(double& xr0, double& xr1, double& xi0, doub
         const double pr0 = __shfl_sync(0xffffffffu, xr0, 4 * p + q), pr1 = __shfl_sync(0xffffffffu, xr1, 4 * p + q);
         const double pi0 = __shfl_sync(0xffffffffu, xi0, 4 * p + q), pi1 = __shfl_sync(0xffffffffu, xi1, 4 * p + q);
         // pivot a_pp (from the pivot-row values held at quad lane qp) and my row's multiplier a_gp
+#ifdef ABZ_INV8_TWO_LEVEL
         const double ppr = __shfl_sync(0xffffffffu, sg ? pr1 : pr0, quad | qp);
         const double ppi = __shfl_sync(0xffffffffu, sg ? pi1 : pi0, quad | qp);
+#else
+        // straight from the lane that owns a_pp (not through the shuffled pivot row: one shuffle less on the critical chain)
+        const double ppr = __shfl_sync(0xffffffffu, sg ? xr1 : xr0, 4 * p + qp);
+        const double ppi = __shfl_sync(0xffffffffu, sg ? xi1 : xi0, 4 * p + qp);
+#endif
         const double fr = __shfl_sync(0xffffffffu, sg ? xr1 : xr0, quad | qp);
         const double fi = __shfl_sync(0xffffffffu, sg ? xi1 : xi0, quad | qp);
         const double d = fma(ppr, ppr, ppi * ppi);
