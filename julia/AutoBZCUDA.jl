@@ -202,6 +202,42 @@ function (rule::DeviceRule{d})(f::F, B::AutoSymPTR.Basis, buffer=nothing) where 
     return acc * abs(det(B.B)) / (rule.npt^d * rule.nsyms)
 end
 
+# ---- S2'': Hermitian eigenvalues on the rule's nodes (eigen(Hermitian(h)), src/dos_ggr.jl:19,34; config C5) -------------
+# kind 0: sum of eigenvalues, 1: Fermi-weighted band energy sum_n e_n f((e_n - mu)/T), 2: occupation sum_n f(..), 3: Gaussian DOS
+# (ABZ_EIG_* in include/autobz_cuda.h); params = (mu, T) or (w, s)
+function eig_sum(rule::DeviceRule, kind::Integer, params::Vector{Float64}, scale::Float64)
+    out = zeros(1)
+    check(rule.ctx, ccall((:abz_rule_eig_sum, LIB), Int32, (Ptr{Cvoid}, UInt64, Int32, Ptr{Float64}, Float64, Ptr{Float64}),
+                          rule.ctx.h, rule.h, kind, params, scale, out))
+    return out[1]
+end
+function eigvals(rule::DeviceRule)
+    e = Matrix{Float64}(undef, rule.series.norb, rule.nnodes)
+    check(rule.ctx, ccall((:abz_rule_eigvals, LIB), Int32, (Ptr{Cvoid}, UInt64, Ptr{Float64}), rule.ctx.h, rule.h, e))
+    return e
+end
+# keep H(k) of this rule on the device between calls (the reference's cached rule, src/fourier.jl:344-360)
+materialize!(rule::DeviceRule) = (check(rule.ctx, ccall((:abz_rule_materialize, LIB), Int32, (Ptr{Cvoid}, UInt64), rule.ctx.h, rule.h)); rule)
+
+# algorithm options (ABZ_OPT_* in the header), e.g. set_option!(ctx, 1, 3): frequency sweep from one tridiagonalisation per k
+set_option!(ctx::Context, option::Integer, value::Integer) =
+    check(ctx, ccall((:abz_ctx_set_option, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), ctx.h, option, value))
+
+# ---- multi-GPU: one process per GPU, the k3 planes (PTR) or outermost panel nodes (IAI) dealt to ranks, ONE sum-allreduce
+# per rule evaluation.  Either pass an MPI.Allreduce! closure as `exchange` to iai_solve / reduce the rule sums with MPI in
+# Julia, or let the library own an NCCL communicator: rank 0 creates the id, everybody gets it (e.g. MPI.Bcast!), then
+function unique_id()
+    id = zeros(UInt8, 128)
+    rc = ccall((:abz_comm_unique_id, LIB), Int32, (Ptr{UInt8},), id)
+    rc == 0 || throw(AbzError(rc, "abz_comm_unique_id"))
+    return id
+end
+comm_init!(ctx::Context, rank::Integer, nranks::Integer, id::Vector{UInt8}) =
+    check(ctx, ccall((:abz_comm_init, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), ctx.h, rank, nranks, id))
+allreduce_sum!(ctx::Context, buf::Vector{Float64}) =
+    (check(ctx, ccall((:abz_allreduce_sum, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64), ctx.h, buf, length(buf))); buf)
+comm_destroy!(ctx::Context) = check(ctx, ccall((:abz_comm_destroy, LIB), Int32, (Ptr{Cvoid},), ctx.h))
+
 # ---- S3: BatchIntegrand f!(y, x, p) for scattered k (src/batch.jl:4-20) -------------------------------
 function resolvent_batch!(y::Vector{ComplexF64}, x::Vector{SVector{3,Float64}}, ds::DeviceSeries, z::ComplexF64)
     resize!(y, length(x))
@@ -224,7 +260,9 @@ end
 function DeviceNest(ds::DeviceSeries, ndim, cap2, cap1)
     h = Ref{UInt64}(0)
     check(ds.ctx, ccall((:abz_nest_create, LIB), Int32, (Ptr{Cvoid}, UInt64, Int32, Int64, Int64, Ref{UInt64}), ds.ctx.h, ds.h, ndim, cap2, cap1, h))
-    return DeviceNest(ds.ctx, h[])
+    nest = DeviceNest(ds.ctx, h[])
+    finalizer(x -> ccall((:abz_nest_destroy, LIB), Int32, (Ptr{Cvoid}, UInt64), x.ctx.h, x.h), nest)
+    return nest
 end
 contract3!(n::DeviceNest, x3::Vector{Float64}, slot2::Vector{Int64}) =
     check(n.ctx, ccall((:abz_nest_contract3, LIB), Int32, (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Ptr{Int64}), n.ctx.h, n.h, length(x3), x3, slot2))
