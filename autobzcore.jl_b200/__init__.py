@@ -13,7 +13,8 @@ from .bz import (FBZ, CubicLimits, CubicSymIBZ, InversionSymIBZ, SymmetricBZ, Te
 from .dos import GGR, DOSCache, DOSProblem, DOSSolution  # noqa: F401
 from .fourier import (AffineTraceIntegrand, BatchIntegrand, DOSIntegrand, EigenIntegrand, FourierIntegrand, FourierSeries,  # noqa: F401
                       FourierValue, GlocIntegrand, NestedBatchIntegrand, TrGlocIntegrand, dos_integrand, gloc_integrand, gloc_trace_integrand)
-from .interfaces import (Basis, IntegralProblem, IntegralSolution, IntegralSolver, Shard, batchsolve, batchsolve_log, init,  # noqa: F401
+from .interfaces import (Basis, IntegralProblem, IntegralSolution, IntegralSolver, MixedParameters, Shard, batchsolve, batchsolve_log, init,
+                         merge, paramproduct, paramzip,  # noqa: F401
                          solve, solve_, torch_allreduce)
 from .wannier import read_w90_hrdat, read_wout_lattice  # noqa: F401
 

@@ -104,6 +104,8 @@ def _alg_norm(salg):
 def _params(p):
     if p is None:
         return ((), {})
+    if isinstance(p, MixedParameters):
+        return (p.args, p.kwargs)
     if isinstance(p, tuple) and len(p) == 2 and isinstance(p[1], dict):
         return p
     if isinstance(p, dict):
@@ -111,6 +113,81 @@ def _params(p):
     if isinstance(p, (tuple, list)):
         return (tuple(p), {})
     return ((p,), {})
+
+
+class MixedParameters:
+    """MixedParameters(args...; kwargs...) (src/parameters.jl:11-35): positional and keyword parameters of an integrand,
+    with the reference's access (`p[i]` positional - 0-based here -, `p.name` / `p["name"]` keyword) and `merge`.
+    Everywhere a parameter is expected, a MixedParameters, a plain ((args...), {kwargs}) pair, a dict, a tuple or a scalar
+    are accepted (`_params` normalises them)."""
+
+    def __init__(self, *args, **kwargs):
+        object.__setattr__(self, "args", tuple(args))
+        object.__setattr__(self, "kwargs", dict(kwargs))
+
+    def __getitem__(self, i):
+        return self.kwargs[i] if isinstance(i, str) else self.args[i]
+
+    def __getattr__(self, name):
+        try:
+            return object.__getattribute__(self, "kwargs")[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def __setattr__(self, name, value):
+        raise AttributeError("MixedParameters is immutable")
+
+    def __eq__(self, other):
+        return isinstance(other, MixedParameters) and self.args == other.args and self.kwargs == other.kwargs
+
+    def __hash__(self):
+        return hash((self.args, tuple(sorted(self.kwargs.items(), key=lambda kv: kv[0]))))
+
+    def merge(self, q):
+        """merge(p, q) (src/parameters.jl:26-35): MixedParameters / dicts (NamedTuples) merge keywords (right wins) and
+        append positional parameters; tuples append their entries; any other value is appended as one positional parameter"""
+        if isinstance(q, MixedParameters):
+            return MixedParameters(*(self.args + q.args), **{**self.kwargs, **q.kwargs})
+        if isinstance(q, tuple) and len(q) == 2 and isinstance(q[1], dict):
+            return MixedParameters(*(self.args + tuple(q[0])), **{**self.kwargs, **q[1]})
+        if isinstance(q, dict):
+            return MixedParameters(*self.args, **{**self.kwargs, **q})
+        if isinstance(q, (tuple, list)):
+            return MixedParameters(*(self.args + tuple(q)), **self.kwargs)
+        return MixedParameters(*(self.args + (q,)), **self.kwargs)
+
+    def __repr__(self):
+        kw = ", ".join(f"{k}={v!r}" for k, v in self.kwargs.items())
+        return "MixedParameters(" + ", ".join([*(repr(a) for a in self.args), *([kw] if kw else [])]) + ")"
+
+
+def merge(p, q):
+    """Base.merge on parameters (src/parameters.jl:26-35)"""
+    a, k = _params(p)
+    return MixedParameters(*a, **k).merge(q)
+
+
+def paramzip(*args, **kwargs):
+    """paramzip(args...; kwargs...) (src/parameters.jl:37-56): result[i] = MixedParameters(args[0][i], ...; name=kwargs[name][i])"""
+    cols = [list(a) for a in args] + [list(v) for v in kwargs.values()]
+    if not cols:
+        return []
+    n = min(len(c) for c in cols)                     # zip semantics
+    names = list(kwargs)
+    return [MixedParameters(*(a[i] for a in (list(x) for x in args)), **{k: list(kwargs[k])[i] for k in names}) for i in range(n)]
+
+
+def paramproduct(*args, **kwargs):
+    """paramproduct(args...; kwargs...) (src/parameters.jl:58-69): the Cartesian product as an object array of shape
+    (len(args[0]), ..., len(kwargs[...]), ...), element [i1, ..., in] = MixedParameters(args[0][i1], ...; name=kwargs[name][in])"""
+    cols = [list(a) for a in args] + [list(v) for v in kwargs.values()]
+    names = list(kwargs)
+    na = len(args)
+    out = np.empty(tuple(len(c) for c in cols), dtype=object)
+    for idx in np.ndindex(*out.shape):
+        vals = [c[i] for c, i in zip(cols, idx)]
+        out[idx] = MixedParameters(*vals[:na], **dict(zip(names, vals[na:])))
+    return out
 
 
 class _BoundIntegrand:
@@ -481,7 +558,8 @@ def batchsolve(solver, ps, callback=None):
     """batchsolve(solver, ps) (src/interfaces.jl:199-243): solve for every parameter in `ps` against ONE cached
     rule.  The reference threads over parameters with the grid shared; here the parameters are an inner batch
     dimension of the device kernels (one H(k) load, n_omega resolvents) whenever the algorithm is a fixed rule."""
-    plist = list(ps)
+    shape = ps.shape if isinstance(ps, np.ndarray) and ps.dtype == object and ps.ndim > 1 else None   # paramproduct
+    plist = list(ps.ravel()) if shape is not None else list(ps)
     base = _params(solver.prob.p)
     merged = []
     for p in plist:
@@ -493,7 +571,8 @@ def batchsolve(solver, ps, callback=None):
     if callback is not None:
         for i, (p, s) in enumerate(zip(plist, sols)):
             callback(solver.prob.f, i, len(plist), p, s, t / max(1, len(plist)))
-    return np.array([s.u for s in sols])
+    out = np.array([s.u for s in sols])
+    return out.reshape(shape + out.shape[1:]) if shape is not None else out
 
 
 def batchsolve_log(path, solver, ps, verb=False):

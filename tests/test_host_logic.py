@@ -299,3 +299,35 @@ def test_nested_batch_integrand_equals_plain(d):
         assert abs(u1 - u2) < 1e-12 * abs(u1) and abs(u1 - 4.2) < 1e-7
     with pytest.raises(TypeError):
         ab.FourierIntegrand(p, s, nest=object())
+
+
+def test_mixed_parameters_paramzip_paramproduct():
+    """test/brillouin.jl:46-61 (MixedParameters merge rules) and :98-111 (batchsolve over paramzip / paramproduct arrays
+    equals the loops over solver(a, b=b)), with the affine Fourier integrand of test/fourier.jl:41 as f(x, a; b)"""
+    args, kwargs = (1, 2), {"a": "a", "b": "b"}
+    p, q = ab.MixedParameters(*args), ab.MixedParameters(**kwargs)
+    for pq in (ab.merge(p, q), ab.merge(p, kwargs), ab.merge(q, args)):
+        assert pq[0] == args[0] and pq[1] == args[1] and pq.a == "a" and pq.b == "b"
+    assert ab.merge(p, 3)[2] == 3 and ab.merge(q, 3)[0] == 3            # generic values are appended
+    assert ab.merge(p, {"a": "c"}).a == "c" and ab.merge(q, {"a": "c"}).a == "c"   # keywords overwritten
+    z = ab.paramzip([1, 2, 3], b=[4, 5, 6])
+    assert [(m[0], m.b) for m in z] == [(1, 4), (2, 5), (3, 6)]
+    pp = ab.paramproduct([1, 2, 3], b=[4, 5])
+    assert pp.shape == (3, 2) and pp[2, 1] == ab.MixedParameters(3, b=5)
+
+    s = lattice_series(2)
+    bz = ab.load_bz(ab.FBZ(), np.eye(2))
+    f = ab.FourierIntegrand(lambda x, a, b=0.0: a * x.s + b, s)
+    solver = ab.IntegralSolver(f, bz, ab.PTR(npt=6), backend=OracleBackend())
+    rng = np.random.default_rng(3)
+    as_, bs = rng.random(3), rng.random(2)
+    want_zip = [solver(a, b=b) for a, b in zip(as_, bs)]
+    assert np.allclose(ab.batchsolve(solver, ab.paramzip(as_, b=bs)), want_zip, rtol=1e-14)
+    want_prod = np.array([[solver(a, b=b) for b in bs] for a in as_])
+    got = ab.batchsolve(solver, ab.paramproduct(as_, b=bs))
+    assert got.shape == (3, 2) and np.allclose(got, want_prod, rtol=1e-14)
+    # parameters preloaded in the integrand merge with the solver's call (ParameterIntegrand, test/brillouin.jl:83-96)
+    f2 = ab.FourierIntegrand(lambda x, a, b=0.0: a * x.s + b, s, b=bs[0])
+    solver2 = ab.IntegralSolver(f2, bz, ab.PTR(npt=6), backend=OracleBackend())
+    assert np.allclose(solver2(as_[0]), solver(as_[0], b=bs[0]), rtol=1e-14)
+    assert np.allclose(ab.batchsolve(solver2, [ab.MixedParameters(a) for a in as_]), [solver(a, b=bs[0]) for a in as_], rtol=1e-14)
