@@ -78,3 +78,32 @@ for case in range(ncase):
     finally:
         ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
 print(f"{ncase} cases, {fails} failures, worst relative errors {worst}, {time.time() - t0:.1f} s")
+
+# ---- symmetry-reduced rules through the public API: the IBZ (device-side symptr_rule) must reproduce the full-BZ integral
+fails2, worst2 = 0, 0.0
+for case in range(max(10, ncase // 8)):
+    n = int(rng.choice([1, 2, 3, 5, 8, 16, 32, 33, 64]))
+    npt = int(rng.integers(2, 14 if n <= 8 else 8))
+    H, lo = ab.synthetic.wannier_hamiltonian(n, int(rng.integers(1, 3)), cubic=True)
+    ext = ab.synthetic.band_extent(H)
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=n)
+    A = np.eye(3) * float(rng.uniform(0.5, 2.0))
+    tag = f"sym case {case}: n={n} npt={npt}"
+    try:
+        if rng.integers(0, 2):
+            f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=0.05 * ext)
+            p = {"omega": float(rng.uniform(-ext, ext))}
+        else:
+            f = ab.FourierIntegrand(ab.EigenIntegrand("fermi_energy"), fs, 0.1 * ext, 0.2 * ext)
+            p = None
+        vals = [ab.solve(ab.IntegralProblem(f, ab.load_bz(kind, A), p), ab.PTR(npt=npt)).u for kind in (ab.FBZ(), ab.InversionSymIBZ(), ab.CubicSymIBZ())]
+        e = max(rel(vals[1], vals[0]), rel(vals[2], vals[0]))
+        worst2 = max(worst2, e)
+        if not e < 1e-10:
+            fails2 += 1
+            print("FAIL", tag, e, vals, flush=True)
+    except Exception as ex:                                 # noqa: BLE001
+        fails2 += 1
+        print("ERROR", tag, type(ex).__name__, str(ex)[:200], flush=True)
+print(f"symmetric rules: {max(10, ncase // 8)} cases, {fails2} failures, worst IBZ-vs-FBZ relative difference {worst2}")
+sys.exit(1 if fails or fails2 else 0)
