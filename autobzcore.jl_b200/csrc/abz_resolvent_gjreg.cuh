@@ -1,7 +1,7 @@
 // K3-generic: (z - H(k) - Sigma_w)^-1 by in-place Gauss-Jordan elimination with partial pivoting (the robustness of
 // LAPACK getrf/getri, i.e. Julia's `inv(::Matrix)`), with the matrix resident in REGISTERS: a team of NP x (NP/CW)
 // threads owns one matrix, thread (r, h) holding row r, columns CW h .. CW h + CW - 1.  Pivoting is implicit: the pivot
-// row of step p is chosen among the rows not used yet (one REDUX over float-bit keys) and stays where it is (no row
+// row of step p is chosen among the rows not used yet (one REDUX over keys made of the high words of |re| + |im|) and stays where it is (no row
 // exchange), the permutation is undone when the trace / the inverse is read out.  Per step the team exchanges one
 // column (multipliers and pivot candidates) and one row (the pivot row) through double-buffered shared memory: two
 // barriers, CW broadcast 128-bit shared loads (fetched LD entries ahead of their FMAs) and CW complex FMAs per thread.
@@ -15,7 +15,7 @@ namespace abz {
 
 template <int NP>
 struct GjShared {
-    unsigned key[2][NP];     // pivot candidates: float bits of |re| + |im| (low 6 bits: 63 - row), 0 = row already used / padding
+    unsigned key[2][NP];     // pivot candidates: high word of the double |re| + |im| (low 6 bits: 63 - row), 0 = row already used / padding
     double2 col[2][NP];      // the current column (multipliers)
     double2 prow[2][NP];     // the pivot row (in the register order of its segment)
     int piv[NP];             // piv[p] = physical row of logical row p
@@ -61,8 +61,8 @@ __device__ __forceinline__ bool gj_reg_invert(double2 (&x)[CW], int n, int r, in
         const bool cur = (NP == CW) || (h == p / CW);
         if (cur) {
             const double2 a = x[0];
-            const float v = (float)(fabs(a.x) + fabs(a.y));
-            sh.key[b][r] = used ? 0u : ((__float_as_uint(v) & ~63u) | (unsigned)(63 - r));
+            const unsigned hi = (unsigned)__double2hiint(fabs(a.x) + fabs(a.y));   // sign 0: ordered like the value
+            sh.key[b][r] = used ? 0u : ((hi & ~63u) | (unsigned)(63 - r));
             sh.col[b][r] = a;
         }
         gj_team_sync<T>();
@@ -70,7 +70,7 @@ __device__ __forceinline__ bool gj_reg_invert(double2 (&x)[CW], int n, int r, in
         unsigned key = sh.key[b][lane];
         if (NP == 64) key = max(key, sh.key[b][lane + 32]);
         key = __reduce_max_sync(0xffffffffu, key);
-        if ((key & ~63u) == 0u || key >= 0x7f800000u) return false;            // uniform: singular, Inf or NaN
+        if ((key & ~63u) == 0u || key >= 0x7ff00000u) return false;            // uniform: singular, Inf or NaN
         const int bi = 63 - (int)(key & 63u);
         const bool me = (r == bi);
         if (me) {
