@@ -520,7 +520,7 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
         }
     }
     if (n > 64) return fail(ctx, ABZ_E_UNSUPPORTED, "norb > 64 is not supported by the resolvent kernels");
-    if (ctx->resolvent_algo != 4 && !(n <= 12 && ctx->resolvent_algo != 1)) {   // (tiny matrices: the padded 32-row teams waste most lanes)
+    if (ctx->resolvent_algo != 4 && !(n <= 16 && ctx->resolvent_algo != 1)) {   // (n <= 16: a padded 32-row team wastes its lanes; measured crossover)
         // register-resident pivoted Gauss-Jordan: one team (1 or 4 warps) per matrix, grid = (node chunks, frequency chunks)
         const long target = (long)sm * gj_ctas_per_sm(n, false);   // one resident wave
         const long chunks_k = std::min<long>(nk, target);
@@ -1230,7 +1230,7 @@ int32_t abz_rule_resolvent_matrix_sum(abz_ctx* ctx, abz_rule_t rid, int32_t nw, 
         }
         cudaEvent_t e1 = next_event(ctx);
         // node chunks per frequency: enough CTAs to fill the chip, few enough that the partials stay small
-        const bool legacy = (ctx->resolvent_algo == 4) || (n <= 12 && ctx->resolvent_algo != 1);   // tiny matrices: a padded 32-row team wastes most of its lanes
+        const bool legacy = (ctx->resolvent_algo == 4) || (n <= 20 && ctx->resolvent_algo != 1);   // n <= 20: a padded 32-row team wastes its lanes (measured crossover)
         const long per_sm = legacy ? 2 : gj_ctas_per_sm(n, true);
         const long target = std::max<long>(1, ((long)ctx->sm_count * per_sm + nw - 1) / nw);
         const int kper = (int)std::max<long>(legacy ? nwarps : 1, (nk + target - 1) / target);

@@ -18,7 +18,10 @@ def best_ms(fn, reps=5):
     return 1e3 * min(ts)
 
 
-for n, N, nw in ((8, 48, 8), (24, 40, 8), (32, 40, 8), (48, 28, 8), (64, 28, 8)):
+CASES = ((8, 48, 8), (24, 40, 8), (32, 40, 8), (48, 28, 8), (64, 28, 8))
+if len(sys.argv) > 1:      # python tools/time_generic_resolvent.py 12 16 20: other orbital counts on a 40^3 grid
+    CASES = tuple((int(a), 40, 8) for a in sys.argv[1:])
+for n, N, nw in CASES:
     H, lo = ab.synthetic.wannier_hamiltonian(n, 2)
     S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
     R = L.DeviceRule(ctx, S, N)
