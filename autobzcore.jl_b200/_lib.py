@@ -15,7 +15,7 @@ ABZ_OK = 0
 ABZ_E_INVALID, ABZ_E_OOM, ABZ_E_CUDA, ABZ_E_SINGULAR, ABZ_E_UNSUPPORTED, ABZ_E_NCCL = -1, -2, -3, -4, -5, -6
 F_RESOLVENT_TRACE, F_TRACE_H = 0, 1
 EIG_SUM, EIG_FERMI_ENERGY, EIG_FERMI_COUNT, EIG_GAUSS_DOS = 0, 1, 2, 3
-OPT_RESOLVENT_ALGO, OPT_MEM_BUDGET_MB, OPT_FUSED_SMALL, OPT_EIG_ALGO, OPT_IAI_LEAF_SPILL = 1, 2, 3, 4, 5
+OPT_RESOLVENT_ALGO, OPT_MEM_BUDGET_MB, OPT_FUSED_SMALL, OPT_EIG_ALGO, OPT_IAI_LEAF_SPILL, OPT_IAI_LANES = 1, 2, 3, 4, 5, 6
 IAI_DEVICE_LEAVES = 1
 
 # every symbol include/autobz_cuda.h declares (tests check that the library exports all of them)

@@ -93,6 +93,20 @@ struct Nest {
 };
 
 struct Chunk { long p0, p1, r0, r1; };
+
+// one in-flight round of the IAI engine (abz_iai_engine.hpp "lanes"): its own stream, staging and scratch buffers
+struct IaiLane {
+    cudaStream_t stream = nullptr;
+    void* pin_in = nullptr; size_t pin_in_cap = 0;
+    void* pin_out = nullptr; size_t pin_out_cap = 0;
+    DevBuf in, out, spill;
+    size_t ns = 0, nt = 0;
+    ~IaiLane() {
+        if (pin_in) cudaFreeHost(pin_in);
+        if (pin_out) cudaFreeHost(pin_out);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
 constexpr int ABZ_RETRY_PIVOTED = 1;   // internal: the unpivoted fast path saw a tiny pivot; rerun with the pivoted kernel
 
 }  // namespace
@@ -112,12 +126,14 @@ struct abz_ctx {
     size_t budget = (size_t)4096 << 20;
     int fused_small = 1;
     int eig_algo = 0;             // 0: tridiagonalisation + QL, 1: two-sided Jacobi
+    int iai_lanes_opt = 4;        // IAI rounds in flight (ABZ_OPT_IAI_LANES)
     int leaf_spill = LEAF_SPILL;  // segments per device-side innermost integral beyond the 63 kept in shared memory
     bool force_generic = false;   // set while re-running a call whose fast path asked for pivoting
     DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d, iai_in, iai_out, eig_d, eig_e, symw, symlist;
     void* pin_in = nullptr; size_t pin_in_cap = 0;     // pinned staging for the IAI engine's per-round traffic
     void* pin_out = nullptr; size_t pin_out_cap = 0;
     long launches = 0;
+    std::vector<std::unique_ptr<IaiLane>> iai_lanes;
     std::vector<cudaEvent_t> events;
     size_t ev_used = 0;
     double eval_ms = 0, matfun_ms = 0;
@@ -661,6 +677,7 @@ int32_t abz_ctx_destroy(abz_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     abz_comm_destroy(ctx);
     ctx->rules.clear(); ctx->nests.clear(); ctx->series.clear();
+    ctx->iai_lanes.clear();
     pool_release(ctx);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
@@ -678,6 +695,8 @@ int32_t abz_ctx_set_option(abz_ctx* ctx, int32_t option, int64_t value) {
             ctx->budget = (size_t)value << 20; return ABZ_OK;
         case ABZ_OPT_FUSED_SMALL: ctx->fused_small = (int)value; return ABZ_OK;
         case ABZ_OPT_EIG_ALGO: ctx->eig_algo = (int)value; return ABZ_OK;
+        case ABZ_OPT_IAI_LANES: if (value < 1 || value > 16) return fail(ctx, ABZ_E_INVALID, "lanes must be in 1..16");
+            ctx->iai_lanes_opt = (int)value; return ABZ_OK;
         case ABZ_OPT_IAI_LEAF_SPILL: if (value == 0 || value < -63 || value > (1 << 20)) return fail(ctx, ABZ_E_INVALID, "spill capacity out of range");
             ctx->leaf_spill = (int)value; return ABZ_OK;
     }
@@ -1756,6 +1775,132 @@ struct IaiDeviceBackend {
         return abz_allreduce_sum(ctx, buf, (int64_t)n);
     }
 
+    // ---- lanes (several rounds in flight, one stream each): the fused small-orbital kernels only; the general path below
+    //      shares the context's work buffers and runs one round at a time
+    int nlanes = 1;
+    int lanes() const { return nlanes; }
+    int submit(int g, abz_iai::Round& R) { return nlanes == 1 ? ABZ_OK : enqueue(*ctx->iai_lanes[g], R); }
+    int wait(int g, abz_iai::Round& R) { return nlanes == 1 ? run_round(R) : collect(*ctx->iai_lanes[g], R); }
+
+    int init_lanes(int want) {
+        nlanes = want < 1 ? 1 : want;
+        if (nlanes == 1) return ABZ_OK;
+        while ((int)ctx->iai_lanes.size() < nlanes) {
+            std::unique_ptr<IaiLane> ln(new IaiLane());
+            CU(ctx, cudaStreamCreateWithFlags(&ln->stream, cudaStreamNonBlocking));
+            ctx->iai_lanes.push_back(std::move(ln));
+        }
+        CU(ctx, cudaStreamSynchronize(ctx->stream));      // parameters uploaded on the context's stream are complete
+        return ABZ_OK;
+    }
+
+    int enqueue(IaiLane& ln, abz_iai::Round& R) {
+        Series* s = nst->s;
+        const int n = s->n;
+        const long nn = (long)n * n;
+        const size_t n3 = R.c3_x.size(), n2 = R.c2_x.size(), ns = R.seg_a.size(), nt = R.task_a.size();
+        if (n3 > 0 && nst->ndim != 3) return fail(ctx, ABZ_E_INVALID, "internal: level-2 contraction on a nest with ndim < 3");
+        cudaStream_t st = ln.stream;
+        const size_t words = 2 * n3 + 3 * n2 + 3 * ns + 4 * nt;
+        int rc = pin_reserve(ctx, &ln.pin_in, &ln.pin_in_cap, words * 8);
+        if (rc) return rc;
+        CU(ctx, ln.in.reserve(words * 8 + 8));
+        char* h = (char*)ln.pin_in;
+        size_t off = 0;
+        auto put = [&](const void* src, size_t cnt) { size_t o = off; if (cnt) memcpy(h + 8 * off, src, 8 * cnt); off += cnt; return o; };
+        const size_t o_c3x = put(R.c3_x.data(), n3), o_c3s = put(R.c3_slot.data(), n3);
+        const size_t o_c2x = put(R.c2_x.data(), n2), o_c2p = put(R.c2_parent.data(), n2), o_c2s = put(R.c2_slot.data(), n2);
+        const size_t o_sa = put(R.seg_a.data(), ns), o_sb = put(R.seg_b.data(), ns), o_ss = put(R.seg_slot.data(), ns);
+        const size_t o_ta = put(R.task_a.data(), nt), o_tb = put(R.task_b.data(), nt), o_tt = put(R.task_atol.data(), nt),
+                     o_ts = put(R.task_slot.data(), nt);
+        if (words) CU(ctx, cudaMemcpyAsync(ln.in.p, h, words * 8, cudaMemcpyHostToDevice, st));
+        const double* dD = ln.in.as<double>();
+        const long* dL = ln.in.as<long>();
+        if (n3) {
+            const long rows = nn * s->M[0] * s->M[1];
+            dim3 grid((unsigned)((rows + 255) / 256), (unsigned)n3);
+            nest_contract_kernel<<<grid, 256, (size_t)s->M[2] * sizeof(double2), st>>>(
+                s->c, 0, nullptr, dD + o_c3x, dL + o_c3s, nst->L2, rows, s->M[2], s->lo[2], s->period[2]);
+            LAUNCH_CHECK(ctx, "nest_contract_kernel");
+        }
+        if (n2) {
+            const long rows = nn * s->M[0];
+            const bool root = (nst->ndim == 2);
+            dim3 grid((unsigned)((rows + 255) / 256), (unsigned)n2);
+            nest_contract_kernel<<<grid, 256, (size_t)s->M[1] * sizeof(double2), st>>>(
+                root ? s->c : nst->L2, root ? 0 : rows * s->M[1], root ? nullptr : dL + o_c2p, dD + o_c2x, dL + o_c2s, nst->L1, rows,
+                s->M[1], s->lo[1], s->period[1]);
+            LAUNCH_CHECK(ctx, "nest_contract_kernel");
+        }
+        const size_t owords = 4 * ns + 4 * nt + 1;
+        rc = pin_reserve(ctx, &ln.pin_out, &ln.pin_out_cap, owords * 8);
+        if (rc) return rc;
+        CU(ctx, ln.out.reserve(owords * 8));
+        double* dout = ln.out.as<double>();
+        int* ef = ctx->errflag.as<int>();
+        const bool has_slots = (nst->ndim >= 2);
+        const double2* L1 = has_slots ? nst->L1 : s->c;
+        const long stride = has_slots ? nn * s->M[0] : 0;
+        if (ns) {
+            const long* sslot = has_slots ? dL + o_ss : nullptr;
+            unsigned g = (unsigned)((ns + 7) / 8);
+            static bool attr_panel = false;
+            if (!attr_panel) {
+                cudaFuncSetAttribute(nest_panel_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                cudaFuncSetAttribute(nest_panel_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                cudaFuncSetAttribute(nest_panel_small_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                attr_panel = true;
+            }
+            if ((size_t)8 * s->M[0] * n * n * sizeof(double2) > 160 * 1024)
+                return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension for the IAI panel kernel");
+#define PANEL_LAUNCH(NORB)                                                                                               \
+    nest_panel_small_kernel<NORB><<<g, 128, (size_t)8 * s->M[0] * NORB * NORB * sizeof(double2), st>>>(L1, stride, dD + o_sa, dD + o_sb, sslot, (long)ns, s->M[0], s->lo[0], \
+                                                             s->period[0], fkind, vkind, z, dsig, la, lb, dout, ef)
+            if (n == 1) PANEL_LAUNCH(1); else if (n == 2) PANEL_LAUNCH(2); else PANEL_LAUNCH(3);
+#undef PANEL_LAUNCH
+            LAUNCH_CHECK(ctx, "nest_panel_small_kernel");
+        }
+        if (nt) {
+            if (!has_slots) return fail(ctx, ABZ_E_UNSUPPORTED, "device-side innermost integrals need ndim >= 2");
+            rc = launch_leaf(dD + o_ta, dD + o_tb, dD + o_tt, dL + o_ts, (long)nt, dout + 4 * ns, st, ln.spill);
+            if (rc) return rc;
+        }
+        CU(ctx, cudaMemcpyAsync(dout + 4 * ns + 4 * nt, ef, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        CU(ctx, cudaMemcpyAsync(ln.pin_out, dout, owords * 8, cudaMemcpyDeviceToHost, st));
+        ln.ns = ns; ln.nt = nt;
+        return ABZ_OK;
+    }
+
+    int collect(IaiLane& ln, abz_iai::Round& R) {
+        CU(ctx, cudaStreamSynchronize(ln.stream));
+        return unpack((const double*)ln.pin_out, ln.ns, ln.nt, R);
+    }
+
+    int unpack(const double* ho, size_t ns, size_t nt, abz_iai::Round& R) {
+        int flag = 0;
+        memcpy(&flag, ho + 4 * ns + 4 * nt, sizeof(int));
+        if (flag) {
+            cudaMemsetAsync(ctx->errflag.as<int>(), 0, sizeof(int), ctx->stream);
+            if ((flag & 2) && !(flag & 1) && !ctx->force_generic) return ABZ_RETRY_PIVOTED;
+            if (flag & 4) { heap_overflow = true; return fail(ctx, ABZ_E_UNSUPPORTED, "abz_iai_solve: an innermost integral outgrew the device segment heap"); }
+            return fail(ctx, ABZ_E_SINGULAR, "abz_iai_solve: singular matrix or NaN/Inf in the integrand");
+        }
+        R.seg_I.resize(ns); R.seg_D.resize(ns);
+        for (size_t i = 0; i < ns; i++) {
+            R.seg_I[i] = abz_iai::cplx{ho[4 * i], ho[4 * i + 1]};
+            R.seg_D[i] = abz_iai::cplx{ho[4 * i + 2], ho[4 * i + 3]};
+        }
+        R.task_I.resize(nt); R.task_E.resize(nt); R.task_ne.resize(nt);
+        const double* ht = ho + 4 * ns;
+        for (size_t i = 0; i < nt; i++) {
+            R.task_I[i] = abz_iai::cplx{ht[4 * i], ht[4 * i + 1]};
+            R.task_E[i] = ht[4 * i + 2];
+            int64_t ne; memcpy(&ne, ht + 4 * i + 3, 8);
+            R.task_ne[i] = ne;
+        }
+        return ABZ_OK;
+    }
+
     int run_round(abz_iai::Round& R) {
         int rc = run_once(R);
         if (rc == ABZ_RETRY_PIVOTED) {       // the unpivoted fast resolvent saw a tiny pivot: redo the round pivoted
@@ -1857,43 +2002,22 @@ struct IaiDeviceBackend {
         }
         if (nt) {
             if (n > 3 || !has_slots) return fail(ctx, ABZ_E_UNSUPPORTED, "device-side innermost integrals need norb <= 3 and ndim >= 2");
-            rc = launch_leaf(R, dD + o_ta, dD + o_tb, dD + o_tt, dL + o_ts, (long)nt, dout + 4 * ns);
+            rc = launch_leaf(dD + o_ta, dD + o_tb, dD + o_tt, dL + o_ts, (long)nt, dout + 4 * ns, ctx->stream, ctx->tmp_d);
             if (rc) return rc;
         }
         CU(ctx, cudaMemcpyAsync(dout + 4 * ns + 4 * nt, ef, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
         CU(ctx, cudaMemcpyAsync(ctx->pin_out, dout, owords * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
-        const double* ho = (const double*)ctx->pin_out;
-        int flag = 0;
-        memcpy(&flag, ho + 4 * ns + 4 * nt, sizeof(int));
-        if (flag) {
-            cudaMemsetAsync(ef, 0, sizeof(int), ctx->stream);
-            if ((flag & 2) && !(flag & 1) && !ctx->force_generic) return ABZ_RETRY_PIVOTED;
-            if (flag & 4) { heap_overflow = true; return fail(ctx, ABZ_E_UNSUPPORTED, "abz_iai_solve: an innermost integral outgrew the device segment heap"); }
-            return fail(ctx, ABZ_E_SINGULAR, "abz_iai_solve: singular matrix or NaN/Inf in the integrand");
-        }
-        R.seg_I.resize(ns); R.seg_D.resize(ns);
-        for (size_t i = 0; i < ns; i++) {
-            R.seg_I[i] = abz_iai::cplx{ho[4 * i], ho[4 * i + 1]};
-            R.seg_D[i] = abz_iai::cplx{ho[4 * i + 2], ho[4 * i + 3]};
-        }
-        R.task_I.resize(nt); R.task_E.resize(nt); R.task_ne.resize(nt);
-        const double* ht = ho + 4 * ns;
-        for (size_t i = 0; i < nt; i++) {
-            R.task_I[i] = abz_iai::cplx{ht[4 * i], ht[4 * i + 1]};
-            R.task_E[i] = ht[4 * i + 2];
-            int64_t ne; memcpy(&ne, ht + 4 * i + 3, 8);
-            R.task_ne[i] = ne;
-        }
-        return ABZ_OK;
+        return unpack((const double*)ctx->pin_out, ns, nt, R);
     }
 
-    int launch_leaf(abz_iai::Round&, const double* ta, const double* tb, const double* tt, const long* ts, long nt, double* out) {
+    int launch_leaf(const double* ta, const double* tb, const double* tt, const long* ts, long nt, double* out, cudaStream_t st,
+                    DevBuf& spillbuf) {
         Series* s = nst->s;
         const long stride = (long)s->n * s->n * s->M[0];
         // global spill area for segment heaps deeper than the shared-memory levels
         const int spill_cap = ctx->leaf_spill;
-        CU(ctx, ctx->tmp_d.reserve((size_t)nt * std::max(spill_cap, 1) * sizeof(LeafSeg) + 64));
+        CU(ctx, spillbuf.reserve((size_t)nt * std::max(spill_cap, 1) * sizeof(LeafSeg) + 64));
         unsigned g = (unsigned)((nt + LEAF_WARPS - 1) / LEAF_WARPS);
         static bool attr_leaf = false;
         if (!attr_leaf) {
@@ -1904,9 +2028,9 @@ struct IaiDeviceBackend {
         }
         if ((size_t)LEAF_WARPS * s->M[0] * s->n * s->n * sizeof(double2) > 160 * 1024)
             return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension for the IAI leaf kernel");
-        LeafSeg* spill = reinterpret_cast<LeafSeg*>(ctx->tmp_d.as<char>() + 64);
+        LeafSeg* spill = reinterpret_cast<LeafSeg*>(spillbuf.as<char>() + 64);
 #define LEAF_LAUNCH(NORB)                                                                                              \
-    iai_leaf_kernel<NORB><<<g, LEAF_WARPS * 32, (size_t)LEAF_WARPS * s->M[0] * NORB * NORB * sizeof(double2), ctx->stream>>>(nst->L1, stride, ta, tb, tt, ts, nt, s->M[0], s->lo[0], s->period[0], \
+    iai_leaf_kernel<NORB><<<g, LEAF_WARPS * 32, (size_t)LEAF_WARPS * s->M[0] * NORB * NORB * sizeof(double2), st>>>(nst->L1, stride, ta, tb, tt, ts, nt, s->M[0], s->lo[0], s->period[0], \
                                                                  fkind, vkind, z, dsig, la, lb, rtol, (long long)maxevals, spill, spill_cap, out, \
                                                                  ctx->errflag.as<int>())
         if (s->n == 1) LEAF_LAUNCH(1); else if (s->n == 2) LEAF_LAUNCH(2); else LEAF_LAUNCH(3);
@@ -1957,9 +2081,21 @@ int32_t abz_iai_solve_sharded(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
     be.xfn = exchange; be.xuser = exchange_user;
     const bool leaf = (flags & ABZ_IAI_DEVICE_LEAVES) && s->n <= 3 && nst->ndim >= 2;
     const long launches0 = ctx->launches;
+    {   // rounds in flight: the fused small-orbital kernels can overlap (a round uses a small part of the chip and is
+        // bound by the dependent chain of its deepest innermost integral); ABZ_IAI_LANES overrides
+        static const int env_lanes = getenv("ABZ_IAI_LANES") ? atoi(getenv("ABZ_IAI_LANES")) : 0;
+        const int want = env_lanes > 0 ? std::min(env_lanes, 16) : ctx->iai_lanes_opt;
+        rc = be.init_lanes((s->n <= 3 && nst->ndim >= 2 && nranks == 1) ? want : 1);   // sharded solves keep one round at a time
+        if (rc) return rc;
+    }
     abz_iai::Engine<IaiDeviceBackend> eng(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, leaf, rank, nranks);
     rc = eng.run();
     ctx->force_generic = false;
+    if (rc && be.nlanes > 1) {
+        // the engine has drained its lanes; kernels of the other lanes may have raised the flag again after it was read
+        cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
     if (rc == ABZ_E_UNSUPPORTED && leaf && be.heap_overflow && nranks == 1) {
         // an innermost integral outgrew the device segment heap (1087 segments): same solve with host-driven innermost panels,
         // whose heaps live in host memory (single rank only: ranks must not diverge in their exchange sequence)
@@ -1967,6 +2103,7 @@ int32_t abz_iai_solve_sharded(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
         abz_iai::Engine<IaiDeviceBackend> eng2(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, false, rank, nranks);
         rc = eng2.run();
         ctx->force_generic = false;
+        if (rc && be.nlanes > 1) { cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->stream); cudaStreamSynchronize(ctx->stream); }
         if (stats) { stats[0] = eng2.numevals; stats[1] = eng.rounds + eng2.rounds; stats[2] = ctx->launches - launches0; stats[3] = 0; }
         if (rc == abz_iai::IAI_E_NAN) return fail(ctx, ABZ_E_SINGULAR, eng2.error);
         if (rc == abz_iai::IAI_E_ARENA) return fail(ctx, ABZ_E_OOM, eng2.error);

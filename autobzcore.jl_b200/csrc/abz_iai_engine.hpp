@@ -208,8 +208,14 @@ struct Round {
 
 enum { IAI_OK = 0, IAI_E_NAN = -4, IAI_E_ARENA = -2, IAI_E_STALL = -7 };
 
-// Backend concept:  int run_round(Round&)  fills the outputs for the queued inputs, returns 0 or an error code;
+// Backend concept:  int lanes()                     number of rounds that may be in flight at once (>= 1);
+//                   int submit(int lane, Round&)    starts the queued inputs of one round (may return before the work is done);
+//                   int wait(int lane, Round&)      completes it and fills the outputs; both return 0 or an error code;
 //                   int exchange(double* buf, size_t n)  in-place sum over ranks (only called when nranks > 1).
+// Lanes: the children of the outermost integral's panels are dealt to the lanes round-robin and everything below a child
+// stays in its lane, so every lane is a sequence of rounds of its own (on the device: its own stream), and the lanes overlap.
+// Every 1-D integral still sees exactly its own evaluations in its own order: results and numevals do not depend on the
+// number of lanes.
 template <class Backend>
 class Engine {
 public:
@@ -219,6 +225,9 @@ public:
           leaf_tasks_(leaf_tasks && ndim >= 2), rank_(rank), nranks_(ndim >= 2 ? nranks : 1) {
         for (int64_t i = cap2 - 1; i >= 0; i--) free2_.push_back(i);
         for (int64_t i = cap1 - 1; i >= 0; i--) free1_.push_back(i);
+        L_ = be.lanes() < 1 ? 1 : be.lanes();
+        q_seg_.resize(L_); q_task_.resize(L_); fl_seg_.resize(L_); fl_task_.resize(L_);
+        cur_.resize(L_); next_.resize(L_); inflight_.assign(L_, 0);
     }
 
     int64_t numevals = 0, rounds = 0, exchanges = 0;   // numevals: all ranks' evaluations once the solve has finished
@@ -229,39 +238,55 @@ public:
     int run() {
         double a, b;
         lims_.segments(&a, &b);
-        int root = new_integral(ndim_ - 1, lims_, atol_, -1, -1, -1, -1);
+        int root = new_integral(ndim_ - 1, lims_, atol_, -1, -1, -1, -1, 0);
         int rc = start_segment(root, a, b, 0);
         if (rc) return rc;
         int local_rc = IAI_OK;
         while (!done_) {
-            if ((q_seg_.empty() && q_task_.empty()) || local_rc) {
+            // start a round in every idle lane that has work queued
+            for (int g = 0; g < L_ && !local_rc; g++) {
+                if (inflight_[g] || (q_seg_[g].empty() && q_task_[g].empty())) continue;
+                rounds++;
+                cur_[g].clear_inputs();
+                std::swap(cur_[g], next_[g]);           // cur_ = inputs queued so far, next_ = empty
+                fl_seg_[g].clear(); fl_task_[g].clear();
+                fl_seg_[g].swap(q_seg_[g]); fl_task_[g].swap(q_task_[g]);
+                rc = be_.submit(g, cur_[g]);
+                if (rc) { local_rc = rc; break; }
+                inflight_[g] = 1;
+                fifo_.push_back(g);
+            }
+            if (local_rc || fifo_.empty()) {
+                drain();
                 // local work exhausted: single rank = stalled; several ranks = meet the others (one allreduce)
                 if (nranks_ == 1) { if (local_rc) return local_rc; error = "IAI engine stalled"; return IAI_E_STALL; }
                 rc = exchange_step(local_rc);
                 if (rc) return rc;
                 continue;
             }
-            rounds++;
-            cur_.clear_inputs();
-            std::swap(cur_, next_);           // cur_ = inputs queued so far, next_ = empty
-            std::vector<Item> segs, tasks;
-            segs.swap(q_seg_); tasks.swap(q_task_);
-            rc = be_.run_round(cur_);
-            if (rc) { if (nranks_ == 1) return rc; local_rc = rc; continue; }
+            const int g = fifo_.front();
+            fifo_.pop_front();
+            rc = be_.wait(g, cur_[g]);
+            inflight_[g] = 0;
+            if (rc) { local_rc = rc; continue; }
+            const std::vector<Item>& segs = fl_seg_[g];
+            const std::vector<Item>& tasks = fl_task_[g];
+            const Round& R = cur_[g];
             numevals += 15 * (int64_t)segs.size();
             for (size_t i = 0; i < segs.size() && !rc; i++) {
-                cplx D = cur_.seg_D[i];
+                cplx D = R.seg_D[i];
                 double E = std::hypot(D.re, D.im);
-                rc = segment_done(segs[i].q, segs[i].pend, cur_.seg_I[i], E);
+                rc = segment_done(segs[i].q, segs[i].pend, R.seg_I[i], E);
             }
             for (size_t i = 0; i < tasks.size() && !rc; i++) {
-                numevals += cur_.task_ne[i];
-                double E = cur_.task_E[i];
+                numevals += R.task_ne[i];
+                double E = R.task_E[i];
                 if (!std::isfinite(E)) rc = nan_error(pends_[tasks[i].pend]);
-                else rc = child_done(tasks[i].q, tasks[i].pend, tasks[i].i, tasks[i].slot, cur_.task_I[i]);
+                else rc = child_done(tasks[i].q, tasks[i].pend, tasks[i].i, tasks[i].slot, R.task_I[i]);
             }
-            if (rc) { if (nranks_ == 1) return rc; local_rc = rc; }
+            if (rc) local_rc = rc;
         }
+        drain();
         if (nranks_ > 1) {   // total evaluation count over the ranks (EvalCounter semantics of the whole solve)
             double ne = (double)numevals;
             rc = be_.exchange(&ne, 1);
@@ -275,6 +300,7 @@ private:
     struct Pend { double a, b; cplx vals[15]; int remaining, tag; bool shared; };
     struct Integral {
         int level; Limits lims; double atol; int64_t slot; int pq, ppend, pi;   // parent integral / panel / node
+        int lane;                                                              // the lane its rounds run in
         std::vector<Seg> heap; cplx I; double E; int64_t numevals; Seg popped, s1, s2; bool has1, has2;
     };
     struct Item { int q, pend, i; int64_t slot; };
@@ -286,16 +312,24 @@ private:
     std::deque<Integral> ints_; std::vector<int> free_int_;
     std::deque<Pend> pends_; std::vector<int> free_pend_;
     std::vector<int64_t> free2_, free1_;
-    std::vector<Item> q_seg_, q_task_;
-    Round cur_, next_;
+    int L_ = 1; int64_t lane_counter_ = 0;
+    std::vector<std::vector<Item>> q_seg_, q_task_, fl_seg_, fl_task_;   // per lane: queued / in flight
+    std::vector<Round> cur_, next_;
+    std::vector<char> inflight_;
+    std::deque<int> fifo_;                                               // lanes in flight, oldest first
     bool done_ = false;
 
-    int new_integral(int level, const Limits& lims, double atol, int64_t slot, int pq, int ppend, int pi) {
+    // complete (and discard) whatever is still in flight: the backend's buffers must be quiescent before we return
+    void drain() {
+        while (!fifo_.empty()) { const int g = fifo_.front(); fifo_.pop_front(); be_.wait(g, cur_[g]); inflight_[g] = 0; }
+    }
+
+    int new_integral(int level, const Limits& lims, double atol, int64_t slot, int pq, int ppend, int pi, int lane) {
         int id;
         if (!free_int_.empty()) { id = free_int_.back(); free_int_.pop_back(); }
         else { id = (int)ints_.size(); ints_.emplace_back(); }
         Integral& q = ints_[id];
-        q.level = level; q.lims = lims; q.atol = atol; q.slot = slot; q.pq = pq; q.ppend = ppend; q.pi = pi;
+        q.level = level; q.lims = lims; q.atol = atol; q.slot = slot; q.pq = pq; q.ppend = ppend; q.pi = pi; q.lane = lane;
         q.heap.clear(); q.I = cplx{0, 0}; q.E = 0; q.numevals = 0; q.has1 = q.has2 = false;
         return id;
     }
@@ -325,8 +359,9 @@ private:
         int pend = new_pend(a, b, tag);
         const int level = ints_[qi].level;
         if (level == 0) {
-            q_seg_.push_back(Item{qi, pend, 0, 0});
-            next_.seg_a.push_back(a); next_.seg_b.push_back(b); next_.seg_slot.push_back(ints_[qi].slot);
+            const int g = ints_[qi].lane;
+            q_seg_[g].push_back(Item{qi, pend, 0, 0});
+            next_[g].seg_a.push_back(a); next_[g].seg_b.push_back(b); next_[g].seg_slot.push_back(ints_[qi].slot);
             return IAI_OK;
         }
         const bool shared = (nranks_ > 1 && level == ndim_ - 1);
@@ -341,16 +376,19 @@ private:
             int64_t slot;
             int rc = alloc_slot(level, &slot);
             if (rc) return rc;
-            if (level == 2) { next_.c3_x.push_back(x); next_.c3_slot.push_back(slot); }
-            else { next_.c2_x.push_back(x); next_.c2_parent.push_back(ints_[qi].slot); next_.c2_slot.push_back(slot); }
+            // children of the outermost integral are dealt to the lanes; below that a child stays in its parent's lane
+            const int g = (level == ndim_ - 1) ? (int)(lane_counter_++ % L_) : ints_[qi].lane;
+            Round& nx = next_[g];
+            if (level == 2) { nx.c3_x.push_back(x); nx.c3_slot.push_back(slot); }
+            else { nx.c2_x.push_back(x); nx.c2_parent.push_back(ints_[qi].slot); nx.c2_slot.push_back(slot); }
             const double catol = ints_[qi].atol / len;        // inner abstol = abstol/len (src/fourier.jl:479-480)
             if (level == 1 && leaf_tasks_) {
-                q_task_.push_back(Item{qi, pend, i, slot});
-                next_.task_a.push_back(ca); next_.task_b.push_back(cb); next_.task_atol.push_back(catol);
-                next_.task_slot.push_back(slot);
+                q_task_[g].push_back(Item{qi, pend, i, slot});
+                nx.task_a.push_back(ca); nx.task_b.push_back(cb); nx.task_atol.push_back(catol);
+                nx.task_slot.push_back(slot);
                 continue;
             }
-            int child = new_integral(level - 1, clims, catol, slot, qi, pend, i);
+            int child = new_integral(level - 1, clims, catol, slot, qi, pend, i, g);
             rc = start_segment(child, ca, cb, 0);
             if (rc) return rc;
         }

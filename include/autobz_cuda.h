@@ -61,6 +61,8 @@ typedef uint64_t abz_nest_t;    /* IAI arena: contracted series for nested panel
 #define ABZ_OPT_IAI_LEAF_SPILL 5   /* segments per device-side innermost integral beyond the 63 held in shared memory (default 1024);
                                     * an integral that outgrows them is redone with host-driven panels (single rank); a negative value -c
                                     * (1 <= c <= 63) limits the TOTAL capacity to c segments - a test hook for that fallback */
+#define ABZ_OPT_IAI_LANES 6        /* IAI rounds in flight in single-rank solves with norb <= 3 (default 4; 1 = one round at a time);
+                                    * results and numevals do not depend on it */
 #define ABZ_OPT_EIG_ALGO 4         /* 0 (default): Householder tridiagonalisation (warp-per-matrix in registers for norb <= 32,
                                     * CTA-per-matrix in shared memory above) + implicit QL; 1: cyclic two-sided Jacobi;
                                     * 2: as 0 but always the shared-memory tridiagonalisation (cross-check) */

@@ -3,6 +3,7 @@
 // slot management, leaf-task plumbing, numevals accounting - is checked on a box without a GPU against the
 // oracle's sequential recursion (orc_iai).  Never linked into libautobz_cuda.so.
 #include <complex.h>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -39,6 +40,13 @@ struct CpuBackend {
         gk_combine(a, b, f, I, D);
     }
     static double cabs_(cplx v) { return std::hypot(v.re, v.im); }
+
+    // lanes: IAI_CPU_LANES rounds in flight; the work of a round is done in wait(), so an engine that read a round's outputs
+    // before waiting for it would see stale data
+    int nlanes = 1;
+    int lanes() const { return nlanes; }
+    int submit(int, Round&) { return 0; }
+    int wait(int, Round& R) { return run_round(R); }
 
     int run_round(Round& R) {
         const long nn = (long)n * n;
@@ -104,6 +112,7 @@ extern "C" int iai_cpu_solve(const double* coeffs, int n, int ndim, const int* M
     be.fkind = fkind; be.vkind = vkind; be.z[0] = z ? z[0] : 0; be.z[1] = z ? z[1] : 0; be.sigma = sigma;
     be.la = cplx{lin ? lin[0] : 1.0, lin ? lin[1] : 0.0}; be.lb = cplx{lin ? lin[2] : 0.0, lin ? lin[3] : 0.0};
     be.rtol = rtol; be.maxevals = maxevals; be.xfn = xfn;
+    if (const char* e = getenv("IAI_CPU_LANES")) be.nlanes = atoi(e) > 0 ? atoi(e) : 1;
     Limits lims; lims.kind = lkind; lims.nd = ndim; lims.s = 1.0;
     for (int d = 0; d < ndim; d++) { lims.a[d] = la[d]; lims.b[d] = lb ? lb[d] : 0.0; }
     Engine<CpuBackend> eng(be, ndim, lims, atol, rtol, maxevals, cap2, cap1, leaf_tasks != 0, rank, nranks);

@@ -600,6 +600,26 @@ def test_iai_device_vs_oracle_on_random_problems(ctx, orc, seed):
         assert abs(I - Io) <= 1e-10 * max(abs(Io), 1e-12)
 
 
+@pytest.mark.parametrize("leaves", [True, False])
+def test_iai_rounds_in_flight_do_not_change_results(ctx, svo, leaves):
+    """ABZ_OPT_IAI_LANES: 1, 2, 4 and 7 rounds in flight (one stream each) give bit-identical integrals, error estimates and
+    numevals (every 1-D integral sees its own evaluations in its own order); more lanes mean more, smaller rounds"""
+    H, lo, A = svo
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
+    nest = L.DeviceNest(ctx, fs.device(ctx), 3, 64, 4096)
+    res = []
+    try:
+        for lanes in (1, 2, 4, 7):
+            ctx.set_option(L.OPT_IAI_LANES, lanes)
+            I, E, ne, rounds, launches = nest.iai_solve(1, [0.5] * 3, None, L.F_RESOLVENT_TRACE, 1, complex(12.5, 0.02), None, None, 1e-3, 0.0,
+                                                        2 ** 62, device_leaves=leaves)
+            res.append((I, E, ne, rounds))
+    finally:
+        ctx.set_option(L.OPT_IAI_LANES, 4)
+    assert all(r[:3] == res[0][:3] for r in res)
+    assert res[2][3] > res[0][3]
+
+
 def test_iai_leaf_heap_overflow_falls_back_to_host_panels(ctx, orc, svo):
     """an innermost integral that outgrows the device segment heap (shrunk here to 2 segments in total) is redone with
     host-driven panels: same numevals and value as the oracle, no error"""

@@ -187,3 +187,24 @@ def test_engine_matches_recursion_on_random_problems(orc, eng):
         assert abs(I - Io) <= 1e-12 * max(abs(Io), 1e-12) and abs(E - Eo) <= 1e-9 * max(Eo, 1e-300)
 
     check()
+
+
+@pytest.mark.parametrize("leaf", [False, True])
+def test_engine_lanes_do_not_change_results(orc, eng, svo, leaf, monkeypatch):
+    """several rounds in flight (the children of the outermost panels dealt to lanes, each lane its own sequence of rounds):
+    bit-identical integral, error estimate and numevals for 1, 3 and 5 lanes, cubic and tetrahedral limits, and fewer
+    engine iterations are NOT required - only that every 1-D integral sees its own evaluations in its own order"""
+    H, lo, A = svo
+    S = orc.Series(H, lo)
+    z = complex(12.5, 0.05)
+    for args, atol in (((0, [0.0] * 3, [1.0] * 3), 3e-2), ((1, [0.5] * 3, None), 1e-3), ((0, [0.0] * 2, [1.0] * 2), 1e-3)):
+        ndim = len(args[1])
+        Sd = S if ndim == 3 else orc.Series(np.ascontiguousarray(H[:, :, :, :, H.shape[4] // 2:H.shape[4] // 2 + 1]), (lo[0], lo[1], 0))
+        res = []
+        for lanes in (1, 3, 5):
+            monkeypatch.setenv("IAI_CPU_LANES", str(lanes))
+            rc, I, E, ne, rounds = _solve(eng, Sd, ndim, args[0], args[1], args[2], 0, 1, z, None, atol, 0.0, leaf)
+            assert rc == 0
+            res.append((I, E, ne))
+        assert res[0] == res[1] == res[2]
+    monkeypatch.delenv("IAI_CPU_LANES", raising=False)
