@@ -146,18 +146,19 @@ sys.exit(0 if ok else 1)
 '''
 
 
-@pytest.mark.parametrize("nranks", [2, 3])
-def test_engine_sharded_over_ranks_gloo(tmp_path, orc, eng, nranks):
+@pytest.mark.parametrize("nranks,lanes", [(2, 1), (3, 1), (2, 3)])
+def test_engine_sharded_over_ranks_gloo(tmp_path, orc, eng, nranks, lanes):
     """world_size 2 and 3 over gloo: the outermost panels' nodes are dealt round-robin to the ranks, one small allreduce per
     outer refinement step; integral, error estimate and total evaluation count are bit-identical to the single-rank solve,
-    and an integrand error on one rank stops every rank."""
+    and an integrand error on one rank stops every rank.  (2, 3): the same with three rounds in flight per rank."""
     import socket
     import subprocess
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "gloo_iai.py"
     script.write_text(_GLOO_IAI.format(root=root, port=port, nranks=nranks))
-    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(nranks)]
+    env = dict(os.environ, IAI_CPU_LANES=str(lanes))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env) for r in range(nranks)]
     outs = [p.communicate(timeout=600)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
