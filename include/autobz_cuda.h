@@ -64,7 +64,7 @@ typedef uint64_t abz_nest_t;    /* IAI arena: contracted series for nested panel
 #define ABZ_OPT_IAI_LANES 6        /* IAI rounds in flight in single-rank solves with norb <= 3 (default 4; 1 = one round at a time);
                                     * results and numevals do not depend on it */
 #define ABZ_OPT_EIG_ALGO 4         /* 0 (default): Householder tridiagonalisation (warp-per-matrix in registers for norb <= 32,
-                                    * CTA-per-matrix in shared memory above) + implicit QL; 1: cyclic two-sided Jacobi;
+                                    * CTA-per-matrix in registers for 33..64) + implicit QL; 1: cyclic two-sided Jacobi;
                                     * 2: as 0 but always the shared-memory tridiagonalisation (cross-check) */
 
 int32_t abz_version(void);
