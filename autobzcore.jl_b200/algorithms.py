@@ -80,6 +80,36 @@ class AutoPTR(AutoBZAlgorithm):
         self.keepmost, self.nthreads = int(keepmost), nthreads
 
 
+class AbsoluteEstimate(IntegralAlgorithm):
+    """AbsoluteEstimate(est_alg, abs_alg; norm, kws...) (src/algorithms.jl:614-653): a rough estimate I from `est_alg` (solved with
+    `kws`: reltol / abstol / maxiters) turns the caller's relative tolerance into an absolute one for `abs_alg`:
+    abstol = max(abstol, reltol * norm(I)), reltol = 0."""
+
+    def __init__(self, est_alg, abs_alg, norm=abs, **kws):
+        for k in kws:
+            if k not in ("abstol", "reltol", "maxiters"):
+                raise ValueError(f"keyword {k} unrecognized")
+        self.est_alg, self.abs_alg, self.norm, self.kws = est_alg, abs_alg, norm, kws
+
+
+def PTR_IAI(ptr=None, iai=None, **kws):
+    """PTR_IAI(; ptr=PTR(), iai=IAI()) (src/brillouin.jl:466-476): IAI with abstol = reltol * norm(PTR estimate)"""
+    return AbsoluteEstimate(ptr if ptr is not None else PTR(), iai if iai is not None else IAI(), **kws)
+
+
+def AutoPTR_IAI(reltol=1.0, ptr=None, iai=None, **kws):
+    """AutoPTR_IAI(; reltol=1.0, ptr=AutoPTR(), iai=IAI()) (src/brillouin.jl:479-490): the estimate comes from AutoPTR at `reltol`"""
+    return AbsoluteEstimate(ptr if ptr is not None else AutoPTR(), iai if iai is not None else IAI(), reltol=reltol, **kws)
+
+
+class TAI(AutoBZAlgorithm):
+    """TAI(; norm, initdiv=1) (src/brillouin.jl:446-463): tree-adaptive integration through HCubature.  Named for completeness of the
+    reference's algorithm list; it is not on the Fourier hot path and `init` refuses it."""
+
+    def __init__(self, norm=abs, initdiv=1):
+        self.norm, self.initdiv = norm, int(initdiv)
+
+
 class EvalCounter(IntegralAlgorithm):
     """EvalCounter(alg) (src/algorithms.jl:662-666): sol.numevals = number of integrand evaluations."""
 

@@ -101,6 +101,14 @@ class FBZ:
         self.ndim = ndim
 
 
+class IBZ:
+    """IBZ(n) (src/brillouin.jl:205-247): the polyhedral irreducible BZ.  In the reference it needs the SymmetryReduceBZ.jl
+    extension and errors without it; that extension is out of scope here, so `load_bz(IBZ(), ...)` raises."""
+
+    def __init__(self, ndim=None):
+        self.ndim = ndim
+
+
 class InversionSymIBZ:
     def __init__(self, ndim=None):
         self.ndim = ndim
@@ -109,6 +117,50 @@ class InversionSymIBZ:
 class CubicSymIBZ:
     def __init__(self, ndim=None):
         self.ndim = ndim
+
+
+# ---- symmetry representations (src/brillouin.jl:44-114)
+class AbstractSymRep:
+    pass
+
+
+class UnknownRep(AbstractSymRep):
+    """fallback for values without a user-defined representation: the IBZ value is returned as is"""
+
+
+class TrivialRep(AbstractSymRep):
+    """values that do not transform under the group (numbers): IBZ value x nsyms"""
+
+
+class FunctionRep(AbstractSymRep):
+    """a user-supplied map (bz, x) -> x on the full BZ, e.g. sum_S S x S^H (the reference's user-defined SymRep + symmetrize_)"""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+
+def SymRep(f):
+    """SymRep(f) (src/brillouin.jl:72-85): the representation of the integral of `f`.  Scalar-valued integrands are handled by
+    `symmetrize` itself (TrivialRep); a matrix-valued integrand carries a FunctionRep if it was given `symmetrize=`."""
+    if isinstance(f, AbstractSymRep):
+        return f
+    inner = getattr(f, "f", f)
+    fn = getattr(inner, "symmetrize", None)
+    return FunctionRep(fn) if callable(fn) else UnknownRep()
+
+
+def symmetrize(f, bz, x):
+    """symmetrize(f, bz, x) (src/brillouin.jl:87-107): map a value computed on the symmetry-reduced domain to the full BZ"""
+    if bz.syms is None:
+        return x
+    if np.ndim(x) == 0:
+        return bz.nsyms * x                       # TrivialRepType = Union{Number, 0-dim array}
+    rep = SymRep(f)
+    if isinstance(rep, TrivialRep):
+        return bz.nsyms * x
+    if isinstance(rep, FunctionRep):
+        return rep.fn(bz, x)
+    return x
 
 
 def sign_flip_matrices(d):
@@ -161,4 +213,6 @@ def load_bz(bz, A=None, B=None, atol=None):
             import warnings
             warnings.warn("Non-orthogonal lattice vectors detected with CubicSymIBZ. Unexpected behavior may occur")
         return SymmetricBZ(A, B, TetrahedralLimits(np.full(d, 0.5)), cube_automorphisms(d))
-    raise TypeError("unsupported BZ type (the polyhedral IBZ of SymmetryReduceBZ.jl is out of scope)")
+    if isinstance(bz, IBZ):
+        raise NotImplementedError("SymmetryReduceBZ extension not loaded (the polyhedral IBZ is out of scope of this build)")   # src/brillouin.jl:234-241
+    raise TypeError("unsupported BZ type")

@@ -8,10 +8,12 @@ AutoPTR's additive grid refinement and convergence test (AutoSymPTR.autosymptr, 
 src/algorithms.jl:418-432), IAI's nested GK panels (iai.py)."""
 import time
 
+import math
+
 import numpy as np
 
 from . import _lib
-from .algorithms import (IAI, PTR, AutoPTR, AutoSymPTRJL, AuxQuadGKJL, EvalCounter, MonkhorstPack, NestedQuad,
+from .algorithms import (IAI, PTR, AbsoluteEstimate, AutoPTR, AutoSymPTRJL, AuxQuadGKJL, EvalCounter, MonkhorstPack, NestedQuad,
                          monkhorst_pack_schedule)
 from .backend import DeviceBackend
 from .bz import CubicLimits, SymmetricBZ, TetrahedralLimits
@@ -286,6 +288,14 @@ def init(prob, alg, backend=None, shard=None, **kwargs):
         raise TypeError("autobz_b200 implements the FourierIntegrand hot path only (SURVEY.md §8)")
     backend = backend if backend is not None else DeviceBackend()
     shard = shard if shard is not None else Shard()
+    inner, counter = _unwrap(alg)
+    if isinstance(inner, AbsoluteEstimate):
+        # init_cacheval(f, dom, p, ::AbsoluteEstimate) (src/algorithms.jl:640-643): one cache per algorithm
+        wrap = (lambda a: EvalCounter(a)) if counter else (lambda a: a)
+        cache = IntegralCache(prob.f, prob.dom, prob.p, alg, kwargs, backend, shard)
+        cache.cacheval["est"] = init(prob, wrap(inner.est_alg), backend=backend, shard=shard, **inner.kws)
+        cache.cacheval["abs"] = init(prob, wrap(inner.abs_alg), backend=backend, shard=shard)
+        return cache
     cache = IntegralCache(prob.f, prob.dom, prob.p, alg, kwargs, backend, shard)
     _init_cacheval(cache)
     return cache
@@ -360,8 +370,29 @@ def _init_cacheval(cache):
         raise TypeError(f"unsupported algorithm {type(salg).__name__} for FourierIntegrand")
 
 
+def _do_solve_absolute_estimate(cache, ps, alg, counter):
+    """do_solve(f, dom, p, ::AbsoluteEstimate, cacheval) (src/algorithms.jl:645-653)"""
+    est, ab_ = cache.cacheval["est"], cache.cacheval["abs"]
+    kws = dict(cache.kwargs)
+    abstol, reltol = kws.get("abstol"), kws.get("reltol")
+    norm = _norm if alg.norm is abs else alg.norm
+    sols = []
+    for p in ps:
+        s_est = _do_solve(est, [p])[0]
+        val = norm(s_est.u)
+        rtol = math.sqrt(np.finfo(np.float64).eps) if reltol is None else reltol
+        atol = max(0.0 if abstol is None else abstol, rtol * val)
+        ab_.kwargs = {"abstol": atol, "reltol": 0.0, **({"maxiters": kws["maxiters"]} if "maxiters" in kws else {})}
+        s_abs = _do_solve(ab_, [p])[0]
+        ne = (s_est.numevals + s_abs.numevals) if counter else -1      # EvalCounter counts the evaluations of both solves
+        sols.append(IntegralSolution(s_abs.u, s_abs.resid, s_abs.retcode, ne))
+    return sols
+
+
 def _do_solve(cache, ps):
     alg, counter = _unwrap(cache.alg)
+    if isinstance(alg, AbsoluteEstimate):
+        return _do_solve_absolute_estimate(cache, ps, alg, counter)
     dom, salg, j, ns, ndim = cache.cacheval["std"]
     kws = dict(cache.kwargs)
     abstol, reltol = kws.get("abstol"), kws.get("reltol")

@@ -331,3 +331,53 @@ def test_mixed_parameters_paramzip_paramproduct():
     solver2 = ab.IntegralSolver(f2, bz, ab.PTR(npt=6), backend=OracleBackend())
     assert np.allclose(solver2(as_[0]), solver(as_[0], b=bs[0]), rtol=1e-14)
     assert np.allclose(ab.batchsolve(solver2, [ab.MixedParameters(a) for a in as_]), [solver(a, b=bs[0]) for a in as_], rtol=1e-14)
+
+
+def test_absolute_estimate_ptr_iai():
+    """AbsoluteEstimate / PTR_IAI / AutoPTR_IAI (src/algorithms.jl:614-653, src/brillouin.jl:466-490): the estimate from the first
+    algorithm turns reltol into the abstol of the second; the result is the IAI solve with that abstol and reltol = 0, and
+    EvalCounter counts the evaluations of both solves"""
+    be = OracleBackend()
+    H, lo = ab.synthetic.wannier_hamiltonian(2, 1, cubic=True)
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=2)
+    ext = ab.synthetic.band_extent(H)
+    bz = ab.load_bz(ab.CubicSymIBZ(), np.eye(3))
+    f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=0.3 * ext)
+    p = {"omega": 0.1 * ext}
+    prob = ab.IntegralProblem(f, bz, p)
+    rtol = 1e-3
+    est = ab.solve(prob, ab.EvalCounter(ab.PTR(npt=6)), backend=be)
+    want = ab.solve(prob, ab.EvalCounter(ab.IAI()), abstol=rtol * abs(est.u), reltol=0.0, backend=be)
+    got = ab.solve(prob, ab.EvalCounter(ab.PTR_IAI(ptr=ab.PTR(npt=6))), reltol=rtol, backend=be)
+    assert got.u == want.u and got.numevals == est.numevals + want.numevals
+    # an explicit abstol larger than reltol * |estimate| wins (abstol = max(abstol, reltol * norm(I)))
+    big = 10 * rtol * abs(est.u)
+    got2 = ab.solve(prob, ab.PTR_IAI(ptr=ab.PTR(npt=6)), reltol=rtol, abstol=big, backend=be)
+    want2 = ab.solve(prob, ab.IAI(), abstol=big, reltol=0.0, backend=be)
+    assert got2.u == want2.u
+    # AutoPTR_IAI: the estimate is an AutoPTR solve at its own (loose) reltol
+    est3 = ab.solve(prob, ab.AutoPTR(nmin=6, a=0.3), reltol=1.0, backend=be)
+    got3 = ab.solve(prob, ab.AutoPTR_IAI(ptr=ab.AutoPTR(nmin=6, a=0.3)), reltol=rtol, backend=be)
+    want3 = ab.solve(prob, ab.IAI(), abstol=rtol * abs(est3.u), reltol=0.0, backend=be)
+    assert got3.u == want3.u
+    # through IntegralSolver / batchsolve as well
+    solver = ab.IntegralSolver(f, bz, ab.PTR_IAI(ptr=ab.PTR(npt=6)), reltol=rtol, backend=be)
+    assert solver(omega=0.1 * ext) == want.u
+    with pytest.raises(ValueError):
+        ab.AbsoluteEstimate(ab.PTR(), ab.IAI(), tolerance=1.0)
+    with pytest.raises(TypeError):
+        ab.solve(prob, ab.TAI(), backend=be)
+
+
+def test_symrep_names():
+    """src/brillouin.jl:44-114: TrivialRep multiplies by nsyms, UnknownRep returns the IBZ value, the full BZ is the identity;
+    load_bz(IBZ()) needs an extension that is out of scope"""
+    ibz, fbz = ab.load_bz(ab.CubicSymIBZ(), np.eye(3)), ab.load_bz(ab.FBZ(), np.eye(3))
+    assert ab.symmetrize(None, ibz, 2.0) == 96.0 and ab.symmetrize(None, fbz, 2.0) == 2.0
+    x = np.ones((2, 2))
+    assert ab.symmetrize(object(), ibz, x) is x and isinstance(ab.SymRep(object()), ab.UnknownRep)
+    assert np.all(ab.symmetrize(ab.TrivialRep(), ibz, x) == 48 * x)
+    g = ab.FourierIntegrand(ab.GlocIntegrand(symmetrize=lambda bz, v: 2 * v), lattice_series(3), eta=0.1)
+    assert isinstance(ab.SymRep(g), ab.FunctionRep) and np.all(ab.symmetrize(g, ibz, x) == 2 * x)
+    with pytest.raises(NotImplementedError):
+        ab.load_bz(ab.IBZ(), np.eye(3))
