@@ -440,7 +440,9 @@ small_values_kernel(const double2* __restrict__ Hmat, long nnodes, int fkind, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3-generic: tr[(z - H(k) - Sigma_w)^-1] by in-place Gauss-Jordan inversion with partial
+// K3-generic, shared-memory formulation (used for norb <= 16 / 20, where the register-resident teams of
+// abz_resolvent_gjreg.cuh would be mostly padding, and as ABZ_OPT_RESOLVENT_ALGO = 4 for cross-checks):
+// tr[(z - H(k) - Sigma_w)^-1] by in-place Gauss-Jordan inversion with partial
 // pivoting (LAPACK getrf/getri-equivalent robustness, as Julia's `inv(::Matrix)`), one warp per
 // (k, w) matrix held in shared memory, any norb <= 64.  The CTA stages H(k) once and its warps
 // sweep the frequencies, so H(k) is read from HBM once for all nw (the reference's batchsolve
