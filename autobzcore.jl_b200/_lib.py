@@ -23,7 +23,7 @@ EXPORTS = [
     "abz_version", "abz_last_error", "abz_ctx_create", "abz_ctx_destroy", "abz_ctx_set_option", "abz_ctx_launch_count",
     "abz_ctx_last_timings", "abz_series_create", "abz_series_destroy", "abz_rule_create_full", "abz_rule_create_sym", "abz_rule_create_nodes",
     "abz_symptr_rule", "abz_rule_create_symptr", "abz_rule_destroy", "abz_rule_info", "abz_rule_materialize", "abz_rule_copy_out",
-    "abz_rule_resolvent_sum", "abz_rule_resolvent_matrix_sum", "abz_rule_eig_sum", "abz_rule_eigvals", "abz_rule_ggr_data", "abz_rule_ggr_sum", "abz_points_eval", "abz_points_resolvent",
+    "abz_rule_resolvent_sum", "abz_rule_resolvent_matrix_sum", "abz_rule_eig_sum", "abz_rule_eig_sum_batch", "abz_rule_eigvals", "abz_rule_ggr_data", "abz_rule_ggr_sum", "abz_points_eval", "abz_points_resolvent",
     "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval", "abz_nest_eval_h", "abz_iai_solve", "abz_iai_solve_sharded",
     "abz_comm_unique_id", "abz_comm_init", "abz_allreduce_sum", "abz_comm_destroy",
 ]
@@ -79,6 +79,7 @@ def load():
     lib.abz_rule_resolvent_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, c_dp, c_dp, C.c_double, c_dp]
     lib.abz_rule_resolvent_matrix_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp, C.c_double, c_dp]
     lib.abz_rule_eig_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, C.c_double, c_dp]
+    lib.abz_rule_eig_sum_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, c_dp, C.c_double, c_dp]
     lib.abz_rule_eigvals.argtypes = [C.c_void_p, C.c_uint64, c_dp]
     lib.abz_rule_ggr_data.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp]
     lib.abz_rule_ggr_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, C.c_double, c_dp]
@@ -247,16 +248,17 @@ class DeviceSeries:
 class DeviceRule:
     """A quadrature rule on the device: FourierPTR (full grid) or FourierMonkhorstPack (wsym given)."""
 
-    def __init__(self, ctx, series, npt, wsym=None, k3_lo=0, k3_hi=None, k3_stride=1, nodes=None, weights=None, syms=None):
+    def __init__(self, ctx, series, npt, wsym=None, k3_lo=0, k3_hi=None, k3_stride=1, nodes=None, weights=None, syms=None, count_all=True):
         self.ctx, self.series, self.npt = ctx, series, int(npt)
         h = C.c_uint64()
         self.nirr_total = None
         if syms is not None:
             sy = np.ascontiguousarray(np.asarray(syms, dtype=np.int32).reshape(-1, 3, 3))
             nirr = C.c_int64()
+            # count_all = False: nirr_total = NULL, the library then builds the orbit weights of the selected planes only
             ctx.check(ctx.lib.abz_rule_create_symptr(ctx.h, series.h, self.npt, sy.shape[0], sy.ctypes.data_as(c_i32p), int(k3_lo),
-                                                     int(k3_stride), C.byref(h), C.byref(nirr)))
-            self.nirr_total = int(nirr.value)
+                                                     int(k3_stride), C.byref(h), C.byref(nirr) if count_all else None))
+            self.nirr_total = int(nirr.value) if count_all else None
         elif nodes is not None:
             idx = np.ascontiguousarray(np.asarray(nodes, dtype=np.int32).reshape(-1, 3))
             wv = None if weights is None else np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
@@ -326,6 +328,13 @@ class DeviceRule:
         out = np.zeros(1)
         self.ctx.check(self.ctx.lib.abz_rule_eig_sum(self.ctx.h, self.h, int(kind), _dp(prm), float(scale), _dp(out)))
         return float(out[0])
+
+    def eig_sum_batch(self, kind, params, scale=1.0):
+        """scale * sum_i w_i g_p(eigvals(H(k_i))) for every parameter pair in params [nparams, 2]: one diagonalisation per node"""
+        prm = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1, 2))
+        out = np.zeros(prm.shape[0])
+        self.ctx.check(self.ctx.lib.abz_rule_eig_sum_batch(self.ctx.h, self.h, int(kind), prm.shape[0], _dp(prm), float(scale), _dp(out)))
+        return out
 
     def eigvals(self):
         ev = np.empty((self.nnodes, self.series.n))

@@ -65,7 +65,7 @@ class DeviceRule:
     """FourierPTR / FourierMonkhorstPack on the device (src/fourier.jl:127-130, 210-214), possibly one
     rank's shard of it.  `nnodes` = local node count; `nnodes_total` = length(rule) of the reference."""
 
-    def __init__(self, backend, series, ndim, npt, syms, rank=0, nranks=1):
+    def __init__(self, backend, series, ndim, npt, syms, rank=0, nranks=1, allreduce=None):
         ctx = backend.ctx
         ds = series.device(ctx)
         self.backend, self.series, self.ndim, self.npt = backend, series, ndim, int(npt)
@@ -80,8 +80,14 @@ class DeviceRule:
             else:
                 # symptr_rule + CSR compaction on the device; the dense weights never visit the host
                 sy = embed_syms(syms, np.asarray(syms[0]).shape[0])
-                self.dev = _lib.DeviceRule(ctx, ds, self.npt, syms=sy, k3_lo=rank, k3_stride=nranks)
-                self.nnodes_total = self.dev.nirr_total
+                # with an allreduce at hand every rank computes the orbit weights of ITS k3 planes only and the ranks add up
+                # their node counts; without one (single rank, or a caller that shards by hand) the library counts all planes
+                local_only = nranks > 1 and allreduce is not None
+                self.dev = _lib.DeviceRule(ctx, ds, self.npt, syms=sy, k3_lo=rank, k3_stride=nranks, count_all=not local_only)
+                if local_only:
+                    self.nnodes_total = int(round(float(np.asarray(allreduce(np.array([float(len(self.dev))]))).reshape(-1)[0])))
+                else:
+                    self.nnodes_total = self.dev.nirr_total
         else:
             idx, w = symptr_nodes_lowdim(self.npt, ndim, syms)
             self.nnodes_total = idx.shape[0]
@@ -106,6 +112,10 @@ class DeviceRule:
 
     def eig_sum(self, kind, params):
         return self.dev.eig_sum(kind, params, scale=1.0)
+
+    def eig_sum_batch(self, kind, params):
+        """all parameter sets over ONE diagonalisation of every H(k) (parameter sweep over a shared grid, src/interfaces.jl:199-243)"""
+        return self.dev.eig_sum_batch(kind, params, scale=1.0)
 
     def copy_out(self):
         return self.dev.copy_out()
@@ -143,8 +153,8 @@ class DeviceBackend:
             self._wsym_cache[key] = self.ctx.symptr_rule(int(npt), sy)
         return self._wsym_cache[key]
 
-    def make_rule(self, series, ndim, npt, syms, rank=0, nranks=1):
-        return DeviceRule(self, series, ndim, npt, syms, rank, nranks)
+    def make_rule(self, series, ndim, npt, syms, rank=0, nranks=1, allreduce=None):
+        return DeviceRule(self, series, ndim, npt, syms, rank, nranks, allreduce)
 
     def make_nest(self, series, ndim, cap2, cap1):
         return _lib.DeviceNest(self.ctx, series.device(self.ctx), ndim, cap2 if ndim == 3 else 0, cap1 if ndim >= 2 else 0)

@@ -62,6 +62,7 @@ struct Rule {
     abz_ctx* ctx = nullptr;
     uint64_t series_id = 0;
     Series* s = nullptr;
+    std::shared_ptr<Series> keep;   // a rule keeps its series alive: abz_series_destroy only retires the handle
     int N = 0;
     bool full = true;
     bool nodes_on_host = true;   // false: node_k1 / node_w live on the device only (abz_rule_create_symptr)
@@ -74,9 +75,10 @@ struct Rule {
     int* d_node_k1 = nullptr; double* d_node_w = nullptr;
     double2* d_ptab[3] = {nullptr, nullptr, nullptr};
     double2* d_H = nullptr;   // materialised H(k) [nnz][n*n]
+    double* d_eig = nullptr;   // eigenvalues [nnz][n] of a materialised rule (cached across parameters, like the reference's cached grid)
     double* d_ggr_e = nullptr; double* d_ggr_v = nullptr; int ggr_ndim = 0;   // GGR data pass: energies [nnz][n], velocities [nnz][ndim][n]
     ~Rule() {
-        pool_free(ctx, d_ggr_e); pool_free(ctx, d_ggr_v);
+        pool_free(ctx, d_ggr_e); pool_free(ctx, d_ggr_v); pool_free(ctx, d_eig);
         pool_free(ctx, d_plane_k3); pool_free(ctx, d_plane_rowptr); pool_free(ctx, d_row_k2); pool_free(ctx, d_row_nodeptr);
         pool_free(ctx, d_node_k1); pool_free(ctx, d_node_w); pool_free(ctx, d_H);
         for (auto& p : d_ptab) pool_free(ctx, p);
@@ -86,6 +88,7 @@ struct Rule {
 struct Nest {
     abz_ctx* ctx = nullptr;
     Series* s = nullptr;
+    std::shared_ptr<Series> keep;   // as Rule::keep
     int ndim = 3;
     long cap2 = 0, cap1 = 0;
     double2* L2 = nullptr; double2* L1 = nullptr;
@@ -119,7 +122,7 @@ struct abz_ctx {
     size_t pool_held = 0, pool_cap = (size_t)16 << 30;              // bytes parked in the free lists / their limit
     std::string err;
     uint64_t next_id = 1;
-    std::unordered_map<uint64_t, std::unique_ptr<Series>> series;
+    std::unordered_map<uint64_t, std::shared_ptr<Series>> series;
     std::unordered_map<uint64_t, std::unique_ptr<Rule>> rules;
     std::unordered_map<uint64_t, std::unique_ptr<Nest>> nests;
     int resolvent_algo = 0;
@@ -315,11 +318,6 @@ size_t stage_smem(int M) { return (size_t)((M + 1) & ~1) * (ST_RT + 2 * ST_JT) *
 int launch_stage(abz_ctx* ctx, const double2* in, double2* out, const double2* ptab, const long* ptr, long b0,
                  long nbatch, const int* klist, int N, int M, long rows, long in_stride) {
     if (nbatch <= 0 || rows <= 0) return ABZ_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(contract_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
     size_t smem = stage_smem(M);
     if (smem > 200 * 1024) return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension");
     dim3 grid((unsigned)nbatch, (unsigned)((rows + ST_RT - 1) / ST_RT));
@@ -405,12 +403,6 @@ static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n, int* h
         eig_tridiag_reg64_kernel<<<(unsigned)ncta, 256, 0, ctx->stream>>>(H, nk, n, dd, ee, herm_flag);
         LAUNCH_CHECK(ctx, "eig_tridiag_reg64_kernel");
         return ABZ_OK;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(eig_tridiag_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaFuncSetAttribute(eig_tridiag_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
     }
     const int RP = n > 32 ? 64 : 32;
     const size_t smem = ((size_t)n * RP + RP + (size_t)(4 * RP / 32) * (RP - 1)) * sizeof(double2);
@@ -562,11 +554,6 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
     while (nwarps > 1 && gj_smem_bytes(n, nw, nwarps) > 200 * 1024) nwarps--;
     size_t smem = gj_smem_bytes(n, nw, nwarps);
     if (smem > 220 * 1024) return fail(ctx, ABZ_E_UNSUPPORTED, "too many frequencies per call for the generic resolvent kernel");
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(resolvent_gj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_set = true;
-    }
     // nodes per CTA: aim at ~4 CTAs per SM worth of CTAs, but keep every warp busy: work per node = nw matrices
     long target_cta = sm * 4;
     int kper = (int)std::max<long>(1, (nk + target_cta - 1) / target_cta);
@@ -596,16 +583,6 @@ int run_small_fused(abz_ctx* ctx, Rule* r, const double2* C1, const double2* Hma
     if (fkind == ABZ_F_TRACE_H) nw = 1;
     int nwy = (nw + SM_WMAX - 1) / SM_WMAX;
     const size_t smem = (size_t)9 * std::min(nw, SM_WMAX) * sizeof(double2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(small_fused_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(small_fused_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(small_fused_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(small_fused_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(small_fused_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(small_fused_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_set = true;
-    }
     CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
     dim3 grid((unsigned)ncta, (unsigned)nwy);
     int* ef = ctx->errflag.as<int>();
@@ -630,6 +607,43 @@ void collect_timings(abz_ctx* ctx, const std::vector<std::pair<cudaEvent_t, cuda
     for (auto& p : ev_eval) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); ctx->eval_ms += ms; }
     for (auto& p : ev_mat) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); ctx->matfun_ms += ms; }
     ctx->ev_used = 0;
+}
+
+// Opt every kernel that needs more than 48 KB of dynamic shared memory in on the CURRENT device.  The attribute is per device
+// (and per kernel), so it is set whenever a context is created - one process may hold one context per GPU.
+cudaError_t opt_in_dynamic_smem() {
+    cudaError_t e = cudaSuccess;
+    auto set = [&](const void* f, int bytes) {
+        cudaError_t r = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (r != cudaSuccess && e == cudaSuccess) e = r;
+    };
+#define ABZ_OPT_IN(kernel, bytes) set(reinterpret_cast<const void*>(&kernel), bytes)
+    ABZ_OPT_IN(contract_stage_kernel, 200 * 1024);
+    ABZ_OPT_IN(eig_tridiag_kernel<32>, 100 * 1024);
+    ABZ_OPT_IN(eig_tridiag_kernel<64>, 100 * 1024);
+    ABZ_OPT_IN(resolvent_gj_kernel, 220 * 1024);
+    ABZ_OPT_IN(resolvent_gj_matrix_kernel, 220 * 1024);
+    { auto k = small_fused_kernel<1, true>; set((const void*)k, 160 * 1024); }
+    { auto k = small_fused_kernel<2, true>; set((const void*)k, 160 * 1024); }
+    { auto k = small_fused_kernel<3, true>; set((const void*)k, 160 * 1024); }
+    { auto k = small_fused_kernel<1, false>; set((const void*)k, 160 * 1024); }
+    { auto k = small_fused_kernel<2, false>; set((const void*)k, 160 * 1024); }
+    { auto k = small_fused_kernel<3, false>; set((const void*)k, 160 * 1024); }
+    { auto k = resolvent_gjreg_matrix_kernel<64, 32, 4, 3>; set((const void*)k, 64 * 1024); }
+    { auto k = resolvent_gjreg_matrix_kernel<64, 32, 16, 2>; set((const void*)k, 64 * 1024); }
+    { auto k = resolvent_gjreg_matrix_kernel<64, 16, 8, 2>; set((const void*)k, 64 * 1024); }
+    ABZ_OPT_IN(eig_jacobi_kernel, 200 * 1024);
+    ABZ_OPT_IN(eig_jacobi_vel_kernel, 200 * 1024);
+    ABZ_OPT_IN(nest_panel_small_kernel<1>, 160 * 1024);
+    ABZ_OPT_IN(nest_panel_small_kernel<2>, 160 * 1024);
+    ABZ_OPT_IN(nest_panel_small_kernel<3>, 160 * 1024);
+    ABZ_OPT_IN(iai_leaf_kernel<1>, 160 * 1024);
+    ABZ_OPT_IN(iai_leaf_kernel<2>, 160 * 1024);
+    ABZ_OPT_IN(iai_leaf_kernel<3>, 160 * 1024);
+#undef ABZ_OPT_IN
+    cudaError_t r = mma_resolvent_opt_in();
+    if (r != cudaSuccess && e == cudaSuccess) e = r;
+    return e;
 }
 
 long node_cap_for(abz_ctx* ctx, int n) { return (long)std::max<size_t>(1, ctx->budget / ((size_t)n * n * sizeof(double2))); }
@@ -657,6 +671,10 @@ int32_t abz_ctx_create(int32_t device, abz_ctx** out) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, ABZ_E_CUDA, cudaGetErrorString(e));
     if (prop.major != 10) return fail(nullptr, ABZ_E_UNSUPPORTED, "libautobz_cuda is built for sm_100a (B200) only");
     if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, ABZ_E_CUDA, cudaGetErrorString(e));
+    if ((e = opt_in_dynamic_smem()) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, ABZ_E_CUDA, std::string("shared-memory opt-in: ") + cudaGetErrorString(e));
+    }
     abz_ctx* ctx = new abz_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
@@ -720,7 +738,7 @@ int32_t abz_series_create(abz_ctx* ctx, const double* coeffs, int32_t is_complex
     for (int d = 0; d < 3; d++)
         if (M[d] < 1 || !(period[d] > 0)) return fail(ctx, ABZ_E_INVALID, "M >= 1 and period > 0 required");
     cudaSetDevice(ctx->device);
-    auto s = std::make_unique<Series>();
+    auto s = std::make_shared<Series>();
     s->ctx = ctx;
     s->n = norb;
     size_t cnt = (size_t)norb * norb;
@@ -756,7 +774,7 @@ int32_t abz_rule_create_full(abz_ctx* ctx, abz_series_t sid, int32_t npt, int32_
     cudaSetDevice(ctx->device);
     auto r = std::make_unique<Rule>();
     r->ctx = ctx;
-    r->series_id = sid; r->s = s; r->N = npt; r->full = true;
+    r->series_id = sid; r->s = s; r->keep = ctx->series[sid]; r->N = npt; r->full = true;
     const long N = npt;
     r->np3 = k3_hi - k3_lo;
     r->nrows = r->np3 * N;
@@ -784,7 +802,7 @@ int32_t abz_rule_create_sym(abz_ctx* ctx, abz_series_t sid, int32_t npt, const i
     cudaSetDevice(ctx->device);
     auto r = std::make_unique<Rule>();
     r->ctx = ctx;
-    r->series_id = sid; r->s = s; r->N = npt; r->full = false;
+    r->series_id = sid; r->s = s; r->keep = ctx->series[sid]; r->N = npt; r->full = false;
     const long N = npt;
     r->h_plane_rowptr.push_back(0);
     r->h_row_nodeptr.push_back(0);
@@ -831,7 +849,7 @@ int32_t abz_rule_create_nodes(abz_ctx* ctx, abz_series_t sid, int32_t npt, int64
     cudaSetDevice(ctx->device);
     auto r = std::make_unique<Rule>();
     r->ctx = ctx;
-    r->series_id = sid; r->s = s; r->N = npt; r->full = false;
+    r->series_id = sid; r->s = s; r->keep = ctx->series[sid]; r->N = npt; r->full = false;
     r->h_plane_rowptr.push_back(0);
     r->h_row_nodeptr.push_back(0);
     long p3 = -1, p2 = -1, p1 = -1;
@@ -891,42 +909,51 @@ static bool syms_form_group(const int32_t* h_syms, int nsyms) {
     return true;
 }
 
-static int launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms, const int* d_syms, int* d_w) {
+// Orbit weights of the planes i3 = k3_lo + p * k3_stride (p < nplanes) into the dense array d_w; other planes are not touched.
+// Every point's test "am I the smallest index of my orbit" is independent of the others, so a rank needs only its own planes.
+static int launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms, const int* d_syms, int* d_w, int k3_lo = 0,
+                         int k3_stride = 1, long nplanes = -1) {
     if (!syms_form_group(h_syms, nsyms))
         return fail(ctx, ABZ_E_INVALID, "the symmetries must form a group (identity included, closed under products, no duplicates)");
+    if (nplanes < 0) nplanes = npt;
+    if (nplanes == 0) return ABZ_OK;
     long smax = 0;
     for (int t = 0; t < 9 * nsyms; t++) smax = std::max<long>(smax, std::labs((long)h_syms[t]));
+    const size_t plane = (size_t)npt * npt;
     const size_t tot = (size_t)npt * npt * npt;
-    const unsigned grid = (unsigned)((tot + 255) / 256);
+    const size_t sel = plane * (size_t)nplanes;
+    const unsigned grid = (unsigned)((sel + 255) / 256);
     const size_t smem = (size_t)nsyms * 9 * sizeof(int);
     const bool fast = 3 * smax * npt < (1L << 22);
     // large grids, at most 64 symmetries: phases with compaction (see abz_iai.cuh); else the one-kernel version
-    if (fast && nsyms <= 64 && nsyms > 8 && tot >= ((size_t)1 << 22) && tot < ((size_t)1 << 32)) {
-        const unsigned cap1 = (unsigned)(tot / 2 + 1024), cap2 = 16u;
+    if (fast && nsyms <= 64 && nsyms > 8 && sel >= ((size_t)1 << 22) && tot < ((size_t)1 << 32)) {
+        const unsigned cap1 = (unsigned)(sel / 2 + 1024), cap2 = 16u;
         DevBuf& lb = ctx->symlist;
         CU(ctx, lb.reserve(((size_t)cap1 + cap2 + 16) * sizeof(unsigned)));
         unsigned* cnt = lb.as<unsigned>();           // [0]: survivors of phase 1, [1]: irreducible points, [2]: overflow flag
         unsigned* l1 = cnt + 16;
         unsigned* l2 = l1 + cap1;
         CU(ctx, cudaMemsetAsync(cnt, 0, 16 * sizeof(unsigned), ctx->stream));
-        CU(ctx, cudaMemsetAsync(d_w, 0, tot * sizeof(int), ctx->stream));
-        dim3 g1((unsigned)(((size_t)npt * npt + 255) / 256), (unsigned)npt);
+        if (k3_stride == 1) CU(ctx, cudaMemsetAsync(d_w + (size_t)k3_lo * plane, 0, sel * sizeof(int), ctx->stream));
+        else CU(ctx, cudaMemset2DAsync(d_w + (size_t)k3_lo * plane, (size_t)k3_stride * plane * sizeof(int), 0, plane * sizeof(int),
+                                        (size_t)nplanes, ctx->stream));
+        dim3 g1((unsigned)((plane + 255) / 256), (unsigned)nplanes);
         symptr_filter_kernel<true, false><<<g1, 256, smem, ctx->stream>>>(npt, nsyms, 0, 8, d_syms, nullptr, nullptr, l1, cnt, cap1,
-                                                                         reinterpret_cast<int*>(cnt + 2), d_w);
+                                                                         reinterpret_cast<int*>(cnt + 2), d_w, k3_lo, k3_stride);
         LAUNCH_CHECK(ctx, "symptr_filter_kernel");
         unsigned h[3] = {0, 0, 0};
         CU(ctx, cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         if (!h[2] && h[0] > 0) {
             symptr_filter_kernel<true, true><<<(h[0] + 255) / 256, 256, smem, ctx->stream>>>(npt, nsyms, 8, nsyms, d_syms, l1, cnt, l2, cnt + 1,
-                                                                                            cap2, reinterpret_cast<int*>(cnt + 2), d_w);
+                                                                                            cap2, reinterpret_cast<int*>(cnt + 2), d_w, 0, 1);
             LAUNCH_CHECK(ctx, "symptr_filter_kernel");
         }
         if (!h[2]) return ABZ_OK;
         // a list overflowed (symmetry list with an unusual order): fall through to the one-kernel version, which overwrites d_w
     }
-    if (fast) symptr_rule_kernel<true><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, d_w);
-    else symptr_rule_kernel<false><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, d_w);
+    if (fast) symptr_rule_kernel<true><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, d_w, k3_lo, k3_stride, (int)nplanes);
+    else symptr_rule_kernel<false><<<grid, 256, smem, ctx->stream>>>(npt, nsyms, d_syms, d_w, k3_lo, k3_stride, (int)nplanes);
     LAUNCH_CHECK(ctx, "symptr_rule_kernel");
     return ABZ_OK;
 }
@@ -970,11 +997,16 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
     CU(ctx, wbuf.reserve(tot * sizeof(int)));
     CU(ctx, ctx->tmp_b.reserve((size_t)nsyms * 9 * sizeof(int)));
     CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, syms, (size_t)nsyms * 9 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    { int rcs = launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), wbuf.as<int>()); if (rcs) return rcs; }
-    // per-row counts: all planes when the total is wanted, else only this rank's
+    // per-row counts: all planes when the total is wanted, else only this rank's (then the orbit weights of the other ranks'
+    // planes are not even computed: the caller sums the local node counts over the ranks)
     const bool want_total = (nirr_total != nullptr) && !(k3_lo == 0 && k3_stride == 1);
     std::vector<int> cnt_all;
     const long nplanes_sel = (k3_lo < N) ? (N - k3_lo + k3_stride - 1) / k3_stride : 0;
+    {
+        int rcs = want_total ? launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), wbuf.as<int>())
+                             : launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), wbuf.as<int>(), k3_lo, k3_stride, nplanes_sel);
+        if (rcs) return rcs;
+    }
     const long rows_sel = nplanes_sel * N;
     std::vector<int> cnt(rows_sel);
     CU(ctx, cntbuf.reserve((size_t)std::max<long>(N * N, 1) * sizeof(int)));
@@ -1001,7 +1033,7 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
     // CSR skeleton on the host (N^2 entries), node arrays on the device
     auto r = std::make_unique<Rule>();
     r->ctx = ctx;
-    r->series_id = sid; r->s = s; r->N = npt; r->full = false; r->nodes_on_host = false;
+    r->series_id = sid; r->s = s; r->keep = ctx->series[sid]; r->N = npt; r->full = false; r->nodes_on_host = false;
     r->h_plane_rowptr.push_back(0);
     r->h_row_nodeptr.push_back(0);
     std::vector<int> row_k3;
@@ -1228,8 +1260,6 @@ int32_t abz_rule_resolvent_matrix_sum(abz_ctx* ctx, abz_rule_t rid, int32_t nw, 
     const size_t per_warp = ((size_t)n * (n + 1) + (n + 1) / 2 + 1 + nn) * sizeof(double2);
     const int nwarps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
     const size_t smem = per_warp * nwarps;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(resolvent_gj_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
     std::vector<Chunk> chunks;
     long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
     if (r->d_H) chunks.push_back({0, r->np3, 0, r->nrows});
@@ -1262,13 +1292,6 @@ int32_t abz_rule_resolvent_matrix_sum(abz_ctx* ctx, abz_rule_t rid, int32_t nw, 
             resolvent_gj_matrix_kernel<<<grid, nwarps * 32, smem, ctx->stream>>>(Hd, wn, nk, n, nw, ctx->zbuf.as<double2>(), sgd, kper,
                                                                                 ctx->partial.as<double2>(), ctx->errflag.as<int>());
         } else {
-            static bool gj_attr = false;
-            if (!gj_attr) {
-                cudaFuncSetAttribute(resolvent_gjreg_matrix_kernel<64, 32, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-                cudaFuncSetAttribute(resolvent_gjreg_matrix_kernel<64, 32, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-                cudaFuncSetAttribute(resolvent_gjreg_matrix_kernel<64, 16, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-                gj_attr = true;
-            }
             GJ_DISPATCH(resolvent_gjreg_matrix_kernel, true, n, grid, (size_t)nn * sizeof(double2), ctx->stream, Hd, wn, nk, n, nw,
                         ctx->zbuf.as<double2>(), sgd, kper, ctx->partial.as<double2>(), ctx->errflag.as<int>());
         }
@@ -1303,8 +1326,6 @@ static int run_eig_jacobi(abz_ctx* ctx, const double2* H, const double* wnode, l
                           double* evals, double* acc) {
     int threads = std::min(256, std::max(32, ((n * ((n + 1) / 2) + 31) / 32) * 32));
     size_t smem = eig_smem_bytes(n, threads);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(eig_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / smem));
     long ncta = std::min<long>(nk, (long)ctx->sm_count * per_sm);
     if (mode == 0) CU(ctx, ctx->partial.reserve((size_t)ncta * sizeof(double)));
@@ -1322,7 +1343,7 @@ static int run_eig_jacobi(abz_ctx* ctx, const double2* H, const double* wnode, l
 static int run_eig(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int n, int mode, int kind, double p0, double p1,
                    double* evals, double* acc) {
     if (nk <= 0) return ABZ_OK;
-    if (ctx->eig_algo == 1 || n > EIG_MAXN) return run_eig_jacobi(ctx, H, wnode, nk, n, mode, kind, p0, p1, evals, acc);
+    if (ctx->eig_algo == 1 || n > EIG_MAXN) return run_eig_jacobi(ctx, H, wnode, nk, n, mode == 2 ? 1 : mode, kind, p0, p1, evals, acc);
     { int rct = launch_tridiag(ctx, H, nk, n); if (rct) return rct; }
     const long nblk = (nk + 31) / 32;
     if (mode == 0) CU(ctx, ctx->partial.reserve((size_t)nblk * sizeof(double)));
@@ -1336,52 +1357,95 @@ static int run_eig(abz_ctx* ctx, const double2* H, const double* wnode, long nk,
     return ABZ_OK;
 }
 
-int32_t abz_rule_eig_sum(abz_ctx* ctx, abz_rule_t rid, int32_t kind, const double* params, double scale, double* out) {
+// sums over the eigenvalues in `evals` ([nk][n]) for every parameter set: acc[p] += sum_k w_k sum_b g_p(e_b)
+static int run_eig_cached_sums(abz_ctx* ctx, const double* evals, const double* wnode, long nk, int n, int kind, int nprm,
+                               const double* dparams, double* acc) {
+    if (nk <= 0) return ABZ_OK;
+    const long ncta = std::max<long>(1, std::min<long>((nk + 255) / 256, (long)ctx->sm_count * 4));
+    CU(ctx, ctx->partial.reserve((size_t)ncta * nprm * sizeof(double)));
+    for (int p0 = 0; p0 < nprm; p0 += 65535) {
+        const int cnt = std::min(65535, nprm - p0);
+        dim3 grid((unsigned)ncta, (unsigned)cnt);
+        eig_cached_sum_kernel<<<grid, 256, 0, ctx->stream>>>(evals, wnode, nk, n, kind, cnt, dparams + 2 * p0, ctx->partial.as<double>());
+        LAUNCH_CHECK(ctx, "eig_cached_sum_kernel");
+        reduce_real_strided_kernel<<<cnt, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), ncta, cnt, 1.0, acc + p0);
+        LAUNCH_CHECK(ctx, "reduce_real_strided_kernel");
+    }
+    return ABZ_OK;
+}
+
+int32_t abz_rule_eig_sum_batch(abz_ctx* ctx, abz_rule_t rid, int32_t kind, int32_t nparams, const double* params, double scale,
+                               double* out) {
     if (!ctx) return ABZ_E_INVALID;
     Rule* r = get_rule(ctx, rid);
     if (!r) return fail(ctx, ABZ_E_INVALID, "unknown rule handle");
-    if (kind < 0 || kind > 3 || !out || (kind != 0 && !params)) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    if (kind < 0 || kind > 3 || !out || nparams < 1 || (kind != 0 && !params)) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
     cudaSetDevice(ctx->device);
     Series* s = r->s;
     const int n = s->n;
     const long nn = (long)n * n;
-    double p0 = params ? params[0] : 0.0, p1 = params ? params[1] : 1.0;
-    CU(ctx, ctx->acc.reserve(sizeof(double2)));
-    CU(ctx, cudaMemsetAsync(ctx->acc.p, 0, sizeof(double2), ctx->stream));
+    std::vector<double> hp((size_t)2 * nparams);
+    for (int p = 0; p < nparams; p++) { hp[2 * p] = params ? params[2 * p] : 0.0; hp[2 * p + 1] = params ? params[2 * p + 1] : 1.0; }
+    CU(ctx, ctx->zbuf.reserve(hp.size() * sizeof(double)));
+    CU(ctx, cudaMemcpyAsync(ctx->zbuf.p, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, ctx->acc.reserve((size_t)nparams * sizeof(double)));
+    CU(ctx, cudaMemsetAsync(ctx->acc.p, 0, (size_t)nparams * sizeof(double), ctx->stream));
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_eval, ev_mat;
     ctx->ev_used = 0;
     int rc;
-    if (r->d_H) {
+    const double* dprm = ctx->zbuf.as<double>();
+    if (r->d_eig) {
+        // a materialised rule that has been diagonalised before: parameters sweep over the cached eigenvalues
         cudaEvent_t e0 = next_event(ctx);
-        rc = run_eig(ctx, r->d_H, r->d_node_w, r->nnz, n, 0, kind, p0, p1, nullptr, ctx->acc.as<double>());
+        rc = run_eig_cached_sums(ctx, r->d_eig, r->d_node_w, r->nnz, n, kind, nparams, dprm, ctx->acc.as<double>());
         if (rc) return rc;
         ev_mat.push_back({e0, next_event(ctx)});
     } else {
+        std::vector<Chunk> chunks;
         long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
-        auto chunks = plan_chunks(r, node_cap_for(ctx, n), (long)(ctx->budget / (rows1 * sizeof(double2))),
+        if (r->d_H) chunks.push_back({0, r->np3, 0, r->nrows});
+        else chunks = plan_chunks(r, node_cap_for(ctx, n), (long)(ctx->budget / (rows1 * sizeof(double2))),
                                   (long)(ctx->budget / (rows2 * sizeof(double2))));
+        double* keep = nullptr;
+        if (r->d_H && r->nnz > 0) CU(ctx, pool_alloc(ctx, (void**)&keep, (size_t)r->nnz * n * sizeof(double)));
         for (auto& ch : chunks) {
-            long n0 = r->h_row_nodeptr[ch.r0], n1 = r->h_row_nodeptr[ch.r1];
+            const long n0 = r->h_row_nodeptr[ch.r0], n1 = r->h_row_nodeptr[ch.r1], nk = n1 - n0;
+            if (nk <= 0) continue;
             cudaEvent_t e0 = next_event(ctx);
-            CU(ctx, ctx->Hc.reserve((size_t)(n1 - n0) * nn * sizeof(double2)));
-            rc = eval_chunk(ctx, r, ch, true, ctx->Hc.as<double2>());
-            if (rc) return rc;
+            const double2* Hd = r->d_H ? r->d_H + n0 * nn : nullptr;
+            if (!Hd) {
+                CU(ctx, ctx->Hc.reserve((size_t)nk * nn * sizeof(double2)));
+                rc = eval_chunk(ctx, r, ch, true, ctx->Hc.as<double2>());
+                if (rc) { pool_free(ctx, keep); return rc; }
+                Hd = ctx->Hc.as<double2>();
+            }
             cudaEvent_t e1 = next_event(ctx);
-            rc = run_eig(ctx, ctx->Hc.as<double2>(), r->d_node_w ? r->d_node_w + n0 : nullptr, n1 - n0, n, 0, kind, p0, p1, nullptr,
-                         ctx->acc.as<double>());
-            if (rc) return rc;
+            double* ev = keep ? keep + n0 * n : nullptr;
+            if (!ev) { CU(ctx, ctx->tmp_a.reserve((size_t)nk * n * sizeof(double))); ev = ctx->tmp_a.as<double>(); }
+            rc = run_eig(ctx, Hd, nullptr, nk, n, 2, 0, 0, 1, ev, nullptr);
+            if (!rc) rc = run_eig_cached_sums(ctx, ev, r->d_node_w ? r->d_node_w + n0 : nullptr, nk, n, kind, nparams, dprm, ctx->acc.as<double>());
+            if (rc) { pool_free(ctx, keep); return rc; }
             cudaEvent_t e2 = next_event(ctx);
             ev_eval.push_back({e0, e1});
             ev_mat.push_back({e1, e2});
         }
+        if (keep) {
+            rc = check_errflag(ctx, "abz_rule_eig_sum");
+            if (rc) { pool_free(ctx, keep); collect_timings(ctx, ev_eval, ev_mat); return rc; }
+            r->d_eig = keep;
+        }
     }
-    double h = 0;
-    CU(ctx, cudaMemcpyAsync(&h, ctx->acc.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<double> h((size_t)nparams);
+    CU(ctx, cudaMemcpyAsync(h.data(), ctx->acc.p, (size_t)nparams * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     rc = check_errflag(ctx, "abz_rule_eig_sum");
     collect_timings(ctx, ev_eval, ev_mat);
     if (rc) return rc;
-    out[0] = scale * h;
+    for (int p = 0; p < nparams; p++) out[p] = scale * h[p];
     return ABZ_OK;
+}
+
+int32_t abz_rule_eig_sum(abz_ctx* ctx, abz_rule_t rid, int32_t kind, const double* params, double scale, double* out) {
+    return abz_rule_eig_sum_batch(ctx, rid, kind, 1, params, scale, out);
 }
 
 int32_t abz_rule_eigvals(abz_ctx* ctx, abz_rule_t rid, double* evals) {
@@ -1446,8 +1510,6 @@ int32_t abz_rule_ggr_data(abz_ctx* ctx, abz_rule_t rid, int32_t ndim, double* en
         const int threads = std::min(256, std::max(64, ((n * ((n + 1) / 2) + 31) / 32) * 32));
         const size_t smem = ((size_t)n * (n + 1) + (size_t)n * n + npair) * 16 + (size_t)(npair + 3 * n + 2 * (threads / 32) + 2) * 8 +
                             (size_t)2 * npair * 4 + 64;
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(eig_jacobi_vel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
         long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
         const size_t share = ctx->budget / 4;
@@ -1580,7 +1642,7 @@ int32_t abz_nest_create(abz_ctx* ctx, abz_series_t sid, int32_t ndim, int64_t ca
     cudaSetDevice(ctx->device);
     auto nst = std::make_unique<Nest>();
     nst->ctx = ctx;
-    nst->s = s; nst->ndim = ndim; nst->cap2 = cap2; nst->cap1 = cap1;
+    nst->s = s; nst->keep = ctx->series[sid]; nst->ndim = ndim; nst->cap2 = cap2; nst->cap1 = cap1;
     const size_t nn = (size_t)s->n * s->n;
     if (ndim == 3 && cap2 > 0) CU(ctx, pool_alloc(ctx, (void**)&nst->L2, (size_t)cap2 * nn * s->M[0] * s->M[1] * sizeof(double2)));
     if (ndim >= 2 && cap1 > 0) CU(ctx, pool_alloc(ctx, (void**)&nst->L1, (size_t)cap1 * nn * s->M[0] * sizeof(double2)));
@@ -1844,13 +1906,6 @@ struct IaiDeviceBackend {
         if (ns) {
             const long* sslot = has_slots ? dL + o_ss : nullptr;
             unsigned g = (unsigned)((ns + 7) / 8);
-            static bool attr_panel = false;
-            if (!attr_panel) {
-                cudaFuncSetAttribute(nest_panel_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-                cudaFuncSetAttribute(nest_panel_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-                cudaFuncSetAttribute(nest_panel_small_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-                attr_panel = true;
-            }
             if ((size_t)8 * s->M[0] * n * n * sizeof(double2) > 160 * 1024)
                 return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension for the IAI panel kernel");
 #define PANEL_LAUNCH(NORB)                                                                                               \
@@ -1963,13 +2018,6 @@ struct IaiDeviceBackend {
             const long* sslot = has_slots ? dL + o_ss : nullptr;
             if (n <= 3) {
                 unsigned g = (unsigned)((ns + 7) / 8);
-                static bool attr_panel = false;
-                if (!attr_panel) {
-                    cudaFuncSetAttribute(nest_panel_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-                    cudaFuncSetAttribute(nest_panel_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-                    cudaFuncSetAttribute(nest_panel_small_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-                    attr_panel = true;
-                }
                 if ((size_t)8 * s->M[0] * n * n * sizeof(double2) > 160 * 1024)
                     return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension for the IAI panel kernel");
 #define PANEL_LAUNCH(NORB)                                                                                               \
@@ -2019,13 +2067,6 @@ struct IaiDeviceBackend {
         const int spill_cap = ctx->leaf_spill;
         CU(ctx, spillbuf.reserve((size_t)nt * std::max(spill_cap, 1) * sizeof(LeafSeg) + 64));
         unsigned g = (unsigned)((nt + LEAF_WARPS - 1) / LEAF_WARPS);
-        static bool attr_leaf = false;
-        if (!attr_leaf) {
-            cudaFuncSetAttribute(iai_leaf_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            cudaFuncSetAttribute(iai_leaf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            cudaFuncSetAttribute(iai_leaf_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            attr_leaf = true;
-        }
         if ((size_t)LEAF_WARPS * s->M[0] * s->n * s->n * sizeof(double2) > 160 * 1024)
             return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension for the IAI leaf kernel");
         LeafSeg* spill = reinterpret_cast<LeafSeg*>(spillbuf.as<char>() + 64);

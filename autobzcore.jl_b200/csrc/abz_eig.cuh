@@ -708,7 +708,7 @@ eig_tridiag_reg64_kernel(const double2* __restrict__ H, long nk, int n, double* 
 
 // Stage B: eigenvalues of the real symmetric tridiagonal (d, e) by the implicit QL algorithm with Wilkinson shifts
 // (EISPACK imtql1 / "tqli" without vectors), one thread per matrix.  mode 0: partial[cta] = sum_k wnode_k sum_n g(e_n);
-// mode 1: evals[k*n + i] ascending.
+// mode 1: evals[k*n + i] ascending; mode 2: evals[k*n + i] unsorted.
 constexpr int EIG_MAXN = 64;
 // The working arrays d[i], e[i] of thread `lane` live in shared memory as ds[i*32 + lane]: whatever index each lane is at
 // (the lanes of a warp diverge in l, m, i), lane t only touches banks 2t, 2t+1 - two wavefronts per access, no conflicts -
@@ -768,7 +768,9 @@ eig_tql_kernel(const double* __restrict__ din, const double* __restrict__ ein, c
                     }
                 } while (m != l);
             }
-            if (mode == 1) {
+            if (mode == 2) {                      // eigenvalues as they come (sums over bands do not need the order)
+                for (int i = 0; i < n; i++) evals[k * n + i] = TQL_D(i);
+            } else if (mode == 1) {
                 for (int i = 1; i < n; i++) {     // insertion sort, ascending
                     const double x = TQL_D(i);
                     int j = i - 1;
@@ -854,6 +856,45 @@ tridiag_resolvent_kernel(const double* __restrict__ din, const double* __restric
             outp[(long)blockIdx.x * nw + w0 + threadIdx.x] = a;
         }
     }
+}
+
+// Parameter sweep over cached eigenvalues (batchsolve over (mu, T), src/interfaces.jl:199-243: the reference shares the cached grid
+// across parameters; here one diagonalisation per node serves every parameter): partial[blockIdx.x * nprm + p] = sum over this
+// CTA's nodes of wnode * sum_b g_p(e_b), p = blockIdx.y, params = {p0, p1} per parameter set.  Fixed strided order + fixed tree.
+__global__ void __launch_bounds__(256)
+eig_cached_sum_kernel(const double* __restrict__ evals, const double* __restrict__ wnode, long nk, int n, int kind, int nprm,
+                      const double* __restrict__ params, double* __restrict__ partial) {
+    __shared__ double sx[256];
+    const int p = blockIdx.y;
+    const double p0 = params[2 * p], p1 = params[2 * p + 1];
+    double acc = 0.0;
+    for (long k = (long)blockIdx.x * 256 + threadIdx.x; k < nk; k += (long)gridDim.x * 256) {
+        const double* e = evals + k * n;
+        double v = 0.0;
+        for (int b = 0; b < n; b++) v += eig_kernel_value(e[b], kind, p0, p1);
+        acc += (wnode ? wnode[k] : 1.0) * v;
+    }
+    sx[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sx[threadIdx.x] += sx[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(long)blockIdx.x * nprm + p] = sx[0];
+}
+// acc[p] += scale * sum_c partial[c * stride + p], p = blockIdx.x
+__global__ void __launch_bounds__(256) reduce_real_strided_kernel(const double* __restrict__ partial, long n, long stride, double scale,
+                                                                  double* __restrict__ acc) {
+    __shared__ double sx[256];
+    double x = 0.0;
+    for (long c = threadIdx.x; c < n; c += 256) x += partial[c * stride + blockIdx.x];
+    sx[threadIdx.x] = x;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sx[threadIdx.x] += sx[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) acc[blockIdx.x] += scale * sx[0];
 }
 
 // deterministic reduction of real partials: acc[0] += scale * sum_c partial[c]

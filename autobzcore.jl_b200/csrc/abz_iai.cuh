@@ -364,15 +364,17 @@ __device__ __forceinline__ long symptr_image(const int* __restrict__ S, int i1, 
 
 template <bool FAST>
 __global__ void __launch_bounds__(256)
-symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restrict__ wsym) {
+symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restrict__ wsym, int k3_lo, int k3_stride, int nplanes) {
     extern __shared__ int sy[];
     for (int t = threadIdx.x; t < 9 * nsyms; t += 256) sy[t] = syms[t];
     __syncthreads();
-    const long tot = (long)N * N * N;
-    const long idx = (long)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= tot) return;
-    const int i1 = (int)(idx % N), i2 = (int)((idx / N) % N), i3 = (int)(idx / ((long)N * N));
+    // the selected planes i3 = k3_lo + p * k3_stride, p < nplanes (one rank's share; all planes: 0, 1, N)
     const long NN = (long)N * N;
+    const long lidx = (long)blockIdx.x * 256 + threadIdx.x;
+    if (lidx >= NN * nplanes) return;
+    const long rr = lidx % NN;
+    const int i1 = (int)(rr % N), i2 = (int)(rr / N), i3 = k3_lo + (int)(lidx / NN) * k3_stride;
+    const long idx = (long)i3 * NN + rr;
     const float invN = 1.0f / (float)N;
     // pass 1: is this node the smallest linear index of its orbit?  (most nodes leave after a few symmetries)
     bool has_self = false;
@@ -409,14 +411,15 @@ symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restri
 //   phase 2  the survivors try the remaining symmetries; an irreducible point gets weight nsyms / |stabiliser| (the list
 //            is a group: checked on the host).
 // wsym must be zero on entry; only irreducible points are written.  Lists hold 32-bit linear indices (N^3 < 2^32).
-// phase 1 (in_list == NULL): grid = (ceil(N^2 / 256), N), blockIdx.y = i3 - 32-bit index arithmetic only;
+// phase 1 (in_list == NULL): grid = (ceil(N^2 / 256), planes), i3 = k3_lo + blockIdx.y * k3_stride (one rank's planes, or all of
+// them with k3_lo = 0, k3_stride = 1) - 32-bit index arithmetic only;
 // phase 2 (in_list != NULL): grid = ceil(count / 256).  GROUP: the symmetry list is a group (checked on the host), so the
 // weight of an irreducible point is nsyms / |stabiliser| and phase 2 writes wsym itself (no phase 3).
 template <bool FAST, bool GROUP>
 __global__ void __launch_bounds__(256)
 symptr_filter_kernel(int N, int nsyms, int s0, int s1, const int* __restrict__ syms, const unsigned* __restrict__ in_list,
                      const unsigned* __restrict__ in_count, unsigned* __restrict__ out_list, unsigned* __restrict__ out_count,
-                     unsigned out_cap, int* __restrict__ overflow, int* __restrict__ wsym) {
+                     unsigned out_cap, int* __restrict__ overflow, int* __restrict__ wsym, int k3_lo, int k3_stride) {
     extern __shared__ int sy[];
     for (int t = threadIdx.x; t < 9 * nsyms; t += 256) sy[t] = syms[t];
     __syncthreads();
@@ -436,7 +439,7 @@ symptr_filter_kernel(int N, int nsyms, int s0, int s1, const int* __restrict__ s
     } else {
         const unsigned r = blockIdx.x * 256u + threadIdx.x;
         if (r < (unsigned)N * (unsigned)N) {
-            i3 = (int)blockIdx.y;
+            i3 = k3_lo + (int)blockIdx.y * k3_stride;
             i2 = (int)(r / (unsigned)N); i1 = (int)(r - (unsigned)i2 * (unsigned)N);
             idx = (unsigned)i3 * (unsigned)N * (unsigned)N + r;
             keep = true;

@@ -300,13 +300,21 @@ inline int mma_resolvent_plan(int n, long nk, int nw, long sm, long* ncta, int* 
 template <int NB, int W>
 inline void mma_launch_one(const double2* H, const double* wnode, long nk, int n, int nw, const double2* z, const double2* sigma,
                            int mode, double2* outp, int* errflag, long ncta, int kper, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(resolvent_mma_kernel<NB, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_set = true;
-    }
     size_t smem = (size_t)nw * W * sizeof(double2);
     resolvent_mma_kernel<NB, W><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
+}
+
+// dynamic shared memory above 48 KB is a per-device opt-in: called for the current device at context creation
+inline cudaError_t mma_resolvent_opt_in() {
+    cudaError_t e = cudaSuccess;
+    auto set = [&](const void* f) {
+        cudaError_t r = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (r != cudaSuccess && e == cudaSuccess) e = r;
+    };
+#define ABZ_MMA_OPT(NBX) { auto k8 = resolvent_mma_kernel<NBX, 8>; set((const void*)k8); auto k12 = resolvent_mma_kernel<NBX, 12>; set((const void*)k12); }
+    ABZ_MMA_OPT(1) ABZ_MMA_OPT(2) ABZ_MMA_OPT(3) ABZ_MMA_OPT(4)
+#undef ABZ_MMA_OPT
+    return e;
 }
 
 inline cudaError_t mma_resolvent_launch(const double2* H, const double* wnode, long nk, int n, int nw, const double2* z,

@@ -65,7 +65,8 @@ def _init_cacheval(cache):
         raise TypeError("GGR supports BZ parameters from load_bz")
     if bz.ndim != h.ndim:
         raise ValueError("variables in Fourier series don't match domain")
-    rule = cache.backend.make_rule(h, h.ndim, alg.npt, bz.syms, cache.shard.rank, cache.shard.nranks)
+    rule = cache.backend.make_rule(h, h.ndim, alg.npt, bz.syms, cache.shard.rank, cache.shard.nranks,
+                                   allreduce=cache.shard.allreduce if cache.shard.nranks > 1 else None)
     if len(rule) == 0:
         raise ValueError("GGR - no data in rule")
     rule.ggr_data(h.ndim, copy=False)

@@ -66,6 +66,11 @@ class Shard:
         return self._allreduce(arr)
 
 
+def _shard_allreduce(shard):
+    """the shard's allreduce for rule construction (node counts of a symmetry-reduced rule built plane-wise), None on one rank"""
+    return shard.allreduce if shard.nranks > 1 else None
+
+
 def torch_allreduce(device=None):
     """allreduce over torch.distributed (NCCL over NVLink on GPU ranks, gloo in the CPU tests)."""
     import torch
@@ -212,6 +217,8 @@ class _BoundIntegrand:
             H, k, w = rule.copy_out()
             return [np.sum(w * f.host_values(H, k[:, :f.s.ndim], p)) if H.shape[2] else 0.0 for p in self.plist]
         if self.is_eig:
+            if hasattr(rule, "eig_sum_batch"):      # every H(k) diagonalised once for all parameters
+                return list(rule.eig_sum_batch(f.f.kind, [tuple(b) for b in self.bound]))
             return [rule.eig_sum(f.f.kind, b) for b in self.bound]
         if self.fkind == _lib.F_TRACE_H:
             t = rule.resolvent_sum(None, None, _lib.F_TRACE_H)[0]
@@ -354,12 +361,12 @@ def _init_cacheval(cache):
     cv["std"] = (dom, salg, j, ns, ndim)
     if isinstance(salg, MonkhorstPack):
         # init_fourier_rule (src/fourier.jl:330-342): the rule (node set + device handles) is built at init
-        cv["rule"] = cache.backend.make_rule(f.s, ndim, salg.npt, salg.syms, cache.shard.rank, cache.shard.nranks)
+        cv["rule"] = cache.backend.make_rule(f.s, ndim, salg.npt, salg.syms, cache.shard.rank, cache.shard.nranks, allreduce=_shard_allreduce(cache.shard))
     elif isinstance(salg, AutoSymPTRJL):
         # AutoSymPTR.alloc_cache builds the first rule at init (src/fourier.jl:348-360)
         n0, dn = monkhorst_pack_schedule(salg.a, salg.nmin, salg.nmax, salg.n0, salg.dn)
         cv["schedule"] = (n0, dn)
-        cv["rules"] = [cache.backend.make_rule(f.s, ndim, n0, salg.syms, cache.shard.rank, cache.shard.nranks)]
+        cv["rules"] = [cache.backend.make_rule(f.s, ndim, n0, salg.syms, cache.shard.rank, cache.shard.nranks, allreduce=_shard_allreduce(cache.shard))]
     elif isinstance(salg, NestedQuad):
         if not isinstance(dom, (CubicLimits, TetrahedralLimits)):
             raise TypeError("NestedQuad needs iterated limits")
@@ -520,7 +527,7 @@ def _autosymptr(cache, bf, salg, atol, reltol, maxevals, ndim):
         while len(rules) <= i:
             prev = rules[-1]
             t0 = time.perf_counter()
-            rules.append(backend.make_rule(f.s, ndim, prev.npt + dn, salg.syms, shard.rank, shard.nranks))
+            rules.append(backend.make_rule(f.s, ndim, prev.npt + dn, salg.syms, shard.rank, shard.nranks, allreduce=_shard_allreduce(shard)))
             timing.append(("make_rule", prev.npt + dn, time.perf_counter() - t0))
         return rules[i]
 

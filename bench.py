@@ -129,14 +129,68 @@ def cpu_sample(threads=None, target_s=15.0):
     nodes = planes * rows * NPT
     return {"value": nodes / t, "unit": "k-points/s", "cores": cores, "kind": "port",
             "sample": f"{planes} k3-planes x {rows} k2-rows x {NPT} k1 = {nodes} k-points x {NW} freqs of the C4 workload in {t:.1f} s "
-                      f"(C/OpenMP restatement of the AutoBZCore 0.3.8 path, not Julia)"}, t
+                      f"(C/OpenMP restatement of the AutoBZCore 0.3.8 path, not Julia)",
+            "lapack_cross_check": lapack_resolvent_rate(orc, S, z, cores)}, t
 
 
-def other_configs(ctx):
-    """The other BASELINE.json configs (C2, C3, C5) through the public API on this GPU, a few seconds in total; reported
-    beside the headline under "other_configs" (parity for them lives in tests/, CPU baselines in tools/run_configs.py)."""
+def lapack_resolvent_rate(orc, S, z, cores, seconds=2.0):
+    """The per-(k, omega) work of the reference's integrand with LAPACK itself, as Julia's `inv(::Matrix)` does it (zgetrf + zgetri
+    through numpy.linalg.inv), on H(k) of the workload: one core, then scaled to the box's cores - printed beside the port's own
+    unblocked LU so that the CPU baseline is not flattered by the port's LU."""
+    try:
+        rng = np.random.default_rng(0)
+        Hk = np.moveaxis(orc.eval_points(S, rng.random((16, 3))), 2, 0)          # [16, n, n]
+        A = z[:, None, None, None] * np.eye(NORB)[None, None] - Hk[None]          # [nw, 16, n, n]
+        np.trace(np.linalg.inv(A[:4]), axis1=2, axis2=3)
+        cnt, t0 = 0, time.time()
+        while time.time() - t0 < seconds:
+            np.trace(np.linalg.inv(A), axis1=2, axis2=3)
+            cnt += A.shape[0] * A.shape[1]
+        r = cnt / (time.time() - t0)
+        return {"inverse_traces_per_s_one_core": r, "kpoints_per_s_scaled_to_cores": r / NW * cores,
+                "note": "numpy.linalg.inv (LAPACK zgesv-class) on 32x32 H(k) of the workload, Fourier interpolation not included"}
+    except Exception as e:          # a cross-check must never cost the baseline
+        return {"error": repr(e)}
+
+
+def oracle_plane_sum(orc, So, N, z, k3):
+    """the oracle's PTR sum over ONE k3 plane, k2 rows dealt to host threads (ctypes releases the GIL)"""
+    from concurrent.futures import ThreadPoolExecutor
+    nt = max(1, min(os.cpu_count() or 1, N))
+    bounds = [(i * N // nt, (i + 1) * N // nt) for i in range(nt)]
+    with ThreadPoolExecutor(nt) as ex:
+        parts = list(ex.map(lambda b: orc.ptr_sum(So, N, z, k3_lo=k3, k3_hi=k3 + 1, k2_lo=b[0], k2_hi=b[1], nthreads=1), bounds))
+    return sum(parts)
+
+
+def parity_check(ctx, S, H, lo, z, k3):
+    """Parity evidence carried by the bench line itself: one whole k3 plane of the timed workload (same series, same full-grid
+    rule interface and kernels as the timed steps) at 4 of the 128 frequencies, GPU against the CPU oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from autobz_b200 import _lib as L
+    orc.build()
+    zi = [0, NW // 3, (2 * NW) // 3, NW - 1]
+    z4 = np.ascontiguousarray(z[zi])
+    Rc = L.DeviceRule(ctx, S, NPT, k3_lo=k3, k3_hi=k3 + 1)
+    got = Rc.resolvent_sum(z4, scale=1.0 / NPT ** 3)
+    Rc.close()
+    t0 = time.time()
+    ref = oracle_plane_sum(orc, orc.Series(H, lo), NPT, z4, k3)
+    err = float(np.max(np.abs(got - ref) / np.abs(ref)))
+    return {"rel_err_vs_cpu": err, "tolerance": 1e-10, "what": f"k3 plane {k3} of the timed slab ({NPT * NPT} k-points, full-grid rule interface) at frequencies "
+            f"{zi} of the sweep, GPU sum vs CPU oracle (pivoted LU)", "gpu": [[float(v.real), float(v.imag)] for v in got],
+            "cpu": [[float(v.real), float(v.imag)] for v in ref], "cpu_seconds": round(time.time() - t0, 2)}
+
+
+def other_configs(ctx, shard=None, world=1):
+    """The other BASELINE.json configs (C2, C3, C5) through the public API, a few seconds in total; reported beside the headline
+    under "other_configs" (parity for them lives in tests/, CPU baselines in tools/run_configs.py).  With world > 1 every rank
+    takes part (k3 planes / outermost IAI nodes dealt to the ranks, one small allreduce per rule or outer step): the SAME problems
+    on N GPUs, i.e. strong scaling - the driver's scaling file then carries them for every N."""
     import autobz_b200 as ab
     out = []
+    kw = {} if shard is None else {"shard": shard}
     d = np.load(os.path.join(ROOT, "tests", "golden", "svo_hr.npz"))
     Hs, los, A = np.asfortranarray(d["H_R"]), tuple(int(x) for x in d["lo"]), d["A"]
     fs = ab.FourierSeries(Hs, period=1.0, lo=los, norb=3)
@@ -149,7 +203,7 @@ def other_configs(ctx):
         return r, t_best
 
     f2 = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=1e-2)
-    solver = ab.IntegralSolver(f2, ibz, ab.PTR(npt=400))
+    solver = ab.IntegralSolver(f2, ibz, ab.PTR(npt=400), **kw)
     ws = [{"omega": w} for w in np.linspace(11.0, 14.0, 64)]
     # the CPU baseline leaves the GPU idle for seconds: bring the clocks back before timing millisecond-sized solves
     t_warm = time.perf_counter()
@@ -157,22 +211,30 @@ def other_configs(ctx):
         ab.batchsolve(solver, ws)
     _, t = best(lambda: ab.batchsolve(solver, ws))
     nn = len(solver.cache.cacheval["rule"])
-    out.append({"config": "C2 SrVO3 Green's-function trace, PTR npt=400 on CubicSymIBZ, 64 freqs, eta=1e-2", "irreducible_kpoints": nn,
+    out.append({"config": "C2 SrVO3 Green's-function trace, PTR npt=400 on CubicSymIBZ, 64 freqs, eta=1e-2", "n_gpus": world, "irreducible_kpoints": nn,
                 "ms": 1e3 * t, "kpoints_per_s": nn / t, "k_omega_per_s": 64 * nn / t, "fbz_equivalent_kpoints_per_s": 400 ** 3 / t})
-    sol, t = best(lambda: ab.solve(ab.IntegralProblem(f2, ibz, {"omega": 12.5}), ab.EvalCounter(ab.AutoPTR(a=1e-2, nmin=50, nmax=1000)), abstol=1e-3), 4)
-    out.append({"config": "C2 SrVO3 AutoPTR(a=eta=1e-2) on CubicSymIBZ, omega=12.5, abstol=1e-3 (rule construction included)",
+    sol, t = best(lambda: ab.solve(ab.IntegralProblem(f2, ibz, {"omega": 12.5}), ab.EvalCounter(ab.AutoPTR(a=1e-2, nmin=50, nmax=1000)), abstol=1e-3, **kw), 4)
+    out.append({"config": "C2 SrVO3 AutoPTR(a=eta=1e-2) on CubicSymIBZ, omega=12.5, abstol=1e-3 (rule construction included)", "n_gpus": world,
                 "numevals": sol.numevals, "ms": 1e3 * t, "kpoints_per_s": sol.numevals / t})
     f3 = ab.FourierIntegrand(ab.dos_integrand, fs, 1e-4)
-    sol, t = best(lambda: ab.solve(ab.IntegralProblem(f3, ibz, 12.0), ab.EvalCounter(ab.IAI()), abstol=1e-3), 2)
-    out.append({"config": "C3 SrVO3 DOS via IAI, eta=1e-4, omega=12.0, abstol=1e-3", "numevals": sol.numevals, "s": t, "evals_per_s": sol.numevals / t})
+    sol, t = best(lambda: ab.solve(ab.IntegralProblem(f3, ibz, 12.0), ab.EvalCounter(ab.IAI()), abstol=1e-3, **kw), 2)
+    out.append({"config": "C3 SrVO3 DOS via IAI, eta=1e-4, omega=12.0, abstol=1e-3", "n_gpus": world, "numevals": sol.numevals, "s": t, "evals_per_s": sol.numevals / t})
     H5, lo5 = ab.synthetic.wannier_hamiltonian(64, 4, cubic=True)
     f5 = ab.FourierIntegrand(ab.EigenIntegrand("fermi_energy"), ab.FourierSeries(H5, period=1.0, lo=lo5, norb=64), 0.0, 0.5)
-    cache = ab.init(ab.IntegralProblem(f5, ab.load_bz(ab.CubicSymIBZ(), 2 * np.pi * np.eye(3))), ab.PTR(npt=96))
+    ibz5 = ab.load_bz(ab.CubicSymIBZ(), 2 * np.pi * np.eye(3))
+    cache = ab.init(ab.IntegralProblem(f5, ibz5), ab.PTR(npt=96), **kw)
     ab.solve_(cache)
     _, t = best(lambda: ab.solve_(cache))
     nn = len(cache.cacheval["rule"])
-    out.append({"config": "C5 norb=64 band-energy integrand (Hermitian eigenvalues) on CubicSymIBZ, PTR npt=96", "irreducible_kpoints": nn,
-                "ms": 1e3 * t, "kpoints_per_s": nn / t, "fbz_equivalent_kpoints_per_s": 96 ** 3 / t})
+    out.append({"config": "C5 norb=64 band-energy integrand (Hermitian eigenvalues) on CubicSymIBZ, PTR npt=96", "n_gpus": world, "irreducible_kpoints": nn,
+                "ms": 1e3 * t, "kpoints_per_s": nn / t, "fbz_equivalent_kpoints_per_s": 96 ** 3 / t,
+                "device_eig_ms": ctx.last_timings()[1], "device_eval_ms": ctx.last_timings()[0]})
+    cache.cacheval["rule"].close()
+    # BASELINE config 5 as written: AutoPTR on the symmetry-reduced IBZ, grids 48 -> 96 -> 144 (rule construction included)
+    alg5 = ab.EvalCounter(ab.AutoPTR(a=1.0, nmin=48, nmax=1000, n0=48.0, dn=48.0))
+    sol, t = best(lambda: ab.solve(ab.IntegralProblem(f5, ibz5), alg5, reltol=1e-12, maxiters=80000, **kw), 2)
+    out.append({"config": "C5 norb=64 band-energy integrand, AutoPTR 48 -> 96 -> 144 on CubicSymIBZ (rule construction included)", "n_gpus": world,
+                "numevals": sol.numevals, "ms": 1e3 * t, "kpoints_per_s": sol.numevals / t})
     return out
 
 
@@ -207,6 +269,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--algo", type=int, default=0, help="resolvent algorithm: 0 auto, 1 generic, 2 DMMA")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the GPU-vs-CPU parity check of one plane of the timed workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -250,8 +313,10 @@ def main():
     # ---------------- device-resident arm: H_R in HBM, rule built, time the sums
     S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
     R = L.DeviceRule(ctx, S, NPT, k3_lo=k3_lo, k3_hi=k3_hi)
+    # the step's one exchange: partial sums of the ranks' slabs meet in a 2 KB allreduce (NCCL over NVLink), inside the timed loop
+    step_allreduce = ab.torch_allreduce(torch.device("cuda", local)) if world > 1 else (lambda a: a)
     for _ in range(args.warmup):
-        R.resolvent_sum(z, scale=1.0 / NPT ** 3)
+        step_allreduce(R.resolvent_sum(z, scale=1.0 / NPT ** 3))
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ctx.launch_count
@@ -261,6 +326,7 @@ def main():
         part = R.resolvent_sum(z, scale=1.0 / NPT ** 3)
         a, b = ctx.last_timings()
         ev_eval += a; ev_mat += b
+        total = step_allreduce(part)
     barrier()
     t_dev = time.perf_counter() - t0
     launches = ctx.launch_count - l0
@@ -290,6 +356,9 @@ def main():
             sweep = {"error": repr(e)}
         finally:
             ctx.set_option(L.OPT_RESOLVENT_ALGO, args.algo)
+    check = None
+    if rank == 0 and not args.no_check:
+        check = parity_check(ctx, S, H, lo, z, k3_lo + planes // 2)
     R.close(); S.close()
 
     # ---------------- end-to-end arm through the public API with host buffers
@@ -337,6 +406,12 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e_max = float(te[0])
 
+    others = None
+    if not args.no_other_configs:
+        try:                            # collective at world > 1: every rank takes part
+            others = other_configs(ctx, shard if world > 1 else None, world)
+        except Exception as e:          # never lose the headline line to a secondary measurement
+            others = [{"error": repr(e)}]
     if rank == 0:
         total_nodes = nodes_rank * world * args.steps
         value = total_nodes / t_dev_max
@@ -357,19 +432,14 @@ def main():
         cb = None
         if not args.no_cpu_baseline:
             cb, _ = cpu_sample(target_s=args.ref_seconds)
-        others = None
-        if world == 1 and not args.no_other_configs:
-            try:
-                others = other_configs(ctx)
-            except Exception as e:      # never lose the headline line to a secondary measurement
-                others = [{"error": repr(e)}]
         line = {"metric": METRIC, "value": value, "unit": "k-points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"C4: synthetic Wannier H norb={NORB}, R in [-{RMAX},{RMAX}]^3 (M=17), PTR {NPT}^3 grid, {NW}-point frequency sweep; "
-                                       f"step = k3 slab of {planes} planes per rank (x{world} ranks; 8 ranks = whole grid)",
+                                       f"step = ONE k3 slab of {planes} planes per rank = {planes}/{NPT} of the grid per GPU per step (x{world} ranks; 8 ranks = the whole "
+                                       f"grid per step; the N=1 line is a 1/8-slab rate, equal to the full-grid rate by linearity of the k-sum)",
                            "kpoints_per_step": nodes_rank * world, "k_omega_evals_per_sec": value * NW,
-                           "l2": "inputs larger than L2 (H(k) chunk 1-4 GB per pass)", "parallelism": f"k3-slab x{world}",
+                           "l2": "inputs larger than L2 (H(k) chunk 1-4 GB per pass)", "parallelism": f"k3-slab x{world}", "exchange": "one allreduce of 128 complex partial sums per step inside the timed loop" if world > 1 else "none (1 rank)",
                            "resolvent_algo": args.algo, "device_event_ms_per_step": 1e3 * t_events_max / args.steps},
                 "roofline": roof, "cpu_baseline": cb,
                 "e2e": {"value": e2e_val, "unit": "k-points/s", "h2d_bytes_per_step": int(H.nbytes + z.nbytes), "d2h_bytes_per_step": int(NW * 16),
@@ -377,7 +447,10 @@ def main():
                         "phases_ms_per_timed_step": [dict(zip(("upload_and_rule", "batchsolve", "teardown", "device_eval", "device_matfun"),
                                                               [round(x, 2) for x in ph])) for ph in e2e_phases[-args.steps:]]},
                 "gpu_launches": int(launches), "clocks": clocks, "other_configs": others, "frequency_sweep_fast_path": sweep,
-                "check": {"G_first": [float(g[0].real), float(g[0].imag)]}}
+                "check": dict(check or {}, G_first=[float(g[0].real), float(g[0].imag)])}
+        if check is not None and not (check["rel_err_vs_cpu"] <= check["tolerance"]):
+            print(f"bench.py: parity check FAILED, no bench line printed: {json.dumps(check)}", file=sys.stderr, flush=True)
+            sys.exit(3)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -84,6 +84,7 @@ int32_t abz_ctx_last_timings(const abz_ctx* ctx, double* eval_ms, double* matfun
  * ndim < 3 series are passed with trailing M = 1, lo = 0. */
 int32_t abz_series_create(abz_ctx* ctx, const double* coeffs, int32_t is_complex, int32_t norb,
                           const int32_t M[3], const int32_t lo[3], const double period[3], abz_series_t* out);
+/* retires the handle; rules and nests built on the series keep its coefficients alive until they are destroyed themselves */
 int32_t abz_series_destroy(abz_ctx* ctx, abz_series_t s);
 
 /* ---- S1: rule construction -------------------------------------------------------------- */
@@ -109,7 +110,9 @@ int32_t abz_symptr_rule(abz_ctx* ctx, int32_t npt, int32_t nsyms, const int32_t*
 /* symptr_rule + FourierMonkhorstPack in one step, entirely on the device (src/fourier.jl:265-277): the dense
  * weight array never visits the host, the CSR node lists are compacted by a warp-per-row kernel.  Same node set,
  * order and weights as abz_symptr_rule followed by abz_rule_create_sym.  nirr_total (may be NULL) = length(rule)
- * over ALL k3 planes, whatever (k3_lo, k3_stride) selects for this rank. */
+ * over ALL k3 planes, whatever (k3_lo, k3_stride) selects for this rank.  With nirr_total == NULL the orbit weights are
+ * computed for the selected planes only (each grid point's orbit test is independent of the others): ranks that split the
+ * planes then share the construction work as well and add up their abz_rule_info node counts to get length(rule). */
 int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t s, int32_t npt, int32_t nsyms, const int32_t* syms, int32_t k3_lo,
                                int32_t k3_stride, abz_rule_t* out, int64_t* nirr_total);
 int32_t abz_rule_destroy(abz_ctx* ctx, abz_rule_t r);
@@ -136,6 +139,12 @@ int32_t abz_rule_resolvent_matrix_sum(abz_ctx* ctx, abz_rule_t r, int32_t nw, co
                                       double* out);
 /* out[0] = scale * sum_i w_i g(eigvals(H(k_i))), kind = ABZ_EIG_* */
 int32_t abz_rule_eig_sum(abz_ctx* ctx, abz_rule_t r, int32_t kind, const double* params, double scale, double* out);
+/* the same for nparams parameter sets at once (params = Float64[2, nparams], out = Float64[nparams]): every H(k) is diagonalised
+ * ONCE per call and all parameters are summed over its eigenvalues - the device analogue of the reference's parameter sweep over a
+ * shared cached grid (batchsolve, src/interfaces.jl:199-243).  On a materialised rule (abz_rule_materialize: the reference's cached
+ * rule) the eigenvalues themselves stay cached on the device, so later calls only re-sum. */
+int32_t abz_rule_eig_sum_batch(abz_ctx* ctx, abz_rule_t r, int32_t kind, int32_t nparams, const double* params, double scale,
+                               double* out);
 /* all eigenvalues, Float64[n, nnodes] ascending per node (GGR data pass, src/dos_ggr.jl:14-44) */
 int32_t abz_rule_eigvals(abz_ctx* ctx, abz_rule_t r, double* evals);
 

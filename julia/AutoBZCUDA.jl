@@ -241,10 +241,11 @@ comm_destroy!(ctx::Context) = check(ctx, ccall((:abz_comm_destroy, LIB), Int32, 
 # ---- S3: BatchIntegrand f!(y, x, p) for scattered k (src/batch.jl:4-20) -------------------------------
 function resolvent_batch!(y::Vector{ComplexF64}, x::Vector{SVector{3,Float64}}, ds::DeviceSeries, z::ComplexF64)
     resize!(y, length(x))
+    zz = Float64[real(z), imag(z)]
     GC.@preserve y x begin
         rc = ccall((:abz_points_resolvent, LIB), Int32,
                    (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                   ds.ctx.h, ds.h, length(x), Ptr{Float64}(pointer(x)), 0, 1, Ref(z), C_NULL, Ptr{Float64}(pointer(y)))
+                   ds.ctx.h, ds.h, length(x), Ptr{Float64}(pointer(x)), 0, 1, zz, C_NULL, Ptr{Float64}(pointer(y)))
     end
     check(ds.ctx, rc)
     return nothing
@@ -270,8 +271,9 @@ contract2!(n::DeviceNest, x2::Vector{Float64}, parent::Vector{Int64}, slot1::Vec
     check(n.ctx, ccall((:abz_nest_contract2, LIB), Int32, (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}), n.ctx.h, n.h, length(x2), x2, parent, slot1))
 function eval!(y::Vector{ComplexF64}, n::DeviceNest, x1::Vector{Float64}, slot1::Vector{Int64}, z::ComplexF64)
     resize!(y, length(x1))
-    check(n.ctx, ccall((:abz_nest_eval, LIB), Int32, (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Ptr{Int64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                       n.ctx.h, n.h, length(x1), x1, slot1, 0, Ref(z), C_NULL, Ptr{Float64}(pointer(y))))
+    zz = Float64[real(z), imag(z)]      # ComplexF64 as the two doubles the ABI takes (a Ref{ComplexF64} does not convert to Ptr{Float64})
+    GC.@preserve y check(n.ctx, ccall((:abz_nest_eval, LIB), Int32, (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Ptr{Int64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       n.ctx.h, n.h, length(x1), x1, slot1, 0, zz, C_NULL, Ptr{Float64}(pointer(y))))
     return y
 end
 
@@ -286,13 +288,16 @@ end
 # control flow as IteratedIntegration/QuadGK, run by the library's host engine.  lims::CubicLimits or TetrahedralLimits.
 # vkind 0: tr G, 1: -Im(tr G)/pi (aps_example.jl:30).  exchange: @cfunction(allreduce!, Int32, (Ptr{Float64}, Int64, Ptr{Cvoid}))
 # for multi-rank solves (outermost panel nodes dealt to ranks), or C_NULL to use the NCCL communicator of abz_comm_init.
-function iai_solve(n::DeviceNest, lkind::Integer, la::Vector{Float64}, lb, z::ComplexF64; vkind=0, abstol=0.0, reltol=0.0,
+# Tolerance defaults follow QuadGK / the reference (src/algorithms.jl:224-237): reltol = sqrt(eps) when abstol == 0, else 0.
+function iai_solve(n::DeviceNest, lkind::Integer, la::Vector{Float64}, lb, z::ComplexF64; vkind=0, abstol=0.0,
+                   reltol=(abstol == 0 ? sqrt(eps(Float64)) : 0.0),
                    maxiters=typemax(Int64) >> 1, device_leaves=true, rank=0, nranks=1, exchange=C_NULL)
     out = zeros(3); stats = zeros(Int64, 4)
+    zz = Float64[real(z), imag(z)]
     check(n.ctx, ccall((:abz_iai_solve_sharded, LIB), Int32,
                        (Ptr{Cvoid}, UInt64, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
                         Float64, Float64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}),
-                       n.ctx.h, n.h, lkind, la, lb === nothing ? C_NULL : lb, 0, vkind, Ref(z), C_NULL, C_NULL,
+                       n.ctx.h, n.h, lkind, la, lb === nothing ? C_NULL : lb, 0, vkind, zz, C_NULL, C_NULL,
                        abstol, reltol, maxiters, device_leaves ? 1 : 0, rank, nranks, exchange, C_NULL, out, stats))
     return IntegralSolution(vkind == 1 ? out[1] : complex(out[1], out[2]), out[3], true, Int(stats[1]))
 end

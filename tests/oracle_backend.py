@@ -179,7 +179,7 @@ class OracleNest:
 class OracleBackend:
     launch_count = 0
 
-    def make_rule(self, series, ndim, npt, syms, rank=0, nranks=1):
+    def make_rule(self, series, ndim, npt, syms, rank=0, nranks=1, allreduce=None):
         return OracleRule(series, ndim, npt, syms, rank, nranks)
 
     def make_nest(self, series, ndim, cap2, cap1):

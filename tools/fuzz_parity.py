@@ -26,6 +26,11 @@ for case in range(ncase):
     rmax = int(rng.integers(0, 3))
     N = int(rng.integers(1, 7 if n <= 32 else 5))
     nw = int(rng.choice([1, 2, 3, 9, 17]))
+    # a slice of the cases on grids with several 32-node phase tiles per (k2,k3) row (the multi-tile TMA pipeline of stage 1)
+    if n <= 8 and rng.integers(0, 5) == 0:
+        N = int(rng.integers(33, 101))
+    elif n <= 32 and rng.integers(0, 8) == 0:
+        N, nw = int(rng.integers(33, 49)), min(nw, 3)
     eta = float(rng.choice([0.3, 0.03, 2e-3]))
     H, lo = ab.synthetic.wannier_hamiltonian(n, rmax)
     ext = ab.synthetic.band_extent(H)

@@ -9,6 +9,19 @@ from autobz_b200 import _lib as L
 ctx = ab.default_context(0)
 syms = np.array(ab.cube_automorphisms(3), dtype=np.int32)
 z = np.array([0.3 + 0.2j, -0.4 + 0.1j, 0.9 + 0.3j])
+if "multitile" in sys.argv:
+    # stage 1 of the contraction with several phase tiles per row: the double-buffered TMA bulk copies and their mbarrier
+    # parity flips (N = 70: 3 tiles, the last one partial), full grid and a symmetric rule with rows longer than one tile
+    for n, rmax in ((4, 8), (32, 1)):
+        H, lo = ab.synthetic.wannier_hamiltonian(n, rmax, cubic=True)
+        S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+        for R in (L.DeviceRule(ctx, S, 70, k3_lo=3, k3_hi=4), L.DeviceRule(ctx, S, 70, syms=syms, k3_lo=0, k3_stride=35)):
+            R.resolvent_sum(z)
+            R.copy_out()
+            R.close()
+        S.close()
+    print("sanitize multitile cases done, launches:", ctx.launch_count)
+    sys.exit(0)
 for n, N in ((1, 5), (2, 5), (3, 6), (5, 4), (17, 3), (32, 3), (33, 3), (64, 2)):
     H, lo = ab.synthetic.wannier_hamiltonian(n, 1, cubic=True)
     S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
