@@ -20,6 +20,7 @@
 #include "abz_iai.cuh"
 #include "abz_kernels.cuh"
 #include "abz_resolvent_mma.cuh"
+#include "abz_resolvent_mma_team.cuh"
 #include "abz_resolvent_gjreg.cuh"
 
 using namespace abz;
@@ -510,7 +511,8 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
         return ABZ_OK;
     }
     // DMMA register-resident fast path (norb <= 32; unpivoted block elimination with growth monitoring)
-    bool use_mma = (ctx->resolvent_algo != 1 && ctx->resolvent_algo != 4) && !ctx->force_generic && mma_resolvent_supported(n);
+    bool use_mma = (ctx->resolvent_algo != 1 && ctx->resolvent_algo != 4) && !ctx->force_generic && mma_resolvent_supported(n) &&
+                   !(getenv("ABZ_MMA_TEAM") && atoi(getenv("ABZ_MMA_TEAM")) == 1 && n > 24);
     if (use_mma) {
         long ncta = 0; int kper_m = 1;
         if (mma_resolvent_plan(n, nk, nw, sm, &ncta, &kper_m) == 0) {
@@ -528,6 +530,33 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
         }
     }
     if (n > 64) return fail(ctx, ABZ_E_UNSUPPORTED, "norb > 64 is not supported by the resolvent kernels");
+    // DMMA block LU with the matrix shared by a team of 4 warps (32 < norb <= 64; unpivoted between blocks, growth-monitored like the
+    // one-warp kernel: the same flag makes the host rerun the call with the pivoted teams below).  ABZ_MMA_TEAM=1 also routes
+    // 24 < norb <= 32 through two-warp teams (measurement hook).
+    static const int team_env = getenv("ABZ_MMA_TEAM") ? atoi(getenv("ABZ_MMA_TEAM")) : 0;
+    const bool team_small = team_env == 1 && n > 24 && n <= 32;
+    if ((ctx->resolvent_algo == 0 || ctx->resolvent_algo == 2) && !ctx->force_generic && (mma_team_supported(n) || team_small) && team_env != -1) {
+        long ncta = 0; int kper_t = 1;
+        const size_t need = mma_team_smem((n + 7) / 8, nw);
+        if (need <= 110 * 1024) {
+            const long per_sm = team_small ? 8 : 2;
+            const long target = sm * per_sm;
+            kper_t = (int)std::max<long>(1, (nk + target - 1) / target);
+            ncta = (nk + kper_t - 1) / kper_t;
+            double2* dst = yout;
+            if (mode == 0) {
+                CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
+                dst = ctx->partial.as<double2>();
+            }
+            CU(ctx, mma_team_launch(H, wnode, nk, n, nw, z, sigma, mode, dst, ef, ncta, kper_t, ctx->stream));
+            ctx->launches++;
+            if (mode == 0) {
+                reduce_partials_kernel<<<nw, 256, 0, ctx->stream>>>(ctx->partial.as<double2>(), ncta, nw, 1.0, ctx->acc.as<double2>());
+                LAUNCH_CHECK(ctx, "reduce_partials_kernel");
+            }
+            return ABZ_OK;
+        }
+    }
     if (ctx->resolvent_algo != 4 && !(n <= 16 && ctx->resolvent_algo != 1)) {   // (n <= 16: a padded 32-row team wastes its lanes; measured crossover)
         // register-resident pivoted Gauss-Jordan: one team (1 or 4 warps) per matrix, grid = (node chunks, frequency chunks)
         const long target = (long)sm * gj_ctas_per_sm(n, false);   // one resident wave
@@ -642,6 +671,8 @@ cudaError_t opt_in_dynamic_smem() {
     ABZ_OPT_IN(iai_leaf_kernel<3>, 160 * 1024);
 #undef ABZ_OPT_IN
     cudaError_t r = mma_resolvent_opt_in();
+    if (r != cudaSuccess && e == cudaSuccess) e = r;
+    r = mma_team_opt_in();
     if (r != cudaSuccess && e == cudaSuccess) e = r;
     return e;
 }

@@ -133,18 +133,33 @@ ABZ_HD inline cplx post_value(int vkind, cplx y, cplx la, cplx lb) {
     return cadd_rn(t, lb);
 }
 
-// ---- iterated limits (IteratedIntegration.CubicLimits / TetrahedralLimits) ----------------------
+// ---- iterated limits (IteratedIntegration.CubicLimits / TetrahedralLimits / any AbstractIteratedLimits) ----------------------
+// kind 2 = general limits served by the caller (the reference's `segments` + `fixandeliminate`, e.g. the polyhedral IBZ of
+// ext/SymmetryReduceBZExt.jl:33-58): fn(dim, x_fixed, segs, maxseg, user) writes the ascending breakpoints of the variable of
+// `dim` (1-based, dim = ndim outermost) given the outer variables fixed so far (x_fixed[0] = outermost) and returns their number.
+typedef int32_t (*limits_fn)(int32_t dim, const double* x_fixed, double* segs, int32_t maxseg, void* user);
+constexpr int MAXSEG = 64;
 struct Limits {
-    int kind = 0, nd = 0;   // kind 0: x_d in [a_d, b_d];  1: 0 <= x_d <= a_d s, then s <- x_d / a_d
+    int kind = 0, nd = 0;   // kind 0: x_d in [a_d, b_d];  1: 0 <= x_d <= a_d s, then s <- x_d / a_d;  2: fn
     double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, s = 1.0;
-    void segments(double* lo, double* hi) const {
-        if (kind == 0) { *lo = a[nd - 1]; *hi = b[nd - 1]; }
-        else { *lo = 0.0; *hi = a[nd - 1] * s; }
+    limits_fn fn = nullptr; void* user = nullptr;
+    double fixed[3] = {0, 0, 0}; int nfixed = 0;
+    // breakpoints of the outermost remaining variable (limit_iterate / segments); false: the callback failed
+    bool segments(std::vector<double>& out) const {
+        out.clear();
+        if (kind == 0) { out.push_back(a[nd - 1]); out.push_back(b[nd - 1]); return true; }
+        if (kind == 1) { out.push_back(0.0); out.push_back(a[nd - 1] * s); return true; }
+        double buf[MAXSEG];
+        const int n = fn ? fn(nd, fixed, buf, MAXSEG, user) : -1;
+        if (n < 2 || n > MAXSEG) return false;
+        for (int i = 0; i < n; i++) { if (i > 0 && !(buf[i] >= buf[i - 1])) return false; out.push_back(buf[i]); }
+        return true;
     }
     Limits fix(double x) const {
         Limits r = *this;
         r.nd = nd - 1;
         if (kind == 1) r.s = x / a[nd - 1];
+        if (kind == 2 && nfixed < 3) r.fixed[r.nfixed++] = x;
         return r;
     }
 };
@@ -206,7 +221,7 @@ struct Round {
     }
 };
 
-enum { IAI_OK = 0, IAI_E_NAN = -4, IAI_E_ARENA = -2, IAI_E_STALL = -7 };
+enum { IAI_OK = 0, IAI_E_NAN = -4, IAI_E_ARENA = -2, IAI_E_STALL = -7, IAI_E_LIMITS = -8 };
 
 // Backend concept:  int lanes()                     number of rounds that may be in flight at once (>= 1);
 //                   int submit(int lane, Round&)    starts the queued inputs of one round (may return before the work is done);
@@ -236,10 +251,10 @@ public:
     std::string error;
 
     int run() {
-        double a, b;
-        lims_.segments(&a, &b);
+        std::vector<double> segs;
+        if (!lims_.segments(segs)) return limits_error();
         int root = new_integral(ndim_ - 1, lims_, atol_, -1, -1, -1, -1, 0);
-        int rc = start_segment(root, a, b, 0);
+        int rc = start_initial(root, segs);
         if (rc) return rc;
         int local_rc = IAI_OK;
         while (!done_) {
@@ -302,6 +317,7 @@ private:
         int level; Limits lims; double atol; int64_t slot; int pq, ppend, pi;   // parent integral / panel / node
         int lane;                                                              // the lane its rounds run in
         std::vector<Seg> heap; cplx I; double E; int64_t numevals; Seg popped, s1, s2; bool has1, has2;
+        int init_remaining;                                                    // initial segments still being evaluated
     };
     struct Item { int q, pend, i; int64_t slot; };
 
@@ -349,6 +365,21 @@ private:
         return IAI_OK;
     }
     void free_slot(int level, int64_t slot) { ((level == 2) ? free2_ : free1_).push_back(slot); }
+    int limits_error() {
+        error = "IAI: the limits callback failed (it must return at least 2 ascending breakpoints, at most 64)";
+        return IAI_E_LIMITS;
+    }
+    // do_quadgk's first pass: evalrule on every initial segment [segs[k], segs[k+1]]; panel k carries tag -k
+    int start_initial(int qi, const std::vector<double>& segs) {
+        const int ns = (int)segs.size() - 1;
+        ints_[qi].init_remaining = ns;
+        ints_[qi].heap.assign((size_t)ns, Seg{0.0, 0.0, 0.0, cplx{0.0, 0.0}});
+        for (int k = 0; k < ns; k++) {
+            int rc = start_segment(qi, segs[k], segs[k + 1], -k);
+            if (rc) return rc;
+        }
+        return IAI_OK;
+    }
     int nan_error(const Pend& p) {
         error = "integrand produced NaN/Inf in the interval (" + std::to_string(p.a) + ", " + std::to_string(p.b) + ")";
         return IAI_E_NAN;
@@ -370,9 +401,10 @@ private:
             if (shared && (spawn_counter_++ % nranks_) != rank_) continue;   // another rank owns this node
             const double x = gk_node(a, b, i);
             const Limits clims = ints_[qi].lims.fix(x);
-            double ca, cb;
-            clims.segments(&ca, &cb);
-            const double len = cb - ca;
+            std::vector<double> csegs;
+            if (!clims.segments(csegs)) return limits_error();
+            const double ca = csegs.front(), cb = csegs.back();
+            const double len = cb - ca;                       // len = segs[end] - segs[1] (src/fourier.jl:476)
             int64_t slot;
             int rc = alloc_slot(level, &slot);
             if (rc) return rc;
@@ -382,14 +414,14 @@ private:
             if (level == 2) { nx.c3_x.push_back(x); nx.c3_slot.push_back(slot); }
             else { nx.c2_x.push_back(x); nx.c2_parent.push_back(ints_[qi].slot); nx.c2_slot.push_back(slot); }
             const double catol = ints_[qi].atol / len;        // inner abstol = abstol/len (src/fourier.jl:479-480)
-            if (level == 1 && leaf_tasks_) {
+            if (level == 1 && leaf_tasks_ && csegs.size() == 2) {
                 q_task_[g].push_back(Item{qi, pend, i, slot});
                 nx.task_a.push_back(ca); nx.task_b.push_back(cb); nx.task_atol.push_back(catol);
                 nx.task_slot.push_back(slot);
                 continue;
             }
             int child = new_integral(level - 1, clims, catol, slot, qi, pend, i, g);
-            rc = start_segment(child, ca, cb, 0);
+            rc = start_initial(child, csegs);
             if (rc) return rc;
         }
         return IAI_OK;
@@ -462,10 +494,16 @@ private:
         if (!std::isfinite(Es)) return nan_error(p);
         Integral& q = ints_[qi];
         const Seg seg{Es, p.a, p.b, Is};
-        if (p.tag == 0) {
-            q.heap.clear(); q.heap.push_back(seg);
-            q.I = Is; q.E = Es; q.numevals = 15;
+        if (p.tag <= 0) {
+            // do_quadgk: I and E are left folds over the initial segments in their order; no subdivision when already converged
+            // (finish() sums the vector in that same order), else heapify! (DataStructures: percolate_down from the last parent)
+            q.heap[(size_t)(-p.tag)] = seg;
+            if (--q.init_remaining > 0) return IAI_OK;
+            q.I = q.heap[0].I; q.E = q.heap[0].E;
+            for (size_t k = 1; k < q.heap.size(); k++) { q.I = cplx{q.I.re + q.heap[k].I.re, q.I.im + q.heap[k].I.im}; q.E += q.heap[k].E; }
+            q.numevals = 15 * (int64_t)q.heap.size();
             if (q.numevals >= maxevals_ || q.E <= q.atol || q.E <= rtol_ * std::hypot(q.I.re, q.I.im)) return finish(qi);
+            for (size_t i = q.heap.size() / 2; i >= 1; i--) heap_percolate_down(q.heap, i, q.heap[i - 1]);
             return refine(qi);
         }
         if (p.tag == 1) { q.s1 = seg; q.has1 = true; } else { q.s2 = seg; q.has2 = true; }

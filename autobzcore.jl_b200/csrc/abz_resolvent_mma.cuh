@@ -103,7 +103,11 @@ __device__ __forceinline__ void inv8(double& xr0, double& xr1, double& xi0, doub
     }
 }
 
-template <int NB>
+// VAR 0: left-looking substitutions (V and M interleaved, one accumulation chain per block);
+// VAR 1: right-looking substitutions - a finished block of V (M) is turned into its fragment once and immediately applied to all
+//        rows above (below) it, so the block products of one step are independent (more DMMA chains in flight, one live fragment
+//        instead of the bV[] / bM[] arrays), and the fragments of M feed the trace as they are made.
+template <int NB, int VAR>
 __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], double (&R1)[NB][NB], double (&I0)[NB][NB],
                                                       double (&I1)[NB][NB], int lane, int& minpiv) {
     const int g = lane >> 2, q = lane & 3;
@@ -142,6 +146,44 @@ __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], doub
     for (int s = 0; s < NB; s++) {
         if (2 * q == g) { tr += R0[s][s]; ti += I0[s][s]; }
         if (2 * q + 1 == g) { tr += R1[s][s]; ti += I1[s][s]; }
+    }
+    if (VAR == 1) {
+        // V = U~^-1, columns right to left (column jv only reads X blocks of columns t < jv, still untouched)
+#pragma unroll
+        for (int jv = NB - 1; jv >= 1; jv--) {
+            const BFrag bD = to_bfrag(R0[jv][jv], R1[jv][jv], I0[jv][jv], I1[jv][jv], src0, src1, par);
+#pragma unroll
+            for (int iv = 0; iv < jv; iv++) {                            // V'_{iv,jv} = -X_{iv,jv} D_jv
+                double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
+                bmm<true>(cr0, cr1, ci0, ci1, R0[iv][jv], R1[iv][jv], I0[iv][jv], I1[iv][jv], bD);
+                R0[iv][jv] = cr0; R1[iv][jv] = cr1; I0[iv][jv] = ci0; I1[iv][jv] = ci1;
+            }
+#pragma unroll
+            for (int t = jv - 1; t >= 1; t--) {                          // V_{t,jv} is final: apply it to the rows above
+                const BFrag bV = to_bfrag(R0[t][jv], R1[t][jv], I0[t][jv], I1[t][jv], src0, src1, par);
+#pragma unroll
+                for (int iv = 0; iv < t; iv++)
+                    bmm<true>(R0[iv][jv], R1[iv][jv], I0[iv][jv], I1[iv][jv], R0[iv][t], R1[iv][t], I0[iv][t], I1[iv][t], bV);
+            }
+        }
+        // M = L~^-1, columns left to right; tr += tr(V_{jm,t} M_{t,jm}) as soon as M_{t,jm} is final
+#pragma unroll
+        for (int jm = 0; jm < NB - 1; jm++) {
+#pragma unroll
+            for (int im = jm + 1; im < NB; im++) {
+                R0[im][jm] = dneg(R0[im][jm]); R1[im][jm] = dneg(R1[im][jm]); I0[im][jm] = dneg(I0[im][jm]); I1[im][jm] = dneg(I1[im][jm]);
+            }
+#pragma unroll
+            for (int t = jm + 1; t < NB; t++) {
+                const BFrag b = to_bfrag(R0[t][jm], R1[t][jm], I0[t][jm], I1[t][jm], src0, src1, par);
+                tr += R0[jm][t] * b.r[0] - I0[jm][t] * b.i[0] + R1[jm][t] * b.r[1] - I1[jm][t] * b.i[1];
+                ti += R0[jm][t] * b.i[0] + I0[jm][t] * b.r[0] + R1[jm][t] * b.i[1] + I1[jm][t] * b.r[1];
+#pragma unroll
+                for (int im = t + 1; im < NB; im++)
+                    bmm<true>(R0[im][jm], R1[im][jm], I0[im][jm], I1[im][jm], R0[im][t], R1[im][t], I0[im][t], I1[im][t], b);
+            }
+        }
+        return make_double2(warp_sum(tr), warp_sum(ti));
     }
     // ---- V = U~^-1 (strict upper blocks, in place over X; columns right to left, rows bottom up) and
     //      M = L~^-1 (strict lower blocks, in place over L; columns left to right, rows top down).
@@ -188,11 +230,14 @@ __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], doub
 }
 
 constexpr int MMA_WARPS_MAX = 12;
+#ifndef ABZ_MMA_DEFAULT_VARIANT
+#define ABZ_MMA_DEFAULT_VARIANT 1    // measured on the C4 workload: 785.7 k vs 781.8 k k-points/s (profiles/r02_k3fast_variants.log)
+#endif
 
 // CTA c handles k-points [c*kper, (c+1)*kper) x all nw frequencies; warp w takes the (k, w) pairs
 // i = w, w + 8, ... of that chunk.  mode 0: outp[c*nw + w] = sum_k wnode_k tr ; mode 1: outp[k*nw + w] = tr
 // shared: acc[MMA_WARPS][nw] double2
-template <int NB, int MMA_WARPS>
+template <int NB, int MMA_WARPS, int VAR = 0>
 __global__ void __launch_bounds__(MMA_WARPS * 32, 1)
 resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ wnode, long nk, int n, int nw,
                      const double2* __restrict__ z, const double2* __restrict__ sigma, int kper, int mode,
@@ -240,7 +285,7 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
                                          max(__double2hiint(a1.x) & 0x7fffffff, __double2hiint(a1.y) & 0x7fffffff)));
             }
         int minhi = 0x7ff00000;
-        double2 t = warp_trace_inverse<NB>(R0, R1, I0, I1, lane, minhi);
+        double2 t = warp_trace_inverse<NB, VAR>(R0, R1, I0, I1, lane, minhi);
         t.x = -t.x - (double)npad; t.y = -t.y;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) amaxhi = max(amaxhi, __shfl_xor_sync(0xffffffffu, amaxhi, off));
@@ -297,11 +342,21 @@ inline int mma_resolvent_plan(int n, long nk, int nw, long sm, long* ncta, int* 
     return 0;
 }
 
+// substitution variant of the norb = 25..32 kernel (ABZ_MMA_VARIANT = 0 / 1, see warp_trace_inverse); smaller matrices use 0
+inline int mma_resolvent_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ABZ_MMA_VARIANT"); v = e ? (atoi(e) == 1 ? 1 : 0) : ABZ_MMA_DEFAULT_VARIANT; }
+    return v;
+}
+
 template <int NB, int W>
 inline void mma_launch_one(const double2* H, const double* wnode, long nk, int n, int nw, const double2* z, const double2* sigma,
                            int mode, double2* outp, int* errflag, long ncta, int kper, cudaStream_t stream) {
     size_t smem = (size_t)nw * W * sizeof(double2);
-    resolvent_mma_kernel<NB, W><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
+    if (NB == 4 && mma_resolvent_variant() == 1)
+        resolvent_mma_kernel<NB, W, (NB == 4 ? 1 : 0)><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
+    else
+        resolvent_mma_kernel<NB, W, 0><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
 }
 
 // dynamic shared memory above 48 KB is a per-device opt-in: called for the current device at context creation
@@ -311,9 +366,10 @@ inline cudaError_t mma_resolvent_opt_in() {
         cudaError_t r = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (r != cudaSuccess && e == cudaSuccess) e = r;
     };
-#define ABZ_MMA_OPT(NBX) { auto k8 = resolvent_mma_kernel<NBX, 8>; set((const void*)k8); auto k12 = resolvent_mma_kernel<NBX, 12>; set((const void*)k12); }
+#define ABZ_MMA_OPT(NBX) { auto k8 = resolvent_mma_kernel<NBX, 8, 0>; set((const void*)k8); auto k12 = resolvent_mma_kernel<NBX, 12, 0>; set((const void*)k12); }
     ABZ_MMA_OPT(1) ABZ_MMA_OPT(2) ABZ_MMA_OPT(3) ABZ_MMA_OPT(4)
 #undef ABZ_MMA_OPT
+    { auto k8 = resolvent_mma_kernel<4, 8, 1>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 1>; set((const void*)k12); }
     return e;
 }
 

@@ -721,10 +721,17 @@ int orc_quadgk_test(int kind, double p0, double p1, double a, double b, double a
  * integrand: vkind 0 = complex trace tr[(z-H-Sigma)^-1]; 1 = DOS -Im(tr)/pi (aps_example.jl:30);
  *            2 = lin[0]*tr H + lin[1] (test/fourier.jl:41)
  * ------------------------------------------------------------------------------------------- */
+/* general iterated limits (IteratedIntegration.AbstractIteratedLimits: segments + fixandeliminate, e.g. the polyhedral IBZ of
+ * ext/SymmetryReduceBZExt.jl:33-58): breakpoints of the variable of `dim` (1-based: dim = ndim is the outermost) given the outer
+ * variables already fixed, x_fixed[0] = outermost; returns the number of breakpoints (>= 2, ascending) or a negative error */
+typedef int (*orc_limits_fn)(int dim, const double* x_fixed, double* segs, int maxseg, void* user);
+#define ORC_MAXSEG 64
+
 typedef struct {
     orc_series s;
     int dim;                   /* number of variables: 1..3 */
     int lkind; double la[3], lb[3];
+    orc_limits_fn lfn; void* luser;   /* lkind 2 */
     int vkind; zc z; const zc* sigma; double lin[2];
     double atol, rtol; long maxevals;
     zc* c[3];                  /* c[2]: after contracting dim3 (rows n^2 M1 M2); c[1]: after dim2 */
@@ -743,18 +750,25 @@ static void iai_limits(const orc_iai_t* q, int level /*0-based variable index*/,
     else *b = q->la[level] * (q->x[level + 1] / q->la[level + 1]);
 }
 
+/* breakpoints of the variable of `level` (0-based) given q->x[level+1 ..]: returns their number (>= 2) */
+static int iai_segments(const orc_iai_t* q, int level, double* segs) {
+    if (q->lkind != 2) { iai_limits(q, level, &segs[0], &segs[1]); return 2; }
+    double xf[3];
+    int nf = 0;
+    for (int d = q->dim - 1; d > level; d--) xf[nf++] = q->x[d];
+    int n = q->lfn(level + 1, xf, segs, ORC_MAXSEG, q->luser);
+    return n;
+}
+
 static zc iai_level(double x, void* ctx, int* err);
 
 typedef struct { orc_iai_t* q; int level; } iai_ctx;
 
-static zc iai_integrate(orc_iai_t* q, int level, double atol, int* err) {
-    double a, b;
-    iai_limits(q, level, &a, &b);
-    double segs[2] = {a, b};
+static zc iai_integrate(orc_iai_t* q, int level, double atol, const double* segs, int nbreaks, int* err) {
     iai_ctx c = {q, level};
     zc Iv = 0; double E = 0; long ne = 0;
     q->cur_atol[level] = atol;
-    int rc = orc_quadgk(iai_level, &c, segs, 1, atol, q->rtol, q->maxevals, &Iv, &E, &ne, &q->heaps[level]);
+    int rc = orc_quadgk(iai_level, &c, segs, nbreaks - 1, atol, q->rtol, q->maxevals, &Iv, &E, &ne, &q->heaps[level]);
     if (rc) *err = rc;
     return Iv;
 }
@@ -786,27 +800,42 @@ static zc iai_level(double x, void* ctx, int* err) {
     long rows = nn;
     for (int d = 0; d < level; d++) rows *= s->M[d];
     orc_contract(src, rows, s->M[level], s->lo[level], s->period[level], x, q->c[level]);
-    double a, b;
-    iai_limits(q, level - 1, &a, &b);
-    double len = b - a;
+    double segs[ORC_MAXSEG];
+    int nb = iai_segments(q, level - 1, segs);
+    if (nb < 2) { *err = ORC_E_ARG; return 0.0; }
+    double len = segs[nb - 1] - segs[0];          /* len = segs[end] - segs[1] (src/fourier.jl:476,479) */
     /* save/restore: the inner integration reuses heaps of lower levels only */
     double my_atol = q->cur_atol[level];
-    zc v = iai_integrate(q, level - 1, my_atol / len, err);
+    zc v = iai_integrate(q, level - 1, my_atol / len, segs, nb, err);
     q->cur_atol[level] = my_atol;
     return v;
 }
+
+int orc_iai_general(const double* coeffs, int n, int dim, const int* M, const int* lo, const double* period,
+            int lkind, const double* la, const double* lb, orc_limits_fn lfn, void* luser,
+            int vkind, const double* z, const double* sigma, const double* lin,
+            double atol, double rtol, long maxevals, double* out /* re, im, E */, long* numevals);
 
 int orc_iai(const double* coeffs, int n, int dim, const int* M, const int* lo, const double* period,
             int lkind, const double* la, const double* lb,
             int vkind, const double* z, const double* sigma, const double* lin,
             double atol, double rtol, long maxevals, double* out /* re, im, E */, long* numevals) {
+    return orc_iai_general(coeffs, n, dim, M, lo, period, lkind, la, lb, NULL, NULL, vkind, z, sigma, lin, atol, rtol, maxevals, out, numevals);
+}
+
+int orc_iai_general(const double* coeffs, int n, int dim, const int* M, const int* lo, const double* period,
+            int lkind, const double* la, const double* lb, orc_limits_fn lfn, void* luser,
+            int vkind, const double* z, const double* sigma, const double* lin,
+            double atol, double rtol, long maxevals, double* out /* re, im, E */, long* numevals) {
     if (dim < 1 || dim > 3) return ORC_E_ARG;
+    if (lkind == 2 && !lfn) return ORC_E_ARG;
     orc_iai_t q; memset(&q, 0, sizeof(q));
+    q.lfn = lfn; q.luser = luser;
     int Mx[3] = {1, 1, 1}, lox[3] = {0, 0, 0}; double px[3] = {1, 1, 1};
     for (int d = 0; d < dim; d++) { Mx[d] = M[d]; lox[d] = lo[d]; px[d] = period[d]; }
     orc_series_fill(&q.s, coeffs, n, Mx, lox, px);
     q.dim = dim; q.lkind = lkind;
-    for (int d = 0; d < dim; d++) { q.la[d] = la[d]; q.lb[d] = lb ? lb[d] : 0.0; }
+    for (int d = 0; d < dim; d++) { q.la[d] = la ? la[d] : 0.0; q.lb[d] = lb ? lb[d] : 0.0; }
     q.vkind = vkind; q.z = z ? z[0] + IU * z[1] : 0.0; q.sigma = (const zc*)sigma;
     q.lin[0] = lin ? lin[0] : 1.0; q.lin[1] = lin ? lin[1] : 0.0;
     q.atol = atol; q.rtol = rtol; q.maxevals = maxevals;
@@ -816,13 +845,12 @@ int orc_iai(const double* coeffs, int n, int dim, const int* M, const int* lo, c
     q.c[2] = (zc*)malloc(sizeof(zc) * nn * Mx[0] * Mx[1]);
     q.work = (zc*)malloc(sizeof(zc) * (nn + n)); q.piv = (int*)malloc(sizeof(int) * n);
     int err = 0;
-    double a, b;
-    iai_limits(&q, dim - 1, &a, &b);
-    double segs[2] = {a, b};
+    double segs[ORC_MAXSEG];
+    int nb = iai_segments(&q, dim - 1, segs);
     iai_ctx c = {&q, dim - 1};
     zc Iv = 0; double E = 0; long ne = 0;
     q.cur_atol[dim - 1] = atol;
-    int rc = orc_quadgk(iai_level, &c, segs, 1, atol, rtol, maxevals, &Iv, &E, &ne, &q.heaps[dim - 1]);
+    int rc = nb < 2 ? ORC_E_ARG : orc_quadgk(iai_level, &c, segs, nb - 1, atol, rtol, maxevals, &Iv, &E, &ne, &q.heaps[dim - 1]);
     out[0] = creal(Iv); out[1] = cimag(Iv); out[2] = E;
     *numevals = q.numevals;
     for (int d = 0; d < 3; d++) { free(q.c[d]); free(q.heaps[d].v); }

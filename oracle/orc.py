@@ -212,6 +212,52 @@ def iai(s, dim, lkind, la, lb=None, vkind=0, z=0.0, sigma=None, lin=(1.0, 0.0), 
     return complex(out[0], out[1]), out[2], int(ne[0])
 
 
+LIMITS_FN = C.CFUNCTYPE(C.c_int, C.c_int, c_dp, c_dp, C.c_int, C.c_void_p)
+
+
+def limits_callback(lims):
+    """ctypes callback (orc_limits_fn) that serves `segments(fixandeliminate(...))` of a Python limits object with
+    .segments() -> breakpoints and .fix(x) -> inner limits (the protocol of autobz_b200.bz)"""
+    def fn(dim, xf, segs, maxseg, user):
+        try:
+            cur = lims
+            for k in range(lims.ndim - dim):
+                cur = cur.fix(xf[k])
+            sg = [float(v) for v in cur.segments()]
+            if len(sg) > maxseg or len(sg) < 2:
+                return -1
+            for i, v in enumerate(sg):
+                segs[i] = v
+            return len(sg)
+        except Exception:
+            return -2
+    return LIMITS_FN(fn)
+
+
+def iai_general(s, dim, lims, vkind=0, z=0.0, sigma=None, lin=(1.0, 0.0), atol=0.0, rtol=None, maxevals=2 ** 62):
+    """orc_iai over general iterated limits (several breakpoints per level, fixandeliminate through a callback).
+    Returns (I, E, numevals)."""
+    if rtol is None:
+        rtol = np.sqrt(np.finfo(float).eps) if atol == 0 else 0.0
+    zz = _z(z)
+    sgp = None
+    if sigma is not None:
+        sg = np.asfortranarray(np.asarray(sigma, dtype=np.complex128))
+        sgp = _dp(sg)
+    linv = np.ascontiguousarray(np.asarray(lin, dtype=np.float64))
+    out = np.zeros(3)
+    ne = (C.c_long * 1)(0)
+    cb = limits_callback(lims)
+    f = lib().orc_iai_general
+    f.argtypes = [c_dp, C.c_int, C.c_int, C.c_int * 3, C.c_int * 3, C.c_double * 3, C.c_int, c_dp, c_dp, LIMITS_FN, C.c_void_p,
+                  C.c_int, c_dp, c_dp, c_dp, C.c_double, C.c_double, C.c_long, c_dp, C.POINTER(C.c_long)]
+    rc = f(_dp(s.c), s.n, dim, _i3(s.M), _i3(s.lo), _d3(s.period), 2, None, None, cb, None, vkind, _dp(zz), sgp, _dp(linv),
+           atol, rtol, maxevals, _dp(out), ne)
+    if rc:
+        raise FloatingPointError(f"oracle: error {rc} (NaN/Inf in integrand or bad limits)")
+    return complex(out[0], out[1]), out[2], int(ne[0])
+
+
 def ggr_data(s, ndim, N, wsym=None):
     """get_ggr_data (src/dos_ggr.jl:14-44): (weights [nnodes], energies [nnodes, n], velocities [nnodes, ndim, n])"""
     nmax = N ** ndim

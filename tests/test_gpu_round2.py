@@ -197,3 +197,53 @@ def test_several_contexts_in_one_process(orc):
         R.close(); S.close()
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("n", [33, 40, 47, 48, 56, 63, 64])
+def test_dmma_team_resolvent_vs_oracle(ctx, orc, n):
+    """32 < norb <= 64 through the default algorithm = the DMMA block LU shared by a team of 4 warps
+    (csrc/abz_resolvent_mma_team.cuh): rule sums (with and without a matrix self-energy, 130 frequencies so that a team walks
+    several matrices), per-point values, against the oracle's pivoted LU and the pivoted Gauss-Jordan teams (<= 1e-10)."""
+    N = 4
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 1)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    So = orc.Series(H, lo)
+    ext = ab.synthetic.band_extent(H)
+    rng = np.random.default_rng(n)
+    z = np.concatenate([rng.uniform(-ext, ext, 127) + 0.02j * ext, rng.uniform(-0.5 * ext, 0.5 * ext, 3) + 2e-3j * ext])
+    sig = 0.05 * ext * (rng.standard_normal((n, n, z.size)) + 1j * rng.standard_normal((n, n, z.size))) - 0.1j * ext * np.eye(n)[:, :, None]
+    R = L.DeviceRule(ctx, S, N)
+    l0 = ctx.launch_count
+    got = R.resolvent_sum(z, scale=1 / N ** 3)
+    assert ctx.launch_count - l0 <= 6           # stages 3, 2, 1 + ONE resolvent launch + reduction: no pivoted rerun
+    assert rel(got, orc.ptr_sum(So, N, z)) < 1e-10
+    assert rel(R.resolvent_sum(z[:9], sigma=sig[:, :, :9], scale=1 / N ** 3), orc.ptr_sum(So, N, z[:9], sigma=sig[:, :, :9])) < 1e-10
+    ctx.set_option(L.OPT_RESOLVENT_ALGO, 1)
+    try:
+        assert rel(got, R.resolvent_sum(z, scale=1 / N ** 3)) < 1e-10
+    finally:
+        ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
+    kp = rng.random((11, 3))
+    assert rel(S.points_resolvent(kp, z[:5]), orc.resolvent_trace_batch(orc.eval_points(So, kp), z[:5])) < 1e-10
+    R.close(); S.close()
+
+
+@pytest.mark.parametrize("n", [33, 64])
+def test_dmma_team_resolvent_falls_back_to_pivoting(ctx, orc, n):
+    """matrices that need row exchanges (zero diagonal, z ~ 0) through the DEFAULT algorithm: the team kernel's pivot monitor
+    raises its flag and the call is rerun with the pivoted teams - the answer is the oracle's"""
+    rng = np.random.default_rng(200 + n)
+    c = np.zeros((n, n, 3, 1, 1), complex)
+    for m in range(3):
+        a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        np.fill_diagonal(a, 0.0)
+        c[:, :, m, 0, 0] = a
+    c[:, :, 2, 0, 0] = c[:, :, 0, 0, 0].conj().T
+    c[:, :, 1, 0, 0] = c[:, :, 1, 0, 0] + c[:, :, 1, 0, 0].conj().T
+    lo = (-1, 0, 0)
+    S = L.DeviceSeries(ctx, c, lo, (1.0,) * 3)
+    So = orc.Series(c, lo)
+    z = np.array([1e-9j, 0.3 + 1e-9j, -0.7 + 0.05j])
+    R = L.DeviceRule(ctx, S, 4)
+    assert rel(R.resolvent_sum(z, scale=1 / 64), orc.ptr_sum(So, 4, z)) < 1e-10
+    R.close(); S.close()
