@@ -8,8 +8,8 @@ from ._lib import AutoBZCudaError, SingularIntegrandError  # noqa: F401
 from .algorithms import (IAI, PTR, PTR_IAI, TAI, AbsoluteEstimate, AutoPTR, AutoPTR_IAI, AutoSymPTRJL, AuxQuadGKJL, EvalCounter, MonkhorstPack,  # noqa: F401
                          NestedQuad)
 from .backend import DeviceBackend, default_context  # noqa: F401
-from .bz import (FBZ, IBZ, AbstractSymRep, CubicLimits, CubicSymIBZ, FunctionRep, InversionSymIBZ, SymmetricBZ, SymRep,  # noqa: F401
-                 TetrahedralLimits, TrivialRep, UnknownRep, cube_automorphisms, load_bz, nsyms, symmetrize)
+from .bz import (FBZ, IBZ, AbstractSymRep, CubicLimits, CubicSymIBZ, FunctionRep, InversionSymIBZ, PolygonLimits, PolyhedronLimits,  # noqa: F401
+                 SegmentedLimits, SymmetricBZ, SymRep, TetrahedralLimits, TrivialRep, UnknownRep, cube_automorphisms, load_bz, nsyms, symmetrize)
 from .dos import GGR, DOSCache, DOSProblem, DOSSolution  # noqa: F401
 from .fourier import (AffineTraceIntegrand, BatchIntegrand, DOSIntegrand, EigenIntegrand, FourierIntegrand, FourierSeries,  # noqa: F401
                       FourierValue, GlocIntegrand, NestedBatchIntegrand, TrGlocIntegrand, dos_integrand, gloc_integrand, gloc_trace_integrand)

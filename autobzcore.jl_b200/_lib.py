@@ -24,7 +24,7 @@ EXPORTS = [
     "abz_ctx_last_timings", "abz_series_create", "abz_series_destroy", "abz_rule_create_full", "abz_rule_create_sym", "abz_rule_create_nodes",
     "abz_symptr_rule", "abz_rule_create_symptr", "abz_rule_destroy", "abz_rule_info", "abz_rule_materialize", "abz_rule_copy_out",
     "abz_rule_resolvent_sum", "abz_rule_resolvent_matrix_sum", "abz_rule_eig_sum", "abz_rule_eig_sum_batch", "abz_rule_eigvals", "abz_rule_ggr_data", "abz_rule_ggr_sum", "abz_points_eval", "abz_points_resolvent",
-    "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval", "abz_nest_eval_h", "abz_iai_solve", "abz_iai_solve_sharded",
+    "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval", "abz_nest_eval_h", "abz_iai_solve", "abz_iai_solve_sharded", "abz_iai_solve_general",
     "abz_comm_unique_id", "abz_comm_init", "abz_allreduce_sum", "abz_comm_destroy",
 ]
 
@@ -42,6 +42,7 @@ class SingularIntegrandError(AutoBZCudaError, FloatingPointError):
 _lib = None
 c_dp = C.POINTER(C.c_double)
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int32, C.POINTER(C.c_double), C.c_int64, C.c_void_p)   # abz_exchange_fn
+LIMITS_FN = C.CFUNCTYPE(C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.c_void_p)   # abz_limits_fn
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 
@@ -94,6 +95,8 @@ def load():
     lib.abz_iai_solve.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, C.c_double,
                                   C.c_double, C.c_int64, C.c_int32, c_dp, c_i64p]
     lib.abz_iai_solve_sharded.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, C.c_double,
+                                          C.c_double, C.c_int64, C.c_int32, C.c_int32, C.c_int32, EXCHANGE_FN, C.c_void_p, c_dp, c_i64p]
+    lib.abz_iai_solve_general.argtypes = [C.c_void_p, C.c_uint64, LIMITS_FN, C.c_void_p, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, C.c_double,
                                           C.c_double, C.c_int64, C.c_int32, C.c_int32, C.c_int32, EXCHANGE_FN, C.c_void_p, c_dp, c_i64p]
     lib.abz_comm_unique_id.argtypes = [C.c_void_p]
     lib.abz_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
@@ -413,11 +416,11 @@ class DeviceNest:
         return H
 
     def iai_solve(self, lkind, la, lb, fkind, vkind, z, sigma, lin, atol, rtol, maxevals, device_leaves=True, rank=0, nranks=1,
-                  allreduce=None):
+                  allreduce=None, limits=None):
         """abz_iai_solve(_sharded): the whole nested adaptive solve with the control flow on the library's host side.
         nranks > 1: outermost panel nodes dealt round-robin to the ranks; `allreduce(np.ndarray) -> np.ndarray` sums over
         the ranks (None = NCCL on the ctx communicator).  Returns (I complex, E, numevals, rounds, launches)."""
-        la_ = np.ascontiguousarray(la, dtype=np.float64)
+        la_ = None if la is None else np.ascontiguousarray(la, dtype=np.float64)
         lb_ = None if lb is None else np.ascontiguousarray(lb, dtype=np.float64)
         zz = _cz(0j if z is None else z)
         n = self.series.n
@@ -440,10 +443,33 @@ class DeviceNest:
                 return -1
 
         xfn = EXCHANGE_FN(_xchg) if (nranks > 1 and allreduce is not None) else EXCHANGE_FN(0)
-        rc = self.ctx.lib.abz_iai_solve_sharded(self.ctx.h, self.h, int(lkind), _dp(la_), _dp(lb_), int(fkind), int(vkind), _dp(zz),
-                                                _dp(sg), _dp(ln), float(atol), float(rtol), int(min(maxevals, 2 ** 62)),
-                                                IAI_DEVICE_LEAVES if device_leaves else 0, int(rank), int(nranks), xfn, None,
-                                                _dp(out), stats.ctypes.data_as(c_i64p))
+        flags = IAI_DEVICE_LEAVES if device_leaves else 0
+        if limits is not None:
+            # general iterated limits (abz_iai_solve_general): `limits` has .ndim, .segments() -> breakpoints and .fix(x) -> inner limits
+            # (segments / fixandeliminate of the reference's AbstractIteratedLimits); the library asks for the breakpoints of one level
+            def _lims(dim, xf, segs, maxseg, user):
+                try:
+                    cur = limits
+                    for k in range(limits.ndim - dim):
+                        cur = cur.fix(xf[k])
+                    sg_ = [float(v) for v in cur.segments()]
+                    if not 2 <= len(sg_) <= maxseg:
+                        raise ValueError(f"limits returned {len(sg_)} breakpoints (2 ... {maxseg} supported)")
+                    for i, v in enumerate(sg_):
+                        segs[i] = v
+                    return len(sg_)
+                except Exception as e:      # never let an exception cross the C boundary
+                    err.append(e)
+                    return -1
+
+            lfn = LIMITS_FN(_lims)
+            rc = self.ctx.lib.abz_iai_solve_general(self.ctx.h, self.h, lfn, None, int(fkind), int(vkind), _dp(zz), _dp(sg), _dp(ln),
+                                                    float(atol), float(rtol), int(min(maxevals, 2 ** 62)), flags, int(rank), int(nranks),
+                                                    xfn, None, _dp(out), stats.ctypes.data_as(c_i64p))
+        else:
+            rc = self.ctx.lib.abz_iai_solve_sharded(self.ctx.h, self.h, int(lkind), _dp(la_), _dp(lb_), int(fkind), int(vkind), _dp(zz),
+                                                    _dp(sg), _dp(ln), float(atol), float(rtol), int(min(maxevals, 2 ** 62)), flags,
+                                                    int(rank), int(nranks), xfn, None, _dp(out), stats.ctypes.data_as(c_i64p))
         if err:
             raise err[0]
         self.ctx.check(rc)

@@ -60,6 +60,125 @@ class TetrahedralLimits:
         return tuple(reversed(pt))
 
 
+class SegmentedLimits:
+    """Iterated limits with several breakpoints per variable, independent of the outer variables: x_d runs over the segments
+    [s_d[0], s_d[1]], [s_d[1], s_d[2]], ... (a PuncturedInterval per level, src/fourier.jl:395,500; IteratedIntegration.CubicLimits is
+    the one-segment case).  Every 1-D integral starts from all of its segments, as QuadGK does."""
+
+    def __init__(self, *breaks):
+        self.breaks = tuple(tuple(float(x) for x in b) for b in breaks)
+        for b in self.breaks:
+            if len(b) < 2 or any(y < x for x, y in zip(b, b[1:])):
+                raise ValueError("every level needs at least two ascending breakpoints")
+
+    @property
+    def ndim(self):
+        return len(self.breaks)
+
+    def segments(self):
+        return self.breaks[-1]
+
+    def fix(self, x):
+        return SegmentedLimits(*self.breaks[:-1])
+
+    def interior_point(self):
+        return tuple((b[0] + b[-1]) / 2 for b in self.breaks)
+
+
+class PolyhedronLimits:
+    """Iterated limits of a convex polyhedron (3-d) given by its vertices - the shape of the reference's IBZ limits
+    (`Polyhedron3` / `Polygon2` of ext/SymmetryReduceBZExt.jl:33-58: `segments` = the distinct z (y) coordinates of the vertices,
+    `fixandeliminate` = the polygon of the slice at z, then the x-interval of the slice at y).  The geometry of the IBZ itself
+    (SymmetryReduceBZ.jl) is out of scope; this class accepts its OUTPUT, a vertex list in lattice coordinates."""
+
+    def __init__(self, vertices, tol=None):
+        from scipy.spatial import ConvexHull
+        v = np.asarray(vertices, dtype=float)
+        if v.ndim != 2 or v.shape[1] != 3 or v.shape[0] < 4:
+            raise ValueError("vertices must be [nvert >= 4, 3]")
+        hull = ConvexHull(v)
+        self.vert = v[hull.vertices]
+        edges = set()
+        for simplex in hull.simplices:
+            for a in range(3):
+                i, j = sorted((int(simplex[a]), int(simplex[(a + 1) % 3])))
+                edges.add((i, j))
+        self._edges = [(v[i], v[j]) for i, j in sorted(edges)]
+        self.tol = np.sqrt(np.finfo(float).eps) if tol is None else tol
+
+    ndim = 3
+
+    @staticmethod
+    def _unique_sorted(vals, tol):
+        out = []
+        for x in sorted(float(t) for t in vals):
+            if not out or abs(x - out[-1]) > tol * max(1.0, abs(x)):
+                out.append(x)
+        return tuple(out)
+
+    def segments(self):
+        return self._unique_sorted(self.vert[:, 2], self.tol)
+
+    def fix(self, z):
+        pts = []
+        for p, q in self._edges:
+            dz = q[2] - p[2]
+            if abs(dz) <= 1e-300:
+                if abs(p[2] - z) <= self.tol:
+                    pts += [p[:2], q[:2]]
+                continue
+            t = (z - p[2]) / dz
+            if -1e-12 <= t <= 1 + 1e-12:
+                pts.append(p[:2] + min(max(t, 0.0), 1.0) * (q[:2] - p[:2]))
+        return PolygonLimits(np.array(pts) if pts else np.zeros((0, 2)), self.tol)
+
+    def interior_point(self):
+        return tuple(self.vert.mean(axis=0))
+
+
+class PolygonLimits:
+    """Iterated limits of a convex polygon (the z-slice of a PolyhedronLimits; `Polygon2` of the reference's extension)"""
+
+    def __init__(self, pts, tol=None):
+        self.tol = np.sqrt(np.finfo(float).eps) if tol is None else tol
+        p = np.asarray(pts, dtype=float).reshape(-1, 2)
+        if p.shape[0] >= 3:
+            from scipy.spatial import ConvexHull, QhullError
+            try:
+                p = p[ConvexHull(p).vertices]
+            except QhullError:          # degenerate slice (a segment or a point)
+                pass
+        self.pts = p
+
+    ndim = 2
+
+    def segments(self):
+        if self.pts.shape[0] == 0:
+            return (0.0, 0.0)
+        s = PolyhedronLimits._unique_sorted(self.pts[:, 1], self.tol)
+        return s if len(s) >= 2 else (s[0], s[0])
+
+    def fix(self, y):
+        n = self.pts.shape[0]
+        xs = []
+        for i in range(n):
+            p, q = self.pts[i], self.pts[(i + 1) % n]
+            dy = q[1] - p[1]
+            if abs(dy) <= 1e-300:
+                if abs(p[1] - y) <= self.tol:
+                    xs += [p[0], q[0]]
+                continue
+            t = (y - p[1]) / dy
+            if -1e-12 <= t <= 1 + 1e-12:
+                xs.append(p[0] + min(max(t, 0.0), 1.0) * (q[0] - p[0]))
+        if not xs:
+            return CubicLimits([0.0], [0.0])
+        return CubicLimits([min(xs)], [max(xs)])
+
+    def interior_point(self):
+        return tuple(self.pts.mean(axis=0))
+
+
 class SymmetricBZ:
     """SymmetricBZ(A, B, lims, syms) (src/brillouin.jl:33-41).  A, B hold the real / reciprocal basis
     vectors in their columns; lims and syms are in the lattice basis (fractional coordinates)."""

@@ -2121,17 +2121,41 @@ int32_t abz_iai_solve(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const double*
                                  out, stats);
 }
 
+static int32_t iai_solve_impl(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const double* la, const double* lb, abz_limits_fn lfn,
+                              void* luser, int32_t fkind, int32_t vkind, const double* z, const double* sigma, const double* lin,
+                              double atol, double rtol, int64_t maxevals, int32_t flags, int32_t rank, int32_t nranks,
+                              abz_exchange_fn exchange, void* exchange_user, double* out, int64_t* stats);
+
 int32_t abz_iai_solve_sharded(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const double* la, const double* lb, int32_t fkind,
                               int32_t vkind, const double* z, const double* sigma, const double* lin, double atol, double rtol,
                               int64_t maxevals, int32_t flags, int32_t rank, int32_t nranks, abz_exchange_fn exchange,
                               void* exchange_user, double* out, int64_t* stats) {
     if (!ctx) return ABZ_E_INVALID;
+    if ((lkind != 0 && lkind != 1) || !la || (lkind == 0 && !lb)) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    return iai_solve_impl(ctx, nid, lkind, la, lb, nullptr, nullptr, fkind, vkind, z, sigma, lin, atol, rtol, maxevals, flags, rank, nranks,
+                          exchange, exchange_user, out, stats);
+}
+
+int32_t abz_iai_solve_general(abz_ctx* ctx, abz_nest_t nid, abz_limits_fn limits, void* limits_user, int32_t fkind, int32_t vkind,
+                              const double* z, const double* sigma, const double* lin, double atol, double rtol, int64_t maxevals,
+                              int32_t flags, int32_t rank, int32_t nranks, abz_exchange_fn exchange, void* exchange_user, double* out,
+                              int64_t* stats) {
+    if (!ctx) return ABZ_E_INVALID;
+    if (!limits) return fail(ctx, ABZ_E_INVALID, "abz_iai_solve_general: the limits callback is NULL");
+    return iai_solve_impl(ctx, nid, 2, nullptr, nullptr, limits, limits_user, fkind, vkind, z, sigma, lin, atol, rtol, maxevals, flags, rank,
+                          nranks, exchange, exchange_user, out, stats);
+}
+
+static int32_t iai_solve_impl(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const double* la, const double* lb, abz_limits_fn lfn,
+                              void* luser, int32_t fkind, int32_t vkind, const double* z, const double* sigma, const double* lin,
+                              double atol, double rtol, int64_t maxevals, int32_t flags, int32_t rank, int32_t nranks,
+                              abz_exchange_fn exchange, void* exchange_user, double* out, int64_t* stats) {
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, ABZ_E_INVALID, "invalid rank/nranks");
     if (nranks > 1 && !exchange && !ctx->nccl_comm)
         return fail(ctx, ABZ_E_NCCL, "abz_iai_solve_sharded: nranks > 1 needs an exchange callback or abz_comm_init");
     Nest* nst = get_nest(ctx, nid);
     if (!nst) return fail(ctx, ABZ_E_INVALID, "unknown nest handle");
-    if ((lkind != 0 && lkind != 1) || !la || (lkind == 0 && !lb) || !out || vkind < 0 || vkind > 2 ||
+    if (!out || vkind < 0 || vkind > 2 ||
         (fkind != ABZ_F_RESOLVENT_TRACE && fkind != ABZ_F_TRACE_H) || (fkind == ABZ_F_RESOLVENT_TRACE && !z) || (vkind == 2 && !lin) ||
         !(atol >= 0) || !(rtol >= 0) || maxevals < 1)
         return fail(ctx, ABZ_E_INVALID, "invalid arguments");
@@ -2142,7 +2166,8 @@ int32_t abz_iai_solve_sharded(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
     if (rc) return rc;
     abz_iai::Limits lims;
     lims.kind = lkind; lims.nd = nst->ndim; lims.s = 1.0;
-    for (int d = 0; d < nst->ndim; d++) { lims.a[d] = la[d]; lims.b[d] = lb ? lb[d] : 0.0; }
+    lims.fn = lfn; lims.user = luser;
+    for (int d = 0; d < nst->ndim; d++) { lims.a[d] = la ? la[d] : 0.0; lims.b[d] = lb ? lb[d] : 0.0; }
     IaiDeviceBackend be;
     be.ctx = ctx; be.nst = nst; be.fkind = fkind; be.vkind = vkind;
     be.z = make_double2(z ? z[0] : 0.0, z ? z[1] : 0.0);
@@ -2179,7 +2204,7 @@ int32_t abz_iai_solve_sharded(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
         if (stats) { stats[0] = eng2.numevals; stats[1] = eng.rounds + eng2.rounds; stats[2] = ctx->launches - launches0; stats[3] = 0; }
         if (rc == abz_iai::IAI_E_NAN) return fail(ctx, ABZ_E_SINGULAR, eng2.error);
         if (rc == abz_iai::IAI_E_ARENA) return fail(ctx, ABZ_E_OOM, eng2.error);
-        if (rc == abz_iai::IAI_E_STALL) return fail(ctx, ABZ_E_INVALID, eng2.error);
+        if (rc == abz_iai::IAI_E_STALL || rc == abz_iai::IAI_E_LIMITS) return fail(ctx, ABZ_E_INVALID, eng2.error);
         if (rc) return rc;
         out[0] = eng2.result.re; out[1] = eng2.result.im; out[2] = eng2.result_err;
         return ABZ_OK;
@@ -2187,7 +2212,7 @@ int32_t abz_iai_solve_sharded(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
     if (stats) { stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = ctx->launches - launches0; stats[3] = eng.exchanges; }
     if (rc == abz_iai::IAI_E_NAN) return fail(ctx, ABZ_E_SINGULAR, eng.error);
     if (rc == abz_iai::IAI_E_ARENA) return fail(ctx, ABZ_E_OOM, eng.error);
-    if (rc == abz_iai::IAI_E_STALL) return fail(ctx, ABZ_E_INVALID, eng.error);
+    if (rc == abz_iai::IAI_E_STALL || rc == abz_iai::IAI_E_LIMITS) return fail(ctx, ABZ_E_INVALID, eng.error);
     if (rc) return rc;
     out[0] = eng.result.re; out[1] = eng.result.im; out[2] = eng.result_err;
     return ABZ_OK;

@@ -570,8 +570,12 @@ __device__ __noinline__ double householder_params64(const double2* __restrict__ 
     sig = warp_sum(sig);
     const double2 alpha = vs[c + 1];
     const double aa = alpha.x * alpha.x + alpha.y * alpha.y;
-    const double yn = sqrt(sig + aa), absa = sqrt(aa);
-    const double ia = absa > 0.0 ? fast_rcp(absa) : 0.0;
+    // |y|, |y_1| and 1/|y_1| from two independent reciprocal square roots (no DSQRT on the per-column dependent chain)
+    const double tot = sig + aa;
+    const bool fast = tot > 1e-280 && tot < 1e280 && (aa == 0.0 || aa > 1e-280);
+    const double rt = fast ? fast_rsqrt(tot) : 0.0, ra = (fast && aa > 0.0) ? fast_rsqrt(aa) : 0.0;
+    const double yn = fast ? tot * rt : sqrt(tot), absa = fast ? aa * ra : sqrt(aa);
+    const double ia = absa > 0.0 ? (fast ? ra : fast_rcp(absa)) : 0.0;
     const double2 ph = absa > 0.0 ? make_double2(alpha.x * ia, alpha.y * ia) : make_double2(1.0, 0.0);
     *v0 = make_double2(alpha.x + ph.x * yn, alpha.y + ph.y * yn);
     *tau = (sig > 0.0) ? fast_rcp(yn * (yn + absa)) : 0.0;
@@ -752,10 +756,14 @@ eig_tql_kernel(const double* __restrict__ din, const double* __restrict__ ein, c
                         for (i = m - 1; i >= l; i--) {
                             const double ei = TQL_E(i);
                             double f = s * ei, b = c * ei;
-                            r = sqrt(fma(f, f, g * g));      // plain sqrt: band energies are nowhere near the overflow range
+                            // r = sqrt(f^2 + g^2) and 1/r from ONE reciprocal square root (MUFU seed + two Newton steps) instead of
+                            // a DSQRT followed by a division: this pair is the dependent chain of every rotation of the sweep
+                            const double h2 = fma(f, f, g * g);
+                            double rinv;
+                            if (h2 > 1e-280 && h2 < 1e280) { rinv = fast_rsqrt(h2); r = h2 * rinv; }
+                            else { r = sqrt(h2); rinv = 1.0 / r; }
                             TQL_E(i + 1) = r;
                             if (r == 0.0) { TQL_D(i + 1) -= p; TQL_E(m) = 0.0; break; }
-                            const double rinv = 1.0 / r;
                             s = f * rinv; c = g * rinv;
                             g = TQL_D(i + 1) - p;
                             r = (TQL_D(i) - g) * s + 2.0 * c * b;

@@ -161,37 +161,25 @@ struct LeafSeg { double E, a, b, Ire, Iim; };
 
 __device__ __forceinline__ double leaf_abs(abz_iai::cplx v) { return v.im == 0.0 ? fabs(v.re) : hypot(v.re, v.im); }
 
+// One innermost adaptive integral by ONE warp (QuadGK do_quadgk / adapt on the 1-D series c[M1][NN] in shared memory): the body of
+// iai_leaf_kernel, shared with iai_mid_kernel so that both take bit-identical decisions.  hs: the warp's 63 shared-memory heap
+// entries, hg: its global spill area, vals: 32 shared complex slots of the warp.  Lane 0 returns I, E, ne (numevals); *err gets the
+// flags (1: non-finite, 4: heap overflow).
 template <int NORB>
-__global__ void __launch_bounds__(LEAF_WARPS * 32)
-iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __restrict__ task_a,
-                const double* __restrict__ task_b, const double* __restrict__ task_atol, const long* __restrict__ task_slot,
-                long ntask, int M1, int lo, double period, int fkind, int vkind, double2 z, const double2* __restrict__ sigma,
-                abz_iai::cplx la, abz_iai::cplx lb, double rtol, long long maxevals, LeafSeg* __restrict__ spill, int spill_cap,
-                double* __restrict__ out, int* __restrict__ errflag) {
-    constexpr int NN = NORB * NORB;
-    __shared__ LeafSeg heap_s[LEAF_WARPS][LEAF_SMEM_SEGS];
-    __shared__ abz_iai::cplx vals[LEAF_WARPS][32];
-    extern __shared__ double2 leaf_coef[];            // [LEAF_WARPS][M1*NN]: this task's 1-D series, staged once per integral
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long task = (long)blockIdx.x * LEAF_WARPS + w;
-    if (task >= ntask) return;
-    double2* c = leaf_coef + w * (M1 * NN);
-    {
-        const double2* cg = L1 + task_slot[task] * l1_stride;
-        for (int e = lane; e < M1 * NN; e += 32) c[e] = cg[e];        // coalesced 128-bit loads
-    }
-    __syncwarp();
-    const double atol = task_atol[task];
-    LeafSeg* hs = heap_s[w];
-    LeafSeg* hg = spill + task * (long)(spill_cap > 0 ? spill_cap : 1);
-    const int cap_total = spill_cap < 0 ? -spill_cap : LEAF_SMEM_SEGS + spill_cap;   // negative: total capacity (test hook)
+__device__ __forceinline__ void leaf_integrate(const double2* __restrict__ c, LeafSeg* __restrict__ hs, LeafSeg* __restrict__ hg,
+                                               int cap_total, abz_iai::cplx* __restrict__ vals, double a0, double b0, double atol,
+                                               int M1, int lo, double period, int fkind, int vkind, double2 z,
+                                               const double2* __restrict__ sigma, abz_iai::cplx la, abz_iai::cplx lb, double rtol,
+                                               long long maxevals, int* __restrict__ errflag, abz_iai::cplx* Iout, double* Eout,
+                                               long long* neout) {
+    const int lane = threadIdx.x & 31;
 #define LEAF_AT(i) (((i) <= LEAF_SMEM_SEGS) ? hs[(i) - 1] : hg[(i) - 1 - LEAF_SMEM_SEGS])
     const int half = lane >> 4, j = lane & 15;
     // ---- first panel
-    double pa = task_a[task], pb = task_b[task];
+    double pa = a0, pb = b0;
     if (half == 0 && j < 15) {
         double2 y = nest_point_small<NORB>(c, abz_iai::gk_node(pa, pb, j), M1, lo, period, fkind, z, sigma, errflag);
-        vals[w][lane] = abz_iai::post_value(vkind, abz_iai::cplx{y.x, y.y}, la, lb);
+        vals[lane] = abz_iai::post_value(vkind, abz_iai::cplx{y.x, y.y}, la, lb);
     }
     __syncwarp();
     abz_iai::cplx I{0.0, 0.0};
@@ -201,7 +189,7 @@ iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __
     int go = 0;
     if (lane == 0) {
         abz_iai::cplx D;
-        abz_iai::gk_combine(pa, pb, vals[w], &I, &D);
+        abz_iai::gk_combine(pa, pb, vals, &I, &D);
         E = leaf_abs(D);
         hs[0] = LeafSeg{E, pa, pb, I.re, I.im};
         if (!isfinite(E)) { atomicOr(errflag, 1); go = 0; }
@@ -240,14 +228,14 @@ iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __
         __syncwarp();
         if (j < 15) {
             double2 y = nest_point_small<NORB>(c, abz_iai::gk_node(pa, pb, j), M1, lo, period, fkind, z, sigma, errflag);
-            vals[w][lane] = abz_iai::post_value(vkind, abz_iai::cplx{y.x, y.y}, la, lb);
+            vals[lane] = abz_iai::post_value(vkind, abz_iai::cplx{y.x, y.y}, la, lb);
         }
         __syncwarp();
         abz_iai::cplx nI{0.0, 0.0};
         double nE = 0.0;
         if (j == 0) {
             abz_iai::cplx D;
-            abz_iai::gk_combine(pa, pb, vals[w] + 16 * half, &nI, &D);
+            abz_iai::gk_combine(pa, pb, vals + 16 * half, &nI, &D);
             nE = leaf_abs(D);
         }
         const double I2re = __shfl_sync(0xffffffffu, nI.re, 16), I2im = __shfl_sync(0xffffffffu, nI.im, 16);
@@ -282,10 +270,211 @@ iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __
         abz_iai::cplx Iv{hs[0].Ire, hs[0].Iim};
         double Ev = hs[0].E;
         for (long k = 2; k <= len; k++) { const LeafSeg sgk = LEAF_AT(k); Iv.re += sgk.Ire; Iv.im += sgk.Iim; Ev += sgk.E; }
+        *Iout = Iv; *Eout = Ev; *neout = ne;
+    }
+#undef LEAF_AT
+}
+
+template <int NORB>
+__global__ void __launch_bounds__(LEAF_WARPS * 32)
+iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __restrict__ task_a,
+                const double* __restrict__ task_b, const double* __restrict__ task_atol, const long* __restrict__ task_slot,
+                long ntask, int M1, int lo, double period, int fkind, int vkind, double2 z, const double2* __restrict__ sigma,
+                abz_iai::cplx la, abz_iai::cplx lb, double rtol, long long maxevals, LeafSeg* __restrict__ spill, int spill_cap,
+                double* __restrict__ out, int* __restrict__ errflag) {
+    constexpr int NN = NORB * NORB;
+    __shared__ LeafSeg heap_s[LEAF_WARPS][LEAF_SMEM_SEGS];
+    __shared__ abz_iai::cplx vals[LEAF_WARPS][32];
+    extern __shared__ double2 leaf_coef[];            // [LEAF_WARPS][M1*NN]: this task's 1-D series, staged once per integral
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long task = (long)blockIdx.x * LEAF_WARPS + w;
+    if (task >= ntask) return;
+    double2* c = leaf_coef + w * (M1 * NN);
+    {
+        const double2* cg = L1 + task_slot[task] * l1_stride;
+        for (int e = lane; e < M1 * NN; e += 32) c[e] = cg[e];        // coalesced 128-bit loads
+    }
+    __syncwarp();
+    LeafSeg* hg = spill + task * (long)(spill_cap > 0 ? spill_cap : 1);
+    const int cap_total = spill_cap < 0 ? -spill_cap : LEAF_SMEM_SEGS + spill_cap;   // negative: total capacity (test hook)
+    abz_iai::cplx Iv{0.0, 0.0};
+    double Ev = 0.0;
+    long long ne = 0;
+    leaf_integrate<NORB>(c, heap_s[w], hg, cap_total, vals[w], task_a[task], task_b[task], task_atol[task], M1, lo, period, fkind, vkind, z,
+                         sigma, la, lb, rtol, maxevals, errflag, &Iv, &Ev, &ne);
+    if (lane == 0) {
         out[4 * task] = Iv.re; out[4 * task + 1] = Iv.im; out[4 * task + 2] = Ev;
         reinterpret_cast<long long*>(out)[4 * task + 3] = ne;
     }
-#undef LEAF_AT
+}
+
+// ---- device-side MIDDLE integrals (3-d solves) -----------------------------------------------------------------------------
+// One CTA per middle-level adaptive integral (over x2, for the series contracted at one x3 node in a level-2 slot): the CTA keeps
+// that integral's segment heap in shared memory and runs QuadGK's loop itself - pop the worst segment, bisect, and for each of
+// the 30 new nodes x2: contract the level-2 series at x2 (workspace_contract!, src/fourier.jl:478), inner abstol = abstol / len
+// (:479-480), and run the whole innermost adaptive integral (leaf_integrate, one warp per node, nodes handed out dynamically);
+// then the two panels are combined in evalrule's order, pushed, and the convergence test decides.  No host round trip below the
+// outermost level: a round of the host engine is one refinement step of the OUTERMOST integral.  Same arithmetic and the same
+// decisions as the host-driven engine, hence identical numevals.
+//   lkind 0: x1 in [la1, lb1];  1: x1 in [0, la1 * x2 / la2]   (CubicLimits / TetrahedralLimits)
+// out[5 t ..]: I.re, I.im, E, (int64) evaluations of all innermost integrals, (int64) evaluations of this integral's own nodes
+constexpr int MID_WARPS = 16;
+constexpr int MID_HEAP = 1023;
+struct MidShared {
+    LeafSeg heap[MID_HEAP];
+    LeafSeg leaf_heap[MID_WARPS][LEAF_SMEM_SEGS];
+    abz_iai::cplx leaf_vals[MID_WARPS][32];
+    abz_iai::cplx node_vals[32];
+    double pa[2], pb[2];
+    int counter, ntasks, go;
+    unsigned long long ne_leaves;
+};
+
+template <int NORB>
+__global__ void __launch_bounds__(MID_WARPS * 32)
+iai_mid_kernel(const double2* __restrict__ L2, long l2_stride, const double* __restrict__ task_a, const double* __restrict__ task_b,
+               const double* __restrict__ task_atol, const long* __restrict__ task_slot, int lkind, double la1, double lb1, double la2,
+               int M1, int lo1, double period1, int M2, int lo2, double period2, int fkind, int vkind, double2 z,
+               const double2* __restrict__ sigma, abz_iai::cplx la, abz_iai::cplx lb, double rtol, long long maxevals,
+               LeafSeg* __restrict__ spill, int spill_cap, double* __restrict__ out, int* __restrict__ errflag) {
+    constexpr int NN = NORB * NORB;
+    extern __shared__ __align__(16) unsigned char mid_raw[];
+    MidShared& sm = *reinterpret_cast<MidShared*>(mid_raw);
+    double2* coef = reinterpret_cast<double2*>(mid_raw + sizeof(MidShared));      // [MID_WARPS][M1*NN]
+    double2* phase = coef + MID_WARPS * (M1 * NN);                                 // [MID_WARPS][M2]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long task = blockIdx.x;
+    const double2* src = L2 + task_slot[task] * l2_stride;                         // [M2][M1*NN]
+    const double atol = task_atol[task];
+    const int rows = M1 * NN;
+    double2* c = coef + w * rows;
+    double2* ph = phase + w * M2;
+    LeafSeg* hg = spill + (task * MID_WARPS + w) * (long)(spill_cap > 0 ? spill_cap : 1);
+    const int cap_leaf = spill_cap < 0 ? -spill_cap : LEAF_SMEM_SEGS + spill_cap;
+    if (threadIdx.x == 0) {
+        sm.pa[0] = task_a[task]; sm.pb[0] = task_b[task];
+        sm.counter = 0; sm.ntasks = 15; sm.go = 1; sm.ne_leaves = 0ull;
+    }
+    __syncthreads();
+    abz_iai::cplx I{0.0, 0.0};           // thread 0 only
+    double E = 0.0;
+    long len = 0;
+    long long ne_own = 0;
+    LeafSeg popped{0, 0, 0, 0, 0};
+    bool first = true;
+    for (;;) {
+        // ---- the nodes of this step's panels, handed to the warps one at a time
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&sm.counter, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= sm.ntasks) break;
+            const int p = t / 15, jn = t - 15 * p;
+            const double x2 = abz_iai::gk_node(sm.pa[p], sm.pb[p], jn);
+            double ca, cb;
+            if (lkind == 0) { ca = la1; cb = lb1; }
+            else { ca = 0.0; cb = la1 * (x2 / la2); }
+            const double catol = atol / (cb - ca);
+            // contract the level-2 series at x2 into this warp's 1-D series
+            __syncwarp();
+            for (int m = lane; m < M2; m += 32) ph[m] = cis2pi(x2 * (double)(m + lo2) / period2);
+            __syncwarp();
+            for (int e = lane; e < rows; e += 32) {
+                double2 acc = make_double2(0.0, 0.0);
+                for (int m = 0; m < M2; m++) acc = cfma(acc, src[(long)m * rows + e], ph[m]);
+                c[e] = acc;
+            }
+            __syncwarp();
+            abz_iai::cplx Iv{0.0, 0.0};
+            double Ev = 0.0;
+            long long ne = 0;
+            leaf_integrate<NORB>(c, sm.leaf_heap[w], hg, cap_leaf, sm.leaf_vals[w], ca, cb, catol, M1, lo1, period1, fkind, vkind, z, sigma,
+                                 la, lb, rtol, maxevals, errflag, &Iv, &Ev, &ne);
+            if (lane == 0) {
+                sm.node_vals[16 * p + jn] = Iv;
+                atomicAdd(&sm.ne_leaves, (unsigned long long)ne);
+                if (!isfinite(Ev)) atomicOr(errflag, 1);
+            }
+        }
+        __syncthreads();
+        // ---- combine, push, decide (thread 0: the DataStructures heap with Reverse on E, as the host engine)
+        if (threadIdx.x == 0) {
+            int go = 1;
+#define MID_AT(i) sm.heap[(i) - 1]
+            if (first) {
+                abz_iai::cplx D;
+                abz_iai::gk_combine(sm.pa[0], sm.pb[0], sm.node_vals, &I, &D);
+                E = leaf_abs(D);
+                MID_AT(1) = LeafSeg{E, sm.pa[0], sm.pb[0], I.re, I.im};
+                len = 1; ne_own = 15;
+                if (!isfinite(E)) { atomicOr(errflag, 1); go = 0; }
+                else go = !(ne_own >= maxevals || E <= atol || E <= rtol * leaf_abs(I));
+            } else {
+                abz_iai::cplx I1, D1, I2, D2;
+                abz_iai::gk_combine(sm.pa[0], sm.pb[0], sm.node_vals, &I1, &D1);
+                abz_iai::gk_combine(sm.pa[1], sm.pb[1], sm.node_vals + 16, &I2, &D2);
+                const double E1 = leaf_abs(D1), E2 = leaf_abs(D2);
+                I = abz_iai::cplx{(I.re - popped.Ire) + I1.re + I2.re, (I.im - popped.Iim) + I1.im + I2.im};
+                E = (E - popped.E) + E1 + E2;
+                ne_own += 30;
+                if (!(isfinite(E1) && isfinite(E2))) { atomicOr(errflag, 1); go = 0; }
+                else if (len + 2 > MID_HEAP) { atomicOr(errflag, 4); go = 0; }
+                else {
+                    LeafSeg sg[2] = {LeafSeg{E1, sm.pa[0], sm.pb[0], I1.re, I1.im}, LeafSeg{E2, sm.pa[1], sm.pb[1], I2.re, I2.im}};
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        len++;
+                        long i = len;
+                        for (;;) {
+                            long p = i / 2;
+                            if (p < 1) break;
+                            if (!(MID_AT(p).E < sg[t].E)) break;
+                            MID_AT(i) = MID_AT(p);
+                            i = p;
+                        }
+                        MID_AT(i) = sg[t];
+                    }
+                    go = (E > atol && E > rtol * leaf_abs(I) && ne_own < maxevals);
+                }
+            }
+            if (go) {          // pop the worst segment and bisect it
+                popped = MID_AT(1);
+                LeafSeg y = MID_AT(len);
+                len--;
+                if (len > 0) {
+                    long i = 1;
+                    for (;;) {
+                        long l = 2 * i;
+                        if (l > len) break;
+                        long r = l + 1;
+                        long jj = l;
+                        if (r <= len) { if (!(MID_AT(r).E < MID_AT(l).E)) jj = r; }
+                        if (!(y.E < MID_AT(jj).E)) break;
+                        MID_AT(i) = MID_AT(jj);
+                        i = jj;
+                    }
+                    MID_AT(i) = y;
+                }
+                const double mid = (popped.a + popped.b) / 2;
+                sm.pa[0] = popped.a; sm.pb[0] = mid; sm.pa[1] = mid; sm.pb[1] = popped.b;
+                sm.ntasks = 30;
+            }
+            sm.counter = 0;
+            sm.go = go;
+        }
+        first = false;
+        __syncthreads();
+        if (!sm.go) break;
+    }
+    if (threadIdx.x == 0) {
+        abz_iai::cplx Iv{MID_AT(1).Ire, MID_AT(1).Iim};
+        double Ev = MID_AT(1).E;
+        for (long k = 2; k <= len; k++) { Iv.re += MID_AT(k).Ire; Iv.im += MID_AT(k).Iim; Ev += MID_AT(k).E; }
+        out[5 * task] = Iv.re; out[5 * task + 1] = Iv.im; out[5 * task + 2] = Ev;
+        reinterpret_cast<long long*>(out)[5 * task + 3] = (long long)sm.ne_leaves;
+        reinterpret_cast<long long*>(out)[5 * task + 4] = ne_own;
+#undef MID_AT
+    }
 }
 
 // general norb: evaluate H at the nodes into a buffer (then the generic resolvent kernel runs on it)

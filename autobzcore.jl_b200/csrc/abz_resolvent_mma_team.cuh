@@ -19,6 +19,10 @@
 #include "abz_common.cuh"
 #include "abz_resolvent_mma.cuh"
 
+#ifndef ABZ_TEAM_PIVOT_THR
+#define ABZ_TEAM_PIVOT_THR 2e-3
+#endif
+
 namespace abz {
 
 struct Blk8 { double r0, r1, i0, i1; int minhi; };
@@ -75,7 +79,7 @@ template <int NB, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 resolvent_mma_team_kernel(const double2* __restrict__ H, const double* __restrict__ wnode, long nk, int n, int nw,
                           const double2* __restrict__ z, const double2* __restrict__ sigma, int kper, int mode,
-                          double2* __restrict__ outp, int* __restrict__ errflag) {
+                          double2* __restrict__ outp, int* __restrict__ errflag, double piv_thr2) {
     constexpr int NC = (NB + NW - 1) / NW;        // block columns per warp
     constexpr int NT = NW * 32;
     extern __shared__ __align__(16) unsigned char team_smem_raw[];
@@ -280,7 +284,7 @@ resolvent_mma_team_kernel(const double2* __restrict__ H, const double* __restric
             for (int wp = 0; wp < NW; wp++) { sx += sm.red[wp][0]; sy += sm.red[wp][1]; am = max(am, sm.redi[wp][0]); mn = min(mn, sm.redi[wp][1]); }
             const double2 t = make_double2(-sx - (double)npad, -sy);
             const double pmin2 = __hiloint2double(mn, 0), amx = __hiloint2double(am, 0);
-            if (!(pmin2 > 4e-6 * amx * amx) || !(isfinite(t.x) && isfinite(t.y))) atomicOr(errflag, 2);   // ask for the pivoted path
+            if (!(pmin2 > piv_thr2 * amx * amx) || !(isfinite(t.x) && isfinite(t.y))) atomicOr(errflag, 2);   // ask for the pivoted path
             if (mode == 0) {
                 const double wt = wnode ? wnode[k] : 1.0;
                 acc[w].x += wt * t.x; acc[w].y += wt * t.y;
@@ -298,11 +302,20 @@ resolvent_mma_team_kernel(const double2* __restrict__ H, const double* __restric
 
 inline bool mma_team_supported(int n) { return n > 32 && n <= 64; }
 
+// smallest |pivot| allowed relative to max|a_ij| before the call is rerun with the pivoted teams (squared); ABZ_MMA_TEAM_PIVOT_THR
+// overrides (measurement hook, profiles/r02_team_resolvent_accuracy.log)
+inline double mma_team_pivot_threshold2() {
+    static double t = -1.0;
+    if (t < 0.0) { const char* e = getenv("ABZ_MMA_TEAM_PIVOT_THR"); const double v = e ? atof(e) : ABZ_TEAM_PIVOT_THR; t = v * v; }
+    return t;
+}
+
 template <int NB, int NW, int MINB>
 inline cudaError_t mma_team_launch_one(const double2* H, const double* wnode, long nk, int n, int nw, const double2* z, const double2* sigma,
                                        int mode, double2* outp, int* errflag, long ncta, int kper, cudaStream_t stream) {
     const size_t smem = sizeof(TeamSmem<NB>) + (size_t)nw * sizeof(double2);
-    resolvent_mma_team_kernel<NB, NW, MINB><<<(unsigned)ncta, NW * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
+    resolvent_mma_team_kernel<NB, NW, MINB><<<(unsigned)ncta, NW * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag,
+                                                                                      mma_team_pivot_threshold2());
     return cudaGetLastError();
 }
 

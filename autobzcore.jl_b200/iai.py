@@ -121,7 +121,7 @@ class _Pend:
 
 
 class _Integral:
-    __slots__ = ("level", "lims", "atol", "slot", "parent", "heap", "I", "E", "numevals", "popped", "s1", "s2", "state", "outer")
+    __slots__ = ("level", "lims", "atol", "slot", "parent", "heap", "I", "E", "numevals", "popped", "s1", "s2", "state", "outer", "init_remaining")
 
     def __init__(self, level, lims, atol, slot, parent, outer=()):
         self.level, self.lims, self.atol, self.slot, self.parent = level, lims, atol, slot, parent
@@ -171,16 +171,24 @@ class NestedGK:
         for i in range(15):
             x = float(xs[i])
             clims = q.lims.fix(x)
-            ca, cb = clims.segments()
-            length = cb - ca
+            csegs = tuple(clims.segments())
+            length = csegs[-1] - csegs[0]                 # len = segs[end] - segs[1] (src/fourier.jl:476)
             slot = self._alloc(q.level)
             if q.level == 2:
                 self.q_c3.append((x, slot))
             else:
                 self.q_c2.append((x, q.slot, slot))
-            child = _Integral(q.level - 1, clims, q.atol / length if self.atol_given else q.atol, slot, (q, pend, i),
-                              (x,) + q.outer)
-            self._start_segment(child, ca, cb, 0)
+            catol = q.atol if not self.atol_given else (q.atol / length if length != 0.0 else float("inf"))
+            child = _Integral(q.level - 1, clims, catol, slot, (q, pend, i), (x,) + q.outer)
+            self._start_initial(child, csegs)
+
+    def _start_initial(self, q, segs):
+        """do_quadgk's first pass: evalrule on every initial segment (panel k carries tag -k)"""
+        ns = len(segs) - 1
+        q.init_remaining = ns
+        q.heap = [None] * ns
+        for k in range(ns):
+            self._start_segment(q, segs[k], segs[k + 1], -k)
 
     def _finish(self, q):
         heap = q.heap
@@ -212,12 +220,22 @@ class NestedGK:
         if not np.isfinite(Es):
             raise DomainError(f"integrand produced {Es} in the interval ({pend.a}, {pend.b})")
         seg = (Es, pend.a, pend.b, Is)
-        if pend.tag == 0:
-            q.heap = [seg]
-            q.I, q.E, q.numevals = Is, Es, 15
+        if pend.tag <= 0:
+            # I, E = left folds over the initial segments; heapify! only when a subdivision is needed (QuadGK do_quadgk)
+            q.heap[-pend.tag] = seg
+            q.init_remaining -= 1
+            if q.init_remaining > 0:
+                return
+            q.I, q.E = q.heap[0][3], q.heap[0][0]
+            for sg in q.heap[1:]:
+                q.I = q.I + sg[3]
+                q.E = q.E + sg[0]
+            q.numevals = 15 * len(q.heap)
             if q.numevals >= self.maxevals or q.E <= q.atol or q.E <= self.rtol * abs(q.I):
                 self._finish(q)
             else:
+                for i in range(len(q.heap) // 2, 0, -1):
+                    _percolate_down(q.heap, i, q.heap[i - 1], len(q.heap))
                 self._refine(q)
             return
         if pend.tag == 1:
@@ -245,9 +263,8 @@ class NestedGK:
         if rtol is None:
             rtol = np.sqrt(np.finfo(float).eps) if atol == 0 else 0.0
         self.rtol = rtol
-        a, b = self.lims.segments()
         root = _Integral(self.ndim - 1, self.lims, atol, None, None)
-        self._start_segment(root, a, b, 0)
+        self._start_initial(root, tuple(self.lims.segments()))
         while self.root_result is None:
             self.rounds += 1
             if self.q_c3:

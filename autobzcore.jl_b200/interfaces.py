@@ -346,9 +346,14 @@ def _standard(dom, alg):
         raise TypeError("unsupported BZ algorithm (TAI is out of scope, SURVEY.md §2)")
     if isinstance(dom, Basis):
         return dom, alg, None, None, dom.ndim
-    if isinstance(dom, (CubicLimits, TetrahedralLimits)):
+    if _is_iterated_limits(dom):
         return dom, alg, None, None, dom.ndim
     raise TypeError("unsupported domain")
+
+
+def _is_iterated_limits(dom):
+    """IteratedIntegration.AbstractIteratedLimits by protocol: ndim, segments() -> breakpoints, fix(x) -> inner limits"""
+    return all(hasattr(dom, a) for a in ("ndim", "segments", "fix")) and not isinstance(dom, SymmetricBZ)
 
 
 def _init_cacheval(cache):
@@ -368,7 +373,7 @@ def _init_cacheval(cache):
         cv["schedule"] = (n0, dn)
         cv["rules"] = [cache.backend.make_rule(f.s, ndim, n0, salg.syms, cache.shard.rank, cache.shard.nranks, allreduce=_shard_allreduce(cache.shard))]
     elif isinstance(salg, NestedQuad):
-        if not isinstance(dom, (CubicLimits, TetrahedralLimits)):
+        if not _is_iterated_limits(dom):
             raise TypeError("NestedQuad needs iterated limits")
         if f.native and f.f.is_eig:
             raise TypeError("IAI on the device supports the resolvent / affine integrands and host (batch) integrands")
@@ -475,16 +480,20 @@ def _do_solve(cache, ps):
                 # abz_iai_solve: same control flow, run by the library's C++ host engine (one ccall per solve)
                 atol_ = 0.0 if atol is None else atol
                 rtol_ = reltol if reltol is not None else (np.sqrt(np.finfo(float).eps) if atol_ == 0 else 0.0)
-                lkind = 1 if isinstance(dom, TetrahedralLimits) else 0
-                la = dom.a
-                lb = dom.b if lkind == 0 else None
-                if lkind == 1 and dom.s != 1.0:
-                    raise ValueError("TetrahedralLimits must start at s = 1")
+                general = None
+                if isinstance(dom, TetrahedralLimits) and dom.s == 1.0:
+                    lkind, la, lb = 1, dom.a, None
+                elif isinstance(dom, CubicLimits):
+                    lkind, la, lb = 0, dom.a, dom.b
+                else:
+                    # any other iterated limits (polyhedral IBZ, several segments per level, ...): the library asks this object for
+                    # the breakpoints of every 1-D integral it starts (abz_iai_solve_general)
+                    lkind, la, lb, general = 2, None, None, dom
                 lin = bound if vkind == 2 else None
                 Iv, Ev, ne, rounds, launches = nest.iai_solve(lkind, la, lb, b1.fkind, vkind, z, sigma, lin, atol_, rtol_, maxiters,
                                                               device_leaves=getattr(cache.backend, "iai_device_leaves", True),
                                                               rank=shard.rank, nranks=shard.nranks,
-                                                              allreduce=shard.allreduce if shard.nranks > 1 else None)
+                                                              allreduce=shard.allreduce if shard.nranks > 1 else None, limits=general)
                 cache.cacheval["iai_rounds"] = rounds
                 Iv = Iv if dtype == np.complex128 else Iv.real
             else:

@@ -210,6 +210,21 @@ int32_t abz_iai_solve_sharded(abz_ctx* ctx, abz_nest_t nest, int32_t lkind, cons
                               int64_t maxevals, int32_t flags, int32_t rank, int32_t nranks, abz_exchange_fn exchange,
                               void* exchange_user, double* out, int64_t* stats);
 
+/* The same solve over GENERAL iterated limits - what a caller gets from the reference's IBZ loader (Polyhedron3 / Polygon2 with
+ * `segments` and `fixandeliminate`, ext/SymmetryReduceBZExt.jl:33-58; PuncturedInterval(segs), src/fourier.jl:493-500), or any
+ * IteratedIntegration.AbstractIteratedLimits.  The geometry stays with the caller: `limits(dim, x_fixed, segs, maxseg, user)` must
+ * write the ascending breakpoints of the variable of `dim` (1-based, dim = ndim is the outermost) given the outer variables fixed
+ * so far (x_fixed[0] = outermost, ndim - dim values) - i.e. segments(fixandeliminate(...fixandeliminate(lims, x_ndim)..., x_{dim+1}))
+ * - and return their number (2 ... maxseg = 64; a negative value aborts the solve with ABZ_E_INVALID).  Every 1-D integral starts
+ * from all of its segments as QuadGK does (sum over the initial panels, heapify, then adapt); inner tolerances are abstol / (last
+ * breakpoint - first breakpoint) (src/fourier.jl:476-480).  Device-side innermost integrals are used where the innermost range is a
+ * single segment (always the case for a convex IBZ).  Other arguments as abz_iai_solve_sharded. */
+typedef int32_t (*abz_limits_fn)(int32_t dim, const double* x_fixed, double* segs, int32_t maxseg, void* user);
+int32_t abz_iai_solve_general(abz_ctx* ctx, abz_nest_t nest, abz_limits_fn limits, void* limits_user, int32_t fkind, int32_t vkind,
+                              const double* z, const double* sigma, const double* lin, double atol, double rtol, int64_t maxevals,
+                              int32_t flags, int32_t rank, int32_t nranks, abz_exchange_fn exchange, void* exchange_user, double* out,
+                              int64_t* stats);
+
 /* ---- multi-GPU: one small allreduce of partial sums ----------------------- */
 /* NCCL is dlopen'ed at first use (libnccl.so.2).  uid = 128-byte ncclUniqueId from rank 0. */
 int32_t abz_comm_unique_id(void* uid128);

@@ -122,3 +122,24 @@ extern "C" int iai_cpu_solve(const double* coeffs, int n, int ndim, const int* M
     out[0] = eng.result.re; out[1] = eng.result.im; out[2] = eng.result_err;
     return 0;
 }
+
+// the same engine over general iterated limits served by a callback (abz_iai_solve_general's control flow on the CPU backend)
+extern "C" int iai_cpu_solve_general(const double* coeffs, int n, int ndim, const int* M, const int* lo, const double* period,
+                                     limits_fn lfn, void* luser, int fkind, int vkind, const double* z, const double* sigma,
+                                     const double* lin, double atol, double rtol, long maxevals, int leaf_tasks, long cap2, long cap1,
+                                     int rank, int nranks, int (*xfn)(double*, long, void*), double* out, long* stats) {
+    CpuBackend be;
+    be.coeffs = coeffs; be.n = n; be.ndim = ndim;
+    for (int d = 0; d < 3; d++) { be.M[d] = d < ndim ? M[d] : 1; be.lo[d] = d < ndim ? lo[d] : 0; be.period[d] = d < ndim ? period[d] : 1.0; }
+    be.fkind = fkind; be.vkind = vkind; be.z[0] = z ? z[0] : 0; be.z[1] = z ? z[1] : 0; be.sigma = sigma;
+    be.la = cplx{lin ? lin[0] : 1.0, lin ? lin[1] : 0.0}; be.lb = cplx{lin ? lin[2] : 0.0, lin ? lin[3] : 0.0};
+    be.rtol = rtol; be.maxevals = maxevals; be.xfn = xfn;
+    if (const char* e = getenv("IAI_CPU_LANES")) be.nlanes = atoi(e) > 0 ? atoi(e) : 1;
+    Limits lims; lims.kind = 2; lims.nd = ndim; lims.s = 1.0; lims.fn = lfn; lims.user = luser;
+    Engine<CpuBackend> eng(be, ndim, lims, atol, rtol, maxevals, cap2, cap1, leaf_tasks != 0, rank, nranks);
+    int rc = eng.run();
+    stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = be.launches; stats[3] = eng.exchanges;
+    if (rc) return rc;
+    out[0] = eng.result.re; out[1] = eng.result.im; out[2] = eng.result_err;
+    return 0;
+}

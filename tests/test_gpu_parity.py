@@ -40,16 +40,25 @@ def test_rule_sums_and_values_vs_oracle(ctx, orc, n, rmax, N):
     sig = 0.1 * (rng.standard_normal((n, n, 3)) + 1j * rng.standard_normal((n, n, 3)))
     R = L.DeviceRule(ctx, S, N)
     ref = orc.ptr_sum(So, N, z)
-    assert rel(R.resolvent_sum(z, scale=1 / N ** 3), ref) < 1e-11
-    assert rel(R.resolvent_sum(z, sigma=sig, scale=1 / N ** 3), orc.ptr_sum(So, N, z, sigma=sig)) < 1e-11
+    # norb > 32: the default path is the block LU without pivoting between blocks (DMMA teams); its error grows like
+    # norb * eps * |A| / eta (profiles/r02_team_resolvent_accuracy.log) - within the 1e-10 of north_star, not 1e-11, at eta = 0.01
+    tol = 1e-11 if n <= 32 else 1e-10
+    assert rel(R.resolvent_sum(z, scale=1 / N ** 3), ref) < tol
+    assert rel(R.resolvent_sum(z, sigma=sig, scale=1 / N ** 3), orc.ptr_sum(So, N, z, sigma=sig)) < tol
+    if n > 32:       # the pivoted teams keep 1e-11
+        ctx.set_option(L.OPT_RESOLVENT_ALGO, 1)
+        try:
+            assert rel(R.resolvent_sum(z, scale=1 / N ** 3), ref) < 1e-11
+        finally:
+            ctx.set_option(L.OPT_RESOLVENT_ALGO, 0)
     Hk, k, w = R.copy_out()
     assert rel(Hk.reshape(n, n, N, N, N, order="F"), orc.grid_eval_full(So, N)) < 1e-13
     assert np.all(w == 1.0) and k.shape == (N ** 3, 3) and abs(k[1, 0] - 1 / N) < 1e-16
     R.materialize()
-    assert rel(R.resolvent_sum(z, scale=1 / N ** 3), ref) < 1e-11
+    assert rel(R.resolvent_sum(z, scale=1 / N ** 3), ref) < tol
     # k3 slabs are additive (the multi-GPU shard unit)
     parts = [L.DeviceRule(ctx, S, N, k3_lo=a, k3_hi=b).resolvent_sum(z, scale=1 / N ** 3) for a, b in ((0, 1), (1, 3), (3, N))]
-    assert rel(sum(parts), ref) < 1e-11
+    assert rel(sum(parts), ref) < tol
     # eigenvalues vs LAPACK and eigenvalue sums vs oracle
     ev = R.eigvals()
     assert rel(ev, np.linalg.eigvalsh(np.moveaxis(Hk, 2, 0))) < 1e-11
@@ -58,7 +67,7 @@ def test_rule_sums_and_values_vs_oracle(ctx, orc, n, rmax, N):
     # scattered points
     kp = rng.random((9, 3))
     assert rel(S.eval_points(kp), orc.eval_points(So, kp)) < 1e-13
-    assert rel(S.points_resolvent(kp, z), orc.resolvent_trace_batch(orc.eval_points(So, kp), z)) < 1e-11
+    assert rel(S.points_resolvent(kp, z), orc.resolvent_trace_batch(orc.eval_points(So, kp), z)) < tol
 
 
 @pytest.mark.parametrize("algo", [1, 2])

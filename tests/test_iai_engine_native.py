@@ -209,3 +209,69 @@ def test_engine_lanes_do_not_change_results(orc, eng, svo, leaf, monkeypatch):
             res.append((I, E, ne))
         assert res[0] == res[1] == res[2]
     monkeypatch.delenv("IAI_CPU_LANES", raising=False)
+
+
+# ---- general iterated limits: several segments per level, limits served by a callback --------------------------------------
+LIMITS_FN = C.CFUNCTYPE(C.c_int32, C.c_int32, c_dp, c_dp, C.c_int32, C.c_void_p)
+
+
+def _solve_general(lib, S, ndim, lims, fkind, vkind, z, lin, atol, rtol, leaf, maxevals=2 ** 62, cap2=64, cap1=2048):
+    import orc as _orc
+    i3 = lambda v: (C.c_int * 3)(*[int(x) for x in v])
+    d3 = lambda v: (C.c_double * 3)(*[float(x) for x in v])
+    zz = np.array([z.real, z.imag])
+    ln = None if lin is None else np.ascontiguousarray(lin, dtype=np.float64)
+    out = np.zeros(3)
+    st = (C.c_long * 4)()
+    dp = lambda a: None if a is None else a.ctypes.data_as(c_dp)
+    cb = C.cast(_orc.limits_callback(lims), LIMITS_FN)
+    cb._keep = lims
+    rc = lib.iai_cpu_solve_general(dp(S.c), C.c_int(S.n), C.c_int(ndim), i3(S.M), i3(S.lo), d3(S.period), cb, None,
+                                   C.c_int(fkind), C.c_int(vkind), dp(zz), None, dp(ln), C.c_double(atol), C.c_double(rtol),
+                                   C.c_long(maxevals), C.c_int(int(leaf)), C.c_long(cap2), C.c_long(cap1), C.c_int(0), C.c_int(1),
+                                   XFN(0), dp(out), st)
+    return rc, complex(out[0], out[1]), out[2], int(st[0]), int(st[1])
+
+
+@pytest.mark.parametrize("leaf", [False, True])
+def test_engine_general_limits_match_recursion(orc, eng, svo, leaf):
+    """Several initial segments per 1-D integral (QuadGK's do_quadgk over a PuncturedInterval, src/fourier.jl:493-500) and limits
+    obtained through the segments / fixandeliminate callback: the engine against the oracle's recursion over the SAME limits
+    object - identical numevals; TetrahedralLimits served through the callback must reproduce the built-in kind bit for bit."""
+    import autobz_b200 as ab
+    H, lo, A = svo
+    S = orc.Series(H, lo)
+    z = complex(12.5, 0.05)
+    seg = ab.SegmentedLimits((0.0, 0.2, 0.5), (0.0, 0.25, 0.3, 0.5), (0.0, 0.1, 0.5))
+    Io, Eo, neo = orc.iai_general(S, 3, seg, vkind=1, z=z, atol=2e-3)
+    rc, I, E, ne, _ = _solve_general(eng, S, 3, seg, 0, 1, z, None, 2e-3, 0.0, leaf)
+    assert rc == 0 and ne == neo and abs(I - Io) <= 1e-13 * abs(Io) and abs(E - Eo) <= 1e-9 * Eo
+    # one segment per level == CubicLimits
+    one = ab.SegmentedLimits((0.0, 0.5), (0.0, 0.5), (0.0, 0.5))
+    Ic, Ec, nec = orc.iai(S, 3, 0, [0.0] * 3, [0.5] * 3, vkind=1, z=z, atol=2e-3)
+    rc, I, E, ne, _ = _solve_general(eng, S, 3, one, 0, 1, z, None, 2e-3, 0.0, leaf)
+    assert rc == 0 and ne == nec and I == Ic and E == Ec
+    # the tetrahedron through the callback == the built-in TetrahedralLimits
+    tet = ab.TetrahedralLimits([0.5] * 3)
+    rc0, I0, E0, ne0, _ = _solve(eng, S, 3, 1, [0.5] * 3, None, 0, 1, z, None, 1e-3, 0.0, leaf)
+    rc, I, E, ne, _ = _solve_general(eng, S, 3, tet, 0, 1, z, None, 1e-3, 0.0, leaf)
+    assert rc == rc0 == 0 and ne == ne0 and I == I0 and E == E0
+
+
+def test_engine_polyhedron_volumes(orc, eng):
+    """nested_quad(1, lims) over hand-built convex polyhedra = their volume (the reference checks its IBZ limits this way,
+    test/test_ibz.jl:121-149): tetrahedron, cube, octahedron, a sheared prism - through PolyhedronLimits' slices and the callback"""
+    import autobz_b200 as ab
+    S = orc.Series(np.zeros((1, 1, 1, 1, 1), complex), (0, 0, 0))
+    shapes = {
+        "tetrahedron": ([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)], 1 / 6),
+        "cube": ([(x, y, z) for x in (0, 0.5) for y in (0, 0.5) for z in (0, 0.5)], 0.125),
+        "octahedron": ([(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)], 4 / 3),
+        "sheared prism": ([(0, 0, 0), (1, 0, 0), (0.3, 1, 0), (0.2, 0.1, 0.7), (1.2, 0.1, 0.7), (0.5, 1.1, 0.7)], 0.35),
+    }
+    for name, (verts, vol) in shapes.items():
+        lims = ab.PolyhedronLimits(np.array(verts, dtype=float))
+        rc, I, E, ne, _ = _solve_general(eng, S, 3, lims, 1, 2, 0j, [0.0, 0.0, 1.0, 0.0], 1e-10, 0.0, False)
+        Io, Eo, neo = orc.iai_general(S, 3, lims, vkind=2, lin=(0.0, 1.0), atol=1e-10)
+        assert rc == 0 and abs(I.real - vol) < 1e-8, (name, I, vol)
+        assert ne == neo and abs(I - Io) <= 1e-13 * abs(Io)
