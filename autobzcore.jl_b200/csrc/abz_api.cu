@@ -103,8 +103,8 @@ struct IaiLane {
     cudaStream_t stream = nullptr;
     void* pin_in = nullptr; size_t pin_in_cap = 0;
     void* pin_out = nullptr; size_t pin_out_cap = 0;
-    DevBuf in, out, spill;
-    size_t ns = 0, nt = 0;
+    DevBuf in, out, spill, mid_spill;
+    size_t ns = 0, nt = 0, nm = 0;
     ~IaiLane() {
         if (pin_in) cudaFreeHost(pin_in);
         if (pin_out) cudaFreeHost(pin_out);
@@ -669,6 +669,9 @@ cudaError_t opt_in_dynamic_smem() {
     ABZ_OPT_IN(iai_leaf_kernel<1>, 160 * 1024);
     ABZ_OPT_IN(iai_leaf_kernel<2>, 160 * 1024);
     ABZ_OPT_IN(iai_leaf_kernel<3>, 160 * 1024);
+    ABZ_OPT_IN(iai_mid_kernel<1>, 200 * 1024);
+    ABZ_OPT_IN(iai_mid_kernel<2>, 200 * 1024);
+    ABZ_OPT_IN(iai_mid_kernel<3>, 200 * 1024);
 #undef ABZ_OPT_IN
     cudaError_t r = mma_resolvent_opt_in();
     if (r != cudaSuccess && e == cudaSuccess) e = r;
@@ -1891,10 +1894,10 @@ struct IaiDeviceBackend {
         Series* s = nst->s;
         const int n = s->n;
         const long nn = (long)n * n;
-        const size_t n3 = R.c3_x.size(), n2 = R.c2_x.size(), ns = R.seg_a.size(), nt = R.task_a.size();
+        const size_t n3 = R.c3_x.size(), n2 = R.c2_x.size(), ns = R.seg_a.size(), nt = R.task_a.size(), nm = R.mid_a.size();
         if (n3 > 0 && nst->ndim != 3) return fail(ctx, ABZ_E_INVALID, "internal: level-2 contraction on a nest with ndim < 3");
         cudaStream_t st = ln.stream;
-        const size_t words = 2 * n3 + 3 * n2 + 3 * ns + 4 * nt;
+        const size_t words = 2 * n3 + 3 * n2 + 3 * ns + 4 * nt + 4 * nm;
         int rc = pin_reserve(ctx, &ln.pin_in, &ln.pin_in_cap, words * 8);
         if (rc) return rc;
         CU(ctx, ln.in.reserve(words * 8 + 8));
@@ -1906,6 +1909,8 @@ struct IaiDeviceBackend {
         const size_t o_sa = put(R.seg_a.data(), ns), o_sb = put(R.seg_b.data(), ns), o_ss = put(R.seg_slot.data(), ns);
         const size_t o_ta = put(R.task_a.data(), nt), o_tb = put(R.task_b.data(), nt), o_tt = put(R.task_atol.data(), nt),
                      o_ts = put(R.task_slot.data(), nt);
+        const size_t o_ma = put(R.mid_a.data(), nm), o_mb = put(R.mid_b.data(), nm), o_mt = put(R.mid_atol.data(), nm),
+                     o_ms = put(R.mid_slot.data(), nm);
         if (words) CU(ctx, cudaMemcpyAsync(ln.in.p, h, words * 8, cudaMemcpyHostToDevice, st));
         const double* dD = ln.in.as<double>();
         const long* dL = ln.in.as<long>();
@@ -1925,7 +1930,7 @@ struct IaiDeviceBackend {
                 s->M[1], s->lo[1], s->period[1]);
             LAUNCH_CHECK(ctx, "nest_contract_kernel");
         }
-        const size_t owords = 4 * ns + 4 * nt + 1;
+        const size_t owords = 4 * ns + 4 * nt + 5 * nm + 1;
         rc = pin_reserve(ctx, &ln.pin_out, &ln.pin_out_cap, owords * 8);
         if (rc) return rc;
         CU(ctx, ln.out.reserve(owords * 8));
@@ -1951,20 +1956,24 @@ struct IaiDeviceBackend {
             rc = launch_leaf(dD + o_ta, dD + o_tb, dD + o_tt, dL + o_ts, (long)nt, dout + 4 * ns, st, ln.spill);
             if (rc) return rc;
         }
-        CU(ctx, cudaMemcpyAsync(dout + 4 * ns + 4 * nt, ef, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        if (nm) {
+            rc = launch_mid(dD + o_ma, dD + o_mb, dD + o_mt, dL + o_ms, (long)nm, dout + 4 * ns + 4 * nt, st, ln.mid_spill);
+            if (rc) return rc;
+        }
+        CU(ctx, cudaMemcpyAsync(dout + 4 * ns + 4 * nt + 5 * nm, ef, sizeof(int), cudaMemcpyDeviceToDevice, st));
         CU(ctx, cudaMemcpyAsync(ln.pin_out, dout, owords * 8, cudaMemcpyDeviceToHost, st));
-        ln.ns = ns; ln.nt = nt;
+        ln.ns = ns; ln.nt = nt; ln.nm = nm;
         return ABZ_OK;
     }
 
     int collect(IaiLane& ln, abz_iai::Round& R) {
         CU(ctx, cudaStreamSynchronize(ln.stream));
-        return unpack((const double*)ln.pin_out, ln.ns, ln.nt, R);
+        return unpack((const double*)ln.pin_out, ln.ns, ln.nt, ln.nm, R);
     }
 
-    int unpack(const double* ho, size_t ns, size_t nt, abz_iai::Round& R) {
+    int unpack(const double* ho, size_t ns, size_t nt, size_t nm, abz_iai::Round& R) {
         int flag = 0;
-        memcpy(&flag, ho + 4 * ns + 4 * nt, sizeof(int));
+        memcpy(&flag, ho + 4 * ns + 4 * nt + 5 * nm, sizeof(int));
         if (flag) {
             cudaMemsetAsync(ctx->errflag.as<int>(), 0, sizeof(int), ctx->stream);
             if ((flag & 2) && !(flag & 1) && !ctx->force_generic) return ABZ_RETRY_PIVOTED;
@@ -1984,6 +1993,14 @@ struct IaiDeviceBackend {
             int64_t ne; memcpy(&ne, ht + 4 * i + 3, 8);
             R.task_ne[i] = ne;
         }
+        R.mid_I.resize(nm); R.mid_E.resize(nm); R.mid_ne.resize(nm);
+        const double* hm = ho + 4 * ns + 4 * nt;
+        for (size_t i = 0; i < nm; i++) {
+            R.mid_I[i] = abz_iai::cplx{hm[5 * i], hm[5 * i + 1]};
+            R.mid_E[i] = hm[5 * i + 2];
+            int64_t ne; memcpy(&ne, hm + 5 * i + 3, 8);
+            R.mid_ne[i] = ne;
+        }
         return ABZ_OK;
     }
 
@@ -2000,10 +2017,10 @@ struct IaiDeviceBackend {
         Series* s = nst->s;
         const int n = s->n;
         const long nn = (long)n * n;
-        const size_t n3 = R.c3_x.size(), n2 = R.c2_x.size(), ns = R.seg_a.size(), nt = R.task_a.size();
+        const size_t n3 = R.c3_x.size(), n2 = R.c2_x.size(), ns = R.seg_a.size(), nt = R.task_a.size(), nm = R.mid_a.size();
         if (n3 > 0 && nst->ndim != 3) return fail(ctx, ABZ_E_INVALID, "internal: level-2 contraction on a nest with ndim < 3");
-        // ---- pack [c3_x | c3_slot | c2_x | c2_parent | c2_slot | seg_a | seg_b | seg_slot | task_a | task_b | task_atol | task_slot]
-        const size_t words = 2 * n3 + 3 * n2 + 3 * ns + 4 * nt;
+        // ---- pack [c3_x | c3_slot | c2_x | c2_parent | c2_slot | seg_a | seg_b | seg_slot | task_a | task_b | task_atol | task_slot | mid_*]
+        const size_t words = 2 * n3 + 3 * n2 + 3 * ns + 4 * nt + 4 * nm;
         int rc = pin_reserve(ctx, &ctx->pin_in, &ctx->pin_in_cap, words * 8);
         if (rc) return rc;
         CU(ctx, ctx->iai_in.reserve(words * 8 + 8));
@@ -2015,6 +2032,8 @@ struct IaiDeviceBackend {
         const size_t o_sa = put(R.seg_a.data(), ns), o_sb = put(R.seg_b.data(), ns), o_ss = put(R.seg_slot.data(), ns);
         const size_t o_ta = put(R.task_a.data(), nt), o_tb = put(R.task_b.data(), nt), o_tt = put(R.task_atol.data(), nt),
                      o_ts = put(R.task_slot.data(), nt);
+        const size_t o_ma = put(R.mid_a.data(), nm), o_mb = put(R.mid_b.data(), nm), o_mt = put(R.mid_atol.data(), nm),
+                     o_ms = put(R.mid_slot.data(), nm);
         if (words) CU(ctx, cudaMemcpyAsync(ctx->iai_in.p, h, words * 8, cudaMemcpyHostToDevice, ctx->stream));
         const double* dD = ctx->iai_in.as<double>();
         const long* dL = ctx->iai_in.as<long>();
@@ -2036,7 +2055,7 @@ struct IaiDeviceBackend {
             LAUNCH_CHECK(ctx, "nest_contract_kernel");
         }
         // ---- innermost panels
-        const size_t owords = 4 * ns + 4 * nt + 1;
+        const size_t owords = 4 * ns + 4 * nt + 5 * nm + 1;
         rc = pin_reserve(ctx, &ctx->pin_out, &ctx->pin_out_cap, owords * 8);
         if (rc) return rc;
         CU(ctx, ctx->iai_out.reserve(owords * 8));
@@ -2084,10 +2103,37 @@ struct IaiDeviceBackend {
             rc = launch_leaf(dD + o_ta, dD + o_tb, dD + o_tt, dL + o_ts, (long)nt, dout + 4 * ns, ctx->stream, ctx->tmp_d);
             if (rc) return rc;
         }
-        CU(ctx, cudaMemcpyAsync(dout + 4 * ns + 4 * nt, ef, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (nm) {
+            if (n > 3) return fail(ctx, ABZ_E_UNSUPPORTED, "device-side middle integrals need norb <= 3");
+            rc = launch_mid(dD + o_ma, dD + o_mb, dD + o_mt, dL + o_ms, (long)nm, dout + 4 * ns + 4 * nt, ctx->stream, ctx->tmp_c);
+            if (rc) return rc;
+        }
+        CU(ctx, cudaMemcpyAsync(dout + 4 * ns + 4 * nt + 5 * nm, ef, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
         CU(ctx, cudaMemcpyAsync(ctx->pin_out, dout, owords * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
-        return unpack((const double*)ctx->pin_out, ns, nt, R);
+        return unpack((const double*)ctx->pin_out, ns, nt, nm, R);
+    }
+
+    // whole middle integrals (3-d, norb <= 3): one CTA each, see iai_mid_kernel
+    int lkind = 0; double lim_a[3] = {0, 0, 0}, lim_b[3] = {0, 0, 0};
+    int launch_mid(const double* ma, const double* mb, const double* mt, const long* ms, long nm, double* out, cudaStream_t st,
+                   DevBuf& spillbuf) {
+        Series* s = nst->s;
+        const long stride2 = (long)s->n * s->n * s->M[0] * s->M[1];
+        const int spill_cap = ctx->leaf_spill;
+        CU(ctx, spillbuf.reserve((size_t)nm * 2 * MID_WARPS * std::max(spill_cap, 1) * sizeof(LeafSeg) + 64));
+        const size_t smem = sizeof(MidShared) + (size_t)MID_WARPS * ((size_t)s->M[0] * s->n * s->n + s->M[1]) * sizeof(double2);
+        if (smem > 200 * 1024) return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension for the IAI middle kernel");
+        LeafSeg* spill = reinterpret_cast<LeafSeg*>(spillbuf.as<char>() + 64);
+#define MID_LAUNCH(NORB)                                                                                               \
+    iai_mid_kernel<NORB><<<(unsigned)(2 * nm), MID_WARPS * 32, smem, st>>>(nst->L2, stride2, ma, mb, mt, ms, lkind, lim_a[0], lim_b[0], lim_a[1], \
+                                                                    s->M[0], s->lo[0], s->period[0], s->M[1], s->lo[1], s->period[1], fkind, vkind, z, \
+                                                                    dsig, la, lb, rtol, (long long)maxevals, spill, spill_cap, out, \
+                                                                    ctx->errflag.as<int>())
+        if (s->n == 1) MID_LAUNCH(1); else if (s->n == 2) MID_LAUNCH(2); else MID_LAUNCH(3);
+#undef MID_LAUNCH
+        LAUNCH_CHECK(ctx, "iai_mid_kernel");
+        return ABZ_OK;
     }
 
     int launch_leaf(const double* ta, const double* tb, const double* tt, const long* ts, long nt, double* out, cudaStream_t st,
@@ -2176,7 +2222,10 @@ static int32_t iai_solve_impl(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
     be.lb = abz_iai::cplx{lin ? lin[2] : 0.0, lin ? lin[3] : 0.0};
     be.rtol = rtol; be.maxevals = maxevals;
     be.xfn = exchange; be.xuser = exchange_user;
-    const bool leaf = (flags & ABZ_IAI_DEVICE_LEAVES) && s->n <= 3 && nst->ndim >= 2;
+    const bool leaf = (flags & (ABZ_IAI_DEVICE_LEAVES | ABZ_IAI_DEVICE_MIDDLES)) && s->n <= 3 && nst->ndim >= 2;
+    const bool mid = leaf && (flags & ABZ_IAI_DEVICE_MIDDLES) && nst->ndim == 3 && lkind != 2;
+    be.lkind = lkind;
+    for (int d = 0; d < 3; d++) { be.lim_a[d] = lims.a[d]; be.lim_b[d] = lims.b[d]; }
     const long launches0 = ctx->launches;
     {   // rounds in flight: the fused small-orbital kernels can overlap (a round uses a small part of the chip and is
         // bound by the dependent chain of its deepest innermost integral); ABZ_IAI_LANES overrides
@@ -2185,7 +2234,7 @@ static int32_t iai_solve_impl(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
         rc = be.init_lanes((s->n <= 3 && nst->ndim >= 2 && nranks == 1) ? want : 1);   // sharded solves keep one round at a time
         if (rc) return rc;
     }
-    abz_iai::Engine<IaiDeviceBackend> eng(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, leaf, rank, nranks);
+    abz_iai::Engine<IaiDeviceBackend> eng(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, leaf, rank, nranks, mid);
     rc = eng.run();
     ctx->force_generic = false;
     if (rc && be.nlanes > 1) {

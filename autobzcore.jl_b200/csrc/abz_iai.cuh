@@ -6,6 +6,7 @@
 #include "abz_common.cuh"
 #include "abz_kernels.cuh"
 #include "abz_iai_engine.hpp"
+#include <cooperative_groups.h>
 
 namespace abz {
 
@@ -309,13 +310,15 @@ iai_leaf_kernel(const double2* __restrict__ L1, long l1_stride, const double* __
 }
 
 // ---- device-side MIDDLE integrals (3-d solves) -----------------------------------------------------------------------------
-// One CTA per middle-level adaptive integral (over x2, for the series contracted at one x3 node in a level-2 slot): the CTA keeps
+// One CLUSTER of two CTAs (2 x 16 warps: one warp for each of the 30 nodes of a refinement step) per middle-level adaptive integral
+// (over x2, for the series contracted at one x3 node in a level-2 slot): CTA 0 of the pair keeps
 // that integral's segment heap in shared memory and runs QuadGK's loop itself - pop the worst segment, bisect, and for each of
 // the 30 new nodes x2: contract the level-2 series at x2 (workspace_contract!, src/fourier.jl:478), inner abstol = abstol / len
 // (:479-480), and run the whole innermost adaptive integral (leaf_integrate, one warp per node, nodes handed out dynamically);
 // then the two panels are combined in evalrule's order, pushed, and the convergence test decides.  No host round trip below the
 // outermost level: a round of the host engine is one refinement step of the OUTERMOST integral.  Same arithmetic and the same
-// decisions as the host-driven engine, hence identical numevals.
+// decisions as the host-driven engine, hence identical numevals.  The two CTAs meet in two cluster barriers per step; node values
+// and the step's panels travel through distributed shared memory.
 //   lkind 0: x1 in [la1, lb1];  1: x1 in [0, la1 * x2 / la2]   (CubicLimits / TetrahedralLimits)
 // out[5 t ..]: I.re, I.im, E, (int64) evaluations of all innermost integrals, (int64) evaluations of this integral's own nodes
 constexpr int MID_WARPS = 16;
@@ -331,7 +334,7 @@ struct MidShared {
 };
 
 template <int NORB>
-__global__ void __launch_bounds__(MID_WARPS * 32)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MID_WARPS * 32)
 iai_mid_kernel(const double2* __restrict__ L2, long l2_stride, const double* __restrict__ task_a, const double* __restrict__ task_b,
                const double* __restrict__ task_atol, const long* __restrict__ task_slot, int lkind, double la1, double lb1, double la2,
                int M1, int lo1, double period1, int M2, int lo2, double period2, int fkind, int vkind, double2 z,
@@ -339,23 +342,28 @@ iai_mid_kernel(const double2* __restrict__ L2, long l2_stride, const double* __r
                LeafSeg* __restrict__ spill, int spill_cap, double* __restrict__ out, int* __restrict__ errflag) {
     constexpr int NN = NORB * NORB;
     extern __shared__ __align__(16) unsigned char mid_raw[];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
     MidShared& sm = *reinterpret_cast<MidShared*>(mid_raw);
+    MidShared* sm0 = cluster.map_shared_rank(&sm, 0);                               // the pair's CTA 0 (owner of the heap)
+    MidShared* sm1 = cluster.map_shared_rank(&sm, 1);
     double2* coef = reinterpret_cast<double2*>(mid_raw + sizeof(MidShared));      // [MID_WARPS][M1*NN]
     double2* phase = coef + MID_WARPS * (M1 * NN);                                 // [MID_WARPS][M2]
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long task = blockIdx.x;
+    const long task = blockIdx.x >> 1;
     const double2* src = L2 + task_slot[task] * l2_stride;                         // [M2][M1*NN]
     const double atol = task_atol[task];
     const int rows = M1 * NN;
     double2* c = coef + w * rows;
     double2* ph = phase + w * M2;
-    LeafSeg* hg = spill + (task * MID_WARPS + w) * (long)(spill_cap > 0 ? spill_cap : 1);
+    LeafSeg* hg = spill + ((task * 2 + crank) * MID_WARPS + w) * (long)(spill_cap > 0 ? spill_cap : 1);
     const int cap_leaf = spill_cap < 0 ? -spill_cap : LEAF_SMEM_SEGS + spill_cap;
     if (threadIdx.x == 0) {
         sm.pa[0] = task_a[task]; sm.pb[0] = task_b[task];
         sm.counter = 0; sm.ntasks = 15; sm.go = 1; sm.ne_leaves = 0ull;
     }
-    __syncthreads();
+    cluster.sync();
     abz_iai::cplx I{0.0, 0.0};           // thread 0 only
     double E = 0.0;
     long len = 0;
@@ -366,7 +374,7 @@ iai_mid_kernel(const double2* __restrict__ L2, long l2_stride, const double* __r
         // ---- the nodes of this step's panels, handed to the warps one at a time
         for (;;) {
             int t = 0;
-            if (lane == 0) t = atomicAdd(&sm.counter, 1);
+            if (lane == 0) t = 2 * atomicAdd(&sm.counter, 1) + crank;      // this CTA's share: every other node
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= sm.ntasks) break;
             const int p = t / 15, jn = t - 15 * p;
@@ -391,14 +399,14 @@ iai_mid_kernel(const double2* __restrict__ L2, long l2_stride, const double* __r
             leaf_integrate<NORB>(c, sm.leaf_heap[w], hg, cap_leaf, sm.leaf_vals[w], ca, cb, catol, M1, lo1, period1, fkind, vkind, z, sigma,
                                  la, lb, rtol, maxevals, errflag, &Iv, &Ev, &ne);
             if (lane == 0) {
-                sm.node_vals[16 * p + jn] = Iv;
+                sm0->node_vals[16 * p + jn] = Iv;                          // distributed shared memory: CTA 0 combines
                 atomicAdd(&sm.ne_leaves, (unsigned long long)ne);
                 if (!isfinite(Ev)) atomicOr(errflag, 1);
             }
         }
-        __syncthreads();
-        // ---- combine, push, decide (thread 0: the DataStructures heap with Reverse on E, as the host engine)
-        if (threadIdx.x == 0) {
+        cluster.sync();
+        // ---- combine, push, decide (thread 0 of CTA 0: the DataStructures heap with Reverse on E, as the host engine)
+        if (crank == 0 && threadIdx.x == 0) {
             int go = 1;
 #define MID_AT(i) sm.heap[(i) - 1]
             if (first) {
@@ -457,16 +465,19 @@ iai_mid_kernel(const double2* __restrict__ L2, long l2_stride, const double* __r
                 }
                 const double mid = (popped.a + popped.b) / 2;
                 sm.pa[0] = popped.a; sm.pb[0] = mid; sm.pa[1] = mid; sm.pb[1] = popped.b;
-                sm.ntasks = 30;
+                sm1->pa[0] = popped.a; sm1->pb[0] = mid; sm1->pa[1] = mid; sm1->pb[1] = popped.b;
+                sm.ntasks = 30; sm1->ntasks = 30;
             }
-            sm.counter = 0;
-            sm.go = go;
+            sm.counter = 0; sm1->counter = 0;
+            sm.go = go; sm1->go = go;
         }
         first = false;
-        __syncthreads();
+        cluster.sync();
         if (!sm.go) break;
     }
-    if (threadIdx.x == 0) {
+    if (crank == 1 && threadIdx.x == 0) atomicAdd(&sm0->ne_leaves, sm.ne_leaves);
+    cluster.sync();
+    if (crank == 0 && threadIdx.x == 0) {
         abz_iai::cplx Iv{MID_AT(1).Ire, MID_AT(1).Iim};
         double Ev = MID_AT(1).E;
         for (long k = 2; k <= len; k++) { Iv.re += MID_AT(k).Ire; Iv.im += MID_AT(k).Iim; Ev += MID_AT(k).E; }

@@ -214,10 +214,14 @@ struct Round {
     // leaf tasks: whole innermost adaptive integrals
     std::vector<double> task_a, task_b, task_atol; std::vector<int64_t> task_slot;
     std::vector<cplx> task_I; std::vector<double> task_E; std::vector<int64_t> task_ne;   // outputs
+    // middle tasks (3-d solves): whole level-1 adaptive integrals over x2 on the series in level-2 slot `slot`
+    std::vector<double> mid_a, mid_b, mid_atol; std::vector<int64_t> mid_slot;
+    std::vector<cplx> mid_I; std::vector<double> mid_E; std::vector<int64_t> mid_ne;       // outputs (mid_ne: innermost evaluations)
     void clear_inputs() {
         c3_x.clear(); c3_slot.clear(); c2_x.clear(); c2_parent.clear(); c2_slot.clear();
         seg_a.clear(); seg_b.clear(); seg_slot.clear();
         task_a.clear(); task_b.clear(); task_atol.clear(); task_slot.clear();
+        mid_a.clear(); mid_b.clear(); mid_atol.clear(); mid_slot.clear();
     }
 };
 
@@ -234,14 +238,18 @@ enum { IAI_OK = 0, IAI_E_NAN = -4, IAI_E_ARENA = -2, IAI_E_STALL = -7, IAI_E_LIM
 template <class Backend>
 class Engine {
 public:
+    // mid_tasks: in 3-d solves over CubicLimits / TetrahedralLimits the middle integrals (one per node of the outermost panels) are
+    // handed to the backend whole as well (abz_iai.cuh, iai_mid_kernel): a round is then one refinement step of the OUTERMOST integral
     Engine(Backend& be, int ndim, const Limits& lims, double atol, double rtol, int64_t maxevals, int64_t cap2,
-           int64_t cap1, bool leaf_tasks, int rank = 0, int nranks = 1)
+           int64_t cap1, bool leaf_tasks, int rank = 0, int nranks = 1, bool mid_tasks = false)
         : be_(be), ndim_(ndim), lims_(lims), atol_(atol), rtol_(rtol), maxevals_(maxevals),
-          leaf_tasks_(leaf_tasks && ndim >= 2), rank_(rank), nranks_(ndim >= 2 ? nranks : 1) {
+          leaf_tasks_(leaf_tasks && ndim >= 2), mid_tasks_(mid_tasks && leaf_tasks && ndim == 3 && lims.kind != 2),
+          rank_(rank), nranks_(ndim >= 2 ? nranks : 1) {
         for (int64_t i = cap2 - 1; i >= 0; i--) free2_.push_back(i);
         for (int64_t i = cap1 - 1; i >= 0; i--) free1_.push_back(i);
         L_ = be.lanes() < 1 ? 1 : be.lanes();
         q_seg_.resize(L_); q_task_.resize(L_); fl_seg_.resize(L_); fl_task_.resize(L_);
+        q_mid_.resize(L_); fl_mid_.resize(L_);
         cur_.resize(L_); next_.resize(L_); inflight_.assign(L_, 0);
     }
 
@@ -260,12 +268,12 @@ public:
         while (!done_) {
             // start a round in every idle lane that has work queued
             for (int g = 0; g < L_ && !local_rc; g++) {
-                if (inflight_[g] || (q_seg_[g].empty() && q_task_[g].empty())) continue;
+                if (inflight_[g] || (q_seg_[g].empty() && q_task_[g].empty() && q_mid_[g].empty())) continue;
                 rounds++;
                 cur_[g].clear_inputs();
                 std::swap(cur_[g], next_[g]);           // cur_ = inputs queued so far, next_ = empty
-                fl_seg_[g].clear(); fl_task_[g].clear();
-                fl_seg_[g].swap(q_seg_[g]); fl_task_[g].swap(q_task_[g]);
+                fl_seg_[g].clear(); fl_task_[g].clear(); fl_mid_[g].clear();
+                fl_seg_[g].swap(q_seg_[g]); fl_task_[g].swap(q_task_[g]); fl_mid_[g].swap(q_mid_[g]);
                 rc = be_.submit(g, cur_[g]);
                 if (rc) { local_rc = rc; break; }
                 inflight_[g] = 1;
@@ -299,6 +307,12 @@ public:
                 if (!std::isfinite(E)) rc = nan_error(pends_[tasks[i].pend]);
                 else rc = child_done(tasks[i].q, tasks[i].pend, tasks[i].i, tasks[i].slot, R.task_I[i]);
             }
+            const std::vector<Item>& mids = fl_mid_[g];
+            for (size_t i = 0; i < mids.size() && !rc; i++) {
+                numevals += R.mid_ne[i];
+                if (!std::isfinite(R.mid_E[i])) rc = nan_error(pends_[mids[i].pend]);
+                else rc = child_done(mids[i].q, mids[i].pend, mids[i].i, mids[i].slot, R.mid_I[i]);
+            }
             if (rc) local_rc = rc;
         }
         drain();
@@ -322,14 +336,14 @@ private:
     struct Item { int q, pend, i; int64_t slot; };
 
     Backend& be_;
-    int ndim_; Limits lims_; double atol_, rtol_; int64_t maxevals_; bool leaf_tasks_;
+    int ndim_; Limits lims_; double atol_, rtol_; int64_t maxevals_; bool leaf_tasks_, mid_tasks_;
     int rank_, nranks_; int64_t spawn_counter_ = 0;
     std::vector<std::pair<int, int>> shared_pends_;    // outstanding (integral, panel) of the outermost integral, creation order
     std::deque<Integral> ints_; std::vector<int> free_int_;
     std::deque<Pend> pends_; std::vector<int> free_pend_;
     std::vector<int64_t> free2_, free1_;
     int L_ = 1; int64_t lane_counter_ = 0;
-    std::vector<std::vector<Item>> q_seg_, q_task_, fl_seg_, fl_task_;   // per lane: queued / in flight
+    std::vector<std::vector<Item>> q_seg_, q_task_, fl_seg_, fl_task_, q_mid_, fl_mid_;   // per lane: queued / in flight
     std::vector<Round> cur_, next_;
     std::vector<char> inflight_;
     std::deque<int> fifo_;                                               // lanes in flight, oldest first
@@ -414,6 +428,11 @@ private:
             if (level == 2) { nx.c3_x.push_back(x); nx.c3_slot.push_back(slot); }
             else { nx.c2_x.push_back(x); nx.c2_parent.push_back(ints_[qi].slot); nx.c2_slot.push_back(slot); }
             const double catol = ints_[qi].atol / len;        // inner abstol = abstol/len (src/fourier.jl:479-480)
+            if (level == 2 && mid_tasks_ && csegs.size() == 2) {
+                q_mid_[g].push_back(Item{qi, pend, i, slot});
+                nx.mid_a.push_back(ca); nx.mid_b.push_back(cb); nx.mid_atol.push_back(catol); nx.mid_slot.push_back(slot);
+                continue;
+            }
             if (level == 1 && leaf_tasks_ && csegs.size() == 2) {
                 q_task_[g].push_back(Item{qi, pend, i, slot});
                 nx.task_a.push_back(ca); nx.task_b.push_back(cb); nx.task_atol.push_back(catol);

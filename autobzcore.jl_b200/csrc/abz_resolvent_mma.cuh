@@ -23,6 +23,7 @@
 // exchanges is safe; the kernel monitors the smallest pivot against max|a_ij| and raises a flag when
 // the smallest pivot falls below 2e-3 max|a_ij|, on which the host reruns the call with the pivoted Gauss-Jordan kernel.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include "abz_common.cuh"
 
@@ -101,6 +102,165 @@ __device__ __forceinline__ void inv8(double& xr0, double& xr1, double& xi0, doub
             if (sg) { xr1 = cr; xi1 = ci; } else { xr0 = cr; xi0 = ci; }
         }
     }
+}
+
+// One pivot step of inv8 in two halves, so that independent DMMA work can be placed BETWEEN them in program order: the exchange
+// (eight shuffles: pivot row, pivot, this row's multiplier) and the arithmetic.  The compiler keeps shuffles and mma.sync in source
+// order and only floats the scalar FP64 chain, so the block product written between the halves is what fills the chain's latency.
+struct PivIn { double pr0, pr1, pi0, pi1, ppr, ppi, fr, fi; };
+template <int P>
+__device__ __forceinline__ PivIn inv8_exchange(double xr0, double xr1, double xi0, double xi1, int lane) {
+    const int q = lane & 3, quad = lane & ~3;
+    constexpr int sg = P & 1, qp = P >> 1;
+    PivIn v;
+    v.pr0 = __shfl_sync(0xffffffffu, xr0, 4 * P + q); v.pr1 = __shfl_sync(0xffffffffu, xr1, 4 * P + q);
+    v.pi0 = __shfl_sync(0xffffffffu, xi0, 4 * P + q); v.pi1 = __shfl_sync(0xffffffffu, xi1, 4 * P + q);
+    v.ppr = __shfl_sync(0xffffffffu, sg ? xr1 : xr0, 4 * P + qp);
+    v.ppi = __shfl_sync(0xffffffffu, sg ? xi1 : xi0, 4 * P + qp);
+    v.fr = __shfl_sync(0xffffffffu, sg ? xr1 : xr0, quad | qp);
+    v.fi = __shfl_sync(0xffffffffu, sg ? xi1 : xi0, quad | qp);
+    return v;
+}
+template <int P>
+__device__ __forceinline__ void inv8_eliminate(double& xr0, double& xr1, double& xi0, double& xi1, const PivIn& v, int lane, int& minhi) {
+    const int g = lane >> 2, q = lane & 3;
+    constexpr int sg = P & 1, qp = P >> 1;
+    const double d = fma(v.ppr, v.ppr, v.ppi * v.ppi);
+    minhi = min(minhi, __double2hiint(d));
+    const double tr_ = fma(v.fr, v.ppr, v.fi * v.ppi), ti_ = fma(-v.fr, v.ppi, v.fi * v.ppr);
+    const double dinv = fast_rcp(d);
+    double mr = tr_ * dinv, mi = ti_ * dinv;
+    const double rr = v.ppr * dinv, nri = v.ppi * dinv;
+    const bool prow = (g == P);
+    if (prow) { mr = 1.0 - rr; mi = nri; }
+    xr0 = fma(-mr, v.pr0, xr0); xr0 = fma(mi, v.pi0, xr0);
+    xi0 = fma(-mr, v.pi0, xi0); xi0 = fma(-mi, v.pr0, xi0);
+    xr1 = fma(-mr, v.pr1, xr1); xr1 = fma(mi, v.pi1, xr1);
+    xi1 = fma(-mr, v.pi1, xi1); xi1 = fma(-mi, v.pr1, xi1);
+    if (q == qp) {
+        const double cr = prow ? rr : dneg(mr), ci = dneg(prow ? nri : mi);
+        if (sg) { xr1 = cr; xi1 = ci; } else { xr0 = cr; xi0 = ci; }
+    }
+}
+
+// VAR 2 (norb 25..32, NB = 4): the same block LU + trace from the factors as a STATIC SOFTWARE PIPELINE.  Each of the 8 pivot steps
+// of a diagonal-block inversion is issued around one independent block product, and the substitution phase is reformulated so that
+// enough independent products exist for every inversion but the first:
+//   W = -(I + X~)^-1 + I (strict upper, in place over X, rows top down): W_ij = X_ij - sum_{i<t<j} W_it X_tj      - needs no D at all
+//   N = -L~^-1 + I      (strict lower, in place over L, columns left to right): N_ij = L_ij - sum_{j<t<i} L_it N_tj
+//   tr A^-1 = sum_s tr D_s + sum_{i<j} tr(W_ij (D_j N_ji))      (U~^-1 = (I + X~)^-1 diag(D); the two sign flips cancel)
+// schedule:  D0 | L_i0, column 1 | D1 with {X_01, columns 2, 3 of step 0} | L_i1, column 2 | D2 with {X_03, X_12, column 3 of step 1,
+// W_02, N_20, N_30, D1 N_10} | L_32, A_33 | D3 with {X_23, W_03, W_13, N_30, N_31, D2 N_20, D2 N_21} | D3 N_3i and the trace.
+__device__ __forceinline__ double2 warp_trace_inverse_pipelined(double (&R0)[4][4], double (&R1)[4][4], double (&I0)[4][4],
+                                                               double (&I1)[4][4], int lane, int& minpiv) {
+    const int g = lane >> 2, q = lane & 3;
+    const bool par = g & 1;
+    const int src0 = 4 * (2 * q + (par ? 1 : 0)) + (g >> 1);
+    const int src1 = 4 * (2 * q + (par ? 0 : 1)) + (g >> 1);
+    double tr = 0.0, ti = 0.0;
+#define ABZ_FRAG(i, j) to_bfrag(R0[i][j], R1[i][j], I0[i][j], I1[i][j], src0, src1, par)
+    // C_ij -= A_it * b      (trailing update, W and N substitutions)
+#define ABZ_UPD(i, j, t, b) bmm<true>(R0[i][j], R1[i][j], I0[i][j], I1[i][j], R0[i][t], R1[i][t], I0[i][t], I1[i][t], b)
+    // C_ij = A_it * b       (L_is = A_is D_s in place with t = j; X_sj = D_s U_sj in place with i = t)
+#define ABZ_SET(i, j, it, tt, b)                                                                                       \
+    {                                                                                                                  \
+        double c0_ = 0, c1_ = 0, c2_ = 0, c3_ = 0;                                                                     \
+        bmm<false>(c0_, c1_, c2_, c3_, R0[it][tt], R1[it][tt], I0[it][tt], I1[it][tt], b);                             \
+        R0[i][j] = c0_; R1[i][j] = c1_; I0[i][j] = c2_; I1[i][j] = c3_;                                                \
+    }
+    // tr += tr(W_ij * (D_j N_ji)): product in C layout, its fragment against W_ij
+#define ABZ_TRACE(ia, ja)                                                                                              \
+    {                                                                                                                  \
+        const BFrag bn_ = ABZ_FRAG(ja, ia);                                                                            \
+        double c0_ = 0, c1_ = 0, c2_ = 0, c3_ = 0;                                                                     \
+        bmm<false>(c0_, c1_, c2_, c3_, R0[ja][ja], R1[ja][ja], I0[ja][ja], I1[ja][ja], bn_);                           \
+        const BFrag bt_ = to_bfrag(c0_, c1_, c2_, c3_, src0, src1, par);                                               \
+        tr += R0[ia][ja] * bt_.r[0] - I0[ia][ja] * bt_.i[0] + R1[ia][ja] * bt_.r[1] - I1[ia][ja] * bt_.i[1];           \
+        ti += R0[ia][ja] * bt_.i[0] + I0[ia][ja] * bt_.r[0] + R1[ia][ja] * bt_.i[1] + I1[ia][ja] * bt_.r[1];           \
+    }
+#define ABZ_PIV(K, P, WORK)                                                                                            \
+    {                                                                                                                  \
+        const PivIn pv_ = inv8_exchange<P>(R0[K][K], R1[K][K], I0[K][K], I1[K][K], lane);                              \
+        WORK;                                                                                                          \
+        inv8_eliminate<P>(R0[K][K], R1[K][K], I0[K][K], I1[K][K], pv_, lane, minpiv);                                  \
+    }
+#define ABZ_DIAG_TRACE(K)                                                                                              \
+    {                                                                                                                  \
+        if (2 * q == g) { tr += R0[K][K]; ti += I0[K][K]; }                                                            \
+        if (2 * q + 1 == g) { tr += R1[K][K]; ti += I1[K][K]; }                                                        \
+    }
+    // ---- D0 (nothing of this matrix to overlap with)
+    inv8(R0[0][0], R1[0][0], I0[0][0], I1[0][0], lane, minpiv);
+    ABZ_DIAG_TRACE(0)
+    {
+        const BFrag bD0 = ABZ_FRAG(0, 0);
+        ABZ_SET(1, 0, 1, 0, bD0) ABZ_SET(2, 0, 2, 0, bD0) ABZ_SET(3, 0, 3, 0, bD0)            // L_i0 = A_i0 D_0
+    }
+    const BFrag bU01 = ABZ_FRAG(0, 1);
+    ABZ_UPD(1, 1, 0, bU01); ABZ_UPD(2, 1, 0, bU01); ABZ_UPD(3, 1, 0, bU01);                   // column 1 of step 0
+    {   // ---- D1 around X_01 and columns 2, 3 of step 0
+        const BFrag bU02 = ABZ_FRAG(0, 2);
+        ABZ_PIV(1, 0, ABZ_SET(0, 1, 0, 0, bU01))
+        ABZ_PIV(1, 1, ABZ_UPD(1, 2, 0, bU02))
+        ABZ_PIV(1, 2, ABZ_UPD(2, 2, 0, bU02))
+        ABZ_PIV(1, 3, ABZ_UPD(3, 2, 0, bU02))
+        const BFrag bU03 = ABZ_FRAG(0, 3);
+        ABZ_PIV(1, 4, ABZ_SET(0, 2, 0, 0, bU02))
+        ABZ_PIV(1, 5, ABZ_UPD(1, 3, 0, bU03))
+        ABZ_PIV(1, 6, ABZ_UPD(2, 3, 0, bU03))
+        ABZ_PIV(1, 7, ABZ_UPD(3, 3, 0, bU03))
+        ABZ_SET(0, 3, 0, 0, bU03)                                                               // X_03
+    }
+    ABZ_DIAG_TRACE(1)
+    {
+        const BFrag bD1 = ABZ_FRAG(1, 1);
+        ABZ_SET(2, 1, 2, 1, bD1) ABZ_SET(3, 1, 3, 1, bD1)                                       // L_i1
+    }
+    const BFrag bU12 = ABZ_FRAG(1, 2);
+    ABZ_UPD(2, 2, 1, bU12); ABZ_UPD(3, 2, 1, bU12);                                            // column 2 of step 1
+    {   // ---- D2 around X_12, column 3 of step 1, W_02, N_20, N_30 (first term), D1 N_10
+        const BFrag bU13 = ABZ_FRAG(1, 3);
+        ABZ_PIV(2, 0, ABZ_SET(1, 2, 1, 1, bU12))                                                // X_12
+        ABZ_PIV(2, 1, ABZ_UPD(2, 3, 1, bU13))
+        ABZ_PIV(2, 2, ABZ_UPD(3, 3, 1, bU13))
+        ABZ_PIV(2, 3, ABZ_SET(1, 3, 1, 1, bU13))                                                // X_13
+        const BFrag bN10 = ABZ_FRAG(1, 0);                                                      // N_10 = L_10
+        ABZ_PIV(2, 4, ABZ_UPD(2, 0, 1, bN10))                                                   // N_20 = L_20 - L_21 N_10
+        ABZ_PIV(2, 5, ABZ_UPD(3, 0, 1, bN10))                                                   // N_30 = L_30 - L_31 N_10 (- L_32 N_20 later)
+        const BFrag bX12 = ABZ_FRAG(1, 2);
+        ABZ_PIV(2, 6, ABZ_UPD(0, 2, 1, bX12))                                                   // W_02 = X_02 - W_01 X_12
+        ABZ_PIV(2, 7, ABZ_TRACE(0, 1))                                                          // tr(W_01 D_1 N_10)
+    }
+    ABZ_DIAG_TRACE(2)
+    {
+        const BFrag bD2 = ABZ_FRAG(2, 2);
+        ABZ_SET(3, 2, 3, 2, bD2)                                                                // L_32
+    }
+    const BFrag bU23 = ABZ_FRAG(2, 3);
+    ABZ_UPD(3, 3, 2, bU23);                                                                    // A_33 of step 2
+    {   // ---- D3 around X_23, W_03, W_13, N_30 (second term), N_31, D2 N_20, D2 N_21
+        const BFrag bX13 = ABZ_FRAG(1, 3);                                                      // X_13, still unmodified
+        ABZ_PIV(3, 0, ABZ_SET(2, 3, 2, 2, bU23))                                                // X_23
+        ABZ_PIV(3, 1, ABZ_UPD(0, 3, 1, bX13))                                                   // W_03 = X_03 - W_01 X_13 ...
+        const BFrag bX23 = ABZ_FRAG(2, 3);
+        ABZ_PIV(3, 2, ABZ_UPD(0, 3, 2, bX23))                                                   //        ... - W_02 X_23
+        ABZ_PIV(3, 3, ABZ_UPD(1, 3, 2, bX23))                                                   // W_13 = X_13 - W_12 X_23
+        const BFrag bN20 = ABZ_FRAG(2, 0);
+        ABZ_PIV(3, 4, ABZ_UPD(3, 0, 2, bN20))                                                   // N_30 -= L_32 N_20
+        const BFrag bN21 = ABZ_FRAG(2, 1);                                                      // N_21 = L_21
+        ABZ_PIV(3, 5, ABZ_UPD(3, 1, 2, bN21))                                                   // N_31 = L_31 - L_32 N_21
+        ABZ_PIV(3, 6, ABZ_TRACE(0, 2))                                                          // tr(W_02 D_2 N_20)
+        ABZ_PIV(3, 7, ABZ_TRACE(1, 2))                                                          // tr(W_12 D_2 N_21)
+    }
+    ABZ_DIAG_TRACE(3)
+    ABZ_TRACE(0, 3) ABZ_TRACE(1, 3) ABZ_TRACE(2, 3)                                             // tr(W_i3 D_3 N_3i)
+#undef ABZ_FRAG
+#undef ABZ_UPD
+#undef ABZ_SET
+#undef ABZ_TRACE
+#undef ABZ_PIV
+#undef ABZ_DIAG_TRACE
+    return make_double2(warp_sum(tr), warp_sum(ti));
 }
 
 // VAR 0: left-looking substitutions (V and M interleaved, one accumulation chain per block);
@@ -285,7 +445,9 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
                                          max(__double2hiint(a1.x) & 0x7fffffff, __double2hiint(a1.y) & 0x7fffffff)));
             }
         int minhi = 0x7ff00000;
-        double2 t = warp_trace_inverse<NB, VAR>(R0, R1, I0, I1, lane, minhi);
+        double2 t;
+        if constexpr (NB == 4 && VAR == 2) t = warp_trace_inverse_pipelined(R0, R1, I0, I1, lane, minhi);
+        else t = warp_trace_inverse<NB, (VAR == 2 ? 1 : VAR)>(R0, R1, I0, I1, lane, minhi);
         t.x = -t.x - (double)npad; t.y = -t.y;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) amaxhi = max(amaxhi, __shfl_xor_sync(0xffffffffu, amaxhi, off));
@@ -345,7 +507,7 @@ inline int mma_resolvent_plan(int n, long nk, int nw, long sm, long* ncta, int* 
 // substitution variant of the norb = 25..32 kernel (ABZ_MMA_VARIANT = 0 / 1, see warp_trace_inverse); smaller matrices use 0
 inline int mma_resolvent_variant() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("ABZ_MMA_VARIANT"); v = e ? (atoi(e) == 1 ? 1 : 0) : ABZ_MMA_DEFAULT_VARIANT; }
+    if (v < 0) { const char* e = getenv("ABZ_MMA_VARIANT"); v = e ? std::min(2, std::max(0, atoi(e))) : ABZ_MMA_DEFAULT_VARIANT; }
     return v;
 }
 
@@ -353,7 +515,9 @@ template <int NB, int W>
 inline void mma_launch_one(const double2* H, const double* wnode, long nk, int n, int nw, const double2* z, const double2* sigma,
                            int mode, double2* outp, int* errflag, long ncta, int kper, cudaStream_t stream) {
     size_t smem = (size_t)nw * W * sizeof(double2);
-    if (NB == 4 && mma_resolvent_variant() == 1)
+    if (NB == 4 && mma_resolvent_variant() == 2)
+        resolvent_mma_kernel<NB, W, (NB == 4 ? 2 : 0)><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
+    else if (NB == 4 && mma_resolvent_variant() == 1)
         resolvent_mma_kernel<NB, W, (NB == 4 ? 1 : 0)><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
     else
         resolvent_mma_kernel<NB, W, 0><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
@@ -370,6 +534,7 @@ inline cudaError_t mma_resolvent_opt_in() {
     ABZ_MMA_OPT(1) ABZ_MMA_OPT(2) ABZ_MMA_OPT(3) ABZ_MMA_OPT(4)
 #undef ABZ_MMA_OPT
     { auto k8 = resolvent_mma_kernel<4, 8, 1>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 1>; set((const void*)k12); }
+    { auto k8 = resolvent_mma_kernel<4, 8, 2>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 2>; set((const void*)k12); }
     return e;
 }
 

@@ -112,12 +112,13 @@ class DomainError(FloatingPointError):
 
 
 class _Pend:
-    __slots__ = ("a", "b", "vals", "remaining", "tag")
+    __slots__ = ("a", "b", "vals", "remaining", "tag", "shared")
 
     def __init__(self, a, b, tag, dtype):
         self.a, self.b, self.tag = a, b, tag
-        self.vals = np.empty(15, dtype=dtype)
+        self.vals = np.zeros(15, dtype=dtype)
         self.remaining = 15
+        self.shared = False
 
 
 class _Integral:
@@ -139,7 +140,13 @@ class NestedGK:
                   k [npts, ndim] the full points (FourierValue(limit_iterate(lims, state, x), H), src/fourier.jl:454)
     """
 
-    def __init__(self, nest, ndim, lims, fkind, z, sigma, post, dtype, atol, rtol, maxevals, cap2=64, cap1=2048, user=None):
+    def __init__(self, nest, ndim, lims, fkind, z, sigma, post, dtype, atol, rtol, maxevals, cap2=64, cap1=2048, user=None,
+                 rank=0, nranks=1, allreduce=None):
+        # multi-rank (ndim >= 2): the 15 nodes of every panel of the OUTERMOST integral are dealt round-robin to the ranks; when a
+        # rank's own work is exhausted all ranks meet in one sum-allreduce of the outstanding outer panels' node values (zeros for
+        # foreign nodes) and take the identical accept/refine decision - the scheme of the C++ engine (csrc/abz_iai_engine.hpp)
+        self.rank, self.nranks, self.allreduce = int(rank), (int(nranks) if ndim >= 2 else 1), allreduce
+        self.spawn_counter, self.shared_pends, self.exchanges = 0, [], 0
         self.nest, self.ndim, self.lims = nest, ndim, lims
         self.fkind, self.z, self.sigma, self.post, self.dtype = fkind, z, sigma, post, dtype
         self.user = user
@@ -168,7 +175,16 @@ class NestedGK:
             self.q_eval.append((q, pend))
             return
         xs = gk15_nodes(a, b)
+        shared = self.nranks > 1 and q.level == self.ndim - 1
+        if shared:
+            pend.shared = True
+            self.shared_pends.append((q, pend))
         for i in range(15):
+            if shared:
+                mine = (self.spawn_counter % self.nranks) == self.rank
+                self.spawn_counter += 1
+                if not mine:
+                    continue                                  # another rank owns this node
             x = float(xs[i])
             clims = q.lims.fix(x)
             csegs = tuple(clims.segments())
@@ -202,6 +218,8 @@ class NestedGK:
         pq, pend, i = q.parent
         self._free(pq.level, q.slot)
         pend.vals[i] = Iv
+        if pend.shared:
+            return                                            # combined in _exchange once every rank has delivered its nodes
         pend.remaining -= 1
         if pend.remaining == 0:
             Is, Es = gk15_combine(pend.a, pend.b, pend.vals)
@@ -281,6 +299,9 @@ class NestedGK:
             batch = self.q_eval
             self.q_eval = []
             if not batch:
+                if self.nranks > 1:
+                    self._exchange()
+                    continue
                 raise RuntimeError("IAI engine stalled")
             nseg = len(batch)
             aa = np.array([p.a for _, p in batch])
@@ -304,4 +325,19 @@ class NestedGK:
             for i in range(nseg):
                 q, pend = batch[i]
                 self._segment_done(q, pend, Is[i], float(Es[i]))
+        if self.nranks > 1:          # evaluations of all ranks (EvalCounter semantics of the whole solve)
+            self.numevals = int(round(float(np.asarray(self.allreduce(np.array([float(self.numevals)]))).reshape(-1)[0])))
         return self.root_result[0], self.root_result[1], self.numevals
+
+    def _exchange(self):
+        """all ranks: sum the outstanding outermost panels' node values, then every rank combines and decides identically"""
+        sp, self.shared_pends = self.shared_pends, []
+        if not sp:
+            raise RuntimeError("IAI engine stalled")
+        self.exchanges += 1
+        buf = np.concatenate([np.asarray(p.vals, dtype=np.complex128) for _, p in sp])
+        buf = np.asarray(self.allreduce(buf), dtype=np.complex128).reshape(len(sp), 15)
+        for (q, pend), vals in zip(sp, buf):
+            pend.vals[:] = vals if np.iscomplexobj(pend.vals) else vals.real
+            Is, Es = gk15_combine(pend.a, pend.b, pend.vals)
+            self._segment_done(q, pend, Is[()], float(Es))

@@ -458,7 +458,8 @@ def _do_solve(cache, ps):
                     real[0] = real[0] and not np.iscomplexobj(v)
                     return v
 
-                eng = NestedGK(cache.cacheval["nest"], ndim, dom, None, None, None, None, np.complex128, atol, reltol, maxiters, user=user)
+                eng = NestedGK(cache.cacheval["nest"], ndim, dom, None, None, None, None, np.complex128, atol, reltol, maxiters, user=user,
+                               rank=shard.rank, nranks=shard.nranks, allreduce=shard.allreduce if shard.nranks > 1 else None)
                 Iv, Ev, ne = eng.run()
                 cache.cacheval["iai_rounds"] = eng.rounds
                 mult = sc * (ns if on_bz else 1)
@@ -492,13 +493,15 @@ def _do_solve(cache, ps):
                 lin = bound if vkind == 2 else None
                 Iv, Ev, ne, rounds, launches = nest.iai_solve(lkind, la, lb, b1.fkind, vkind, z, sigma, lin, atol_, rtol_, maxiters,
                                                               device_leaves=getattr(cache.backend, "iai_device_leaves", True),
+                                                              device_middles=getattr(cache.backend, "iai_device_middles", True),
                                                               rank=shard.rank, nranks=shard.nranks,
                                                               allreduce=shard.allreduce if shard.nranks > 1 else None, limits=general)
                 cache.cacheval["iai_rounds"] = rounds
                 Iv = Iv if dtype == np.complex128 else Iv.real
             else:
                 eng = NestedGK(nest, ndim, dom, b1.fkind, z, sigma, lambda y, ff=ff, bound=bound: ff.post(y, bound),
-                               dtype, atol, reltol, maxiters)
+                               dtype, atol, reltol, maxiters,
+                               rank=shard.rank, nranks=shard.nranks, allreduce=shard.allreduce if shard.nranks > 1 else None)
                 Iv, Ev, ne = eng.run()
                 cache.cacheval["iai_rounds"] = eng.rounds
             mult = sc * (ns if on_bz else 1)                # val = j * symmetrize(f, bz, sol.u) (TrivialRep: x nsyms)

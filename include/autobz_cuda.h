@@ -194,6 +194,11 @@ int32_t abz_nest_eval_h(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const doubl
  *   out = {Re I, Im I, E};  stats = Int64[4] {numevals (EvalCounter semantics), device rounds, kernel launches,
  *   exchanges} or NULL */
 #define ABZ_IAI_DEVICE_LEAVES 1
+/* ABZ_IAI_DEVICE_MIDDLES (implies the leaves): in 3-d solves over CubicLimits / TetrahedralLimits every MIDDLE integral (one per node of
+ * the outermost panels) runs entirely on the device too - one CTA keeps its segment heap in shared memory, contracts the series at
+ * each of its nodes and hands the innermost integrals to its warps - so the host engine only steps the outermost integral:
+ * stats[1] (device rounds) drops from one per middle-level refinement to one per outermost refinement.  Same decisions, same numevals. */
+#define ABZ_IAI_DEVICE_MIDDLES 2
 int32_t abz_iai_solve(abz_ctx* ctx, abz_nest_t nest, int32_t lkind, const double* la, const double* lb, int32_t fkind,
                       int32_t vkind, const double* z, const double* sigma, const double* lin, double atol, double rtol,
                       int64_t maxevals, int32_t flags, double* out, int64_t* stats);

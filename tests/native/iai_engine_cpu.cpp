@@ -41,6 +41,82 @@ struct CpuBackend {
     }
     static double cabs_(cplx v) { return std::hypot(v.re, v.im); }
 
+    void leaf_task(const std::vector<double>* c1, double a, double b, double atol, cplx* Iout, double* Eout, int64_t* neout) {
+        std::vector<Seg> heap;
+        cplx I, D;
+        panel(c1, a, b, &I, &D);
+        double E = cabs_(D);
+        heap.push_back(Seg{E, a, b, I});
+        int64_t ne = 15;
+        bool go = std::isfinite(E) && !(ne >= maxevals || E <= atol || E <= rtol * cabs_(I));
+        while (go) {
+            Seg s = heap_pop(heap);
+            double mid = (s.a + s.b) / 2;
+            cplx I1, D1, I2, D2;
+            panel(c1, s.a, mid, &I1, &D1);
+            panel(c1, mid, s.b, &I2, &D2);
+            double E1 = cabs_(D1), E2 = cabs_(D2);
+            I = cplx{(I.re - s.I.re) + I1.re + I2.re, (I.im - s.I.im) + I1.im + I2.im};
+            E = (E - s.E) + E1 + E2;
+            ne += 30;
+            heap_push(heap, Seg{E1, s.a, mid, I1});
+            heap_push(heap, Seg{E2, mid, s.b, I2});
+            if (!(std::isfinite(E1) && std::isfinite(E2))) { E = NAN; break; }
+            go = (E > atol && E > rtol * cabs_(I) && ne < maxevals);
+        }
+        cplx Iv = heap[0].I; double Ev = heap[0].E;
+        for (size_t k = 1; k < heap.size(); k++) { Iv.re += heap[k].I.re; Iv.im += heap[k].I.im; Ev += heap[k].E; }
+        *Iout = Iv; *Eout = std::isfinite(E) ? Ev : NAN; *neout = ne;
+    }
+
+    // limits of the innermost variable below a middle node x2 (CubicLimits / TetrahedralLimits), as iai_mid_kernel derives them
+    int lkind = 0; double lima[3] = {0, 0, 0}, limb[3] = {0, 0, 0};
+    void mid_task(const std::vector<double>& c2, double a, double b, double atol, cplx* Iout, double* Eout, int64_t* ne_leaves) {
+        const long rows = (long)n * n * M[0];
+        int64_t nel = 0;
+        bool bad = false;
+        auto panel_mid = [&](double pa, double pb, cplx* I, cplx* D) {
+            cplx f[15];
+            for (int j = 0; j < 15; j++) {
+                const double x2 = gk_node(pa, pb, j);
+                std::vector<double> c1(2 * rows);
+                orc_contract(c2.data(), rows, M[1], lo[1], period[1], x2, c1.data());
+                double ca, cb;
+                if (lkind == 0) { ca = lima[0]; cb = limb[0]; } else { ca = 0.0; cb = lima[0] * (x2 / lima[1]); }
+                double E; int64_t ne;
+                leaf_task(&c1, ca, cb, atol / (cb - ca), &f[j], &E, &ne);
+                nel += ne;
+                if (!std::isfinite(E)) bad = true;
+            }
+            gk_combine(pa, pb, f, I, D);
+        };
+        std::vector<Seg> heap;
+        cplx I, D;
+        panel_mid(a, b, &I, &D);
+        double E = cabs_(D);
+        heap.push_back(Seg{E, a, b, I});
+        int64_t ne = 15;
+        bool go = std::isfinite(E) && !bad && !(ne >= maxevals || E <= atol || E <= rtol * cabs_(I));
+        while (go) {
+            Seg s = heap_pop(heap);
+            double mid = (s.a + s.b) / 2;
+            cplx I1, D1, I2, D2;
+            panel_mid(s.a, mid, &I1, &D1);
+            panel_mid(mid, s.b, &I2, &D2);
+            double E1 = cabs_(D1), E2 = cabs_(D2);
+            I = cplx{(I.re - s.I.re) + I1.re + I2.re, (I.im - s.I.im) + I1.im + I2.im};
+            E = (E - s.E) + E1 + E2;
+            ne += 30;
+            heap_push(heap, Seg{E1, s.a, mid, I1});
+            heap_push(heap, Seg{E2, mid, s.b, I2});
+            if (!(std::isfinite(E1) && std::isfinite(E2)) || bad) { E = NAN; break; }
+            go = (E > atol && E > rtol * cabs_(I) && ne < maxevals);
+        }
+        cplx Iv = heap[0].I; double Ev = heap[0].E;
+        for (size_t k = 1; k < heap.size(); k++) { Iv.re += heap[k].I.re; Iv.im += heap[k].I.im; Ev += heap[k].E; }
+        *Iout = Iv; *Eout = (std::isfinite(E) && !bad) ? Ev : NAN; *ne_leaves = nel;
+    }
+
     // lanes: IAI_CPU_LANES rounds in flight; the work of a round is done in wait(), so an engine that read a round's outputs
     // before waiting for it would see stale data
     int nlanes = 1;
@@ -68,35 +144,12 @@ struct CpuBackend {
         for (size_t i = 0; i < ns; i++)
             panel(ndim >= 2 ? &L1.at(R.seg_slot[i]) : nullptr, R.seg_a[i], R.seg_b[i], &R.seg_I[i], &R.seg_D[i]);
         R.task_I.resize(nt); R.task_E.resize(nt); R.task_ne.resize(nt);
-        for (size_t t = 0; t < nt; t++) {   // whole innermost adaptive integral (what iai_leaf_kernel does per warp)
-            const std::vector<double>* c1 = &L1.at(R.task_slot[t]);
-            const double atol = R.task_atol[t];
-            std::vector<Seg> heap;
-            cplx I, D;
-            panel(c1, R.task_a[t], R.task_b[t], &I, &D);
-            double E = cabs_(D);
-            heap.push_back(Seg{E, R.task_a[t], R.task_b[t], I});
-            int64_t ne = 15;
-            bool go = std::isfinite(E) && !(ne >= maxevals || E <= atol || E <= rtol * cabs_(I));
-            while (go) {
-                Seg s = heap_pop(heap);
-                double mid = (s.a + s.b) / 2;
-                cplx I1, D1, I2, D2;
-                panel(c1, s.a, mid, &I1, &D1);
-                panel(c1, mid, s.b, &I2, &D2);
-                double E1 = cabs_(D1), E2 = cabs_(D2);
-                I = cplx{(I.re - s.I.re) + I1.re + I2.re, (I.im - s.I.im) + I1.im + I2.im};
-                E = (E - s.E) + E1 + E2;
-                ne += 30;
-                heap_push(heap, Seg{E1, s.a, mid, I1});
-                heap_push(heap, Seg{E2, mid, s.b, I2});
-                if (!(std::isfinite(E1) && std::isfinite(E2))) { E = NAN; break; }
-                go = (E > atol && E > rtol * cabs_(I) && ne < maxevals);
-            }
-            cplx Iv = heap[0].I; double Ev = heap[0].E;
-            for (size_t k = 1; k < heap.size(); k++) { Iv.re += heap[k].I.re; Iv.im += heap[k].I.im; Ev += heap[k].E; }
-            R.task_I[t] = Iv; R.task_E[t] = std::isfinite(E) ? Ev : NAN; R.task_ne[t] = ne;
-        }
+        for (size_t t = 0; t < nt; t++)      // whole innermost adaptive integral (what iai_leaf_kernel does per warp)
+            leaf_task(&L1.at(R.task_slot[t]), R.task_a[t], R.task_b[t], R.task_atol[t], &R.task_I[t], &R.task_E[t], &R.task_ne[t]);
+        const size_t nm = R.mid_a.size();
+        R.mid_I.resize(nm); R.mid_E.resize(nm); R.mid_ne.resize(nm);
+        for (size_t t = 0; t < nm; t++)      // whole middle adaptive integral (what iai_mid_kernel does per CTA)
+            mid_task(L2.at(R.mid_slot[t]), R.mid_a[t], R.mid_b[t], R.mid_atol[t], &R.mid_I[t], &R.mid_E[t], &R.mid_ne[t]);
         launches++;
         return 0;
     }
@@ -115,7 +168,10 @@ extern "C" int iai_cpu_solve(const double* coeffs, int n, int ndim, const int* M
     if (const char* e = getenv("IAI_CPU_LANES")) be.nlanes = atoi(e) > 0 ? atoi(e) : 1;
     Limits lims; lims.kind = lkind; lims.nd = ndim; lims.s = 1.0;
     for (int d = 0; d < ndim; d++) { lims.a[d] = la[d]; lims.b[d] = lb ? lb[d] : 0.0; }
-    Engine<CpuBackend> eng(be, ndim, lims, atol, rtol, maxevals, cap2, cap1, leaf_tasks != 0, rank, nranks);
+    be.lkind = lkind;
+    for (int d = 0; d < ndim; d++) { be.lima[d] = lims.a[d]; be.limb[d] = lims.b[d]; }
+    // leaf_tasks: 0 host-driven panels, 1 innermost integrals as tasks, 2 middle integrals as tasks too
+    Engine<CpuBackend> eng(be, ndim, lims, atol, rtol, maxevals, cap2, cap1, leaf_tasks != 0, rank, nranks, leaf_tasks == 2);
     int rc = eng.run();
     stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = be.launches; stats[3] = eng.exchanges;
     if (rc) return rc;

@@ -42,7 +42,7 @@ def _solve(lib, S, ndim, lkind, la, lb, fkind, vkind, z, lin, atol, rtol, leaf, 
     return rc, complex(out[0], out[1]), out[2], int(st[0]), int(st[1])
 
 
-@pytest.mark.parametrize("leaf", [False, True])
+@pytest.mark.parametrize("leaf", [False, True, 2])
 @pytest.mark.parametrize("lims", ["cubic", "tetra"])
 def test_engine_matches_recursion_svo(orc, eng, svo, lims, leaf):
     H, lo, A = svo
@@ -62,7 +62,7 @@ def test_engine_matches_recursion_svo(orc, eng, svo, lims, leaf):
         assert rounds < rounds_host
 
 
-@pytest.mark.parametrize("leaf", [False, True])
+@pytest.mark.parametrize("leaf", [False, True, 2])
 def test_engine_complex_values_and_rtol(orc, eng, svo, leaf):
     """complex-valued integrand (tr G), relative tolerance only, maxevals cut-off"""
     H, lo, A = svo
