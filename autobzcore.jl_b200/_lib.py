@@ -24,7 +24,7 @@ EXPORTS = [
     "abz_ctx_last_timings", "abz_series_create", "abz_series_destroy", "abz_rule_create_full", "abz_rule_create_sym", "abz_rule_create_nodes",
     "abz_symptr_rule", "abz_rule_create_symptr", "abz_rule_destroy", "abz_rule_info", "abz_rule_materialize", "abz_rule_copy_out",
     "abz_rule_resolvent_sum", "abz_rule_resolvent_matrix_sum", "abz_rule_eig_sum", "abz_rule_eig_sum_batch", "abz_rule_eigvals", "abz_rule_ggr_data", "abz_rule_ggr_sum", "abz_points_eval", "abz_points_resolvent",
-    "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval", "abz_nest_eval_h", "abz_iai_solve", "abz_iai_solve_sharded", "abz_iai_solve_general",
+    "abz_nest_create", "abz_nest_destroy", "abz_nest_contract3", "abz_nest_contract2", "abz_nest_eval", "abz_nest_eval_h", "abz_nest_eval_matrix", "abz_iai_solve", "abz_iai_solve_sharded", "abz_iai_solve_general",
     "abz_comm_unique_id", "abz_comm_init", "abz_allreduce_sum", "abz_comm_destroy",
 ]
 
@@ -92,6 +92,7 @@ def load():
     lib.abz_nest_contract2.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p, c_i64p]
     lib.abz_nest_eval.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p, C.c_int32, c_dp, c_dp, c_dp]
     lib.abz_nest_eval_h.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p, c_dp]
+    lib.abz_nest_eval_matrix.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, c_dp, c_i64p, c_dp, c_dp, c_dp]
     lib.abz_iai_solve.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, C.c_double,
                                   C.c_double, C.c_int64, C.c_int32, c_dp, c_i64p]
     lib.abz_iai_solve_sharded.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, c_dp, c_dp, C.c_int32, C.c_int32, c_dp, c_dp, c_dp, C.c_double,
@@ -404,6 +405,18 @@ class DeviceNest:
         self.ctx.check(self.ctx.lib.abz_nest_eval(self.ctx.h, self.h, x.size, _dp(x), None if s is None else s.ctypes.data_as(c_i64p),
                                                   fkind, _dp(zz), _dp(sg), _dp(y)))
         return y
+
+    def eval_matrix(self, x1, slot1, z, sigma=None):
+        """(z - H - Sigma)^-1 at the nodes of innermost panels, [npts, n, n] (matrix-valued gloc_integrand under IAI)"""
+        x = np.ascontiguousarray(x1, dtype=np.float64)
+        s = None if slot1 is None else np.ascontiguousarray(slot1, dtype=np.int64)
+        zz = _cz(z)
+        n = self.series.n
+        sg = None if sigma is None else np.asfortranarray(np.asarray(sigma, dtype=np.complex128).reshape(n, n))
+        Y = np.empty((n, n, x.size), dtype=np.complex128, order="F")
+        self.ctx.check(self.ctx.lib.abz_nest_eval_matrix(self.ctx.h, self.h, x.size, _dp(x), None if s is None else s.ctypes.data_as(c_i64p),
+                                                         _dp(zz), _dp(sg), _dp(Y)))
+        return np.ascontiguousarray(np.moveaxis(Y, 2, 0))
 
     def eval_h(self, x1, slot1):
         """H at the nodes of innermost panels, [n, n, npts] (for integrands evaluated on the host)"""

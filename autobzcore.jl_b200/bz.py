@@ -221,11 +221,14 @@ class FBZ:
 
 
 class IBZ:
-    """IBZ(n) (src/brillouin.jl:205-247): the polyhedral irreducible BZ.  In the reference it needs the SymmetryReduceBZ.jl
-    extension and errors without it; that extension is out of scope here, so `load_bz(IBZ(), ...)` raises."""
+    """IBZ(n) (src/brillouin.jl:205-247): the polyhedral irreducible BZ.  In the reference the polyhedron and the point group come
+    from the SymmetryReduceBZ.jl extension (ext/SymmetryReduceBZExt.jl: `calc_ibz` -> convex hull -> `load_limits`) and `load_bz`
+    errors without it.  That package is not available here, so the caller supplies what it would compute: the IBZ's vertices in
+    lattice coordinates (`polyhedron`, [nv, 3]) and the point-group operators in lattice coordinates (`syms`); `load_bz` then
+    builds the same SymmetricBZ(A, B, polyhedral limits, syms).  Without them `load_bz(IBZ(), ...)` raises like the reference."""
 
-    def __init__(self, ndim=None):
-        self.ndim = ndim
+    def __init__(self, ndim=None, polyhedron=None, syms=None):
+        self.ndim, self.polyhedron, self.syms = ndim, polyhedron, syms
 
 
 class InversionSymIBZ:
@@ -333,5 +336,10 @@ def load_bz(bz, A=None, B=None, atol=None):
             warnings.warn("Non-orthogonal lattice vectors detected with CubicSymIBZ. Unexpected behavior may occur")
         return SymmetricBZ(A, B, TetrahedralLimits(np.full(d, 0.5)), cube_automorphisms(d))
     if isinstance(bz, IBZ):
-        raise NotImplementedError("SymmetryReduceBZ extension not loaded (the polyhedral IBZ is out of scope of this build)")   # src/brillouin.jl:234-241
+        if bz.polyhedron is None or bz.syms is None:
+            raise NotImplementedError("SymmetryReduceBZ extension not loaded: pass IBZ(polyhedron=vertices, syms=point group)")   # src/brillouin.jl:234-241
+        verts = np.asarray(bz.polyhedron, dtype=float)
+        if d != 3 or verts.ndim != 2 or verts.shape[1] != 3 or verts.shape[0] < 4:
+            raise ValueError("IBZ(polyhedron=...) takes the [nv >= 4, 3] vertices of a convex polyhedron in lattice coordinates")
+        return SymmetricBZ(A, B, PolyhedronLimits(verts), [np.asarray(S) for S in bz.syms])
     raise TypeError("unsupported BZ type")

@@ -1844,6 +1844,53 @@ int32_t abz_nest_eval_h(abz_ctx* ctx, abz_nest_t nid, int64_t npts, const double
 }
 
 
+// matrix-valued innermost closure: Y[:, :, i] = (z - H(x1_i on slot1_i) - Sigma)^-1 (gloc_integrand under IAI, docs/src/examples.md:90-106)
+int32_t abz_nest_eval_matrix(abz_ctx* ctx, abz_nest_t nid, int64_t npts, const double* x1, const int64_t* slot1, const double* z,
+                             const double* sigma, double* Y) {
+    if (!ctx) return ABZ_E_INVALID;
+    Nest* nst = get_nest(ctx, nid);
+    if (!nst) return fail(ctx, ABZ_E_INVALID, "unknown nest handle");
+    if (npts < 0 || !z || (npts > 0 && (!x1 || !Y || (nst->ndim >= 2 && !slot1)))) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    if (npts == 0) return ABZ_OK;
+    int rc;
+    if (nst->ndim >= 2 && (rc = check_slots(ctx, slot1, npts, nst->cap1, "abz_nest_eval_matrix"))) return rc;
+    cudaSetDevice(ctx->device);
+    Series* s = nst->s;
+    const int n = s->n;
+    const long nn = (long)n * n;
+    CU(ctx, ctx->tmp_a.reserve((size_t)npts * sizeof(double)));
+    CU(ctx, ctx->tmp_b.reserve((size_t)npts * sizeof(long)));
+    CU(ctx, ctx->Hc.reserve((size_t)npts * nn * sizeof(double2)));
+    CU(ctx, ctx->partial.reserve((size_t)npts * nn * sizeof(double2)));
+    CU(ctx, cudaMemcpyAsync(ctx->tmp_a.p, x1, (size_t)npts * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const long* dslot = nullptr; const double2* L1 = s->c; long stride = 0;
+    if (nst->ndim >= 2) {
+        CU(ctx, cudaMemcpyAsync(ctx->tmp_b.p, slot1, (size_t)npts * sizeof(long), cudaMemcpyHostToDevice, ctx->stream));
+        dslot = ctx->tmp_b.as<long>(); L1 = nst->L1; stride = nn * s->M[0];
+    }
+    rc = upload_params(ctx, n, 1, z, sigma);
+    if (rc) return rc;
+    dim3 gh((unsigned)((nn + 127) / 128), (unsigned)npts);
+    nest_eval_h_kernel<<<gh, 128, (size_t)s->M[0] * sizeof(double2), ctx->stream>>>(L1, stride, dslot, ctx->tmp_a.as<double>(), (int)nn,
+                                                                                   s->M[0], s->lo[0], s->period[0], ctx->Hc.as<double2>());
+    LAUNCH_CHECK(ctx, "nest_eval_h_kernel");
+    // one node per team and kper = 1: the matrix-sum kernels then leave every node's inverse in its own partial block
+    const double2* sgd = sigma ? ctx->sigbuf.as<double2>() : nullptr;
+    dim3 grid((unsigned)npts, 1);
+    if (n <= 20) {
+        const size_t smem = ((size_t)n * (n + 1) + (n + 1) / 2 + 1 + nn) * sizeof(double2);
+        resolvent_gj_matrix_kernel<<<grid, 32, smem, ctx->stream>>>(ctx->Hc.as<double2>(), nullptr, npts, n, 1, ctx->zbuf.as<double2>(), sgd, 1,
+                                                                   ctx->partial.as<double2>(), ctx->errflag.as<int>());
+    } else {
+        GJ_DISPATCH(resolvent_gjreg_matrix_kernel, true, n, grid, (size_t)nn * sizeof(double2), ctx->stream, ctx->Hc.as<double2>(), nullptr, npts, n, 1,
+                    ctx->zbuf.as<double2>(), sgd, 1, ctx->partial.as<double2>(), ctx->errflag.as<int>());
+    }
+    LAUNCH_CHECK(ctx, "resolvent_gj_matrix_kernel");
+    CU(ctx, cudaMemcpyAsync(Y, ctx->partial.p, (size_t)npts * nn * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = check_errflag(ctx, "abz_nest_eval_matrix");
+    return rc == ABZ_RETRY_PIVOTED ? ABZ_OK : rc;
+}
+
 // ---- IAI: the whole nested adaptive solve, control flow on the library's host side -------------------
 namespace {
 

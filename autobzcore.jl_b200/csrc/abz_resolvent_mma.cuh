@@ -62,6 +62,41 @@ __device__ __forceinline__ void bmm(double& cr0, double& cr1, double& ci0, doubl
     dmma884(ci0, ci1, pi1, b.r[1]);
 }
 
+// Two INDEPENDENT block products issued DMMA by DMMA: four accumulation chains in flight instead of two.  A dependent DMMA may issue
+// 32.6 cycles after its predecessor (2 issue slots of 16.3 cycles, profiles/r01_microbench_fp64.log), so the two chains of one product
+// leave no slack at all - ptxas pads them with NOPs (12 % of the stall samples of the kernel, profiles/r02_ncu_k3fast_summary.txt) -
+// while four chains put every dependent DMMA four slots behind its predecessor.
+template <bool NEG1, bool NEG2>
+__device__ __forceinline__ void bmm2(double& c1r0, double& c1r1, double& c1i0, double& c1i1, double a1r0, double a1r1, double a1i0, double a1i1,
+                                     const BFrag& b1, double& c2r0, double& c2r1, double& c2i0, double& c2i1, double a2r0, double a2r1,
+                                     double a2i0, double a2i1, const BFrag& b2) {
+    const double p1r0 = NEG1 ? -a1r0 : a1r0, p1r1 = NEG1 ? -a1r1 : a1r1, p1i0 = NEG1 ? -a1i0 : a1i0, p1i1 = NEG1 ? -a1i1 : a1i1;
+    const double m1i0 = NEG1 ? a1i0 : -a1i0, m1i1 = NEG1 ? a1i1 : -a1i1;
+    const double p2r0 = NEG2 ? -a2r0 : a2r0, p2r1 = NEG2 ? -a2r1 : a2r1, p2i0 = NEG2 ? -a2i0 : a2i0, p2i1 = NEG2 ? -a2i1 : a2i1;
+    const double m2i0 = NEG2 ? a2i0 : -a2i0, m2i1 = NEG2 ? a2i1 : -a2i1;
+    dmma884(c1r0, c1r1, p1r0, b1.r[0]); dmma884(c1i0, c1i1, p1r0, b1.i[0]);
+    dmma884(c2r0, c2r1, p2r0, b2.r[0]); dmma884(c2i0, c2i1, p2r0, b2.i[0]);
+    dmma884(c1r0, c1r1, p1r1, b1.r[1]); dmma884(c1i0, c1i1, p1r1, b1.i[1]);
+    dmma884(c2r0, c2r1, p2r1, b2.r[1]); dmma884(c2i0, c2i1, p2r1, b2.i[1]);
+    dmma884(c1r0, c1r1, m1i0, b1.i[0]); dmma884(c1i0, c1i1, p1i0, b1.r[0]);
+    dmma884(c2r0, c2r1, m2i0, b2.i[0]); dmma884(c2i0, c2i1, p2i0, b2.r[0]);
+    dmma884(c1r0, c1r1, m1i1, b1.i[1]); dmma884(c1i0, c1i1, p1i1, b1.r[1]);
+    dmma884(c2r0, c2r1, m2i1, b2.i[1]); dmma884(c2i0, c2i1, p2i1, b2.r[1]);
+}
+// one block product on four chains: the two k-slabs accumulate separately and are added at the end (4 DADD)
+template <bool NEG>
+__device__ __forceinline__ void bmm_split(double& cr0, double& cr1, double& ci0, double& ci1, double ar0, double ar1, double ai0, double ai1,
+                                          const BFrag& b) {
+    const double pr0 = NEG ? -ar0 : ar0, pr1 = NEG ? -ar1 : ar1, pi0 = NEG ? -ai0 : ai0, pi1 = NEG ? -ai1 : ai1;
+    const double mi0 = NEG ? ai0 : -ai0, mi1 = NEG ? ai1 : -ai1;
+    double tr0 = 0, tr1 = 0, ti0 = 0, ti1 = 0;
+    dmma884(cr0, cr1, pr0, b.r[0]); dmma884(ci0, ci1, pr0, b.i[0]);
+    dmma884(tr0, tr1, pr1, b.r[1]); dmma884(ti0, ti1, pr1, b.i[1]);
+    dmma884(cr0, cr1, mi0, b.i[0]); dmma884(ci0, ci1, pi0, b.r[0]);
+    dmma884(tr0, tr1, mi1, b.i[1]); dmma884(ti0, ti1, pi1, b.r[1]);
+    cr0 += tr0; cr1 += tr1; ci0 += ti0; ci1 += ti1;
+}
+
 // sign flip on the integer pipe (keeps the FP64 pipe for FMA/DMMA work)
 __device__ __forceinline__ double dneg(double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
 
@@ -263,6 +298,110 @@ __device__ __forceinline__ double2 warp_trace_inverse_pipelined(double (&R0)[4][
     return make_double2(warp_sum(tr), warp_sum(ti));
 }
 
+// VAR 3: VAR 1 (right-looking substitutions) with the independent block products of every step issued in PAIRS (bmm2: four DMMA
+// accumulation chains in flight), single left-overs on four chains too (bmm_split).  Same block algebra as VAR 0 / 1.
+template <int NB>
+__device__ __forceinline__ double2 warp_trace_inverse_paired(double (&R0)[NB][NB], double (&R1)[NB][NB], double (&I0)[NB][NB],
+                                                            double (&I1)[NB][NB], int lane, int& minpiv) {
+    const int g = lane >> 2, q = lane & 3;
+    const bool par = g & 1;
+    const int src0 = 4 * (2 * q + (par ? 1 : 0)) + (g >> 1);
+    const int src1 = 4 * (2 * q + (par ? 0 : 1)) + (g >> 1);
+#define ABZ_B(i, j) R0[i][j], R1[i][j], I0[i][j], I1[i][j]
+    inv8(ABZ_B(0, 0), lane, minpiv);
+#pragma unroll
+    for (int s = 0; s < NB - 1; s++) {
+        const BFrag bD = to_bfrag(ABZ_B(s, s), src0, src1, par);
+        {   // L_is = A_is D_s, rows in pairs
+#pragma unroll
+            for (int pp = 0; pp < (NB - 1 - s) / 2; pp++) {
+                const int i = s + 1 + 2 * pp;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+                bmm2<false, false>(a0, a1, a2, a3, ABZ_B(i, s), bD, b0, b1, b2, b3, ABZ_B(i + 1, s), bD);
+                R0[i][s] = a0; R1[i][s] = a1; I0[i][s] = a2; I1[i][s] = a3;
+                R0[i + 1][s] = b0; R1[i + 1][s] = b1; I0[i + 1][s] = b2; I1[i + 1][s] = b3;
+            }
+            if ((NB - 1 - s) & 1) {
+                const int i = NB - 1;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                bmm_split<false>(a0, a1, a2, a3, ABZ_B(i, s), bD);
+                R0[i][s] = a0; R1[i][s] = a1; I0[i][s] = a2; I1[i][s] = a3;
+            }
+        }
+#pragma unroll
+        for (int j = s + 1; j < NB; j++) {
+            const BFrag bU = to_bfrag(ABZ_B(s, j), src0, src1, par);
+            // A_ij -= L_is U_sj (i > s) and X_sj = D_s U_sj: NB - s independent products sharing bU, in pairs
+#pragma unroll
+            for (int pp = 0; pp < (NB - 1 - s) / 2; pp++) {
+                const int i = s + 1 + 2 * pp;
+                bmm2<true, true>(ABZ_B(i, j), ABZ_B(i, s), bU, ABZ_B(i + 1, j), ABZ_B(i + 1, s), bU);
+            }
+            double x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+            if ((NB - 1 - s) & 1) bmm2<true, false>(ABZ_B(NB - 1, j), ABZ_B(NB - 1, s), bU, x0, x1, x2, x3, ABZ_B(s, s), bU);
+            else bmm_split<false>(x0, x1, x2, x3, ABZ_B(s, s), bU);
+            R0[s][j] = x0; R1[s][j] = x1; I0[s][j] = x2; I1[s][j] = x3;
+            if (j == s + 1) inv8(ABZ_B(j, j), lane, minpiv);                 // D_{s+1} (look-ahead)
+        }
+    }
+    double tr = 0.0, ti = 0.0;
+#pragma unroll
+    for (int s = 0; s < NB; s++) {
+        if (2 * q == g) { tr += R0[s][s]; ti += I0[s][s]; }
+        if (2 * q + 1 == g) { tr += R1[s][s]; ti += I1[s][s]; }
+    }
+    // V = U~^-1, columns right to left
+#pragma unroll
+    for (int jv = NB - 1; jv >= 1; jv--) {
+        const BFrag bD = to_bfrag(ABZ_B(jv, jv), src0, src1, par);
+        {
+#pragma unroll
+            for (int pp = 0; pp < jv / 2; pp++) {                            // V'_{iv,jv} = -X_{iv,jv} D_jv
+                const int iv = 2 * pp;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+                bmm2<true, true>(a0, a1, a2, a3, ABZ_B(iv, jv), bD, b0, b1, b2, b3, ABZ_B(iv + 1, jv), bD);
+                R0[iv][jv] = a0; R1[iv][jv] = a1; I0[iv][jv] = a2; I1[iv][jv] = a3;
+                R0[iv + 1][jv] = b0; R1[iv + 1][jv] = b1; I0[iv + 1][jv] = b2; I1[iv + 1][jv] = b3;
+            }
+            if (jv & 1) {
+                const int iv = jv - 1;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                bmm_split<true>(a0, a1, a2, a3, ABZ_B(iv, jv), bD);
+                R0[iv][jv] = a0; R1[iv][jv] = a1; I0[iv][jv] = a2; I1[iv][jv] = a3;
+            }
+        }
+#pragma unroll
+        for (int t = jv - 1; t >= 1; t--) {
+            const BFrag bV = to_bfrag(ABZ_B(t, jv), src0, src1, par);
+#pragma unroll
+            for (int pp = 0; pp < t / 2; pp++) bmm2<true, true>(ABZ_B(2 * pp, jv), ABZ_B(2 * pp, t), bV, ABZ_B(2 * pp + 1, jv), ABZ_B(2 * pp + 1, t), bV);
+            if (t & 1) bmm_split<true>(ABZ_B(t - 1, jv), ABZ_B(t - 1, t), bV);
+        }
+    }
+    // M = L~^-1, columns left to right; tr += tr(V_{jm,t} M_{t,jm}) as soon as M_{t,jm} is final
+#pragma unroll
+    for (int jm = 0; jm < NB - 1; jm++) {
+#pragma unroll
+        for (int im = jm + 1; im < NB; im++) {
+            R0[im][jm] = dneg(R0[im][jm]); R1[im][jm] = dneg(R1[im][jm]); I0[im][jm] = dneg(I0[im][jm]); I1[im][jm] = dneg(I1[im][jm]);
+        }
+#pragma unroll
+        for (int t = jm + 1; t < NB; t++) {
+            const BFrag b = to_bfrag(ABZ_B(t, jm), src0, src1, par);
+            tr += R0[jm][t] * b.r[0] - I0[jm][t] * b.i[0] + R1[jm][t] * b.r[1] - I1[jm][t] * b.i[1];
+            ti += R0[jm][t] * b.i[0] + I0[jm][t] * b.r[0] + R1[jm][t] * b.i[1] + I1[jm][t] * b.r[1];
+#pragma unroll
+            for (int pp = 0; pp < (NB - 1 - t) / 2; pp++) {
+                const int im = t + 1 + 2 * pp;
+                bmm2<true, true>(ABZ_B(im, jm), ABZ_B(im, t), b, ABZ_B(im + 1, jm), ABZ_B(im + 1, t), b);
+            }
+            if ((NB - 1 - t) & 1) bmm_split<true>(ABZ_B(NB - 1, jm), ABZ_B(NB - 1, t), b);
+        }
+    }
+#undef ABZ_B
+    return make_double2(warp_sum(tr), warp_sum(ti));
+}
+
 // VAR 0: left-looking substitutions (V and M interleaved, one accumulation chain per block);
 // VAR 1: right-looking substitutions - a finished block of V (M) is turned into its fragment once and immediately applied to all
 //        rows above (below) it, so the block products of one step are independent (more DMMA chains in flight, one live fragment
@@ -447,6 +586,7 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
         int minhi = 0x7ff00000;
         double2 t;
         if constexpr (NB == 4 && VAR == 2) t = warp_trace_inverse_pipelined(R0, R1, I0, I1, lane, minhi);
+        else if constexpr (VAR == 3) t = warp_trace_inverse_paired<NB>(R0, R1, I0, I1, lane, minhi);
         else t = warp_trace_inverse<NB, (VAR == 2 ? 1 : VAR)>(R0, R1, I0, I1, lane, minhi);
         t.x = -t.x - (double)npad; t.y = -t.y;
 #pragma unroll
@@ -485,7 +625,7 @@ inline int mma_resolvent_warps() {
     static int w = 0;
     if (!w) {
         const char* e = getenv("ABZ_MMA_WARPS");
-        w = (e && atoi(e) == 12) ? 12 : 8;
+        w = (e && atoi(e) == 12) ? 12 : (e && atoi(e) == 4) ? 4 : 8;      // 4: one warp per sub-partition (measurement hook, norb 25..32)
     }
     return w;
 }
@@ -507,7 +647,7 @@ inline int mma_resolvent_plan(int n, long nk, int nw, long sm, long* ncta, int* 
 // substitution variant of the norb = 25..32 kernel (ABZ_MMA_VARIANT = 0 / 1, see warp_trace_inverse); smaller matrices use 0
 inline int mma_resolvent_variant() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("ABZ_MMA_VARIANT"); v = e ? std::min(2, std::max(0, atoi(e))) : ABZ_MMA_DEFAULT_VARIANT; }
+    if (v < 0) { const char* e = getenv("ABZ_MMA_VARIANT"); v = e ? std::min(3, std::max(0, atoi(e))) : ABZ_MMA_DEFAULT_VARIANT; }
     return v;
 }
 
@@ -515,7 +655,10 @@ template <int NB, int W>
 inline void mma_launch_one(const double2* H, const double* wnode, long nk, int n, int nw, const double2* z, const double2* sigma,
                            int mode, double2* outp, int* errflag, long ncta, int kper, cudaStream_t stream) {
     size_t smem = (size_t)nw * W * sizeof(double2);
-    if (NB == 4 && mma_resolvent_variant() == 2)
+    if (W == 4) smem = std::max<size_t>(smem, 120 * 1024);      // measurement hook: keeps a second 4-warp CTA off the SM
+    if (NB == 4 && mma_resolvent_variant() == 3)
+        resolvent_mma_kernel<NB, W, (NB == 4 ? 3 : 0)><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
+    else if (NB == 4 && mma_resolvent_variant() == 2)
         resolvent_mma_kernel<NB, W, (NB == 4 ? 2 : 0)><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
     else if (NB == 4 && mma_resolvent_variant() == 1)
         resolvent_mma_kernel<NB, W, (NB == 4 ? 1 : 0)><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
@@ -535,6 +678,9 @@ inline cudaError_t mma_resolvent_opt_in() {
 #undef ABZ_MMA_OPT
     { auto k8 = resolvent_mma_kernel<4, 8, 1>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 1>; set((const void*)k12); }
     { auto k8 = resolvent_mma_kernel<4, 8, 2>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 2>; set((const void*)k12); }
+    { auto k8 = resolvent_mma_kernel<4, 8, 3>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 3>; set((const void*)k12); }
+    { auto k4 = resolvent_mma_kernel<4, 4, 0>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 1>; set((const void*)k41); }
+    { auto k4 = resolvent_mma_kernel<4, 4, 2>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 3>; set((const void*)k41); }
     return e;
 }
 
@@ -550,7 +696,10 @@ inline cudaError_t mma_resolvent_launch(const double2* H, const double* wnode, l
         case 1: ABZ_MMA_CASE(1) break;
         case 2: ABZ_MMA_CASE(2) break;
         case 3: ABZ_MMA_CASE(3) break;
-        default: ABZ_MMA_CASE(4) break;
+        default:
+            if (W == 4) mma_launch_one<4, 4>(H, wnode, nk, n, nw, z, sigma, mode, outp, errflag, ncta, kper, stream);
+            else { ABZ_MMA_CASE(4) }
+            break;
     }
 #undef ABZ_MMA_CASE
     return cudaGetLastError();

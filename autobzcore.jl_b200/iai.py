@@ -40,9 +40,14 @@ def gk15_nodes(a, b):
     return a[..., None] + _OFF * s[..., None]
 
 
-def gk15_combine(a, b, f):
-    """QuadGK.evalrule: f (..., 15) values in gk15_nodes order -> (I, E), same operation order."""
+def gk15_combine(a, b, f, vdim=0):
+    """QuadGK.evalrule: f (..., 15) values in gk15_nodes order -> (I, E), same operation order.
+    vdim > 0: array-valued integrand, f is (..., 15, *value_shape) with vdim value axes; E = norm(Ik s - Ig s) (Frobenius, LinearAlgebra.norm)"""
+    if vdim:
+        f = np.moveaxis(np.asarray(f), -1 - vdim, -1)          # (..., *value_shape, 15)
     s = 0.5 * (np.asarray(b, dtype=np.float64) - np.asarray(a, dtype=np.float64))
+    if vdim:
+        s = s.reshape(s.shape + (1,) * vdim)
     fg = f[..., 0] + f[..., 1]
     fk = f[..., 2] + f[..., 3]
     Ig = fg * GK_GW[0]
@@ -60,6 +65,9 @@ def gk15_combine(a, b, f):
     Ik = Ik + (f0 * GK_W[7] + (f[..., 13] + f[..., 14]) * GK_W[6])
     Iks = Ik * s
     Igs = Ig * s
+    if vdim:
+        D = Iks - Igs
+        return Iks, np.sqrt(np.sum(np.abs(D) ** 2, axis=tuple(range(-vdim, 0))))
     return Iks, np.abs(Iks - Igs)
 
 
@@ -114,9 +122,9 @@ class DomainError(FloatingPointError):
 class _Pend:
     __slots__ = ("a", "b", "vals", "remaining", "tag", "shared")
 
-    def __init__(self, a, b, tag, dtype):
+    def __init__(self, a, b, tag, dtype, vshape=()):
         self.a, self.b, self.tag = a, b, tag
-        self.vals = np.zeros(15, dtype=dtype)
+        self.vals = np.zeros((15,) + tuple(vshape), dtype=dtype)
         self.remaining = 15
         self.shared = False
 
@@ -141,7 +149,9 @@ class NestedGK:
     """
 
     def __init__(self, nest, ndim, lims, fkind, z, sigma, post, dtype, atol, rtol, maxevals, cap2=64, cap1=2048, user=None,
-                 rank=0, nranks=1, allreduce=None):
+                 rank=0, nranks=1, allreduce=None, vshape=(), matrix=False):
+        # vshape: shape of an array-valued integrand (() = scalar); matrix=True: values are the device's (z - H - Sigma)^-1
+        self.vshape, self.vdim, self.matrix = tuple(vshape), len(tuple(vshape)), matrix
         # multi-rank (ndim >= 2): the 15 nodes of every panel of the OUTERMOST integral are dealt round-robin to the ranks; when a
         # rank's own work is exhausted all ranks meet in one sum-allreduce of the outstanding outer panels' node values (zeros for
         # foreign nodes) and take the identical accept/refine decision - the scheme of the C++ engine (csrc/abz_iai_engine.hpp)
@@ -170,7 +180,7 @@ class NestedGK:
 
     # ---- state machine
     def _start_segment(self, q, a, b, tag):
-        pend = _Pend(a, b, tag, self.dtype)
+        pend = _Pend(a, b, tag, self.dtype, self.vshape)
         if q.level == 0:
             self.q_eval.append((q, pend))
             return
@@ -222,8 +232,8 @@ class NestedGK:
             return                                            # combined in _exchange once every rank has delivered its nodes
         pend.remaining -= 1
         if pend.remaining == 0:
-            Is, Es = gk15_combine(pend.a, pend.b, pend.vals)
-            self._segment_done(pq, pend, Is[()], float(Es))
+            Is, Es = gk15_combine(pend.a, pend.b, pend.vals, self.vdim)
+            self._segment_done(pq, pend, Is[()] if not self.vdim else Is, float(Es))
 
     def _refine(self, q):
         s = heappop(q.heap)
@@ -249,7 +259,7 @@ class NestedGK:
                 q.I = q.I + sg[3]
                 q.E = q.E + sg[0]
             q.numevals = 15 * len(q.heap)
-            if q.numevals >= self.maxevals or q.E <= q.atol or q.E <= self.rtol * abs(q.I):
+            if q.numevals >= self.maxevals or q.E <= q.atol or q.E <= self.rtol * self._nrm(q.I):
                 self._finish(q)
             else:
                 for i in range(len(q.heap) // 2, 0, -1):
@@ -268,10 +278,13 @@ class NestedGK:
         q.numevals += 30
         heappush(q.heap, q.s1)
         heappush(q.heap, q.s2)
-        if q.E > q.atol and q.E > self.rtol * abs(q.I) and q.numevals < self.maxevals:
+        if q.E > q.atol and q.E > self.rtol * self._nrm(q.I) and q.numevals < self.maxevals:
             self._refine(q)
         else:
             self._finish(q)
+
+    def _nrm(self, v):
+        return abs(v) if not self.vdim else float(np.sqrt(np.sum(np.abs(v) ** 2)))
 
     # ---- driver
     def run(self):
@@ -310,18 +323,20 @@ class NestedGK:
             slots = None
             if self.ndim >= 2:
                 slots = np.repeat(np.array([q.slot for q, _ in batch], dtype=np.int64), 15)
-            if self.user is not None:
+            if self.matrix:
+                vals = self.nest.eval_matrix(xs.reshape(-1), slots, self.z, self.sigma).reshape((nseg, 15) + self.vshape)
+            elif self.user is not None:
                 H = self.nest.eval_h(xs.reshape(-1), slots)
                 k = np.empty((15 * nseg, self.ndim))
                 k[:, 0] = xs.reshape(-1)
                 if self.ndim > 1:
                     k[:, 1:] = np.repeat(np.array([q.outer for q, _ in batch], dtype=np.float64).reshape(nseg, self.ndim - 1), 15, axis=0)
-                vals = np.asarray(self.user(H, k), dtype=self.dtype).reshape(nseg, 15)
+                vals = np.asarray(self.user(H, k), dtype=self.dtype).reshape((nseg, 15) + self.vshape)
             else:
                 y = self.nest.eval(xs.reshape(-1), slots, self.z, self.sigma, self.fkind)
                 vals = self.post(y).reshape(nseg, 15)
             self.numevals += 15 * nseg
-            Is, Es = gk15_combine(aa, bb, vals)
+            Is, Es = gk15_combine(aa, bb, vals, self.vdim)
             for i in range(nseg):
                 q, pend = batch[i]
                 self._segment_done(q, pend, Is[i], float(Es[i]))
@@ -335,9 +350,9 @@ class NestedGK:
         if not sp:
             raise RuntimeError("IAI engine stalled")
         self.exchanges += 1
-        buf = np.concatenate([np.asarray(p.vals, dtype=np.complex128) for _, p in sp])
-        buf = np.asarray(self.allreduce(buf), dtype=np.complex128).reshape(len(sp), 15)
+        buf = np.concatenate([np.asarray(p.vals, dtype=np.complex128).reshape(-1) for _, p in sp])
+        buf = np.asarray(self.allreduce(buf), dtype=np.complex128).reshape((len(sp), 15) + self.vshape)
         for (q, pend), vals in zip(sp, buf):
-            pend.vals[:] = vals if np.iscomplexobj(pend.vals) else vals.real
-            Is, Es = gk15_combine(pend.a, pend.b, pend.vals)
-            self._segment_done(q, pend, Is[()], float(Es))
+            pend.vals[...] = vals if np.iscomplexobj(pend.vals) else vals.real
+            Is, Es = gk15_combine(pend.a, pend.b, pend.vals, self.vdim)
+            self._segment_done(q, pend, Is[()] if not self.vdim else Is, float(Es))

@@ -414,8 +414,6 @@ def _do_solve(cache, ps):
     bf.bz = cache.dom
     shard = cache.shard
     if bf.native and not bf.is_eig and cache.f.f.is_matrix:
-        if isinstance(salg, NestedQuad):
-            raise TypeError("IAI on the device supports scalar-valued integrands; use PTR / AutoPTR for the matrix-valued gloc_integrand")
         if on_bz and cache.dom.syms is not None and cache.f.f.symmetrize is None:
             # do_solve_autobz (src/brillouin.jl:348-353): unknown SymRep + non-trivial value => repeat on the full BZ
             import warnings
@@ -468,6 +466,21 @@ def _do_solve(cache, ps):
                 continue
             bound = b1.bound[0]
             ff = cache.f.f
+            if getattr(ff, "is_matrix", False):
+                # matrix-valued gloc_integrand under IAI (docs/src/examples.md:90-106; the reference's nest is generic in the value
+                # type, src/fourier.jl:452-456): (z - H - Sigma)^-1 at the panel nodes comes from the device (abz_nest_eval_matrix), the
+                # nested GK recursion with norm = Frobenius runs in the Python engine; SymRep maps the IBZ value to the full BZ
+                z, sigma = bound
+                n = cache.f.s.norb
+                eng = NestedGK(cache.cacheval["nest"], ndim, dom, None, z, sigma, None, np.complex128, atol, reltol, maxiters,
+                               rank=shard.rank, nranks=shard.nranks, allreduce=shard.allreduce if shard.nranks > 1 else None,
+                               vshape=(n, n), matrix=True)
+                Iv, Ev, ne = eng.run()
+                cache.cacheval["iai_rounds"] = eng.rounds
+                if on_bz and cache.dom.syms is not None and ff.symmetrize is not None:
+                    Iv = ff.symmetrize(cache.dom, Iv)
+                sols.append(IntegralSolution(sc * Iv, float(Ev) * sc * (ns if on_bz else 1), True, ne if counter else -1))
+                continue
             if b1.fkind == _lib.F_TRACE_H:
                 z, sigma = 0j, None
                 test = ff.post(np.zeros(1, dtype=np.complex128), bound)

@@ -182,6 +182,11 @@ int32_t abz_nest_eval(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const double*
 /* the same closure for a generic user integrand evaluated by the host (f.f(FourierValue(k, H(k)), p), src/fourier.jl:452-456;
  * BatchIntegrand's f!(y, x, p), src/batch.jl:4-20): only H at the nodes, Hk = ComplexF64[n,n,npts] */
 int32_t abz_nest_eval_h(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const double* x1, const int64_t* slot1, double* Hk);
+/* the matrix-valued innermost closure, gloc_integrand(h_k; eta, omega) = inv(complex(omega, eta) I - h_k.s) under IAI
+ * (docs/src/examples.md:90-106; the reference's nest is generic in the value type, src/fourier.jl:452-456): Y = ComplexF64[n,n,npts],
+ * Y[:,:,i] = (z I - H(x1_i on level-1 slot slot1_i) - Sigma)^-1 by pivoted Gauss-Jordan; z = ComplexF64[1], sigma = ComplexF64[n,n] or NULL */
+int32_t abz_nest_eval_matrix(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const double* x1, const int64_t* slot1, const double* z,
+                             const double* sigma, double* Y);
 /* The whole nested adaptive solve do_solve(f::FourierIntegrand, lims, ::NestedQuad) (src/fourier.jl:493-510) with
  * GK(7,15) at every level (AuxQuadGKJL/QuadGKJL defaults, src/algorithms.jl:215-240): the adaptive control flow
  * (QuadGK do_quadgk/adapt/refine, DataStructures heap, inner abstol = abstol/len, src/fourier.jl:479-480) runs on

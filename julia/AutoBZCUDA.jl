@@ -302,6 +302,42 @@ function iai_solve(n::DeviceNest, lkind::Integer, la::Vector{Float64}, lb, z::Co
     return IntegralSolution(vkind == 1 ? out[1] : complex(out[1], out[2]), out[3], true, Int(stats[1]))
 end
 
+# General iterated limits (any IteratedIntegration.AbstractIteratedLimits, e.g. the Polyhedron3 of ext/SymmetryReduceBZExt.jl:33-58):
+# the library asks for the breakpoints of the variable `dim` given the outer variables fixed so far (outermost first).
+function _limits_cb(dim::Int32, xfixed::Ptr{Float64}, segs::Ptr{Float64}, maxseg::Int32, user::Ptr{Cvoid})::Int32
+    try
+        lims = unsafe_pointer_to_objref(user)[]
+        nd = ndims(lims)
+        cur = lims
+        for k in 1:(nd - dim)                      # fixandeliminate from the outermost variable inwards
+            cur = fixandeliminate(cur, unsafe_load(xfixed, k), Val(nd - k + 1))
+        end
+        sg = segments(cur, dim)
+        length(sg) > maxseg && return Int32(-1)
+        for (i, v) in enumerate(sg)
+            unsafe_store!(segs, Float64(v), i)
+        end
+        return Int32(length(sg))
+    catch
+        return Int32(-2)
+    end
+end
+function iai_solve_general(n::DeviceNest, lims, z::ComplexF64; vkind=0, abstol=0.0, reltol=(abstol == 0 ? sqrt(eps(Float64)) : 0.0),
+                           maxiters=typemax(Int64) >> 1, device_leaves=true, rank=0, nranks=1, exchange=C_NULL)
+    out = zeros(3); stats = zeros(Int64, 4)
+    zz = Float64[real(z), imag(z)]
+    box = Ref(lims)
+    cb = @cfunction(_limits_cb, Int32, (Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Cvoid}))
+    GC.@preserve box begin
+        check(n.ctx, ccall((:abz_iai_solve_general, LIB), Int32,
+                           (Ptr{Cvoid}, UInt64, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                            Float64, Float64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}),
+                           n.ctx.h, n.h, cb, pointer_from_objref(box), 0, vkind, zz, C_NULL, C_NULL,
+                           abstol, reltol, maxiters, device_leaves ? 3 : 0, rank, nranks, exchange, C_NULL, out, stats))
+    end
+    return IntegralSolution(vkind == 1 ? out[1] : complex(out[1], out[2]), out[3], true, Int(stats[1]))
+end
+
 # v0.4+ API names (BASELINE.json north_star) as thin aliases
 const FourierIntegralFunction = FourierIntegrand
 

@@ -162,6 +162,15 @@ class OracleNest:
             H[:, :, i] = self._contract(src, nn, s.M[0], s.lo[0], s.period[0], float(x)).reshape(s.n, s.n, order="F")
         return H
 
+    def eval_matrix(self, x1, slot1, z, sigma=None):
+        """(z - H - Sigma)^-1 at the nodes -> [npts, n, n] (numpy / LAPACK inverse: the reference's `inv` on a Matrix)"""
+        H = np.moveaxis(self.eval_h(x1, slot1), 2, 0)
+        n = self.so.n
+        A = complex(np.atleast_1d(z)[0]) * np.eye(n)[None] - H
+        if sigma is not None:
+            A = A - np.asarray(sigma, dtype=np.complex128).reshape(n, n)[None]
+        return np.linalg.inv(A)
+
     def eval(self, x1, slot1, z, sigma, fkind):
         s = self.so
         nn = s.n * s.n

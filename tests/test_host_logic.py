@@ -1,6 +1,7 @@
 """Host control flow (BZ conventions, tolerance rescaling, AutoPTR loop, IAI engine, sharding) exercised on CPU
 through the oracle-backed test double, against the reference's own tests (test/fourier.jl, test/brillouin.jl).
 CPU only; the same tests run against the device backend in test_gpu_parity.py."""
+import json
 import math
 import os
 import subprocess
@@ -266,8 +267,27 @@ def test_matrix_valued_gloc_integrand_and_symrep(orc):
     solver = ab.IntegralSolver(ab.FourierIntegrand(ab.gloc_integrand, fs, eta=0.4), fbz, ab.PTR(npt=6), backend=be)
     G = ab.batchsolve(solver, [{"omega": w} for w in (0.0, 0.3)])
     assert G.shape == (2, n, n)
-    with pytest.raises(TypeError):
-        ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_integrand, fs, eta=0.4), fbz, p), ab.IAI(), backend=be)
+    # IAI on the matrix-valued integrand (the nest is generic in the value type, src/fourier.jl:452-456; norm = Frobenius):
+    # same integral as PTR within the tolerance, SymRep applied to the IBZ value, trace consistent with the scalar integrand
+    # (eta = 4 and abstol = 0.1 on a value of size 50 keep the Python engine + CPU oracle to ~1e5 evaluations)
+    gi = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_integrand, fs, eta=4.0), fbz, p), ab.EvalCounter(ab.IAI()), abstol=0.1, backend=be)
+    assert gi.u.shape == (n, n) and gi.numevals > 0 and gi.resid <= 0.1
+    fine = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_integrand, fs, eta=4.0), fbz, p), ab.PTR(npt=32), backend=be).u
+    assert np.max(np.abs(gi.u - fine)) < 0.1
+    gt = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=4.0), fbz, p), ab.IAI(), abstol=0.1, backend=be).u
+    assert abs(np.trace(gi.u) - gt) < 0.2
+    gs = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(sym, fs, eta=4.0), ibz, p), ab.IAI(), abstol=0.1, backend=be).u
+    assert np.max(np.abs(gs - fine)) < 0.1
+    # a 1 x 1 "matrix" takes exactly the decisions of the scalar integrand (docs/src/examples.md:90-105: IAI on gloc_integrand of a
+    # scalar series, 2-d): same numevals, same value, and the value the reference's docs print
+    c2 = np.zeros((1, 1, 3, 3)); c2[0, 0, 0, 1] = c2[0, 0, 2, 1] = c2[0, 0, 1, 0] = c2[0, 0, 1, 2] = 0.5
+    h2 = ab.FourierSeries(c2, period=1.0, lo=(-1, -1), norb=1)
+    bz2 = ab.load_bz(ab.FBZ(2), np.eye(2) * 2 * np.pi)
+    sm = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_integrand, h2, eta=0.1), bz2, {"omega": 0.0}), ab.EvalCounter(ab.IAI()), abstol=1e-3, backend=be)
+    ss = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_trace_integrand, h2, eta=0.1), bz2, {"omega": 0.0}), ab.EvalCounter(ab.IAI()), abstol=1e-3, backend=be)
+    assert sm.numevals == ss.numevals and abs(sm.u[0, 0] - ss.u) <= 1e-13 * abs(ss.u)
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))["reference_known_answers"]
+    assert abs(ss.u - complex(*gold["docs/src/examples.md:105 (IAI abstol=1e-3, 2-D gloc on FBZ(2), eta=0.1, omega=0)"])) < 1e-3
 
 
 def test_batchsolve_log_archive(tmp_path, orc, svo):
@@ -390,3 +410,25 @@ def test_symrep_names():
     assert isinstance(ab.SymRep(g), ab.FunctionRep) and np.all(ab.symmetrize(g, ibz, x) == 2 * x)
     with pytest.raises(NotImplementedError):
         ab.load_bz(ab.IBZ(), np.eye(3))
+
+
+def test_ibz_with_supplied_polyhedron(orc):
+    """src/brillouin.jl:205-247 + ext/SymmetryReduceBZExt.jl: load_bz(IBZ) = SymmetricBZ(A, B, polyhedral limits, point group).  The
+    polyhedron and the group (what SymmetryReduceBZ computes) are supplied by the caller; for the cubic group they are the
+    tetrahedron and the 48 automorphisms of load_bz(CubicSymIBZ), and the integral over the two must agree
+    (test/test_ibz.jl:151-180 compares IBZ against FBZ integrals the same way)."""
+    from autobz_b200.bz import cube_automorphisms
+    verts = [(0, 0, 0), (0, 0, 0.5), (0, 0.5, 0.5), (0.5, 0.5, 0.5)]
+    pbz = ab.load_bz(ab.IBZ(3, polyhedron=verts, syms=cube_automorphisms(3)), np.eye(3))
+    cbz, fbz = ab.load_bz(ab.CubicSymIBZ(), np.eye(3)), ab.load_bz(ab.FBZ(), np.eye(3))
+    assert pbz.nsyms == 48 and isinstance(pbz.lims, ab.PolyhedronLimits)
+    H, lo = ab.synthetic.wannier_hamiltonian(2, 1, cubic=True)
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=2)
+    be = OracleBackend()
+    f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=4.0)
+    a = ab.solve(ab.IntegralProblem(f, pbz, {"omega": 0.3}), ab.EvalCounter(ab.IAI()), abstol=0.05, backend=be)
+    b = ab.solve(ab.IntegralProblem(f, cbz, {"omega": 0.3}), ab.EvalCounter(ab.IAI()), abstol=0.05, backend=be)
+    c = ab.solve(ab.IntegralProblem(f, fbz, {"omega": 0.3}), ab.PTR(npt=32), backend=be)
+    assert abs(a.u - c.u) < 0.05 and abs(b.u - c.u) < 0.05 and a.numevals > 0
+    with pytest.raises(ValueError):
+        ab.load_bz(ab.IBZ(polyhedron=[(0, 0, 0), (1, 0, 0)], syms=[np.eye(3)]), np.eye(3))

@@ -38,5 +38,6 @@ print(f"# SASS histogram of {os.path.basename(so)} (sm_100a), static instruction
 print("# " + " ".join(f"{c:>6s}" for c in ["total"] + COLS) + "  kernel")
 for k, h in hist.items():
     name = demangled.get(k, k)
+    name = re.sub(r"\((int|bool|unsigned int)\)", "", name)           # template arguments print as (int)4
     name = re.sub(r"\(.*", "", name).replace("void ", "").replace("abz::", "")
     print("  " + " ".join(f"{h.get(c, 0):6d}" for c in ["total"] + COLS) + "  " + name)
