@@ -13,12 +13,14 @@ class AutoBZAlgorithm(IntegralAlgorithm):
 
 
 class AuxQuadGKJL(IntegralAlgorithm):
-    """AuxQuadGKJL(; order=7, norm=norm) (src/algorithms.jl:202-208).  Only order 7 (GK 7/15) is supported."""
+    """AuxQuadGKJL(; order=7, norm=norm) (src/algorithms.jl:202-208).  Order 7 (GK 7/15) runs in the library's native IAI engine and
+    its device-side integrals; any other order >= 2 runs the same state machine in the Python engine (iai.NestedGK) with the device
+    evaluating the panel nodes."""
 
     def __init__(self, order=7, norm=abs):
-        if order != 7:
-            raise ValueError("only the Gauss-Kronrod (7,15) rule is implemented")
-        self.order, self.norm = order, norm
+        if int(order) != order or order < 2:
+            raise ValueError("the Gauss-Kronrod order must be an integer >= 2")
+        self.order, self.norm = int(order), norm
 
 
 class NestedQuad(IntegralAlgorithm):

@@ -67,8 +67,107 @@ def gk15_combine(a, b, f, vdim=0):
     Igs = Ig * s
     if vdim:
         D = Iks - Igs
-        return Iks, np.sqrt(np.sum(np.abs(D) ** 2, axis=tuple(range(-vdim, 0))))
+        return Iks, np.sqrt(np.sum(D.real ** 2 + D.imag ** 2, axis=tuple(range(-vdim, 0))))     # LinearAlgebra.norm = sqrt(sum(abs2, D))
     return Iks, np.abs(Iks - Igs)
+
+
+def kronrod(n):
+    """Gauss-Kronrod rule of order n in QuadGK.kronrod's conventions: x (the n+1 nodes in [-1, 0], ascending, x[n] = 0),
+    w (their Kronrod weights), gw (the Gauss weights of x[1], x[3], ...).  The Kronrod nodes are the Gauss-Legendre nodes plus the roots
+    of the Stieltjes polynomial E_{n+1} (orthogonal to every polynomial of degree <= n under the signed weight P_n); E_{n+1} is found
+    in the Legendre basis from those n+1 conditions, its roots are polished by Newton steps, the weights come from exactness on
+    P_0 .. P_2n.  Reproduces QUADPACK's qk15 / qk21 / qk31 tables to 3e-16 (tests/test_host_logic.py); QuadGK.jl computes the same rule by
+    Laurie's Jacobi-Kronrod matrix, so agreement with the reference for orders != 7 is at rounding level, not bitwise."""
+    from numpy.polynomial import legendre as L
+    if n < 2:
+        raise ValueError("Gauss-Kronrod order must be at least 2")
+    xq, wq = L.leggauss(2 * n + 3)
+    eye = np.eye(2 * n + 2)
+    P = np.stack([L.legval(xq, eye[j, : j + 1]) for j in range(n + 2)])
+    G = np.einsum("q,q,jq,kq->kj", wq, P[n], P, P[: n + 1])
+    idx = [j for j in range(n + 1) if (j - (n + 1)) % 2 == 0]                   # E_{n+1} has the parity of n + 1
+    csub = np.linalg.lstsq(G[:, idx], -G[:, n + 1], rcond=None)[0]
+    c = np.zeros(n + 2)
+    c[n + 1] = 1.0
+    c[idx] = csub
+    xe = np.sort(L.legroots(c).real)
+    dc = L.legder(c)
+    for _ in range(4):
+        xe = xe - L.legval(xe, c) / L.legval(xe, dc)
+    xg, gwf = L.leggauss(n)
+    xs = np.sort(np.concatenate([xe, xg]))
+    xs = 0.5 * (xs - xs[::-1])
+    xs[n] = 0.0
+    V = np.stack([L.legval(xs, eye[k, : k + 1]) for k in range(2 * n + 1)])
+    rhs = np.zeros(2 * n + 1)
+    rhs[0] = 2.0
+    w = np.linalg.solve(V, rhs)
+    w = 0.5 * (w + w[::-1])
+    return xs[: n + 1].copy(), w[: n + 1].copy(), gwf[: (n + 1) // 2].copy()
+
+
+class GKRule:
+    """QuadGK.evalrule for one Gauss-Kronrod order (AuxQuadGKJL(order=n), src/algorithms.jl:202-208): K = 2n + 1 nodes per panel in
+    evalrule's evaluation order, and the (I, E) combination in its operation order.  Order 7 uses the QUADPACK table above (the
+    constants QuadGK.jl caches for Float64), so it is bit-identical to gk15_nodes / gk15_combine."""
+    _cache = {}
+
+    def __new__(cls, n=7):
+        n = int(n)
+        if n not in cls._cache:
+            r = super().__new__(cls)
+            r.n, r.K = n, 2 * n + 1
+            r.x, r.w, r.gw = (GK_X, GK_W, GK_GW) if n == 7 else kronrod(n)
+            r.odd = (n % 2 == 1)                                   # n1 = 1 - (length(x) & 1)
+            r.npairs = len(r.gw) - (1 if r.odd else 0)
+            off = []
+            for i in range(1, r.npairs + 1):                       # (x[2i]+, x[2i]-), (x[2i-1]+, x[2i-1]-), 1-based
+                off += [1.0 + r.x[2 * i - 1], 1.0 - r.x[2 * i - 1], 1.0 + r.x[2 * i - 2], 1.0 - r.x[2 * i - 2]]
+            off += [1.0]
+            if r.odd:
+                off += [1.0 + r.x[n - 1], 1.0 - r.x[n - 1]]
+            r.off = np.array(off)
+            assert r.off.size == r.K
+            cls._cache[n] = r
+        return cls._cache[n]
+
+    def nodes(self, a, b):
+        a = np.asarray(a, dtype=np.float64)
+        s = 0.5 * (np.asarray(b, dtype=np.float64) - a)
+        return a[..., None] + self.off * s[..., None]
+
+    def combine(self, a, b, f, vdim=0):
+        if self.n == 7:
+            return gk15_combine(a, b, f, vdim)
+        if vdim:
+            f = np.moveaxis(np.asarray(f), -1 - vdim, -1)
+        s = 0.5 * (np.asarray(b, dtype=np.float64) - np.asarray(a, dtype=np.float64))
+        if vdim:
+            s = s.reshape(s.shape + (1,) * vdim)
+        w, gw = self.w, self.gw
+        fg = f[..., 0] + f[..., 1]
+        fk = f[..., 2] + f[..., 3]
+        Ig = fg * gw[0]
+        Ik = fg * w[1] + fk * w[0]
+        p = 4
+        for i in range(2, self.npairs + 1):
+            fg = f[..., p] + f[..., p + 1]
+            fk = f[..., p + 2] + f[..., p + 3]
+            Ig = Ig + fg * gw[i - 1]
+            Ik = Ik + (fg * w[2 * i - 1] + fk * w[2 * i - 2])
+            p += 4
+        if self.odd:
+            f0 = f[..., p]
+            Ig = Ig + f0 * gw[-1]
+            Ik = Ik + (f0 * w[-1] + (f[..., p + 1] + f[..., p + 2]) * w[-2])
+        else:
+            Ik = Ik + f[..., p] * w[-1]
+        Iks = Ik * s
+        Igs = Ig * s
+        if vdim:
+            D = Iks - Igs
+            return Iks, np.sqrt(np.sum(D.real ** 2 + D.imag ** 2, axis=tuple(range(-vdim, 0))))     # LinearAlgebra.norm = sqrt(sum(abs2, D))
+        return Iks, np.abs(Iks - Igs)
 
 
 # ---- DataStructures.jl binary heap with Base.Reverse on Segment.E (segments are (E, a, b, I)) ---------
@@ -122,10 +221,10 @@ class DomainError(FloatingPointError):
 class _Pend:
     __slots__ = ("a", "b", "vals", "remaining", "tag", "shared")
 
-    def __init__(self, a, b, tag, dtype, vshape=()):
+    def __init__(self, a, b, tag, dtype, vshape=(), K=15):
         self.a, self.b, self.tag = a, b, tag
-        self.vals = np.zeros((15,) + tuple(vshape), dtype=dtype)
-        self.remaining = 15
+        self.vals = np.zeros((K,) + tuple(vshape), dtype=dtype)
+        self.remaining = K
         self.shared = False
 
 
@@ -149,7 +248,10 @@ class NestedGK:
     """
 
     def __init__(self, nest, ndim, lims, fkind, z, sigma, post, dtype, atol, rtol, maxevals, cap2=64, cap1=2048, user=None,
-                 rank=0, nranks=1, allreduce=None, vshape=(), matrix=False):
+                 rank=0, nranks=1, allreduce=None, vshape=(), matrix=False, orders=None):
+        # orders[level]: Gauss-Kronrod order of each level, level 0 = innermost variable (NestedQuad(algs...): alg = algs[dim],
+        # src/algorithms.jl:462-463); None = GK(7,15) everywhere
+        self.rules = [GKRule(7 if orders is None else orders[l]) for l in range(ndim)]
         # vshape: shape of an array-valued integrand (() = scalar); matrix=True: values are the device's (z - H - Sigma)^-1
         self.vshape, self.vdim, self.matrix = tuple(vshape), len(tuple(vshape)), matrix
         # multi-rank (ndim >= 2): the 15 nodes of every panel of the OUTERMOST integral are dealt round-robin to the ranks; when a
@@ -180,16 +282,17 @@ class NestedGK:
 
     # ---- state machine
     def _start_segment(self, q, a, b, tag):
-        pend = _Pend(a, b, tag, self.dtype, self.vshape)
+        rule = self.rules[q.level]
+        pend = _Pend(a, b, tag, self.dtype, self.vshape, rule.K)
         if q.level == 0:
             self.q_eval.append((q, pend))
             return
-        xs = gk15_nodes(a, b)
+        xs = rule.nodes(a, b)
         shared = self.nranks > 1 and q.level == self.ndim - 1
         if shared:
             pend.shared = True
             self.shared_pends.append((q, pend))
-        for i in range(15):
+        for i in range(rule.K):
             if shared:
                 mine = (self.spawn_counter % self.nranks) == self.rank
                 self.spawn_counter += 1
@@ -232,7 +335,7 @@ class NestedGK:
             return                                            # combined in _exchange once every rank has delivered its nodes
         pend.remaining -= 1
         if pend.remaining == 0:
-            Is, Es = gk15_combine(pend.a, pend.b, pend.vals, self.vdim)
+            Is, Es = self.rules[pq.level].combine(pend.a, pend.b, pend.vals, self.vdim)
             self._segment_done(pq, pend, Is[()] if not self.vdim else Is, float(Es))
 
     def _refine(self, q):
@@ -258,7 +361,7 @@ class NestedGK:
             for sg in q.heap[1:]:
                 q.I = q.I + sg[3]
                 q.E = q.E + sg[0]
-            q.numevals = 15 * len(q.heap)
+            q.numevals = self.rules[q.level].K * len(q.heap)
             if q.numevals >= self.maxevals or q.E <= q.atol or q.E <= self.rtol * self._nrm(q.I):
                 self._finish(q)
             else:
@@ -275,7 +378,7 @@ class NestedGK:
         s = q.popped
         q.I = (q.I - s[3]) + q.s1[3] + q.s2[3]
         q.E = (q.E - s[0]) + q.s1[0] + q.s2[0]
-        q.numevals += 30
+        q.numevals += 2 * self.rules[q.level].K
         heappush(q.heap, q.s1)
         heappush(q.heap, q.s2)
         if q.E > q.atol and q.E > self.rtol * self._nrm(q.I) and q.numevals < self.maxevals:
@@ -284,7 +387,7 @@ class NestedGK:
             self._finish(q)
 
     def _nrm(self, v):
-        return abs(v) if not self.vdim else float(np.sqrt(np.sum(np.abs(v) ** 2)))
+        return abs(v) if not self.vdim else float(np.sqrt(np.sum(np.real(v) ** 2 + np.imag(v) ** 2)))
 
     # ---- driver
     def run(self):
@@ -319,24 +422,26 @@ class NestedGK:
             nseg = len(batch)
             aa = np.array([p.a for _, p in batch])
             bb = np.array([p.b for _, p in batch])
-            xs = gk15_nodes(aa, bb)
+            rule0 = self.rules[0]
+            K0 = rule0.K
+            xs = rule0.nodes(aa, bb)
             slots = None
             if self.ndim >= 2:
-                slots = np.repeat(np.array([q.slot for q, _ in batch], dtype=np.int64), 15)
+                slots = np.repeat(np.array([q.slot for q, _ in batch], dtype=np.int64), K0)
             if self.matrix:
-                vals = self.nest.eval_matrix(xs.reshape(-1), slots, self.z, self.sigma).reshape((nseg, 15) + self.vshape)
+                vals = self.nest.eval_matrix(xs.reshape(-1), slots, self.z, self.sigma).reshape((nseg, K0) + self.vshape)
             elif self.user is not None:
                 H = self.nest.eval_h(xs.reshape(-1), slots)
-                k = np.empty((15 * nseg, self.ndim))
+                k = np.empty((K0 * nseg, self.ndim))
                 k[:, 0] = xs.reshape(-1)
                 if self.ndim > 1:
-                    k[:, 1:] = np.repeat(np.array([q.outer for q, _ in batch], dtype=np.float64).reshape(nseg, self.ndim - 1), 15, axis=0)
-                vals = np.asarray(self.user(H, k), dtype=self.dtype).reshape((nseg, 15) + self.vshape)
+                    k[:, 1:] = np.repeat(np.array([q.outer for q, _ in batch], dtype=np.float64).reshape(nseg, self.ndim - 1), K0, axis=0)
+                vals = np.asarray(self.user(H, k), dtype=self.dtype).reshape((nseg, K0) + self.vshape)
             else:
                 y = self.nest.eval(xs.reshape(-1), slots, self.z, self.sigma, self.fkind)
-                vals = self.post(y).reshape(nseg, 15)
-            self.numevals += 15 * nseg
-            Is, Es = gk15_combine(aa, bb, vals, self.vdim)
+                vals = self.post(y).reshape(nseg, K0)
+            self.numevals += K0 * nseg
+            Is, Es = rule0.combine(aa, bb, vals, self.vdim)
             for i in range(nseg):
                 q, pend = batch[i]
                 self._segment_done(q, pend, Is[i], float(Es[i]))
@@ -351,8 +456,9 @@ class NestedGK:
             raise RuntimeError("IAI engine stalled")
         self.exchanges += 1
         buf = np.concatenate([np.asarray(p.vals, dtype=np.complex128).reshape(-1) for _, p in sp])
-        buf = np.asarray(self.allreduce(buf), dtype=np.complex128).reshape((len(sp), 15) + self.vshape)
+        top = self.rules[self.ndim - 1]
+        buf = np.asarray(self.allreduce(buf), dtype=np.complex128).reshape((len(sp), top.K) + self.vshape)
         for (q, pend), vals in zip(sp, buf):
             pend.vals[...] = vals if np.iscomplexobj(pend.vals) else vals.real
-            Is, Es = gk15_combine(pend.a, pend.b, pend.vals, self.vdim)
+            Is, Es = top.combine(pend.a, pend.b, pend.vals, self.vdim)
             self._segment_done(q, pend, Is[()] if not self.vdim else Is, float(Es))

@@ -377,7 +377,11 @@ def _init_cacheval(cache):
             raise TypeError("NestedQuad needs iterated limits")
         if f.native and f.f.is_eig:
             raise TypeError("IAI on the device supports the resolvent / affine integrands and host (batch) integrands")
-        cv["nest"] = cache.backend.make_nest(f.s, ndim, 64, 2048)
+        # arena of contracted series: live level-2 slots <= 2 outstanding outer panels x K nodes (x initial segments), live level-1
+        # slots <= that x 2 panels x K nodes; GK(7,15) fits the default 64 / 2048
+        K = max(2 * a.order + 1 for a in salg.algs)
+        cv["nest_caps"] = (max(64, 4 * K), max(2048, max(64, 4 * K) * 2 * K))
+        cv["nest"] = cache.backend.make_nest(f.s, ndim, *cv["nest_caps"])
     else:
         raise TypeError(f"unsupported algorithm {type(salg).__name__} for FourierIntegrand")
 
@@ -444,6 +448,18 @@ def _do_solve(cache, ps):
         atol = abstol
         if on_bz and abstol is not None:
             atol = abstol / (j * ns)                        # src/brillouin.jl:342
+        # per-level algorithms (NestedQuad(algs...): algs[dim] belongs to variable `dim`, src/algorithms.jl:462-463, 503-505); one
+        # algorithm is repeated for every level.  A custom norm or an order other than 7 keeps the solve in the Python engine.
+        algs = salg.algs
+        if len(algs) == 1:
+            algs = algs * ndim
+        if len(algs) != ndim:
+            raise ValueError(f"NestedQuad got {len(algs)} algorithms for a {ndim}-dimensional domain")
+        if any(a.norm is not abs for a in algs):
+            raise NotImplementedError("AuxQuadGKJL(norm=...) other than abs / the Frobenius norm is not supported")
+        orders = tuple(a.order for a in algs)
+        default_gk = all(o == 7 for o in orders)
+        caps = cache.cacheval.get("nest_caps", (64, 2048))
         for p in ps:
             b1 = _BoundIntegrand(cache.f, [p])
             if not b1.native:
@@ -457,7 +473,7 @@ def _do_solve(cache, ps):
                     return v
 
                 eng = NestedGK(cache.cacheval["nest"], ndim, dom, None, None, None, None, np.complex128, atol, reltol, maxiters, user=user,
-                               rank=shard.rank, nranks=shard.nranks, allreduce=shard.allreduce if shard.nranks > 1 else None)
+                               rank=shard.rank, nranks=shard.nranks, allreduce=shard.allreduce if shard.nranks > 1 else None, orders=orders, cap2=caps[0], cap1=caps[1])
                 Iv, Ev, ne = eng.run()
                 cache.cacheval["iai_rounds"] = eng.rounds
                 mult = sc * (ns if on_bz else 1)
@@ -474,7 +490,7 @@ def _do_solve(cache, ps):
                 n = cache.f.s.norb
                 eng = NestedGK(cache.cacheval["nest"], ndim, dom, None, z, sigma, None, np.complex128, atol, reltol, maxiters,
                                rank=shard.rank, nranks=shard.nranks, allreduce=shard.allreduce if shard.nranks > 1 else None,
-                               vshape=(n, n), matrix=True)
+                               vshape=(n, n), matrix=True, orders=orders, cap2=caps[0], cap1=caps[1])
                 Iv, Ev, ne = eng.run()
                 cache.cacheval["iai_rounds"] = eng.rounds
                 if on_bz and cache.dom.syms is not None and ff.symmetrize is not None:
@@ -490,7 +506,7 @@ def _do_solve(cache, ps):
             dtype = np.complex128 if np.iscomplexobj(test) else np.float64
             nest = cache.cacheval["nest"]
             vkind = _native_vkind(ff)
-            if vkind is not None and hasattr(nest, "iai_solve") and getattr(cache.backend, "iai_engine", "python") == "native":
+            if default_gk and vkind is not None and hasattr(nest, "iai_solve") and getattr(cache.backend, "iai_engine", "python") == "native":
                 # abz_iai_solve: same control flow, run by the library's C++ host engine (one ccall per solve)
                 atol_ = 0.0 if atol is None else atol
                 rtol_ = reltol if reltol is not None else (np.sqrt(np.finfo(float).eps) if atol_ == 0 else 0.0)
@@ -514,7 +530,7 @@ def _do_solve(cache, ps):
             else:
                 eng = NestedGK(nest, ndim, dom, b1.fkind, z, sigma, lambda y, ff=ff, bound=bound: ff.post(y, bound),
                                dtype, atol, reltol, maxiters,
-                               rank=shard.rank, nranks=shard.nranks, allreduce=shard.allreduce if shard.nranks > 1 else None)
+                               rank=shard.rank, nranks=shard.nranks, allreduce=shard.allreduce if shard.nranks > 1 else None, orders=orders, cap2=caps[0], cap1=caps[1])
                 Iv, Ev, ne = eng.run()
                 cache.cacheval["iai_rounds"] = eng.rounds
             mult = sc * (ns if on_bz else 1)                # val = j * symmetrize(f, bz, sol.u) (TrivialRep: x nsyms)

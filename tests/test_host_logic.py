@@ -432,3 +432,115 @@ def test_ibz_with_supplied_polyhedron(orc):
     assert abs(a.u - c.u) < 0.05 and abs(b.u - c.u) < 0.05 and a.numevals > 0
     with pytest.raises(ValueError):
         ab.load_bz(ab.IBZ(polyhedron=[(0, 0, 0), (1, 0, 0)], syms=[np.eye(3)]), np.eye(3))
+
+
+def test_kronrod_rules_match_quadpack_tables():
+    """AuxQuadGKJL(order=n) (src/algorithms.jl:202-208): the rule generator against QUADPACK's published qk15 / qk21 / qk31 constants,
+    polynomial exactness (degree 3n+1, or 3n+2 for odd n) and the embedded Gauss rule, n = 2 ... 20"""
+    from autobz_b200 import iai
+    x, w, gw = iai.kronrod(7)
+    assert np.abs(x - iai.GK_X).max() < 5e-16 and np.abs(w - iai.GK_W).max() < 5e-16 and np.abs(gw - iai.GK_GW).max() < 5e-16
+    x, w, gw = iai.kronrod(10)
+    assert abs(x[0] + 0.995657163025808080735527280689003) < 5e-16 and abs(w[-1] - 0.149445554002916905664936468389821) < 5e-16
+    x, w, gw = iai.kronrod(15)
+    assert abs(x[0] + 0.998002298693397060285172840152271) < 5e-16 and abs(w[-1] - 0.101330007014791549017374792767493) < 5e-16
+    for n in range(2, 21):
+        r = iai.GKRule(n)
+        assert r.K == 2 * n + 1 and r.off.size == r.K and np.all(r.w > 0)
+        xs = np.concatenate([r.x, -r.x[:-1][::-1]])
+        ws = np.concatenate([r.w, r.w[:-1][::-1]])
+        deg = 3 * n + 1 + (n % 2)
+        for k in range(0, deg + 1, 2):
+            assert abs(np.sum(ws * xs ** k) - 2 / (k + 1)) < 2e-15
+        xg, wg = np.polynomial.legendre.leggauss(n)
+        assert np.abs(r.x[1::2] - xg[: n // 2 + (n % 2)][: len(r.x[1::2])]).max() < 5e-16
+        # evalrule of a polynomial of degree 2n - 1: Gauss and Kronrod agree, E ~ 0, I exact
+        f = lambda t: t ** (2 * n - 1) + 3 * t ** 2
+        I, E = r.combine(0.5, 2.0, f(r.nodes(0.5, 2.0)))
+        exact = (2.0 ** (2 * n) - 0.5 ** (2 * n)) / (2 * n) + 2.0 ** 3 - 0.5 ** 3
+        assert abs(I - exact) < 1e-13 * abs(exact) and E < 1e-12 * abs(exact)
+    assert iai.GKRule(7) is iai.GKRule(7)
+    with pytest.raises(ValueError):
+        ab.AuxQuadGKJL(order=1)
+
+
+def _nested_quadgk_sequential(point_value, lims, orders, atol, rtol, maxevals):
+    """The reference's recursion written down directly (QuadGK do_quadgk + adapt per level, abstol / len for the inner levels,
+    src/fourier.jl:474-481): an independent control flow against which the level-synchronous engine is checked."""
+    from autobz_b200 import iai
+    count = [0]
+
+    def quadgk(f, segs, rule, atol_):
+        heap = []
+        for a, b in zip(segs[:-1], segs[1:]):
+            I, E = rule.combine(a, b, np.array([f(x) for x in rule.nodes(a, b)]))
+            heap.append((float(E), a, b, I[()]))
+        I, E = heap[0][3], heap[0][0]
+        for s in heap[1:]:
+            I, E = I + s[3], E + s[0]
+        ne = rule.K * len(heap)
+        if ne >= maxevals or E <= atol_ or E <= rtol * abs(I):
+            return I
+        for i in range(len(heap) // 2, 0, -1):
+            iai._percolate_down(heap, i, heap[i - 1], len(heap))
+        while E > atol_ and E > rtol * abs(I) and ne < maxevals:
+            s = iai.heappop(heap)
+            mid = (s[1] + s[2]) / 2
+            new = []
+            for a, b in ((s[1], mid), (mid, s[2])):
+                Ii, Ei = rule.combine(a, b, np.array([f(x) for x in rule.nodes(a, b)]))
+                new.append((float(Ei), a, b, Ii[()]))
+            I = (I - s[3]) + new[0][3] + new[1][3]
+            E = (E - s[0]) + new[0][0] + new[1][0]
+            ne += 2 * rule.K
+            iai.heappush(heap, new[0])
+            iai.heappush(heap, new[1])
+        I = heap[0][3]
+        for s in heap[1:]:
+            I = I + s[3]
+        return I
+
+    def level(l, lims_, outer, atol_):
+        rule = iai.GKRule(orders[l])
+        segs = tuple(lims_.segments())
+        if l == 0:
+            def f(x):
+                count[0] += 1
+                return point_value((float(x),) + outer)
+        else:
+            def f(x):
+                cl = lims_.fix(float(x))
+                cs = tuple(cl.segments())
+                return level(l - 1, cl, (float(x),) + outer, atol_ / (cs[-1] - cs[0]))
+        return quadgk(f, segs, rule, atol_)
+
+    return level(len(orders) - 1, lims, (), atol), count[0]
+
+
+@pytest.mark.parametrize("ndim,orders", [(1, (10,)), (2, (4, 9)), (3, (5, 7, 3)), (3, (7, 7, 7))])
+def test_per_level_gauss_kronrod_orders(orc, ndim, orders):
+    """IAI(algs...) with a different AuxQuadGKJL order per variable (src/brillouin.jl:368-377, src/algorithms.jl:462-463: algs[dim]
+    belongs to variable dim, the innermost is algs[1]): same evaluation count and value as the sequential recursion"""
+    n = 2
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 1, cubic=True)
+    H = np.asfortranarray(H[(slice(None),) * (2 + ndim) + (1,) * (3 - ndim)])
+    fs = ab.FourierSeries(H, period=1.0, lo=lo[:ndim], norb=n)
+    S = orc.Series(np.asfortranarray(H.reshape(H.shape + (1,) * (3 - ndim))), tuple(lo[:ndim]) + (0,) * (3 - ndim))
+    z = complex(0.3, 3.0)
+    bz = ab.load_bz(ab.InversionSymIBZ(ndim), np.eye(ndim))
+    mult = abs(np.linalg.det(bz.B)) * bz.nsyms
+    atol = 2e-3
+
+    def point_value(k):
+        Hk = orc.eval_points(S, np.array([tuple(k) + (0.0,) * (3 - ndim)]))[:, :, 0]
+        return np.trace(np.linalg.inv(z * np.eye(n) - Hk))
+
+    Iref, nref = _nested_quadgk_sequential(point_value, bz.lims, orders, atol, 0.0, 10 ** 7)
+    alg = ab.IAI(*[ab.AuxQuadGKJL(order=o) for o in orders])
+    sol = ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=z.imag), bz, {"omega": z.real}), ab.EvalCounter(alg),
+                   abstol=atol * mult, backend=OracleBackend())
+    assert sol.numevals == nref
+    assert abs(sol.u - mult * Iref) <= 1e-12 * abs(sol.u)
+    with pytest.raises(ValueError):
+        ab.solve(ab.IntegralProblem(ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=1.0), bz, {"omega": 0.0}),
+                 ab.IAI(ab.AuxQuadGKJL(), ab.AuxQuadGKJL(), ab.AuxQuadGKJL(), ab.AuxQuadGKJL()), abstol=1.0, backend=OracleBackend())
