@@ -129,7 +129,7 @@ struct abz_ctx {
     int resolvent_algo = 0;
     size_t budget = (size_t)4096 << 20;
     int fused_small = 1;
-    int eig_algo = 0;             // 0: tridiagonalisation + QL, 1: two-sided Jacobi
+    int eig_algo = 0;             // 0: tridiagonalisation + QL / bisection, 1: two-sided Jacobi, 2: shared-memory tridiagonalisation, 3 / 4: force QL / bisection
     int iai_lanes_opt = 4;        // IAI rounds in flight (ABZ_OPT_IAI_LANES)
     int leaf_spill = LEAF_SPILL;  // segments per device-side innermost integral beyond the 63 kept in shared memory
     bool force_generic = false;   // set while re-running a call whose fast path asked for pivoting
@@ -1373,12 +1373,38 @@ static int run_eig_jacobi(abz_ctx* ctx, const double2* H, const double* wnode, l
     return ABZ_OK;
 }
 
+// Stage B choice (profiles/r02_eig_stage_b_timing.log, one B200): the warp-per-matrix bisection kernel wins while the batch leaves the
+// thread-per-matrix QL kernel latency-bound - up to ~5 k matrices at n = 16, ~12 k at n = 32, ~16 k at n = 48, every measured batch
+// (67 k) at n = 64.  ABZ_EIG_BISECT_MAX overrides the batch limit (0 = never bisect).
+static bool eig_use_bisect(const abz_ctx* ctx, long nk, int n) {
+    static const long lim = [] { const char* e = getenv("ABZ_EIG_BISECT_MAX"); return e ? atol(e) : -1L; }();
+    if (ctx->eig_algo == 3 || n > EIG_MAXN) return false;        // ABZ_OPT_EIG_ALGO 3: always QL, 4: always bisection
+    if (ctx->eig_algo == 4) return true;
+    if (n < 12) return false;
+    const long t = lim >= 0 ? lim : (n < 24 ? 5000L : n < 40 ? 12000L : n < 56 ? 16000L : 150000L);
+    return nk <= t;
+}
+
 // eigenvalues of nk materialised matrices: Householder tridiagonalisation (CTA per matrix) + implicit QL (thread per matrix)
 static int run_eig(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int n, int mode, int kind, double p0, double p1,
                    double* evals, double* acc) {
     if (nk <= 0) return ABZ_OK;
     if (ctx->eig_algo == 1 || n > EIG_MAXN) return run_eig_jacobi(ctx, H, wnode, nk, n, mode == 2 ? 1 : mode, kind, p0, p1, evals, acc);
     { int rct = launch_tridiag(ctx, H, nk, n); if (rct) return rct; }
+    // stage B: a warp per matrix (Sturm bisection) while the batch is small enough that the thread-per-matrix QL kernel would be bound by
+    // the latency of one thread (1.6 ms at n = 64 whatever the batch); QL for large batches, where its lower operation count wins
+    if (eig_use_bisect(ctx, nk, n)) {
+        const long nb = (nk + BIS_WARPS - 1) / BIS_WARPS;
+        if (mode == 0) CU(ctx, ctx->partial.reserve((size_t)nb * sizeof(double)));
+        eig_bisect_kernel<<<(unsigned)nb, BIS_WARPS * 32, 0, ctx->stream>>>(ctx->eig_d.as<double>(), ctx->eig_e.as<double>(), wnode, nk, n, mode, kind,
+                                                                          p0, p1, evals, ctx->partial.as<double>(), ctx->errflag.as<int>());
+        LAUNCH_CHECK(ctx, "eig_bisect_kernel");
+        if (mode == 0) {
+            reduce_real_kernel<<<1, 256, 0, ctx->stream>>>(ctx->partial.as<double>(), nb, 1.0, acc);
+            LAUNCH_CHECK(ctx, "reduce_real_kernel");
+        }
+        return ABZ_OK;
+    }
     const long nblk = (nk + 31) / 32;
     if (mode == 0) CU(ctx, ctx->partial.reserve((size_t)nblk * sizeof(double)));
     eig_tql_kernel<<<(unsigned)nblk, 32, (size_t)2 * n * 32 * sizeof(double), ctx->stream>>>(ctx->eig_d.as<double>(), ctx->eig_e.as<double>(), wnode, nk, n, mode, kind, p0,

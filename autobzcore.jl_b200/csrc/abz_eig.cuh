@@ -801,6 +801,124 @@ eig_tql_kernel(const double* __restrict__ din, const double* __restrict__ ein, c
 #undef TQL_D
 #undef TQL_E
 
+// Stage B (small and medium batches): eigenvalues of the real symmetric tridiagonal (d, e) by Sturm-count bisection, one WARP per
+// matrix, lane l owns the eigenvalues of index l and l + 32 (ascending).  The QL kernel above is one thread per matrix: whatever the
+// batch, a launch lasts as long as one thread needs for its ~3 500 dependent rotations (1.6 ms at n = 64), and the lanes of a warp
+// diverge in their sweep bounds.  Here all 64 eigenvalues of a matrix are refined at the same time and every lane runs the same
+// instruction stream.  Count: the number of eigenvalues below x is the number of sign changes in p_0 = 1, p_k = det(T_k - x),
+// p_k = (d_k - x) p_{k-1} - e_{k-1}^2 p_{k-2} (three FP64 instructions per row, no division); the matrix is first scaled by an exact
+// power of two to the Gershgorin radius so that |p| grows by at most 5x per row, and both running values are rescaled by 2^+-512 every 16
+// rows.  BIS_ITERS halvings of [-R, R]: final interval 2^-49 R.  mode as in eig_tql_kernel (mode 2 = mode 1: the output is sorted
+// by construction); partial[blockIdx.x] = sum over the block's BIS_WARPS matrices in warp order (fixed order).
+constexpr int BIS_WARPS = 8, BIS_ITERS = 50;
+__device__ __forceinline__ void bisect_rescale(double& p, double& pm) {
+    const int e = max(__double2hiint(p) & 0x7ff00000, __double2hiint(pm) & 0x7ff00000);
+    if (e > 0x5ff00000 || e < 0x1ff00000) {
+        const double s = (e > 0x5ff00000) ? 7.458340731200207e-155 : 1.3407807929942597e154;      // 2^-512 : 2^512
+        p *= s; pm *= s;
+    }
+}
+// rows [r0, r1) of the Sturm recurrence for two shifts at once; the sign of every p_r is shifted into h0 / h1 (one SHF per row
+// and shift: the sign changes are counted from the two history words afterwards, off the FP64 pipe)
+__device__ __forceinline__ void bisect_rows(const double2* __restrict__ de, int r0, int r1, double x0, double x1, double& pa, double& pm0,
+                                            double& pb, double& pm1, unsigned& h0, unsigned& h1) {
+#pragma unroll 8
+    for (int r = r0; r < r1; r++) {
+        const double2 v = de[r];                                  // (d_r, e_{r-1}^2): one 128-bit broadcast load
+        const double ta = fma(v.x - x0, pa, -(v.y * pm0)), tb = fma(v.x - x1, pb, -(v.y * pm1));
+        h0 = __funnelshift_l((unsigned)__double2hiint(ta), h0, 1);
+        h1 = __funnelshift_l((unsigned)__double2hiint(tb), h1, 1);
+        pm0 = pa; pa = ta; pm1 = pb; pb = tb;
+        if ((r & 15) == 15) { bisect_rescale(pa, pm0); bisect_rescale(pb, pm1); }
+    }
+}
+__global__ void __launch_bounds__(BIS_WARPS * 32)
+eig_bisect_kernel(const double* __restrict__ din, const double* __restrict__ ein, const double* __restrict__ wnode, long nk, int n,
+                  int mode, int kind, double prm0, double prm1, double* __restrict__ evals, double* __restrict__ partial,
+                  int* __restrict__ errflag) {
+    __shared__ double2 sde[BIS_WARPS][EIG_MAXN + 1];
+    __shared__ double red[BIS_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long k = (long)blockIdx.x * BIS_WARPS + warp;
+    double val = 0.0;
+    if (k < nk) {
+        const int i0 = lane, i1 = lane + 32;
+        const double d0 = (i0 < n) ? din[(long)i0 * nk + k] : 0.0, d1 = (i1 < n) ? din[(long)i1 * nk + k] : 0.0;
+        const double e0 = (i0 < n - 1) ? ein[(long)i0 * nk + k] : 0.0, e1 = (i1 < n - 1) ? ein[(long)i1 * nk + k] : 0.0;   // e_i couples i, i+1
+        const bool bad = !(isfinite(d0) && isfinite(d1) && isfinite(e0) && isfinite(e1));
+        if (__any_sync(0xffffffffu, bad)) {
+            if (lane == 0) *errflag = 1;
+        } else {
+            // Gershgorin interval
+            const double a0 = fabs(e0), a1 = fabs(e1);
+            double up0 = __shfl_up_sync(0xffffffffu, a0, 1), up1 = __shfl_up_sync(0xffffffffu, a1, 1);
+            const double a0last = __shfl_sync(0xffffffffu, a0, 31);
+            if (lane == 0) { up0 = 0.0; up1 = a0last; }
+            double glo = (i0 < n) ? d0 - (a0 + up0) : 1e300, ghi = (i0 < n) ? d0 + (a0 + up0) : -1e300;
+            if (i1 < n) { glo = fmin(glo, d1 - (a1 + up1)); ghi = fmax(ghi, d1 + (a1 + up1)); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                glo = fmin(glo, __shfl_xor_sync(0xffffffffu, glo, o));
+                ghi = fmax(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
+            }
+            const double R = fmax(fabs(glo), fabs(ghi));
+            double ev0 = 0.0, ev1 = 0.0;
+            if (R > 0.0) {
+                int ex;
+                (void)frexp(R, &ex);                                   // R = m 2^ex, m in [0.5, 1)
+                ex = max(-1000, min(1000, ex));
+                const double sc = ldexp(1.0, -ex), isc = ldexp(1.0, ex);
+                const double s0 = e0 * sc, s1 = e1 * sc;
+                double2* de = sde[warp];
+                de[i0].x = d0 * sc; de[i1].x = d1 * sc;
+                if (lane == 0) de[0].y = 0.0;
+                de[i0 + 1].y = s0 * s0;
+                de[i1 + 1].y = s1 * s1;                               // row 64 is padding
+                __syncwarp();
+                const int na = min(n, 32), nb = n - na;
+                double lo0 = -1.0, hi0 = 1.0, lo1 = -1.0, hi1 = 1.0;
+                for (int it = 0; it < BIS_ITERS; it++) {
+                    const double x0 = 0.5 * (lo0 + hi0), x1 = 0.5 * (lo1 + hi1);
+                    double pa = 1.0, pm0 = 0.0, pb = 1.0, pm1 = 0.0;        // p_{-1} = 1; e_{-1}^2 = 0 makes p_0 = d_0 - x
+                    unsigned A0 = 0u, A1 = 0u, B0 = 0u, B1 = 0u;
+                    bisect_rows(de, 0, na, x0, x1, pa, pm0, pb, pm1, A0, A1);
+                    // word A: s_0 at bit na-1 ... s_{na-1} at bit 0, zeros (= the sign of p_{-1}) above: changes = popc(A ^ (A >> 1))
+                    int c0 = __popc(A0 ^ (A0 >> 1)), c1 = __popc(A1 ^ (A1 >> 1));
+                    if (nb > 0) {
+                        bisect_rows(de, 32, n, x0, x1, pa, pm0, pb, pm1, B0, B1);
+                        // word B: s_32 at bit nb-1 ...; its predecessor s_31 is bit 0 of A
+                        c0 += __popc(B0 ^ ((B0 >> 1) | ((A0 & 1u) << (nb - 1))));
+                        c1 += __popc(B1 ^ ((B1 >> 1) | ((A1 & 1u) << (nb - 1))));
+                    }
+                    if (c0 > i0) hi0 = x0; else lo0 = x0;
+                    if (c1 > i1) hi1 = x1; else lo1 = x1;
+                }
+                ev0 = 0.5 * (lo0 + hi0) * isc; ev1 = 0.5 * (lo1 + hi1) * isc;
+                __syncwarp();
+            }
+            if (mode != 0) {
+                if (i0 < n) evals[k * n + i0] = ev0;
+                if (i1 < n) evals[k * n + i1] = ev1;
+            } else {
+                double v = (i0 < n) ? eig_kernel_value(ev0, kind, prm0, prm1) : 0.0;
+                if (i1 < n) v += eig_kernel_value(ev1, kind, prm0, prm1);
+                v = warp_sum(v);
+                val = (wnode ? wnode[k] : 1.0) * v;
+            }
+        }
+    }
+    if (mode == 0) {
+        if (lane == 0) red[warp] = val;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < BIS_WARPS; w++) t += red[w];
+            partial[blockIdx.x] = t;
+        }
+    }
+}
+
 // ---- K3-sweep: tr[(z_w - H(k))^-1] for MANY frequencies from ONE tridiagonalisation per k --------------------------
 // For Hermitian H(k) and a scalar self-energy (folded into z) the trace of the resolvent is invariant under the
 // unitary reduction T = Q^H H Q of eig_tridiag_kernel, and for the real symmetric tridiagonal T (diagonal d, off-diagonal

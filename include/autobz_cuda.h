@@ -64,8 +64,11 @@ typedef uint64_t abz_nest_t;    /* IAI arena: contracted series for nested panel
 #define ABZ_OPT_IAI_LANES 6        /* IAI rounds in flight in single-rank solves with norb <= 3 (default 4; 1 = one round at a time);
                                     * results and numevals do not depend on it */
 #define ABZ_OPT_EIG_ALGO 4         /* 0 (default): Householder tridiagonalisation (warp-per-matrix in registers for norb <= 32,
-                                    * CTA-per-matrix in registers for 33..64) + implicit QL; 1: cyclic two-sided Jacobi;
-                                    * 2: as 0 but always the shared-memory tridiagonalisation (cross-check) */
+                                    * CTA-per-matrix in registers for 33..64) followed by the eigenvalues of the tridiagonal: implicit QL
+                                    * of the tridiagonal matrix for large batches, Sturm-count bisection (one warp per matrix) for batches
+                                    * that would leave the thread-per-matrix QL kernel latency-bound; 1: cyclic two-sided Jacobi;
+                                    * 2: as 0 but always the shared-memory tridiagonalisation (cross-check);
+                                    * 3 / 4: as 0 but always QL / always bisection */
 
 int32_t abz_version(void);
 const char* abz_last_error(const abz_ctx* ctx);  /* ctx may be NULL: last error of abz_ctx_create */

@@ -247,3 +247,58 @@ def test_dmma_team_resolvent_falls_back_to_pivoting(ctx, orc, n):
     R = L.DeviceRule(ctx, S, 4)
     assert rel(R.resolvent_sum(z, scale=1 / 64), orc.ptr_sum(So, 4, z)) < 1e-10
     R.close(); S.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 16, 17, 31, 32, 33, 40, 63, 64])
+def test_eigenvalues_stage_b_ql_and_bisection_vs_lapack(ctx, n):
+    """Stage B of the eigenvalue path (eigen(Hermitian(H(k))), src/dos_ggr.jl:19,34): the thread-per-matrix QL kernel (ABZ_OPT_EIG_ALGO 3)
+    and the warp-per-matrix Sturm bisection kernel (4) against LAPACK, sorted output, and the band sums of both against numpy;
+    includes sizes that leave lanes without an eigenvalue and degenerate spectra (cubic symmetry at the zone centre)"""
+    from autobz_b200 import _lib as L
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 1, cubic=True)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    R = L.DeviceRule(ctx, S, 5)
+    Hk, _, _ = R.copy_out()
+    ref = np.linalg.eigvalsh(np.moveaxis(Hk, 2, 0))
+    rad = np.max(np.abs(ref))
+    out = {}
+    try:
+        for algo in (3, 4):
+            ctx.set_option(L.OPT_EIG_ALGO, algo)
+            ev = R.eigvals()
+            assert np.max(np.abs(ev - ref)) <= 1e-13 * rad, (algo, np.max(np.abs(ev - ref)) / rad)
+            assert np.all(np.diff(ev, axis=1) >= 0)
+            out[algo] = [R.eig_sum(0, (0.0, 1.0), scale=1.0), R.eig_sum(1, (0.1 * rad, 0.05 * rad), scale=1.0),
+                         R.eig_sum(3, (0.0, 0.1 * rad), scale=1.0)]
+    finally:
+        ctx.set_option(L.OPT_EIG_ALGO, 0)
+    f = lambda x: 1.0 / (1.0 + np.exp(x))
+    exact = [ref.sum(), (ref * f((ref - 0.1 * rad) / (0.05 * rad))).sum(), (np.exp(-(ref / (0.1 * rad)) ** 2) / (0.1 * rad * np.sqrt(np.pi))).sum()]
+    for algo in (3, 4):
+        for got, want in zip(out[algo], exact):
+            assert abs(got - want) <= 1e-11 * max(abs(want), rad), (algo, got, want)
+
+
+def test_bisection_handles_decoupled_and_scaled_matrices(ctx):
+    """diagonal H (every off-diagonal exactly zero), a zero matrix, and spectra scaled by 1e-150 / 1e+150: the power-of-two scaling
+    and the periodic rescaling of the Sturm recurrence keep the counts exact"""
+    from autobz_b200 import _lib as L
+    n = 48
+    rng = np.random.default_rng(5)
+    try:
+        ctx.set_option(L.OPT_EIG_ALGO, 4)
+        for scale in (1.0, 1e-150, 1e150, 0.0):
+            H = np.zeros((n, n, 3, 3, 3), dtype=np.complex128, order="F")
+            dvals = rng.normal(size=n)
+            H[:, :, 1, 1, 1] = np.diag(dvals) * scale
+            if scale == 1.0:                     # a second case with weak coupling between nearly equal diagonal entries
+                A = 1e-9 * (rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n)))
+                H[:, :, 1, 1, 1] += A + A.conj().T
+            S = L.DeviceSeries(ctx, H, (-1, -1, -1), (1.0,) * 3)
+            R = L.DeviceRule(ctx, S, 2)
+            ev = R.eigvals()
+            ref = np.linalg.eigvalsh(H[:, :, 1, 1, 1])
+            assert np.max(np.abs(ev - ref[None])) <= 1e-13 * max(np.max(np.abs(ref)), 1e-300)
+            R.close(); S.close()
+    finally:
+        ctx.set_option(L.OPT_EIG_ALGO, 0)

@@ -8,7 +8,7 @@ from autobz_b200 import _lib as L
 
 ctx = ab.default_context(0)
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-which = sys.argv[1:] or ["contract", "small", "eig", "iai", "sweep", "ggr", "matrix"]
+which = sys.argv[1:] or ["contract", "small", "eig", "iai", "sweep", "ggr", "matrix", "team", "mid"]
 d = np.load(os.path.join(ROOT, "tests", "golden", "svo_hr.npz"))
 Hs, los, A = np.asfortranarray(d["H_R"]), tuple(int(x) for x in d["lo"]), d["A"]
 
@@ -76,3 +76,22 @@ if "matrix" in which:
     z = np.linspace(-1.0, 1.0, 8) + 0.05j
     print("matrix", R.resolvent_matrix_sum(z)[0, 0, :2], ctx.last_timings())
     R.close(); S.close()
+
+if "team" in which:
+    # norb 64 resolvent traces: the four-warp DMMA block-LU team kernel (32 < norb <= 64), 32^3 grid x 8 frequencies
+    H, lo = ab.synthetic.wannier_hamiltonian(64, 2)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    R = L.DeviceRule(ctx, S, 32)
+    R.materialize()
+    ext = ab.synthetic.band_extent(H)
+    z = np.linspace(-0.2 * ext, 0.2 * ext, 8) + 1j * 0.01 * ext
+    print("team", R.resolvent_sum(z)[:2], ctx.last_timings())
+    R.close(); S.close()
+
+if "mid" in which:
+    # C3 (SrVO3 DOS by IAI on the cubic IBZ, eta = 1e-3): device-side middle integrals (iai_mid_kernel, one 2-CTA cluster per task)
+    fs = ab.FourierSeries(Hs, period=1.0, lo=los, norb=3)
+    ibz = ab.load_bz(ab.CubicSymIBZ(), A)
+    f = ab.FourierIntegrand(ab.dos_integrand, fs, 1e-3)
+    sol = ab.solve(ab.IntegralProblem(f, ibz, 12.0), ab.EvalCounter(ab.IAI()), abstol=1e-3)
+    print("mid", sol.u, sol.numevals)
