@@ -16,7 +16,7 @@ ABZ_E_INVALID, ABZ_E_OOM, ABZ_E_CUDA, ABZ_E_SINGULAR, ABZ_E_UNSUPPORTED, ABZ_E_N
 F_RESOLVENT_TRACE, F_TRACE_H = 0, 1
 EIG_SUM, EIG_FERMI_ENERGY, EIG_FERMI_COUNT, EIG_GAUSS_DOS = 0, 1, 2, 3
 OPT_RESOLVENT_ALGO, OPT_MEM_BUDGET_MB, OPT_FUSED_SMALL, OPT_EIG_ALGO, OPT_IAI_LEAF_SPILL, OPT_IAI_LANES = 1, 2, 3, 4, 5, 6
-IAI_DEVICE_LEAVES, IAI_DEVICE_MIDDLES = 1, 2
+IAI_DEVICE_LEAVES, IAI_DEVICE_MIDDLES, IAI_SPECULATE = 1, 2, 4
 
 # every symbol include/autobz_cuda.h declares (tests check that the library exports all of them)
 EXPORTS = [
@@ -429,7 +429,7 @@ class DeviceNest:
         return H
 
     def iai_solve(self, lkind, la, lb, fkind, vkind, z, sigma, lin, atol, rtol, maxevals, device_leaves=True, rank=0, nranks=1,
-                  allreduce=None, limits=None, device_middles=True):
+                  allreduce=None, limits=None, device_middles=True, speculate=True):
         """abz_iai_solve(_sharded): the whole nested adaptive solve with the control flow on the library's host side.
         nranks > 1: outermost panel nodes dealt round-robin to the ranks; `allreduce(np.ndarray) -> np.ndarray` sums over
         the ranks (None = NCCL on the ctx communicator).  Returns (I complex, E, numevals, rounds, launches)."""
@@ -456,7 +456,7 @@ class DeviceNest:
                 return -1
 
         xfn = EXCHANGE_FN(_xchg) if (nranks > 1 and allreduce is not None) else EXCHANGE_FN(0)
-        flags = (IAI_DEVICE_LEAVES | (IAI_DEVICE_MIDDLES if device_middles else 0)) if device_leaves else 0
+        flags = (IAI_DEVICE_LEAVES | (IAI_DEVICE_MIDDLES if device_middles else 0) | (IAI_SPECULATE if speculate else 0)) if device_leaves else 0
         if limits is not None:
             # general iterated limits (abz_iai_solve_general): `limits` has .ndim, .segments() -> breakpoints and .fix(x) -> inner limits
             # (segments / fixandeliminate of the reference's AbstractIteratedLimits); the library asks for the breakpoints of one level

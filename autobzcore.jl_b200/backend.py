@@ -136,12 +136,14 @@ class DeviceBackend:
     """iai_engine: "native" (default) runs IAI's adaptive control flow in the library's C++ host engine
     (abz_iai_solve, one call per solve); "python" drives abz_nest_* round by round from iai.NestedGK.
     iai_device_leaves: run each innermost 1-D adaptive integral entirely on the device (norb <= 3);
-    iai_device_middles: in 3-d solves also each middle integral (one CTA per node of the outermost panels)."""
+    iai_device_middles: in 3-d solves also each middle integral (one CTA per node of the outermost panels).
+    iai_speculate: look-ahead on the outermost integral (two bisections per device round; same decisions and numevals)."""
 
-    def __init__(self, device=None, ctx=None, iai_engine="native", iai_device_leaves=True, iai_device_middles=True):
+    def __init__(self, device=None, ctx=None, iai_engine="native", iai_device_leaves=True, iai_device_middles=True, iai_speculate=True):
         self.ctx = ctx if ctx is not None else default_context(device)
         self.iai_engine, self.iai_device_leaves = iai_engine, iai_device_leaves
         self.iai_device_middles = iai_device_middles      # 3-d solves: whole middle integrals on the device too (abz_iai.cuh)
+        self.iai_speculate = iai_speculate
         self._wsym_cache = {}
 
     def symptr_rule(self, npt, syms):

@@ -2307,6 +2307,23 @@ static int32_t iai_solve_impl(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
         rc = be.init_lanes((s->n <= 3 && nst->ndim >= 2 && nranks == 1) ? want : 1);   // sharded solves keep one round at a time
         if (rc) return rc;
     }
+    int64_t rounds0 = 0;
+    if ((flags & ABZ_IAI_SPECULATE) && leaf && lkind != 2) {
+        // look-ahead on the outermost integral (abz_iai_engine.hpp): same decisions, fewer rounds.  A failure of this attempt may have
+        // come from a panel the sequential algorithm never reaches, so it is not reported: the plain engine below decides.
+        abz_iai::Engine<IaiDeviceBackend> eng0(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, leaf, rank, nranks, mid, true);
+        rc = eng0.run();
+        ctx->force_generic = false;
+        if (rc == 0) {
+            if (stats) { stats[0] = eng0.numevals; stats[1] = eng0.rounds; stats[2] = ctx->launches - launches0; stats[3] = eng0.exchanges; }
+            out[0] = eng0.result.re; out[1] = eng0.result.im; out[2] = eng0.result_err;
+            return ABZ_OK;
+        }
+        cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        be.heap_overflow = false;
+        rounds0 = eng0.rounds;
+    }
     abz_iai::Engine<IaiDeviceBackend> eng(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, leaf, rank, nranks, mid);
     rc = eng.run();
     ctx->force_generic = false;
@@ -2323,7 +2340,7 @@ static int32_t iai_solve_impl(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
         rc = eng2.run();
         ctx->force_generic = false;
         if (rc && be.nlanes > 1) { cudaMemsetAsync(ctx->errflag.p, 0, sizeof(int), ctx->stream); cudaStreamSynchronize(ctx->stream); }
-        if (stats) { stats[0] = eng2.numevals; stats[1] = eng.rounds + eng2.rounds; stats[2] = ctx->launches - launches0; stats[3] = 0; }
+        if (stats) { stats[0] = eng2.numevals; stats[1] = rounds0 + eng.rounds + eng2.rounds; stats[2] = ctx->launches - launches0; stats[3] = 0; }
         if (rc == abz_iai::IAI_E_NAN) return fail(ctx, ABZ_E_SINGULAR, eng2.error);
         if (rc == abz_iai::IAI_E_ARENA) return fail(ctx, ABZ_E_OOM, eng2.error);
         if (rc == abz_iai::IAI_E_STALL || rc == abz_iai::IAI_E_LIMITS) return fail(ctx, ABZ_E_INVALID, eng2.error);
@@ -2331,7 +2348,7 @@ static int32_t iai_solve_impl(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
         out[0] = eng2.result.re; out[1] = eng2.result.im; out[2] = eng2.result_err;
         return ABZ_OK;
     }
-    if (stats) { stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = ctx->launches - launches0; stats[3] = eng.exchanges; }
+    if (stats) { stats[0] = eng.numevals; stats[1] = rounds0 + eng.rounds; stats[2] = ctx->launches - launches0; stats[3] = eng.exchanges; }
     if (rc == abz_iai::IAI_E_NAN) return fail(ctx, ABZ_E_SINGULAR, eng.error);
     if (rc == abz_iai::IAI_E_ARENA) return fail(ctx, ABZ_E_OOM, eng.error);
     if (rc == abz_iai::IAI_E_STALL || rc == abz_iai::IAI_E_LIMITS) return fail(ctx, ABZ_E_INVALID, eng.error);

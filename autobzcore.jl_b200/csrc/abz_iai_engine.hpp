@@ -19,6 +19,14 @@
 // With leaf_tasks = true the innermost (level-0) integrals are not run by this state machine: each is
 // handed to the backend as ONE task (slot, a, b, atol) that returns (I, E, numevals) - the device runs
 // the whole 1-D adaptive loop with one warp per task (abz_iai.cuh, iai_leaf_kernel).
+//
+// Look-ahead on the outermost integral (speculate = true, children of the outermost panels handed to the backend as whole
+// tasks): QuadGK refines one panel at a time, so a round would carry the 2 x 15 tasks of ONE bisection and the device would idle between
+// rounds.  When the outermost integral bisects its worst panel, the engine also starts the bisection of the panel that is next in its
+// heap and parks the two results in a cache keyed by (a, b).  When QuadGK's own order reaches that panel the halves are taken from the
+// cache (or claimed while still in flight) instead of being evaluated; what is never reached is dropped and its evaluations are not
+// counted.  Every accept / refine decision is taken on exactly the values and in exactly the order of the sequential algorithm, so the
+// integral, the error estimate and numevals are unchanged - only the number of rounds drops (up to 2x).
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -241,10 +249,14 @@ public:
     // mid_tasks: in 3-d solves over CubicLimits / TetrahedralLimits the middle integrals (one per node of the outermost panels) are
     // handed to the backend whole as well (abz_iai.cuh, iai_mid_kernel): a round is then one refinement step of the OUTERMOST integral
     Engine(Backend& be, int ndim, const Limits& lims, double atol, double rtol, int64_t maxevals, int64_t cap2,
-           int64_t cap1, bool leaf_tasks, int rank = 0, int nranks = 1, bool mid_tasks = false)
+           int64_t cap1, bool leaf_tasks, int rank = 0, int nranks = 1, bool mid_tasks = false, bool speculate = false)
         : be_(be), ndim_(ndim), lims_(lims), atol_(atol), rtol_(rtol), maxevals_(maxevals),
           leaf_tasks_(leaf_tasks && ndim >= 2), mid_tasks_(mid_tasks && leaf_tasks && ndim == 3 && lims.kind != 2),
           rank_(rank), nranks_(ndim >= 2 ? nranks : 1) {
+        // look-ahead needs every child of an outermost panel to be one backend task (so that its evaluations can be kept apart)
+        // (several ranks: look-ahead panels are shared panels like the regular ones - their node values meet in the same allreduce, every
+        // rank parks / claims / drops them identically, and a failure on one rank reaches all of them through that exchange)
+        spec_on_ = speculate && lims.kind != 2 && ((ndim == 3 && mid_tasks_) || (ndim == 2 && leaf_tasks_));
         for (int64_t i = cap2 - 1; i >= 0; i--) free2_.push_back(i);
         for (int64_t i = cap1 - 1; i >= 0; i--) free1_.push_back(i);
         L_ = be.lanes() < 1 ? 1 : be.lanes();
@@ -254,6 +266,7 @@ public:
     }
 
     int64_t numevals = 0, rounds = 0, exchanges = 0;   // numevals: all ranks' evaluations once the solve has finished
+    int64_t spec_started = 0, spec_used = 0;           // look-ahead: half-panels started ahead of QuadGK's order / later consumed
     cplx result{0, 0};
     double result_err = 0;
     std::string error;
@@ -301,18 +314,11 @@ public:
                 double E = std::hypot(D.re, D.im);
                 rc = segment_done(segs[i].q, segs[i].pend, R.seg_I[i], E);
             }
-            for (size_t i = 0; i < tasks.size() && !rc; i++) {
-                numevals += R.task_ne[i];
-                double E = R.task_E[i];
-                if (!std::isfinite(E)) rc = nan_error(pends_[tasks[i].pend]);
-                else rc = child_done(tasks[i].q, tasks[i].pend, tasks[i].i, tasks[i].slot, R.task_I[i]);
-            }
+            for (size_t i = 0; i < tasks.size() && !rc; i++)
+                rc = task_done(tasks[i], R.task_I[i], R.task_E[i], R.task_ne[i]);
             const std::vector<Item>& mids = fl_mid_[g];
-            for (size_t i = 0; i < mids.size() && !rc; i++) {
-                numevals += R.mid_ne[i];
-                if (!std::isfinite(R.mid_E[i])) rc = nan_error(pends_[mids[i].pend]);
-                else rc = child_done(mids[i].q, mids[i].pend, mids[i].i, mids[i].slot, R.mid_I[i]);
-            }
+            for (size_t i = 0; i < mids.size() && !rc; i++)
+                rc = task_done(mids[i], R.mid_I[i], R.mid_E[i], R.mid_ne[i]);
             if (rc) local_rc = rc;
         }
         drain();
@@ -326,7 +332,9 @@ public:
     }
 
 private:
-    struct Pend { double a, b; cplx vals[15]; int remaining, tag; bool shared; };
+    struct Pend { double a, b; cplx vals[15]; int remaining, tag; bool shared; int spec; };   // spec: look-ahead cache entry or -1
+    // a half-panel of the outermost integral evaluated ahead of QuadGK's order
+    struct Spec { double a, b; bool live, done, bad; int claim_tag; Seg seg; int64_t ne; };
     struct Integral {
         int level; Limits lims; double atol; int64_t slot; int pq, ppend, pi;   // parent integral / panel / node
         int lane;                                                              // the lane its rounds run in
@@ -348,6 +356,8 @@ private:
     std::vector<char> inflight_;
     std::deque<int> fifo_;                                               // lanes in flight, oldest first
     bool done_ = false;
+    bool spec_on_ = false;
+    std::vector<Spec> spec_;
 
     // complete (and discard) whatever is still in flight: the backend's buffers must be quiescent before we return
     void drain() {
@@ -368,7 +378,7 @@ private:
         if (!free_pend_.empty()) { id = free_pend_.back(); free_pend_.pop_back(); }
         else { id = (int)pends_.size(); pends_.emplace_back(); }
         Pend& p = pends_[id];
-        p.a = a; p.b = b; p.tag = tag; p.remaining = 15; p.shared = false;
+        p.a = a; p.b = b; p.tag = tag; p.remaining = 15; p.shared = false; p.spec = -1;
         for (int i = 0; i < 15; i++) p.vals[i] = cplx{0.0, 0.0};
         return id;
     }
@@ -383,6 +393,28 @@ private:
         error = "IAI: the limits callback failed (it must return at least 2 ascending breakpoints, at most 64)";
         return IAI_E_LIMITS;
     }
+    // a whole-integral task of the backend finished: (I, E, evaluations).  Evaluations of a look-ahead panel stay with its cache entry.
+    int task_done(const Item& it, cplx I, double E, int64_t ne) {
+        const int sp = pends_[it.pend].spec;
+        if (sp >= 0) spec_[sp].ne += ne; else numevals += ne;
+        if (!std::isfinite(E)) {
+            if (sp < 0) return nan_error(pends_[it.pend]);
+            spec_[sp].bad = true;                     // reported only if QuadGK's own order reaches this panel
+        }
+        return child_done(it.q, it.pend, it.i, it.slot, I);
+    }
+    int find_spec(double a, double b) const {
+        for (size_t k = 0; k < spec_.size(); k++) if (spec_[k].live && spec_[k].a == a && spec_[k].b == b) return (int)k;
+        return -1;
+    }
+    int new_spec(double a, double b) {
+        size_t k = 0;
+        while (k < spec_.size() && spec_[k].live) k++;
+        if (k == spec_.size()) spec_.emplace_back();
+        spec_[k] = Spec{a, b, true, false, false, 0, Seg{0.0, a, b, cplx{0.0, 0.0}}, 0};
+        return (int)k;
+    }
+
     // do_quadgk's first pass: evalrule on every initial segment [segs[k], segs[k+1]]; panel k carries tag -k
     int start_initial(int qi, const std::vector<double>& segs) {
         const int ns = (int)segs.size() - 1;
@@ -400,8 +432,9 @@ private:
     }
 
     // evalrule on [a, b] of integral q: innermost -> queue the panel; outer -> spawn 15 child integrals
-    int start_segment(int qi, double a, double b, int tag) {
+    int start_segment(int qi, double a, double b, int tag, int spec = -1) {
         int pend = new_pend(a, b, tag);
+        pends_[pend].spec = spec;
         const int level = ints_[qi].level;
         if (level == 0) {
             const int g = ints_[qi].lane;
@@ -502,17 +535,64 @@ private:
         q.popped = s;
         const double mid = (s.a + s.b) / 2;
         q.has1 = q.has2 = false;
-        int rc = start_segment(qi, s.a, mid, 1);
-        if (rc) return rc;
-        return start_segment(qi, mid, s.b, 2);
+        if (!(spec_on_ && q.pq < 0)) {
+            int rc = start_segment(qi, s.a, mid, 1);
+            if (rc) return rc;
+            return start_segment(qi, mid, s.b, 2);
+        }
+        // outermost integral with look-ahead: take the halves from the cache where they were started ahead of time
+        int ntake = 0; int take_tag[2]; Seg take_seg[2];
+        for (int t = 1; t <= 2; t++) {
+            const double a = (t == 1) ? s.a : mid, b = (t == 1) ? mid : s.b;
+            const int e = find_spec(a, b);
+            if (e < 0) { int rc = start_segment(qi, a, b, t); if (rc) return rc; continue; }
+            spec_used++;
+            if (!spec_[e].done) { spec_[e].claim_tag = t; continue; }            // still in flight: delivered when it completes
+            spec_[e].live = false;
+            numevals += spec_[e].ne;
+            if (spec_[e].bad || !std::isfinite(spec_[e].seg.E)) { Pend p{}; p.a = a; p.b = b; return nan_error(p); }
+            take_tag[ntake] = t; take_seg[ntake] = spec_[e].seg; ntake++;
+        }
+        // start the bisection of the panel that is next in the heap (first of the top three whose halves are not cached yet), as long as
+        // the arena keeps room for the next regular bisection (30 slots) on top of this one (30)
+        const std::vector<int64_t>& fr = (q.level == 2) ? free2_ : free1_;
+        if (!q.heap.empty() && fr.size() >= 60) {
+            size_t cand[3] = {0, 1, 2};
+            if (q.heap.size() > 2 && seg_lt_rev(q.heap[2], q.heap[1])) { cand[1] = 2; cand[2] = 1; }
+            for (size_t c = 0; c < 3 && cand[c] < q.heap.size(); c++) {
+                const Seg t = q.heap[cand[c]];
+                const double tm = (t.a + t.b) / 2;
+                if (find_spec(t.a, tm) >= 0 || find_spec(tm, t.b) >= 0) continue;
+                int e1 = new_spec(t.a, tm);
+                int rc = start_segment(qi, t.a, tm, 3, e1);
+                if (rc) return rc;
+                int e2 = new_spec(tm, t.b);
+                rc = start_segment(qi, tm, t.b, 3, e2);
+                if (rc) return rc;
+                spec_started += 2;
+                break;
+            }
+        }
+        for (int k = 0; k < ntake; k++) { int rc = accept_half(qi, take_tag[k], take_seg[k]); if (rc) return rc; }
+        return IAI_OK;
     }
 
     int segment_done(int qi, int pend, cplx Is, double Es) {
         const Pend p = pends_[pend];
         free_pend_.push_back(pend);
+        const Seg seg{Es, p.a, p.b, Is};
+        if (p.spec >= 0) {
+            // look-ahead panel: park the result, or hand it over if QuadGK's order has reached it in the meantime
+            Spec& e = spec_[p.spec];
+            e.done = true; e.seg = seg;
+            if (e.claim_tag == 0) return IAI_OK;
+            e.live = false;
+            numevals += e.ne;
+            if (e.bad || !std::isfinite(Es)) return nan_error(p);
+            return accept_half(qi, e.claim_tag, seg);
+        }
         if (!std::isfinite(Es)) return nan_error(p);
         Integral& q = ints_[qi];
-        const Seg seg{Es, p.a, p.b, Is};
         if (p.tag <= 0) {
             // do_quadgk: I and E are left folds over the initial segments in their order; no subdivision when already converged
             // (finish() sums the vector in that same order), else heapify! (DataStructures: percolate_down from the last parent)
@@ -525,7 +605,13 @@ private:
             for (size_t i = q.heap.size() / 2; i >= 1; i--) heap_percolate_down(q.heap, i, q.heap[i - 1]);
             return refine(qi);
         }
-        if (p.tag == 1) { q.s1 = seg; q.has1 = true; } else { q.s2 = seg; q.has2 = true; }
+        return accept_half(qi, p.tag, seg);
+    }
+
+    // one half (tag 1: left, 2: right) of the bisected panel of integral qi is known; both known -> QuadGK's refine bookkeeping
+    int accept_half(int qi, int tag, const Seg& seg) {
+        Integral& q = ints_[qi];
+        if (tag == 1) { q.s1 = seg; q.has1 = true; } else { q.s2 = seg; q.has2 = true; }
         if (!(q.has1 && q.has2)) return IAI_OK;
         const Seg& s = q.popped;
         q.I = cplx{(q.I.re - s.I.re) + q.s1.I.re + q.s2.I.re, (q.I.im - s.I.im) + q.s1.I.im + q.s2.I.im};

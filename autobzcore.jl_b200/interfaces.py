@@ -380,7 +380,9 @@ def _init_cacheval(cache):
         # arena of contracted series: live level-2 slots <= 2 outstanding outer panels x K nodes (x initial segments), live level-1
         # slots <= that x 2 panels x K nodes; GK(7,15) fits the default 64 / 2048
         K = max(2 * a.order + 1 for a in salg.algs)
-        cv["nest_caps"] = (max(64, 4 * K), max(2048, max(64, 4 * K) * 2 * K))
+        # (small series: 160 level-2 slots leave room for the look-ahead bisection of the native engine, abz_iai_engine.hpp)
+        c2 = max(160 if f.s.norb <= 3 else 64, 4 * K)
+        cv["nest_caps"] = (c2, max(2048, max(64, 4 * K) * 2 * K))
         cv["nest"] = cache.backend.make_nest(f.s, ndim, *cv["nest_caps"])
     else:
         raise TypeError(f"unsupported algorithm {type(salg).__name__} for FourierIntegrand")
@@ -523,6 +525,7 @@ def _do_solve(cache, ps):
                 Iv, Ev, ne, rounds, launches = nest.iai_solve(lkind, la, lb, b1.fkind, vkind, z, sigma, lin, atol_, rtol_, maxiters,
                                                               device_leaves=getattr(cache.backend, "iai_device_leaves", True),
                                                               device_middles=getattr(cache.backend, "iai_device_middles", True),
+                                                              speculate=getattr(cache.backend, "iai_speculate", True),
                                                               rank=shard.rank, nranks=shard.nranks,
                                                               allreduce=shard.allreduce if shard.nranks > 1 else None, limits=general)
                 cache.cacheval["iai_rounds"] = rounds

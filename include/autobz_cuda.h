@@ -207,6 +207,12 @@ int32_t abz_nest_eval_matrix(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const 
  * each of its nodes and hands the innermost integrals to its warps - so the host engine only steps the outermost integral:
  * stats[1] (device rounds) drops from one per middle-level refinement to one per outermost refinement.  Same decisions, same numevals. */
 #define ABZ_IAI_DEVICE_MIDDLES 2
+/* ABZ_IAI_SPECULATE (with device leaves / middles; any number of ranks): when the outermost integral bisects its worst panel the engine also
+ * starts the bisection of the panel that is next in its heap and parks the result until QuadGK's own order reaches it (dropped, and
+ * not counted, if it never does).  Decisions, integral, error estimate and numevals are those of the sequential algorithm; a round
+ * carries up to two bisections, so stats[1] drops by up to 2x.  If the attempt fails (e.g. a singular point inside a panel the
+ * sequential algorithm would not have refined) the solve is repeated without look-ahead and that result / error is returned. */
+#define ABZ_IAI_SPECULATE 4
 int32_t abz_iai_solve(abz_ctx* ctx, abz_nest_t nest, int32_t lkind, const double* la, const double* lb, int32_t fkind,
                       int32_t vkind, const double* z, const double* sigma, const double* lin, double atol, double rtol,
                       int64_t maxevals, int32_t flags, double* out, int64_t* stats);

@@ -170,10 +170,13 @@ extern "C" int iai_cpu_solve(const double* coeffs, int n, int ndim, const int* M
     for (int d = 0; d < ndim; d++) { lims.a[d] = la[d]; lims.b[d] = lb ? lb[d] : 0.0; }
     be.lkind = lkind;
     for (int d = 0; d < ndim; d++) { be.lima[d] = lims.a[d]; be.limb[d] = lims.b[d]; }
-    // leaf_tasks: 0 host-driven panels, 1 innermost integrals as tasks, 2 middle integrals as tasks too
-    Engine<CpuBackend> eng(be, ndim, lims, atol, rtol, maxevals, cap2, cap1, leaf_tasks != 0, rank, nranks, leaf_tasks == 2);
+    // leaf_tasks & 3: 0 host-driven panels, 1 innermost integrals as tasks, 2 middle integrals as tasks too; | 4: look-ahead on the
+    // outermost integral (stats[4], stats[5] = half-panels started ahead / consumed)
+    const int mode = leaf_tasks & 3;
+    Engine<CpuBackend> eng(be, ndim, lims, atol, rtol, maxevals, cap2, cap1, mode != 0, rank, nranks, mode == 2, (leaf_tasks & 4) != 0);
     int rc = eng.run();
     stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = be.launches; stats[3] = eng.exchanges;
+    stats[4] = eng.spec_started; stats[5] = eng.spec_used;
     if (rc) return rc;
     out[0] = eng.result.re; out[1] = eng.result.im; out[2] = eng.result_err;
     return 0;

@@ -60,3 +60,40 @@ def test_device_middles_maxevals_rtol_and_errors(ctx, orc, svo):
     g = ab.FourierIntegrand(ab.gloc_trace_integrand, ab.FourierSeries(np.zeros((1, 1, 1, 1, 1)), period=1.0, lo=(0, 0, 0), norb=1), eta=0.0)
     with pytest.raises(FloatingPointError):
         ab.solve(ab.IntegralProblem(g, ab.load_bz(ab.CubicSymIBZ(), np.eye(3)), {"omega": 0.0}), ab.IAI(), abstol=1e-3)
+
+
+@pytest.mark.parametrize("lims", ["tetra", "cubic"])
+def test_lookahead_on_the_outermost_integral(ctx, orc, svo, lims):
+    """ABZ_IAI_SPECULATE: two bisections of the outermost integral per device round.  Bit-identical value and error estimate, identical
+    numevals (oracle's sequential recursion), fewer rounds; 2-d solves (innermost integrals as tasks) take part too."""
+    H, lo, A = svo
+    fs = ab.FourierSeries(H, period=1.0, lo=lo, norb=3)
+    S = orc.Series(H, lo)
+    z = complex(12.5, 0.005)
+    f = ab.FourierIntegrand(ab.dos_integrand, fs, z.imag)
+    bz = ab.load_bz(ab.CubicSymIBZ() if lims == "tetra" else ab.InversionSymIBZ(), A)
+    mult = abs(np.linalg.det(bz.B)) * bz.nsyms
+    atol = 2e-5 if lims == "tetra" else 1e-4
+    if lims == "tetra":
+        Io, Eo, neo = orc.iai(S, 3, 1, [0.5] * 3, vkind=1, z=z, atol=atol)
+    else:
+        Io, Eo, neo = orc.iai(S, 3, 0, [0.0] * 3, [0.5] * 3, vkind=1, z=z, atol=atol)
+    res = {}
+    for spec in (False, True):
+        be = ab.DeviceBackend(ctx=ctx, iai_speculate=spec)
+        cache = ab.init(ab.IntegralProblem(f, bz, z.real), ab.EvalCounter(ab.IAI()), abstol=atol * mult, backend=be)
+        sol = ab.solve_(cache)
+        res[spec] = (sol, cache.cacheval["iai_rounds"])
+        assert sol.numevals == neo and abs(sol.u - mult * Io.real) <= 1e-10 * abs(sol.u)
+    assert res[True][0].u == res[False][0].u and res[True][0].resid == res[False][0].resid
+    assert res[True][1] < res[False][1]
+    # 2-d
+    c2 = np.zeros((1, 1, 3, 3)); c2[0, 0, 0, 1] = c2[0, 0, 2, 1] = c2[0, 0, 1, 0] = c2[0, 0, 1, 2] = 0.5
+    h2 = ab.FourierSeries(c2, period=1.0, lo=(-1, -1), norb=1)
+    bz2 = ab.load_bz(ab.InversionSymIBZ(2), np.eye(2))
+    g = ab.FourierIntegrand(ab.gloc_trace_integrand, h2, eta=0.005)
+    out = []
+    for spec in (False, True):
+        cache = ab.init(ab.IntegralProblem(g, bz2, {"omega": 0.3}), ab.EvalCounter(ab.IAI()), abstol=1e-6, backend=ab.DeviceBackend(ctx=ctx, iai_speculate=spec))
+        out.append((ab.solve_(cache), cache.cacheval["iai_rounds"]))
+    assert out[0][0].u == out[1][0].u and out[0][0].numevals == out[1][0].numevals and out[1][1] < out[0][1]

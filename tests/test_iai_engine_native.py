@@ -33,12 +33,13 @@ def _solve(lib, S, ndim, lkind, la, lb, fkind, vkind, z, lin, atol, rtol, leaf, 
     zz = np.array([z.real, z.imag])
     ln = None if lin is None else np.ascontiguousarray(lin, dtype=np.float64)
     out = np.zeros(3)
-    st = (C.c_long * 4)()
+    st = (C.c_long * 6)()
     dp = lambda a: None if a is None else a.ctypes.data_as(c_dp)
     rc = lib.iai_cpu_solve(dp(S.c), C.c_int(S.n), C.c_int(ndim), i3(S.M), i3(S.lo), d3(S.period), C.c_int(lkind), dp(la_), dp(lb_),
                            C.c_int(fkind), C.c_int(vkind), dp(zz), None, dp(ln), C.c_double(atol), C.c_double(rtol),
                            C.c_long(maxevals), C.c_int(int(leaf)), C.c_long(cap2), C.c_long(cap1), C.c_int(rank), C.c_int(nranks),
                            xfn if xfn is not None else XFN(0), dp(out), st)
+    _solve.last_stats = [int(x) for x in st]
     return rc, complex(out[0], out[1]), out[2], int(st[0]), int(st[1])
 
 
@@ -127,11 +128,15 @@ xfn = XFN(allreduce)
 d = np.load(os.path.join({root!r}, "tests", "golden", "svo_hr.npz"))
 S = orc.Series(np.asfortranarray(d["H_R"]), tuple(int(x) for x in d["lo"]))
 ok = True
-for leaf in (False, True):
+for leaf in (False, True, 2, 6):      # 6: middle integrals as tasks + look-ahead on the outermost integral
     for (lk, la, lb, atol) in ((1, [0.5] * 3, None, 1e-3), (0, [0.0] * 3, [1.0] * 3, 3e-2)):
         z = complex(12.5, 0.05)
-        rc1, I1, E1, ne1, r1 = _solve(lib, S, 3, lk, la, lb, 0, 1, z, None, atol, 0.0, leaf)
-        rc2, I2, E2, ne2, r2 = _solve(lib, S, 3, lk, la, lb, 0, 1, z, None, atol, 0.0, leaf, rank=rank, nranks=nranks, xfn=xfn)
+        if leaf == 6:
+            if lk == 0: continue
+            z, atol = complex(12.5, 0.005), 2e-5          # enough refinements of the outermost integral for look-ahead to happen
+        rc1, I1, E1, ne1, r1 = _solve(lib, S, 3, lk, la, lb, 0, 1, z, None, atol, 0.0, leaf if leaf != 6 else 2, cap2=160)
+        rc2, I2, E2, ne2, r2 = _solve(lib, S, 3, lk, la, lb, 0, 1, z, None, atol, 0.0, leaf, cap2=160, rank=rank, nranks=nranks, xfn=xfn)
+        if leaf == 6 and not (_solve.last_stats[5] > 0 and r2 < r1): rc2 = -99      # the look-ahead case must actually look ahead
         good = rc1 == 0 and rc2 == 0 and I1 == I2 and E1 == E2 and ne1 == ne2     # bit-identical, evaluations of all ranks
         ok = ok and good
         print("RANK", rank, "leaf", leaf, "lims", lk, "OK" if good else "FAIL", I1, I2, ne1, ne2, "rounds", r1, r2, flush=True)
@@ -222,7 +227,7 @@ def _solve_general(lib, S, ndim, lims, fkind, vkind, z, lin, atol, rtol, leaf, m
     zz = np.array([z.real, z.imag])
     ln = None if lin is None else np.ascontiguousarray(lin, dtype=np.float64)
     out = np.zeros(3)
-    st = (C.c_long * 4)()
+    st = (C.c_long * 6)()
     dp = lambda a: None if a is None else a.ctypes.data_as(c_dp)
     cb = C.cast(_orc.limits_callback(lims), LIMITS_FN)
     cb._keep = lims
@@ -275,3 +280,46 @@ def test_engine_polyhedron_volumes(orc, eng):
         Io, Eo, neo = orc.iai_general(S, 3, lims, vkind=2, lin=(0.0, 1.0), atol=1e-10)
         assert rc == 0 and abs(I.real - vol) < 1e-8, (name, I, vol)
         assert ne == neo and abs(I - Io) <= 1e-13 * abs(Io)
+
+
+@pytest.mark.parametrize("case", ["svo3d_tetra", "svo3d_cubic", "cos2d", "cos2d_rtol", "cos2d_maxevals", "svo3d_maxevals"])
+def test_engine_lookahead_keeps_decisions_and_counts(orc, eng, svo, case):
+    """Look-ahead on the outermost integral (abz_iai_engine.hpp, ABZ_IAI_SPECULATE): the bisection of the panel next in the heap is
+    started together with the current one and parked until QuadGK's order reaches it.  Same integral, same error estimate, same
+    numevals as the sequential recursion (what is never reached is not counted), fewer rounds."""
+    H, lo, A = svo
+    atol, rtol, mx = 0.0, 0.0, 2 ** 62
+    if case.startswith("cos2d"):
+        c = np.zeros((1, 1, 3, 3, 1), dtype=complex)
+        c[0, 0, 0, 1, 0] = c[0, 0, 2, 1, 0] = c[0, 0, 1, 0, 0] = c[0, 0, 1, 2, 0] = 0.5
+        S, ndim, z, vk, mode = orc.Series(c, (-1, -1, 0)), 2, complex(0.3, 0.005), 0, 1
+        lk, la, lb = 0, [0.0, 0.0], [0.5, 0.5]
+        if case == "cos2d":
+            atol = 1e-6
+        elif case == "cos2d_rtol":
+            rtol = 1e-7
+        else:
+            atol, mx = 1e-9, 100
+    else:
+        S, ndim, vk, mode = orc.Series(H, lo), 3, 1, 2
+        if case == "svo3d_cubic":
+            lk, la, lb, z, atol = 0, [0.0] * 3, [0.5] * 3, complex(12.5, 0.02), 3e-5
+        elif case == "svo3d_tetra":
+            lk, la, lb, z, atol = 1, [0.5] * 3, None, complex(12.5, 0.005), 2e-5
+        else:
+            lk, la, lb, z, atol, mx = 1, [0.5] * 3, None, complex(12.5, 0.005), 1e-9, 100
+    Io, Eo, neo = orc.iai(S, ndim, lk, la, lb, vkind=vk, z=z, atol=atol, rtol=rtol, maxevals=mx)
+    rc0, I0, E0, ne0, rounds0 = _solve(eng, S, ndim, lk, la, lb, 0, vk, z, None, atol, rtol, mode, maxevals=mx, cap2=160)
+    rc1, I1, E1, ne1, rounds1 = _solve(eng, S, ndim, lk, la, lb, 0, vk, z, None, atol, rtol, mode | 4, maxevals=mx, cap2=160)
+    started, used = _solve.last_stats[4], _solve.last_stats[5]
+    assert rc0 == 0 and rc1 == 0
+    assert ne1 == ne0 == neo
+    assert I1 == I0 and E1 == E0                       # bit-identical: the same values combined in the same order
+    assert abs(I1 - Io) <= 1e-13 * abs(Io)
+    if "maxevals" in case:
+        assert started > 0 and used == 0               # started ahead, never reached, never counted
+    else:
+        assert 0 < used <= started and rounds1 < rounds0
+    # too small an arena for look-ahead: the engine simply does not speculate
+    rc2, I2, E2, ne2, rounds2 = _solve(eng, S, ndim, lk, la, lb, 0, vk, z, None, atol, rtol, mode | 4, maxevals=mx, cap2=64, cap1=64)
+    assert rc2 == 0 and ne2 == neo and I2 == I0 and _solve.last_stats[4] == 0
