@@ -267,6 +267,7 @@ public:
 
     int64_t numevals = 0, rounds = 0, exchanges = 0;   // numevals: all ranks' evaluations once the solve has finished
     int64_t spec_started = 0, spec_used = 0;           // look-ahead: half-panels started ahead of QuadGK's order / later consumed
+    int spec_depth = 1;                                // panels bisected ahead per refinement of the outermost integral (1 or 2)
     cplx result{0, 0};
     double result_err = 0;
     std::string error;
@@ -556,10 +557,11 @@ private:
         // start the bisection of the panel that is next in the heap (first of the top three whose halves are not cached yet), as long as
         // the arena keeps room for the next regular bisection (30 slots) on top of this one (30)
         const std::vector<int64_t>& fr = (q.level == 2) ? free2_ : free1_;
-        if (!q.heap.empty() && fr.size() >= 60) {
+        {
             size_t cand[3] = {0, 1, 2};
             if (q.heap.size() > 2 && seg_lt_rev(q.heap[2], q.heap[1])) { cand[1] = 2; cand[2] = 1; }
-            for (size_t c = 0; c < 3 && cand[c] < q.heap.size(); c++) {
+            int started = 0;
+            for (size_t c = 0; c < 3 && cand[c] < q.heap.size() && started < spec_depth && fr.size() >= 60; c++) {
                 const Seg t = q.heap[cand[c]];
                 const double tm = (t.a + t.b) / 2;
                 if (find_spec(t.a, tm) >= 0 || find_spec(tm, t.b) >= 0) continue;
@@ -570,7 +572,7 @@ private:
                 rc = start_segment(qi, tm, t.b, 3, e2);
                 if (rc) return rc;
                 spec_started += 2;
-                break;
+                started++;
             }
         }
         for (int k = 0; k < ntake; k++) { int rc = accept_half(qi, take_tag[k], take_seg[k]); if (rc) return rc; }
