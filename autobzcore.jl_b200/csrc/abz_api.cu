@@ -2312,6 +2312,7 @@ static int32_t iai_solve_impl(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
         // look-ahead on the outermost integral (abz_iai_engine.hpp): same decisions, fewer rounds.  A failure of this attempt may have
         // come from a panel the sequential algorithm never reaches, so it is not reported: the plain engine below decides.
         abz_iai::Engine<IaiDeviceBackend> eng0(be, nst->ndim, lims, atol, rtol, maxevals, nst->cap2, nst->cap1, leaf, rank, nranks, mid, true);
+        { static const int pol = getenv("ABZ_IAI_LOOKAHEAD") ? atoi(getenv("ABZ_IAI_LOOKAHEAD")) : 3; eng0.spec_policy = (pol >= 1 && pol <= 3) ? pol : 3; }
         rc = eng0.run();
         ctx->force_generic = false;
         if (rc == 0) {

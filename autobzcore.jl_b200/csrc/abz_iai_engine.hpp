@@ -22,11 +22,13 @@
 //
 // Look-ahead on the outermost integral (speculate = true, children of the outermost panels handed to the backend as whole
 // tasks): QuadGK refines one panel at a time, so a round would carry the 2 x 15 tasks of ONE bisection and the device would idle between
-// rounds.  When the outermost integral bisects its worst panel, the engine also starts the bisection of the panel that is next in its
-// heap and parks the two results in a cache keyed by (a, b).  When QuadGK's own order reaches that panel the halves are taken from the
-// cache (or claimed while still in flight) instead of being evaluated; what is never reached is dropped and its evaluations are not
-// counted.  Every accept / refine decision is taken on exactly the values and in exactly the order of the sequential algorithm, so the
-// integral, the error estimate and numevals are unchanged - only the number of rounds drops (up to 2x).
+// rounds.  When the outermost integral bisects its worst panel, the engine also starts the bisections QuadGK is most likely to ask for
+// next - the four quarters of that panel (its halves usually stay the worst ones while a feature is being resolved) and the panel that
+// is next in the heap - and parks the results in a cache keyed by (a, b).  When QuadGK's own order reaches such a panel the halves are
+// taken from the cache (or claimed while still in flight) instead of being evaluated; what is never reached is dropped and its
+// evaluations are not counted.  Every accept / refine decision is taken on exactly the values and in exactly the order of the
+// sequential algorithm, so the integral, the error estimate and numevals are unchanged - only the number of rounds drops
+// (C3, eta = 1e-4: 80 -> 32 rounds, 105 -> 58 ms; profiles/r02_c3_lookahead_timing.log).
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -267,7 +269,8 @@ public:
 
     int64_t numevals = 0, rounds = 0, exchanges = 0;   // numevals: all ranks' evaluations once the solve has finished
     int64_t spec_started = 0, spec_used = 0;           // look-ahead: half-panels started ahead of QuadGK's order / later consumed
-    int spec_depth = 1;                                // panels bisected ahead per refinement of the outermost integral (1 or 2)
+    int spec_depth = 1;                                // panels of the heap bisected ahead per refinement of the outermost integral
+    int spec_policy = 3;                               // 1: the panel(s) next in the heap, 2: the quarters of the panel being bisected, 3: both
     cplx result{0, 0};
     double result_err = 0;
     std::string error;
@@ -557,7 +560,22 @@ private:
         // start the bisection of the panel that is next in the heap (first of the top three whose halves are not cached yet), as long as
         // the arena keeps room for the next regular bisection (30 slots) on top of this one (30)
         const std::vector<int64_t>& fr = (q.level == 2) ? free2_ : free1_;
-        {
+        if (spec_policy & 2) {
+            // the four quarters of the panel being bisected: if one of its halves is QuadGK's next choice (the usual case while a
+            // feature is being resolved) its bisection is already there
+            const double m1 = (s.a + mid) / 2, m2 = (mid + s.b) / 2;
+            const double qa[4] = {s.a, m1, mid, m2}, qb[4] = {m1, mid, m2, s.b};
+            for (int h = 0; h < 2 && fr.size() >= 60; h++) {
+                if (find_spec(qa[2 * h], qb[2 * h]) >= 0 || find_spec(qa[2 * h + 1], qb[2 * h + 1]) >= 0) continue;
+                for (int k = 2 * h; k < 2 * h + 2; k++) {
+                    int e = new_spec(qa[k], qb[k]);
+                    int rc = start_segment(qi, qa[k], qb[k], 3, e);
+                    if (rc) return rc;
+                }
+                spec_started += 2;
+            }
+        }
+        if (spec_policy & 1) {
             size_t cand[3] = {0, 1, 2};
             if (q.heap.size() > 2 && seg_lt_rev(q.heap[2], q.heap[1])) { cand[1] = 2; cand[2] = 1; }
             int started = 0;

@@ -283,6 +283,18 @@ class IntegralCache:
         self.backend, self.shard = backend, shard
         self.cacheval = {}
 
+    def close(self):
+        """Release the device objects of the cache (rules, arena) now instead of when Python collects the cache: a one-shot
+        `solve` must hand its multi-GB rule buffers back to the library's pool before the next solve asks for them."""
+        for v in list(self.cacheval.values()):
+            for o in (v if isinstance(v, (list, tuple)) else (v,)):
+                if isinstance(o, IntegralCache) or (hasattr(o, "close") and not isinstance(o, type)):
+                    try:
+                        o.close()
+                    except Exception:
+                        pass
+        self.cacheval = {}
+
 
 def init(prob, alg, backend=None, shard=None, **kwargs):
     """init(prob, alg; kwargs...) (src/interfaces.jl:78-82): build the cache (rules / arena) once.
@@ -322,7 +334,12 @@ def solve_(cache, plist=None):
 
 def solve(prob, alg, backend=None, shard=None, **kwargs):
     """solve(prob, alg; kwargs...) = solve!(init(prob, alg; kwargs...)) (src/interfaces.jl:106-109)"""
-    return solve_(init(prob, alg, backend=backend, shard=shard, **kwargs))
+    cache = init(prob, alg, backend=backend, shard=shard, **kwargs)
+    try:
+        return solve_(cache)
+    finally:
+        if hasattr(cache, "close"):
+            cache.close()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -380,8 +397,8 @@ def _init_cacheval(cache):
         # arena of contracted series: live level-2 slots <= 2 outstanding outer panels x K nodes (x initial segments), live level-1
         # slots <= that x 2 panels x K nodes; GK(7,15) fits the default 64 / 2048
         K = max(2 * a.order + 1 for a in salg.algs)
-        # (small series: 160 level-2 slots leave room for the look-ahead bisection of the native engine, abz_iai_engine.hpp)
-        c2 = max(160 if f.s.norb <= 3 else 64, 4 * K)
+        # (small series: 256 level-2 slots leave room for the look-ahead bisection of the native engine, abz_iai_engine.hpp)
+        c2 = max(256 if f.s.norb <= 3 else 64, 4 * K)
         cv["nest_caps"] = (c2, max(2048, max(64, 4 * K) * 2 * K))
         cv["nest"] = cache.backend.make_nest(f.s, ndim, *cv["nest_caps"])
     else:

@@ -208,9 +208,10 @@ int32_t abz_nest_eval_matrix(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const 
  * stats[1] (device rounds) drops from one per middle-level refinement to one per outermost refinement.  Same decisions, same numevals. */
 #define ABZ_IAI_DEVICE_MIDDLES 2
 /* ABZ_IAI_SPECULATE (with device leaves / middles; any number of ranks): when the outermost integral bisects its worst panel the engine also
- * starts the bisection of the panel that is next in its heap and parks the result until QuadGK's own order reaches it (dropped, and
- * not counted, if it never does).  Decisions, integral, error estimate and numevals are those of the sequential algorithm; a round
- * carries up to two bisections, so stats[1] drops by up to 2x.  If the attempt fails (e.g. a singular point inside a panel the
+ * starts the bisections QuadGK is likely to ask for next (the quarters of that panel and the panel next in its heap; environment
+ * ABZ_IAI_LOOKAHEAD = 1 heap only, 2 quarters only, 3 both = default) and parks the results until QuadGK's own order reaches them
+ * (dropped, and not counted, if it never does).  Decisions, integral, error estimate and numevals are those of the sequential
+ * algorithm; a round carries several bisections, so stats[1] drops (C3: 80 -> 32).  If the attempt fails (e.g. a singular point inside a panel the
  * sequential algorithm would not have refined) the solve is repeated without look-ahead and that result / error is returned. */
 #define ABZ_IAI_SPECULATE 4
 int32_t abz_iai_solve(abz_ctx* ctx, abz_nest_t nest, int32_t lkind, const double* la, const double* lb, int32_t fkind,

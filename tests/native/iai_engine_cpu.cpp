@@ -175,6 +175,7 @@ extern "C" int iai_cpu_solve(const double* coeffs, int n, int ndim, const int* M
     const int mode = leaf_tasks & 3;
     Engine<CpuBackend> eng(be, ndim, lims, atol, rtol, maxevals, cap2, cap1, mode != 0, rank, nranks, mode == 2, (leaf_tasks & 4) != 0);
     if (leaf_tasks & 8) eng.spec_depth = 2;              // | 8: two panels ahead
+    if (leaf_tasks & 48) eng.spec_policy = (leaf_tasks >> 4) & 3;   // | 16: heap-top policy, | 32: quarters, | 48: both
     int rc = eng.run();
     stats[0] = eng.numevals; stats[1] = eng.rounds; stats[2] = be.launches; stats[3] = eng.exchanges;
     stats[4] = eng.spec_started; stats[5] = eng.spec_used;

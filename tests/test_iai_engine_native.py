@@ -310,16 +310,16 @@ def test_engine_lookahead_keeps_decisions_and_counts(orc, eng, svo, case):
             lk, la, lb, z, atol, mx = 1, [0.5] * 3, None, complex(12.5, 0.005), 1e-9, 100
     Io, Eo, neo = orc.iai(S, ndim, lk, la, lb, vkind=vk, z=z, atol=atol, rtol=rtol, maxevals=mx)
     rc0, I0, E0, ne0, rounds0 = _solve(eng, S, ndim, lk, la, lb, 0, vk, z, None, atol, rtol, mode, maxevals=mx, cap2=160)
-    rc1, I1, E1, ne1, rounds1 = _solve(eng, S, ndim, lk, la, lb, 0, vk, z, None, atol, rtol, mode | 4, maxevals=mx, cap2=160)
-    started, used = _solve.last_stats[4], _solve.last_stats[5]
-    assert rc0 == 0 and rc1 == 0
-    assert ne1 == ne0 == neo
-    assert I1 == I0 and E1 == E0                       # bit-identical: the same values combined in the same order
-    assert abs(I1 - Io) <= 1e-13 * abs(Io)
-    if "maxevals" in case:
-        assert started > 0 and used == 0               # started ahead, never reached, never counted
-    else:
-        assert 0 < used <= started and rounds1 < rounds0
+    assert rc0 == 0 and ne0 == neo and abs(I0 - Io) <= 1e-13 * abs(Io)
+    for policy in ((16, 32, 48) if ndim == 2 else (48,)):  # the panel next in the heap / the quarters of the bisected panel / both
+        rc1, I1, E1, ne1, rounds1 = _solve(eng, S, ndim, lk, la, lb, 0, vk, z, None, atol, rtol, mode | 4 | policy, maxevals=mx, cap2=256)
+        started, used = _solve.last_stats[4], _solve.last_stats[5]
+        assert rc1 == 0 and ne1 == neo
+        assert I1 == I0 and E1 == E0                       # bit-identical: the same values combined in the same order
+        if "maxevals" in case:
+            assert started > used                          # some were started ahead, never reached, and (ne1 == neo) never counted
+        else:
+            assert 0 < used <= started and rounds1 < rounds0
     # too small an arena for look-ahead: the engine simply does not speculate
     rc2, I2, E2, ne2, rounds2 = _solve(eng, S, ndim, lk, la, lb, 0, vk, z, None, atol, rtol, mode | 4, maxevals=mx, cap2=64, cap1=64)
     assert rc2 == 0 and ne2 == neo and I2 == I0 and _solve.last_stats[4] == 0
