@@ -31,14 +31,18 @@ for case in range(ncase):
     tag = f"case {case}: ndim={ndim} n={n} M={m} lkind={lkind} vkind={vkind} z={z} atol={tol}"
     try:
         Io, Eo, neo = orc.iai(So, ndim, lkind, la, lb, vkind=vkind, z=z, atol=tol)
-        nest = L.DeviceNest(ctx, fs.device(ctx), ndim, 64 if ndim == 3 else 0, 4096 if ndim >= 2 else 0)
-        for leaves in (True, False):
-            I, E, ne, rounds, launches = nest.iai_solve(lkind, la, lb, L.F_RESOLVENT_TRACE, vkind, z, None, None, tol, 0.0, 2 ** 62, device_leaves=leaves)
+        nest = L.DeviceNest(ctx, fs.device(ctx), ndim, 256 if ndim == 3 else 0, 4096 if ndim >= 2 else 0)
+        first = None
+        # (device leaves, device middles, look-ahead): every engine configuration must take the oracle's decisions
+        for leaves, mids, spec in ((True, True, True), (True, True, False), (True, False, True), (True, False, False), (False, False, False)):
+            I, E, ne, rounds, launches = nest.iai_solve(lkind, la, lb, L.F_RESOLVENT_TRACE, vkind, z, None, None, tol, 0.0, 2 ** 62,
+                                                        device_leaves=leaves, device_middles=mids, speculate=spec)
             e = abs(I - Io) / max(abs(Io), 1e-12)
             worst = max(worst, e)
-            if ne != neo or not e <= 1e-10:
+            first = (I, E) if first is None else first
+            if ne != neo or not e <= 1e-10 or (leaves and (I, E) != first):     # device-task configurations agree bit for bit
                 fails += 1
-                print("FAIL", tag, "leaves", leaves, "numevals", ne, neo, "rel", e, flush=True)
+                print("FAIL", tag, "leaves/middles/lookahead", leaves, mids, spec, "numevals", ne, neo, "rel", e, flush=True)
         tot += neo
     except Exception as ex:                                 # noqa: BLE001
         fails += 1
