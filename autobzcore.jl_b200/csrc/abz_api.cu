@@ -133,7 +133,7 @@ struct abz_ctx {
     int iai_lanes_opt = 4;        // IAI rounds in flight (ABZ_OPT_IAI_LANES)
     int leaf_spill = LEAF_SPILL;  // segments per device-side innermost integral beyond the 63 kept in shared memory
     bool force_generic = false;   // set while re-running a call whose fast path asked for pivoting
-    DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d, iai_in, iai_out, eig_d, eig_e, symw, symlist;
+    DevBuf C2, C1, Hc, partial, acc, zbuf, sigbuf, errflag, tmp_a, tmp_b, tmp_c, tmp_d, iai_in, iai_out, eig_d, eig_e, eig_trail, symw, symlist;
     void* pin_in = nullptr; size_t pin_in_cap = 0;     // pinned staging for the IAI engine's per-round traffic
     void* pin_out = nullptr; size_t pin_out_cap = 0;
     long launches = 0;
@@ -401,8 +401,25 @@ static int launch_tridiag(abz_ctx* ctx, const double2* H, long nk, int n, int* h
     }
     if (n > 32 && n <= 64 && ctx->eig_algo != 2) {
         const long ncta = std::min<long>(nk, (long)ctx->sm_count * 2);
-        eig_tridiag_reg64_kernel<<<(unsigned)ncta, 256, 0, ctx->stream>>>(H, nk, n, dd, ee, herm_flag);
+        static const bool split = getenv("ABZ_TRIDIAG_SPLIT") ? atoi(getenv("ABZ_TRIDIAG_SPLIT")) != 0 : true;
+        if (!split) {
+            eig_tridiag_reg64_kernel<63><<<(unsigned)ncta, 256, 0, ctx->stream>>>(H, nk, n, dd, ee, herm_flag, nullptr, 0);
+            LAUNCH_CHECK(ctx, "eig_tridiag_reg64_kernel");
+            return ABZ_OK;
+        }
+        // the first 32 reflections with the CTA-per-matrix kernel, the trailing (n - 32)^2 block with the warp-per-matrix kernel
+        const int n2 = n - 32;
+        CU(ctx, ctx->eig_trail.reserve((size_t)nk * n2 * n2 * sizeof(double2)));
+        double2* tr = ctx->eig_trail.as<double2>();
+        eig_tridiag_reg64_kernel<32><<<(unsigned)ncta, 256, 0, ctx->stream>>>(H, nk, n, dd, ee, herm_flag, tr, n2);
         LAUNCH_CHECK(ctx, "eig_tridiag_reg64_kernel");
+        const long nblk2 = std::min<long>((nk + 3) / 4, (long)ctx->sm_count * 16);
+        double* d2 = dd + 32 * nk; double* e2 = ee + 32 * nk;
+        if (n2 <= 8) eig_tridiag_warp_kernel<8, 3><<<(unsigned)nblk2, 128, 0, ctx->stream>>>(tr, nk, n2, d2, e2, nullptr);
+        else if (n2 <= 16) eig_tridiag_warp_kernel<16, 3><<<(unsigned)nblk2, 128, 0, ctx->stream>>>(tr, nk, n2, d2, e2, nullptr);
+        else if (n2 <= 24) eig_tridiag_warp_kernel<24, 3><<<(unsigned)nblk2, 128, 0, ctx->stream>>>(tr, nk, n2, d2, e2, nullptr);
+        else eig_tridiag_warp_kernel<32, 3><<<(unsigned)nblk2, 128, 0, ctx->stream>>>(tr, nk, n2, d2, e2, nullptr);
+        LAUNCH_CHECK(ctx, "eig_tridiag_warp_kernel");
         return ABZ_OK;
     }
     const int RP = n > 32 ? 64 : 32;

@@ -614,9 +614,13 @@ __device__ __noinline__ void householder_w64(const double2* __restrict__ pb, con
 // buffered), the mat-vec result and one copy of w per warp: the shared-memory kernel above spends 66 % of the LSU
 // wavefront budget on re-reading A, this one reads v_j / w_j broadcasts only.  Two block barriers per column; warps whose
 // eight rows are all above the current column only take part in the barriers.
+// CSTOP = 63: all columns.  CSTOP = 32 (default, "split"): the first 32 reflections only; the trailing 32 x 32 block - by then half of
+// the CTA's warps have no rows left and every column still costs two block barriers and two reductions - is written to `trail`
+// ([nk][n2][n2] column-major, n2 = n - 32) and finished by the barrier-free warp-per-matrix kernel above, which writes d[32..], e[32..].
+template <int CSTOP>
 __global__ void __launch_bounds__(256, 2)
 eig_tridiag_reg64_kernel(const double2* __restrict__ H, long nk, int n, double* __restrict__ dout, double* __restrict__ eout,
-                         int* __restrict__ herm_flag) {
+                         int* __restrict__ herm_flag, double2* __restrict__ trail, int n2) {
     constexpr int N = 64, NS = 16;
     __shared__ double2 vbuf[2][N];
     __shared__ double2 pb[N];
@@ -653,7 +657,7 @@ eig_tridiag_reg64_kernel(const double2* __restrict__ H, long nk, int n, double* 
             }
         }
 #pragma unroll
-        for (int c = 0; c < N - 1; c++) {
+        for (int c = 0; c < CSTOP; c++) {
             double2* vs = vbuf[c & 1];
             const bool warp_on = (warp * 8 + 7 > c);                   // some of this warp's rows lie below the diagonal entry
             if (warp_on && q == (c & 3)) vs[i] = a[c >> 2];            // column c of the current matrix (rows > c are needed)
@@ -705,7 +709,16 @@ eig_tridiag_reg64_kernel(const double2* __restrict__ H, long nk, int n, double* 
             // no barrier here: the next column publishes into the other half of vbuf, pb is rewritten only after the next
             // barrier, and wv is private to the warp
         }
-        if (i == N - 1 && q == 3 && N - 1 < n) { dout[(long)(N - 1) * nk + k] = a[NS - 1].x; eout[(long)(N - 1) * nk + k] = 0.0; }
+        if (CSTOP == N - 1) {
+            if (i == N - 1 && q == 3 && N - 1 < n) { dout[(long)(N - 1) * nk + k] = a[NS - 1].x; eout[(long)(N - 1) * nk + k] = 0.0; }
+        } else if (i >= CSTOP && i - CSTOP < n2) {
+            double2* tk = trail + k * (long)n2 * n2;
+#pragma unroll
+            for (int s = CSTOP / 4; s < NS; s++) {
+                const int j = q + 4 * s - CSTOP;
+                if (j < n2) tk[(i - CSTOP) + (long)j * n2] = a[s];
+            }
+        }
         __syncthreads();
     }
 }
