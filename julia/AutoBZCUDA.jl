@@ -284,6 +284,17 @@ function eval_h!(Hk::Array{ComplexF64,3}, n::DeviceNest, x1::Vector{Float64}, sl
     return Hk
 end
 
+# (z - H(k) - Sigma)^-1 at the nodes of innermost panels: the value type of `gloc_integrand` under IAI (docs/src/examples.md:90-106).
+# G is n x n x npts, column-major per node.
+function eval_matrix!(G::Array{ComplexF64,3}, n::DeviceNest, x1::Vector{Float64}, slot1::Vector{Int64}, z::ComplexF64,
+                      Σ::Union{Nothing,Matrix{ComplexF64}}=nothing)
+    zz = Float64[real(z), imag(z)]
+    GC.@preserve G Σ check(n.ctx, ccall((:abz_nest_eval_matrix, LIB), Int32,
+        (Ptr{Cvoid}, UInt64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        n.ctx.h, n.h, length(x1), x1, slot1, zz, Σ === nothing ? C_NULL : Ptr{Float64}(pointer(Σ)), Ptr{Float64}(pointer(G))))
+    return G
+end
+
 # The whole nested solve in one call (do_solve(f::FourierIntegrand, lims, ::NestedQuad), src/fourier.jl:493-510): same
 # control flow as IteratedIntegration/QuadGK, run by the library's host engine.  lims::CubicLimits or TetrahedralLimits.
 # vkind 0: tr G, 1: -Im(tr G)/pi (aps_example.jl:30).  exchange: @cfunction(allreduce!, Int32, (Ptr{Float64}, Int64, Ptr{Cvoid}))
@@ -298,7 +309,8 @@ function iai_solve(n::DeviceNest, lkind::Integer, la::Vector{Float64}, lb, z::Co
                        (Ptr{Cvoid}, UInt64, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
                         Float64, Float64, Int64, Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}),
                        n.ctx.h, n.h, lkind, la, lb === nothing ? C_NULL : lb, 0, vkind, zz, C_NULL, C_NULL,
-                       abstol, reltol, maxiters, device_leaves ? 1 : 0, rank, nranks, exchange, C_NULL, out, stats))
+                       abstol, reltol, maxiters, device_leaves ? 7 : 0,   # ABZ_IAI_DEVICE_LEAVES | _MIDDLES | ABZ_IAI_SPECULATE
+                       rank, nranks, exchange, C_NULL, out, stats))
     return IntegralSolution(vkind == 1 ? out[1] : complex(out[1], out[2]), out[3], true, Int(stats[1]))
 end
 
