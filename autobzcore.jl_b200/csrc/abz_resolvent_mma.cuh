@@ -139,6 +139,57 @@ __device__ __forceinline__ void inv8(double& xr0, double& xr1, double& xi0, doub
     }
 }
 
+// Division-free form of inv8 (VAR 4).  The dependent chain of a pivot step of inv8 is  exchange -> |pivot|^2 -> reciprocal (MUFU seed + two
+// Newton steps) -> multiplier -> two FMAs, about nine visits of the FP64 pipe that DMMA shares; here a step is the cross-multiplied row
+// operation  row_g <- a_pp row_g - a_gp row_p  (g != p): exchange -> four FMAs, no reciprocal at all.  Every row carries its own scale:
+// z_g is that scale c_g until the row's own pivot step and the diagonal entry s_g = pivot_g c_g afterwards (both are multiplied by a_pp in every
+// other step), the freed column p receives the new column of R with R_pp = c_p, and ONE reciprocal per row at the end gives
+// inv = diag(1/s) R.  Row scales square from step to step (c ~ pivot^(2^p - 1)), so the rows are rescaled by an exact power of two
+// after four steps (|entries| stay below ~ max|a|^30: overflow needs max|a| > 1e10 and ends as NaN -> flag -> pivoted rerun).  Same FP64
+// instruction count as inv8 (8 x 20 + 22 against 8 x 23), less than half its dependent depth.  The pivot monitor works on exponents:
+// log2|pivot_p| ~ mag(a_pp) - mag(c_p) with mag = high word of max(|re|, |im|), kept per lane (row) and min-reduced by the caller.
+__device__ __forceinline__ int dmag(double re, double im) { return max(__double2hiint(re) & 0x7fffffff, __double2hiint(im) & 0x7fffffff); }
+__device__ __forceinline__ void inv8_ff(double& xr0, double& xr1, double& xi0, double& xi1, int lane, int& minhi) {
+    const int g = lane >> 2, q = lane & 3, quad = lane & ~3;
+    double zr = 1.0, zi = 0.0;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const int sg = p & 1, qp = p >> 1;
+        const bool prow = (g == p), pcol = (q == qp);
+        const double ppr = __shfl_sync(0xffffffffu, sg ? xr1 : xr0, 4 * p + qp);       // a_pp
+        const double ppi = __shfl_sync(0xffffffffu, sg ? xi1 : xi0, 4 * p + qp);
+        const double gfr = __shfl_sync(0xffffffffu, sg ? xr1 : xr0, quad | qp);        // a_gp of my row
+        const double gfi = __shfl_sync(0xffffffffu, sg ? xi1 : xi0, quad | qp);
+        // column p turns into the new column of R: c_p in row p, zero elsewhere (then updated like every other column)
+        const double cr = prow ? zr : 0.0, ci = prow ? zi : 0.0;
+        if (sg) { xr1 = pcol ? cr : xr1; xi1 = pcol ? ci : xi1; } else { xr0 = pcol ? cr : xr0; xi0 = pcol ? ci : xi0; }
+        const double pr0 = __shfl_sync(0xffffffffu, xr0, 4 * p + q), pi0 = __shfl_sync(0xffffffffu, xi0, 4 * p + q);
+        const double pr1 = __shfl_sync(0xffffffffu, xr1, 4 * p + q), pi1 = __shfl_sync(0xffffffffu, xi1, 4 * p + q);
+        const int dl = min(max(dmag(ppr, ppi) - dmag(zr, zi), -0x1ff00000), 0x1ff00000);
+        minhi = min(minhi, prow ? 0x3ff00000 + 2 * dl : 0x7ff00000);                    // ~ high word of |pivot_p|^2
+        // the pivot row itself is only scaled by a_pp (f = 0); its z becomes the diagonal entry
+        const double fr = prow ? 0.0 : gfr, fi = prow ? 0.0 : gfi;
+        const double wr = prow ? ppr : zr, wi = prow ? ppi : zi;
+        double t;
+        t = ppr * xr0; t = fma(-ppi, xi0, t); t = fma(-fr, pr0, t); const double nr0 = fma(fi, pi0, t);
+        t = ppr * xi0; t = fma(ppi, xr0, t); t = fma(-fr, pi0, t); const double ni0 = fma(-fi, pr0, t);
+        t = ppr * xr1; t = fma(-ppi, xi1, t); t = fma(-fr, pr1, t); const double nr1 = fma(fi, pi1, t);
+        t = ppr * xi1; t = fma(ppi, xr1, t); t = fma(-fr, pi1, t); const double ni1 = fma(-fi, pr1, t);
+        xr0 = nr0; xi0 = ni0; xr1 = nr1; xi1 = ni1;
+        zr = fma(-ppi, wi, ppr * wr); zi = fma(ppi, wr, ppr * wi);
+        if (p == 3) {                        // exact rescaling of my row by 2^-exponent(z)
+            const double r = __hiloint2double(0x7fe00000 - (dmag(zr, zi) & 0x7ff00000), 0);
+            xr0 *= r; xi0 *= r; xr1 *= r; xi1 *= r; zr *= r; zi *= r;
+        }
+    }
+    const double dinv = fast_rcp(fma(zr, zr, zi * zi));
+    const double ir = zr * dinv, ii = -zi * dinv;                                      // 1 / s_g
+    double t;
+    t = ir * xr0; const double nr0 = fma(-ii, xi0, t); t = ir * xi0; const double ni0 = fma(ii, xr0, t);
+    t = ir * xr1; const double nr1 = fma(-ii, xi1, t); t = ir * xi1; const double ni1 = fma(ii, xr1, t);
+    xr0 = nr0; xi0 = ni0; xr1 = nr1; xi1 = ni1;
+}
+
 // One pivot step of inv8 in two halves, so that independent DMMA work can be placed BETWEEN them in program order: the exchange
 // (eight shuffles: pivot row, pivot, this row's multiplier) and the arithmetic.  The compiler keeps shuffles and mma.sync in source
 // order and only floats the scalar FP64 chain, so the block product written between the halves is what fills the chain's latency.
@@ -406,7 +457,7 @@ __device__ __forceinline__ double2 warp_trace_inverse_paired(double (&R0)[NB][NB
 // VAR 1: right-looking substitutions - a finished block of V (M) is turned into its fragment once and immediately applied to all
 //        rows above (below) it, so the block products of one step are independent (more DMMA chains in flight, one live fragment
 //        instead of the bV[] / bM[] arrays), and the fragments of M feed the trace as they are made.
-template <int NB, int VAR>
+template <int NB, int VAR, bool FF = false>
 __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], double (&R1)[NB][NB], double (&I0)[NB][NB],
                                                       double (&I1)[NB][NB], int lane, int& minpiv) {
     const int g = lane >> 2, q = lane & 3;
@@ -415,7 +466,8 @@ __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], doub
     const int src1 = 4 * (2 * q + (par ? 0 : 1)) + (g >> 1);
     // ---- block LU with look-ahead: S_{s+1} is inverted as soon as its update is complete, so that the
     //      latency-bound pivot steps overlap the remaining (independent) trailing-update DMMAs
-    inv8(R0[0][0], R1[0][0], I0[0][0], I1[0][0], lane, minpiv);          // D_0
+    if constexpr (FF) inv8_ff(R0[0][0], R1[0][0], I0[0][0], I1[0][0], lane, minpiv);
+    else inv8(R0[0][0], R1[0][0], I0[0][0], I1[0][0], lane, minpiv);          // D_0
 #pragma unroll
     for (int s = 0; s < NB - 1; s++) {
         const BFrag bD = to_bfrag(R0[s][s], R1[s][s], I0[s][s], I1[s][s], src0, src1, par);
@@ -431,7 +483,10 @@ __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], doub
 #pragma unroll
             for (int i = s + 1; i < NB; i++)                             // A_ij -= L_is U_sj
                 bmm<true>(R0[i][j], R1[i][j], I0[i][j], I1[i][j], R0[i][s], R1[i][s], I0[i][s], I1[i][s], bU);
-            if (j == s + 1) inv8(R0[j][j], R1[j][j], I0[j][j], I1[j][j], lane, minpiv);   // D_{s+1} (look-ahead)
+            if (j == s + 1) {                                            // D_{s+1} (look-ahead)
+                if constexpr (FF) inv8_ff(R0[j][j], R1[j][j], I0[j][j], I1[j][j], lane, minpiv);
+                else inv8(R0[j][j], R1[j][j], I0[j][j], I1[j][j], lane, minpiv);
+            }
             {                                                            // X_sj = D_s U_sj (replaces U_sj)
                 double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
                 bmm<false>(cr0, cr1, ci0, ci1, R0[s][s], R1[s][s], I0[s][s], I1[s][s], bU);
@@ -587,7 +642,11 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
         double2 t;
         if constexpr (NB == 4 && VAR == 2) t = warp_trace_inverse_pipelined(R0, R1, I0, I1, lane, minhi);
         else if constexpr (VAR == 3) t = warp_trace_inverse_paired<NB>(R0, R1, I0, I1, lane, minhi);
-        else t = warp_trace_inverse<NB, (VAR == 2 ? 1 : VAR)>(R0, R1, I0, I1, lane, minhi);
+        else if constexpr (VAR == 4) {
+            t = warp_trace_inverse<NB, 1, true>(R0, R1, I0, I1, lane, minhi);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) minhi = min(minhi, __shfl_xor_sync(0xffffffffu, minhi, off));   // kept per row
+        } else t = warp_trace_inverse<NB, (VAR == 2 ? 1 : VAR)>(R0, R1, I0, I1, lane, minhi);
         t.x = -t.x - (double)npad; t.y = -t.y;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) amaxhi = max(amaxhi, __shfl_xor_sync(0xffffffffu, amaxhi, off));
@@ -647,7 +706,7 @@ inline int mma_resolvent_plan(int n, long nk, int nw, long sm, long* ncta, int* 
 // substitution variant of the norb = 25..32 kernel (ABZ_MMA_VARIANT = 0 / 1, see warp_trace_inverse); smaller matrices use 0
 inline int mma_resolvent_variant() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("ABZ_MMA_VARIANT"); v = e ? std::min(3, std::max(0, atoi(e))) : ABZ_MMA_DEFAULT_VARIANT; }
+    if (v < 0) { const char* e = getenv("ABZ_MMA_VARIANT"); v = e ? std::min(4, std::max(0, atoi(e))) : ABZ_MMA_DEFAULT_VARIANT; }
     return v;
 }
 
@@ -656,7 +715,9 @@ inline void mma_launch_one(const double2* H, const double* wnode, long nk, int n
                            int mode, double2* outp, int* errflag, long ncta, int kper, cudaStream_t stream) {
     size_t smem = (size_t)nw * W * sizeof(double2);
     if (W == 4) smem = std::max<size_t>(smem, 120 * 1024);      // measurement hook: keeps a second 4-warp CTA off the SM
-    if (NB == 4 && mma_resolvent_variant() == 3)
+    if (NB == 4 && mma_resolvent_variant() == 4)
+        resolvent_mma_kernel<NB, W, (NB == 4 ? 4 : 0)><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
+    else if (NB == 4 && mma_resolvent_variant() == 3)
         resolvent_mma_kernel<NB, W, (NB == 4 ? 3 : 0)><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
     else if (NB == 4 && mma_resolvent_variant() == 2)
         resolvent_mma_kernel<NB, W, (NB == 4 ? 2 : 0)><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
@@ -679,6 +740,7 @@ inline cudaError_t mma_resolvent_opt_in() {
     { auto k8 = resolvent_mma_kernel<4, 8, 1>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 1>; set((const void*)k12); }
     { auto k8 = resolvent_mma_kernel<4, 8, 2>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 2>; set((const void*)k12); }
     { auto k8 = resolvent_mma_kernel<4, 8, 3>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 3>; set((const void*)k12); }
+    { auto k8 = resolvent_mma_kernel<4, 8, 4>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 4>; set((const void*)k12); auto k4 = resolvent_mma_kernel<4, 4, 4>; set((const void*)k4); }
     { auto k4 = resolvent_mma_kernel<4, 4, 0>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 1>; set((const void*)k41); }
     { auto k4 = resolvent_mma_kernel<4, 4, 2>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 3>; set((const void*)k41); }
     return e;
