@@ -1247,19 +1247,37 @@ static int32_t abz_rule_resolvent_sum_impl(abz_ctx* ctx, abz_rule_t rid, int32_t
         ev_mat.push_back({e0, next_event(ctx)});
     } else {
         const bool fused = small && ctx->fused_small;
+        // K3-fused: the DMMA one-warp kernel forms H(k) itself from the C1 rows (stage 1 folded in, no H(k) in HBM)
+        static const int fused_mma_env = getenv("ABZ_FUSED_MMA") ? atoi(getenv("ABZ_FUSED_MMA")) : 1;
+        const bool fused_mma = !small && fused_mma_env && fkind == ABZ_F_RESOLVENT_TRACE && nw >= 8 && mma_resolvent_supported(n) &&
+                               (ctx->resolvent_algo == 0 || ctx->resolvent_algo == 2) && !ctx->force_generic &&
+                               !(getenv("ABZ_MMA_TEAM") && atoi(getenv("ABZ_MMA_TEAM")) == 1 && n > 24) &&
+                               mma_resolvent_variant() == ABZ_MMA_DEFAULT_VARIANT && mma_resolvent_warps() == 8 &&
+                               mma_fused_smem(n, nw) <= 160 * 1024;
         long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
-        long ncap = fused ? ((long)1 << 28) : node_cap_for(ctx, n);
+        long ncap = (fused || fused_mma) ? ((long)1 << 40) : node_cap_for(ctx, n);
         auto chunks = plan_chunks(r, ncap, (long)(ctx->budget / (rows1 * sizeof(double2))),
                                   (long)(ctx->budget / (rows2 * sizeof(double2))));
         for (auto& ch : chunks) {
             long n0 = r->h_row_nodeptr[ch.r0], n1 = r->h_row_nodeptr[ch.r1];
             cudaEvent_t e0 = next_event(ctx);
-            if (!fused) CU(ctx, ctx->Hc.reserve((size_t)(n1 - n0) * nn * sizeof(double2)));
-            rc = eval_chunk(ctx, r, ch, !fused, ctx->Hc.as<double2>());
+            if (!fused && !fused_mma) CU(ctx, ctx->Hc.reserve((size_t)(n1 - n0) * nn * sizeof(double2)));
+            rc = eval_chunk(ctx, r, ch, !fused && !fused_mma, ctx->Hc.as<double2>());
             if (rc) return rc;
             cudaEvent_t e1 = next_event(ctx);
             if (fused) rc = run_small_fused<false>(ctx, r, ctx->C1.as<double2>(), nullptr, ch.r0, ch.r1 - ch.r0, fkind, nw, dz, dsig);
-            else if (small) {
+            else if (fused_mma) {
+                long ncta = 0; int kper_m = 1;
+                if (n1 > n0 && mma_resolvent_plan(n, n1 - n0, nw, ctx->sm_count, &ncta, &kper_m) == 0) {
+                    CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
+                    CU(ctx, mma_fused_launch(ctx->C1.as<double2>(), r->d_ptab[0], r->d_row_nodeptr, ch.r0, ch.r1, r->d_node_k1, r->N, s->M[0],
+                                             r->d_node_w, n0, n1 - n0, n, nw, dz, dsig, ctx->partial.as<double2>(), ctx->errflag.as<int>(),
+                                             ncta, kper_m, ctx->stream));
+                    ctx->launches++;
+                    reduce_partials_kernel<<<nw, 256, 0, ctx->stream>>>(ctx->partial.as<double2>(), ncta, nw, 1.0, ctx->acc.as<double2>());
+                    LAUNCH_CHECK(ctx, "reduce_partials_kernel");
+                } else if (n1 > n0) rc = fail(ctx, ABZ_E_UNSUPPORTED, "internal: no launch plan for the fused DMMA resolvent");
+            } else if (small) {
                 // unfused small path (option): treat the chunk as a materialised block
                 rc = fail(ctx, ABZ_E_UNSUPPORTED, "unfused small-norb streaming is not implemented; materialize the rule");
             } else

@@ -673,6 +673,120 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
     }
 }
 
+// K3-fused: the same one-warp-per-matrix block LU with the innermost contraction stage folded in, so that H(k) never exists in
+// HBM (FourierSeriesEvaluators evaluates H(k) and hands it to the integrand, src/fourier.jl:127-164; here the CTA is that hand-over).
+// A CTA walks its nodes k; for each node all 256 threads form H(k) = sum_m C1[row(k)][m] e^{2 pi i k1 R_m} (the stage-1 sum, 4 matrix
+// entries per thread, C1 and the phase table from L2) into one of two shared-memory buffers (leading dimension n | 1: the C-layout
+// loads of a quarter-warp then fall into 8 different 16-byte bank groups), and the 8 warps take the frequencies w = warp, warp + 8, ...
+// of that node from the buffer while the next node's H is formed into the other one (one block barrier per node).  Per node the
+// contraction costs 4 M complex FMAs per thread - for nw = 128 that is 17 FP64 instructions per matrix against ~1150 - and reads the
+// M n^2 coefficients of its row from L2; what disappears is the 16 n^2 B per node written and read back by the separate stage-1 kernel.
+// Weighted sums only (mode 0), nw >= MMA_WARPS.
+template <int NB, int MMA_WARPS, int VAR>
+__global__ void __launch_bounds__(MMA_WARPS * 32, 1)
+resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __restrict__ ptab, const long* __restrict__ row_nodeptr,
+                           long r0, long r1, const int* __restrict__ klist, int N, int M, const double* __restrict__ wnode, long n0,
+                           long nk, int n, int nw, const double2* __restrict__ z, const double2* __restrict__ sigma, int kper,
+                           double2* __restrict__ outp, int* __restrict__ errflag) {
+    extern __shared__ double2 mma_acc[];                 // acc[MMA_WARPS][nw] | sH[2][n * LDH]
+    constexpr int NT = MMA_WARPS * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int LDH = n | 1;
+    const int nn = n * n;
+    double2* acc = mma_acc + (long)warp * nw;
+    double2* sH = mma_acc + (long)MMA_WARPS * nw;
+    for (int w = lane; w < nw; w += 32) acc[w] = make_double2(0.0, 0.0);
+    const long ka = n0 + (long)blockIdx.x * kper;
+    const long kb = ka + kper < n0 + nk ? ka + kper : n0 + nk;
+    long row = r0;
+    {   // row of the first node: row_nodeptr[row] <= ka < row_nodeptr[row + 1]
+        long lo = r0, hi = r1;
+        while (hi - lo > 1) { const long mid = (lo + hi) >> 1; if (row_nodeptr[mid] <= ka) lo = mid; else hi = mid; }
+        row = lo;
+    }
+    const int npad = 8 * NB - n;
+    auto build = [&](long k, int buf) {
+        while (row_nodeptr[row + 1] <= k) row++;
+        const int k1 = klist ? klist[k] : (int)(k - row_nodeptr[row]);
+        const double2* c1 = C1 + (row - r0) * (long)M * nn;
+        double2 h[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = make_double2(0.0, 0.0);
+        for (int m = 0; m < M; m++) {
+            const double2 ph = ptab[(long)m * N + k1];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int e = threadIdx.x + NT * i;
+                if (e < nn) {
+                    const double2 a = c1[(long)m * nn + e];
+                    h[i].x = fma(a.x, ph.x, h[i].x); h[i].x = fma(-a.y, ph.y, h[i].x);
+                    h[i].y = fma(a.x, ph.y, h[i].y); h[i].y = fma(a.y, ph.x, h[i].y);
+                }
+            }
+        }
+        double2* dst = sH + (long)buf * n * LDH;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = threadIdx.x + NT * i;
+            if (e < nn) dst[(e % n) + (e / n) * LDH] = h[i];
+        }
+    };
+    if (ka < kb) build(ka, 0);
+    __syncthreads();
+    for (long k = ka; k < kb; k++) {
+        const int buf = (int)((k - ka) & 1);
+        if (k + 1 < kb) build(k + 1, buf ^ 1);
+        const double2* Hk = sH + (long)buf * n * LDH;
+        const double wt = wnode ? wnode[k] : 1.0;
+        for (int w = warp; w < nw; w += MMA_WARPS) {
+            const double2* sg = sigma ? sigma + (long)w * nn : nullptr;
+            const double2 zz = z[w];
+            double R0[NB][NB], R1[NB][NB], I0[NB][NB], I1[NB][NB];
+            int amaxhi = 0;
+#pragma unroll
+            for (int bj = 0; bj < NB; bj++)
+#pragma unroll
+                for (int bi = 0; bi < NB; bi++) {
+                    const int rw = 8 * bi + g, c0 = 8 * bj + 2 * q, c1i = c0 + 1;
+                    double2 a0 = make_double2(0.0, 0.0), a1 = a0;
+                    if (rw < n && c0 < n) {
+                        a0 = Hk[rw + c0 * LDH];
+                        if (sg) { double2 s0 = sg[rw + (long)c0 * n]; a0.x += s0.x; a0.y += s0.y; }
+                    }
+                    if (rw < n && c1i < n) {
+                        a1 = Hk[rw + c1i * LDH];
+                        if (sg) { double2 s1 = sg[rw + (long)c1i * n]; a1.x += s1.x; a1.y += s1.y; }
+                    }
+                    if (bi == bj) {
+                        if (rw == c0) { if (rw < n) { a0.x -= zz.x; a0.y -= zz.y; } else { a0.x = -1.0; a0.y = 0.0; } }
+                        if (rw == c1i) { if (rw < n) { a1.x -= zz.x; a1.y -= zz.y; } else { a1.x = -1.0; a1.y = 0.0; } }
+                    }
+                    R0[bi][bj] = a0.x; I0[bi][bj] = a0.y; R1[bi][bj] = a1.x; I1[bi][bj] = a1.y;
+                    amaxhi = max(amaxhi, max(max(__double2hiint(a0.x) & 0x7fffffff, __double2hiint(a0.y) & 0x7fffffff),
+                                             max(__double2hiint(a1.x) & 0x7fffffff, __double2hiint(a1.y) & 0x7fffffff)));
+                }
+            int minhi = 0x7ff00000;
+            double2 t = warp_trace_inverse<NB, VAR>(R0, R1, I0, I1, lane, minhi);
+            t.x = -t.x - (double)npad; t.y = -t.y;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) amaxhi = max(amaxhi, __shfl_xor_sync(0xffffffffu, amaxhi, off));
+            if (lane == 0) {
+                const double pmin2 = __hiloint2double(minhi, 0), am = __hiloint2double(amaxhi, 0);
+                if (!(pmin2 > 4e-6 * am * am) || !(isfinite(t.x) && isfinite(t.y))) atomicOr(errflag, 2);
+                acc[w].x += wt * t.x; acc[w].y += wt * t.y;
+            }
+        }
+        __syncthreads();        // buffer buf may be refilled (node k + 2), buffer buf ^ 1 is complete
+    }
+    for (int w = threadIdx.x; w < nw; w += NT) {
+        double sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int wp = 0; wp < MMA_WARPS; wp++) { double2 v = mma_acc[(long)wp * nw + w]; sx += v.x; sy += v.y; }
+        outp[(long)blockIdx.x * nw + w] = make_double2(sx, sy);
+    }
+}
+
 inline bool mma_resolvent_supported(int n) { return n >= 4 && n <= 32; }
 
 // warps per CTA (= per SM): 8 (255 registers) and 12 (168 registers, ~150 spill accesses) measure the same on B200;
@@ -727,6 +841,26 @@ inline void mma_launch_one(const double2* H, const double* wnode, long nk, int n
         resolvent_mma_kernel<NB, W, 0><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
 }
 
+inline size_t mma_fused_smem(int n, int nw) { return ((size_t)nw * 8 + 2 * (size_t)n * (n | 1)) * sizeof(double2); }
+// nodes [n0, n0 + nk) of rows [r0, r1) of a rule; C1 holds the contracted series of those rows (row r0 first)
+inline cudaError_t mma_fused_launch(const double2* C1, const double2* ptab, const long* row_nodeptr, long r0, long r1, const int* klist,
+                                    int N, int M, const double* wnode, long n0, long nk, int n, int nw, const double2* z,
+                                    const double2* sigma, double2* outp, int* errflag, long ncta, int kper, cudaStream_t stream) {
+    const size_t smem = mma_fused_smem(n, nw);
+    switch ((n + 7) / 8) {
+#define ABZ_FUSED_CASE(NBX, V)                                                                                                      \
+    case NBX:                                                                                                                       \
+        resolvent_mma_fused_kernel<NBX, 8, V><<<(unsigned)ncta, 256, smem, stream>>>(C1, ptab, row_nodeptr, r0, r1, klist, N, M,    \
+                                                                                      wnode, n0, nk, n, nw, z, sigma, kper, outp,   \
+                                                                                      errflag);                                     \
+        break;
+        ABZ_FUSED_CASE(1, 0) ABZ_FUSED_CASE(2, 0) ABZ_FUSED_CASE(3, 0) ABZ_FUSED_CASE(4, 1)
+#undef ABZ_FUSED_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 // dynamic shared memory above 48 KB is a per-device opt-in: called for the current device at context creation
 inline cudaError_t mma_resolvent_opt_in() {
     cudaError_t e = cudaSuccess;
@@ -741,6 +875,8 @@ inline cudaError_t mma_resolvent_opt_in() {
     { auto k8 = resolvent_mma_kernel<4, 8, 2>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 2>; set((const void*)k12); }
     { auto k8 = resolvent_mma_kernel<4, 8, 3>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 3>; set((const void*)k12); }
     { auto k8 = resolvent_mma_kernel<4, 8, 4>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 4>; set((const void*)k12); auto k4 = resolvent_mma_kernel<4, 4, 4>; set((const void*)k4); }
+    { auto f1 = resolvent_mma_fused_kernel<1, 8, 0>; set((const void*)f1); auto f2 = resolvent_mma_fused_kernel<2, 8, 0>; set((const void*)f2); }
+    { auto f3 = resolvent_mma_fused_kernel<3, 8, 0>; set((const void*)f3); auto f4 = resolvent_mma_fused_kernel<4, 8, 1>; set((const void*)f4); }
     { auto k4 = resolvent_mma_kernel<4, 4, 0>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 1>; set((const void*)k41); }
     { auto k4 = resolvent_mma_kernel<4, 4, 2>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 3>; set((const void*)k41); }
     return e;
