@@ -1252,7 +1252,7 @@ static int32_t abz_rule_resolvent_sum_impl(abz_ctx* ctx, abz_rule_t rid, int32_t
         const bool fused_mma = !small && fused_mma_env && fkind == ABZ_F_RESOLVENT_TRACE && nw >= 8 && mma_resolvent_supported(n) &&
                                (ctx->resolvent_algo == 0 || ctx->resolvent_algo == 2) && !ctx->force_generic &&
                                !(getenv("ABZ_MMA_TEAM") && atoi(getenv("ABZ_MMA_TEAM")) == 1 && n > 24) &&
-                               mma_resolvent_variant() == ABZ_MMA_DEFAULT_VARIANT && mma_resolvent_warps() == 8 &&
+                               mma_resolvent_variant() == ABZ_MMA_DEFAULT_VARIANT && mma_resolvent_warps() >= 8 &&
                                mma_fused_smem(n, nw) <= 160 * 1024;
         long rows1 = nn * s->M[0], rows2 = rows1 * s->M[1];
         long ncap = (fused || fused_mma) ? ((long)1 << 40) : node_cap_for(ctx, n);

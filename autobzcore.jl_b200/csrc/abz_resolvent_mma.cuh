@@ -682,13 +682,14 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
 // contraction costs 4 M complex FMAs per thread - for nw = 128 that is 17 FP64 instructions per matrix against ~1150 - and reads the
 // M n^2 coefficients of its row from L2; what disappears is the 16 n^2 B per node written and read back by the separate stage-1 kernel.
 // Weighted sums only (mode 0), nw >= MMA_WARPS.
-template <int NB, int MMA_WARPS, int VAR>
+// FULL: norb == 8 NB (no padding rows or columns: the guards of the ragged case are compiled out)
+template <int NB, int MMA_WARPS, int VAR, bool FULL>
 __global__ void __launch_bounds__(MMA_WARPS * 32, 1)
 resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __restrict__ ptab, const long* __restrict__ row_nodeptr,
                            long r0, long r1, const int* __restrict__ klist, int N, int M, const double* __restrict__ wnode, long n0,
                            long nk, int n, int nw, const double2* __restrict__ z, const double2* __restrict__ sigma, int kper,
                            double2* __restrict__ outp, int* __restrict__ errflag) {
-    extern __shared__ double2 mma_acc[];                 // acc[MMA_WARPS][nw] | sH[2][n * LDH]
+    extern __shared__ double2 mma_acc[];                 // acc[MMA_WARPS][nw] | sH[2][n * LDH] | amax[2][MMA_WARPS] (int)
     constexpr int NT = MMA_WARPS * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
@@ -696,6 +697,7 @@ resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __rest
     const int nn = n * n;
     double2* acc = mma_acc + (long)warp * nw;
     double2* sH = mma_acc + (long)MMA_WARPS * nw;
+    int* sAmax = reinterpret_cast<int*>(sH + 2L * n * LDH);     // per buffer and warp: max over H(k) of max(|re|, |im|), high words
     for (int w = lane; w < nw; w += 32) acc[w] = make_double2(0.0, 0.0);
     const long ka = n0 + (long)blockIdx.x * kper;
     const long kb = ka + kper < n0 + nk ? ka + kper : n0 + nk;
@@ -705,18 +707,19 @@ resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __rest
         while (hi - lo > 1) { const long mid = (lo + hi) >> 1; if (row_nodeptr[mid] <= ka) lo = mid; else hi = mid; }
         row = lo;
     }
-    const int npad = 8 * NB - n;
+    const int npad = FULL ? 0 : 8 * NB - n;
+    constexpr int EPT = (64 * NB * NB + NT - 1) / NT;      // matrix entries per thread in the contraction
     auto build = [&](long k, int buf) {
         while (row_nodeptr[row + 1] <= k) row++;
         const int k1 = klist ? klist[k] : (int)(k - row_nodeptr[row]);
         const double2* c1 = C1 + (row - r0) * (long)M * nn;
-        double2 h[4];
+        double2 h[EPT];
 #pragma unroll
-        for (int i = 0; i < 4; i++) h[i] = make_double2(0.0, 0.0);
+        for (int i = 0; i < EPT; i++) h[i] = make_double2(0.0, 0.0);
         for (int m = 0; m < M; m++) {
             const double2 ph = ptab[(long)m * N + k1];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < EPT; i++) {
                 const int e = threadIdx.x + NT * i;
                 if (e < nn) {
                     const double2 a = c1[(long)m * nn + e];
@@ -726,11 +729,17 @@ resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __rest
             }
         }
         double2* dst = sH + (long)buf * n * LDH;
+        int hmax = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < EPT; i++) {
             const int e = threadIdx.x + NT * i;
-            if (e < nn) dst[(e % n) + (e / n) * LDH] = h[i];
+            if (e < nn) {
+                dst[(e % n) + (e / n) * LDH] = h[i];
+                hmax = max(hmax, max(__double2hiint(h[i].x) & 0x7fffffff, __double2hiint(h[i].y) & 0x7fffffff));
+            }
         }
+        hmax = __reduce_max_sync(0xffffffffu, hmax);
+        if (lane == 0) sAmax[buf * MMA_WARPS + warp] = hmax;
     };
     if (ka < kb) build(ka, 0);
     __syncthreads();
@@ -739,38 +748,43 @@ resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __rest
         if (k + 1 < kb) build(k + 1, buf ^ 1);
         const double2* Hk = sH + (long)buf * n * LDH;
         const double wt = wnode ? wnode[k] : 1.0;
+        // the pivot monitor's scale max|a_ij|: once per node from H(k) (the matrix entries are H + Sigma - z: Sigma is added per matrix below)
+        const int hmaxk = __reduce_max_sync(0xffffffffu, sAmax[buf * MMA_WARPS + (lane % MMA_WARPS)]);
         for (int w = warp; w < nw; w += MMA_WARPS) {
             const double2* sg = sigma ? sigma + (long)w * nn : nullptr;
             const double2 zz = z[w];
             double R0[NB][NB], R1[NB][NB], I0[NB][NB], I1[NB][NB];
-            int amaxhi = 0;
+            int amaxhi = max(hmaxk, max(__double2hiint(zz.x) & 0x7fffffff, __double2hiint(zz.y) & 0x7fffffff));
 #pragma unroll
             for (int bj = 0; bj < NB; bj++)
 #pragma unroll
                 for (int bi = 0; bi < NB; bi++) {
                     const int rw = 8 * bi + g, c0 = 8 * bj + 2 * q, c1i = c0 + 1;
                     double2 a0 = make_double2(0.0, 0.0), a1 = a0;
-                    if (rw < n && c0 < n) {
+                    if (FULL || (rw < n && c0 < n)) {
                         a0 = Hk[rw + c0 * LDH];
-                        if (sg) { double2 s0 = sg[rw + (long)c0 * n]; a0.x += s0.x; a0.y += s0.y; }
+                        if (sg) {
+                            double2 s0 = sg[rw + (long)c0 * n]; a0.x += s0.x; a0.y += s0.y;
+                            amaxhi = max(amaxhi, max(__double2hiint(a0.x) & 0x7fffffff, __double2hiint(a0.y) & 0x7fffffff));
+                        }
                     }
-                    if (rw < n && c1i < n) {
+                    if (FULL || (rw < n && c1i < n)) {
                         a1 = Hk[rw + c1i * LDH];
-                        if (sg) { double2 s1 = sg[rw + (long)c1i * n]; a1.x += s1.x; a1.y += s1.y; }
+                        if (sg) {
+                            double2 s1 = sg[rw + (long)c1i * n]; a1.x += s1.x; a1.y += s1.y;
+                            amaxhi = max(amaxhi, max(__double2hiint(a1.x) & 0x7fffffff, __double2hiint(a1.y) & 0x7fffffff));
+                        }
                     }
                     if (bi == bj) {
-                        if (rw == c0) { if (rw < n) { a0.x -= zz.x; a0.y -= zz.y; } else { a0.x = -1.0; a0.y = 0.0; } }
-                        if (rw == c1i) { if (rw < n) { a1.x -= zz.x; a1.y -= zz.y; } else { a1.x = -1.0; a1.y = 0.0; } }
+                        if (rw == c0) { if (FULL || rw < n) { a0.x -= zz.x; a0.y -= zz.y; } else { a0.x = -1.0; a0.y = 0.0; } }
+                        if (rw == c1i) { if (FULL || rw < n) { a1.x -= zz.x; a1.y -= zz.y; } else { a1.x = -1.0; a1.y = 0.0; } }
                     }
                     R0[bi][bj] = a0.x; I0[bi][bj] = a0.y; R1[bi][bj] = a1.x; I1[bi][bj] = a1.y;
-                    amaxhi = max(amaxhi, max(max(__double2hiint(a0.x) & 0x7fffffff, __double2hiint(a0.y) & 0x7fffffff),
-                                             max(__double2hiint(a1.x) & 0x7fffffff, __double2hiint(a1.y) & 0x7fffffff)));
                 }
             int minhi = 0x7ff00000;
             double2 t = warp_trace_inverse<NB, VAR>(R0, R1, I0, I1, lane, minhi);
             t.x = -t.x - (double)npad; t.y = -t.y;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) amaxhi = max(amaxhi, __shfl_xor_sync(0xffffffffu, amaxhi, off));
+            if (sg) amaxhi = __reduce_max_sync(0xffffffffu, amaxhi);
             if (lane == 0) {
                 const double pmin2 = __hiloint2double(minhi, 0), am = __hiloint2double(amaxhi, 0);
                 if (!(pmin2 > 4e-6 * am * am) || !(isfinite(t.x) && isfinite(t.y))) atomicOr(errflag, 2);
@@ -841,23 +855,28 @@ inline void mma_launch_one(const double2* H, const double* wnode, long nk, int n
         resolvent_mma_kernel<NB, W, 0><<<(unsigned)ncta, W * 32, smem, stream>>>(H, wnode, nk, n, nw, z, sigma, kper, mode, outp, errflag);
 }
 
-inline size_t mma_fused_smem(int n, int nw) { return ((size_t)nw * 8 + 2 * (size_t)n * (n | 1)) * sizeof(double2); }
+inline size_t mma_fused_smem(int n, int nw, int W = 12) { return ((size_t)nw * W + 2 * (size_t)n * (n | 1)) * sizeof(double2) + 2 * W * sizeof(int); }
 // nodes [n0, n0 + nk) of rows [r0, r1) of a rule; C1 holds the contracted series of those rows (row r0 first)
 inline cudaError_t mma_fused_launch(const double2* C1, const double2* ptab, const long* row_nodeptr, long r0, long r1, const int* klist,
                                     int N, int M, const double* wnode, long n0, long nk, int n, int nw, const double2* z,
                                     const double2* sigma, double2* outp, int* errflag, long ncta, int kper, cudaStream_t stream) {
-    const size_t smem = mma_fused_smem(n, nw);
+    const int W = mma_resolvent_warps() == 12 && n > 24 ? 12 : 8;
+    const size_t smem = mma_fused_smem(n, nw, W);
+#define ABZ_FUSED_GO(NBX, WX, V, F)                                                                                                 \
+    resolvent_mma_fused_kernel<NBX, WX, V, F><<<(unsigned)ncta, WX * 32, smem, stream>>>(C1, ptab, row_nodeptr, r0, r1, klist, N, M, \
+                                                                                        wnode, n0, nk, n, nw, z, sigma, kper, outp, \
+                                                                                        errflag)
     switch ((n + 7) / 8) {
-#define ABZ_FUSED_CASE(NBX, V)                                                                                                      \
-    case NBX:                                                                                                                       \
-        resolvent_mma_fused_kernel<NBX, 8, V><<<(unsigned)ncta, 256, smem, stream>>>(C1, ptab, row_nodeptr, r0, r1, klist, N, M,    \
-                                                                                      wnode, n0, nk, n, nw, z, sigma, kper, outp,   \
-                                                                                      errflag);                                     \
-        break;
-        ABZ_FUSED_CASE(1, 0) ABZ_FUSED_CASE(2, 0) ABZ_FUSED_CASE(3, 0) ABZ_FUSED_CASE(4, 1)
-#undef ABZ_FUSED_CASE
+        case 1: if (n == 8) ABZ_FUSED_GO(1, 8, 0, true); else ABZ_FUSED_GO(1, 8, 0, false); break;
+        case 2: if (n == 16) ABZ_FUSED_GO(2, 8, 0, true); else ABZ_FUSED_GO(2, 8, 0, false); break;
+        case 3: if (n == 24) ABZ_FUSED_GO(3, 8, 0, true); else ABZ_FUSED_GO(3, 8, 0, false); break;
+        case 4:
+            if (W == 12) { if (n == 32) ABZ_FUSED_GO(4, 12, 1, true); else ABZ_FUSED_GO(4, 12, 1, false); }
+            else { if (n == 32) ABZ_FUSED_GO(4, 8, 1, true); else ABZ_FUSED_GO(4, 8, 1, false); }
+            break;
         default: return cudaErrorInvalidValue;
     }
+#undef ABZ_FUSED_GO
     return cudaGetLastError();
 }
 
@@ -875,8 +894,9 @@ inline cudaError_t mma_resolvent_opt_in() {
     { auto k8 = resolvent_mma_kernel<4, 8, 2>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 2>; set((const void*)k12); }
     { auto k8 = resolvent_mma_kernel<4, 8, 3>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 3>; set((const void*)k12); }
     { auto k8 = resolvent_mma_kernel<4, 8, 4>; set((const void*)k8); auto k12 = resolvent_mma_kernel<4, 12, 4>; set((const void*)k12); auto k4 = resolvent_mma_kernel<4, 4, 4>; set((const void*)k4); }
-    { auto f1 = resolvent_mma_fused_kernel<1, 8, 0>; set((const void*)f1); auto f2 = resolvent_mma_fused_kernel<2, 8, 0>; set((const void*)f2); }
-    { auto f3 = resolvent_mma_fused_kernel<3, 8, 0>; set((const void*)f3); auto f4 = resolvent_mma_fused_kernel<4, 8, 1>; set((const void*)f4); }
+#define ABZ_FUSED_OPT(NBX, WX, V) { auto f = resolvent_mma_fused_kernel<NBX, WX, V, false>; set((const void*)f); auto t = resolvent_mma_fused_kernel<NBX, WX, V, true>; set((const void*)t); }
+    ABZ_FUSED_OPT(1, 8, 0) ABZ_FUSED_OPT(2, 8, 0) ABZ_FUSED_OPT(3, 8, 0) ABZ_FUSED_OPT(4, 8, 1) ABZ_FUSED_OPT(4, 12, 1)
+#undef ABZ_FUSED_OPT
     { auto k4 = resolvent_mma_kernel<4, 4, 0>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 1>; set((const void*)k41); }
     { auto k4 = resolvent_mma_kernel<4, 4, 2>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 3>; set((const void*)k41); }
     return e;
