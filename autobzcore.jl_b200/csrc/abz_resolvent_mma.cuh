@@ -457,7 +457,10 @@ __device__ __forceinline__ double2 warp_trace_inverse_paired(double (&R0)[NB][NB
 // VAR 1: right-looking substitutions - a finished block of V (M) is turned into its fragment once and immediately applied to all
 //        rows above (below) it, so the block products of one step are independent (more DMMA chains in flight, one live fragment
 //        instead of the bV[] / bM[] arrays), and the fragments of M feed the trace as they are made.
-template <int NB, int VAR, bool FF = false>
+// PF = 1 / 2: the B fragments of the LU phase are made one product group AHEAD of their use (ptxas keeps shfl.sync and mma.sync in source
+// order, so a fragment made right before its products exposes the shuffle + select latency to the warp every time): U_{s,j+1} is
+// exchanged before the products of column j (PF >= 1), D_{s+1} right after its inversion, before the rest of step s (PF = 2).
+template <int NB, int VAR, bool FF = false, int PF = 0>
 __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], double (&R1)[NB][NB], double (&I0)[NB][NB],
                                                       double (&I1)[NB][NB], int lane, int& minpiv) {
     const int g = lane >> 2, q = lane & 3;
@@ -468,9 +471,13 @@ __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], doub
     //      latency-bound pivot steps overlap the remaining (independent) trailing-update DMMAs
     if constexpr (FF) inv8_ff(R0[0][0], R1[0][0], I0[0][0], I1[0][0], lane, minpiv);
     else inv8(R0[0][0], R1[0][0], I0[0][0], I1[0][0], lane, minpiv);          // D_0
+    BFrag bDn;
+    if constexpr (PF >= 2) bDn = to_bfrag(R0[0][0], R1[0][0], I0[0][0], I1[0][0], src0, src1, par);
 #pragma unroll
     for (int s = 0; s < NB - 1; s++) {
-        const BFrag bD = to_bfrag(R0[s][s], R1[s][s], I0[s][s], I1[s][s], src0, src1, par);
+        const BFrag bD = PF >= 2 ? bDn : to_bfrag(R0[s][s], R1[s][s], I0[s][s], I1[s][s], src0, src1, par);
+        BFrag bUn;
+        if constexpr (PF >= 1) bUn = to_bfrag(R0[s][s + 1], R1[s][s + 1], I0[s][s + 1], I1[s][s + 1], src0, src1, par);
 #pragma unroll
         for (int i = s + 1; i < NB; i++) {                               // L_is = A_is D_s
             double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
@@ -479,13 +486,17 @@ __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], doub
         }
 #pragma unroll
         for (int j = s + 1; j < NB; j++) {
-            const BFrag bU = to_bfrag(R0[s][j], R1[s][j], I0[s][j], I1[s][j], src0, src1, par);
+            const BFrag bU = PF >= 1 ? bUn : to_bfrag(R0[s][j], R1[s][j], I0[s][j], I1[s][j], src0, src1, par);
+            if constexpr (PF >= 1) {
+                if (j + 1 < NB) bUn = to_bfrag(R0[s][j + 1], R1[s][j + 1], I0[s][j + 1], I1[s][j + 1], src0, src1, par);
+            }
 #pragma unroll
             for (int i = s + 1; i < NB; i++)                             // A_ij -= L_is U_sj
                 bmm<true>(R0[i][j], R1[i][j], I0[i][j], I1[i][j], R0[i][s], R1[i][s], I0[i][s], I1[i][s], bU);
             if (j == s + 1) {                                            // D_{s+1} (look-ahead)
                 if constexpr (FF) inv8_ff(R0[j][j], R1[j][j], I0[j][j], I1[j][j], lane, minpiv);
                 else inv8(R0[j][j], R1[j][j], I0[j][j], I1[j][j], lane, minpiv);
+                if constexpr (PF >= 2) bDn = to_bfrag(R0[j][j], R1[j][j], I0[j][j], I1[j][j], src0, src1, par);
             }
             {                                                            // X_sj = D_s U_sj (replaces U_sj)
                 double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
@@ -683,7 +694,7 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
 // M n^2 coefficients of its row from L2; what disappears is the 16 n^2 B per node written and read back by the separate stage-1 kernel.
 // Weighted sums only (mode 0), nw >= MMA_WARPS.
 // FULL: norb == 8 NB (no padding rows or columns: the guards of the ragged case are compiled out)
-template <int NB, int MMA_WARPS, int VAR, bool FULL>
+template <int NB, int MMA_WARPS, int VAR, bool FULL, int PF = 0>
 __global__ void __launch_bounds__(MMA_WARPS * 32, 1)
 resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __restrict__ ptab, const long* __restrict__ row_nodeptr,
                            long r0, long r1, const int* __restrict__ klist, int N, int M, const double* __restrict__ wnode, long n0,
@@ -782,7 +793,7 @@ resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __rest
                     R0[bi][bj] = a0.x; I0[bi][bj] = a0.y; R1[bi][bj] = a1.x; I1[bi][bj] = a1.y;
                 }
             int minhi = 0x7ff00000;
-            double2 t = warp_trace_inverse<NB, VAR>(R0, R1, I0, I1, lane, minhi);
+            double2 t = warp_trace_inverse<NB, VAR, false, PF>(R0, R1, I0, I1, lane, minhi);
             t.x = -t.x - (double)npad; t.y = -t.y;
             if (sg) amaxhi = __reduce_max_sync(0xffffffffu, amaxhi);
             if (lane == 0) {
@@ -872,7 +883,14 @@ inline cudaError_t mma_fused_launch(const double2* C1, const double2* ptab, cons
         case 3: if (n == 24) ABZ_FUSED_GO(3, 8, 0, true); else ABZ_FUSED_GO(3, 8, 0, false); break;
         case 4:
             if (W == 12) { if (n == 32) ABZ_FUSED_GO(4, 12, 1, true); else ABZ_FUSED_GO(4, 12, 1, false); }
-            else { if (n == 32) ABZ_FUSED_GO(4, 8, 1, true); else ABZ_FUSED_GO(4, 8, 1, false); }
+            else if (n == 32) {
+                // U fragments one product group ahead (PF = 1): 908.6 -> 919.3 k k-points/s on the C4 workload; also prefetching D_{s+1}
+                // (PF = 2) gives the gain back (907.1 k) - profiles/r02_k3fused_timing.log.  ABZ_MMA_PREFETCH = 0 / 2 select the others.
+                static const int pf = getenv("ABZ_MMA_PREFETCH") ? atoi(getenv("ABZ_MMA_PREFETCH")) : 1;
+                if (pf == 0) ABZ_FUSED_GO(4, 8, 1, true);
+                else if (pf == 2) resolvent_mma_fused_kernel<4, 8, 1, true, 2><<<(unsigned)ncta, 256, smem, stream>>>(C1, ptab, row_nodeptr, r0, r1, klist, N, M, wnode, n0, nk, n, nw, z, sigma, kper, outp, errflag);
+                else resolvent_mma_fused_kernel<4, 8, 1, true, 1><<<(unsigned)ncta, 256, smem, stream>>>(C1, ptab, row_nodeptr, r0, r1, klist, N, M, wnode, n0, nk, n, nw, z, sigma, kper, outp, errflag);
+            } else ABZ_FUSED_GO(4, 8, 1, false);
             break;
         default: return cudaErrorInvalidValue;
     }
@@ -897,6 +915,7 @@ inline cudaError_t mma_resolvent_opt_in() {
 #define ABZ_FUSED_OPT(NBX, WX, V) { auto f = resolvent_mma_fused_kernel<NBX, WX, V, false>; set((const void*)f); auto t = resolvent_mma_fused_kernel<NBX, WX, V, true>; set((const void*)t); }
     ABZ_FUSED_OPT(1, 8, 0) ABZ_FUSED_OPT(2, 8, 0) ABZ_FUSED_OPT(3, 8, 0) ABZ_FUSED_OPT(4, 8, 1) ABZ_FUSED_OPT(4, 12, 1)
 #undef ABZ_FUSED_OPT
+    { auto f = resolvent_mma_fused_kernel<4, 8, 1, true, 1>; set((const void*)f); auto t = resolvent_mma_fused_kernel<4, 8, 1, true, 2>; set((const void*)t); }
     { auto k4 = resolvent_mma_kernel<4, 4, 0>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 1>; set((const void*)k41); }
     { auto k4 = resolvent_mma_kernel<4, 4, 2>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 3>; set((const void*)k41); }
     return e;
