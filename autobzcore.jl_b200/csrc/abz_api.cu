@@ -533,7 +533,17 @@ int run_matfun(abz_ctx* ctx, const double2* H, const double* wnode, long nk, int
     if (use_mma) {
         long ncta = 0; int kper_m = 1;
         if (mma_resolvent_plan(n, nk, nw, sm, &ncta, &kper_m) == 0) {
-            if (mode == 0) {
+            static const int fused_mma_env = getenv("ABZ_FUSED_MMA") ? atoi(getenv("ABZ_FUSED_MMA")) : 1;
+            if (mode == 0 && fused_mma_env && nw >= 8 && mma_resolvent_variant() == ABZ_MMA_DEFAULT_VARIANT && mma_resolvent_warps() >= 8 &&
+                mma_fused_smem(n, nw) <= 160 * 1024) {
+                // K3-fused in direct mode: every node's H(k) is staged once in shared memory for all of its frequencies
+                CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
+                CU(ctx, mma_fused_launch(H, nullptr, nullptr, 0, 0, nullptr, 0, 0, wnode, 0, nk, n, nw, z, sigma, ctx->partial.as<double2>(), ef,
+                                         ncta, kper_m, ctx->stream));
+                ctx->launches++;
+                reduce_partials_kernel<<<nw, 256, 0, ctx->stream>>>(ctx->partial.as<double2>(), ncta, nw, 1.0, ctx->acc.as<double2>());
+                LAUNCH_CHECK(ctx, "reduce_partials_kernel");
+            } else if (mode == 0) {
                 CU(ctx, ctx->partial.reserve((size_t)ncta * nw * sizeof(double2)));
                 CU(ctx, mma_resolvent_launch(H, wnode, nk, n, nw, z, sigma, 0, ctx->partial.as<double2>(), ef, ncta, kper_m, ctx->stream));
                 ctx->launches++;

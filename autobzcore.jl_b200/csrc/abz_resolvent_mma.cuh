@@ -694,7 +694,8 @@ resolvent_mma_kernel(const double2* __restrict__ H, const double* __restrict__ w
 // M n^2 coefficients of its row from L2; what disappears is the 16 n^2 B per node written and read back by the separate stage-1 kernel.
 // Weighted sums only (mode 0), nw >= MMA_WARPS.
 // FULL: norb == 8 NB (no padding rows or columns: the guards of the ragged case are compiled out)
-template <int NB, int MMA_WARPS, int VAR, bool FULL, int PF = 0>
+// DIRECT: materialised rule - C1 IS H(k), node-major from node n0 on, and the contraction is a copy into the shared-memory buffer
+template <int NB, int MMA_WARPS, int VAR, bool FULL, int PF = 0, bool DIRECT = false>
 __global__ void __launch_bounds__(MMA_WARPS * 32, 1)
 resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __restrict__ ptab, const long* __restrict__ row_nodeptr,
                            long r0, long r1, const int* __restrict__ klist, int N, int M, const double* __restrict__ wnode, long n0,
@@ -713,7 +714,7 @@ resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __rest
     const long ka = n0 + (long)blockIdx.x * kper;
     const long kb = ka + kper < n0 + nk ? ka + kper : n0 + nk;
     long row = r0;
-    {   // row of the first node: row_nodeptr[row] <= ka < row_nodeptr[row + 1]
+    if constexpr (!DIRECT) {   // row of the first node: row_nodeptr[row] <= ka < row_nodeptr[row + 1]
         long lo = r0, hi = r1;
         while (hi - lo > 1) { const long mid = (lo + hi) >> 1; if (row_nodeptr[mid] <= ka) lo = mid; else hi = mid; }
         row = lo;
@@ -721,12 +722,20 @@ resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __rest
     const int npad = FULL ? 0 : 8 * NB - n;
     constexpr int EPT = (64 * NB * NB + NT - 1) / NT;      // matrix entries per thread in the contraction
     auto build = [&](long k, int buf) {
-        while (row_nodeptr[row + 1] <= k) row++;
-        const int k1 = klist ? klist[k] : (int)(k - row_nodeptr[row]);
-        const double2* c1 = C1 + (row - r0) * (long)M * nn;
         double2 h[EPT];
 #pragma unroll
         for (int i = 0; i < EPT; i++) h[i] = make_double2(0.0, 0.0);
+        if constexpr (DIRECT) {
+            const double2* src = C1 + (k - n0) * (long)nn;
+#pragma unroll
+            for (int i = 0; i < EPT; i++) {
+                const int e = threadIdx.x + NT * i;
+                if (e < nn) h[i] = src[e];
+            }
+        } else {
+        while (row_nodeptr[row + 1] <= k) row++;
+        const int k1 = klist ? klist[k] : (int)(k - row_nodeptr[row]);
+        const double2* c1 = C1 + (row - r0) * (long)M * nn;
         for (int m = 0; m < M; m++) {
             const double2 ph = ptab[(long)m * N + k1];
 #pragma unroll
@@ -738,6 +747,7 @@ resolvent_mma_fused_kernel(const double2* __restrict__ C1, const double2* __rest
                     h[i].y = fma(a.x, ph.y, h[i].y); h[i].y = fma(a.y, ph.x, h[i].y);
                 }
             }
+        }
         }
         double2* dst = sH + (long)buf * n * LDH;
         int hmax = 0;
@@ -871,8 +881,23 @@ inline size_t mma_fused_smem(int n, int nw, int W = 12) { return ((size_t)nw * W
 inline cudaError_t mma_fused_launch(const double2* C1, const double2* ptab, const long* row_nodeptr, long r0, long r1, const int* klist,
                                     int N, int M, const double* wnode, long n0, long nk, int n, int nw, const double2* z,
                                     const double2* sigma, double2* outp, int* errflag, long ncta, int kper, cudaStream_t stream) {
-    const int W = mma_resolvent_warps() == 12 && n > 24 ? 12 : 8;
+    const int W = mma_resolvent_warps() == 12 && n > 24 && ptab ? 12 : 8;
     const size_t smem = mma_fused_smem(n, nw, W);
+    if (!ptab) {            // direct mode (materialised H)
+#define ABZ_DIRECT_GO(NBX, V, F, P)                                                                                                  \
+    resolvent_mma_fused_kernel<NBX, 8, V, F, P, true><<<(unsigned)ncta, 256, smem, stream>>>(C1, ptab, row_nodeptr, r0, r1, klist, N, M, \
+                                                                                            wnode, n0, nk, n, nw, z, sigma, kper,   \
+                                                                                            outp, errflag)
+        switch ((n + 7) / 8) {
+            case 1: if (n == 8) ABZ_DIRECT_GO(1, 0, true, 0); else ABZ_DIRECT_GO(1, 0, false, 0); break;
+            case 2: if (n == 16) ABZ_DIRECT_GO(2, 0, true, 0); else ABZ_DIRECT_GO(2, 0, false, 0); break;
+            case 3: if (n == 24) ABZ_DIRECT_GO(3, 0, true, 0); else ABZ_DIRECT_GO(3, 0, false, 0); break;
+            case 4: if (n == 32) ABZ_DIRECT_GO(4, 1, true, 1); else ABZ_DIRECT_GO(4, 1, false, 0); break;
+            default: return cudaErrorInvalidValue;
+        }
+#undef ABZ_DIRECT_GO
+        return cudaGetLastError();
+    }
 #define ABZ_FUSED_GO(NBX, WX, V, F)                                                                                                 \
     resolvent_mma_fused_kernel<NBX, WX, V, F><<<(unsigned)ncta, WX * 32, smem, stream>>>(C1, ptab, row_nodeptr, r0, r1, klist, N, M, \
                                                                                         wnode, n0, nk, n, nw, z, sigma, kper, outp, \
@@ -916,6 +941,9 @@ inline cudaError_t mma_resolvent_opt_in() {
     ABZ_FUSED_OPT(1, 8, 0) ABZ_FUSED_OPT(2, 8, 0) ABZ_FUSED_OPT(3, 8, 0) ABZ_FUSED_OPT(4, 8, 1) ABZ_FUSED_OPT(4, 12, 1)
 #undef ABZ_FUSED_OPT
     { auto f = resolvent_mma_fused_kernel<4, 8, 1, true, 1>; set((const void*)f); auto t = resolvent_mma_fused_kernel<4, 8, 1, true, 2>; set((const void*)t); }
+#define ABZ_DIRECT_OPT(NBX, V, P) { auto f = resolvent_mma_fused_kernel<NBX, 8, V, false, 0, true>; set((const void*)f); auto t = resolvent_mma_fused_kernel<NBX, 8, V, true, P, true>; set((const void*)t); }
+    ABZ_DIRECT_OPT(1, 0, 0) ABZ_DIRECT_OPT(2, 0, 0) ABZ_DIRECT_OPT(3, 0, 0) ABZ_DIRECT_OPT(4, 1, 1)
+#undef ABZ_DIRECT_OPT
     { auto k4 = resolvent_mma_kernel<4, 4, 0>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 1>; set((const void*)k41); }
     { auto k4 = resolvent_mma_kernel<4, 4, 2>; set((const void*)k4); auto k41 = resolvent_mma_kernel<4, 4, 3>; set((const void*)k41); }
     return e;

@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NORB, RMAX, NPT, NW = 32, 8, 256, 128
+FUSED_DRAM_BYTES_PER_KPOINT = 1100.0    # placeholder until the ncu capture of the fused kernel is read (profiles/r02_ncu_full_fused_raw.csv)
 METRIC = "k-points/sec (H(k)+resolvent)"
 
 
@@ -425,11 +426,15 @@ def main():
         # dominant kernel: the resolvent (matfun phase).  One launch = one chunk of nodes x 128 frequencies.
         mat_s = ev_mat * 1e-3 / args.steps
         achieved = f_res * nodes_rank / mat_s * 1e-12
-        roof = {"bound": "tensor", "kernel": "resolvent (FP64, DMMA/DFMA pipe)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+        fused = os.environ.get("ABZ_FUSED_MMA", "1") != "0" and args.algo in (0, 2)
+        roof = {"bound": "tensor", "kernel": "resolvent_mma_fused_kernel (FP64, DMMA/DFMA pipe; stage 1 of the Fourier evaluation folded in)" if fused
+                else "resolvent (FP64, DMMA/DFMA pipe)", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
-                # dram__bytes_read+write of one resolvent launch, from the ncu --set full capture in profiles/ (16.68 kB per k-point
-                # = the 16 n^2 B of H(k) read once for all 128 frequencies; no re-reads), scaled to this run's launch size
-                "traffic": 16678.0 * min(nodes_rank, 262144), "traffic_source": "profiles/r01_ncu_full_resolvent_mma_raw.csv",
+                # dram__bytes_read+write of one resolvent launch, from the ncu --set full capture in profiles/, scaled to this run's
+                # launch size.  Fused: the C1 rows (M n^2 16 B per (k2,k3) row = 1.09 kB per k-point at N = 256) are read once, H(k) never
+                # exists in HBM.  Unfused: 16.68 kB per k-point = the 16 n^2 B of H(k) read once for all 128 frequencies.
+                "traffic": (FUSED_DRAM_BYTES_PER_KPOINT * nodes_rank) if fused else 16678.0 * min(nodes_rank, 262144),
+                "traffic_source": "profiles/r02_ncu_full_fused_raw.csv" if fused else "profiles/r01_ncu_full_resolvent_mma_raw.csv",
                 "peak_source": "cuBLAS ZGEMM 4096^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 entry; a 4 s sustained ZGEMM "
                                "measures the same 36.8 TFLOP/s, profiles/r01_fp64_peaks.json)",
                 "algorithmic_flops_per_kpoint": {"fourier": f_four, "resolvent": f_res},

@@ -23,6 +23,17 @@ if "contract" in which:
     print("contract", R.resolvent_sum(z)[:2], ctx.last_timings())
     R.close(); S.close()
 
+if "fused" in which:
+    # C4 shape streamed (not materialised): stages 3 / 2, then K3-fused (stage 1 folded into the DMMA resolvent kernel), 128 frequencies
+    # as in the bench (the kernel synchronises its 8 warps once per node: nw / 8 matrices per warp between barriers)
+    H, lo = ab.synthetic.wannier_hamiltonian(32, 8)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    R = L.DeviceRule(ctx, S, 256, k3_lo=0, k3_hi=1)
+    ext = ab.synthetic.band_extent(H)
+    z = np.linspace(-0.2 * ext, 0.2 * ext, 128) + 1j * 0.01 * ext
+    print("fused", R.resolvent_sum(z)[:2], ctx.last_timings())
+    R.close(); S.close()
+
 if "small" in which:
     fs = ab.FourierSeries(Hs, period=1.0, lo=los, norb=3)
     f = ab.FourierIntegrand(ab.gloc_trace_integrand, fs, eta=1e-2)
