@@ -27,7 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NORB, RMAX, NPT, NW = 32, 8, 256, 128
-FUSED_DRAM_BYTES_PER_KPOINT = 1100.0    # placeholder until the ncu capture of the fused kernel is read (profiles/r02_ncu_full_fused_raw.csv)
+FUSED_DRAM_BYTES_PER_KPOINT = 1177.5    # (71.92 MB read + 5.25 MB written) / 65 536 k-points of one launch, profiles/r02_ncu_full_fused_raw.csv
 METRIC = "k-points/sec (H(k)+resolvent)"
 
 
@@ -166,7 +166,7 @@ def oracle_plane_sum(orc, So, N, z, k3):
 
 def parity_check(ctx, S, H, lo, z, k3):
     """Parity evidence carried by the bench line itself: one whole k3 plane of the timed workload (same series, same full-grid
-    rule interface and kernels as the timed steps) at 4 of the 128 frequencies, GPU against the CPU oracle."""
+    rule interface, kernels and frequency count as the timed steps), 4 of the 128 frequencies compared, GPU against the CPU oracle."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
     from autobz_b200 import _lib as L
@@ -174,7 +174,9 @@ def parity_check(ctx, S, H, lo, z, k3):
     zi = [0, NW // 3, (2 * NW) // 3, NW - 1]
     z4 = np.ascontiguousarray(z[zi])
     Rc = L.DeviceRule(ctx, S, NPT, k3_lo=k3, k3_hi=k3 + 1)
-    got = Rc.resolvent_sum(z4, scale=1.0 / NPT ** 3)
+    # the GPU runs the plane with ALL frequencies - the timed step's kernel configuration (the fused kernel serves nw >= 8) - and the
+    # oracle checks 4 of them
+    got = Rc.resolvent_sum(np.ascontiguousarray(z), scale=1.0 / NPT ** 3)[zi]
     Rc.close()
     t0 = time.time()
     ref = oracle_plane_sum(orc, orc.Series(H, lo), NPT, z4, k3)

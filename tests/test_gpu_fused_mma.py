@@ -2,8 +2,8 @@
 contraction stage folded in (H(k) = sum_m C1[row][m] e^{2 pi i k1 R_m} formed per node in shared memory, never written to HBM).
 It serves streamed (not materialised) rules with 4 <= norb <= 32 and at least 8 frequencies - the headline workload's shape.
 Every case is compared with the CPU oracle (src/fourier.jl:127-164 + the docs' `tr(inv(...))` integrand restated in
-oracle/autobz_oracle.c); the unfused path (ABZ_FUSED_MMA=0 in a fresh process is not needed: a materialised rule takes the
-separate stage-1 kernel + K3-fast) must agree with the fused one.
+oracle/autobz_oracle.c); a materialised rule (separate stage-1 kernel, then the same kernel in its direct mode: H(k) copied
+into the shared-memory buffer) must agree with the streamed one.
 
 Tolerances: rule sums <= 1e-11 relative."""
 import numpy as np
