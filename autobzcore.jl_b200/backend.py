@@ -135,8 +135,8 @@ class DeviceRule:
 class DeviceBackend:
     """iai_engine: "native" (default) runs IAI's adaptive control flow in the library's C++ host engine
     (abz_iai_solve, one call per solve); "python" drives abz_nest_* round by round from iai.NestedGK.
-    iai_device_leaves: run each innermost 1-D adaptive integral entirely on the device (norb <= 3);
-    iai_device_middles: in 3-d solves also each middle integral (one CTA per node of the outermost panels).
+    iai_device_leaves: run each innermost 1-D adaptive integral entirely on the device (norb <= 6);
+    iai_device_middles: in 3-d solves also each middle integral (one CTA pair per node of the outermost panels; norb <= 5).
     iai_speculate: look-ahead on the outermost integral (two bisections per device round; same decisions and numevals)."""
 
     def __init__(self, device=None, ctx=None, iai_engine="native", iai_device_leaves=True, iai_device_middles=True, iai_speculate=True):

@@ -97,6 +97,9 @@ struct Nest {
 };
 
 struct Chunk { long p0, p1, r0, r1; };
+// IAI kernels that evaluate the innermost series and the integrand per thread (nest_*_small, iai_leaf, iai_mid): norb <= IAI_SMALL_MAXN
+// (closed-form adjugate up to 3, in-register pivoted Gauss-Jordan up to 6); rule sums keep their own n <= 3 fused path
+constexpr int IAI_SMALL_MAXN = 6;
 
 // one in-flight round of the IAI engine (abz_iai_engine.hpp "lanes"): its own stream, staging and scratch buffers
 struct IaiLane {
@@ -690,6 +693,9 @@ cudaError_t opt_in_dynamic_smem() {
     { auto k = resolvent_gjreg_matrix_kernel<64, 16, 8, 2>; set((const void*)k, 64 * 1024); }
     ABZ_OPT_IN(eig_jacobi_kernel, 200 * 1024);
     ABZ_OPT_IN(eig_jacobi_vel_kernel, 200 * 1024);
+    ABZ_OPT_IN(nest_panel_small_kernel<4>, 160 * 1024); ABZ_OPT_IN(nest_panel_small_kernel<5>, 160 * 1024); ABZ_OPT_IN(nest_panel_small_kernel<6>, 160 * 1024);
+    ABZ_OPT_IN(iai_leaf_kernel<4>, 160 * 1024); ABZ_OPT_IN(iai_leaf_kernel<5>, 160 * 1024); ABZ_OPT_IN(iai_leaf_kernel<6>, 160 * 1024);
+    ABZ_OPT_IN(iai_mid_kernel<4>, 200 * 1024); ABZ_OPT_IN(iai_mid_kernel<5>, 200 * 1024); ABZ_OPT_IN(iai_mid_kernel<6>, 200 * 1024);
     ABZ_OPT_IN(nest_panel_small_kernel<1>, 160 * 1024);
     ABZ_OPT_IN(nest_panel_small_kernel<2>, 160 * 1024);
     ABZ_OPT_IN(nest_panel_small_kernel<3>, 160 * 1024);
@@ -1852,12 +1858,12 @@ static int32_t abz_nest_eval_impl(abz_ctx* ctx, abz_nest_t nid, int64_t npts, co
     const double2* dsig = sigma ? ctx->sigbuf.as<double2>() : nullptr;
     double2* yd = ctx->tmp_c.as<double2>();
     int* ef = ctx->errflag.as<int>();
-    if (n <= 3) {
+    if (n <= IAI_SMALL_MAXN) {
         unsigned g = (unsigned)((npts + 127) / 128);
 #define NEST_LAUNCH(NORB) \
     nest_eval_small_kernel<NORB><<<g, 128, 0, ctx->stream>>>(L1, stride, dslot, ctx->tmp_a.as<double>(), npts, s->M[0], s->lo[0], \
                                                             s->period[0], fkind, zz, dsig, yd, ef)
-        if (n == 1) NEST_LAUNCH(1); else if (n == 2) NEST_LAUNCH(2); else NEST_LAUNCH(3);
+        switch (s->n) { case 1: NEST_LAUNCH(1); break; case 2: NEST_LAUNCH(2); break; case 3: NEST_LAUNCH(3); break; case 4: NEST_LAUNCH(4); break; case 5: NEST_LAUNCH(5); break; default: NEST_LAUNCH(6); break; }
 #undef NEST_LAUNCH
         LAUNCH_CHECK(ctx, "nest_eval_small_kernel");
     } else {
@@ -2065,7 +2071,7 @@ struct IaiDeviceBackend {
 #define PANEL_LAUNCH(NORB)                                                                                               \
     nest_panel_small_kernel<NORB><<<g, 128, (size_t)8 * s->M[0] * NORB * NORB * sizeof(double2), st>>>(L1, stride, dD + o_sa, dD + o_sb, sslot, (long)ns, s->M[0], s->lo[0], \
                                                              s->period[0], fkind, vkind, z, dsig, la, lb, dout, ef)
-            if (n == 1) PANEL_LAUNCH(1); else if (n == 2) PANEL_LAUNCH(2); else PANEL_LAUNCH(3);
+            switch (s->n) { case 1: PANEL_LAUNCH(1); break; case 2: PANEL_LAUNCH(2); break; case 3: PANEL_LAUNCH(3); break; case 4: PANEL_LAUNCH(4); break; case 5: PANEL_LAUNCH(5); break; default: PANEL_LAUNCH(6); break; }
 #undef PANEL_LAUNCH
             LAUNCH_CHECK(ctx, "nest_panel_small_kernel");
         }
@@ -2184,14 +2190,14 @@ struct IaiDeviceBackend {
         const long stride = has_slots ? nn * s->M[0] : 0;
         if (ns) {
             const long* sslot = has_slots ? dL + o_ss : nullptr;
-            if (n <= 3) {
+            if (n <= IAI_SMALL_MAXN && (n <= 3 || (size_t)8 * s->M[0] * n * n * sizeof(double2) <= 160 * 1024)) {
                 unsigned g = (unsigned)((ns + 7) / 8);
                 if ((size_t)8 * s->M[0] * n * n * sizeof(double2) > 160 * 1024)
                     return fail(ctx, ABZ_E_UNSUPPORTED, "series has too many coefficients per dimension for the IAI panel kernel");
 #define PANEL_LAUNCH(NORB)                                                                                               \
     nest_panel_small_kernel<NORB><<<g, 128, (size_t)8 * s->M[0] * NORB * NORB * sizeof(double2), ctx->stream>>>(L1, stride, dD + o_sa, dD + o_sb, sslot, (long)ns, s->M[0], s->lo[0], \
                                                              s->period[0], fkind, vkind, z, dsig, la, lb, dout, ef)
-                if (n == 1) PANEL_LAUNCH(1); else if (n == 2) PANEL_LAUNCH(2); else PANEL_LAUNCH(3);
+                switch (s->n) { case 1: PANEL_LAUNCH(1); break; case 2: PANEL_LAUNCH(2); break; case 3: PANEL_LAUNCH(3); break; case 4: PANEL_LAUNCH(4); break; case 5: PANEL_LAUNCH(5); break; default: PANEL_LAUNCH(6); break; }
 #undef PANEL_LAUNCH
                 LAUNCH_CHECK(ctx, "nest_panel_small_kernel");
             } else {
@@ -2217,12 +2223,12 @@ struct IaiDeviceBackend {
             }
         }
         if (nt) {
-            if (n > 3 || !has_slots) return fail(ctx, ABZ_E_UNSUPPORTED, "device-side innermost integrals need norb <= 3 and ndim >= 2");
+            if (n > IAI_SMALL_MAXN || !has_slots) return fail(ctx, ABZ_E_UNSUPPORTED, "device-side innermost integrals need norb <= 6 and ndim >= 2");
             rc = launch_leaf(dD + o_ta, dD + o_tb, dD + o_tt, dL + o_ts, (long)nt, dout + 4 * ns, ctx->stream, ctx->tmp_d);
             if (rc) return rc;
         }
         if (nm) {
-            if (n > 3) return fail(ctx, ABZ_E_UNSUPPORTED, "device-side middle integrals need norb <= 3");
+            if (n > IAI_SMALL_MAXN) return fail(ctx, ABZ_E_UNSUPPORTED, "device-side middle integrals need norb <= 6");
             rc = launch_mid(dD + o_ma, dD + o_mb, dD + o_mt, dL + o_ms, (long)nm, dout + 4 * ns + 4 * nt, ctx->stream, ctx->tmp_c);
             if (rc) return rc;
         }
@@ -2248,7 +2254,7 @@ struct IaiDeviceBackend {
                                                                     s->M[0], s->lo[0], s->period[0], s->M[1], s->lo[1], s->period[1], fkind, vkind, z, \
                                                                     dsig, la, lb, rtol, (long long)maxevals, spill, spill_cap, out, \
                                                                     ctx->errflag.as<int>())
-        if (s->n == 1) MID_LAUNCH(1); else if (s->n == 2) MID_LAUNCH(2); else MID_LAUNCH(3);
+        switch (s->n) { case 1: MID_LAUNCH(1); break; case 2: MID_LAUNCH(2); break; case 3: MID_LAUNCH(3); break; case 4: MID_LAUNCH(4); break; case 5: MID_LAUNCH(5); break; default: MID_LAUNCH(6); break; }
 #undef MID_LAUNCH
         LAUNCH_CHECK(ctx, "iai_mid_kernel");
         return ABZ_OK;
@@ -2269,7 +2275,7 @@ struct IaiDeviceBackend {
     iai_leaf_kernel<NORB><<<g, LEAF_WARPS * 32, (size_t)LEAF_WARPS * s->M[0] * NORB * NORB * sizeof(double2), st>>>(nst->L1, stride, ta, tb, tt, ts, nt, s->M[0], s->lo[0], s->period[0], \
                                                                  fkind, vkind, z, dsig, la, lb, rtol, (long long)maxevals, spill, spill_cap, out, \
                                                                  ctx->errflag.as<int>())
-        if (s->n == 1) LEAF_LAUNCH(1); else if (s->n == 2) LEAF_LAUNCH(2); else LEAF_LAUNCH(3);
+        switch (s->n) { case 1: LEAF_LAUNCH(1); break; case 2: LEAF_LAUNCH(2); break; case 3: LEAF_LAUNCH(3); break; case 4: LEAF_LAUNCH(4); break; case 5: LEAF_LAUNCH(5); break; default: LEAF_LAUNCH(6); break; }
 #undef LEAF_LAUNCH
         LAUNCH_CHECK(ctx, "iai_leaf_kernel");
         return ABZ_OK;
@@ -2340,8 +2346,16 @@ static int32_t iai_solve_impl(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
     be.lb = abz_iai::cplx{lin ? lin[2] : 0.0, lin ? lin[3] : 0.0};
     be.rtol = rtol; be.maxevals = maxevals;
     be.xfn = exchange; be.xuser = exchange_user;
-    const bool leaf = (flags & (ABZ_IAI_DEVICE_LEAVES | ABZ_IAI_DEVICE_MIDDLES)) && s->n <= 3 && nst->ndim >= 2;
-    const bool mid = leaf && (flags & ABZ_IAI_DEVICE_MIDDLES) && nst->ndim == 3 && lkind != 2;
+    // device-side integrals: norb <= 6 and the per-warp copies of the 1-D series must fit the kernels' shared memory (otherwise the
+    // host-driven panels serve the solve: same decisions, more rounds)
+    const size_t coef1 = (size_t)s->M[0] * s->n * s->n * sizeof(double2);
+    const bool small_ok = s->n <= IAI_SMALL_MAXN && (size_t)8 * coef1 <= 160 * 1024;
+    const bool leaf = (flags & (ABZ_IAI_DEVICE_LEAVES | ABZ_IAI_DEVICE_MIDDLES)) && small_ok && nst->ndim >= 2 &&
+                      (size_t)LEAF_WARPS * coef1 <= 160 * 1024;
+    // (norb = 6: the 36 complex entries of a node's matrix exceed the 128 registers of the 512-thread middle-integral CTAs - measured
+    //  0.45 s against 0.20 s with device-side innermost integrals only, profiles/r02_iai_norb6_timing.log)
+    const bool mid = leaf && (flags & ABZ_IAI_DEVICE_MIDDLES) && nst->ndim == 3 && lkind != 2 && s->n <= 5 &&
+                     sizeof(MidShared) + (size_t)MID_WARPS * (coef1 + (size_t)s->M[1] * sizeof(double2)) <= 200 * 1024;
     be.lkind = lkind;
     for (int d = 0; d < 3; d++) { be.lim_a[d] = lims.a[d]; be.lim_b[d] = lims.b[d]; }
     const long launches0 = ctx->launches;
@@ -2349,7 +2363,7 @@ static int32_t iai_solve_impl(abz_ctx* ctx, abz_nest_t nid, int32_t lkind, const
         // bound by the dependent chain of its deepest innermost integral); ABZ_IAI_LANES overrides
         static const int env_lanes = getenv("ABZ_IAI_LANES") ? atoi(getenv("ABZ_IAI_LANES")) : 0;
         const int want = env_lanes > 0 ? std::min(env_lanes, 16) : ctx->iai_lanes_opt;
-        rc = be.init_lanes((s->n <= 3 && nst->ndim >= 2 && nranks == 1) ? want : 1);   // sharded solves keep one round at a time
+        rc = be.init_lanes((small_ok && nst->ndim >= 2 && nranks == 1) ? want : 1);   // sharded solves keep one round at a time
         if (rc) return rc;
     }
     int64_t rounds0 = 0;

@@ -236,6 +236,61 @@ __device__ __forceinline__ double2 small_resolvent_trace(const double2 (&h)[NORB
             if (i == j) { v.x += z.x; v.y += z.y; }
             a[i + j * NORB] = v;
         }
+    if constexpr (NORB > 3) {
+        // 4 <= norb <= SMALL_MAXN (device-side IAI integrals): in-place Gauss-Jordan inversion with partial pivoting in the registers of
+        // ONE thread - every index below is a compile-time constant (full unrolling), the data-dependent pivot row is brought up by
+        // predicated exchanges, and the row permutation is undone on the columns at the end (A^-1 = (PA)^-1 P).  Julia's `inv` of an
+        // SMatrix larger than 3 x 3 is the pivoted LU as well.
+        int perm[NORB];
+#pragma unroll
+        for (int p = 0; p < NORB; p++) {
+            int r = p;
+            double best = fma(a[p + p * NORB].x, a[p + p * NORB].x, a[p + p * NORB].y * a[p + p * NORB].y);
+#pragma unroll
+            for (int i = p + 1; i < NORB; i++) {
+                const double m = fma(a[i + p * NORB].x, a[i + p * NORB].x, a[i + p * NORB].y * a[i + p * NORB].y);
+                if (m > best) { best = m; r = i; }
+            }
+            perm[p] = r;
+#pragma unroll
+            for (int i = p + 1; i < NORB; i++) {
+                const bool sw = (r == i);
+#pragma unroll
+                for (int j = 0; j < NORB; j++) {
+                    const double2 x = a[p + j * NORB], y = a[i + j * NORB];
+                    a[p + j * NORB] = sw ? y : x; a[i + j * NORB] = sw ? x : y;
+                }
+            }
+            const double2 piv = crecip_fast(a[p + p * NORB]);
+            a[p + p * NORB] = make_double2(1.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < NORB; j++) a[p + j * NORB] = cmul(a[p + j * NORB], piv);
+#pragma unroll
+            for (int i = 0; i < NORB; i++) {
+                if (i == p) continue;
+                const double2 f = a[i + p * NORB];
+                a[i + p * NORB] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int j = 0; j < NORB; j++) a[i + j * NORB] = csub(a[i + j * NORB], cmul(f, a[p + j * NORB]));
+            }
+        }
+#pragma unroll
+        for (int p = NORB - 1; p >= 0; p--) {
+#pragma unroll
+            for (int i = p + 1; i < NORB; i++) {
+                const bool sw = (perm[p] == i);
+#pragma unroll
+                for (int k = 0; k < NORB; k++) {
+                    const double2 x = a[k + p * NORB], y = a[k + i * NORB];
+                    a[k + p * NORB] = sw ? y : x; a[k + i * NORB] = sw ? x : y;
+                }
+            }
+        }
+        double2 t = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int d = 0; d < NORB; d++) { t.x += a[d * (NORB + 1)].x; t.y += a[d * (NORB + 1)].y; }
+        return t;
+    }
     if (NORB == 1) return crecip_fast(a[0]);
     if (NORB == 2) {
         double2 det = csub(cmul(a[0], a[3]), cmul(a[1], a[2]));

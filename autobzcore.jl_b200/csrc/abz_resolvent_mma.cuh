@@ -512,6 +512,67 @@ __device__ __forceinline__ double2 warp_trace_inverse(double (&R0)[NB][NB], doub
         if (2 * q == g) { tr += R0[s][s]; ti += I0[s][s]; }
         if (2 * q + 1 == g) { tr += R1[s][s]; ti += I1[s][s]; }
     }
+    if constexpr (VAR == 1 && PF >= 3) {
+        // The right-looking substitutions of VAR 1 with every fragment made AHEAD of its products: the block that becomes final first
+        // (row t-1 of a V column, row t+1 of an M column) is updated first and exchanged while the remaining products of the step issue.
+        // Every block still receives its terms in the same order: bit-identical to VAR 1.
+#define ABZ_B(i, j) R0[i][j], R1[i][j], I0[i][j], I1[i][j]
+#pragma unroll
+        for (int jv = NB - 1; jv >= 1; jv--) {
+            const BFrag bD = to_bfrag(ABZ_B(jv, jv), src0, src1, par);
+            BFrag bV;
+            {   // V'_{iv,jv} = -X_{iv,jv} D_jv, row jv-1 first (final at once: no t between jv-1 and jv)
+                double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
+                bmm<true>(cr0, cr1, ci0, ci1, ABZ_B(jv - 1, jv), bD);
+                R0[jv - 1][jv] = cr0; R1[jv - 1][jv] = cr1; I0[jv - 1][jv] = ci0; I1[jv - 1][jv] = ci1;
+                if (jv - 1 >= 1) bV = to_bfrag(ABZ_B(jv - 1, jv), src0, src1, par);
+            }
+#pragma unroll
+            for (int iv = jv - 2; iv >= 0; iv--) {
+                double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
+                bmm<true>(cr0, cr1, ci0, ci1, ABZ_B(iv, jv), bD);
+                R0[iv][jv] = cr0; R1[iv][jv] = cr1; I0[iv][jv] = ci0; I1[iv][jv] = ci1;
+            }
+#pragma unroll
+            for (int t = jv - 1; t >= 1; t--) {                          // bV = fragment of the final V_{t,jv}
+                bmm<true>(ABZ_B(t - 1, jv), ABZ_B(t - 1, t), bV);        // V_{t-1,jv} is final after this term
+                BFrag bVn;
+                if (t - 1 >= 1) bVn = to_bfrag(ABZ_B(t - 1, jv), src0, src1, par);
+#pragma unroll
+                for (int iv = t - 2; iv >= 0; iv--) bmm<true>(ABZ_B(iv, jv), ABZ_B(iv, t), bV);
+                if (t - 1 >= 1) bV = bVn;
+            }
+        }
+        // M = L~^-1: every strictly lower block starts as -L (all columns negated up front, so the left operands L_{im,t} of the
+        // updates below are read with the opposite sign: C += (-L) b)
+#pragma unroll
+        for (int jm = 0; jm < NB - 1; jm++)
+#pragma unroll
+            for (int im = jm + 1; im < NB; im++) {
+                R0[im][jm] = dneg(R0[im][jm]); R1[im][jm] = dneg(R1[im][jm]); I0[im][jm] = dneg(I0[im][jm]); I1[im][jm] = dneg(I1[im][jm]);
+            }
+        BFrag bcol = to_bfrag(ABZ_B(1, 0), src0, src1, par);             // first fragment of column 0 (M_{jm+1,jm} = -L is final from the start)
+#pragma unroll
+        for (int jm = 0; jm < NB - 1; jm++) {
+            BFrag b = bcol;
+#pragma unroll
+            for (int t = jm + 1; t < NB; t++) {
+                tr += R0[jm][t] * b.r[0] - I0[jm][t] * b.i[0] + R1[jm][t] * b.r[1] - I1[jm][t] * b.i[1];
+                ti += R0[jm][t] * b.i[0] + I0[jm][t] * b.r[0] + R1[jm][t] * b.i[1] + I1[jm][t] * b.r[1];
+                BFrag bn;
+                if (t + 1 < NB) {
+                    bmm<false>(ABZ_B(t + 1, jm), ABZ_B(t + 1, t), b);    // -= L_{t+1,t} b (the array holds -L); M_{t+1,jm} is final after this term
+                    bn = to_bfrag(ABZ_B(t + 1, jm), src0, src1, par);
+                }
+                if (t == jm + 1 && jm + 2 < NB) bcol = to_bfrag(ABZ_B(jm + 2, jm + 1), src0, src1, par);   // next column's first fragment
+#pragma unroll
+                for (int im = t + 2; im < NB; im++) bmm<false>(ABZ_B(im, jm), ABZ_B(im, t), b);
+                if (t + 1 < NB) b = bn;
+            }
+        }
+#undef ABZ_B
+        return make_double2(warp_sum(tr), warp_sum(ti));
+    }
     if (VAR == 1) {
         // V = U~^-1, columns right to left (column jv only reads X blocks of columns t < jv, still untouched)
 #pragma unroll
@@ -913,6 +974,7 @@ inline cudaError_t mma_fused_launch(const double2* C1, const double2* ptab, cons
                 // (PF = 2) gives the gain back (907.1 k) - profiles/r02_k3fused_timing.log.  ABZ_MMA_PREFETCH = 0 / 2 select the others.
                 static const int pf = getenv("ABZ_MMA_PREFETCH") ? atoi(getenv("ABZ_MMA_PREFETCH")) : 1;
                 if (pf == 0) ABZ_FUSED_GO(4, 8, 1, true);
+                else if (pf == 3) resolvent_mma_fused_kernel<4, 8, 1, true, 3><<<(unsigned)ncta, 256, smem, stream>>>(C1, ptab, row_nodeptr, r0, r1, klist, N, M, wnode, n0, nk, n, nw, z, sigma, kper, outp, errflag);
                 else if (pf == 2) resolvent_mma_fused_kernel<4, 8, 1, true, 2><<<(unsigned)ncta, 256, smem, stream>>>(C1, ptab, row_nodeptr, r0, r1, klist, N, M, wnode, n0, nk, n, nw, z, sigma, kper, outp, errflag);
                 else resolvent_mma_fused_kernel<4, 8, 1, true, 1><<<(unsigned)ncta, 256, smem, stream>>>(C1, ptab, row_nodeptr, r0, r1, klist, N, M, wnode, n0, nk, n, nw, z, sigma, kper, outp, errflag);
             } else ABZ_FUSED_GO(4, 8, 1, false);
@@ -941,6 +1003,7 @@ inline cudaError_t mma_resolvent_opt_in() {
     ABZ_FUSED_OPT(1, 8, 0) ABZ_FUSED_OPT(2, 8, 0) ABZ_FUSED_OPT(3, 8, 0) ABZ_FUSED_OPT(4, 8, 1) ABZ_FUSED_OPT(4, 12, 1)
 #undef ABZ_FUSED_OPT
     { auto f = resolvent_mma_fused_kernel<4, 8, 1, true, 1>; set((const void*)f); auto t = resolvent_mma_fused_kernel<4, 8, 1, true, 2>; set((const void*)t); }
+    { auto f = resolvent_mma_fused_kernel<4, 8, 1, true, 3>; set((const void*)f); }
 #define ABZ_DIRECT_OPT(NBX, V, P) { auto f = resolvent_mma_fused_kernel<NBX, 8, V, false, 0, true>; set((const void*)f); auto t = resolvent_mma_fused_kernel<NBX, 8, V, true, P, true>; set((const void*)t); }
     ABZ_DIRECT_OPT(1, 0, 0) ABZ_DIRECT_OPT(2, 0, 0) ABZ_DIRECT_OPT(3, 0, 0) ABZ_DIRECT_OPT(4, 1, 1)
 #undef ABZ_DIRECT_OPT

@@ -61,7 +61,7 @@ typedef uint64_t abz_nest_t;    /* IAI arena: contracted series for nested panel
 #define ABZ_OPT_IAI_LEAF_SPILL 5   /* segments per device-side innermost integral beyond the 63 held in shared memory (default 1024);
                                     * an integral that outgrows them is redone with host-driven panels (single rank); a negative value -c
                                     * (1 <= c <= 63) limits the TOTAL capacity to c segments - a test hook for that fallback */
-#define ABZ_OPT_IAI_LANES 6        /* IAI rounds in flight in single-rank solves with norb <= 3 (default 4; 1 = one round at a time);
+#define ABZ_OPT_IAI_LANES 6        /* IAI rounds in flight in single-rank solves with norb <= 6 (default 4; 1 = one round at a time);
                                     * results and numevals do not depend on it */
 #define ABZ_OPT_EIG_ALGO 4         /* 0 (default): Householder tridiagonalisation (warp-per-matrix in registers for norb <= 32,
                                     * CTA-per-matrix in registers for 33..64) followed by the eigenvalues of the tridiagonal: implicit QL
@@ -198,7 +198,7 @@ int32_t abz_nest_eval_matrix(abz_ctx* ctx, abz_nest_t nest, int64_t npts, const 
  *   lkind 0: CubicLimits(la, lb);  1: TetrahedralLimits(la)  (load_bz(CubicSymIBZ), src/brillouin.jl:301-307)
  *   fkind = ABZ_F_*;  vkind 0: value = y;  1: -Im(y)/pi (aps_example.jl:30);  2: lin[0:2]*y + lin[2:4] (complex a, b)
  *   atol, rtol, maxevals apply to the outermost integral exactly as abstol/reltol/maxiters of the reference.
- *   flags: ABZ_IAI_DEVICE_LEAVES = run each innermost 1-D adaptive integral entirely on the device (norb <= 3)
+ *   flags: ABZ_IAI_DEVICE_LEAVES = run each innermost 1-D adaptive integral entirely on the device (norb <= 6)
  *   out = {Re I, Im I, E};  stats = Int64[4] {numevals (EvalCounter semantics), device rounds, kernel launches,
  *   exchanges} or NULL */
 #define ABZ_IAI_DEVICE_LEAVES 1
