@@ -83,7 +83,7 @@ class DeviceRule:
                 # with an allreduce at hand every rank computes the orbit weights of ITS k3 planes only and the ranks add up
                 # their node counts; without one (single rank, or a caller that shards by hand) the library counts all planes
                 local_only = nranks > 1 and allreduce is not None
-                self.dev = _lib.DeviceRule(ctx, ds, self.npt, syms=sy, k3_lo=rank, k3_stride=nranks, count_all=not local_only)
+                self.dev = _lib.DeviceRule(ctx, ds, self.npt, syms=sy, k3_lo=rank, k3_stride=(-nranks if nranks > 1 else 1), count_all=not local_only)
                 if local_only:
                     self.nnodes_total = int(round(float(np.asarray(allreduce(np.array([float(len(self.dev))]))).reshape(-1)[0])))
                 else:

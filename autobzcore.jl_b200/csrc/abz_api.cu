@@ -285,6 +285,14 @@ int finish_rule(abz_ctx* ctx, Rule* r) {
     return ABZ_OK;
 }
 
+// number of planes share_plane(p, k3_lo, k3_stride) < N (the sequence increases with p)
+static long share_nplanes(long N, int k3_lo, int k3_stride) {
+    long n = 0;
+    while (share_plane((int)n, k3_lo, k3_stride) < N) n++;
+    return n;
+}
+static bool share_valid(int k3_lo, int k3_stride) { return k3_lo >= 0 && (k3_stride >= 1 || (k3_stride < 0 && k3_lo < -k3_stride)); }
+
 // ---- chunk planning: consecutive planes while they fit; a plane larger than the cap is split by rows
 std::vector<Chunk> plan_chunks(const Rule* r, long node_cap, long row_cap, long plane_cap) {
     std::vector<Chunk> out;
@@ -865,7 +873,7 @@ int32_t abz_rule_create_sym(abz_ctx* ctx, abz_series_t sid, int32_t npt, const i
     if (!ctx) return ABZ_E_INVALID;
     Series* s = get_series(ctx, sid);
     if (!s) return fail(ctx, ABZ_E_INVALID, "unknown series handle");
-    if (!out || !wsym || npt < 1 || k3_lo < 0 || k3_stride < 1) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
+    if (!out || !wsym || npt < 1 || !share_valid(k3_lo, k3_stride)) return fail(ctx, ABZ_E_INVALID, "invalid arguments");
     cudaSetDevice(ctx->device);
     auto r = std::make_unique<Rule>();
     r->ctx = ctx;
@@ -873,7 +881,8 @@ int32_t abz_rule_create_sym(abz_ctx* ctx, abz_series_t sid, int32_t npt, const i
     const long N = npt;
     r->h_plane_rowptr.push_back(0);
     r->h_row_nodeptr.push_back(0);
-    for (long i3 = k3_lo; i3 < N; i3 += k3_stride) {
+    for (int psel = 0; share_plane(psel, k3_lo, k3_stride) < N; psel++) {
+        const long i3 = share_plane(psel, k3_lo, k3_stride);
         bool plane_open = false;
         for (long i2 = 0; i2 < N; i2++) {
             const int32_t* row = wsym + (i3 * N + i2) * N;
@@ -976,7 +985,7 @@ static bool syms_form_group(const int32_t* h_syms, int nsyms) {
     return true;
 }
 
-// Orbit weights of the planes i3 = k3_lo + p * k3_stride (p < nplanes) into the dense array d_w; other planes are not touched.
+// Orbit weights of the planes i3 = share_plane(p, k3_lo, k3_stride) (p < nplanes) into the dense array d_w; other planes are not touched.
 // Every point's test "am I the smallest index of my orbit" is independent of the others, so a rank needs only its own planes.
 static int launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms, const int* d_syms, int* d_w, int k3_lo = 0,
                          int k3_stride = 1, long nplanes = -1) {
@@ -1002,8 +1011,14 @@ static int launch_symptr(abz_ctx* ctx, int npt, int nsyms, const int32_t* h_syms
         unsigned* l2 = l1 + cap1;
         CU(ctx, cudaMemsetAsync(cnt, 0, 16 * sizeof(unsigned), ctx->stream));
         if (k3_stride == 1) CU(ctx, cudaMemsetAsync(d_w + (size_t)k3_lo * plane, 0, sel * sizeof(int), ctx->stream));
-        else CU(ctx, cudaMemset2DAsync(d_w + (size_t)k3_lo * plane, (size_t)k3_stride * plane * sizeof(int), 0, plane * sizeof(int),
-                                        (size_t)nplanes, ctx->stream));
+        else if (k3_stride > 0) CU(ctx, cudaMemset2DAsync(d_w + (size_t)k3_lo * plane, (size_t)k3_stride * plane * sizeof(int), 0, plane * sizeof(int),
+                                                         (size_t)nplanes, ctx->stream));
+        else {      // serpentine share: the even and the odd planes of the sequence are two strided sets
+            const size_t pitch = (size_t)(-2 * k3_stride) * plane * sizeof(int);
+            CU(ctx, cudaMemset2DAsync(d_w + (size_t)share_plane(0, k3_lo, k3_stride) * plane, pitch, 0, plane * sizeof(int), (size_t)((nplanes + 1) / 2), ctx->stream));
+            if (nplanes > 1)
+                CU(ctx, cudaMemset2DAsync(d_w + (size_t)share_plane(1, k3_lo, k3_stride) * plane, pitch, 0, plane * sizeof(int), (size_t)(nplanes / 2), ctx->stream));
+        }
         dim3 g1((unsigned)((plane + 255) / 256), (unsigned)nplanes);
         symptr_filter_kernel<true, false><<<g1, 256, smem, ctx->stream>>>(npt, nsyms, 0, 8, d_syms, nullptr, nullptr, l1, cnt, cap1,
                                                                          reinterpret_cast<int*>(cnt + 2), d_w, k3_lo, k3_stride);
@@ -1051,7 +1066,7 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
     if (!ctx) return ABZ_E_INVALID;
     Series* s = get_series(ctx, sid);
     if (!s) return fail(ctx, ABZ_E_INVALID, "unknown series handle");
-    if (!out || npt < 1 || nsyms < 1 || nsyms > 1024 || !syms || k3_lo < 0 || k3_stride < 1)
+    if (!out || npt < 1 || nsyms < 1 || nsyms > 1024 || !syms || !share_valid(k3_lo, k3_stride))
         return fail(ctx, ABZ_E_INVALID, "invalid arguments");
     for (int t = 0; t < 9 * nsyms; t++)
         if ((long)std::abs((long)syms[t]) * 3 * npt >= ((long)1 << 31)) return fail(ctx, ABZ_E_INVALID, "symmetry matrix entries too large");
@@ -1068,7 +1083,7 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
     // planes are not even computed: the caller sums the local node counts over the ranks)
     const bool want_total = (nirr_total != nullptr) && !(k3_lo == 0 && k3_stride == 1);
     std::vector<int> cnt_all;
-    const long nplanes_sel = (k3_lo < N) ? (N - k3_lo + k3_stride - 1) / k3_stride : 0;
+    const long nplanes_sel = share_nplanes(N, k3_lo, k3_stride);
     {
         int rcs = want_total ? launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), wbuf.as<int>())
                              : launch_symptr(ctx, npt, nsyms, syms, ctx->tmp_b.as<int>(), wbuf.as<int>(), k3_lo, k3_stride, nplanes_sel);
@@ -1084,7 +1099,7 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
         CU(ctx, cudaMemcpyAsync(cnt_all.data(), cntbuf.p, (size_t)N * N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         for (long p = 0; p < nplanes_sel; p++)
-            memcpy(cnt.data() + p * N, cnt_all.data() + (k3_lo + p * k3_stride) * N, (size_t)N * sizeof(int));
+            memcpy(cnt.data() + p * N, cnt_all.data() + (long)share_plane((int)p, k3_lo, k3_stride) * N, (size_t)N * sizeof(int));
     } else if (rows_sel > 0) {
         sym_row_count_kernel<<<(unsigned)((rows_sel * 32 + 255) / 256), 256, 0, ctx->stream>>>(wbuf.as<int>(), npt, k3_lo, k3_stride,
                                                                                              rows_sel, cntbuf.as<int>());
@@ -1113,11 +1128,11 @@ int32_t abz_rule_create_symptr(abz_ctx* ctx, abz_series_t sid, int32_t npt, int3
             open = true;
             nnz += c;
             r->h_row_k2.push_back((int)i2);
-            row_k3.push_back((int)(k3_lo + p * k3_stride));
+            row_k3.push_back(share_plane((int)p, k3_lo, k3_stride));
             r->h_row_nodeptr.push_back(nnz);
         }
         if (open) {
-            r->h_plane_k3.push_back((int)(k3_lo + p * k3_stride));
+            r->h_plane_k3.push_back(share_plane((int)p, k3_lo, k3_stride));
             r->h_plane_rowptr.push_back((long)r->h_row_k2.size());
         }
     }

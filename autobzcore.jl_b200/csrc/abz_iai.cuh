@@ -573,7 +573,7 @@ symptr_rule_kernel(int N, int nsyms, const int* __restrict__ syms, int* __restri
     const long lidx = (long)blockIdx.x * 256 + threadIdx.x;
     if (lidx >= NN * nplanes) return;
     const long rr = lidx % NN;
-    const int i1 = (int)(rr % N), i2 = (int)(rr / N), i3 = k3_lo + (int)(lidx / NN) * k3_stride;
+    const int i1 = (int)(rr % N), i2 = (int)(rr / N), i3 = share_plane((int)(lidx / NN), k3_lo, k3_stride);
     const long idx = (long)i3 * NN + rr;
     const float invN = 1.0f / (float)N;
     // pass 1: is this node the smallest linear index of its orbit?  (most nodes leave after a few symmetries)
@@ -639,7 +639,7 @@ symptr_filter_kernel(int N, int nsyms, int s0, int s1, const int* __restrict__ s
     } else {
         const unsigned r = blockIdx.x * 256u + threadIdx.x;
         if (r < (unsigned)N * (unsigned)N) {
-            i3 = k3_lo + (int)blockIdx.y * k3_stride;
+            i3 = share_plane((int)blockIdx.y, k3_lo, k3_stride);
             i2 = (int)(r / (unsigned)N); i1 = (int)(r - (unsigned)i2 * (unsigned)N);
             idx = (unsigned)i3 * (unsigned)N * (unsigned)N + r;
             keep = true;
@@ -686,7 +686,7 @@ sym_row_count_kernel(const int* __restrict__ wsym, int N, int k3_lo, int k3_stri
     const int lane = threadIdx.x & 31;
     if (row >= nrows_all) return;
     const long p = row / N, i2 = row % N;
-    const int* w = wsym + (((long)k3_lo + p * k3_stride) * N + i2) * N;
+    const int* w = wsym + ((long)share_plane((int)p, k3_lo, k3_stride) * N + i2) * N;
     int c = 0;
     for (int i1 = lane; i1 < N; i1 += 32) c += (w[i1] != 0);
 #pragma unroll

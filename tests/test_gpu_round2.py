@@ -302,3 +302,37 @@ def test_bisection_handles_decoupled_and_scaled_matrices(ctx):
             R.close(); S.close()
     finally:
         ctx.set_option(L.OPT_EIG_ALGO, 0)
+
+
+@pytest.mark.parametrize("W", [2, 3, 8])
+def test_serpentine_plane_shares_partition_the_rule(ctx, orc, W):
+    """k3_stride = -W deals the k3 planes of a symmetry-reduced rule in serpentine order (rank r: r, 2W-1-r, 2W+r, 4W-1-r, ...):
+    the shares are disjoint, cover every plane, follow that sequence, give the same rules through both construction paths
+    (device symptr / host wsym array), add up to the whole rule's sums - and balance the node counts of the cubic wedge better than
+    the round-robin dealing (src/fourier.jl:246-255 deals its thread chunks round-robin; the node set and the sums are the same)."""
+    n, N = 3, 21
+    H, lo = ab.synthetic.wannier_hamiltonian(n, 2, cubic=True)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    syms = np.array(ab.cube_automorphisms(3), dtype=np.int32)
+    w_host, nirr = ctx.symptr_rule(N, syms)
+    whole = L.DeviceRule(ctx, S, N, syms=syms)
+    z = np.array([0.3 + 0.05j, -0.7 + 0.2j])
+    ref = orc.symptr_sum(orc.Series(H, lo), N, w_host, z, scale=1.0)[0]
+    shares = [L.DeviceRule(ctx, S, N, syms=syms, k3_lo=r, k3_stride=-W, count_all=False) for r in range(W)]
+    assert sum(len(s) for s in shares) == nirr == len(whole)
+    seen = set()
+    for r, sh in enumerate(shares):
+        Hk, k, w = sh.copy_out()
+        planes = sorted(set(np.rint(k[:, 2] * N).astype(int).tolist()))
+        expect = [p for p in range(N) if (p % (2 * W)) in (r, 2 * W - 1 - r)]
+        assert set(planes) <= set(expect) and not (seen & set(planes))
+        seen |= set(planes)
+        via_host = L.DeviceRule(ctx, S, N, wsym=w_host, k3_lo=r, k3_stride=-W)
+        Hh, kh, wh = via_host.copy_out()
+        assert np.array_equal(k, kh) and np.array_equal(w, wh) and np.array_equal(Hk, Hh)
+    tot = sum(s.resolvent_sum(z) for s in shares)
+    assert np.max(np.abs(tot - ref) / np.abs(ref)) < 1e-11
+    rr = [len(L.DeviceRule(ctx, S, N, syms=syms, k3_lo=r, k3_stride=W, count_all=False)) for r in range(W)]
+    assert max(len(s) for s in shares) <= max(rr)
+    with pytest.raises(Exception):
+        L.DeviceRule(ctx, S, N, syms=syms, k3_lo=W, k3_stride=-W)
