@@ -2014,7 +2014,13 @@ struct IaiDeviceBackend {
     //      shares the context's work buffers and runs one round at a time
     int nlanes = 1;
     int lanes() const { return nlanes; }
-    int submit(int g, abz_iai::Round& R) { return nlanes == 1 ? ABZ_OK : enqueue(*ctx->iai_lanes[g], R); }
+    int submit(int g, abz_iai::Round& R) {
+        if (nlanes == 1) return ABZ_OK;
+        IaiLane& ln = *ctx->iai_lanes[g];
+        const int rc = enqueue(ln, R);
+        if (rc) cudaStreamSynchronize(ln.stream);      // a failed submit is not in the engine's fifo: what it queued must finish before the caller unwinds
+        return rc;
+    }
     int wait(int g, abz_iai::Round& R) { return nlanes == 1 ? run_round(R) : collect(*ctx->iai_lanes[g], R); }
 
     int init_lanes(int want) {

@@ -44,9 +44,10 @@ class FourierSeries:
     def device(self, ctx):
         """The series uploaded to `ctx` (cached)."""
         key = id(ctx)
-        if key not in self._dev or self._dev[key].h is None:
-            self._dev[key] = _lib.DeviceSeries(ctx, self.c, self.lo, self.period)
-        return self._dev[key]
+        d = self._dev.get(key)
+        if d is None or d.h is None or d.ctx is not ctx:        # (the cached handle keeps its context alive, so an id is not reused under it)
+            d = self._dev[key] = _lib.DeviceSeries(ctx, self.c, self.lo, self.period)
+        return d
 
     def drop_device(self):
         for d in self._dev.values():

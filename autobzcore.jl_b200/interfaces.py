@@ -619,7 +619,7 @@ def _autosymptr(cache, bf, salg, atol, reltol, maxevals, ndim):
     # keep the `keepmost` most refined rules for the next parameter (src/algorithms.jl:429 keepmost)
     keep = max(1, salg.keepmost)
     used = rules[: i + 1]
-    drop = used[:-keep] if len(used) > keep else []
+    drop = (used[:-keep] if len(used) > keep else []) + rules[i + 1:]      # also rules an earlier parameter refined beyond this one's last grid
     for r in drop:
         r.close()
     cache.cacheval["rules"] = used[-keep:] if len(used) > keep else used
