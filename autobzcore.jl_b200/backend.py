@@ -132,6 +132,16 @@ class DeviceRule:
         self.dev.close()
 
 
+def share_planes(npt, rank, k3_stride):
+    """The k3 planes `abz_rule_create_sym / _symptr(..., k3_lo=rank, k3_stride)` select (`share_plane`, csrc/abz_common.cuh):
+    k3_stride > 0: rank, rank + k3_stride, ... (the reference's round-robin dealing, src/fourier.jl:246-255);
+    k3_stride < 0: serpentine dealing among W = -k3_stride ranks: rank, 2W-1-rank, 2W+rank, 4W-1-rank, ..."""
+    if k3_stride > 0:
+        return list(range(rank, npt, k3_stride))
+    w2 = -2 * k3_stride
+    return [p for p in range(npt) if p % w2 in (rank, w2 - 1 - rank)]
+
+
 class DeviceBackend:
     """iai_engine: "native" (default) runs IAI's adaptive control flow in the library's C++ host engine
     (abz_iai_solve, one call per solve); "python" drives abz_nest_* round by round from iai.NestedGK.

@@ -75,7 +75,7 @@ __device__ __forceinline__ double2 cdiv_fast(double2 a, double2 b) { return cmul
 // Plane p of one rank's share of the k3 planes.  k3_stride > 0: k3_lo + p * k3_stride (round-robin among k3_stride ranks).
 // k3_stride < 0: "serpentine" dealing among W = -k3_stride ranks, rank k3_lo < W taking planes r, 2W-1-r, 2W+r, 4W-1-r, ...:
 // the planes of a symmetry-reduced grid shrink monotonically with k3 (the irreducible wedge), so round-robin hands rank 0 up to
-// ~18 % more nodes than the average at W = 8, the serpentine ~1 %.
+// ~22 % more nodes than the average at W = 8 (cubic group, npt = 96), the serpentine ~4 %.
 __host__ __device__ __forceinline__ int share_plane(int p, int k3_lo, int k3_stride) {
     if (k3_stride > 0) return k3_lo + p * k3_stride;
     const int w2 = -2 * k3_stride;
