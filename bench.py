@@ -451,7 +451,9 @@ def main():
                                        f"step = ONE k3 slab of {planes} planes per rank = {planes}/{NPT} of the grid per GPU per step (x{world} ranks; 8 ranks = the whole "
                                        f"grid per step; the N=1 line is a 1/8-slab rate, equal to the full-grid rate by linearity of the k-sum)",
                            "kpoints_per_step": nodes_rank * world, "k_omega_evals_per_sec": value * NW,
-                           "l2": "inputs larger than L2 (H(k) chunk 1-4 GB per pass)", "parallelism": f"k3-slab x{world}", "exchange": "one allreduce of 128 complex partial sums per step inside the timed loop" if world > 1 else "none (1 rank)",
+                           "l2": ("inputs larger than L2 (per step the stage-2 output C1, 2.3 GB for 32 planes, is written and streamed once by the fused kernel; "
+                                  "H(k) itself is never in HBM)") if os.environ.get("ABZ_FUSED_MMA", "1") != "0" and args.algo in (0, 2)
+                           else "inputs larger than L2 (H(k) chunk 1-4 GB per pass)", "parallelism": f"k3-slab x{world}", "exchange": "one allreduce of 128 complex partial sums per step inside the timed loop" if world > 1 else "none (1 rank)",
                            "resolvent_algo": args.algo, "device_event_ms_per_step": 1e3 * t_events_max / args.steps},
                 "roofline": roof, "cpu_baseline": cb,
                 "e2e": {"value": e2e_val, "unit": "k-points/s", "h2d_bytes_per_step": int(H.nbytes + z.nbytes), "d2h_bytes_per_step": int(NW * 16),

@@ -107,3 +107,19 @@ def test_fused_path_keeps_the_pivot_monitor(ctx, orc):
     ref = orc.ptr_sum(orc.Series(H, lo), N, z)
     assert rel(got, ref) < 1e-10
     S.close()
+
+
+def test_fused_many_frequencies_streamed_and_materialised(ctx, orc):
+    """128 frequencies (the bench's count): the kernel's dynamic shared memory (8 x nw accumulators + two H(k) buffers = 50 KB) is above
+    the 48 KB that need the per-device opt-in, in the streamed and in the direct (materialised) instantiation."""
+    n, rmax, N, nw = 32, 1, 5, 128
+    H, lo = ab.synthetic.wannier_hamiltonian(n, rmax)
+    S = L.DeviceSeries(ctx, H, lo, (1.0,) * 3)
+    z = freqs(H, nw)
+    ref = orc.ptr_sum(orc.Series(H, lo), N, z)
+    R = L.DeviceRule(ctx, S, N)
+    got = R.resolvent_sum(z, scale=1.0 / N ** 3)
+    assert rel(got, ref) < 1e-11
+    R.materialize()
+    assert rel(R.resolvent_sum(z, scale=1.0 / N ** 3), ref) < 1e-11
+    R.close(); S.close()
