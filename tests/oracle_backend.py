@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 
 import orc
-from autobz_b200.backend import symptr_nodes_lowdim
+from autobz_b200.backend import share_planes, symptr_nodes_lowdim
 
 
 def _oseries(fs):
@@ -38,7 +38,8 @@ class OracleRule:
                 order = np.lexsort((i1, i2, i3))
                 idx = np.stack([i1[order], i2[order], i3[order]], axis=1)
                 w = ws[i1[order], i2[order], i3[order]].astype(float)
-                sel = (idx[:, 2] % nranks) == rank
+                # the product's dealing of the k3 planes of a symmetric rule (backend.make_rule: serpentine for nranks > 1)
+                sel = np.isin(idx[:, 2], share_planes(npt, rank, -nranks if nranks > 1 else 1))
             self.nnodes_total = idx.shape[0]
             self.idx, self.w = idx[sel], w[sel]
             self._sel = sel
